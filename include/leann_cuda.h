@@ -1,0 +1,208 @@
+/*
+ * leann_cuda.h — C ABI of the B200-native (sm_100a) search path for decisiongraph/leann-rs.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the leann-rs
+ * repository). Plain pointers and sizes only; no C++/torch types cross this boundary. All functions
+ * return LEANN_OK (0) or a negative error class and copy a message into `err` (nullable).
+ * Nothing here aborts or throws across the ABI. There is NO CPU fallback: every search entry point
+ * returns LEANN_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Threading: `*_search*` calls are re-entrant on one handle (src/cli/serve.rs:84,289 shares one
+ * searcher behind read locks); open/build/close must not race with searches on the same handle.
+ */
+#ifndef LEANN_CUDA_H
+#define LEANN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEANN_OK 0
+#define LEANN_ERR_NOT_FOUND (-1)    /* hnsw.rs:34-40, diskann.rs:26-32 "index not found" */
+#define LEANN_ERR_BAD_FORMAT (-2)   /* hnsw.rs:55-70 "incompatible format" */
+#define LEANN_ERR_DIM_MISMATCH (-3) /* usearch load / diskann assert on dimension */
+#define LEANN_ERR_CUDA (-4)
+#define LEANN_ERR_NCCL (-5)
+#define LEANN_ERR_INVALID_ARG (-6)
+#define LEANN_ERR_FAISS_FORMAT (-7) /* backend/compat.rs:15-38 + hnsw.rs:24-32 */
+#define LEANN_ERR_PARSE (-8)        /* MetadataFilter::parse returned None (filter.rs:52) */
+
+/* backend/mod.rs:16-19 `enum BackendType { Hnsw, DiskAnn }` + the exact scan of index/recompute.rs */
+#define LEANN_BACKEND_HNSW 0
+#define LEANN_BACKEND_VAMANA 1
+#define LEANN_BACKEND_FLAT 2
+
+/* Distance / score conventions.
+ *  IP        1 - <q,x>, ascending     usearch MetricKind::IP            (hnsw.rs:45)
+ *  L2SQ      |q-x|^2,   ascending     BASELINE config C4
+ *  IP_CLAMP  max(0, 1 - <q,x>)        anndists DistDot                  (diskann.rs:16,36)
+ *  DOT_DESC  <q,x>,     descending    RecomputeSearcher score           (recompute.rs:96-106)
+ * LEANN_METRIC_DEFAULT takes the metric recorded in the file / the reference default of the backend. */
+#define LEANN_METRIC_DEFAULT (-1)
+#define LEANN_METRIC_IP 0
+#define LEANN_METRIC_L2SQ 1
+#define LEANN_METRIC_IP_CLAMP 2
+#define LEANN_METRIC_DOT_DESC 3
+
+#define LEANN_MASK_NONE 0
+#define LEANN_MASK_INLINE 1 /* bit i set = passage i may be returned; tested inside the traversal */
+
+typedef struct leann_cuda_index leann_cuda_index;
+typedef struct leann_cuda_bm25 leann_cuda_bm25;
+typedef struct leann_cuda_filter leann_cuda_filter;
+typedef struct leann_cuda_searcher leann_cuda_searcher;
+
+/* ---------------------------------------------------------------------------------------------
+ * Backend: replaces BackendType::load_searcher (backend/mod.rs:23-45), HnswSearcher::load
+ * (backend/hnsw.rs:18-75), DiskAnnSearcher::load (backend/diskann.rs:21-43).
+ * `base_path` is the extension-less base (".../documents.leann"); ".index" / ".diskann" /
+ * ".embeddings" is appended exactly as `with_extension` does in the reference.
+ * ------------------------------------------------------------------------------------------- */
+int leann_cuda_open(const char* base_path, int backend, size_t dims, int metric, int device,
+                    leann_cuda_index** out, char* err, size_t errlen);
+
+/* In-memory constructors (same device layout as open): host row-major f32 vectors. */
+int leann_cuda_flat_from_host(const float* vectors, size_t n, size_t dims, int metric, int device,
+                              leann_cuda_index** out, char* err, size_t errlen);
+int leann_cuda_flat_from_device(const float* d_vectors, size_t n, size_t dims, int metric, int device,
+                                leann_cuda_index** out, char* err, size_t errlen);
+
+/* hnsw::build_index (backend/hnsw.rs:96-139): builds on the GPU; keys are ordinals 0..n-1.
+ * `vectors_on_device` != 0: `vectors` is a device pointer on `device`. */
+int leann_cuda_hnsw_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
+                          size_t graph_degree, size_t complexity, int metric, uint64_t seed, int device,
+                          leann_cuda_index** out, char* err, size_t errlen);
+/* diskann::build_index (backend/diskann.rs:70-105), alpha as DiskAnnParams.alpha (:91). */
+int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
+                            size_t graph_degree, size_t complexity, float alpha, int metric,
+                            uint64_t seed, int device, leann_cuda_index** out, char* err, size_t errlen);
+/* index.save(<base>.index) (hnsw.rs:134) / build_index_with_params file output (diskann.rs:94-99) /
+ * EmbeddingsWriter (index/embeddings.rs:126-147). Writes the reference's on-disk formats. */
+int leann_cuda_save(const leann_cuda_index* index, const char* base_path, char* err, size_t errlen);
+
+/* BackendSearcher::len (backend/traits.rs:24). */
+size_t leann_cuda_len(const leann_cuda_index* index);
+size_t leann_cuda_dims(const leann_cuda_index* index);
+/* info[0..7] = n, dims, backend, metric, M (or R), M0, max_level, entry (or medoid). */
+int leann_cuda_info(const leann_cuda_index* index, uint64_t* info8);
+/* Number of lanes that cooperate on one distance for dimension `dims` (the oracle mirrors this
+ * reduction order bit for bit in tests). */
+int leann_cuda_reduction_lanes(size_t dims);
+/* Capacity of the bounded candidate queue the traversal uses for expansion `ef`
+ * (ef without a mask; min(4*ef, 2048) with an inline mask). Exposed so tests can drive the oracle's
+ * bounded-queue mode with the same number. */
+size_t leann_cuda_queue_capacity(size_t ef, int masked);
+
+/* BackendSearcher::search (backend/traits.rs:16-21; hnsw.rs:79-88; diskann.rs:47-62), batched.
+ * queries: nq x dims row-major f32 (host). keys/dists: nq x k, ascending distance (descending score
+ * for DOT_DESC); unused tail = UINT64_MAX / +inf (-inf for DOT_DESC); counts[i] = valid entries.
+ * ef: HNSW expansion_search / Vamana beam; effective value is max(ef, k) as in both reference
+ * engines. (HnswSearcher ignores `complexity` and always runs ef = 64, hnsw.rs:49,83 — callers that
+ * want that behaviour pass ef = 64.)
+ * mask_bits: nullable, ceil(n/64) words, bit s%64 of word s/64 belongs to slot s. */
+int leann_cuda_search(const leann_cuda_index* index, const float* queries, size_t nq, size_t k,
+                      size_t ef, const uint64_t* mask_bits, int mask_mode, uint64_t* keys,
+                      float* dists, uint32_t* counts, char* err, size_t errlen);
+
+/* Same, all pointers in device memory of the index's device, enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = default stream) without host synchronisation.
+ * d_stats: nullable, nq x 4 u64 = (distance evaluations, level-0 hops, upper-level hops, queue drops). */
+int leann_cuda_search_device(const leann_cuda_index* index, const float* d_queries, size_t nq,
+                             size_t k, size_t ef, const uint64_t* d_mask_bits, int mask_mode,
+                             uint64_t* d_keys, float* d_dists, uint32_t* d_counts, uint64_t* d_stats,
+                             void* cuda_stream, char* err, size_t errlen);
+
+/* Per-query top-k merge of `n_shards` result sets laid out [shard][nq][k] (the buffer an
+ * ncclAllGather of each shard's keys/dists produces). descending != 0 for DOT_DESC. Device pointers. */
+int leann_cuda_topk_merge_device(const uint64_t* d_keys_in, const float* d_dists_in, size_t n_shards,
+                                 size_t nq, size_t k, int descending, uint64_t* d_keys_out,
+                                 float* d_dists_out, uint32_t* d_counts_out, void* cuda_stream,
+                                 char* err, size_t errlen);
+
+void leann_cuda_close(leann_cuda_index* index);
+
+/* ---------------------------------------------------------------------------------------------
+ * BM25: replaces Bm25Scorer::{build,score_query,search} (index/bm25.rs:33-122), tokenize (:127-132)
+ * and hybrid_rerank (:135-170). The inverted index is built once and kept in HBM.
+ * ------------------------------------------------------------------------------------------- */
+int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size_t n_docs, int device,
+                          leann_cuda_bm25** out, char* err, size_t errlen);
+size_t leann_cuda_bm25_len(const leann_cuda_bm25* bm25);
+/* stats[0..3] = n_docs, n_terms, n_postings, total_tokens; avg_doc_len out (bm25.rs:61-65). */
+int leann_cuda_bm25_stats(const leann_cuda_bm25* bm25, uint64_t* stats4, float* avg_doc_len);
+/* tokenize (bm25.rs:127-132): writes tokens separated by '\n' into out (truncated to cap),
+ * returns the number of tokens. */
+size_t leann_cuda_tokenize(const char* text, size_t text_bytes, char* out, size_t cap);
+/* Bm25Scorer::score_query (bm25.rs:77-106): dense scores[n_docs] (host). */
+int leann_cuda_bm25_score(const leann_cuda_bm25* bm25, const char* query, size_t query_bytes,
+                          float* scores, char* err, size_t errlen);
+/* Bm25Scorer::search (bm25.rs:109-122), batched: idx/scores nq x top_k (host), score > 0 only,
+ * stable descending (ties by ascending document index). */
+int leann_cuda_bm25_search(const leann_cuda_bm25* bm25, const char* const* queries,
+                           const size_t* query_bytes, size_t nq, size_t top_k, uint64_t* idx,
+                           float* scores, uint32_t* counts, char* err, size_t errlen);
+/* hybrid_rerank (bm25.rs:135-170) for one candidate list, evaluated on the device. bm25_scores is
+ * the dense host vector of n_docs scores. Output has n entries, stable descending. */
+int leann_cuda_hybrid_rerank(const uint64_t* idx, const float* vec_scores, size_t n,
+                             const float* bm25_scores, size_t n_docs, float alpha, int device,
+                             uint64_t* out_idx, float* out_scores, char* err, size_t errlen);
+void leann_cuda_bm25_free(leann_cuda_bm25* bm25);
+
+/* IndexSearcher::search_with_options (index/searcher.rs:123-210) without the passage fetch:
+ * fetch_k = 5k when a filter or hybrid is present (:129-133); backend search (:136); BM25 union with
+ * vector score 0.0 (:156-165); hybrid_rerank (:167); post-filter walk until k results (:174-207).
+ * query_texts nullable (no hybrid). filter_mask nullable: bit i = passage i passes
+ * MetadataFilter::matches (post-filter, reference semantics; may return < k).
+ * ef: the backend `complexity` (pass 64 for HNSW to reproduce hnsw.rs:49,83).
+ * Outputs nq x top_k (host): passage ordinals and the score searcher.rs returns (distance, or fused
+ * score when hybrid). */
+int leann_cuda_hybrid_search(const leann_cuda_index* index, const leann_cuda_bm25* bm25,
+                             const float* queries, const char* const* query_texts,
+                             const size_t* query_text_bytes, size_t nq, size_t top_k, size_t ef,
+                             int hybrid, float alpha, const uint64_t* filter_mask, uint64_t* idx,
+                             float* scores, uint32_t* counts, char* err, size_t errlen);
+
+/* ---------------------------------------------------------------------------------------------
+ * Metadata filter: replaces MetadataFilter::parse / matches (index/filter.rs:52-134,137-316,319-439).
+ * Evaluated once on the host into a bitmask; kernels test bits.
+ * ------------------------------------------------------------------------------------------- */
+int leann_cuda_filter_parse(const char* expr, leann_cuda_filter** out, char* err, size_t errlen);
+/* JSON rendering of the parsed tree in serde's shape ({"field","op","value"} / {"and":[..]} / {"or":[..]}). */
+size_t leann_cuda_filter_describe(const leann_cuda_filter* f, char* out, size_t cap);
+/* matches(&serde_json::Value): metadata given as JSON text. *result = 0/1. */
+int leann_cuda_filter_matches(const leann_cuda_filter* f, const char* metadata_json, size_t bytes,
+                              int* result, char* err, size_t errlen);
+/* Bulk: one JSON document per passage -> bitmask words (ceil(n/64)). */
+int leann_cuda_filter_mask(const leann_cuda_filter* f, const char* const* metadata_json,
+                           const size_t* bytes, size_t n, uint64_t* mask_bits, char* err, size_t errlen);
+void leann_cuda_filter_free(leann_cuda_filter* f);
+
+/* ---------------------------------------------------------------------------------------------
+ * IndexSearcher (index/searcher.rs:76-109 load; :123-210 search; :228-246 bm25_search):
+ * opens <base>.passages.jsonl / .passages.idx.json / .ids.txt + the backend; BM25 is built once
+ * on first hybrid use (the reference rebuilds it per query, searcher.rs:149-150).
+ * backend_name: "hnsw" | "diskann" (index/meta.rs backend_name) | "flat" (pruned index, recompute.rs).
+ * ------------------------------------------------------------------------------------------- */
+int leann_cuda_searcher_load(const char* base_path, const char* backend_name, size_t dims, int device,
+                             leann_cuda_searcher** out, char* err, size_t errlen);
+size_t leann_cuda_searcher_len(const leann_cuda_searcher* s);
+/* id_map[idx] or idx.to_string() when out of range (searcher.rs:180-184). Returns bytes written. */
+size_t leann_cuda_searcher_id(const leann_cuda_searcher* s, uint64_t idx, char* out, size_t cap);
+int leann_cuda_searcher_search(const leann_cuda_searcher* s, const float* queries,
+                               const char* const* query_texts, const size_t* query_text_bytes,
+                               size_t nq, size_t top_k, size_t complexity, const char* filter_expr,
+                               int hybrid, float alpha, uint64_t* idx, float* scores,
+                               uint32_t* counts, char* err, size_t errlen);
+void leann_cuda_searcher_close(leann_cuda_searcher* s);
+
+/* Library / device probe: returns the CUDA device count usable by the library (0 = none). */
+int leann_cuda_device_count(void);
+const char* leann_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEANN_CUDA_H */

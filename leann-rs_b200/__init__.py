@@ -1,0 +1,361 @@
+"""leann_rs_b200 — host-side mirror of leann-rs's search interfaces over ``libleann_cuda.so``.
+
+The product is the C-ABI library (``include/leann_cuda.h``, sources in ``csrc/``). This module is
+the thin host layer the tests and ``bench.py`` drive it through; class and method names follow the
+reference (``src/backend/traits.rs``, ``src/backend/{hnsw,diskann}.rs``, ``src/index/{searcher,
+bm25,filter,recompute}.rs``). PyTorch appears only as the owner of device buffers and streams.
+
+There is no CPU fallback: importing works anywhere, but every compute call raises ``LeannCudaError``
+when the CUDA library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libleann_cuda.so")
+
+OK = 0
+BACKEND_HNSW, BACKEND_VAMANA, BACKEND_FLAT = 0, 1, 2
+METRIC_DEFAULT, METRIC_IP, METRIC_L2SQ, METRIC_IP_CLAMP, METRIC_DOT_DESC = -1, 0, 1, 2, 3
+MASK_NONE, MASK_INLINE = 0, 1
+ERR_NOT_FOUND, ERR_BAD_FORMAT, ERR_DIM_MISMATCH, ERR_CUDA, ERR_NCCL, ERR_INVALID_ARG, ERR_FAISS_FORMAT, ERR_PARSE = (
+    -1, -2, -3, -4, -5, -6, -7, -8)
+
+
+class LeannCudaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[leann_cuda {code}] {msg}")
+        self.code = code
+        self.message = msg
+
+
+_lib = None
+
+
+def lib():
+    """Loads libleann_cuda.so; fails loudly when it has not been built (no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LeannCudaError(ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, cp = C.c_void_p, C.c_size_t, C.c_char_p
+    u64p, f32p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    pp = C.POINTER(C.c_void_p)
+    szp = C.POINTER(C.c_size_t)
+    cpp = C.POINTER(C.c_char_p)
+    sig = {
+        "leann_cuda_open": (C.c_int, [cp, C.c_int, sz, C.c_int, C.c_int, pp, cp, sz]),
+        "leann_cuda_flat_from_host": (C.c_int, [vp, sz, sz, C.c_int, C.c_int, pp, cp, sz]),
+        "leann_cuda_flat_from_device": (C.c_int, [vp, sz, sz, C.c_int, C.c_int, pp, cp, sz]),
+        "leann_cuda_hnsw_build": (C.c_int, [vp, C.c_int, sz, sz, sz, sz, C.c_int, C.c_uint64, C.c_int, pp, cp, sz]),
+        "leann_cuda_vamana_build": (C.c_int, [vp, C.c_int, sz, sz, sz, sz, C.c_float, C.c_int, C.c_uint64, C.c_int, pp, cp, sz]),
+        "leann_cuda_save": (C.c_int, [vp, cp, cp, sz]),
+        "leann_cuda_len": (sz, [vp]),
+        "leann_cuda_dims": (sz, [vp]),
+        "leann_cuda_info": (C.c_int, [vp, u64p]),
+        "leann_cuda_reduction_lanes": (C.c_int, [sz]),
+        "leann_cuda_queue_capacity": (sz, [sz, C.c_int]),
+        "leann_cuda_search": (C.c_int, [vp, vp, sz, sz, sz, vp, C.c_int, vp, vp, vp, cp, sz]),
+        "leann_cuda_search_device": (C.c_int, [vp, vp, sz, sz, sz, vp, C.c_int, vp, vp, vp, vp, vp, cp, sz]),
+        "leann_cuda_topk_merge_device": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, vp, vp, vp, vp, cp, sz]),
+        "leann_cuda_close": (None, [vp]),
+        "leann_cuda_device_count": (C.c_int, []),
+        "leann_cuda_version": (cp, []),
+        "leann_cuda_bm25_build": (C.c_int, [cpp, szp, sz, C.c_int, pp, cp, sz]),
+        "leann_cuda_bm25_len": (sz, [vp]),
+        "leann_cuda_bm25_stats": (C.c_int, [vp, u64p, f32p]),
+        "leann_cuda_tokenize": (sz, [cp, sz, cp, sz]),
+        "leann_cuda_bm25_score": (C.c_int, [vp, cp, sz, vp, cp, sz]),
+        "leann_cuda_bm25_search": (C.c_int, [vp, cpp, szp, sz, sz, vp, vp, vp, cp, sz]),
+        "leann_cuda_hybrid_rerank": (C.c_int, [vp, vp, sz, vp, sz, C.c_float, C.c_int, vp, vp, cp, sz]),
+        "leann_cuda_bm25_free": (None, [vp]),
+        "leann_cuda_hybrid_search": (C.c_int, [vp, vp, vp, cpp, szp, sz, sz, sz, C.c_int, C.c_float, vp, vp, vp, vp, cp, sz]),
+        "leann_cuda_filter_parse": (C.c_int, [cp, pp, cp, sz]),
+        "leann_cuda_filter_describe": (sz, [vp, cp, sz]),
+        "leann_cuda_filter_matches": (C.c_int, [vp, cp, sz, C.POINTER(C.c_int), cp, sz]),
+        "leann_cuda_filter_mask": (C.c_int, [vp, cpp, szp, sz, vp, cp, sz]),
+        "leann_cuda_filter_free": (None, [vp]),
+        "leann_cuda_searcher_load": (C.c_int, [cp, cp, sz, C.c_int, pp, cp, sz]),
+        "leann_cuda_searcher_len": (sz, [vp]),
+        "leann_cuda_searcher_id": (sz, [vp, C.c_uint64, cp, sz]),
+        "leann_cuda_searcher_search": (C.c_int, [vp, vp, cpp, szp, sz, sz, sz, cp, C.c_int, C.c_float, vp, vp, vp, cp, sz]),
+        "leann_cuda_searcher_close": (None, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name, None)
+        if fn is None:
+            continue  # reported by tests/test_abi.py
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+ABI_SYMBOLS = None  # filled by tests from include/leann_cuda.h
+
+
+def _check(code: int, err) -> None:
+    if code != OK:
+        raise LeannCudaError(code, err.value.decode(errors="replace"))
+
+
+def _err():
+    return C.create_string_buffer(1024)
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def pack_mask(bits) -> np.ndarray:
+    """bool[N] -> u64 words (bit s%64 of word s//64)."""
+    bits = np.asarray(bits, dtype=bool)
+    pad = (-bits.shape[0]) % 64
+    b = np.concatenate([bits, np.zeros(pad, dtype=bool)]).reshape(-1, 64)
+    return (b.astype(np.uint64) << np.arange(64, dtype=np.uint64)[None, :]).sum(axis=1, dtype=np.uint64)
+
+
+def reduction_lanes(dims: int) -> int:
+    return int(lib().leann_cuda_reduction_lanes(dims))
+
+
+def queue_capacity(ef: int, masked: bool) -> int:
+    return int(lib().leann_cuda_queue_capacity(ef, 1 if masked else 0))
+
+
+def device_count() -> int:
+    return int(lib().leann_cuda_device_count())
+
+
+def _strs(items: Sequence):
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in items]
+    arr = (C.c_char_p * len(bs))(*bs)
+    lens = (C.c_size_t * len(bs))(*[len(b) for b in bs])
+    return bs, arr, lens
+
+
+# ------------------------------------------------------------------------------------------------
+# backend/traits.rs:11-30  trait BackendSearcher
+# ------------------------------------------------------------------------------------------------
+class BackendSearcher:
+    """`trait BackendSearcher` (src/backend/traits.rs:11-30) over a device-resident index."""
+
+    backend = BACKEND_HNSW
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    # -- construction ----------------------------------------------------------------------------
+    @classmethod
+    def _open(cls, base_path: str, backend: int, dimensions: int, metric: int = METRIC_DEFAULT, device: int = 0):
+        h = C.c_void_p()
+        e = _err()
+        _check(lib().leann_cuda_open(os.fsencode(base_path), backend, dimensions, metric, device, C.byref(h), e, 1024), e)
+        return cls(h.value)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().leann_cuda_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- trait methods ---------------------------------------------------------------------------
+    def __len__(self) -> int:
+        return int(lib().leann_cuda_len(self._h))
+
+    def len(self) -> int:
+        return len(self)
+
+    def is_empty(self) -> bool:
+        return len(self) == 0
+
+    @property
+    def dims(self) -> int:
+        return int(lib().leann_cuda_dims(self._h))
+
+    def info(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        lib().leann_cuda_info(self._h, out)
+        names = ["n", "dims", "backend", "metric", "M", "M0", "max_level", "entry"]
+        return dict(zip(names, [int(x) for x in out]))
+
+    def _effective_ef(self, complexity: int) -> int:
+        return complexity
+
+    def search(self, query, top_k: int, complexity: int = 64):
+        """One query, exactly the trait call: returns (keys: list[int], distances: list[float])."""
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(1, -1)
+        keys, dists, counts = self.search_batch(q, top_k, self._effective_ef(complexity))
+        c = int(counts[0])
+        return [int(x) for x in keys[0, :c]], [float(x) for x in dists[0, :c]]
+
+    def search_batch(self, queries, top_k: int, ef: int, mask: Optional[np.ndarray] = None):
+        """Host buffers in, host buffers out (H2D/D2H inside the call)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dims:
+            raise LeannCudaError(ERR_DIM_MISMATCH, f"queries must be [nq, {self.dims}]")
+        nq = q.shape[0]
+        keys = np.empty((nq, top_k), dtype=np.uint64)
+        dists = np.empty((nq, top_k), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.uint32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint64)
+        e = _err()
+        _check(lib().leann_cuda_search(self._h, _np_ptr(q), nq, top_k, ef, None if m is None else _np_ptr(m),
+                                       MASK_NONE if m is None else MASK_INLINE, _np_ptr(keys), _np_ptr(dists),
+                                       _np_ptr(counts), e, 1024), e)
+        return keys, dists, counts
+
+    def search_device(self, queries, top_k: int, ef: int, mask=None, out=None, stats=None, stream=None):
+        """torch CUDA tensors in/out, enqueued on torch's current stream, no host sync."""
+        import torch
+
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        nq = queries.shape[0]
+        if out is None:
+            keys = torch.empty((nq, top_k), dtype=torch.int64, device=queries.device)
+            dists = torch.empty((nq, top_k), dtype=torch.float32, device=queries.device)
+            counts = torch.empty((nq,), dtype=torch.int32, device=queries.device)
+        else:
+            keys, dists, counts = out
+        st = stream if stream is not None else torch.cuda.current_stream(queries.device).cuda_stream
+        e = _err()
+        _check(lib().leann_cuda_search_device(
+            self._h, C.c_void_p(queries.data_ptr()), nq, top_k, ef,
+            None if mask is None else C.c_void_p(mask.data_ptr()), MASK_NONE if mask is None else MASK_INLINE,
+            C.c_void_p(keys.data_ptr()), C.c_void_p(dists.data_ptr()), C.c_void_p(counts.data_ptr()),
+            None if stats is None else C.c_void_p(stats.data_ptr()), C.c_void_p(st), e, 1024), e)
+        return keys, dists, counts
+
+    def save(self, base_path: str):
+        e = _err()
+        _check(lib().leann_cuda_save(self._h, os.fsencode(base_path), e, 1024), e)
+
+
+class HnswSearcher(BackendSearcher):
+    """src/backend/hnsw.rs:12-93. `search` ignores `complexity` and runs ef = max(64, top_k)
+    exactly as hnsw.rs:49,83 do; `search_batch`/`search_device` take a real ef."""
+
+    backend = BACKEND_HNSW
+
+    @classmethod
+    def load(cls, index_path: str, dimensions: int, device: int = 0, metric: int = METRIC_DEFAULT):
+        return cls._open(index_path, BACKEND_HNSW, dimensions, metric, device)
+
+    def _effective_ef(self, complexity: int) -> int:
+        return 64  # expansion_search: 64 (hnsw.rs:49); `_complexity` unused (hnsw.rs:83)
+
+    @classmethod
+    def build(cls, embeddings, graph_degree: int = 32, complexity: int = 64, metric: int = METRIC_DEFAULT,
+              seed: int = 1, device: int = 0):
+        """hnsw::build_index (hnsw.rs:96-139) on the GPU; `embeddings` numpy [n,d] or CUDA tensor."""
+        h = C.c_void_p()
+        e = _err()
+        if isinstance(embeddings, np.ndarray):
+            x = np.ascontiguousarray(embeddings, dtype=np.float32)
+            ptr, on_dev, n, d = _np_ptr(x), 0, x.shape[0], x.shape[1]
+        else:
+            assert embeddings.is_cuda and embeddings.is_contiguous()
+            ptr, on_dev, n, d = C.c_void_p(embeddings.data_ptr()), 1, embeddings.shape[0], embeddings.shape[1]
+            device = embeddings.device.index or 0
+        _check(lib().leann_cuda_hnsw_build(ptr, on_dev, n, d, graph_degree, complexity, metric, seed, device,
+                                           C.byref(h), e, 1024), e)
+        return cls(h.value)
+
+
+class DiskAnnSearcher(BackendSearcher):
+    """src/backend/diskann.rs:12-66: beam = max(complexity, top_k) (:54), DistDot metric (:16)."""
+
+    backend = BACKEND_VAMANA
+
+    @classmethod
+    def load(cls, index_path: str, dimensions: int = 0, device: int = 0, metric: int = METRIC_DEFAULT):
+        return cls._open(index_path, BACKEND_VAMANA, dimensions, metric, device)
+
+    @classmethod
+    def build(cls, embeddings, graph_degree: int = 64, complexity: int = 100, alpha: float = 1.2,
+              metric: int = METRIC_DEFAULT, seed: int = 1, device: int = 0):
+        h = C.c_void_p()
+        e = _err()
+        if isinstance(embeddings, np.ndarray):
+            x = np.ascontiguousarray(embeddings, dtype=np.float32)
+            ptr, on_dev, n, d = _np_ptr(x), 0, x.shape[0], x.shape[1]
+        else:
+            ptr, on_dev, n, d = C.c_void_p(embeddings.data_ptr()), 1, embeddings.shape[0], embeddings.shape[1]
+            device = embeddings.device.index or 0
+        _check(lib().leann_cuda_vamana_build(ptr, on_dev, n, d, graph_degree, complexity, alpha, metric, seed, device,
+                                             C.byref(h), e, 1024), e)
+        return cls(h.value)
+
+
+class FlatSearcher(BackendSearcher):
+    """Exact scan with RecomputeSearcher's scoring (src/index/recompute.rs:96-110): raw dot,
+    descending, ties by ascending index."""
+
+    backend = BACKEND_FLAT
+
+    @classmethod
+    def load(cls, index_path: str, dimensions: int, device: int = 0, metric: int = METRIC_DEFAULT):
+        return cls._open(index_path, BACKEND_FLAT, dimensions, metric, device)
+
+    @classmethod
+    def from_vectors(cls, vectors, metric: int = METRIC_DOT_DESC, device: int = 0):
+        h = C.c_void_p()
+        e = _err()
+        if isinstance(vectors, np.ndarray):
+            x = np.ascontiguousarray(vectors, dtype=np.float32)
+            _check(lib().leann_cuda_flat_from_host(_np_ptr(x), x.shape[0], x.shape[1], metric, device, C.byref(h), e, 1024), e)
+        else:
+            assert vectors.is_cuda and vectors.is_contiguous()
+            device = vectors.device.index or 0
+            _check(lib().leann_cuda_flat_from_device(C.c_void_p(vectors.data_ptr()), vectors.shape[0], vectors.shape[1],
+                                                     metric, device, C.byref(h), e, 1024), e)
+        return cls(h.value)
+
+
+class BackendType:
+    """src/backend/mod.rs:16-45."""
+
+    Hnsw = "hnsw"
+    DiskAnn = "diskann"
+
+    @staticmethod
+    def load_searcher(backend_name: str, index_path: str, dimensions: int, device: int = 0) -> BackendSearcher:
+        if backend_name == "hnsw":
+            return HnswSearcher.load(index_path, dimensions, device)
+        if backend_name == "diskann":
+            return DiskAnnSearcher.load(index_path, dimensions, device)
+        if backend_name == "flat":
+            return FlatSearcher.load(index_path, dimensions, device)
+        raise LeannCudaError(ERR_INVALID_ARG, f"Unknown backend: {backend_name}")  # searcher.rs:98
+
+
+def topk_merge_device(keys_in, dists_in, descending: bool = False):
+    """keys_in/dists_in: CUDA tensors [n_shards, nq, k] (an all_gather result) -> merged [nq, k]."""
+    import torch
+
+    g, nq, k = keys_in.shape
+    keys = torch.empty((nq, k), dtype=torch.int64, device=keys_in.device)
+    dists = torch.empty((nq, k), dtype=torch.float32, device=keys_in.device)
+    counts = torch.empty((nq,), dtype=torch.int32, device=keys_in.device)
+    e = _err()
+    st = torch.cuda.current_stream(keys_in.device).cuda_stream
+    _check(lib().leann_cuda_topk_merge_device(C.c_void_p(keys_in.data_ptr()), C.c_void_p(dists_in.data_ptr()), g, nq, k,
+                                              1 if descending else 0, C.c_void_p(keys.data_ptr()),
+                                              C.c_void_p(dists.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                              C.c_void_p(st), e, 1024), e)
+    return keys, dists, counts
+
+
+from .text import Bm25Scorer, MetadataFilter, IndexSearcher, SearchOptions, SearchResult, hybrid_rerank, tokenize  # noqa: E402,F401

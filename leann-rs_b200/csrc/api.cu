@@ -1,0 +1,446 @@
+// api.cu — the C ABI of the vector path (include/leann_cuda.h): open/build/save/search/merge/close.
+// Host logic only; kernels live in graph_search.cu, exact_scan.cu, hnsw_build.cu.
+#include <algorithm>
+#include <functional>
+#include <memory>
+
+#include "internal.h"
+
+using namespace leann;
+
+namespace leann {
+int guard_impl(char* err, size_t errlen, const std::function<void()>& f);
+// builders (hnsw_build.cu / vamana_build.cu)
+void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed);
+void gpu_vamana_build(leann_cuda_index* ix, size_t R, size_t L, float alpha, uint64_t seed);
+}  // namespace leann
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        cudaError_t e = cudaSetDevice(dev);
+        if (e != cudaSuccess) throw Error(LEANN_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void require_gpu(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error(LEANN_ERR_CUDA, "no CUDA device available: libleann_cuda has no CPU fallback");
+    }
+    if (device < 0 || device >= n) throw Error(LEANN_ERR_INVALID_ARG, "device ordinal out of range");
+    cudaDeviceProp p;
+    LEANN_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) throw Error(LEANN_ERR_CUDA, std::string("device is sm_") + std::to_string(p.major * 10 + p.minor) + ", this library is built for sm_100a only");
+}
+
+template <typename T>
+T* dalloc(size_t count) {
+    T* p = nullptr;
+    if (count == 0) count = 1;
+    LEANN_CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    return p;
+}
+
+void upload_vectors(leann_cuda_index* ix, const float* src, bool on_device) {
+    ix->d4 = (uint32_t)((ix->d + 3) / 4);
+    ix->vecs = dalloc<float4>(ix->n * ix->d4);
+    if (ix->n == 0) return;
+    if (on_device) {
+        launch_pad_rows(src, ix->vecs, ix->n, (uint32_t)ix->d, ix->d4, nullptr);
+    } else if (ix->d % 4 == 0) {
+        LEANN_CUDA_CHECK(cudaMemcpy(ix->vecs, src, ix->n * ix->d * 4, cudaMemcpyHostToDevice));
+    } else {
+        float* tmp = dalloc<float>(ix->n * ix->d);
+        LEANN_CUDA_CHECK(cudaMemcpy(tmp, src, ix->n * ix->d * 4, cudaMemcpyHostToDevice));
+        launch_pad_rows(tmp, ix->vecs, ix->n, (uint32_t)ix->d, ix->d4, nullptr);
+        LEANN_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(tmp);
+    }
+    LEANN_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+template <typename T>
+T* upload(const std::vector<T>& v) {
+    T* p = dalloc<T>(v.size());
+    if (!v.empty()) LEANN_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+leann_cuda_index* from_hnsw(HostHnsw& h, int device, int metric) {
+    std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
+    ix->backend = LEANN_BACKEND_HNSW; ix->device = device;
+    ix->metric = metric == LEANN_METRIC_DEFAULT ? h.metric : metric;
+    ix->n = h.n; ix->d = h.d; ix->M = (uint32_t)h.M; ix->M0 = (uint32_t)h.M0;
+    ix->max_level = (int)h.max_level; ix->entry = (uint32_t)h.entry;
+    ix->n_upper_lists = h.M ? h.adjU.size() / h.M : 0;
+    ix->h_levels = h.levels;
+    upload_vectors(ix.get(), h.vecs.data(), false);
+    ix->adj0 = upload(h.adj0);
+    ix->upper_base = upload(h.upper_base);
+    ix->adjU = upload(h.adjU);
+    ix->identity_keys = true;
+    for (size_t i = 0; i < h.n; ++i) if (h.keys[i] != i) { ix->identity_keys = false; break; }
+    ix->keys = upload(h.keys);
+    return ix.release();
+}
+
+leann_cuda_index* from_vamana(HostVamana& h, int device, int metric) {
+    std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
+    ix->backend = LEANN_BACKEND_VAMANA; ix->device = device;
+    // diskann.rs:16,36 hard-wires DistDot
+    ix->metric = metric == LEANN_METRIC_DEFAULT ? LEANN_METRIC_IP_CLAMP : metric;
+    ix->n = h.n; ix->d = h.d; ix->M = (uint32_t)h.R; ix->M0 = (uint32_t)h.R;
+    ix->max_level = 0; ix->entry = h.medoid; ix->distance_name = h.distance_name;
+    upload_vectors(ix.get(), h.vecs.data(), false);
+    ix->adj0 = upload(h.adj);
+    ix->identity_keys = true;
+    return ix.release();
+}
+
+void ensure_workspace(const leann_cuda_index* ix, size_t nq) {
+    SearchWorkspace& ws = ix->ws;
+    if (!ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+    if (ix->backend == LEANN_BACKEND_FLAT) return;
+    int max_warps = graph_search_max_warps(ix->device);
+    size_t n_pad = (ix->n + 127) & ~(size_t)127;
+    // bound the visited workspace to ~1/8 of device memory
+    size_t free_b = 0, total_b = 0;
+    LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = total_b / 8;
+    while (max_warps > 64 && (size_t)max_warps * n_pad > budget) max_warps /= 2;
+    int want = (int)std::min<size_t>((size_t)max_warps, std::max<size_t>(nq, 1));
+    want = (want + 3) & ~3;
+    if (ws.n_warps >= want && ws.n_pad == n_pad) return;
+    if (ws.visited) cudaFree(ws.visited);
+    if (ws.epochs) cudaFree(ws.epochs);
+    if (!ws.counter) ws.counter = dalloc<uint32_t>(1);
+    // allocate for the full pool once a large batch has been seen, else just what is needed
+    ws.n_warps = want;
+    ws.n_pad = n_pad;
+    ws.visited = dalloc<uint8_t>((size_t)want * n_pad);
+    ws.epochs = dalloc<uint32_t>(want);
+    LEANN_CUDA_CHECK(cudaMemset(ws.visited, 0, (size_t)want * n_pad));
+    LEANN_CUDA_CHECK(cudaMemset(ws.epochs, 0, (size_t)want * 4));
+}
+
+uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
+                        const uint64_t* d_mask, int mask_mode, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
+                        uint64_t* d_stats, cudaStream_t stream) {
+    if (!ix) throw Error(LEANN_ERR_INVALID_ARG, "null index");
+    if (nq == 0) return;
+    if (k == 0) throw Error(LEANN_ERR_INVALID_ARG, "k must be > 0");
+    if (mask_mode == LEANN_MASK_NONE) d_mask = nullptr;
+    ensure_workspace(ix, nq);
+    if (ix->backend == LEANN_BACKEND_FLAT) {
+        size_t need = exact_scan_scratch_bytes(ix->d4, (uint32_t)nq, (uint32_t)k);
+        if (ix->scan_scratch_bytes < need) {
+            if (ix->scan_scratch) cudaFree(ix->scan_scratch);
+            ix->scan_scratch = nullptr; ix->scan_scratch_bytes = 0;
+            LEANN_CUDA_CHECK(cudaMalloc(&ix->scan_scratch, need));
+            ix->scan_scratch_bytes = need;
+        }
+        FlatView f{ix->vecs, (uint32_t)ix->n, (uint32_t)ix->d, ix->d4, ix->metric};
+        launch_exact_scan(f, d_queries, (uint32_t)nq, (uint32_t)k, d_mask, d_keys, d_dists, d_counts, ix->scan_scratch,
+                          ix->scan_scratch_bytes, stream);
+        if (d_stats) LEANN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, nq * 4 * sizeof(uint64_t), stream));
+        return;
+    }
+    if (ix->n == 0) throw Error(LEANN_ERR_INVALID_ARG, "index is empty");
+    size_t eff = std::max(ef, k);
+    if (eff > (size_t)MAX_EF) throw Error(LEANN_ERR_INVALID_ARG, "max(ef, k) exceeds 1024");
+    SearchParams p;
+    p.queries = d_queries;
+    p.nq = (uint32_t)nq; p.k = (uint32_t)k; p.ef = (uint32_t)eff;
+    p.next_cap = (uint32_t)leann_cuda_queue_capacity(eff, d_mask != nullptr);
+    p.next_capp = next_pow2(p.next_cap);
+    p.mask = d_mask;
+    p.nonstrict_term = ix->backend == LEANN_BACKEND_VAMANA ? 1 : 0;
+    p.out_keys = d_keys; p.out_dists = d_dists; p.out_counts = d_counts; p.out_stats = d_stats;
+    p.visited = ix->ws.visited; p.epochs = ix->ws.epochs; p.counter = ix->ws.counter;
+    p.n_pad = ix->ws.n_pad;
+    p.n_warps = (int)std::min<size_t>((size_t)ix->ws.n_warps, (nq + 3) & ~(size_t)3);
+    launch_graph_search(ix->view(), p, stream);
+}
+
+template <typename T>
+void ensure_buf(T*& p, size_t& cap, size_t need) {
+    if (cap >= need) return;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    LEANN_CUDA_CHECK(cudaMalloc(&p, need * sizeof(T)));
+    cap = need;
+}
+
+}  // namespace
+
+namespace leann {
+int guard_impl(char* err, size_t errlen, const std::function<void()>& f) {
+    auto put = [&](const char* m) { if (err && errlen) { snprintf(err, errlen, "%s", m); } };
+    try {
+        if (err && errlen) err[0] = 0;
+        f();
+        return LEANN_OK;
+    } catch (const Error& e) {
+        put(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        put("out of host memory");
+        return LEANN_ERR_INVALID_ARG;
+    } catch (const std::exception& e) {
+        put(e.what());
+        return LEANN_ERR_INVALID_ARG;
+    } catch (...) {
+        put("unknown error");
+        return LEANN_ERR_INVALID_ARG;
+    }
+}
+}  // namespace leann
+
+#define GUARD(...) return leann::guard_impl(err, errlen, [&]() __VA_ARGS__)
+
+extern "C" {
+
+int leann_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char* leann_cuda_version(void) { return "leann-cuda 0.1.0 (sm_100a)"; }
+int leann_cuda_reduction_lanes(size_t dims) { return reduction_lanes(dims); }
+size_t leann_cuda_queue_capacity(size_t ef, int masked) { return masked ? std::min<size_t>(4 * ef, 2048) : ef; }
+
+int leann_cuda_open(const char* base_path, int backend, size_t dims, int metric, int device,
+                    leann_cuda_index** out, char* err, size_t errlen) {
+    GUARD({
+        if (!base_path || !out) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        std::string base(base_path);
+        if (backend == LEANN_BACKEND_HNSW) {
+            std::string file = with_extension(base, "index");
+            if (is_faiss_index(file))  // hnsw.rs:24-32
+                throw Error(LEANN_ERR_FAISS_FORMAT,
+                            "This index was built with Python LEANN (FAISS format).\nRust LEANN uses usearch which has a different binary format.\n\n"
+                            "To use this index with Rust LEANN, you need to rebuild it:\n  leann build <name> --docs <path> --force\n\n"
+                            "The passages and metadata files are compatible and will be preserved.");
+            HostHnsw h;
+            read_usearch_index(file, dims, h);
+            require_gpu(device);
+            DeviceGuard dg(device);
+            *out = from_hnsw(h, device, metric);
+        } else if (backend == LEANN_BACKEND_VAMANA) {
+            HostVamana h;
+            read_diskann(with_extension(base, "diskann"), dims, h);
+            require_gpu(device);
+            DeviceGuard dg(device);
+            *out = from_vamana(h, device, metric);
+        } else if (backend == LEANN_BACKEND_FLAT) {
+            std::vector<float> v;
+            size_t n = 0;
+            read_embeddings(with_extension(base, "embeddings"), dims, v, n);
+            require_gpu(device);
+            DeviceGuard dg(device);
+            std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
+            ix->backend = LEANN_BACKEND_FLAT; ix->device = device;
+            ix->metric = metric == LEANN_METRIC_DEFAULT ? LEANN_METRIC_DOT_DESC : metric;
+            ix->n = n; ix->d = dims;
+            upload_vectors(ix.get(), v.data(), false);
+            *out = ix.release();
+        } else {
+            throw Error(LEANN_ERR_INVALID_ARG, "Unknown backend");  // searcher.rs:98
+        }
+    });
+}
+
+static int flat_from(const float* vectors, bool on_device, size_t n, size_t dims, int metric, int device,
+                     leann_cuda_index** out, char* err, size_t errlen) {
+    GUARD({
+        if (!out || (!vectors && n)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        if (dims == 0) throw Error(LEANN_ERR_INVALID_ARG, "dims must be > 0");
+        require_gpu(device);
+        DeviceGuard dg(device);
+        std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
+        ix->backend = LEANN_BACKEND_FLAT; ix->device = device;
+        ix->metric = metric == LEANN_METRIC_DEFAULT ? LEANN_METRIC_DOT_DESC : metric;
+        ix->n = n; ix->d = dims;
+        upload_vectors(ix.get(), vectors, on_device);
+        *out = ix.release();
+    });
+}
+int leann_cuda_flat_from_host(const float* vectors, size_t n, size_t dims, int metric, int device,
+                              leann_cuda_index** out, char* err, size_t errlen) {
+    return flat_from(vectors, false, n, dims, metric, device, out, err, errlen);
+}
+int leann_cuda_flat_from_device(const float* d_vectors, size_t n, size_t dims, int metric, int device,
+                                leann_cuda_index** out, char* err, size_t errlen) {
+    return flat_from(d_vectors, true, n, dims, metric, device, out, err, errlen);
+}
+
+int leann_cuda_hnsw_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
+                          size_t graph_degree, size_t complexity, int metric, uint64_t seed, int device,
+                          leann_cuda_index** out, char* err, size_t errlen) {
+    GUARD({
+        if (!out || (!vectors && n)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        if (dims == 0 || graph_degree < 2 || 2 * graph_degree > (size_t)MAX_DEG)
+            throw Error(LEANN_ERR_INVALID_ARG, "graph_degree must be in 2..64 and dims > 0");
+        if (complexity == 0 || complexity > (size_t)MAX_EF) throw Error(LEANN_ERR_INVALID_ARG, "complexity must be in 1..1024");
+        require_gpu(device);
+        DeviceGuard dg(device);
+        std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
+        ix->backend = LEANN_BACKEND_HNSW; ix->device = device;
+        ix->metric = metric == LEANN_METRIC_DEFAULT ? LEANN_METRIC_IP : metric;  // hnsw.rs:112
+        ix->n = n; ix->d = dims;
+        upload_vectors(ix.get(), vectors, vectors_on_device != 0);
+        gpu_hnsw_build(ix.get(), graph_degree, complexity, seed);
+        *out = ix.release();
+    });
+}
+
+int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
+                            size_t graph_degree, size_t complexity, float alpha, int metric,
+                            uint64_t seed, int device, leann_cuda_index** out, char* err, size_t errlen) {
+    GUARD({
+        if (!out || (!vectors && n)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        if (dims == 0 || graph_degree < 2 || graph_degree > (size_t)MAX_DEG)
+            throw Error(LEANN_ERR_INVALID_ARG, "graph_degree must be in 2..128 and dims > 0");
+        if (complexity == 0 || complexity > (size_t)MAX_EF) throw Error(LEANN_ERR_INVALID_ARG, "complexity must be in 1..1024");
+        require_gpu(device);
+        DeviceGuard dg(device);
+        std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
+        ix->backend = LEANN_BACKEND_VAMANA; ix->device = device;
+        ix->metric = metric == LEANN_METRIC_DEFAULT ? LEANN_METRIC_IP_CLAMP : metric;
+        ix->n = n; ix->d = dims; ix->distance_name = "DistDot";
+        upload_vectors(ix.get(), vectors, vectors_on_device != 0);
+        gpu_vamana_build(ix.get(), graph_degree, complexity, alpha, seed);
+        *out = ix.release();
+    });
+}
+
+int leann_cuda_save(const leann_cuda_index* ix, const char* base_path, char* err, size_t errlen) {
+    GUARD({
+        if (!ix || !base_path) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        DeviceGuard dg(ix->device);
+        std::string base(base_path);
+        // un-pad vectors
+        std::vector<float> padded(ix->n * ix->d4 * 4), vecs(ix->n * ix->d);
+        if (ix->n) LEANN_CUDA_CHECK(cudaMemcpy(padded.data(), ix->vecs, padded.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < ix->n; ++i) memcpy(&vecs[i * ix->d], &padded[i * ix->d4 * 4], ix->d * 4);
+        padded.clear(); padded.shrink_to_fit();
+        auto download = [](auto& v, const void* src) { if (!v.empty()) LEANN_CUDA_CHECK(cudaMemcpy(v.data(), src, v.size() * sizeof(v[0]), cudaMemcpyDeviceToHost)); };
+        if (ix->backend == LEANN_BACKEND_HNSW) {
+            HostHnsw h;
+            h.n = ix->n; h.d = ix->d; h.M = ix->M; h.M0 = ix->M0; h.max_level = ix->max_level; h.entry = ix->entry;
+            h.metric = ix->metric; h.vecs.swap(vecs); h.levels = ix->h_levels;
+            h.keys.resize(ix->n); h.adj0.resize(ix->n * ix->M0); h.upper_base.resize(ix->n); h.adjU.resize(ix->n_upper_lists * ix->M);
+            download(h.keys, ix->keys); download(h.adj0, ix->adj0); download(h.upper_base, ix->upper_base); download(h.adjU, ix->adjU);
+            write_usearch_index(with_extension(base, "index"), h);
+        } else if (ix->backend == LEANN_BACKEND_VAMANA) {
+            HostVamana h;
+            h.n = ix->n; h.d = ix->d; h.R = ix->M0; h.medoid = ix->entry; h.distance_name = ix->distance_name;
+            h.vecs.swap(vecs); h.adj.resize(ix->n * ix->M0);
+            download(h.adj, ix->adj0);
+            write_diskann(with_extension(base, "diskann"), h);
+        } else {
+            write_embeddings(with_extension(base, "embeddings"), vecs.data(), ix->n, ix->d);
+        }
+    });
+}
+
+size_t leann_cuda_len(const leann_cuda_index* ix) { return ix ? ix->n : 0; }
+size_t leann_cuda_dims(const leann_cuda_index* ix) { return ix ? ix->d : 0; }
+int leann_cuda_info(const leann_cuda_index* ix, uint64_t* info) {
+    if (!ix || !info) return LEANN_ERR_INVALID_ARG;
+    info[0] = ix->n; info[1] = ix->d; info[2] = (uint64_t)ix->backend; info[3] = (uint64_t)ix->metric;
+    info[4] = ix->M; info[5] = ix->M0; info[6] = (uint64_t)ix->max_level; info[7] = ix->entry;
+    return LEANN_OK;
+}
+
+int leann_cuda_search_device(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
+                             const uint64_t* d_mask_bits, int mask_mode, uint64_t* d_keys, float* d_dists,
+                             uint32_t* d_counts, uint64_t* d_stats, void* cuda_stream, char* err, size_t errlen) {
+    GUARD({
+        if (!ix) throw Error(LEANN_ERR_INVALID_ARG, "null index");
+        DeviceGuard dg(ix->device);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        search_device_impl(ix, d_queries, nq, k, ef, d_mask_bits, mask_mode, d_keys, d_dists, d_counts, d_stats,
+                           (cudaStream_t)cuda_stream);
+    });
+}
+
+int leann_cuda_search(const leann_cuda_index* ix, const float* queries, size_t nq, size_t k, size_t ef,
+                      const uint64_t* mask_bits, int mask_mode, uint64_t* keys, float* dists, uint32_t* counts,
+                      char* err, size_t errlen) {
+    GUARD({
+        if (!ix) throw Error(LEANN_ERR_INVALID_ARG, "null index");
+        if (nq == 0) return;
+        if (!queries || !keys || !dists) throw Error(LEANN_ERR_INVALID_ARG, "null buffer");
+        DeviceGuard dg(ix->device);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ensure_workspace(ix, nq);
+        SearchWorkspace& ws = ix->ws;
+        ensure_buf(ws.d_queries, ws.cap_q, nq * ix->d);
+        size_t out_need = nq * k;
+        if (ws.cap_out < out_need) {
+            if (ws.d_keys) cudaFree(ws.d_keys);
+            if (ws.d_dists) cudaFree(ws.d_dists);
+            ws.d_keys = nullptr; ws.d_dists = nullptr; ws.cap_out = 0;
+            LEANN_CUDA_CHECK(cudaMalloc(&ws.d_keys, out_need * 8));
+            LEANN_CUDA_CHECK(cudaMalloc(&ws.d_dists, out_need * 4));
+            ws.cap_out = out_need;
+        }
+        ensure_buf(ws.d_counts, ws.cap_counts, nq);
+        uint32_t* d_counts = ws.d_counts;
+        const uint64_t* d_mask = nullptr;
+        if (mask_bits && mask_mode != LEANN_MASK_NONE) {
+            size_t words = (ix->n + 63) / 64;
+            ensure_buf(ws.d_mask, ws.cap_mask, words);
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(ws.d_mask, mask_bits, words * 8, cudaMemcpyHostToDevice, ws.stream));
+            d_mask = ws.d_mask;
+        }
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(ws.d_queries, queries, nq * ix->d * 4, cudaMemcpyHostToDevice, ws.stream));
+        search_device_impl(ix, ws.d_queries, nq, k, ef, d_mask, mask_mode, ws.d_keys, ws.d_dists, d_counts, nullptr, ws.stream);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(keys, ws.d_keys, out_need * 8, cudaMemcpyDeviceToHost, ws.stream));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(dists, ws.d_dists, out_need * 4, cudaMemcpyDeviceToHost, ws.stream));
+        if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts, nq * 4, cudaMemcpyDeviceToHost, ws.stream));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(ws.stream));
+    });
+}
+
+int leann_cuda_topk_merge_device(const uint64_t* d_keys_in, const float* d_dists_in, size_t n_shards, size_t nq,
+                                 size_t k, int descending, uint64_t* d_keys_out, float* d_dists_out,
+                                 uint32_t* d_counts_out, void* cuda_stream, char* err, size_t errlen) {
+    GUARD({
+        if (!d_keys_in || !d_dists_in || !d_keys_out || !d_dists_out) throw Error(LEANN_ERR_INVALID_ARG, "null buffer");
+        launch_topk_merge(d_keys_in, d_dists_in, (uint32_t)n_shards, (uint32_t)nq, (uint32_t)k, descending, d_keys_out,
+                          d_dists_out, d_counts_out, (cudaStream_t)cuda_stream);
+    });
+}
+
+void leann_cuda_close(leann_cuda_index* ix) {
+    if (!ix) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ix->device);
+    cudaFree(ix->vecs); cudaFree(ix->adj0); cudaFree(ix->upper_base); cudaFree(ix->adjU); cudaFree(ix->keys);
+    SearchWorkspace& ws = ix->ws;
+    cudaFree(ws.visited); cudaFree(ws.epochs); cudaFree(ws.counter); cudaFree(ws.d_queries); cudaFree(ws.d_keys);
+    cudaFree(ws.d_dists); cudaFree(ws.d_counts); cudaFree(ws.d_mask);
+    if (ws.stream) cudaStreamDestroy(ws.stream);
+    cudaFree(ix->scan_scratch);
+    cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+    delete ix;
+}
+
+}  // extern "C"

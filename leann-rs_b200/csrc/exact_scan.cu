@@ -1,0 +1,403 @@
+// exact_scan.cu — K2 / K2r: exact brute-force scan with a fused top-k, replacing
+// RecomputeSearcher::search's scoring + sort + take(k) (leann-rs src/index/recompute.rs:96-110,
+// dot_product :137-139), plus K4 (per-query merge of per-shard top-k lists).
+//
+// Round structure ("progressive threshold"): the database is visited in growing row chunks. A tile
+// kernel computes a 128-query x 128-row block of f32 scores and appends only the scores that can
+// still enter the top-k (packed 64-bit key <= the query's current k-th best key) to a per-query
+// candidate list; a select kernel then merges candidates into the running top-k and tightens the
+// threshold. The full nq x N score matrix is never materialised.
+// Ordering is total: key = (ordered(score) << 32) | row, so equal scores rank by ascending row —
+// exactly what the reference's stable sort over the enumerate() order yields (recompute.rs:106).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "internal.h"
+
+namespace leann {
+
+namespace {
+
+constexpr int TM = 128, TN = 128, TK = 16, LDS_STRIDE = 132;
+
+__device__ __forceinline__ uint32_t order_f32(float f) {  // monotone float -> uint
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(uint32_t u) {
+    u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+
+struct ScanScratch {
+    unsigned long long* cand;      // [nq][cap]
+    uint32_t* cand_cnt;            // [nq]
+    unsigned long long* best;      // [nq][kpad]
+    uint32_t* best_cnt;            // [nq]
+    unsigned long long* thr;       // [nq]
+    uint32_t* overflow;            // [1]
+    float4* qpad;                  // [nq][d4]
+};
+
+// One 128x128 tile of scores, K-loop over the padded dimension, threshold epilogue.
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+scan_tile_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32_t d4, uint32_t nq,
+                 uint32_t r0, uint32_t r1, const uint64_t* __restrict__ mask,
+                 const unsigned long long* __restrict__ thr, unsigned long long* __restrict__ cand,
+                 uint32_t* __restrict__ cand_cnt, uint32_t cap, uint32_t* __restrict__ overflow) {
+    __shared__ __align__(16) float As[2][TK][LDS_STRIDE];
+    __shared__ __align__(16) float Bs[2][TK][LDS_STRIDE];
+    __shared__ unsigned long long s_thr[TM];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const uint32_t m0 = blockIdx.y * TM, n0 = r0 + blockIdx.x * TN;
+    if (tid < TM) s_thr[tid] = (m0 + tid < nq) ? thr[m0 + tid] : 0ull;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const uint32_t kt = (d4 + 3) / 4;  // TK=16 floats = 4 float4 per k-tile
+    float4 ra[2], rb[2];
+    auto gload = [&](uint32_t t) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            int idx = tid + u * 256;
+            int row = idx >> 2, c4 = idx & 3;
+            uint32_t kc = t * 4 + c4;
+            uint32_t qa = m0 + row, xb = n0 + row;
+            ra[u] = (qa < nq && kc < d4) ? Q[(size_t)qa * d4 + kc] : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[u] = (xb < r1 && kc < d4) ? __ldg(&X[(size_t)xb * d4 + kc]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            int idx = tid + u * 256;
+            int row = idx >> 2, c4 = idx & 3;
+            As[buf][c4 * 4 + 0][row] = ra[u].x; As[buf][c4 * 4 + 1][row] = ra[u].y;
+            As[buf][c4 * 4 + 2][row] = ra[u].z; As[buf][c4 * 4 + 3][row] = ra[u].w;
+            Bs[buf][c4 * 4 + 0][row] = rb[u].x; Bs[buf][c4 * 4 + 1][row] = rb[u].y;
+            Bs[buf][c4 * 4 + 2][row] = rb[u].z; Bs[buf][c4 * 4 + 3][row] = rb[u].w;
+        }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (uint32_t t = 0; t < kt; ++t) {
+        int buf = t & 1;
+        if (t + 1 < kt) gload(t + 1);
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (METRIC == LEANN_METRIC_L2SQ) {
+                        float df = a[i] - b[j];
+                        acc[i][j] = fmaf(df, df, acc[i][j]);
+                    } else {
+                        acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    }
+                }
+        }
+        if (t + 1 < kt) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    // epilogue: score -> rank key -> threshold test -> append
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int ml = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        uint32_t qi = m0 + ml;
+        if (qi >= nq) continue;
+        unsigned long long th = s_thr[ml];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int nl = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            uint32_t row = n0 + nl;
+            if (row >= r1) continue;
+            float s = acc[i][j];
+            uint32_t ok;
+            if (METRIC == LEANN_METRIC_DOT_DESC) ok = ~order_f32(s);
+            else if (METRIC == LEANN_METRIC_L2SQ) ok = order_f32(s);
+            else {
+                float dd = 1.0f - s;
+                if (METRIC == LEANN_METRIC_IP_CLAMP) dd = dd < 0.f ? 0.f : dd;
+                ok = order_f32(dd);
+            }
+            unsigned long long key = ((unsigned long long)ok << 32) | row;
+            if (key > th) continue;
+            if (mask && !((mask[row >> 6] >> (row & 63u)) & 1ull)) continue;
+            uint32_t pos = atomicAdd(&cand_cnt[qi], 1u);
+            if (pos < cap) cand[(size_t)qi * cap + pos] = key;
+            else *overflow = 1u;
+        }
+    }
+}
+
+// In-place bitonic sort of n (power of two) 64-bit keys in shared memory, ascending.
+__device__ void block_bitonic_sort(unsigned long long* keys, uint32_t n) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Merge (running best) + (candidates) -> new best, dedupe, new threshold. One block per query.
+__global__ void __launch_bounds__(256)
+select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand_cnt, uint32_t cap,
+              unsigned long long* __restrict__ best, uint32_t* __restrict__ best_cnt, uint32_t k, uint32_t kpad,
+              unsigned long long* __restrict__ thr, uint32_t nq) {
+    extern __shared__ unsigned long long skeys[];
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    uint32_t nc = cand_cnt[q];
+    if (nc > cap) nc = cap;
+    uint32_t nb = best_cnt[q];
+    if (nc == 0) return;  // nothing new: best/thr unchanged
+    uint32_t total = nc + nb;
+    uint32_t n2 = 1;
+    while (n2 < total) n2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long v = ~0ull;
+        if (i < nb) v = best[(size_t)q * kpad + i];
+        else if (i < total) v = cand[(size_t)q * cap + (i - nb)];
+        skeys[i] = v;
+    }
+    block_bitonic_sort(skeys, n2);
+    // dedupe adjacent equal keys (a chunk re-run after overflow re-appends rows already kept);
+    // single thread compaction of at most k survivors.
+    __shared__ uint32_t s_out;
+    if (threadIdx.x == 0) {
+        uint32_t o = 0;
+        unsigned long long prev = ~0ull;
+        for (uint32_t i = 0; i < total && o < k; ++i) {
+            unsigned long long v = skeys[i];
+            if (v == ~0ull) break;
+            if (i > 0 && v == prev) continue;
+            best[(size_t)q * kpad + o++] = v;
+            prev = v;
+        }
+        s_out = o;
+        best_cnt[q] = o;
+        thr[q] = (o == k) ? best[(size_t)q * kpad + k - 1] : ~0ull;
+        cand_cnt[q] = 0;
+    }
+}
+
+__global__ void scan_init_kernel(uint32_t* cand_cnt, uint32_t* best_cnt, unsigned long long* thr, uint32_t nq, uint32_t* overflow) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { cand_cnt[i] = 0; best_cnt[i] = 0; thr[i] = ~0ull; }
+    if (i == 0) *overflow = 0;
+}
+
+__global__ void scan_finish_kernel(const unsigned long long* __restrict__ best, const uint32_t* __restrict__ best_cnt,
+                                   uint32_t k, uint32_t kpad, uint32_t nq, int metric, uint64_t* __restrict__ keys,
+                                   float* __restrict__ dists, uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * k) return;
+    uint32_t q = i / k, j = i % k;
+    uint32_t c = best_cnt[q];
+    if (j == 0 && counts) counts[q] = c;
+    if (j < c) {
+        unsigned long long v = best[(size_t)q * kpad + j];
+        uint32_t ok = (uint32_t)(v >> 32);
+        keys[i] = (uint64_t)(v & 0xFFFFFFFFull);
+        dists[i] = metric == LEANN_METRIC_DOT_DESC ? unorder_f32(~ok) : unorder_f32(ok);
+    } else {
+        keys[i] = ~0ull;
+        dists[i] = metric == LEANN_METRIC_DOT_DESC ? -CUDART_INF_F : CUDART_INF_F;
+    }
+}
+
+__global__ void pad_rows_kernel(const float* __restrict__ src, float4* __restrict__ dst, size_t n, uint32_t d, uint32_t d4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d4) return;
+    size_t r = i / d4;
+    uint32_t c = (uint32_t)(i % d4) * 4;
+    const float* p = src + r * d;
+    float4 v;
+    v.x = c + 0 < d ? p[c + 0] : 0.f;
+    v.y = c + 1 < d ? p[c + 1] : 0.f;
+    v.z = c + 2 < d ? p[c + 2] : 0.f;
+    v.w = c + 3 < d ? p[c + 3] : 0.f;
+    dst[i] = v;
+}
+
+// K4: merge n_shards x k sorted lists per query. One block (128 threads) per query.
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const uint64_t* __restrict__ keys_in, const float* __restrict__ dists_in, uint32_t n_shards,
+                  uint32_t nq, uint32_t k, int descending, uint64_t* __restrict__ keys_out,
+                  float* __restrict__ dists_out, uint32_t* __restrict__ counts_out) {
+    extern __shared__ unsigned long long skeys[];  // n2 packed (rank, position) + position -> source index
+    const uint32_t q = blockIdx.x;
+    const uint32_t total = n_shards * k;
+    uint32_t n2 = 1;
+    while (n2 < total) n2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long v = ~0ull;
+        if (i < total) {
+            uint32_t s = i / k, j = i % k;
+            size_t src = ((size_t)s * nq + q) * k + j;
+            if (keys_in[src] != ~0ull) {
+                uint32_t ok = order_f32(dists_in[src]);
+                if (descending) ok = ~ok;
+                v = ((unsigned long long)ok << 32) | i;  // ties: lower shard, then lower rank first
+            }
+        }
+        skeys[i] = v;
+    }
+    block_bitonic_sort(skeys, n2);
+    uint32_t cnt = 0;
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        unsigned long long v = j < n2 ? skeys[j] : ~0ull;
+        size_t dst = (size_t)q * k + j;
+        if (v != ~0ull) {
+            uint32_t i = (uint32_t)(v & 0xFFFFFFFFull);
+            uint32_t s = i / k, jj = i % k;
+            size_t src = ((size_t)s * nq + q) * k + jj;
+            keys_out[dst] = keys_in[src];
+            dists_out[dst] = dists_in[src];
+        } else {
+            keys_out[dst] = ~0ull;
+            dists_out[dst] = descending ? -CUDART_INF_F : CUDART_INF_F;
+        }
+    }
+    if (counts_out) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (uint32_t j = 0; j < k && j < n2; ++j) if (skeys[j] != ~0ull) cnt++;
+            counts_out[q] = cnt;
+        }
+    }
+}
+
+constexpr uint32_t SCAN_CAP = 4096;
+
+}  // namespace
+
+void launch_pad_rows(const float* src, float4* dst, size_t n, uint32_t d, uint32_t d4, cudaStream_t stream) {
+    size_t total = n * d4;
+    if (!total) return;
+    pad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, n, d, d4);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
+    uint32_t kpad = (k + 31) & ~31u;
+    size_t d4max = d4;
+    return align256((size_t)nq * SCAN_CAP * 8) + align256((size_t)nq * 4) + align256((size_t)nq * kpad * 8) +
+           align256((size_t)nq * 4) + align256((size_t)nq * 8) + 256 + align256((size_t)nq * d4max * 16);
+}
+
+void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
+                       uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
+                       cudaStream_t stream) {
+    if (k == 0 || k > 1024) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: k must be in 1..1024");
+    if (nq == 0) return;
+    const uint32_t kpad = (k + 31) & ~31u;
+    unsigned char* p = (unsigned char*)scratch;
+    ScanScratch s;
+    s.cand = (unsigned long long*)p; p += align256((size_t)nq * SCAN_CAP * 8);
+    s.cand_cnt = (uint32_t*)p; p += align256((size_t)nq * 4);
+    s.best = (unsigned long long*)p; p += align256((size_t)nq * kpad * 8);
+    s.best_cnt = (uint32_t*)p; p += align256((size_t)nq * 4);
+    s.thr = (unsigned long long*)p; p += align256((size_t)nq * 8);
+    s.overflow = (uint32_t*)p; p += 256;
+    s.qpad = (float4*)p; p += align256((size_t)nq * f.d4 * 16);
+    if ((size_t)(p - (unsigned char*)scratch) > scratch_bytes) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: scratch too small");
+
+    scan_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.cand_cnt, s.best_cnt, s.thr, nq, s.overflow);
+    launch_pad_rows(d_queries, s.qpad, nq, f.d, f.d4, stream);
+
+    const uint32_t growth = std::max<uint32_t>(2u, SCAN_CAP / (8u * k));
+    uint32_t r0 = 0;
+    uint32_t done_rows = 0;
+    uint32_t* h_over = nullptr;
+    LEANN_CUDA_CHECK(cudaMallocHost(&h_over, sizeof(uint32_t)));
+    try {
+        while (r0 < f.n) {
+            uint64_t want = done_rows == 0 ? SCAN_CAP : (uint64_t)done_rows * growth;
+            uint32_t r1 = (uint32_t)std::min<uint64_t>(f.n, (uint64_t)r0 + want);
+            for (int attempt = 0;; ++attempt) {
+                dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);
+                switch (f.metric) {
+                    case LEANN_METRIC_L2SQ:
+                        scan_tile_kernel<LEANN_METRIC_L2SQ><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                        break;
+                    case LEANN_METRIC_IP_CLAMP:
+                        scan_tile_kernel<LEANN_METRIC_IP_CLAMP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                        break;
+                    case LEANN_METRIC_DOT_DESC:
+                        scan_tile_kernel<LEANN_METRIC_DOT_DESC><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                        break;
+                    default:
+                        scan_tile_kernel<LEANN_METRIC_IP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                }
+                LEANN_CUDA_CHECK(cudaGetLastError());
+                size_t smem = (size_t)2 * SCAN_CAP * 8;  // best (<=1024) + cand (<=4096) rounded to 8192 keys
+                static bool attr_set = false;
+                if (!attr_set) {
+                    LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_set = true;
+                }
+                select_kernel<<<nq, 256, smem, stream>>>(s.cand, s.cand_cnt, SCAN_CAP, s.best, s.best_cnt, k, kpad, s.thr, nq);
+                LEANN_CUDA_CHECK(cudaGetLastError());
+                LEANN_CUDA_CHECK(cudaMemcpyAsync(h_over, s.overflow, 4, cudaMemcpyDeviceToHost, stream));
+                LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
+                if (*h_over == 0) break;
+                // A candidate list overflowed: the threshold is tighter now; re-run the same chunk
+                // (duplicates of rows already kept are removed by the select kernel).
+                LEANN_CUDA_CHECK(cudaMemsetAsync(s.overflow, 0, 4, stream));
+                if (attempt > 64) throw Error(LEANN_ERR_CUDA, "exact scan: candidate overflow did not converge");
+            }
+            done_rows = r1;
+            r0 = r1;
+        }
+    } catch (...) {
+        cudaFreeHost(h_over);
+        throw;
+    }
+    cudaFreeHost(h_over);
+    uint32_t tot = nq * k;
+    scan_finish_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(s.best, s.best_cnt, k, kpad, nq, f.metric, d_keys, d_dists, d_counts);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_topk_merge(const uint64_t* keys_in, const float* dists_in, uint32_t n_shards, uint32_t nq, uint32_t k,
+                       int descending, uint64_t* keys_out, float* dists_out, uint32_t* counts_out, cudaStream_t stream) {
+    if (nq == 0 || k == 0) return;
+    uint32_t total = n_shards * k, n2 = 1;
+    while (n2 < total) n2 <<= 1;
+    size_t smem = (size_t)n2 * 8;
+    if (smem > 200 * 1024) throw Error(LEANN_ERR_INVALID_ARG, "topk merge: n_shards*k too large");
+    if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_kernel<<<nq, 128, smem, stream>>>(keys_in, dists_in, n_shards, nq, k, descending, keys_out, dists_out, counts_out);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace leann

@@ -1,0 +1,287 @@
+// graph_device.cuh — warp-cooperative building blocks of the graph traversal kernels (K1/K1f and
+// the HNSW builder). One warp owns one query: the query lives in registers, `top` (the bounded
+// result list, usearch sorted_buffer_gt) and `next` (the candidate queue) live in shared memory,
+// the visited set is an epoch-tagged byte map in HBM (exact, no clearing between queries).
+//
+// Semantics restated from usearch search_for_one_ / search_to_find_in_base_ / search_to_insert_
+// (call site leann-rs src/backend/hnsw.rs:85) and diskann-rs search_with_dists (diskann.rs:56);
+// see oracle/graph_oracle.cpp for the CPU restatement the tests compare against.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "internal.h"
+
+namespace leann {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// Per-warp shared-memory state.
+struct WarpLists {
+    float* top_d; uint32_t* top_s;    // ascending, size <= ef
+    float* next_d; uint32_t* next_s;  // ascending ring buffer, physical index (head+i)&(capp-1)
+    uint32_t* st_slot; float* st_dist;  // staging for one adjacency row (MAX_DEG)
+    int top_size, next_size, next_head;
+};
+
+// Lane-partial of one distance: float4 index i*LPV+lig, four fma accumulators, (x+y)+(z+w).
+template <int VPL>
+__device__ __forceinline__ float lane_partial(const float4 (&q)[VPL], const float4 (&x)[VPL], int metric) {
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    if (metric == LEANN_METRIC_L2SQ) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            float tx = __fsub_rn(q[i].x, x[i].x), ty = __fsub_rn(q[i].y, x[i].y);
+            float tz = __fsub_rn(q[i].z, x[i].z), tw = __fsub_rn(q[i].w, x[i].w);
+            ax = __fmaf_rn(tx, tx, ax); ay = __fmaf_rn(ty, ty, ay);
+            az = __fmaf_rn(tz, tz, az); aw = __fmaf_rn(tw, tw, aw);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            ax = __fmaf_rn(q[i].x, x[i].x, ax); ay = __fmaf_rn(q[i].y, x[i].y, ay);
+            az = __fmaf_rn(q[i].z, x[i].z, az); aw = __fmaf_rn(q[i].w, x[i].w, aw);
+        }
+    }
+    return __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw));
+}
+
+template <int LPV>
+__device__ __forceinline__ float group_reduce(float v) {
+#pragma unroll
+    for (int off = LPV / 2; off >= 1; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+
+__device__ __forceinline__ float finish_distance(float s, int metric) {
+    if (metric == LEANN_METRIC_L2SQ) return s;
+    float r = __fsub_rn(1.0f, s);
+    if (metric == LEANN_METRIC_IP_CLAMP) r = r < 0.0f ? 0.0f : r;
+    return r;
+}
+
+// Distances from the register-resident query to st_slot[0..cnt) -> st_dist[0..cnt).
+// 32/LPV vectors are evaluated side by side, U deep: U*VPL independent 16-byte loads per lane are
+// in flight before the first FMA.
+template <int LPV, int VPL, int U>
+__device__ __forceinline__ void eval_distances(const float4* __restrict__ vecs, uint32_t d4, int metric,
+                                               const float4 (&q)[VPL], const uint32_t* st_slot,
+                                               float* st_dist, int cnt, int lane) {
+    constexpr int GROUPS = 32 / LPV;
+    constexpr int BATCH = U * GROUPS;
+    const int gid = lane / LPV, lig = lane % LPV;
+    for (int b = 0; b < cnt; b += BATCH) {
+        float4 x[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int j = b + u * GROUPS + gid;
+            bool ok = j < cnt;
+            uint32_t s = ok ? st_slot[j] : 0u;
+            const float4* row = vecs + (size_t)s * d4;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                uint32_t idx = (uint32_t)(i * LPV + lig);
+                if (ok && idx < d4) x[u][i] = ldg_stream(row + idx);
+                else x[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float v = group_reduce<LPV>(lane_partial<VPL>(q, x[u], metric));
+            int j = b + u * GROUPS + gid;
+            if (j < cnt && lig == 0) st_dist[j] = finish_distance(v, metric);
+        }
+    }
+    __syncwarp();
+}
+
+template <int LPV, int VPL>
+__device__ __forceinline__ void load_query(const float* __restrict__ qrow, uint32_t d, float4 (&q)[VPL], int lane) {
+    const int lig = lane % LPV;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        uint32_t j = (uint32_t)(i * LPV + lig) * 4u;
+        q[i].x = j + 0 < d ? qrow[j + 0] : 0.f;
+        q[i].y = j + 1 < d ? qrow[j + 1] : 0.f;
+        q[i].z = j + 2 < d ? qrow[j + 2] : 0.f;
+        q[i].w = j + 3 < d ? qrow[j + 3] : 0.f;
+    }
+}
+
+// Sorted insert into an ascending (optionally ring-indexed) array.
+//  UPPER == false: position = #elements <  dd  (usearch sorted_buffer_gt: newcomer before equals)
+//  UPPER == true : position = #elements <= dd  (FIFO among equals; candidate queue)
+// When the array already holds `limit` entries the last one is dropped; pos == limit rejects.
+template <bool UPPER, bool RING>
+__device__ __forceinline__ bool sorted_insert(float* D, uint32_t* S, int& size, int limit, int head, int mask,
+                                              float dd, uint32_t ss, int lane) {
+    auto phys = [&](int i) { return RING ? ((head + i) & mask) : i; };
+    int pos = 0;
+    for (int base = 0; base < size; base += 32) {
+        int i = base + lane;
+        bool lt = false;
+        if (i < size) {
+            float v = D[phys(i)];
+            lt = UPPER ? (v <= dd) : (v < dd);
+        }
+        unsigned b = __ballot_sync(FULL, lt);
+        pos += __popc(b);
+        if (b != FULL) break;
+    }
+    if (pos == limit) return false;
+    int new_size = size + 1 < limit ? size + 1 : limit;
+    int last = new_size - 1;
+    for (int base = (last >> 5) << 5; base >= 0 && base + 31 > pos; base -= 32) {
+        int i = base + lane;
+        bool mv = (i > pos) && (i <= last);
+        float td = 0.f; uint32_t ts = 0u;
+        if (mv) { td = D[phys(i - 1)]; ts = S[phys(i - 1)]; }
+        __syncwarp();
+        if (mv) { D[phys(i)] = td; S[phys(i)] = ts; }
+        __syncwarp();
+    }
+    if (lane == 0) { D[phys(pos)] = dd; S[phys(pos)] = ss; }
+    __syncwarp();
+    size = new_size;
+    return true;
+}
+
+// Adjacency addressing of one level.
+struct LevelAdj {
+    const uint32_t* adj0; const uint32_t* adjU; const uint32_t* upper_base;
+    uint32_t deg; int level;
+    __device__ __forceinline__ const uint32_t* row(uint32_t s) const {
+        return level == 0 ? adj0 + (size_t)s * deg : adjU + ((size_t)upper_base[s] + (uint32_t)(level - 1)) * deg;
+    }
+};
+
+struct Counters { uint32_t n_dist, n_hops0, n_hops_upper, dropped; };
+
+// Greedy descent over (from_level .. to_level] — usearch search_for_one_. Every neighbour of the
+// current closest node is measured each pass (no visited set); strict `<` keeps the first minimum.
+template <int LPV, int VPL, int U>
+__device__ __forceinline__ void greedy_descend(const GraphView& g, const float4 (&q)[VPL], WarpLists& w,
+                                               uint32_t& cur, float& cur_d, int from_level, int to_level,
+                                               Counters& c, int lane) {
+    for (int level = from_level; level > to_level; --level) {
+        bool changed;
+        do {
+            changed = false;
+            const uint32_t* row = g.adjU + ((size_t)g.upper_base[cur] + (uint32_t)(level - 1)) * g.degU;
+            int cnt = 0;
+            for (uint32_t base = 0; base < g.degU; base += 32) {
+                uint32_t j = base + lane;
+                uint32_t s = j < g.degU ? __ldg(row + j) : SENT;
+                bool ok = s != SENT;
+                unsigned b = __ballot_sync(FULL, ok);
+                if (ok) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = s;
+                cnt += __popc(b);
+            }
+            __syncwarp();
+            c.n_hops_upper++;
+            c.n_dist += cnt;
+            eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+            float bd = CUDART_INF_F; int bj = 0x7fffffff;
+            for (int j = lane; j < cnt; j += 32) {
+                float dj = w.st_dist[j];
+                if (dj < bd) { bd = dj; bj = j; }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                float od = __shfl_xor_sync(FULL, bd, off);
+                int oj = __shfl_xor_sync(FULL, bj, off);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+            }
+            if (bd < cur_d) { cur_d = bd; cur = w.st_slot[bj]; changed = true; }
+            __syncwarp();
+        } while (changed);
+    }
+}
+
+// Beam search on one level (usearch search_to_find_in_base_ / search_to_insert_, diskann-rs
+// search_with_dists). radius = worst distance in `top` once it holds `ef` entries, +inf before.
+//   nonstrict == 0 : stop when cand.d >  radius   (usearch)
+//   nonstrict == 1 : stop when cand.d >= radius   (diskann-rs; only reachable when top is full)
+// mask: nullable; nodes failing it are traversed but never enter `top` (usearch predicate shape).
+template <int LPV, int VPL, int U>
+__device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL],
+                                           WarpLists& w, int ef, int next_cap, int next_mask, int nonstrict,
+                                           const uint64_t* __restrict__ mask, uint8_t* vis, uint8_t tag,
+                                           uint32_t start, float start_d, Counters& c, int lane) {
+    auto passes = [&](uint32_t s) { return mask == nullptr || ((mask[s >> 6] >> (s & 63u)) & 1ull); };
+    w.top_size = 0; w.next_size = 0; w.next_head = 0;
+    float radius = CUDART_INF_F;
+    sorted_insert<true, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, start_d, start, lane);
+    if (lane == 0) vis[start] = tag;
+    if (passes(start)) sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, start_d, start, lane);
+    if (w.top_size == ef) radius = w.top_d[ef - 1];
+    __syncwarp();
+    while (w.next_size > 0) {
+        float cd = w.next_d[w.next_head & next_mask];
+        uint32_t cs = w.next_s[w.next_head & next_mask];
+        if (nonstrict ? (cd >= radius) : (cd > radius)) break;
+        w.next_head = (w.next_head + 1) & next_mask;
+        w.next_size--;
+        if (adj.level == 0) c.n_hops0++; else c.n_hops_upper++;
+        // ---- adjacency row -> unvisited neighbours, list order preserved ----
+        const uint32_t* row = adj.row(cs);
+        int cnt = 0;
+        for (uint32_t base = 0; base < adj.deg; base += 32) {
+            uint32_t j = base + lane;
+            uint32_t s = j < adj.deg ? __ldg(row + j) : SENT;
+            bool fresh = false;
+            if (s != SENT) {
+                if (vis[s] != tag) { vis[s] = tag; fresh = true; }
+            }
+            unsigned b = __ballot_sync(FULL, fresh);
+            if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = s;
+            cnt += __popc(b);
+        }
+        __syncwarp();
+        c.n_dist += cnt;
+        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+        // ---- replay the inserts in list order ----
+        for (int base = 0; base < cnt; base += 32) {
+            int j = base + lane;
+            float dj = j < cnt ? w.st_dist[j] : CUDART_INF_F;
+            bool maybe = j < cnt && (w.top_size < ef || dj < radius);
+            unsigned m = __ballot_sync(FULL, maybe);
+            while (m) {
+                int l = __ffs(m) - 1;
+                m &= m - 1;
+                float dd = __shfl_sync(FULL, dj, l);
+                if (w.top_size < ef || dd < radius) {
+                    uint32_t ss = w.st_slot[base + l];
+                    if (w.next_size == next_cap) c.dropped = 1;
+                    sorted_insert<true, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, dd, ss, lane);
+                    if (passes(ss)) sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, dd, ss, lane);
+                    radius = w.top_size == ef ? w.top_d[ef - 1] : CUDART_INF_F;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Epoch handling of the visited byte map: tag in [1,255]; the map is wiped when the tag wraps.
+__device__ __forceinline__ uint8_t next_epoch(uint32_t* epoch_slot, uint8_t* vis, size_t n_pad, int lane) {
+    uint32_t e = *epoch_slot;
+    __syncwarp();
+    if (e != 0 && e % 255u == 0) {
+        uint4* v4 = reinterpret_cast<uint4*>(vis);
+        for (size_t i = lane; i < n_pad / 16; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (lane == 0) *epoch_slot = e + 1;
+    return (uint8_t)(e % 255u + 1u);
+}
+
+}  // namespace leann

@@ -1,0 +1,141 @@
+// graph_search.cu — K1 / K1f: warp-per-query graph beam search (HNSW upper-level greedy descent +
+// level-0 beam; Vamana single-level beam), replacing usearch::Index::search behind
+// HnswSearcher::search (leann-rs src/backend/hnsw.rs:79-88) and DiskANN::search_with_dists behind
+// DiskAnnSearcher::search (src/backend/diskann.rs:47-62).
+//
+// Persistent grid: a fixed pool of warps pulls queries from an atomic counter, so long and short
+// traversals balance and the visited workspace is sized by the grid, not the batch.
+// Bound: HBM gather bandwidth. Algorithmic bytes per query =
+//     n_dist * d4*16  +  n_hops0 * deg0*4  +  n_hops_upper * degU*4      
+// all three counted by the kernel itself (out_stats) and by the oracle.
+#include "graph_device.cuh"
+
+namespace leann {
+
+template <int LPV, int VPL, int U>
+__global__ void __launch_bounds__(128)
+graph_search_kernel(const GraphView g, const SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    if (warp_global >= p.n_warps) return;
+
+    const uint32_t ef_pad = (p.ef + 31u) & ~31u;
+    const size_t per_warp = (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 8;
+    unsigned char* base = smem_raw + per_warp * warp_in_block;
+    WarpLists w;
+    w.top_d = reinterpret_cast<float*>(base);
+    w.top_s = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 4);
+    w.next_d = reinterpret_cast<float*>(base + (size_t)ef_pad * 8);
+    w.next_s = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 4);
+    w.st_slot = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8);
+    w.st_dist = reinterpret_cast<float*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 4);
+
+    uint8_t* vis = p.visited + (size_t)warp_global * p.n_pad;
+    uint32_t* epoch_slot = p.epochs + warp_global;
+
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(p.counter, 1u);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= p.nq) break;
+
+        float4 q[VPL];
+        load_query<LPV, VPL>(p.queries + (size_t)qi * g.d, g.d, q, lane);
+        const uint8_t tag = next_epoch(epoch_slot, vis, p.n_pad, lane);
+        Counters c{0u, 0u, 0u, 0u};
+
+        // entry point distance
+        uint32_t cur = g.entry;
+        if (lane == 0) w.st_slot[0] = cur;
+        __syncwarp();
+        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, 1, lane);
+        float cur_d = w.st_dist[0];
+        c.n_dist = 1;
+        __syncwarp();
+        if (g.max_level > 0) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, 0, c, lane);
+
+        LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
+        beam_level<LPV, VPL, U>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
+                                p.mask, vis, tag, cur, cur_d, c, lane);
+
+        // results: ascending, truncated to k; tail = UINT64_MAX / +inf
+        const int cnt = w.top_size < (int)p.k ? w.top_size : (int)p.k;
+        for (uint32_t i = lane; i < p.k; i += 32) {
+            uint64_t key = ~0ull;
+            float dd = CUDART_INF_F;
+            if ((int)i < cnt) {
+                uint32_t s = w.top_s[i];
+                key = g.keys ? g.keys[s] : (uint64_t)s;
+                dd = w.top_d[i];
+            }
+            p.out_keys[(size_t)qi * p.k + i] = key;
+            p.out_dists[(size_t)qi * p.k + i] = dd;
+        }
+        if (lane == 0) {
+            if (p.out_counts) p.out_counts[qi] = (uint32_t)cnt;
+            if (p.out_stats) {
+                p.out_stats[(size_t)qi * 4 + 0] = c.n_dist;
+                p.out_stats[(size_t)qi * 4 + 1] = c.n_hops0;
+                p.out_stats[(size_t)qi * 4 + 2] = c.n_hops_upper;
+                p.out_stats[(size_t)qi * 4 + 3] = c.dropped;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Lanes cooperating on one distance: 8 for d <= 256 (four vectors side by side), else 32.
+int reduction_lanes(size_t dims) { return dims <= 256 ? 8 : 32; }
+
+size_t graph_search_smem_per_warp(uint32_t ef, uint32_t next_capp) {
+    uint32_t ef_pad = (ef + 31u) & ~31u;
+    return (size_t)ef_pad * 8 + (size_t)next_capp * 8 + (size_t)MAX_DEG * 8;
+}
+
+int graph_search_max_warps(int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return sms * 12;  // 3 CTAs x 4 warps per SM (register-bound, see -Xptxas -v)
+}
+
+namespace {
+template <int LPV, int VPL, int U>
+void launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream) {
+    const int warps_per_block = 4;
+    size_t smem = graph_search_smem_per_warp(p.ef, p.next_capp) * warps_per_block;
+    auto kern = graph_search_kernel<LPV, VPL, U>;
+    if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (p.n_warps + warps_per_block - 1) / warps_per_block;
+    LEANN_CUDA_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), stream));
+    kern<<<blocks, warps_per_block * 32, smem, stream>>>(g, p);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+void launch_graph_search(const GraphView& g, const SearchParams& p, cudaStream_t stream) {
+    if (g.deg0 > (uint32_t)MAX_DEG || g.degU > (uint32_t)MAX_DEG)
+        throw Error(LEANN_ERR_INVALID_ARG, "graph degree exceeds MAX_DEG (128)");
+    if (p.ef > (uint32_t)MAX_EF) throw Error(LEANN_ERR_INVALID_ARG, "ef exceeds 1024");
+    const uint32_t d4 = g.d4;
+    if (reduction_lanes(g.d) == 8) {
+        uint32_t vpl = (d4 + 7) / 8;
+        if (vpl <= 2) launch_t<8, 2, 8>(g, p, stream);
+        else if (vpl <= 3) launch_t<8, 3, 8>(g, p, stream);
+        else if (vpl <= 4) launch_t<8, 4, 4>(g, p, stream);
+        else launch_t<8, 8, 2>(g, p, stream);
+    } else {
+        uint32_t vpl = (d4 + 31) / 32;
+        if (vpl <= 3) launch_t<32, 3, 8>(g, p, stream);
+        else if (vpl <= 4) launch_t<32, 4, 4>(g, p, stream);
+        else if (vpl <= 6) launch_t<32, 6, 4>(g, p, stream);
+        else if (vpl <= 8) launch_t<32, 8, 2>(g, p, stream);
+        else if (vpl <= 12) launch_t<32, 12, 2>(g, p, stream);
+        else if (vpl <= 16) launch_t<32, 16, 1>(g, p, stream);
+        else if (vpl <= 32) launch_t<32, 32, 1>(g, p, stream);
+        else throw Error(LEANN_ERR_INVALID_ARG, "dimension above 4096 is not supported");
+    }
+}
+
+}  // namespace leann

@@ -1,0 +1,152 @@
+// internal.h — shared host-side declarations of libleann_cuda (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/leann_cuda.h"
+
+namespace leann {
+
+constexpr uint32_t SENT = 0xFFFFFFFFu;  // padding slot in every adjacency row
+constexpr int MAX_DEG = 128;            // largest adjacency row the kernels stage in shared memory
+constexpr int MAX_EF = 1024;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define LEANN_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::leann::Error(LEANN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- host-side images of the reference's files (formats.cpp) --------------------------------
+struct HostHnsw {  // usearch `.index` (hnsw.rs:55,134), SURVEY.md Appendix A.1
+    size_t n = 0, d = 0, M = 0, M0 = 0;
+    int64_t max_level = 0;
+    uint64_t entry = 0;
+    int metric = LEANN_METRIC_IP;
+    std::vector<float> vecs;       // n*d
+    std::vector<int16_t> levels;   // n
+    std::vector<uint64_t> keys;    // n
+    std::vector<uint32_t> adj0;    // n*M0, SENT padded, list order preserved
+    std::vector<uint32_t> upper_base;  // n: first upper list of the node (valid when level > 0)
+    std::vector<uint32_t> adjU;    // n_upper_lists*M, SENT padded
+};
+struct HostVamana {  // diskann-rs `.diskann` (diskann.rs:34-37,94-99), Appendix A.3
+    size_t n = 0, d = 0, R = 0;
+    uint32_t medoid = 0;
+    std::string distance_name;
+    std::vector<float> vecs;
+    std::vector<uint32_t> adj;  // n*R, SENT padded
+};
+
+bool is_faiss_index(const std::string& index_file);                       // backend/compat.rs:15-38
+void read_usearch_index(const std::string& path, size_t dims, HostHnsw& out);   // throws Error
+void write_usearch_index(const std::string& path, const HostHnsw& g);
+void read_diskann(const std::string& path, size_t dims, HostVamana& out);
+void write_diskann(const std::string& path, const HostVamana& g);
+void read_embeddings(const std::string& path, size_t dims, std::vector<float>& out, size_t& n);  // index/embeddings.rs:21-36
+void write_embeddings(const std::string& path, const float* v, size_t n, size_t dims);
+std::string with_extension(const std::string& base, const std::string& ext);  // Path::with_extension
+
+// ---- device-resident index --------------------------------------------------------------------
+struct GraphView {  // passed by value to kernels
+    const float4* vecs;          // [n][d4] rows padded with zeros to a multiple of 4 floats
+    const uint32_t* adj0;        // [n][deg0]
+    const uint32_t* upper_base;  // [n]
+    const uint32_t* adjU;        // [n_upper_lists][degU]
+    const uint64_t* keys;        // [n] or nullptr (key == slot)
+    uint32_t n, d, d4, deg0, degU;
+    int max_level;
+    uint32_t entry;
+    int metric;
+};
+
+struct SearchWorkspace {
+    uint8_t* visited = nullptr;  // [n_warps][n_pad] epoch tags
+    uint32_t* epochs = nullptr;  // [n_warps]
+    uint32_t* counter = nullptr; // dynamic query scheduler
+    int n_warps = 0;
+    size_t n_pad = 0;
+    cudaStream_t stream = nullptr;  // private stream for host-pointer calls
+    float* d_queries = nullptr; uint64_t* d_keys = nullptr; float* d_dists = nullptr; uint32_t* d_counts = nullptr;
+    uint64_t* d_mask = nullptr;
+    size_t cap_q = 0, cap_out = 0, cap_mask = 0, cap_counts = 0;
+};
+
+struct SearchParams {
+    const float* queries;  // [nq][d]
+    uint32_t nq, k, ef, next_cap, next_capp;
+    const uint64_t* mask;  // nullable
+    int nonstrict_term;    // 0: usearch (cand.d > radius), 1: diskann-rs (full && cand.d >= worst)
+    uint64_t* out_keys; float* out_dists; uint32_t* out_counts; uint64_t* out_stats;
+    uint8_t* visited; uint32_t* epochs; uint32_t* counter;
+    size_t n_pad;
+    int n_warps;
+};
+
+int reduction_lanes(size_t dims);
+// Enqueues the K1/K1f beam search on `stream`. Throws Error.
+void launch_graph_search(const GraphView& g, const SearchParams& p, cudaStream_t stream);
+size_t graph_search_smem_per_warp(uint32_t ef, uint32_t next_capp);
+int graph_search_max_warps(int device);
+
+// Exact scan (K2 + K2r)
+struct FlatView { const float4* vecs; uint32_t n, d, d4; int metric; };
+void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
+                       uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
+                       cudaStream_t stream);
+size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k);
+
+void launch_topk_merge(const uint64_t* keys_in, const float* dists_in, uint32_t n_shards, uint32_t nq, uint32_t k,
+                       int descending, uint64_t* keys_out, float* dists_out, uint32_t* counts_out, cudaStream_t stream);
+
+void launch_pad_rows(const float* src, float4* dst, size_t n, uint32_t d, uint32_t d4, cudaStream_t stream);
+
+}  // namespace leann
+
+struct leann_cuda_index {
+    int backend = LEANN_BACKEND_HNSW;
+    int device = 0;
+    int metric = LEANN_METRIC_IP;
+    size_t n = 0, d = 0;
+    uint32_t d4 = 0;
+    // device memory
+    float4* vecs = nullptr;
+    uint32_t* adj0 = nullptr;
+    uint32_t* upper_base = nullptr;
+    uint32_t* adjU = nullptr;
+    uint64_t* keys = nullptr;
+    std::vector<int16_t> h_levels;  // host copy kept for save()
+    std::string distance_name;      // diskann metadata string
+    size_t n_upper_lists = 0;
+    uint32_t M = 0, M0 = 0;
+    int max_level = 0;
+    uint32_t entry = 0;
+    bool identity_keys = true;
+    // workspaces (guarded by mu: concurrent callers serialise on the GPU queue)
+    mutable std::mutex mu;
+    mutable leann::SearchWorkspace ws;
+    mutable void* scan_scratch = nullptr;
+    mutable size_t scan_scratch_bytes = 0;
+    leann::GraphView view() const {
+        leann::GraphView g;
+        g.vecs = vecs; g.adj0 = adj0; g.upper_base = upper_base; g.adjU = adjU;
+        g.keys = identity_keys ? nullptr : keys;
+        g.n = (uint32_t)n; g.d = (uint32_t)d; g.d4 = d4; g.deg0 = M0; g.degU = M;
+        g.max_level = max_level; g.entry = entry; g.metric = metric;
+        return g;
+    }
+};

@@ -1,0 +1,859 @@
+// =============================================================================
+// oracle/graph_oracle.cpp — TEST INFRASTRUCTURE ONLY. NOT PART OF THE PRODUCT.
+//
+// CPU restatement of the search arithmetic that decisiongraph/leann-rs executes
+// on its vector path. Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.
+//
+// PARITY STATUS: **parity unpinned** for HNSW search, Vamana search and both
+// file formats. The reference delegates these to third-party crates whose
+// sources are NOT under /root/reference and cannot be built offline:
+//     usearch   2.23.0  (Cargo.lock:4381-4388)   call sites src/backend/hnsw.rs:53,55,85,122-134
+//     diskann-rs 0.3.4  (Cargo.lock:987-1002)    call sites src/backend/diskann.rs:34-38,56,94-100
+//     anndists   0.1.3  (Cargo.lock:59-73)       DistDot at src/backend/diskann.rs:8,16,36,96
+// and the reference holds no golden vector / known-answer test for them
+// (SURVEY.md §4, §8c). What follows restates the published algorithms of those
+// crates (usearch index_gt::search / search_for_one_ / search_to_find_in_base_ /
+// sorted_buffer_gt::insert / refine_ / save_to_stream; diskann-rs
+// search_with_dists and its file header; anndists DistDot::eval) and is anchored
+// on the reference's own call sites and parameters:
+//     hnsw.rs:43-51   IP metric, f32, connectivity 32, expansion_add 64, expansion_search 64
+//     hnsw.rs:79-88   search(query, top_k); `complexity` ignored -> ef = max(64, top_k)
+//     hnsw.rs:128-130 keys are ordinals, added sequentially
+//     diskann.rs:54   beam = max(complexity, top_k);  diskann.rs:91 alpha = 1.2
+// The exact scan IS pinned by in-repo source: src/index/recompute.rs:96-110,137-139.
+//
+// Self-checks that stand in for golden vectors: recall against f64 brute force,
+// strict file-size equations in both readers, bounded-queue == unbounded-queue
+// equality, and two independent reduction orders.
+// =============================================================================
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <queue>
+#include <random>
+#include <string>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+enum Metric { METRIC_IP = 0, METRIC_L2SQ = 1, METRIC_IP_CLAMP = 2 };
+// Reduction order of one distance evaluation.
+//   lanes == 0 : plain sequential f32 fold, mul then add (recompute.rs:137-139; anndists DistDot)
+//   lanes  > 0 : bit-exact model of the CUDA kernel: float4 index i belongs to lane i % lanes,
+//                four fma accumulators per lane (x,y,z,w), lane sum = (x+y)+(z+w), then an xor
+//                butterfly over `lanes` lanes (offsets lanes/2 .. 1).
+struct DistCfg {
+    int metric;
+    int lanes;
+};
+
+inline float dist_seq(const float* q, const float* x, size_t d, int metric) {
+    float s = 0.0f;
+    if (metric == METRIC_L2SQ) {
+        for (size_t i = 0; i < d; ++i) {
+            float t = q[i] - x[i];
+            s += t * t;
+        }
+        return s;
+    }
+    for (size_t i = 0; i < d; ++i) s += q[i] * x[i];
+    float r = 1.0f - s;
+    if (metric == METRIC_IP_CLAMP && r < 0.0f) r = 0.0f;  // anndists DistDot::eval clamps at 0
+    return r;
+}
+
+inline float dist_lanes(const float* q, const float* x, size_t d, int metric, int lanes) {
+    float acc[32][4];
+    for (int l = 0; l < lanes; ++l) acc[l][0] = acc[l][1] = acc[l][2] = acc[l][3] = 0.0f;
+    size_t d4 = (d + 3) / 4;
+    for (size_t i = 0; i < d4; ++i) {
+        int l = (int)(i % (size_t)lanes);
+        for (int c = 0; c < 4; ++c) {
+            size_t j = i * 4 + c;
+            float a = j < d ? q[j] : 0.0f, b = j < d ? x[j] : 0.0f;
+            if (metric == METRIC_L2SQ) {
+                float t = a - b;
+                acc[l][c] = fmaf(t, t, acc[l][c]);
+            } else {
+                acc[l][c] = fmaf(a, b, acc[l][c]);
+            }
+        }
+    }
+    float v[32];
+    for (int l = 0; l < lanes; ++l) v[l] = (acc[l][0] + acc[l][1]) + (acc[l][2] + acc[l][3]);
+    for (int off = lanes / 2; off >= 1; off >>= 1) {
+        float w[32];
+        for (int l = 0; l < lanes; ++l) w[l] = v[l] + v[l ^ off];
+        for (int l = 0; l < lanes; ++l) v[l] = w[l];
+    }
+    float s = v[0];
+    if (metric == METRIC_L2SQ) return s;
+    float r = 1.0f - s;
+    if (metric == METRIC_IP_CLAMP && r < 0.0f) r = 0.0f;
+    return r;
+}
+
+// lanes == -1: SIMD-shaped fold (16 fma accumulators, pairwise tree) — the shape SimSIMD's AVX2/AVX-512
+// f32 dot inside usearch has. Used only for the timed CPU baseline; results differ from the other
+// two orders in the last ulp.
+inline float dist_simd(const float* q, const float* x, size_t d, int metric) {
+    float acc[16];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+    size_t i = 0;
+    if (metric == METRIC_L2SQ) {
+        for (; i + 16 <= d; i += 16)
+            for (int j = 0; j < 16; ++j) { float t = q[i + j] - x[i + j]; acc[j] = fmaf(t, t, acc[j]); }
+        for (; i < d; ++i) { float t = q[i] - x[i]; acc[i & 15] = fmaf(t, t, acc[i & 15]); }
+    } else {
+        for (; i + 16 <= d; i += 16)
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(q[i + j], x[i + j], acc[j]);
+        for (; i < d; ++i) acc[i & 15] = fmaf(q[i], x[i], acc[i & 15]);
+    }
+    for (int w = 8; w >= 1; w >>= 1) for (int j = 0; j < w; ++j) acc[j] += acc[j + w];
+    if (metric == METRIC_L2SQ) return acc[0];
+    float r = 1.0f - acc[0];
+    if (metric == METRIC_IP_CLAMP && r < 0.0f) r = 0.0f;
+    return r;
+}
+
+inline float dist(const float* q, const float* x, size_t d, DistCfg c) {
+    if (c.lanes > 0) return dist_lanes(q, x, d, c.metric, c.lanes);
+    if (c.lanes < 0) return dist_simd(q, x, d, c.metric);
+    return dist_seq(q, x, d, c.metric);
+}
+
+struct Cand {
+    float d;
+    uint32_t s;
+};
+
+// usearch sorted_buffer_gt::insert(element, limit): lower_bound on distance, reject when the
+// position equals the limit, shift right and drop the last when full. A newcomer lands BEFORE
+// equal distances.
+inline bool top_insert(std::vector<Cand>& top, Cand e, size_t limit) {
+    size_t pos = 0, n = top.size();
+    {
+        size_t lo = 0, hi = n;
+        while (lo < hi) {
+            size_t mid = (lo + hi) / 2;
+            if (top[mid].d < e.d) lo = mid + 1; else hi = mid;
+        }
+        pos = lo;
+    }
+    if (pos == limit) return false;
+    if (n == limit) top.pop_back();
+    top.insert(top.begin() + pos, e);
+    return true;
+}
+
+// The candidate queue ("next"). usearch keeps an unbounded binary max-heap on -distance whose order
+// among equal distances is an implementation detail; the restatement fixes it: ascending distance,
+// FIFO among equal distances (upper_bound insert). cap == 0: unbounded (reference behaviour).
+// cap > 0: the bounded policy the CUDA kernel uses (drop the farthest when full).
+struct NextQueue {
+    std::vector<Cand> v;  // ascending
+    size_t cap = 0;
+    bool dropped = false;
+    void clear() { v.clear(); dropped = false; }
+    bool empty() const { return v.empty(); }
+    const Cand& front() const { return v.front(); }
+    void pop() { v.erase(v.begin()); }
+    void insert(Cand e) {
+        size_t lo = 0, hi = v.size();
+        while (lo < hi) {
+            size_t mid = (lo + hi) / 2;
+            if (v[mid].d <= e.d) lo = mid + 1; else hi = mid;
+        }
+        if (cap && v.size() == cap) {
+            dropped = true;
+            if (lo == cap) return;
+            v.pop_back();
+        }
+        v.insert(v.begin() + lo, e);
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// HNSW index in memory, mirroring the usearch node layout
+// ----------------------------------------------------------------------------------------------
+struct Hnsw {
+    size_t n = 0, d = 0, M = 0, M0 = 0;
+    int64_t max_level = 0;
+    uint64_t entry = 0;
+    int metric = METRIC_IP;
+    std::vector<float> vecs;
+    std::vector<int16_t> levels;
+    std::vector<uint64_t> keys;
+    std::vector<size_t> off;      // index into links
+    std::vector<uint32_t> links;  // per node: [cnt, M0 slots] then per upper level [cnt, M slots]
+    size_t node_words(int level) const { return (1 + M0) + (size_t)level * (1 + M); }
+    uint32_t* list(size_t i, int level) {
+        return &links[off[i] + (level ? (1 + M0) + (size_t)(level - 1) * (1 + M) : 0)];
+    }
+    const uint32_t* list(size_t i, int level) const { return const_cast<Hnsw*>(this)->list(i, level); }
+    const float* vec(size_t i) const { return &vecs[i * d]; }
+};
+
+struct SearchStats {
+    uint64_t n_dist = 0, n_hops0 = 0, n_hops_upper = 0, dropped = 0;
+};
+
+// usearch search_for_one_: greedy descent on levels (from_level .. to_level+1]
+uint32_t greedy_upper(const Hnsw& g, const float* q, DistCfg dc, uint32_t start, float& start_d,
+                      int from_level, int to_level, SearchStats& st) {
+    uint32_t closest = start;
+    float closest_d = start_d;
+    for (int level = from_level; level > to_level; --level) {
+        bool changed;
+        do {
+            changed = false;
+            const uint32_t* l = g.list(closest, level);  // list captured at pass start
+            uint32_t cnt = l[0];
+            st.n_hops_upper++;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                uint32_t s = l[1 + i];
+                float dd = dist(q, g.vec(s), g.d, dc);
+                st.n_dist++;
+                if (dd < closest_d) { closest_d = dd; closest = s; changed = true; }
+            }
+        } while (changed);
+    }
+    start_d = closest_d;
+    return closest;
+}
+
+// Generic level beam search used for both usearch variants:
+//  insert_variant == false : search_to_find_in_base_  (break when cand.d > radius)
+//  insert_variant == true  : search_to_insert_        (break when cand.d > radius && top full)
+// `radius` follows usearch (largest distance in top) for the unfiltered call. With a mask the
+// rule is: radius = +inf until top holds `ef` matching entries (documented extension, the
+// reference never calls usearch's filtered_search; searcher.rs:190-194 post-filters instead).
+void beam_level(const Hnsw& g, const float* q, DistCfg dc, uint32_t start, float start_d, int level,
+                size_t ef, bool insert_variant, const uint64_t* mask, size_t next_cap,
+                std::vector<uint8_t>& visited, std::vector<uint32_t>& touched,
+                std::vector<Cand>& top, NextQueue& next, SearchStats& st) {
+    top.clear();
+    next.clear();
+    next.cap = next_cap;
+    for (uint32_t t : touched) visited[t] = 0;
+    touched.clear();
+    auto pass = [&](uint32_t s) { return !mask || ((mask[s >> 6] >> (s & 63)) & 1ull); };
+    const float INF = std::numeric_limits<float>::infinity();
+    float radius = INF;
+    next.insert({start_d, start});
+    visited[start] = 1;
+    touched.push_back(start);
+    if (pass(start)) top_insert(top, {start_d, start}, ef);
+    auto upd_radius = [&]() { radius = (top.size() == ef) ? top.back().d : INF; };
+    upd_radius();
+    while (!next.empty()) {
+        Cand c = next.front();
+        // Equivalent to usearch's `cand.d > radius` for the unfiltered case: while top is not full
+        // every queued candidate is also in top, so the test can never fire.
+        if (c.d > radius) break;
+        (void)insert_variant;
+        next.pop();
+        const uint32_t* l = g.list(c.s, level);
+        uint32_t cnt = l[0];
+        if (level == 0) st.n_hops0++; else st.n_hops_upper++;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            uint32_t s = l[1 + i];
+            if (visited[s]) continue;
+            visited[s] = 1;
+            touched.push_back(s);
+            float dd = dist(q, g.vec(s), g.d, dc);
+            st.n_dist++;
+            if (top.size() < ef || dd < radius) {
+                next.insert({dd, s});
+                if (pass(s)) top_insert(top, {dd, s}, ef);
+                upd_radius();
+            }
+        }
+    }
+    if (next.dropped) st.dropped++;
+}
+
+struct Ctx {
+    std::vector<uint8_t> visited;
+    std::vector<uint32_t> touched;
+    std::vector<Cand> top;
+    NextQueue next;
+};
+
+// usearch index_gt::search (exact=false): expansion = max(ef, wanted)
+size_t hnsw_search_one(const Hnsw& g, const float* q, size_t k, size_t ef, DistCfg dc,
+                       const uint64_t* mask, size_t next_cap, Ctx& cx, uint64_t* keys, float* dists,
+                       SearchStats& st) {
+    if (g.n == 0) return 0;
+    size_t expansion = std::max(ef, k);
+    if (cx.visited.size() != g.n) cx.visited.assign(g.n, 0), cx.touched.clear();
+    uint32_t start = (uint32_t)g.entry;
+    float sd = dist(q, g.vec(start), g.d, dc);
+    st.n_dist++;
+    start = greedy_upper(g, q, dc, start, sd, (int)g.max_level, 0, st);
+    beam_level(g, q, dc, start, sd, 0, expansion, false, mask, next_cap ? std::max(next_cap, (size_t)1) : 0,
+               cx.visited, cx.touched, cx.top, cx.next, st);
+    size_t cnt = std::min(k, cx.top.size());
+    for (size_t i = 0; i < cnt; ++i) {
+        keys[i] = g.keys[cx.top[i].s];
+        dists[i] = cx.top[i].d;
+    }
+    return cnt;
+}
+
+// usearch refine_ (neighbour-selection heuristic). `top` ascending by distance to the node.
+void refine(const Hnsw& g, std::vector<Cand>& top, size_t needed, DistCfg dc) {
+    if (top.size() < needed) return;
+    size_t submitted = 1, consumed = 1;
+    while (submitted < needed && consumed < top.size()) {
+        Cand c = top[consumed];
+        bool good = true;
+        for (size_t i = 0; i < submitted; ++i) {
+            float dd = dist(g.vec(c.s), g.vec(top[i].s), g.d, dc);
+            if (dd < c.d) { good = false; break; }
+        }
+        if (good) top[submitted++] = top[consumed];
+        consumed++;
+    }
+    top.resize(submitted);
+}
+
+// usearch index_gt::add restated (single thread, sequential; hnsw.rs:128-130). The level generator
+// (std::default_random_engine per thread in usearch) is a builder detail that no file pins; a
+// seeded std::mt19937_64 is used here.
+Hnsw* hnsw_build(const float* vecs, size_t n, size_t d, size_t M, size_t ef_add, uint64_t seed, int metric) {
+    Hnsw* g = new Hnsw();
+    g->n = n; g->d = d; g->M = M; g->M0 = 2 * M; g->metric = metric;
+    g->vecs.assign(vecs, vecs + n * d);
+    g->levels.resize(n); g->keys.resize(n); g->off.resize(n);
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    double inv_log = 1.0 / std::log((double)M);
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        double u = uni(rng);
+        if (u <= 0.0) u = 1e-300;
+        int lvl = (int)(-std::log(u) * inv_log);
+        if (lvl > 30) lvl = 30;
+        g->levels[i] = (int16_t)lvl;
+        g->keys[i] = i;
+        g->off[i] = total;
+        total += g->node_words(lvl);
+    }
+    g->links.assign(total, 0);
+    DistCfg dc{metric, 0};
+    Ctx cx;
+    cx.visited.assign(n, 0);
+    SearchStats st;
+    for (size_t i = 0; i < n; ++i) {
+        int lvl = g->levels[i];
+        if (i == 0) { g->entry = 0; g->max_level = lvl; continue; }
+        const float* q = g->vec(i);
+        uint32_t closest = (uint32_t)g->entry;
+        float cd = dist(q, g->vec(closest), d, dc);
+        int maxl = (int)g->max_level;
+        closest = greedy_upper(*g, q, dc, closest, cd, maxl, lvl, st);
+        for (int level = std::min(lvl, maxl); level >= 0; --level) {
+            beam_level(*g, q, dc, closest, cd, level, ef_add, true, nullptr, 0, cx.visited, cx.touched,
+                       cx.top, cx.next, st);
+            std::vector<Cand> sel = cx.top;
+            refine(*g, sel, M, dc);  // outgoing links use `connectivity` on every level
+            uint32_t* mine = g->list(i, level);
+            mine[0] = 0;
+            for (auto& c : sel) mine[1 + mine[0]++] = c.s;
+            closest = sel[0].s; cd = sel[0].d;
+            size_t cap = level ? M : g->M0;
+            for (auto& c : sel) {
+                uint32_t* theirs = g->list(c.s, level);
+                if (theirs[0] < cap) { theirs[1 + theirs[0]++] = (uint32_t)i; continue; }
+                std::vector<Cand> cand;
+                cand.reserve(cap + 1);
+                cand.push_back({dist(q, g->vec(c.s), d, dc), (uint32_t)i});
+                for (uint32_t j = 0; j < theirs[0]; ++j)
+                    cand.push_back({dist(g->vec(c.s), g->vec(theirs[1 + j]), d, dc), theirs[1 + j]});
+                std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.d < b.d; });
+                refine(*g, cand, cap, dc);
+                theirs[0] = 0;
+                for (auto& cc : cand) theirs[1 + theirs[0]++] = cc.s;
+            }
+        }
+        if (lvl > maxl) { g->entry = i; g->max_level = lvl; }
+    }
+    return g;
+}
+
+// ----------------------------------------------------------------------------------------------
+// usearch `.index` serialisation (Appendix A.1). Writer exists because real usearch cannot run here.
+// ----------------------------------------------------------------------------------------------
+#pragma pack(push, 1)
+struct DenseHead {
+    char magic[7];
+    uint16_t vmaj, vmin, vpatch;
+    uint8_t metric_kind, scalar_kind, key_kind, slot_kind;
+    uint64_t count_present, count_deleted, dimensions;
+    uint8_t multi;
+    uint8_t pad[22];
+};
+struct GraphHead {
+    uint64_t size, connectivity, connectivity_base, max_level, entry_slot;
+};
+#pragma pack(pop)
+static_assert(sizeof(DenseHead) == 64, "usearch dense head is 64 bytes");
+static_assert(sizeof(GraphHead) == 40, "usearch graph header is 40 bytes");
+
+int hnsw_save(const Hnsw& g, const char* path) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    uint32_t dims[2] = {(uint32_t)g.n, (uint32_t)(g.d * 4)};
+    fwrite(dims, 4, 2, f);
+    fwrite(g.vecs.data(), 4, g.n * g.d, f);
+    DenseHead h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "usearch", 7);
+    h.vmaj = 2; h.vmin = 23; h.vpatch = 0;
+    h.metric_kind = g.metric == METRIC_L2SQ ? 'e' : 'i';
+    h.scalar_kind = 11; h.key_kind = 14; h.slot_kind = 15;
+    h.count_present = g.n; h.count_deleted = 0; h.dimensions = g.d; h.multi = 0;
+    fwrite(&h, sizeof h, 1, f);
+    GraphHead gh{g.n, g.M, g.M0, (uint64_t)g.max_level, g.entry};
+    fwrite(&gh, sizeof gh, 1, f);
+    fwrite(g.levels.data(), 2, g.n, f);
+    for (size_t i = 0; i < g.n; ++i) {
+        fwrite(&g.keys[i], 8, 1, f);
+        fwrite(&g.levels[i], 2, 1, f);
+        fwrite(&g.links[g.off[i]], 4, g.node_words(g.levels[i]), f);
+    }
+    fclose(f);
+    return 0;
+}
+
+Hnsw* hnsw_load(const char* path, size_t dims_expected, char* err, size_t errlen) {
+    auto fail = [&](const char* m) -> Hnsw* { if (err && errlen) snprintf(err, errlen, "%s", m); return nullptr; };
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail("index file not found");
+    fseek(f, 0, SEEK_END);
+    size_t fsize = (size_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf(fsize);
+    if (fread(buf.data(), 1, fsize, f) != fsize) { fclose(f); return fail("short read"); }
+    fclose(f);
+    size_t p = 0;
+    auto need = [&](size_t b) { return p + b <= fsize; };
+    if (!need(8)) return fail("truncated: matrix dims");
+    uint32_t rows, cols;
+    memcpy(&rows, &buf[0], 4); memcpy(&cols, &buf[4], 4);
+    p = 8;
+    if (!need((size_t)rows * cols)) return fail("truncated: vectors");
+    size_t vec_off = p;
+    p += (size_t)rows * cols;
+    if (!need(sizeof(DenseHead))) return fail("truncated: head");
+    DenseHead h;
+    memcpy(&h, &buf[p], sizeof h);
+    p += sizeof h;
+    if (memcmp(h.magic, "usearch", 7) != 0) return fail("bad magic");
+    if (h.scalar_kind != 11 || h.key_kind != 14 || h.slot_kind != 15) return fail("unsupported scalar/key/slot kind");
+    if (h.metric_kind != 'i' && h.metric_kind != 'e' && h.metric_kind != 'c') return fail("unsupported metric");
+    if (h.dimensions * 4 != cols) return fail("dimension/cols mismatch");
+    if (dims_expected && h.dimensions != dims_expected) return fail("dimension mismatch");
+    if (!need(sizeof(GraphHead))) return fail("truncated: graph header");
+    GraphHead gh;
+    memcpy(&gh, &buf[p], sizeof gh);
+    p += sizeof gh;
+    if (gh.size != rows) return fail("rows != graph size");
+    Hnsw* g = new Hnsw();
+    g->n = rows; g->d = h.dimensions; g->M = gh.connectivity; g->M0 = gh.connectivity_base;
+    g->max_level = (int64_t)gh.max_level; g->entry = gh.entry_slot;
+    g->metric = h.metric_kind == 'e' ? METRIC_L2SQ : METRIC_IP;
+    g->vecs.resize(g->n * g->d);
+    memcpy(g->vecs.data(), &buf[vec_off], g->n * g->d * 4);
+    if (!need(2 * g->n)) { delete g; return fail("truncated: levels"); }
+    g->levels.resize(g->n);
+    memcpy(g->levels.data(), &buf[p], 2 * g->n);
+    p += 2 * g->n;
+    g->keys.resize(g->n); g->off.resize(g->n);
+    size_t total = 0;
+    for (size_t i = 0; i < g->n; ++i) { g->off[i] = total; total += g->node_words(g->levels[i]); }
+    g->links.resize(total);
+    for (size_t i = 0; i < g->n; ++i) {
+        size_t nb = 10 + 4 * g->node_words(g->levels[i]);
+        if (!need(nb)) { delete g; return fail("truncated: nodes"); }
+        memcpy(&g->keys[i], &buf[p], 8);
+        int16_t lv;
+        memcpy(&lv, &buf[p + 8], 2);
+        if (lv != g->levels[i]) { delete g; return fail("node level != level table"); }
+        memcpy(&g->links[g->off[i]], &buf[p + 10], nb - 10);
+        p += nb;
+    }
+    if (p != fsize) { delete g; return fail("file size equation violated (trailing bytes)"); }
+    return g;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Vamana (diskann-rs 0.3.4) restated — Appendix A.3
+// ----------------------------------------------------------------------------------------------
+struct Vamana {
+    size_t n = 0, d = 0, R = 0;
+    uint32_t medoid = 0;
+    int metric = METRIC_IP_CLAMP;
+    std::vector<float> vecs;
+    std::vector<uint32_t> adj;  // n*R, padded with UINT32_MAX
+    const float* vec(size_t i) const { return &vecs[i * d]; }
+};
+const uint32_t PAD = 0xFFFFFFFFu;
+
+// diskann-rs search_with_dists: visited set, frontier min-heap, working max-heap `w` (<= beam).
+// Termination: w full && best.dist >= worst.dist (non-strict). Restated with the same sorted-array
+// containers as above so the bounded/unbounded policies are shared with the kernel.
+size_t vamana_search_one(const Vamana& g, const float* q, size_t k, size_t beam, DistCfg dc,
+                         const uint64_t* mask, size_t next_cap, Ctx& cx, uint64_t* keys, float* dists,
+                         SearchStats& st) {
+    if (g.n == 0) return 0;
+    beam = std::max(beam, k);
+    if (cx.visited.size() != g.n) cx.visited.assign(g.n, 0), cx.touched.clear();
+    for (uint32_t t : cx.touched) cx.visited[t] = 0;
+    cx.touched.clear();
+    auto& top = cx.top;
+    auto& next = cx.next;
+    top.clear(); next.clear(); next.cap = next_cap;
+    auto pass = [&](uint32_t s) { return !mask || ((mask[s >> 6] >> (s & 63)) & 1ull); };
+    const float INF = std::numeric_limits<float>::infinity();
+    uint32_t start = g.medoid;
+    float sd = dist(q, g.vec(start), g.d, dc);
+    st.n_dist++;
+    next.insert({sd, start});
+    cx.visited[start] = 1; cx.touched.push_back(start);
+    if (pass(start)) top_insert(top, {sd, start}, beam);
+    float radius = top.size() == beam ? top.back().d : INF;
+    while (!next.empty()) {
+        Cand c = next.front();
+        if (top.size() >= beam && c.d >= radius) break;
+        next.pop();
+        st.n_hops0++;
+        const uint32_t* l = &g.adj[(size_t)c.s * g.R];
+        for (size_t i = 0; i < g.R; ++i) {
+            uint32_t s = l[i];
+            if (s == PAD) continue;
+            if (cx.visited[s]) continue;
+            cx.visited[s] = 1; cx.touched.push_back(s);
+            float dd = dist(q, g.vec(s), g.d, dc);
+            st.n_dist++;
+            if (top.size() < beam || dd < radius) {
+                next.insert({dd, s});
+                if (pass(s)) top_insert(top, {dd, s}, beam);
+                radius = top.size() == beam ? top.back().d : INF;
+            }
+        }
+    }
+    if (next.dropped) st.dropped++;
+    size_t cnt = std::min(k, top.size());
+    for (size_t i = 0; i < cnt; ++i) { keys[i] = top[i].s; dists[i] = top[i].d; }
+    return cnt;
+}
+
+// Greedy search returning the visited list (for the builder).
+void vamana_greedy_visit(const Vamana& g, const float* q, size_t L, DistCfg dc, Ctx& cx,
+                         std::vector<Cand>& visited_out) {
+    for (uint32_t t : cx.touched) cx.visited[t] = 0;
+    cx.touched.clear();
+    auto& top = cx.top; auto& next = cx.next;
+    top.clear(); next.clear(); next.cap = 0;
+    visited_out.clear();
+    const float INF = std::numeric_limits<float>::infinity();
+    uint32_t start = g.medoid;
+    float sd = dist(q, g.vec(start), g.d, dc);
+    next.insert({sd, start});
+    cx.visited[start] = 1; cx.touched.push_back(start);
+    top_insert(top, {sd, start}, L);
+    float radius = top.size() == L ? top.back().d : INF;
+    while (!next.empty()) {
+        Cand c = next.front();
+        if (top.size() >= L && c.d >= radius) break;
+        next.pop();
+        visited_out.push_back(c);
+        const uint32_t* l = &g.adj[(size_t)c.s * g.R];
+        for (size_t i = 0; i < g.R; ++i) {
+            uint32_t s = l[i];
+            if (s == PAD || cx.visited[s]) continue;
+            cx.visited[s] = 1; cx.touched.push_back(s);
+            float dd = dist(q, g.vec(s), g.d, dc);
+            if (top.size() < L || dd < radius) {
+                next.insert({dd, s});
+                top_insert(top, {dd, s}, L);
+                radius = top.size() == L ? top.back().d : INF;
+            }
+        }
+    }
+}
+
+// alpha-robust prune (DiskANN paper Alg. 2; diskann.rs:91 alpha = 1.2)
+void robust_prune(Vamana& g, uint32_t p, std::vector<Cand>& cand, float alpha, DistCfg dc) {
+    std::sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.d < b.d || (a.d == b.d && a.s < b.s); });
+    cand.erase(std::unique(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.s == b.s; }), cand.end());
+    std::vector<uint32_t> out;
+    std::vector<char> dead(cand.size(), 0);
+    for (size_t i = 0; i < cand.size() && out.size() < g.R; ++i) {
+        if (dead[i] || cand[i].s == p) continue;
+        out.push_back(cand[i].s);
+        for (size_t j = i + 1; j < cand.size(); ++j) {
+            if (dead[j]) continue;
+            float dij = dist(g.vec(cand[i].s), g.vec(cand[j].s), g.d, dc);
+            if (alpha * dij <= cand[j].d) dead[j] = 1;
+        }
+    }
+    uint32_t* l = &g.adj[(size_t)p * g.R];
+    for (size_t i = 0; i < g.R; ++i) l[i] = i < out.size() ? out[i] : PAD;
+}
+
+Vamana* vamana_build(const float* vecs, size_t n, size_t d, size_t R, size_t L, float alpha, uint64_t seed, int metric) {
+    Vamana* g = new Vamana();
+    g->n = n; g->d = d; g->R = R; g->metric = metric;
+    g->vecs.assign(vecs, vecs + n * d);
+    g->adj.assign(n * R, PAD);
+    DistCfg dc{metric, 0};
+    std::mt19937_64 rng(seed);
+    // medoid: point nearest the centroid
+    std::vector<double> cen(d, 0.0);
+    for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < d; ++j) cen[j] += vecs[i * d + j];
+    std::vector<float> cf(d);
+    for (size_t j = 0; j < d; ++j) cf[j] = (float)(cen[j] / (double)std::max<size_t>(n, 1));
+    float best = std::numeric_limits<float>::infinity();
+    for (size_t i = 0; i < n; ++i) {
+        float dd = dist_seq(cf.data(), g->vec(i), d, METRIC_L2SQ);
+        if (dd < best) { best = dd; g->medoid = (uint32_t)i; }
+    }
+    // random initial graph
+    size_t r0 = std::min(R, n > 1 ? n - 1 : 0);
+    for (size_t i = 0; i < n; ++i) {
+        std::unordered_set<uint32_t> s;
+        while (s.size() < r0) { uint32_t v = (uint32_t)(rng() % n); if (v != i) s.insert(v); }
+        size_t j = 0;
+        for (uint32_t v : s) g->adj[i * R + j++] = v;
+    }
+    Ctx cx; cx.visited.assign(n, 0);
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    for (int pass = 0; pass < 2; ++pass) {
+        float a = pass == 0 ? 1.0f : alpha;
+        std::shuffle(order.begin(), order.end(), rng);
+        std::vector<Cand> vis;
+        for (uint32_t p : order) {
+            vamana_greedy_visit(*g, g->vec(p), L, dc, cx, vis);
+            std::vector<Cand> cand = vis;
+            for (auto& c : cx.top) cand.push_back(c);
+            for (size_t i = 0; i < R; ++i) { uint32_t s = g->adj[(size_t)p * R + i]; if (s != PAD) cand.push_back({dist(g->vec(p), g->vec(s), d, dc), s}); }
+            robust_prune(*g, p, cand, a, dc);
+            for (size_t i = 0; i < R; ++i) {
+                uint32_t s = g->adj[(size_t)p * R + i];
+                if (s == PAD) break;
+                uint32_t* l = &g->adj[(size_t)s * R];
+                size_t cnt = 0; bool has = false;
+                while (cnt < R && l[cnt] != PAD) { if (l[cnt] == p) has = true; cnt++; }
+                if (has) continue;
+                if (cnt < R) { l[cnt] = p; continue; }
+                std::vector<Cand> c2;
+                c2.push_back({dist(g->vec(s), g->vec(p), d, dc), p});
+                for (size_t j = 0; j < R; ++j) c2.push_back({dist(g->vec(s), g->vec(l[j]), d, dc), l[j]});
+                robust_prune(*g, s, c2, a, dc);
+            }
+        }
+    }
+    return g;
+}
+
+// `.diskann` file: u64 meta_len | bincode-1 meta | zero pad to vectors_offset | vectors | adjacency
+const uint64_t DISKANN_VECTORS_OFFSET = 1u << 20;
+void put_u64(std::vector<uint8_t>& b, uint64_t v) { for (int i = 0; i < 8; ++i) b.push_back((uint8_t)(v >> (8 * i))); }
+void put_u32(std::vector<uint8_t>& b, uint32_t v) { for (int i = 0; i < 4; ++i) b.push_back((uint8_t)(v >> (8 * i))); }
+
+int vamana_save(const Vamana& g, const char* path) {
+    std::vector<uint8_t> meta;
+    std::string name = "DistDot";
+    uint64_t voff = DISKANN_VECTORS_OFFSET, aoff = voff + (uint64_t)g.n * g.d * 4;
+    put_u64(meta, g.d); put_u64(meta, g.n); put_u64(meta, g.R); put_u32(meta, g.medoid);
+    put_u64(meta, voff); put_u64(meta, aoff); put_u64(meta, name.size());
+    for (char c : name) meta.push_back((uint8_t)c);
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    uint64_t ml = meta.size();
+    fwrite(&ml, 8, 1, f);
+    fwrite(meta.data(), 1, meta.size(), f);
+    std::vector<uint8_t> zeros(voff - 8 - meta.size(), 0);
+    fwrite(zeros.data(), 1, zeros.size(), f);
+    fwrite(g.vecs.data(), 4, g.n * g.d, f);
+    fwrite(g.adj.data(), 4, g.n * g.R, f);
+    fclose(f);
+    return 0;
+}
+
+Vamana* vamana_load(const char* path, char* err, size_t errlen) {
+    auto fail = [&](const char* m) -> Vamana* { if (err && errlen) snprintf(err, errlen, "%s", m); return nullptr; };
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail("diskann file not found");
+    fseek(f, 0, SEEK_END); size_t fsize = (size_t)ftell(f); fseek(f, 0, SEEK_SET);
+    uint64_t ml;
+    if (fread(&ml, 8, 1, f) != 1 || ml > 4096 || ml < 52) { fclose(f); return fail("bad meta length"); }
+    std::vector<uint8_t> m(ml);
+    if (fread(m.data(), 1, ml, f) != ml) { fclose(f); return fail("truncated meta"); }
+    auto u64 = [&](size_t o) { uint64_t v; memcpy(&v, &m[o], 8); return v; };
+    Vamana* g = new Vamana();
+    g->d = u64(0); g->n = u64(8); g->R = u64(16);
+    memcpy(&g->medoid, &m[24], 4);
+    uint64_t voff = u64(28), aoff = u64(36);
+    if (aoff != voff + (uint64_t)g->n * g->d * 4 || fsize != aoff + (uint64_t)g->n * g->R * 4) { fclose(f); delete g; return fail("file size equation violated"); }
+    g->vecs.resize(g->n * g->d); g->adj.resize(g->n * g->R);
+    fseek(f, (long)voff, SEEK_SET);
+    bool ok = fread(g->vecs.data(), 4, g->n * g->d, f) == g->n * g->d && fread(g->adj.data(), 4, g->n * g->R, f) == g->n * g->R;
+    fclose(f);
+    if (!ok) { delete g; return fail("short read"); }
+    return g;
+}
+
+template <typename F>
+void parallel_for(size_t n, int nthreads, F f) {
+    if (nthreads <= 1 || n < 2) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    std::atomic<size_t> nextq{0};
+    const size_t chunk = 16;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t]() {
+            for (;;) {
+                size_t b = nextq.fetch_add(chunk);
+                if (b >= n) break;
+                f(b, std::min(n, b + chunk), t);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- HNSW ----
+void* orc_hnsw_build(const float* vecs, size_t n, size_t d, size_t M, size_t ef_add, uint64_t seed, int metric) {
+    return hnsw_build(vecs, n, d, M, ef_add, seed, metric);
+}
+int orc_hnsw_save(void* h, const char* path) { return hnsw_save(*(Hnsw*)h, path); }
+void* orc_hnsw_load(const char* path, size_t dims, char* err, size_t errlen) { return hnsw_load(path, dims, err, errlen); }
+void orc_hnsw_free(void* h) { delete (Hnsw*)h; }
+size_t orc_hnsw_len(void* h) { return ((Hnsw*)h)->n; }
+void orc_hnsw_info(void* h, uint64_t* out /*n,d,M,M0,max_level,entry,metric*/) {
+    Hnsw* g = (Hnsw*)h;
+    out[0] = g->n; out[1] = g->d; out[2] = g->M; out[3] = g->M0; out[4] = (uint64_t)g->max_level; out[5] = g->entry; out[6] = (uint64_t)g->metric;
+}
+// stats: per query [n_dist, n_hops0, n_hops_upper, dropped]
+void orc_hnsw_search(void* h, const float* queries, size_t nq, size_t k, size_t ef, int lanes,
+                     const uint64_t* mask, size_t next_cap, uint64_t* keys, float* dists,
+                     uint32_t* counts, uint64_t* stats, int nthreads) {
+    Hnsw* g = (Hnsw*)h;
+    DistCfg dc{g->metric, lanes};
+    int nt = std::max(1, nthreads);
+    std::vector<Ctx> ctx(nt);
+    parallel_for(nq, nt, [&](size_t b, size_t e, int t) {
+        for (size_t i = b; i < e; ++i) {
+            for (size_t j = 0; j < k; ++j) { keys[i * k + j] = UINT64_MAX; dists[i * k + j] = std::numeric_limits<float>::infinity(); }
+            SearchStats st;
+            size_t c = hnsw_search_one(*g, queries + i * g->d, k, ef, dc, mask, next_cap, ctx[t], keys + i * k, dists + i * k, st);
+            if (counts) counts[i] = (uint32_t)c;
+            if (stats) { stats[i * 4] = st.n_dist; stats[i * 4 + 1] = st.n_hops0; stats[i * 4 + 2] = st.n_hops_upper; stats[i * 4 + 3] = st.dropped; }
+        }
+    });
+}
+
+// ---- Vamana ----
+void* orc_vamana_build(const float* vecs, size_t n, size_t d, size_t R, size_t L, float alpha, uint64_t seed, int metric) {
+    return vamana_build(vecs, n, d, R, L, alpha, seed, metric);
+}
+int orc_vamana_save(void* h, const char* path) { return vamana_save(*(Vamana*)h, path); }
+void* orc_vamana_load(const char* path, char* err, size_t errlen) { return vamana_load(path, err, errlen); }
+void orc_vamana_free(void* h) { delete (Vamana*)h; }
+void orc_vamana_info(void* h, uint64_t* out /*n,d,R,medoid*/) {
+    Vamana* g = (Vamana*)h; out[0] = g->n; out[1] = g->d; out[2] = g->R; out[3] = g->medoid;
+}
+void orc_vamana_set_metric(void* h, int metric) { ((Vamana*)h)->metric = metric; }
+void orc_vamana_search(void* h, const float* queries, size_t nq, size_t k, size_t beam, int lanes,
+                       const uint64_t* mask, size_t next_cap, uint64_t* keys, float* dists,
+                       uint32_t* counts, uint64_t* stats, int nthreads) {
+    Vamana* g = (Vamana*)h;
+    DistCfg dc{g->metric, lanes};
+    int nt = std::max(1, nthreads);
+    std::vector<Ctx> ctx(nt);
+    parallel_for(nq, nt, [&](size_t b, size_t e, int t) {
+        for (size_t i = b; i < e; ++i) {
+            for (size_t j = 0; j < k; ++j) { keys[i * k + j] = UINT64_MAX; dists[i * k + j] = std::numeric_limits<float>::infinity(); }
+            SearchStats st;
+            size_t c = vamana_search_one(*g, queries + i * g->d, k, beam, dc, mask, next_cap, ctx[t], keys + i * k, dists + i * k, st);
+            if (counts) counts[i] = (uint32_t)c;
+            if (stats) { stats[i * 4] = st.n_dist; stats[i * 4 + 1] = st.n_hops0; stats[i * 4 + 2] = 0; stats[i * 4 + 3] = st.dropped; }
+        }
+    });
+}
+
+// ---- Exact scan: recompute.rs:96-110 + 137-139 ----
+// score_i = sequential f32 fold of q_j*x_ij (mul, then add); stable sort descending (ties keep
+// ascending row order, NaN compares Equal is not modelled: inputs are finite); take k.
+// metric 0: raw dot, descending (recompute.rs:100). metric 1: L2sq ascending (BASELINE C4 extension).
+// metric 2: 1-dot ascending (backend convention, traits.rs:16-21).
+// mask (nullable, N bits): pre-filter as recompute.rs:65-79 does.
+void orc_exact_scan(const float* queries, size_t nq, const float* db, size_t n, size_t d, size_t k,
+                    int metric, const uint64_t* mask, uint64_t* idx, float* scores, uint32_t* counts,
+                    int nthreads) {
+    parallel_for(nq, std::max(1, nthreads), [&](size_t b, size_t e, int) {
+        std::vector<std::pair<float, uint32_t>> sc;
+        for (size_t qi = b; qi < e; ++qi) {
+            const float* q = queries + qi * d;
+            sc.clear();
+            for (size_t i = 0; i < n; ++i) {
+                if (mask && !((mask[i >> 6] >> (i & 63)) & 1ull)) continue;
+                const float* x = db + i * d;
+                float s;
+                if (metric == 1) s = dist_seq(q, x, d, METRIC_L2SQ);
+                else { s = 0.0f; for (size_t j = 0; j < d; ++j) s += q[j] * x[j]; if (metric == 2) s = 1.0f - s; }
+                sc.emplace_back(s, (uint32_t)i);
+            }
+            size_t kk = std::min(k, sc.size());
+            auto cmp_desc = [](const std::pair<float, uint32_t>& a, const std::pair<float, uint32_t>& b2) { return a.first > b2.first || (a.first == b2.first && a.second < b2.second); };
+            auto cmp_asc = [](const std::pair<float, uint32_t>& a, const std::pair<float, uint32_t>& b2) { return a.first < b2.first || (a.first == b2.first && a.second < b2.second); };
+            if (metric == 0) std::partial_sort(sc.begin(), sc.begin() + kk, sc.end(), cmp_desc);
+            else std::partial_sort(sc.begin(), sc.begin() + kk, sc.end(), cmp_asc);
+            for (size_t j = 0; j < k; ++j) {
+                idx[qi * k + j] = j < kk ? sc[j].second : UINT64_MAX;
+                scores[qi * k + j] = j < kk ? sc[j].first : (metric == 0 ? -std::numeric_limits<float>::infinity() : std::numeric_limits<float>::infinity());
+            }
+            if (counts) counts[qi] = (uint32_t)kk;
+        }
+    });
+}
+
+// f64 brute force ground truth (self-pin for recall)
+void orc_exact_f64(const float* queries, size_t nq, const float* db, size_t n, size_t d, size_t k, int metric, uint64_t* idx, int nthreads) {
+    parallel_for(nq, std::max(1, nthreads), [&](size_t b, size_t e, int) {
+        std::vector<std::pair<double, uint32_t>> sc(n);
+        for (size_t qi = b; qi < e; ++qi) {
+            const float* q = queries + qi * d;
+            for (size_t i = 0; i < n; ++i) {
+                const float* x = db + i * d;
+                double s = 0;
+                if (metric == 1) for (size_t j = 0; j < d; ++j) { double t = (double)q[j] - x[j]; s += t * t; }
+                else { for (size_t j = 0; j < d; ++j) s += (double)q[j] * x[j]; s = -s; }
+                sc[i] = {s, (uint32_t)i};
+            }
+            size_t kk = std::min(k, n);
+            std::partial_sort(sc.begin(), sc.begin() + kk, sc.end());
+            for (size_t j = 0; j < k; ++j) idx[qi * k + j] = j < kk ? sc[j].second : UINT64_MAX;
+        }
+    });
+}
+
+float orc_distance(const float* a, const float* b, size_t d, int metric, int lanes) { return dist(a, b, d, DistCfg{metric, lanes}); }
+int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+"""GPU parity of K1/K1f (graph beam search) against the CPU oracle on the same index file and ef:
+keys, f32 distance bits and the algorithmic-work counters must be identical."""
+import numpy as np
+import pytest
+
+from conftest import make_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _hnsw_case(orc, pkg, tmp_path, n, d, M, nq, efs, k=10, seed=7, mask_frac=None):
+    x, q = make_data(n, d, seed, nq=nq)
+    g = orc.Hnsw.build(x, M=M, ef_add=64, seed=seed)
+    base = str(tmp_path / "documents.leann")
+    g.save(base.replace(".leann", ".index"))
+    s = pkg.HnswSearcher.load(base, d)
+    assert len(s) == n and s.info()["M0"] == 2 * M
+    lanes = pkg.reduction_lanes(d)
+    mask = None
+    if mask_frac is not None:
+        rng = np.random.default_rng(seed + 1)
+        mask = pkg.pack_mask(rng.random(n) < mask_frac)
+    for ef in efs:
+        cap = pkg.queue_capacity(max(ef, k), mask is not None)
+        ok, od, oc, ost = g.search(q, k, ef, lanes=lanes, mask=mask, next_cap=cap)
+        keys, dists, counts = s.search_batch(q, k, ef, mask=mask)
+        assert np.array_equal(counts, oc)
+        assert np.array_equal(keys, ok), f"ef={ef}: {np.mean(keys == ok):.4f} id agreement"
+        assert np.array_equal(dists.view(np.uint32), od.view(np.uint32))
+        # the bounded queue the kernel uses must equal the reference's unbounded heap here
+        uk, ud, uc, ust = g.search(q, k, ef, lanes=lanes, mask=mask, next_cap=0)
+        if mask is None:
+            assert np.array_equal(uk, ok)
+    return s, g, x, q
+
+
+def test_hnsw_parity_d128(orc, pkg, tmp_path):
+    _hnsw_case(orc, pkg, tmp_path, n=4000, d=128, M=16, nq=300, efs=(16, 64, 128))
+
+
+def test_hnsw_parity_d768_m32(orc, pkg, tmp_path):
+    s, g, x, q = _hnsw_case(orc, pkg, tmp_path, n=2500, d=768, M=32, nq=200, efs=(64, 256))
+    # trait call: one query, complexity ignored -> ef = 64 (hnsw.rs:49,83)
+    keys, dists = s.search(q[0], 5, 999)
+    ok, od, _, _ = g.search(q[:1], 5, 64, lanes=pkg.reduction_lanes(768), next_cap=64)
+    assert keys == [int(v) for v in ok[0]] and np.allclose(dists, od[0])
+
+
+def test_hnsw_parity_odd_dims(orc, pkg, tmp_path):
+    _hnsw_case(orc, pkg, tmp_path, n=1500, d=100, M=8, nq=100, efs=(32,))
+    _hnsw_case(orc, pkg, tmp_path, n=1500, d=70, M=8, nq=100, efs=(32,))
+    _hnsw_case(orc, pkg, tmp_path, n=1200, d=1536, M=8, nq=50, efs=(32,))
+
+
+def test_hnsw_inline_mask(orc, pkg, tmp_path):
+    _hnsw_case(orc, pkg, tmp_path, n=4000, d=128, M=16, nq=200, efs=(64,), mask_frac=0.25)
+    _hnsw_case(orc, pkg, tmp_path, n=4000, d=128, M=16, nq=200, efs=(64,), mask_frac=0.02)
+
+
+def test_hnsw_stats_counters(orc, pkg, tmp_path):
+    import torch
+    n, d, k, ef = 3000, 128, 10, 64
+    x, q = make_data(n, d, 3, nq=128)
+    g = orc.Hnsw.build(x, M=16, ef_add=64, seed=3)
+    base = str(tmp_path / "documents.leann")
+    g.save(base.replace(".leann", ".index"))
+    s = pkg.HnswSearcher.load(base, d)
+    qt = torch.from_numpy(q).cuda()
+    stats = torch.zeros((q.shape[0], 4), dtype=torch.int64, device="cuda")
+    keys, dists, counts = s.search_device(qt, k, ef, stats=stats)
+    torch.cuda.synchronize()
+    ok, od, oc, ost = g.search(q, k, ef, lanes=pkg.reduction_lanes(d), next_cap=ef)
+    assert np.array_equal(keys.cpu().numpy().astype(np.uint64), ok)
+    assert np.array_equal(stats.cpu().numpy().astype(np.uint64), ost)
+
+
+def test_hnsw_small_and_k_gt_n(orc, pkg, tmp_path):
+    x, q = make_data(5, 64, 1, nq=4)
+    g = orc.Hnsw.build(x, M=4, ef_add=16, seed=1)
+    base = str(tmp_path / "documents.leann")
+    g.save(base.replace(".leann", ".index"))
+    s = pkg.HnswSearcher.load(base, 64)
+    keys, dists, counts = s.search_batch(q, 10, 16)
+    ok, od, oc, _ = g.search(q, 10, 16, lanes=pkg.reduction_lanes(64), next_cap=16)
+    assert np.array_equal(counts, oc) and np.array_equal(keys, ok) and (counts == 5).all()
+    assert (keys[:, 5:] == np.uint64(2**64 - 1)).all() and np.isinf(dists[:, 5:]).all()
+
+
+def test_vamana_parity(orc, pkg, tmp_path):
+    n, d, R, L, k = 3000, 96, 32, 50, 10
+    x, q = make_data(n, d, 11, nq=200)
+    g = orc.Vamana.build(x, R=R, L=L, alpha=1.2, seed=11)
+    base = str(tmp_path / "documents.leann")
+    g.save(base.replace(".leann", ".diskann"))
+    s = pkg.DiskAnnSearcher.load(base, d)
+    assert s.info()["M0"] == R and s.info()["entry"] == g.info()["medoid"]
+    lanes = pkg.reduction_lanes(d)
+    for beam in (10, 50, 100):
+        ok, od, oc, _ = g.search(q, k, beam, lanes=lanes, next_cap=max(beam, k))
+        keys, dists, counts = s.search_batch(q, k, beam)
+        assert np.array_equal(keys, ok) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
+    # trait call honours complexity: beam = max(complexity, top_k)  (diskann.rs:54)
+    keys, dists = s.search(q[0], 10, 3)
+    ok, od, _, _ = g.search(q[:1], 10, 10, lanes=lanes, next_cap=10)
+    assert keys == [int(v) for v in ok[0]]
+    # L2 variant (BASELINE config C4) on un-normalised vectors
+    x2, q2 = make_data(n, d, 12, nq=100, normalize=False)
+    g2 = orc.Vamana.build(x2, R=R, L=L, alpha=1.2, seed=12, metric=orc.METRIC_L2SQ)
+    base2 = str(tmp_path / "l2.leann")
+    g2.save(base2.replace(".leann", ".diskann"))
+    s2 = pkg.DiskAnnSearcher.load(base2, d, metric=pkg.METRIC_L2SQ)
+    ok, od, oc, _ = g2.search(q2, k, 64, lanes=lanes, next_cap=64)
+    keys, dists, counts = s2.search_batch(q2, k, 64)
+    assert np.array_equal(keys, ok) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
