@@ -1,6 +1,5 @@
-// temporary: builders arrive in hnsw_build.cu / vamana_build.cu
+// temporary: the Vamana builder arrives in vamana_build.cu
 #include "internal.h"
 namespace leann {
-void gpu_hnsw_build(leann_cuda_index*, size_t, size_t, uint64_t) { throw Error(LEANN_ERR_INVALID_ARG, "hnsw build: not implemented yet"); }
 void gpu_vamana_build(leann_cuda_index*, size_t, size_t, float, uint64_t) { throw Error(LEANN_ERR_INVALID_ARG, "vamana build: not implemented yet"); }
 }

@@ -1,0 +1,403 @@
+// hnsw_build.cu — GPU construction of the usearch-format HNSW graph (replaces the sequential
+// `index.add(i, v)` loop of hnsw::build_index, leann-rs src/backend/hnsw.rs:96-139, and writes the
+// same `.index` file through leann_cuda_save). SURVEY.md §8(f) N1.
+//
+// Batched insertion: nodes are added in slot order in batches that grow with the graph
+// (batch <= size/16). Per batch, three stream-ordered kernels:
+//   A  insert_search : one warp per new node — greedy descent, then per level the same beam search
+//                      as K1 with ef = expansion_add, usearch's neighbour-selection heuristic
+//                      (refine_) down to M links, forward links written, reverse edges emitted;
+//   B  reverse_append: one thread per reverse edge — claims a slot in the target list with an
+//                      atomic counter; overflowing lists are queued for pruning;
+//   C  prune         : one warp per overflowing list — re-ranks (existing + incoming) by distance to
+//                      the owner and re-applies the heuristic down to the level's capacity.
+// Nodes of one batch do not see each other (they are linked by later batches); everything else
+// follows usearch index_gt::add. Level assignment: floor(-ln(U) / ln(M)) as in usearch.
+#include <algorithm>
+#include <cmath>
+#include <random>
+
+#include "graph_device.cuh"
+
+namespace leann {
+
+namespace {
+
+constexpr int EXTRA = 16;        // incoming links buffered per list and batch beyond its capacity
+constexpr int STAGE = 160;       // staging entries per warp in the builder kernels (>= MAX_DEG + EXTRA)
+
+struct BuildParams {
+    uint32_t* adj0; uint32_t* adjU; const uint32_t* upper_base; const uint8_t* levels;
+    uint32_t* cnt;      // [n + n_upper] entries per list (may exceed capacity until pruned)
+    uint32_t* flag;     // [n + n_upper] queued-for-prune marker
+    uint32_t* extra;    // [n + n_upper][EXTRA]
+    uint2* edges;       // (target list owner c, new node p | level << 28 in .y? no: see below)
+    uint32_t* edge_level;
+    uint32_t* edge_count; uint32_t max_edges;
+    uint2* work; uint32_t* work_count; uint32_t* work_cursor;
+    uint32_t first, count;   // batch = slots [first, first+count)
+    uint32_t M, M0, ef_add, n;
+    uint32_t next_cap, next_capp;
+    uint8_t* visited; uint32_t* epochs; uint32_t* counter; size_t n_pad; int n_warps;
+    uint32_t* overflow;  // [0]: edge buffer overflow, [1]: extra overflow (dropped links)
+};
+
+__device__ __forceinline__ void carve(unsigned char* base, uint32_t top_cap, uint32_t next_capp, WarpLists& w) {
+    w.top_d = reinterpret_cast<float*>(base);
+    w.top_s = reinterpret_cast<uint32_t*>(base + (size_t)top_cap * 4);
+    w.next_d = reinterpret_cast<float*>(base + (size_t)top_cap * 8);
+    w.next_s = reinterpret_cast<uint32_t*>(base + (size_t)top_cap * 8 + (size_t)next_capp * 4);
+    w.st_slot = reinterpret_cast<uint32_t*>(base + (size_t)top_cap * 8 + (size_t)next_capp * 8);
+    w.st_dist = reinterpret_cast<float*>(base + (size_t)top_cap * 8 + (size_t)next_capp * 8 + (size_t)STAGE * 4);
+}
+__host__ __device__ inline size_t build_smem_per_warp(uint32_t top_cap, uint32_t next_capp) {
+    return (size_t)top_cap * 8 + (size_t)next_capp * 8 + (size_t)STAGE * 8;
+}
+
+// usearch refine_: `top` ascending by distance to the owner; keeps candidate x unless an already
+// kept neighbour is closer to x than the owner is. Returns the new size.
+template <int LPV, int VPL, int U>
+__device__ __forceinline__ int refine_heuristic(const GraphView& g, WarpLists& w, int needed, int lane) {
+    int total = w.top_size;
+    if (total < needed) return total;
+    int submitted = 1;
+    for (int consumed = 1; consumed < total && submitted < needed; ++consumed) {
+        uint32_t x = w.top_s[consumed];
+        float xd = w.top_d[consumed];
+        float4 qx[VPL];
+        {
+            const int lig = lane % LPV;
+            const float4* row = g.vecs + (size_t)x * g.d4;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                uint32_t idx = (uint32_t)(i * LPV + lig);
+                qx[i] = idx < g.d4 ? __ldg(row + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        bool good = true;
+        // check kept neighbours in chunks of 8 (closest first): most rejections happen early
+        for (int b = 0; b < submitted && good; b += 8) {
+            int c = submitted - b < 8 ? submitted - b : 8;
+            eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, qx, w.top_s + b, w.st_dist, c, lane);
+            bool closer = lane < c && w.st_dist[lane] < xd;
+            if (__any_sync(FULL, closer)) good = false;
+            __syncwarp();
+        }
+        if (good) {
+            if (lane == 0) { w.top_d[submitted] = xd; w.top_s[submitted] = x; }
+            submitted++;
+        }
+        __syncwarp();
+    }
+    return submitted;
+}
+
+template <int LPV, int VPL, int U>
+__global__ void __launch_bounds__(128)
+insert_search_kernel(const GraphView g, const BuildParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (warp_global >= p.n_warps) return;
+    const uint32_t top_cap = (p.ef_add + 31u) & ~31u;
+    WarpLists w;
+    carve(smem_raw + build_smem_per_warp(top_cap, p.next_capp) * wib, top_cap, p.next_capp, w);
+    uint8_t* vis = p.visited + (size_t)warp_global * p.n_pad;
+    uint32_t* epoch_slot = p.epochs + warp_global;
+
+    for (;;) {
+        uint32_t bi = 0;
+        if (lane == 0) bi = atomicAdd(p.counter, 1u);
+        bi = __shfl_sync(FULL, bi, 0);
+        if (bi >= p.count) break;
+        const uint32_t node = p.first + bi;
+        const int node_level = p.levels[node];
+        float4 q[VPL];
+        {
+            const int lig = lane % LPV;
+            const float4* row = g.vecs + (size_t)node * g.d4;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                uint32_t idx = (uint32_t)(i * LPV + lig);
+                q[i] = idx < g.d4 ? __ldg(row + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        Counters c{0u, 0u, 0u, 0u};
+        uint32_t cur = g.entry;
+        if (lane == 0) w.st_slot[0] = cur;
+        __syncwarp();
+        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, 1, lane);
+        float cur_d = w.st_dist[0];
+        __syncwarp();
+        if (g.max_level > node_level) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, node_level, c, lane);
+        const int top_level = node_level < g.max_level ? node_level : g.max_level;
+        for (int level = top_level; level >= 0; --level) {
+            const uint8_t tag = next_epoch(epoch_slot, vis, p.n_pad, lane);
+            LevelAdj adj{g.adj0, g.adjU, g.upper_base, level == 0 ? g.deg0 : g.degU, level};
+            beam_level<LPV, VPL, U>(g, adj, q, w, (int)p.ef_add, (int)p.next_cap, (int)p.next_capp - 1, 0, nullptr,
+                                    vis, tag, cur, cur_d, c, lane);
+            int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)p.M, lane);
+            // forward links of the new node (its rows are pre-filled with SENT)
+            uint32_t* myrow = level == 0 ? p.adj0 + (size_t)node * p.M0
+                                         : p.adjU + ((size_t)p.upper_base[node] + (uint32_t)(level - 1)) * p.M;
+            const uint32_t list_id = level == 0 ? node : p.n + p.upper_base[node] + (uint32_t)(level - 1);
+            uint32_t ebase = 0;
+            if (lane == 0) {
+                p.cnt[list_id] = (uint32_t)kept;
+                ebase = atomicAdd(p.edge_count, (uint32_t)kept);
+            }
+            ebase = __shfl_sync(FULL, ebase, 0);
+            for (int j = lane; j < kept; j += 32) {
+                uint32_t nb = w.top_s[j];
+                myrow[j] = nb;
+                if (ebase + j < p.max_edges) {
+                    p.edges[ebase + j] = make_uint2(nb, node);
+                    p.edge_level[ebase + j] = (uint32_t)level;
+                } else {
+                    p.overflow[0] = 1u;
+                }
+            }
+            cur = w.top_s[0];
+            cur_d = w.top_d[0];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void reverse_append_kernel(const BuildParams p) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ne = *p.edge_count;
+    if (ne > p.max_edges) ne = p.max_edges;
+    if (i >= ne) return;
+    uint2 e = p.edges[i];
+    uint32_t c = e.x, node = e.y, level = p.edge_level[i];
+    uint32_t list_id = level == 0 ? c : p.n + p.upper_base[c] + (level - 1);
+    uint32_t cap = level == 0 ? p.M0 : p.M;
+    uint32_t* row = level == 0 ? p.adj0 + (size_t)c * p.M0 : p.adjU + ((size_t)p.upper_base[c] + (level - 1)) * p.M;
+    uint32_t slot = atomicAdd(&p.cnt[list_id], 1u);
+    if (slot < cap) {
+        row[slot] = node;
+    } else {
+        uint32_t x = slot - cap;
+        if (x < (uint32_t)EXTRA) p.extra[(size_t)list_id * EXTRA + x] = node;
+        else p.overflow[1] = 1u;
+        if (atomicExch(&p.flag[list_id], 1u) == 0u) {
+            uint32_t wpos = atomicAdd(p.work_count, 1u);
+            p.work[wpos] = make_uint2(c, level);
+        }
+    }
+}
+
+template <int LPV, int VPL, int U>
+__global__ void __launch_bounds__(128)
+prune_kernel(const GraphView g, const BuildParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    WarpLists w;
+    carve(smem_raw + build_smem_per_warp(STAGE, 32) * wib, STAGE, 32, w);
+    const uint32_t nwork = *p.work_count;
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(p.work_cursor, 1u);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= nwork) break;
+        uint2 it = p.work[wi];
+        const uint32_t c = it.x, level = it.y;
+        const uint32_t list_id = level == 0 ? c : p.n + p.upper_base[c] + (level - 1);
+        const uint32_t cap = level == 0 ? p.M0 : p.M;
+        uint32_t* row = level == 0 ? p.adj0 + (size_t)c * p.M0 : p.adjU + ((size_t)p.upper_base[c] + (level - 1)) * p.M;
+        uint32_t total = p.cnt[list_id];
+        uint32_t n_ext = total > cap ? total - cap : 0;
+        if (n_ext > (uint32_t)EXTRA) n_ext = EXTRA;
+        const int m = (int)(cap + n_ext);
+        for (int j = lane; j < m; j += 32)
+            w.st_slot[j] = j < (int)cap ? row[j] : p.extra[(size_t)list_id * EXTRA + (j - cap)];
+        float4 q[VPL];
+        {
+            const int lig = lane % LPV;
+            const float4* vr = g.vecs + (size_t)c * g.d4;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                uint32_t idx = (uint32_t)(i * LPV + lig);
+                q[i] = idx < g.d4 ? __ldg(vr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncwarp();
+        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, m, lane);
+        w.top_size = 0;
+        for (int j = 0; j < m; ++j) {
+            float dj = w.st_dist[j];
+            uint32_t sj = w.st_slot[j];
+            __syncwarp();
+            sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, STAGE, 0, 0, dj, sj, lane);
+        }
+        int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)cap, lane);
+        for (int j = lane; j < (int)cap; j += 32) row[j] = j < kept ? w.top_s[j] : SENT;
+        if (lane == 0) { p.cnt[list_id] = (uint32_t)kept; p.flag[list_id] = 0u; }
+        __syncwarp();
+    }
+}
+
+template <typename F>
+void dispatch_dims(uint32_t d, uint32_t d4, F&& f) {
+    if (reduction_lanes(d) == 8) {
+        uint32_t vpl = (d4 + 7) / 8;
+        if (vpl <= 2) f.template operator()<8, 2, 8>();
+        else if (vpl <= 3) f.template operator()<8, 3, 8>();
+        else if (vpl <= 4) f.template operator()<8, 4, 4>();
+        else f.template operator()<8, 8, 2>();
+    } else {
+        uint32_t vpl = (d4 + 31) / 32;
+        if (vpl <= 3) f.template operator()<32, 3, 8>();
+        else if (vpl <= 4) f.template operator()<32, 4, 4>();
+        else if (vpl <= 6) f.template operator()<32, 6, 4>();
+        else if (vpl <= 8) f.template operator()<32, 8, 2>();
+        else if (vpl <= 12) f.template operator()<32, 12, 2>();
+        else if (vpl <= 16) f.template operator()<32, 16, 1>();
+        else if (vpl <= 32) f.template operator()<32, 32, 1>();
+        else throw Error(LEANN_ERR_INVALID_ARG, "dimension above 4096 is not supported");
+    }
+}
+
+struct LaunchA {
+    GraphView g; BuildParams p; cudaStream_t s;
+    template <int LPV, int VPL, int U> void operator()() {
+        uint32_t top_cap = (p.ef_add + 31u) & ~31u;
+        size_t smem = build_smem_per_warp(top_cap, p.next_capp) * 4;
+        auto k = insert_search_kernel<LPV, VPL, U>;
+        if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(p.n_warps + 3) / 4, 128, smem, s>>>(g, p);
+        LEANN_CUDA_CHECK(cudaGetLastError());
+    }
+};
+struct LaunchC {
+    GraphView g; BuildParams p; cudaStream_t s; int blocks;
+    template <int LPV, int VPL, int U> void operator()() {
+        size_t smem = build_smem_per_warp(STAGE, 32) * 4;
+        prune_kernel<LPV, VPL, U><<<blocks, 128, smem, s>>>(g, p);
+        LEANN_CUDA_CHECK(cudaGetLastError());
+    }
+};
+
+template <typename T>
+T* dmalloc(size_t count) {
+    T* p = nullptr;
+    LEANN_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    return p;
+}
+
+}  // namespace
+
+void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed) {
+    const size_t n = ix->n, M0 = 2 * M;
+    ix->M = (uint32_t)M; ix->M0 = (uint32_t)M0;
+    ix->identity_keys = true;
+    // --- levels: usearch choose_random_level_ = floor(-ln(U) * 1/ln(connectivity)) ---
+    std::vector<uint8_t> lv8(n);
+    ix->h_levels.resize(n);
+    std::vector<uint32_t> upper_base(n);
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    const double inv_log = 1.0 / std::log((double)M);
+    size_t n_upper = 0;
+    for (size_t i = 0; i < n; ++i) {
+        double u = uni(rng);
+        if (u <= 0.0) u = 1e-300;
+        int l = (int)(-std::log(u) * inv_log);
+        if (l > 15) l = 15;
+        lv8[i] = (uint8_t)l;
+        ix->h_levels[i] = (int16_t)l;
+        upper_base[i] = (uint32_t)n_upper;
+        n_upper += (size_t)l;
+    }
+    ix->n_upper_lists = n_upper;
+    cudaStream_t stream = nullptr;
+    LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    std::vector<void*> temps;
+    auto cleanup = [&]() { for (void* t : temps) cudaFree(t); cudaStreamDestroy(stream); };
+    try {
+        ix->adj0 = dmalloc<uint32_t>(n * M0);
+        ix->adjU = dmalloc<uint32_t>(n_upper * M);
+        ix->upper_base = dmalloc<uint32_t>(n);
+        ix->keys = dmalloc<uint64_t>(n);
+        LEANN_CUDA_CHECK(cudaMemset(ix->adj0, 0xFF, std::max<size_t>(n * M0, 1) * 4));
+        LEANN_CUDA_CHECK(cudaMemset(ix->adjU, 0xFF, std::max<size_t>(n_upper * M, 1) * 4));
+        if (n) LEANN_CUDA_CHECK(cudaMemcpy(ix->upper_base, upper_base.data(), n * 4, cudaMemcpyHostToDevice));
+        {
+            std::vector<uint64_t> keys(n);
+            for (size_t i = 0; i < n; ++i) keys[i] = i;
+            if (n) LEANN_CUDA_CHECK(cudaMemcpy(ix->keys, keys.data(), n * 8, cudaMemcpyHostToDevice));
+        }
+        ix->entry = 0;
+        ix->max_level = n ? lv8[0] : 0;
+        if (n <= 1) { cleanup(); return; }
+
+        const uint32_t MAXB = 16384;
+        const size_t n_lists = n + n_upper;
+        BuildParams p{};
+        p.adj0 = ix->adj0; p.adjU = ix->adjU; p.upper_base = ix->upper_base;
+        uint8_t* d_levels = dmalloc<uint8_t>(n); temps.push_back(d_levels);
+        LEANN_CUDA_CHECK(cudaMemcpy(d_levels, lv8.data(), n, cudaMemcpyHostToDevice));
+        p.levels = d_levels;
+        p.cnt = dmalloc<uint32_t>(n_lists); temps.push_back(p.cnt);
+        p.flag = dmalloc<uint32_t>(n_lists); temps.push_back(p.flag);
+        p.extra = dmalloc<uint32_t>(n_lists * EXTRA); temps.push_back(p.extra);
+        LEANN_CUDA_CHECK(cudaMemset(p.cnt, 0, n_lists * 4));
+        LEANN_CUDA_CHECK(cudaMemset(p.flag, 0, n_lists * 4));
+        p.max_edges = (uint32_t)std::min<size_t>((size_t)MAXB * M * 3, (size_t)0x7FFFFFFF);
+        p.edges = dmalloc<uint2>(p.max_edges); temps.push_back(p.edges);
+        p.edge_level = dmalloc<uint32_t>(p.max_edges); temps.push_back(p.edge_level);
+        p.work = dmalloc<uint2>(p.max_edges); temps.push_back(p.work);
+        uint32_t* ctrs = dmalloc<uint32_t>(8); temps.push_back(ctrs);
+        LEANN_CUDA_CHECK(cudaMemset(ctrs, 0, 32));
+        p.edge_count = ctrs; p.work_count = ctrs + 1; p.work_cursor = ctrs + 2; p.counter = ctrs + 3; p.overflow = ctrs + 4;
+        p.M = (uint32_t)M; p.M0 = (uint32_t)M0; p.ef_add = (uint32_t)ef_add; p.n = (uint32_t)n;
+        p.next_cap = (uint32_t)ef_add;
+        p.next_capp = 1; while (p.next_capp < p.next_cap) p.next_capp <<= 1;
+        int max_warps = graph_search_max_warps(ix->device);
+        p.n_pad = (n + 127) & ~(size_t)127;
+        {
+            size_t free_b = 0, total_b = 0;
+            LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            while (max_warps > 64 && (size_t)max_warps * p.n_pad > free_b / 4) max_warps /= 2;
+        }
+        max_warps = (int)std::min<size_t>((size_t)max_warps, (size_t)MAXB);
+        p.visited = dmalloc<uint8_t>((size_t)max_warps * p.n_pad); temps.push_back(p.visited);
+        p.epochs = dmalloc<uint32_t>(max_warps); temps.push_back(p.epochs);
+        LEANN_CUDA_CHECK(cudaMemset(p.visited, 0, (size_t)max_warps * p.n_pad));
+        LEANN_CUDA_CHECK(cudaMemset(p.epochs, 0, (size_t)max_warps * 4));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+
+        size_t inserted = 1;
+        while (inserted < n) {
+            uint32_t b = (uint32_t)std::min<size_t>(std::min<size_t>(n - inserted, MAXB), std::max<size_t>(1, inserted / 16));
+            p.first = (uint32_t)inserted; p.count = b;
+            p.n_warps = (int)std::min<uint32_t>((uint32_t)max_warps, (b + 3u) & ~3u);
+            GraphView g = ix->view();
+            LEANN_CUDA_CHECK(cudaMemsetAsync(ctrs, 0, 16, stream));  // edge_count, work_count, work_cursor, counter
+            dispatch_dims((uint32_t)ix->d, ix->d4, LaunchA{g, p, stream});
+            uint32_t max_e = std::min<uint32_t>(p.max_edges, b * (uint32_t)M * 3u);
+            reverse_append_kernel<<<(max_e + 255) / 256, 256, 0, stream>>>(p);
+            LEANN_CUDA_CHECK(cudaGetLastError());
+            int pblocks = (int)std::min<uint32_t>((uint32_t)sms * 3u, (max_e + 3u) / 4u);
+            dispatch_dims((uint32_t)ix->d, ix->d4, LaunchC{g, p, stream, std::max(pblocks, 1)});
+            // entry point / top level follow the sequential rule of index_gt::add
+            for (size_t i = inserted; i < inserted + b; ++i)
+                if ((int)lv8[i] > ix->max_level) { ix->max_level = lv8[i]; ix->entry = (uint32_t)i; }
+            inserted += b;
+        }
+        uint32_t h_over[2] = {0, 0};
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(h_over, p.overflow, 8, cudaMemcpyDeviceToHost, stream));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (h_over[0]) throw Error(LEANN_ERR_CUDA, "hnsw build: reverse-edge buffer overflow");
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+}  // namespace leann
