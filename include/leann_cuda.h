@@ -196,6 +196,13 @@ int leann_cuda_searcher_search(const leann_cuda_searcher* s, const float* querie
                                size_t nq, size_t top_k, size_t complexity, const char* filter_expr,
                                int hybrid, float alpha, uint64_t* idx, float* scores,
                                uint32_t* counts, char* err, size_t errlen);
+/* IndexSearcher::bm25_search (searcher.rs:228-246): BM25-only top-k passage ordinals + scores. */
+int leann_cuda_searcher_bm25_search(const leann_cuda_searcher* s, const char* query, size_t query_bytes,
+                                    size_t top_k, uint64_t* idx, float* scores, uint32_t* count,
+                                    char* err, size_t errlen);
+/* HnswSearcher discards `complexity` and always searches with ef = 64 (hnsw.rs:49,83); that is the
+ * default here too. on != 0 makes the HNSW backend honour `complexity` as ef. */
+int leann_cuda_searcher_set_honor_complexity(leann_cuda_searcher* s, int on);
 void leann_cuda_searcher_close(leann_cuda_searcher* s);
 
 /* Library / device probe: returns the CUDA device count usable by the library (0 = none). */

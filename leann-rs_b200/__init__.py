@@ -87,6 +87,8 @@ def lib():
         "leann_cuda_searcher_id": (sz, [vp, C.c_uint64, cp, sz]),
         "leann_cuda_searcher_search": (C.c_int, [vp, vp, cpp, szp, sz, sz, sz, cp, C.c_int, C.c_float, vp, vp, vp, cp, sz]),
         "leann_cuda_searcher_close": (None, [vp]),
+        "leann_cuda_searcher_set_honor_complexity": (C.c_int, [vp, C.c_int]),
+        "leann_cuda_searcher_bm25_search": (C.c_int, [vp, cp, sz, sz, vp, vp, vp, cp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name, None)
@@ -358,4 +360,5 @@ def topk_merge_device(keys_in, dists_in, descending: bool = False):
     return keys, dists, counts
 
 
+from . import text  # noqa: E402,F401
 from .text import Bm25Scorer, MetadataFilter, IndexSearcher, SearchOptions, SearchResult, hybrid_rerank, tokenize  # noqa: E402,F401

@@ -183,6 +183,15 @@ void ensure_buf(T*& p, size_t& cap, size_t need) {
 }  // namespace
 
 namespace leann {
+void backend_search_device(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
+                           const uint64_t* d_mask, uint64_t* d_keys, float* d_dists, uint32_t* d_counts, cudaStream_t stream) {
+    search_device_impl(ix, d_queries, nq, k, ef, d_mask, d_mask ? LEANN_MASK_INLINE : LEANN_MASK_NONE, d_keys, d_dists, d_counts,
+                       nullptr, stream);
+}
+cudaStream_t backend_stream(const leann_cuda_index* ix) {
+    if (!ix->ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->ws.stream, cudaStreamNonBlocking));
+    return ix->ws.stream;
+}
 int guard_impl(char* err, size_t errlen, const std::function<void()>& f) {
     auto put = [&](const char* m) { if (err && errlen) { snprintf(err, errlen, "%s", m); } };
     try {

@@ -1,0 +1,355 @@
+// bm25.cu — K3 / K3f: BM25 over a CSR inverted index resident in HBM, BM25 top-k, and the hybrid
+// fusion + post-filter walk of IndexSearcher::search_with_options.
+//   Bm25Scorer::score_query   leann-rs src/index/bm25.rs:77-106   (bm25_token_dense_kernel)
+//   Bm25Scorer::search        src/index/bm25.rs:109-122           (bm25_query_kernel, top-k part)
+//   hybrid_rerank             src/index/bm25.rs:135-170           (hybrid_fuse_kernel)
+//   search_with_options glue  src/index/searcher.rs:146-207       (hybrid_fuse_kernel)
+// The reference re-tokenises and re-indexes every passage on every hybrid query and probes a hash
+// map per (token, document); here the index is built once and a query touches only its postings.
+// Arithmetic is f32 with the reference's operation order and no FMA contraction, so scores are
+// bit-identical: per document the contributions are added in query-token order (tokens are
+// processed one after another; inside one token every posting is a distinct document).
+// Bound: HBM (postings stream). Algorithmic bytes per query = sum_t df_t * 8.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "bm25_dev.h"
+
+namespace leann {
+
+namespace {
+
+constexpr int BM_THREADS = 256;
+constexpr int BM_CAP = 4096;      // candidate keys held in shared memory between prunes
+constexpr int BM_CHUNK = 1024;    // postings examined per block step (4 per thread)
+
+__device__ __forceinline__ uint32_t order_f32(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(uint32_t u) {
+    u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+
+// bm25.rs:97-100 with norm precomputed: score = idf * (tf * (K1 + 1)) / (tf + K1 * norm)
+__device__ __forceinline__ float bm25_term(float idf, float tf, float norm) {
+    const float K1 = 1.2f;
+    const float K1P1 = __fadd_rn(K1, 1.0f);
+    float num = __fmul_rn(idf, __fmul_rn(tf, K1P1));
+    float den = __fadd_rn(tf, __fmul_rn(K1, norm));
+    return __fdiv_rn(num, den);
+}
+
+__global__ void bm25_token_dense_kernel(Bm25Dev b, uint32_t term, float* __restrict__ scores) {
+    uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
+    uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    uint32_t doc = b.post_doc[p];
+    float s = bm25_term(b.idf[term], (float)b.post_tf[p], b.norm[doc]);
+    scores[doc] = __fadd_rn(scores[doc], s);
+}
+
+__device__ void block_sort_4096(unsigned long long* keys) {
+    const uint32_t n = BM_CAP;
+    for (uint32_t size = 2; size <= n; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                unsigned long long a = keys[lo], c = keys[hi];
+                if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+            }
+        }
+    __syncthreads();
+}
+
+// One CTA per query (persistent). acc: this CTA's dense f32 accumulator [n_docs], all zero on entry
+// and restored to zero on exit.
+__global__ void __launch_bounds__(BM_THREADS)
+bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32_t* __restrict__ qtok_term,
+                  uint32_t nq, uint32_t K, float* __restrict__ acc_all, const uint64_t* __restrict__ cand_idx,
+                  const uint32_t* __restrict__ cand_cnt, uint32_t fk, float* __restrict__ cand_bm,
+                  uint64_t* __restrict__ top_idx, float* __restrict__ top_score, uint32_t* __restrict__ top_cnt,
+                  float* __restrict__ bmax, float* __restrict__ bmin, uint32_t* __restrict__ qcounter) {
+    __shared__ unsigned long long buf[BM_CAP];
+    __shared__ uint32_t s_cnt, s_q, s_pos, s_minbits;
+    __shared__ unsigned long long s_thr;
+    float* acc = acc_all + (size_t)blockIdx.x * b.n_docs;
+    const int tid = threadIdx.x;
+
+    auto prune = [&]() {  // all threads; keeps the K best keys and tightens the threshold
+        __syncthreads();
+        uint32_t c = s_cnt;
+        for (uint32_t i = c + tid; i < BM_CAP; i += BM_THREADS) buf[i] = ~0ull;
+        block_sort_4096(buf);
+        if (tid == 0) {
+            uint32_t keep = c < K ? c : K;
+            s_cnt = keep;
+            if (keep == K) s_thr = buf[K - 1];
+        }
+        __syncthreads();
+    };
+
+    for (;;) {
+        if (tid == 0) s_q = atomicAdd(qcounter, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= nq) break;
+        const uint64_t t0 = qtok_off[q], t1 = qtok_off[q + 1];
+        // ---- pass 1: accumulate, tokens in query order (duplicates counted again, bm25.rs:81) ----
+        for (uint64_t t = t0; t < t1; ++t) {
+            const uint32_t term = qtok_term[t];
+            const float idf = b.idf[term];
+            const uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
+            for (uint64_t p = p0 + tid; p < p1; p += BM_THREADS) {
+                uint32_t doc = b.post_doc[p];
+                float s = bm25_term(idf, (float)b.post_tf[p], b.norm[doc]);
+                acc[doc] = __fadd_rn(acc[doc], s);
+            }
+            __syncthreads();
+        }
+        // ---- BM25 score of the vector candidates (bm25_scores.get(idx).unwrap_or(0.0), bm25.rs:160) ----
+        if (cand_idx) {
+            uint32_t nc = cand_cnt[q];
+            for (uint32_t j = tid; j < nc; j += BM_THREADS) {
+                uint64_t idx = cand_idx[(size_t)q * fk + j];
+                cand_bm[(size_t)q * fk + j] = idx < b.n_docs ? acc[idx] : 0.0f;
+            }
+        }
+        if (tid == 0) { s_cnt = 0; s_thr = ~0ull; s_pos = 0; s_minbits = 0xFFFFFFFFu; }
+        __syncthreads();
+        // ---- pass 2: collect positives (score > 0, bm25.rs:115), zero the accumulator ----
+        uint32_t my_pos = 0, my_min = 0xFFFFFFFFu;
+        for (uint64_t t = t0; t < t1; ++t) {
+            const uint32_t term = qtok_term[t];
+            const uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
+            for (uint64_t base = p0; base < p1; base += BM_CHUNK) {
+                if (s_cnt > BM_CAP - BM_CHUNK) prune();
+                const unsigned long long thr = s_thr;
+#pragma unroll
+                for (int i = 0; i < BM_CHUNK / BM_THREADS; ++i) {
+                    uint64_t p = base + tid + (uint64_t)i * BM_THREADS;
+                    if (p < p1) {
+                        uint32_t doc = b.post_doc[p];
+                        float v = acc[doc];
+                        if (v != 0.0f) {
+                            acc[doc] = 0.0f;
+                            if (v > 0.0f) {
+                                my_pos++;
+                                uint32_t o = order_f32(v);
+                                my_min = o < my_min ? o : my_min;
+                                unsigned long long key = ((unsigned long long)(~o) << 32) | doc;
+                                if (key <= thr) buf[atomicAdd(&s_cnt, 1u)] = key;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        atomicAdd(&s_pos, my_pos);
+        atomicMin(&s_minbits, my_min);
+        prune();
+        const uint32_t cnt = s_cnt;
+        for (uint32_t j = tid; j < K; j += BM_THREADS) {
+            size_t o = (size_t)q * K + j;
+            if (j < cnt) {
+                unsigned long long key = buf[j];
+                top_idx[o] = (uint64_t)(key & 0xFFFFFFFFull);
+                top_score[o] = unorder_f32(~(uint32_t)(key >> 32));
+            } else {
+                top_idx[o] = ~0ull;
+                top_score[o] = 0.0f;
+            }
+        }
+        if (tid == 0) {
+            top_cnt[q] = cnt;
+            // bm25.rs:152-153: max / min over the ENTIRE dense score vector (zeros included)
+            float mx = cnt ? unorder_f32(~(uint32_t)(buf[0] >> 32)) : 0.0f;
+            float mn = (s_pos < b.n_docs) ? 0.0f : unorder_f32(s_minbits);
+            if (b.n_docs == 0) { mx = -CUDART_INF_F; mn = CUDART_INF_F; }
+            bmax[q] = mx;
+            bmin[q] = mn;
+        }
+        __syncthreads();
+    }
+}
+
+// searcher.rs:146-207 + bm25.rs:135-170 for one query per block.
+__global__ void __launch_bounds__(128)
+hybrid_fuse_kernel(const uint64_t* __restrict__ vkeys, const float* __restrict__ vdists, const uint32_t* __restrict__ vcnt,
+                   uint32_t fk, const float* __restrict__ cand_bm, const uint64_t* __restrict__ bm_idx,
+                   const float* __restrict__ bm_score, const uint32_t* __restrict__ bm_cnt, uint32_t bm_k,
+                   const float* __restrict__ bmax, const float* __restrict__ bmin, int hybrid, float alpha,
+                   const uint64_t* __restrict__ mask, uint64_t mask_bits, uint32_t top_k, uint64_t* __restrict__ out_idx,
+                   float* __restrict__ out_score, uint32_t* __restrict__ out_cnt, uint32_t nq, uint32_t cap) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint64_t* idx = reinterpret_cast<uint64_t*>(sm);                       // [cap]
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm + (size_t)cap * 8);  // [n2 <= 2*cap pow2]
+    float* vs = reinterpret_cast<float*>(sm + (size_t)cap * 8 + (size_t)2 * cap * 8);  // [cap]
+    float* bs = vs + cap;                                                  // [cap]
+    uint8_t* fresh = reinterpret_cast<uint8_t*>(bs + cap);                 // [bm_k]
+    __shared__ uint32_t s_len, s_vmin, s_vmax;
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const int tid = threadIdx.x;
+    const uint32_t nv = vcnt[q];
+    for (uint32_t i = tid; i < nv; i += blockDim.x) {
+        idx[i] = vkeys[(size_t)q * fk + i];
+        vs[i] = vdists[(size_t)q * fk + i];
+        bs[i] = (hybrid && cand_bm) ? cand_bm[(size_t)q * fk + i] : 0.0f;
+    }
+    if (tid == 0) { s_len = nv; s_vmin = 0xFFFFFFFFu; s_vmax = 0u; }
+    __syncthreads();
+    uint32_t len = nv;
+    if (hybrid) {
+        // BM25 top results not already among the vector results enter with vector score 0.0
+        const uint32_t nb = bm_cnt[q];
+        for (uint32_t j = tid; j < nb; j += blockDim.x) {
+            uint64_t d = bm_idx[(size_t)q * bm_k + j];
+            bool present = false;
+            for (uint32_t i = 0; i < nv; ++i) if (idx[i] == d) { present = true; break; }
+            fresh[j] = present ? 0 : 1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t l = nv;
+            for (uint32_t j = 0; j < nb && l < cap; ++j)
+                if (fresh[j]) { idx[l] = bm_idx[(size_t)q * bm_k + j]; vs[l] = 0.0f; bs[l] = bm_score[(size_t)q * bm_k + j]; ++l; }
+            s_len = l;
+        }
+        __syncthreads();
+        len = s_len;
+        for (uint32_t i = tid; i < len; i += blockDim.x) {
+            uint32_t o = order_f32(vs[i]);
+            atomicMin(&s_vmin, o);
+            atomicMax(&s_vmax, o);
+        }
+        __syncthreads();
+        // fold(NEG_INFINITY, max) / fold(INFINITY, min): an empty list leaves the infinities in place
+        const float vmax = len ? unorder_f32(s_vmax) : -CUDART_INF_F;
+        const float vmin = len ? unorder_f32(s_vmin) : CUDART_INF_F;
+        const float vr = fmaxf(__fsub_rn(vmax, vmin), 1e-6f);
+        const float bmn = bmin[q];
+        const float br = fmaxf(__fsub_rn(bmax[q], bmn), 1e-6f);
+        const float one_minus = __fsub_rn(1.0f, alpha);
+        for (uint32_t i = tid; i < len; i += blockDim.x) {
+            float nvv = __fdiv_rn(__fsub_rn(vs[i], vmin), vr);
+            float nbv = __fdiv_rn(__fsub_rn(bs[i], bmn), br);
+            vs[i] = __fadd_rn(__fmul_rn(alpha, nvv), __fmul_rn(one_minus, nbv));
+        }
+        __syncthreads();
+        // stable descending sort: key = (~ordered(score), position)
+        uint32_t n2 = 1;
+        while (n2 < len) n2 <<= 1;
+        for (uint32_t i = tid; i < n2; i += blockDim.x)
+            keys[i] = i < len ? (((unsigned long long)(~order_f32(vs[i])) << 32) | i) : ~0ull;
+        for (uint32_t size = 2; size <= n2; size <<= 1)
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (uint32_t t = tid; t < n2 / 2; t += blockDim.x) {
+                    uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    bool up = ((lo & size) == 0);
+                    unsigned long long a = keys[lo], c = keys[hi];
+                    if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+                }
+            }
+        __syncthreads();
+    } else {
+        for (uint32_t i = tid; i < len; i += blockDim.x) keys[i] = i;
+        __syncthreads();
+    }
+    // post-filter walk (searcher.rs:174-207): take in rank order until top_k pass
+    if (tid == 0) {
+        uint32_t o = 0;
+        for (uint32_t r = 0; r < len && o < top_k; ++r) {
+            uint32_t pos = (uint32_t)(keys[r] & 0xFFFFFFFFull);
+            uint64_t d = idx[pos];
+            if (mask && !(d < mask_bits && ((mask[d >> 6] >> (d & 63ull)) & 1ull))) continue;
+            out_idx[(size_t)q * top_k + o] = d;
+            out_score[(size_t)q * top_k + o] = vs[pos];
+            ++o;
+        }
+        out_cnt[q] = o;
+        for (; o < top_k; ++o) { out_idx[(size_t)q * top_k + o] = ~0ull; out_score[(size_t)q * top_k + o] = 0.0f; }
+    }
+}
+
+// min / max over a dense f32 vector (for the stand-alone hybrid_rerank entry point)
+__global__ void minmax_kernel(const float* __restrict__ v, uint32_t n, uint32_t* __restrict__ out /*[min,max] ordered*/) {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t o = order_f32(v[i]);
+        mn = o < mn ? o : mn;
+        mx = o > mx ? o : mx;
+    }
+    for (int off = 16; off; off >>= 1) {
+        uint32_t a = __shfl_xor_sync(0xFFFFFFFFu, mn, off), c = __shfl_xor_sync(0xFFFFFFFFu, mx, off);
+        mn = a < mn ? a : mn;
+        mx = c > mx ? c : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], mn); atomicMax(&out[1], mx); }
+}
+__global__ void minmax_finish_kernel(const uint32_t* in, uint32_t n, float* bmax, float* bmin) {
+    if (n == 0) { *bmax = -CUDART_INF_F; *bmin = CUDART_INF_F; return; }
+    *bmin = unorder_f32(in[0]);
+    *bmax = unorder_f32(in[1]);
+}
+__global__ void gather_kernel(const float* __restrict__ dense, uint32_t n, const uint64_t* __restrict__ idx, uint32_t m, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = idx[i] < n ? dense[idx[i]] : 0.0f;
+}
+
+}  // namespace
+
+void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
+                       cudaStream_t s) {
+    for (size_t i = 0; i < n_tokens; ++i) {
+        if (dfs[i] == 0) continue;
+        unsigned blocks = (unsigned)((dfs[i] + 255) / 256);
+        bm25_token_dense_kernel<<<blocks, 256, 0, s>>>(b, terms[i], d_scores);
+    }
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
+                       float* acc_all, int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
+                       float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,
+                       uint32_t* qcounter, cudaStream_t s) {
+    if (K == 0 || K > 1024) throw Error(LEANN_ERR_INVALID_ARG, "bm25: top_k must be in 1..1024");
+    LEANN_CUDA_CHECK(cudaMemsetAsync(qcounter, 0, 4, s));
+    bm25_query_kernel<<<n_ctas, BM_THREADS, 0, s>>>(b, qtok_off, qtok_term, nq, K, acc_all, cand_idx, cand_cnt, fk, cand_bm,
+                                                     top_idx, top_score, top_cnt, bmax, bmin, qcounter);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, uint32_t fk, const float* cand_bm,
+                        const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, uint32_t bm_k,
+                        const float* bmax, const float* bmin, int hybrid, float alpha, const uint64_t* mask, uint64_t mask_bits,
+                        uint32_t top_k, uint64_t* out_idx, float* out_score, uint32_t* out_cnt, uint32_t nq, cudaStream_t s) {
+    if (nq == 0) return;
+    uint32_t cap = fk + (hybrid ? bm_k : 0);
+    if (cap == 0) cap = 1;
+    if (cap > 4096) throw Error(LEANN_ERR_INVALID_ARG, "hybrid: fetch_k too large (top_k <= 400)");
+    uint32_t n2 = 1;
+    while (n2 < cap) n2 <<= 1;
+    size_t smem = (size_t)cap * 8 + (size_t)2 * cap * 8 + (size_t)cap * 8 + bm_k + 16;
+    if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(hybrid_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hybrid_fuse_kernel<<<nq, 128, smem, s>>>(vkeys, vdists, vcnt, fk, cand_bm, bm_idx, bm_score, bm_cnt, bm_k, bmax, bmin, hybrid,
+                                             alpha, mask, mask_bits, top_k, out_idx, out_score, out_cnt, nq, cap);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_dense_minmax_gather(const float* dense, uint32_t n, const uint64_t* idx, uint32_t m, float* cand_bm, float* bmax,
+                                float* bmin, uint32_t* scratch2, cudaStream_t s) {
+    uint32_t init[2] = {0xFFFFFFFFu, 0u};
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(scratch2, init, 8, cudaMemcpyHostToDevice, s));
+    if (n) minmax_kernel<<<296, 256, 0, s>>>(dense, n, scratch2);
+    minmax_finish_kernel<<<1, 1, 0, s>>>(scratch2, n, bmax, bmin);
+    if (m) gather_kernel<<<(m + 255) / 256, 256, 0, s>>>(dense, n, idx, m, cand_bm);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace leann

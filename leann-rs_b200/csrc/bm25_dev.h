@@ -1,0 +1,52 @@
+// bm25_dev.h — device view of the BM25 inverted index and kernel launchers (bm25.cu).
+#pragma once
+#include "internal.h"
+#include "text.h"
+
+namespace leann {
+
+struct Bm25Dev {
+    uint32_t n_docs;
+    const uint64_t* term_off;  // [n_terms + 1]
+    const uint32_t* post_doc;  // [n_postings] ascending inside a term
+    const uint32_t* post_tf;   // [n_postings]
+    const float* idf;          // [n_terms]
+    const float* norm;         // [n_docs]
+};
+
+void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
+                       cudaStream_t s);
+void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
+                       float* acc_all, int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
+                       float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,
+                       uint32_t* qcounter, cudaStream_t s);
+void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, uint32_t fk, const float* cand_bm,
+                        const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, uint32_t bm_k,
+                        const float* bmax, const float* bmin, int hybrid, float alpha, const uint64_t* mask, uint64_t mask_bits,
+                        uint32_t top_k, uint64_t* out_idx, float* out_score, uint32_t* out_cnt, uint32_t nq, cudaStream_t s);
+void launch_dense_minmax_gather(const float* dense, uint32_t n, const uint64_t* idx, uint32_t m, float* cand_bm, float* bmax,
+                                float* bmin, uint32_t* scratch2, cudaStream_t s);
+
+// search entry shared between api.cu and text_api.cu: enqueue a backend search with device buffers
+void backend_search_device(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
+                           const uint64_t* d_mask, uint64_t* d_keys, float* d_dists, uint32_t* d_counts, cudaStream_t stream);
+cudaStream_t backend_stream(const leann_cuda_index* ix);
+
+}  // namespace leann
+
+struct leann_cuda_bm25 {
+    int device = 0;
+    leann::Bm25Host host;
+    uint64_t* d_term_off = nullptr;
+    uint32_t* d_post_doc = nullptr;
+    uint32_t* d_post_tf = nullptr;
+    float* d_idf = nullptr;
+    float* d_norm = nullptr;
+    // per-handle workspace
+    mutable std::mutex mu;
+    mutable float* d_acc = nullptr;   // [n_ctas][n_docs], zero between calls
+    mutable int n_ctas = 0;
+    mutable uint32_t* d_qcounter = nullptr;
+    mutable cudaStream_t stream = nullptr;
+    leann::Bm25Dev view() const { return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_tf, d_idf, d_norm}; }
+};

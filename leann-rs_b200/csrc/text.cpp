@@ -1,0 +1,516 @@
+// text.cpp — host side of the text path:
+//   tokenize            index/bm25.rs:127-132   regex [a-zA-Z0-9]+, lower-case, drop byte length <= 1
+//   bm25_build_host     index/bm25.rs:33-74     same statistics as Bm25Scorer::build, stored inverted (CSR)
+//   filter_parse        index/filter.rs:52-134, 137-316, 420-439
+//   filter_matches      index/filter.rs:319-418
+//   json_parse          serde_json::Value stand-in (metadata documents of index/passages.rs:12-17)
+#include "text.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace leann {
+
+// ================================= JSON =================================
+namespace {
+struct JP {
+    const char* p; const char* e; std::string err;
+    void ws() { while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
+    bool fail(const char* m) { if (err.empty()) err = m; return false; }
+    static void utf8(std::string& o, uint32_t c) {
+        if (c < 0x80) o += (char)c;
+        else if (c < 0x800) { o += (char)(0xC0 | (c >> 6)); o += (char)(0x80 | (c & 63)); }
+        else if (c < 0x10000) { o += (char)(0xE0 | (c >> 12)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
+        else { o += (char)(0xF0 | (c >> 18)); o += (char)(0x80 | ((c >> 12) & 63)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
+    }
+    bool hex4(uint32_t& v) {
+        if (e - p < 4) return fail("bad \\u escape");
+        v = 0;
+        for (int i = 0; i < 4; ++i) {
+            char c = *p++;
+            v <<= 4;
+            if (c >= '0' && c <= '9') v |= c - '0';
+            else if (c >= 'a' && c <= 'f') v |= c - 'a' + 10;
+            else if (c >= 'A' && c <= 'F') v |= c - 'A' + 10;
+            else return fail("bad \\u escape");
+        }
+        return true;
+    }
+    bool str(std::string& o) {
+        if (p >= e || *p != '"') return fail("expected string");
+        ++p;
+        while (p < e && *p != '"') {
+            if (*p == '\\') {
+                if (++p >= e) return fail("bad escape");
+                char c = *p++;
+                switch (c) {
+                    case '"': o += '"'; break; case '\\': o += '\\'; break; case '/': o += '/'; break;
+                    case 'b': o += '\b'; break; case 'f': o += '\f'; break; case 'n': o += '\n'; break;
+                    case 'r': o += '\r'; break; case 't': o += '\t'; break;
+                    case 'u': {
+                        uint32_t c1;
+                        if (!hex4(c1)) return false;
+                        if (c1 >= 0xD800 && c1 < 0xDC00 && e - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+                            p += 2;
+                            uint32_t c2;
+                            if (!hex4(c2)) return false;
+                            c1 = 0x10000 + ((c1 - 0xD800) << 10) + (c2 - 0xDC00);
+                        }
+                        utf8(o, c1);
+                        break;
+                    }
+                    default: return fail("bad escape");
+                }
+            } else {
+                o += *p++;
+            }
+        }
+        if (p >= e) return fail("unterminated string");
+        ++p;
+        return true;
+    }
+    bool val(Json& v, int depth) {
+        if (depth > 128) return fail("nesting too deep");
+        ws();
+        if (p >= e) return fail("unexpected end");
+        char c = *p;
+        if (c == '{') {
+            ++p; v.kind = Json::Obj; ws();
+            if (p < e && *p == '}') { ++p; return true; }
+            for (;;) {
+                ws();
+                std::string k;
+                if (!str(k)) return false;
+                ws();
+                if (p >= e || *p != ':') return fail("expected ':'");
+                ++p;
+                Json child;
+                if (!val(child, depth + 1)) return false;
+                // serde_json maps keep the last value of a duplicated key
+                bool rep = false;
+                for (auto& kv : v.obj) if (kv.first == k) { kv.second = std::move(child); rep = true; break; }
+                if (!rep) v.obj.emplace_back(std::move(k), std::move(child));
+                ws();
+                if (p < e && *p == ',') { ++p; continue; }
+                if (p < e && *p == '}') { ++p; return true; }
+                return fail("expected ',' or '}'");
+            }
+        }
+        if (c == '[') {
+            ++p; v.kind = Json::Arr; ws();
+            if (p < e && *p == ']') { ++p; return true; }
+            for (;;) {
+                Json child;
+                if (!val(child, depth + 1)) return false;
+                v.arr.push_back(std::move(child));
+                ws();
+                if (p < e && *p == ',') { ++p; continue; }
+                if (p < e && *p == ']') { ++p; return true; }
+                return fail("expected ',' or ']'");
+            }
+        }
+        if (c == '"') { v.kind = Json::Str; return str(v.str); }
+        if (e - p >= 4 && !memcmp(p, "true", 4)) { p += 4; v.kind = Json::Bool; v.b = true; return true; }
+        if (e - p >= 5 && !memcmp(p, "false", 5)) { p += 5; v.kind = Json::Bool; v.b = false; return true; }
+        if (e - p >= 4 && !memcmp(p, "null", 4)) { p += 4; v.kind = Json::Null; return true; }
+        if (c == '-' || (c >= '0' && c <= '9')) {
+            const char* s = p;
+            bool isint = true;
+            if (*p == '-') ++p;
+            while (p < e && *p >= '0' && *p <= '9') ++p;
+            if (p < e && *p == '.') { isint = false; ++p; while (p < e && *p >= '0' && *p <= '9') ++p; }
+            if (p < e && (*p == 'e' || *p == 'E')) { isint = false; ++p; if (p < e && (*p == '+' || *p == '-')) ++p; while (p < e && *p >= '0' && *p <= '9') ++p; }
+            std::string t(s, p);
+            v.kind = Json::Num; v.is_int = isint; v.num = strtod(t.c_str(), nullptr);
+            return true;
+        }
+        return fail("unexpected character");
+    }
+};
+
+void dump_str(std::string& o, const std::string& s) {
+    o += '"';
+    for (unsigned char c : s) {
+        if (c == '"') o += "\\\"";
+        else if (c == '\\') o += "\\\\";
+        else if (c == '\n') o += "\\n";
+        else if (c == '\r') o += "\\r";
+        else if (c == '\t') o += "\\t";
+        else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+        else o += (char)c;
+    }
+    o += '"';
+}
+void dump(std::string& o, const Json& v) {
+    switch (v.kind) {
+        case Json::Null: o += "null"; break;
+        case Json::Bool: o += v.b ? "true" : "false"; break;
+        case Json::Num: {
+            char b[40];
+            if (v.is_int && std::fabs(v.num) < 9.2e18) snprintf(b, sizeof b, "%lld", (long long)v.num);
+            else snprintf(b, sizeof b, "%.17g", v.num);
+            o += b;
+            break;
+        }
+        case Json::Str: dump_str(o, v.str); break;
+        case Json::Arr: o += '['; for (size_t i = 0; i < v.arr.size(); ++i) { if (i) o += ','; dump(o, v.arr[i]); } o += ']'; break;
+        case Json::Obj: o += '{'; for (size_t i = 0; i < v.obj.size(); ++i) { if (i) o += ','; dump_str(o, v.obj[i].first); o += ':'; dump(o, v.obj[i].second); } o += '}'; break;
+    }
+}
+}  // namespace
+
+const Json* Json::get(const std::string& key) const {
+    if (kind != Obj) return nullptr;
+    for (auto& kv : obj) if (kv.first == key) return &kv.second;
+    return nullptr;
+}
+bool json_parse(const char* s, size_t n, Json& out, std::string& err) {
+    JP jp{s, s + n, {}};
+    out = Json();
+    if (!jp.val(out, 0)) { err = jp.err; return false; }
+    jp.ws();
+    if (jp.p != jp.e) { err = "trailing characters"; return false; }
+    return true;
+}
+std::string json_dump(const Json& v) { std::string o; dump(o, v); return o; }
+
+// ================================= tokenizer =================================
+void tokenize(const char* text, size_t n, std::vector<std::string>& out) {
+    out.clear();
+    size_t i = 0;
+    auto alnum = [](unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9'); };
+    while (i < n) {
+        while (i < n && !alnum((unsigned char)text[i])) ++i;
+        size_t s = i;
+        while (i < n && alnum((unsigned char)text[i])) ++i;
+        if (i - s > 1) {  // .filter(|s| s.len() > 1)
+            std::string t(text + s, i - s);
+            for (auto& c : t) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+            out.push_back(std::move(t));
+        }
+    }
+}
+
+// ================================= BM25 build =================================
+void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& o) {
+    const float K1 = 1.2f, B = 0.75f;
+    (void)K1;
+    o = Bm25Host();
+    o.num_docs = n_docs;
+    o.doc_len.resize(n_docs);
+    std::vector<uint32_t> df;
+    std::vector<std::pair<uint32_t, uint32_t>> doc_terms;  // flattened (term, tf) per doc
+    std::vector<uint64_t> doc_off(n_docs + 1, 0);
+    std::vector<std::string> toks;
+    std::vector<uint32_t> ids;
+    for (size_t d = 0; d < n_docs; ++d) {
+        tokenize(docs[d], doc_bytes[d], toks);
+        o.doc_len[d] = (uint32_t)toks.size();
+        o.total_tokens += toks.size();
+        ids.clear();
+        for (auto& t : toks) {
+            auto it = o.dict.find(t);
+            uint32_t id;
+            if (it == o.dict.end()) { id = (uint32_t)o.dict.size(); o.dict.emplace(t, id); df.push_back(0); }
+            else id = it->second;
+            ids.push_back(id);
+        }
+        std::sort(ids.begin(), ids.end());
+        for (size_t i = 0; i < ids.size();) {
+            size_t j = i;
+            while (j < ids.size() && ids[j] == ids[i]) ++j;
+            doc_terms.emplace_back(ids[i], (uint32_t)(j - i));
+            df[ids[i]]++;
+            i = j;
+        }
+        doc_off[d + 1] = doc_terms.size();
+    }
+    // bm25.rs:61-65
+    o.avg_doc_len = n_docs > 0 ? (float)o.total_tokens / (float)n_docs : 1.0f;
+    size_t nt = df.size();
+    o.term_off.assign(nt + 1, 0);
+    for (size_t t = 0; t < nt; ++t) o.term_off[t + 1] = o.term_off[t] + df[t];
+    o.post_doc.resize(doc_terms.size());
+    o.post_tf.resize(doc_terms.size());
+    std::vector<uint64_t> cur(o.term_off.begin(), o.term_off.end() - 1);
+    for (size_t d = 0; d < n_docs; ++d)
+        for (uint64_t i = doc_off[d]; i < doc_off[d + 1]; ++i) {
+            uint64_t pos = cur[doc_terms[i].first]++;
+            o.post_doc[pos] = (uint32_t)d;
+            o.post_tf[pos] = doc_terms[i].second;
+        }
+    // bm25.rs:88  idf = ((N - df + 0.5) / (df + 0.5) + 1.0).ln()   — all f32
+    o.idf.resize(nt);
+    const float Nf = (float)n_docs;
+    for (size_t t = 0; t < nt; ++t) {
+        float dff = (float)df[t];
+        volatile float a = Nf - dff;
+        volatile float num = a + 0.5f;
+        volatile float den = dff + 0.5f;
+        volatile float r = num / den;
+        volatile float s = r + 1.0f;
+        o.idf[t] = logf(s);
+    }
+    // bm25.rs:96-97  norm = 1.0 - B + B * (doc_len / avg_doc_len)
+    o.norm.resize(n_docs);
+    for (size_t d = 0; d < n_docs; ++d) {
+        volatile float ratio = (float)o.doc_len[d] / o.avg_doc_len;
+        volatile float m = B * ratio;
+        volatile float base = 1.0f - B;
+        o.norm[d] = base + m;
+    }
+}
+
+// ================================= filter =================================
+namespace {
+std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    auto sp = [](unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };
+    while (a < b && sp((unsigned char)s[a])) ++a;
+    while (b > a && sp((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+std::vector<std::string> split(const std::string& s, const std::string& sep) {
+    std::vector<std::string> out;
+    size_t pos = 0;
+    for (;;) {
+        size_t f = s.find(sep, pos);
+        if (f == std::string::npos) { out.push_back(s.substr(pos)); break; }
+        out.push_back(s.substr(pos, f - pos));
+        pos = f + sep.size();
+    }
+    return out;
+}
+bool parse_i64(const std::string& s, long long& v) {  // Rust i64::from_str: [+-]?[0-9]+ with overflow check
+    if (s.empty()) return false;
+    size_t i = 0;
+    bool neg = false;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+    if (i >= s.size()) return false;
+    unsigned long long acc = 0;
+    const unsigned long long lim = neg ? 9223372036854775808ull : 9223372036854775807ull;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        unsigned d = s[i] - '0';
+        if (acc > (lim - d) / 10) return false;
+        acc = acc * 10 + d;
+    }
+    v = neg ? (long long)(0ull - acc) : (long long)acc;
+    return true;
+}
+bool parse_f64(const std::string& s, double& v) {  // Rust f64::from_str grammar; non-finite rejected by Number::from_f64
+    if (s.empty()) return false;
+    size_t i = 0;
+    if (s[i] == '+' || s[i] == '-') ++i;
+    std::string rest = s.substr(i);
+    std::string low = rest;
+    for (auto& c : low) c = (char)tolower((unsigned char)c);
+    if (low == "inf" || low == "infinity" || low == "nan") return false;  // parses, but from_f64 -> None
+    size_t digits = 0, j = i;
+    while (j < s.size() && isdigit((unsigned char)s[j])) { ++j; ++digits; }
+    if (j < s.size() && s[j] == '.') { ++j; while (j < s.size() && isdigit((unsigned char)s[j])) { ++j; ++digits; } }
+    if (digits == 0) return false;
+    if (j < s.size() && (s[j] == 'e' || s[j] == 'E')) {
+        ++j;
+        if (j < s.size() && (s[j] == '+' || s[j] == '-')) ++j;
+        size_t ed = 0;
+        while (j < s.size() && isdigit((unsigned char)s[j])) { ++j; ++ed; }
+        if (ed == 0) return false;
+    }
+    if (j != s.size()) return false;
+    v = strtod(s.c_str(), nullptr);
+    return std::isfinite(v);
+}
+Json parse_value(const std::string& s) {  // filter.rs:420-439
+    Json v;
+    long long iv;
+    if (parse_i64(s, iv)) { v.kind = Json::Num; v.num = (double)iv; v.is_int = true; return v; }
+    double dv;
+    if (parse_f64(s, dv)) { v.kind = Json::Num; v.num = dv; v.is_int = false; return v; }
+    if (s == "true") { v.kind = Json::Bool; v.b = true; return v; }
+    if (s == "false") { v.kind = Json::Bool; v.b = false; return v; }
+    v.kind = Json::Str; v.str = s;
+    return v;
+}
+Json jstr(const std::string& s) { Json v; v.kind = Json::Str; v.str = s; return v; }
+bool cond(FilterNode& out, const std::string& field, FilterOp op, Json value) {
+    out = FilterNode();
+    out.kind = FilterNode::Condition; out.field = field; out.op = op; out.value = std::move(value);
+    return true;
+}
+bool contains(const std::string& s, const char* t) { return s.find(t) != std::string::npos; }
+bool splitn2(const std::string& s, const std::string& sep, std::string& a, std::string& b) {
+    size_t f = s.find(sep);
+    if (f == std::string::npos) return false;
+    a = s.substr(0, f); b = s.substr(f + sep.size());
+    return true;
+}
+
+bool parse_single(const std::string& in, FilterNode& out) {  // filter.rs:137-316
+    std::string s = trim(in);
+    if (!s.empty() && s.back() == '?') return cond(out, s.substr(0, s.size() - 1), FilterOp::Exists, Json());
+    for (int pass = 0; pass < 2; ++pass) {
+        const char* key = pass == 0 ? " in [" : " not_in [";
+        size_t klen = strlen(key);
+        size_t idx = s.find(key);
+        if (idx != std::string::npos) {
+            std::string field = trim(s.substr(0, idx));
+            std::string rest = s.substr(idx + klen);
+            size_t end = rest.find(']');
+            if (end != std::string::npos) {
+                Json arr; arr.kind = Json::Arr;
+                for (auto& v : split(rest.substr(0, end), ",")) arr.arr.push_back(parse_value(trim(v)));
+                return cond(out, field, pass == 0 ? FilterOp::In : FilterOp::NotIn, std::move(arr));
+            }
+        }
+    }
+    std::string a, b;
+    if (contains(s, "~")) { splitn2(s, "~", a, b); return cond(out, a, FilterOp::Contains, jstr(b)); }
+    if (contains(s, "^") && !contains(s, ">=")) { splitn2(s, "^", a, b); return cond(out, a, FilterOp::StartsWith, jstr(b)); }
+    if (contains(s, "$")) { splitn2(s, "$", a, b); return cond(out, a, FilterOp::EndsWith, jstr(b)); }
+    if (contains(s, "!=")) { splitn2(s, "!=", a, b); return cond(out, a, FilterOp::Ne, parse_value(b)); }
+    if (contains(s, ">=")) { splitn2(s, ">=", a, b); return cond(out, a, FilterOp::Gte, parse_value(b)); }
+    if (contains(s, "<=")) { splitn2(s, "<=", a, b); return cond(out, a, FilterOp::Lte, parse_value(b)); }
+    if (contains(s, ">")) { splitn2(s, ">", a, b); return cond(out, a, FilterOp::Gt, parse_value(b)); }
+    if (contains(s, "<")) { splitn2(s, "<", a, b); return cond(out, a, FilterOp::Lt, parse_value(b)); }
+    if (contains(s, "=")) splitn2(s, "=", a, b);
+    else if (contains(s, ":")) splitn2(s, ":", a, b);
+    else return false;
+    const std::string& value = b;
+    if (contains(value, "*")) {
+        bool st = value.front() == '*', en = value.back() == '*';
+        if (st && en && value.size() > 2) return cond(out, a, FilterOp::Contains, jstr(value.substr(1, value.size() - 2)));
+        if (st) return cond(out, a, FilterOp::EndsWith, jstr(value.substr(1)));
+        if (en) return cond(out, a, FilterOp::StartsWith, jstr(value.substr(0, value.size() - 1)));
+    }
+    return cond(out, a, FilterOp::Eq, parse_value(value));
+}
+
+const Json* nested(const Json& md, const std::string& path) {  // filter.rs:376-388
+    const Json* cur = &md;
+    for (auto& part : split(path, ".")) {
+        cur = cur->get(part);
+        if (!cur) return nullptr;
+    }
+    return cur;
+}
+bool values_equal(const Json& a, const Json& b) {  // filter.rs:390-400
+    if (a.kind == Json::Str && b.kind == Json::Str) return a.str == b.str;
+    if (a.kind == Json::Num && b.kind == Json::Num) return std::fabs(a.num - b.num) < 2.220446049250313e-16;
+    if (a.kind == Json::Bool && b.kind == Json::Bool) return a.b == b.b;
+    if (a.kind == Json::Null && b.kind == Json::Null) return true;
+    return false;
+}
+int compare_values(const Json& a, const Json& b) {  // filter.rs:402-418
+    if (a.kind == Json::Num && b.kind == Json::Num) return a.num < b.num ? -1 : (a.num > b.num ? 1 : 0);
+    if (a.kind == Json::Str && b.kind == Json::Str) { int c = a.str.compare(b.str); return c < 0 ? -1 : (c > 0 ? 1 : 0); }
+    return 0;
+}
+bool cond_matches(const FilterNode& c, const Json& md) {  // filter.rs:329-373
+    const Json* fv = nested(md, c.field);
+    auto pat = [&]() -> const std::string& { static const std::string empty; return c.value.kind == Json::Str ? c.value.str : empty; };
+    switch (c.op) {
+        case FilterOp::Exists: return fv != nullptr;
+        case FilterOp::Eq: return fv && values_equal(*fv, c.value);
+        case FilterOp::Ne: return !fv || !values_equal(*fv, c.value);
+        case FilterOp::Gt: return fv && compare_values(*fv, c.value) > 0;
+        case FilterOp::Gte: return fv && compare_values(*fv, c.value) >= 0;
+        case FilterOp::Lt: return fv && compare_values(*fv, c.value) < 0;
+        case FilterOp::Lte: return fv && compare_values(*fv, c.value) <= 0;
+        case FilterOp::In:
+            if (c.value.kind != Json::Arr) return false;
+            if (!fv) return false;
+            for (auto& it : c.value.arr) if (values_equal(*fv, it)) return true;
+            return false;
+        case FilterOp::NotIn:
+            if (c.value.kind != Json::Arr) return true;
+            if (!fv) return true;
+            for (auto& it : c.value.arr) if (values_equal(*fv, it)) return false;
+            return true;
+        case FilterOp::Contains: return fv && fv->kind == Json::Str && fv->str.find(pat()) != std::string::npos;
+        case FilterOp::StartsWith: return fv && fv->kind == Json::Str && fv->str.compare(0, pat().size(), pat()) == 0 && fv->str.size() >= pat().size();
+        case FilterOp::EndsWith:
+            return fv && fv->kind == Json::Str && fv->str.size() >= pat().size() &&
+                   fv->str.compare(fv->str.size() - pat().size(), pat().size(), pat()) == 0;
+    }
+    return false;
+}
+const char* op_name(FilterOp op) {
+    switch (op) {
+        case FilterOp::Eq: return "eq"; case FilterOp::Ne: return "ne"; case FilterOp::Gt: return "gt";
+        case FilterOp::Gte: return "gte"; case FilterOp::Lt: return "lt"; case FilterOp::Lte: return "lte";
+        case FilterOp::In: return "in"; case FilterOp::NotIn: return "notin"; case FilterOp::Contains: return "contains";
+        case FilterOp::StartsWith: return "startswith"; case FilterOp::EndsWith: return "endswith"; case FilterOp::Exists: return "exists";
+    }
+    return "?";
+}
+}  // namespace
+
+bool filter_parse(const std::string& in, FilterNode& out) {  // filter.rs:52-134
+    std::string s = trim(in);
+    if (contains(s, " OR ")) {
+        std::vector<FilterNode> fs;
+        for (auto& p : split(s, " OR ")) { FilterNode n; if (filter_parse(trim(p), n)) fs.push_back(std::move(n)); }
+        if (fs.size() > 1) { out = FilterNode(); out.kind = FilterNode::Or; out.children = std::move(fs); return true; }
+        if (fs.size() == 1) { out = std::move(fs[0]); return true; }
+        return false;
+    }
+    bool has_and = contains(s, " AND ");
+    bool has_comma = false;
+    {
+        int depth = 0;
+        for (char c : s) {
+            if (c == '[') depth++;
+            else if (c == ']') depth--;
+            else if (c == ',' && depth == 0) { has_comma = true; break; }
+        }
+    }
+    if (has_and || has_comma) {
+        std::vector<std::string> parts;
+        if (has_and) parts = split(s, " AND ");
+        else {
+            std::string cur;
+            int depth = 0;
+            for (char c : s) {
+                if (c == '[') { depth++; cur += c; }
+                else if (c == ']') { depth--; cur += c; }
+                else if (c == ',' && depth == 0) { parts.push_back(cur); cur.clear(); }
+                else cur += c;
+            }
+            if (!cur.empty()) parts.push_back(cur);
+        }
+        std::vector<FilterNode> fs;
+        for (auto& p : parts) { FilterNode n; if (parse_single(trim(p), n)) fs.push_back(std::move(n)); }
+        if (fs.size() > 1) { out = FilterNode(); out.kind = FilterNode::And; out.children = std::move(fs); return true; }
+        if (fs.size() == 1) { out = std::move(fs[0]); return true; }
+        return false;
+    }
+    return parse_single(s, out);
+}
+
+bool filter_matches(const FilterNode& f, const Json& md) {  // filter.rs:319-325
+    switch (f.kind) {
+        case FilterNode::Condition: return cond_matches(f, md);
+        case FilterNode::And: for (auto& c : f.children) if (!filter_matches(c, md)) return false; return true;
+        case FilterNode::Or: for (auto& c : f.children) if (filter_matches(c, md)) return true; return false;
+    }
+    return false;
+}
+
+std::string filter_describe(const FilterNode& f) {
+    std::string o;
+    if (f.kind == FilterNode::Condition) {
+        o += "{\"field\":"; dump_str(o, f.field);
+        o += ",\"op\":\""; o += op_name(f.op); o += "\",\"value\":"; o += json_dump(f.value); o += "}";
+        return o;
+    }
+    o += f.kind == FilterNode::And ? "{\"and\":[" : "{\"or\":[";
+    for (size_t i = 0; i < f.children.size(); ++i) { if (i) o += ','; o += filter_describe(f.children[i]); }
+    o += "]}";
+    return o;
+}
+
+}  // namespace leann

@@ -1,0 +1,56 @@
+// text.h — host-side text structures: tokenizer, BM25 inverted index, metadata filter, mini JSON.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace leann {
+
+// ---- JSON value (serde_json::Value stand-in for filter evaluation) --------------------------------
+struct Json {
+    enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+    bool b = false;
+    double num = 0.0;
+    bool is_int = false;   // number written without fraction/exponent (serde i64/u64)
+    std::string str;
+    std::vector<Json> arr;
+    std::vector<std::pair<std::string, Json>> obj;
+    const Json* get(const std::string& key) const;  // Value::get(&str): objects only
+};
+bool json_parse(const char* s, size_t n, Json& out, std::string& err);
+std::string json_dump(const Json& v);
+
+// ---- index/bm25.rs:127-132 ---------------------------------------------------------------------------
+void tokenize(const char* text, size_t n, std::vector<std::string>& out);
+
+// ---- index/filter.rs ---------------------------------------------------------------------------------------
+enum class FilterOp { Eq, Ne, Gt, Gte, Lt, Lte, In, NotIn, Contains, StartsWith, EndsWith, Exists };
+struct FilterNode {
+    enum Kind { Condition, And, Or } kind = Condition;
+    std::string field;
+    FilterOp op = FilterOp::Eq;
+    Json value;
+    std::vector<FilterNode> children;
+};
+bool filter_parse(const std::string& s, FilterNode& out);             // MetadataFilter::parse
+bool filter_matches(const FilterNode& f, const Json& metadata);       // MetadataFilter::matches
+std::string filter_describe(const FilterNode& f);
+
+// ---- index/bm25.rs:17-74: inverted (CSR) form of Bm25Scorer ------------------------------------------------
+struct Bm25Host {
+    size_t num_docs = 0;
+    uint64_t total_tokens = 0;
+    float avg_doc_len = 1.0f;
+    std::unordered_map<std::string, uint32_t> dict;  // term -> term id
+    std::vector<uint64_t> term_off;   // n_terms + 1
+    std::vector<uint32_t> post_doc;   // ascending doc id inside a term
+    std::vector<uint32_t> post_tf;
+    std::vector<float> idf;           // per term, f32 exactly as bm25.rs:88
+    std::vector<float> norm;          // per doc: 1 - B + B * (len / avg), bm25.rs:97
+    std::vector<uint32_t> doc_len;
+};
+void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& out);
+
+}  // namespace leann

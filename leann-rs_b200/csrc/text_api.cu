@@ -1,0 +1,571 @@
+// text_api.cu — C ABI of the text path: BM25 handle, filter handle, hybrid search, IndexSearcher.
+// Reference interfaces: src/index/bm25.rs, src/index/filter.rs, src/index/searcher.rs,
+// src/index/passages.rs (read side only: <base>.passages.jsonl + <base>.passages.idx.json + <base>.ids.txt).
+#include <algorithm>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <sstream>
+
+#include "bm25_dev.h"
+
+using namespace leann;
+
+namespace leann {
+int guard_impl(char* err, size_t errlen, const std::function<void()>& f);
+}
+#define GUARD(...) return leann::guard_impl(err, errlen, [&]() __VA_ARGS__)
+
+struct leann_cuda_filter {
+    leann::FilterNode root;
+    std::string expr;
+};
+
+namespace {
+
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        cudaError_t e = cudaSetDevice(dev);
+        if (e != cudaSuccess) throw Error(LEANN_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (no CPU fallback)");
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct DevBuf {  // scoped device allocation
+    void* p = nullptr;
+    DevBuf() = default;
+    explicit DevBuf(size_t bytes) { LEANN_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+void require_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error(LEANN_ERR_CUDA, "no CUDA device available: libleann_cuda has no CPU fallback");
+    }
+    if (device < 0 || device >= n) throw Error(LEANN_ERR_INVALID_ARG, "device ordinal out of range");
+}
+
+template <typename T>
+T* upload_vec(const std::vector<T>& v) {
+    T* p = nullptr;
+    LEANN_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) LEANN_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+void bm25_ensure_ws(const leann_cuda_bm25* b, size_t nq) {
+    if (!b->stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    if (!b->d_qcounter) LEANN_CUDA_CHECK(cudaMalloc(&b->d_qcounter, 16));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+    int want = (int)std::min<size_t>((size_t)sms * 2, std::max<size_t>(nq, 1));
+    // bound the accumulators to 8 GB
+    size_t per = std::max<size_t>(b->host.num_docs, 1) * 4;
+    while (want > 1 && (size_t)want * per > ((size_t)8 << 30)) want /= 2;
+    if (b->n_ctas >= want) return;
+    if (b->d_acc) cudaFree(b->d_acc);
+    b->d_acc = nullptr; b->n_ctas = 0;
+    LEANN_CUDA_CHECK(cudaMalloc(&b->d_acc, (size_t)want * per));
+    LEANN_CUDA_CHECK(cudaMemset(b->d_acc, 0, (size_t)want * per));
+    b->n_ctas = want;
+}
+
+// query texts -> CSR of known term ids (unknown terms contribute nothing: bm25.rs:82-85)
+void tokenize_queries(const leann_cuda_bm25* b, const char* const* texts, const size_t* bytes, size_t nq,
+                      std::vector<uint64_t>& off, std::vector<uint32_t>& terms) {
+    off.assign(nq + 1, 0);
+    terms.clear();
+    std::vector<std::string> toks;
+    for (size_t i = 0; i < nq; ++i) {
+        if (texts && texts[i]) {
+            tokenize(texts[i], bytes ? bytes[i] : strlen(texts[i]), toks);
+            for (auto& t : toks) {
+                auto it = b->host.dict.find(t);
+                if (it != b->host.dict.end()) terms.push_back(it->second);
+            }
+        }
+        off[i + 1] = terms.size();
+    }
+}
+
+// The device half of search_with_options for a batch. All host pointers.
+void hybrid_search_impl(const leann_cuda_index* ix, const leann_cuda_bm25* bm, const float* queries,
+                        const char* const* texts, const size_t* text_bytes, size_t nq, size_t top_k, size_t ef,
+                        int hybrid, float alpha, const uint64_t* mask, size_t mask_words, uint64_t* out_idx,
+                        float* out_score, uint32_t* out_cnt) {
+    if (!ix) throw Error(LEANN_ERR_INVALID_ARG, "null index");
+    if (nq == 0) return;
+    if (top_k == 0) throw Error(LEANN_ERR_INVALID_ARG, "top_k must be > 0");
+    const size_t fk = (mask || hybrid) ? top_k * 5 : top_k;  // searcher.rs:129-133 (decided by the flag, not the text)
+    if (hybrid && !texts) hybrid = 0;  // searcher.rs:147: hybrid without query_text leaves the vector order
+    if (hybrid && !bm) throw Error(LEANN_ERR_INVALID_ARG, "hybrid search needs a BM25 handle");
+    if (hybrid && bm->device != ix->device) throw Error(LEANN_ERR_INVALID_ARG, "BM25 handle lives on another device");
+    if (fk > 1024) throw Error(LEANN_ERR_INVALID_ARG, "top_k too large for the fused path (5*top_k <= 1024)");
+    DevGuard dg(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    cudaStream_t s = backend_stream(ix);
+    DevBuf dq(nq * ix->d * 4), vk(nq * fk * 8), vd(nq * fk * 4), vc(nq * 4);
+    DevBuf oi(nq * top_k * 8), os(nq * top_k * 4), oc(nq * 4);
+    DevBuf dmask(mask ? mask_words * 8 : 16);
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(dq.p, queries, nq * ix->d * 4, cudaMemcpyHostToDevice, s));
+    if (mask) LEANN_CUDA_CHECK(cudaMemcpyAsync(dmask.p, mask, mask_words * 8, cudaMemcpyHostToDevice, s));
+    backend_search_device(ix, dq.as<float>(), nq, fk, ef, nullptr, vk.as<uint64_t>(), vd.as<float>(), vc.as<uint32_t>(), s);
+    std::unique_ptr<DevBuf> qo, qt, cb, bi, bs, bc, bx, bn;
+    std::unique_ptr<std::lock_guard<std::mutex>> blk;
+    if (hybrid) {
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> terms;
+        tokenize_queries(bm, texts, text_bytes, nq, off, terms);
+        blk.reset(new std::lock_guard<std::mutex>(bm->mu));
+        bm25_ensure_ws(bm, nq);
+        qo.reset(new DevBuf(off.size() * 8)); qt.reset(new DevBuf(terms.size() * 4));
+        cb.reset(new DevBuf(nq * fk * 4)); bi.reset(new DevBuf(nq * fk * 8)); bs.reset(new DevBuf(nq * fk * 4));
+        bc.reset(new DevBuf(nq * 4)); bx.reset(new DevBuf(nq * 4)); bn.reset(new DevBuf(nq * 4));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(qo->p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+        if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt->p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(s));  // off/terms are stack-owned host vectors
+        launch_bm25_query(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, (uint32_t)fk, bm->d_acc, bm->n_ctas,
+                          vk.as<uint64_t>(), vc.as<uint32_t>(), (uint32_t)fk, cb->as<float>(), bi->as<uint64_t>(), bs->as<float>(),
+                          bc->as<uint32_t>(), bx->as<float>(), bn->as<float>(), bm->d_qcounter, s);
+    }
+    launch_hybrid_fuse(vk.as<uint64_t>(), vd.as<float>(), vc.as<uint32_t>(), (uint32_t)fk, hybrid ? cb->as<float>() : nullptr,
+                       hybrid ? bi->as<uint64_t>() : nullptr, hybrid ? bs->as<float>() : nullptr,
+                       hybrid ? bc->as<uint32_t>() : nullptr, (uint32_t)(hybrid ? fk : 0), hybrid ? bx->as<float>() : nullptr,
+                       hybrid ? bn->as<float>() : nullptr, hybrid, alpha, mask ? dmask.as<uint64_t>() : nullptr,
+                       (uint64_t)mask_words * 64, (uint32_t)top_k, oi.as<uint64_t>(), os.as<float>(), oc.as<uint32_t>(),
+                       (uint32_t)nq, s);
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(out_idx, oi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(out_score, os.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
+    if (out_cnt) LEANN_CUDA_CHECK(cudaMemcpyAsync(out_cnt, oc.p, nq * 4, cudaMemcpyDeviceToHost, s));
+    LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+std::string read_file(const std::string& path, bool& ok) {
+    std::ifstream f(path, std::ios::binary);
+    ok = (bool)f;
+    if (!f) return {};
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+struct leann_cuda_searcher {
+    std::string base, backend_name;
+    leann_cuda_index* backend = nullptr;
+    leann_cuda_bm25* bm25 = nullptr;       // built once, on first hybrid use
+    std::vector<std::string> id_map;       // <base>.ids.txt (searcher.rs:83-92)
+    std::string jsonl;                     // whole <base>.passages.jsonl
+    std::vector<uint64_t> line_off;        // per ordinal: byte offset of its passage line, or ~0 when missing
+    std::vector<uint64_t> exists_mask;     // passages.get(id) succeeds
+    std::unordered_map<std::string, std::vector<uint64_t>> mask_cache;
+    bool honor_complexity = false;
+    std::mutex mu;
+    int device = 0;
+
+    bool passage(size_t ordinal, Json& out) const {
+        if (ordinal >= line_off.size() || line_off[ordinal] == ~0ull) return false;
+        size_t o = line_off[ordinal];
+        size_t e = jsonl.find('\n', o);
+        if (e == std::string::npos) e = jsonl.size();
+        std::string err;
+        return json_parse(jsonl.data() + o, e - o, out, err) && out.kind == Json::Obj;
+    }
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------ BM25
+int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size_t n_docs, int device,
+                          leann_cuda_bm25** out, char* err, size_t errlen) {
+    GUARD({
+        if (!out || (n_docs && (!docs || !doc_bytes))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        require_device(device);
+        if (n_docs > 0xFFFFFFF0ull) throw Error(LEANN_ERR_INVALID_ARG, "too many documents");
+        std::unique_ptr<leann_cuda_bm25> b(new leann_cuda_bm25());
+        b->device = device;
+        bm25_build_host(docs, doc_bytes, n_docs, b->host);
+        DevGuard dg(device);
+        b->d_term_off = upload_vec(b->host.term_off);
+        b->d_post_doc = upload_vec(b->host.post_doc);
+        b->d_post_tf = upload_vec(b->host.post_tf);
+        b->d_idf = upload_vec(b->host.idf);
+        b->d_norm = upload_vec(b->host.norm);
+        *out = b.release();
+    });
+}
+size_t leann_cuda_bm25_len(const leann_cuda_bm25* b) { return b ? b->host.num_docs : 0; }
+int leann_cuda_bm25_stats(const leann_cuda_bm25* b, uint64_t* st, float* avg) {
+    if (!b || !st) return LEANN_ERR_INVALID_ARG;
+    st[0] = b->host.num_docs; st[1] = b->host.idf.size(); st[2] = b->host.post_doc.size(); st[3] = b->host.total_tokens;
+    if (avg) *avg = b->host.avg_doc_len;
+    return LEANN_OK;
+}
+size_t leann_cuda_tokenize(const char* text, size_t bytes, char* out, size_t cap) {
+    std::vector<std::string> toks;
+    tokenize(text, bytes, toks);
+    size_t w = 0;
+    for (size_t i = 0; i < toks.size(); ++i) {
+        for (char c : toks[i]) if (out && w + 1 < cap) out[w++] = c;
+        if (out && w + 1 < cap) out[w++] = '\n';
+    }
+    if (out && cap) out[w < cap ? w : cap - 1] = 0;
+    return toks.size();
+}
+void leann_cuda_bm25_free(leann_cuda_bm25* b) {
+    if (!b) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(b->device);
+    cudaFree(b->d_term_off); cudaFree(b->d_post_doc); cudaFree(b->d_post_tf); cudaFree(b->d_idf); cudaFree(b->d_norm);
+    cudaFree(b->d_acc); cudaFree(b->d_qcounter);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+    delete b;
+}
+
+int leann_cuda_bm25_score(const leann_cuda_bm25* b, const char* query, size_t query_bytes, float* scores,
+                          char* err, size_t errlen) {
+    GUARD({
+        if (!b || !query || (!scores && b->host.num_docs)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        DevGuard dg(b->device);
+        std::lock_guard<std::mutex> lk(b->mu);
+        bm25_ensure_ws(b, 1);
+        std::vector<std::string> toks;
+        tokenize(query, query_bytes, toks);
+        std::vector<uint32_t> terms;
+        std::vector<uint64_t> dfs;
+        for (auto& t : toks) {
+            auto it = b->host.dict.find(t);
+            if (it == b->host.dict.end()) continue;
+            terms.push_back(it->second);
+            dfs.push_back(b->host.term_off[it->second + 1] - b->host.term_off[it->second]);
+        }
+        size_t n = b->host.num_docs;
+        if (n == 0) return;
+        // uses CTA slot 0 of the accumulator as the dense score vector, then clears it again
+        launch_bm25_dense(b->view(), terms.data(), dfs.data(), terms.size(), b->d_acc, b->stream);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(scores, b->d_acc, n * 4, cudaMemcpyDeviceToHost, b->stream));
+        LEANN_CUDA_CHECK(cudaMemsetAsync(b->d_acc, 0, n * 4, b->stream));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+    });
+}
+
+int leann_cuda_bm25_search(const leann_cuda_bm25* b, const char* const* queries, const size_t* query_bytes, size_t nq,
+                           size_t top_k, uint64_t* idx, float* scores, uint32_t* counts, char* err, size_t errlen) {
+    GUARD({
+        if (!b || (nq && (!queries || !idx || !scores))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        if (nq == 0) return;
+        DevGuard dg(b->device);
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> terms;
+        tokenize_queries(b, queries, query_bytes, nq, off, terms);
+        std::lock_guard<std::mutex> lk(b->mu);
+        bm25_ensure_ws(b, nq);
+        cudaStream_t s = b->stream;
+        DevBuf qo(off.size() * 8), qt(terms.size() * 4), bi(nq * top_k * 8), bs(nq * top_k * 4), bc(nq * 4), bx(nq * 4), bn(nq * 4);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(qo.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+        if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt.p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
+        launch_bm25_query(b->view(), qo.as<uint64_t>(), qt.as<uint32_t>(), (uint32_t)nq, (uint32_t)top_k, b->d_acc, b->n_ctas,
+                          nullptr, nullptr, 0, nullptr, bi.as<uint64_t>(), bs.as<float>(), bc.as<uint32_t>(), bx.as<float>(),
+                          bn.as<float>(), b->d_qcounter, s);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(idx, bi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(scores, bs.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
+        if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, bc.p, nq * 4, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+int leann_cuda_hybrid_rerank(const uint64_t* idx, const float* vec_scores, size_t n, const float* bm25_scores,
+                             size_t n_docs, float alpha, int device, uint64_t* out_idx, float* out_scores,
+                             char* err, size_t errlen) {
+    GUARD({
+        if (n && (!idx || !vec_scores || !out_idx || !out_scores)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        if (n == 0) return;
+        if (n > 4096) throw Error(LEANN_ERR_INVALID_ARG, "hybrid_rerank: at most 4096 candidates");
+        require_device(device);
+        DevGuard dg(device);
+        cudaStream_t s = nullptr;
+        LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        try {
+            DevBuf di(n * 8), dv(n * 4), dc(4), dense(n_docs * 4), cb(n * 4), bx(4), bn(4), sc(8), oi(n * 8), os(n * 4), oc(4);
+            uint32_t cnt = (uint32_t)n;
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(di.p, idx, n * 8, cudaMemcpyHostToDevice, s));
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(dv.p, vec_scores, n * 4, cudaMemcpyHostToDevice, s));
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(dc.p, &cnt, 4, cudaMemcpyHostToDevice, s));
+            if (n_docs) LEANN_CUDA_CHECK(cudaMemcpyAsync(dense.p, bm25_scores, n_docs * 4, cudaMemcpyHostToDevice, s));
+            launch_dense_minmax_gather(dense.as<float>(), (uint32_t)n_docs, di.as<uint64_t>(), (uint32_t)n, cb.as<float>(),
+                                       bx.as<float>(), bn.as<float>(), sc.as<uint32_t>(), s);
+            uint32_t zero = 0;
+            DevBuf bc(4);
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(bc.p, &zero, 4, cudaMemcpyHostToDevice, s));
+            launch_hybrid_fuse(di.as<uint64_t>(), dv.as<float>(), dc.as<uint32_t>(), (uint32_t)n, cb.as<float>(), di.as<uint64_t>(),
+                               dv.as<float>(), bc.as<uint32_t>(), 0, bx.as<float>(), bn.as<float>(), 1, alpha, nullptr, 0,
+                               (uint32_t)n, oi.as<uint64_t>(), os.as<float>(), oc.as<uint32_t>(), 1, s);
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(out_idx, oi.p, n * 8, cudaMemcpyDeviceToHost, s));
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(out_scores, os.p, n * 4, cudaMemcpyDeviceToHost, s));
+            LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        cudaStreamDestroy(s);
+    });
+}
+
+int leann_cuda_hybrid_search(const leann_cuda_index* index, const leann_cuda_bm25* bm25, const float* queries,
+                             const char* const* query_texts, const size_t* query_text_bytes, size_t nq, size_t top_k,
+                             size_t ef, int hybrid, float alpha, const uint64_t* filter_mask, uint64_t* idx,
+                             float* scores, uint32_t* counts, char* err, size_t errlen) {
+    GUARD({
+        if (!index) throw Error(LEANN_ERR_INVALID_ARG, "null index");
+        hybrid_search_impl(index, bm25, queries, query_texts, query_text_bytes, nq, top_k, ef, hybrid, alpha, filter_mask,
+                           filter_mask ? (index->n + 63) / 64 : 0, idx, scores, counts);
+    });
+}
+
+// ------------------------------------------------------------------ filter
+int leann_cuda_filter_parse(const char* expr, leann_cuda_filter** out, char* err, size_t errlen) {
+    GUARD({
+        if (!expr || !out) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        std::unique_ptr<leann_cuda_filter> f(new leann_cuda_filter());
+        f->expr = expr;
+        if (!filter_parse(f->expr, f->root)) throw Error(LEANN_ERR_PARSE, std::string("cannot parse filter: ") + expr);
+        *out = f.release();
+    });
+}
+size_t leann_cuda_filter_describe(const leann_cuda_filter* f, char* out, size_t cap) {
+    if (!f) return 0;
+    std::string d = filter_describe(f->root);
+    if (out && cap) { size_t n = std::min(cap - 1, d.size()); memcpy(out, d.data(), n); out[n] = 0; }
+    return d.size();
+}
+int leann_cuda_filter_matches(const leann_cuda_filter* f, const char* metadata_json, size_t bytes, int* result,
+                              char* err, size_t errlen) {
+    GUARD({
+        if (!f || !metadata_json || !result) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        Json md;
+        std::string e;
+        if (!json_parse(metadata_json, bytes, md, e)) throw Error(LEANN_ERR_BAD_FORMAT, "metadata is not valid JSON: " + e);
+        *result = filter_matches(f->root, md) ? 1 : 0;
+    });
+}
+int leann_cuda_filter_mask(const leann_cuda_filter* f, const char* const* metadata_json, const size_t* bytes, size_t n,
+                           uint64_t* mask_bits, char* err, size_t errlen) {
+    GUARD({
+        if (!f || (n && (!metadata_json || !bytes || !mask_bits))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        size_t words = (n + 63) / 64;
+        for (size_t w = 0; w < words; ++w) mask_bits[w] = 0;
+        Json md;
+        std::string e;
+        for (size_t i = 0; i < n; ++i) {
+            if (!json_parse(metadata_json[i], bytes[i], md, e)) throw Error(LEANN_ERR_BAD_FORMAT, "metadata " + std::to_string(i) + " is not valid JSON: " + e);
+            if (filter_matches(f->root, md)) mask_bits[i >> 6] |= 1ull << (i & 63);
+        }
+    });
+}
+void leann_cuda_filter_free(leann_cuda_filter* f) { delete f; }
+
+// ------------------------------------------------------------------ IndexSearcher
+int leann_cuda_searcher_load(const char* base_path, const char* backend_name, size_t dims, int device,
+                             leann_cuda_searcher** out, char* err, size_t errlen) {
+    GUARD({
+        if (!base_path || !backend_name || !out) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        std::unique_ptr<leann_cuda_searcher> s(new leann_cuda_searcher());
+        s->base = base_path; s->backend_name = backend_name; s->device = device;
+        int backend;
+        if (s->backend_name == "hnsw") backend = LEANN_BACKEND_HNSW;
+        else if (s->backend_name == "diskann") backend = LEANN_BACKEND_VAMANA;
+        else if (s->backend_name == "flat") backend = LEANN_BACKEND_FLAT;
+        else throw Error(LEANN_ERR_INVALID_ARG, "Unknown backend: " + s->backend_name);  // searcher.rs:98
+        // PassageStore::open (passages.rs:47-59)
+        bool ok = false;
+        std::string idx_txt = read_file(with_extension(s->base, "passages.idx.json"), ok);
+        if (!ok) throw Error(LEANN_ERR_NOT_FOUND, "cannot read " + with_extension(s->base, "passages.idx.json"));
+        Json offsets;
+        std::string e;
+        if (!json_parse(idx_txt.data(), idx_txt.size(), offsets, e) || offsets.kind != Json::Obj)
+            throw Error(LEANN_ERR_BAD_FORMAT, "passages.idx.json is not a JSON object: " + e);
+        s->jsonl = read_file(with_extension(s->base, "passages.jsonl"), ok);
+        if (!ok) throw Error(LEANN_ERR_NOT_FOUND, "cannot read " + with_extension(s->base, "passages.jsonl"));
+        std::unordered_map<std::string, uint64_t> off;
+        off.reserve(offsets.obj.size() * 2);
+        for (auto& kv : offsets.obj) if (kv.second.kind == Json::Num) off[kv.first] = (uint64_t)kv.second.num;
+        // ids.txt -> id_map (searcher.rs:83-92). The HashMap-order fallback of the reference is
+        // nondeterministic; without ids.txt the JSONL order is used.
+        std::string ids = read_file(with_extension(s->base, "ids.txt"), ok);
+        if (ok) {
+            size_t p = 0;
+            while (p < ids.size()) {  // str::lines(): split on \n, strip one trailing \r, no empty tail
+                size_t nl = ids.find('\n', p);
+                std::string line = ids.substr(p, nl == std::string::npos ? std::string::npos : nl - p);
+                if (!line.empty() && line.back() == '\r') line.pop_back();
+                s->id_map.push_back(line);
+                if (nl == std::string::npos) break;
+                p = nl + 1;
+            }
+        } else {
+            std::vector<std::pair<uint64_t, std::string>> byoff;
+            for (auto& kv : off) byoff.emplace_back(kv.second, kv.first);
+            std::sort(byoff.begin(), byoff.end());
+            for (auto& kv : byoff) s->id_map.push_back(kv.second);
+        }
+        s->line_off.assign(s->id_map.size(), ~0ull);
+        s->exists_mask.assign((s->id_map.size() + 63) / 64, 0);
+        for (size_t i = 0; i < s->id_map.size(); ++i) {
+            auto it = off.find(s->id_map[i]);
+            if (it == off.end() || it->second >= s->jsonl.size()) continue;
+            s->line_off[i] = it->second;
+            Json p;
+            if (s->passage(i, p)) s->exists_mask[i >> 6] |= 1ull << (i & 63);
+            else s->line_off[i] = ~0ull;
+        }
+        int rc = leann_cuda_open(base_path, backend, dims, LEANN_METRIC_DEFAULT, device, &s->backend, err, errlen);
+        if (rc != LEANN_OK) throw Error(rc, err ? std::string(err) : std::string("backend open failed"));
+        *out = s.release();
+    });
+}
+size_t leann_cuda_searcher_len(const leann_cuda_searcher* s) { return s && s->backend ? s->backend->n : 0; }
+size_t leann_cuda_searcher_id(const leann_cuda_searcher* s, uint64_t idx, char* out, size_t cap) {
+    if (!s) return 0;
+    std::string id = idx < s->id_map.size() ? s->id_map[idx] : std::to_string(idx);  // searcher.rs:180-184
+    if (out && cap) { size_t n = std::min(cap - 1, id.size()); memcpy(out, id.data(), n); out[n] = 0; }
+    return id.size();
+}
+void leann_cuda_searcher_close(leann_cuda_searcher* s) {
+    if (!s) return;
+    if (s->bm25) leann_cuda_bm25_free(s->bm25);
+    if (s->backend) leann_cuda_close(s->backend);
+    delete s;
+}
+
+int leann_cuda_searcher_search(const leann_cuda_searcher* cs, const float* queries, const char* const* query_texts,
+                               const size_t* query_text_bytes, size_t nq, size_t top_k, size_t complexity,
+                               const char* filter_expr, int hybrid, float alpha, uint64_t* idx, float* scores,
+                               uint32_t* counts, char* err, size_t errlen) {
+    GUARD({
+        leann_cuda_searcher* s = const_cast<leann_cuda_searcher*>(cs);
+        if (!s || !s->backend) throw Error(LEANN_ERR_INVALID_ARG, "null searcher");
+        const size_t n_ord = std::max(s->id_map.size(), s->backend->n);
+        const size_t words = (n_ord + 63) / 64;
+        // the walk of searcher.rs:174-207 drops ordinals whose passage cannot be loaded, then applies the filter
+        std::vector<uint64_t> mask(words, 0);
+        const std::vector<uint64_t>* use = nullptr;
+        bool have_filter = filter_expr && filter_expr[0];
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (have_filter) {
+                auto it = s->mask_cache.find(filter_expr);
+                if (it == s->mask_cache.end()) {
+                    FilterNode root;
+                    if (!filter_parse(filter_expr, root)) throw Error(LEANN_ERR_PARSE, std::string("cannot parse filter: ") + filter_expr);
+                    std::vector<uint64_t> m(words, 0);
+                    Json p;
+                    static const Json null_json;
+                    for (size_t i = 0; i < s->id_map.size(); ++i) {
+                        if (!s->passage(i, p)) continue;
+                        const Json* md = p.get("metadata");
+                        if (filter_matches(root, md ? *md : null_json)) m[i >> 6] |= 1ull << (i & 63);
+                    }
+                    it = s->mask_cache.emplace(filter_expr, std::move(m)).first;
+                }
+                use = &it->second;
+            }
+            if (hybrid && query_texts && !s->bm25) {
+                // get_all_texts (searcher.rs:213-224): missing passages contribute an empty document
+                std::vector<std::string> texts(s->id_map.size());
+                Json p;
+                for (size_t i = 0; i < s->id_map.size(); ++i)
+                    if (s->passage(i, p)) { const Json* t = p.get("text"); if (t && t->kind == Json::Str) texts[i] = t->str; }
+                std::vector<const char*> ptrs(texts.size());
+                std::vector<size_t> lens(texts.size());
+                for (size_t i = 0; i < texts.size(); ++i) { ptrs[i] = texts[i].data(); lens[i] = texts[i].size(); }
+                int rc = leann_cuda_bm25_build(ptrs.data(), lens.data(), texts.size(), s->device, &s->bm25, err, errlen);
+                if (rc != LEANN_OK) throw Error(rc, err ? std::string(err) : std::string("bm25 build failed"));
+            }
+        }
+        // mask = exists AND filter; it is passed whenever a filter is set or some passage is missing
+        bool all_exist = true;
+        for (size_t i = 0; i < s->id_map.size() && all_exist; ++i) all_exist = (s->exists_mask[i >> 6] >> (i & 63)) & 1ull;
+        if (s->backend->n > s->id_map.size()) all_exist = false;  // ordinals beyond ids.txt have no passage
+        const uint64_t* mask_ptr = nullptr;
+        if (have_filter || !all_exist) {
+            for (size_t w = 0; w < s->exists_mask.size(); ++w) mask[w] = s->exists_mask[w] & (use ? (*use)[w] : ~0ull);
+            mask_ptr = mask.data();
+        }
+        // fetch_k is 5k only when a filter or hybrid was REQUESTED (searcher.rs:129); a mask that exists
+        // only because passages are missing must not widen it.
+        size_t ef = complexity;
+        if (s->backend->backend == LEANN_BACKEND_HNSW && !s->honor_complexity) ef = 64;  // hnsw.rs:49,83
+        if (!have_filter && !hybrid && mask_ptr) {
+            // plain search with holes: fetch top_k, then drop missing ones (may return < k, as the reference does)
+            std::vector<uint64_t> k0(nq * top_k);
+            std::vector<float> d0(nq * top_k);
+            std::vector<uint32_t> c0(nq);
+            int rc = leann_cuda_search(s->backend, queries, nq, top_k, ef, nullptr, LEANN_MASK_NONE, k0.data(), d0.data(), c0.data(), err, errlen);
+            if (rc != LEANN_OK) throw Error(rc, err ? std::string(err) : std::string("search failed"));
+            for (size_t q = 0; q < nq; ++q) {
+                uint32_t o = 0;
+                for (uint32_t j = 0; j < c0[q]; ++j) {
+                    uint64_t d = k0[q * top_k + j];
+                    if (d < words * 64 && ((mask[d >> 6] >> (d & 63)) & 1ull)) { idx[q * top_k + o] = d; scores[q * top_k + o] = d0[q * top_k + j]; ++o; }
+                }
+                if (counts) counts[q] = o;
+                for (; o < top_k; ++o) { idx[q * top_k + o] = ~0ull; scores[q * top_k + o] = 0.0f; }
+            }
+            return;
+        }
+        hybrid_search_impl(s->backend, s->bm25, queries, (hybrid ? query_texts : nullptr), query_text_bytes, nq, top_k, ef,
+                           hybrid, alpha, mask_ptr, mask_ptr ? words : 0, idx, scores, counts);
+        (void)n_ord;
+    });
+}
+
+// IndexSearcher::bm25_search (searcher.rs:228-246): BM25-only top-k passage ordinals (the caller maps
+// them to texts through the passage store, as the reference does).
+int leann_cuda_searcher_bm25_search(const leann_cuda_searcher* cs, const char* query, size_t query_bytes, size_t top_k,
+                                    uint64_t* idx, float* scores, uint32_t* count, char* err, size_t errlen) {
+    GUARD({
+        leann_cuda_searcher* s = const_cast<leann_cuda_searcher*>(cs);
+        if (!s || !query || !idx || !scores || !count) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (!s->bm25) {
+                std::vector<std::string> texts(s->id_map.size());
+                Json p;
+                for (size_t i = 0; i < s->id_map.size(); ++i)
+                    if (s->passage(i, p)) { const Json* t = p.get("text"); if (t && t->kind == Json::Str) texts[i] = t->str; }
+                std::vector<const char*> ptrs(texts.size());
+                std::vector<size_t> lens(texts.size());
+                for (size_t i = 0; i < texts.size(); ++i) { ptrs[i] = texts[i].data(); lens[i] = texts[i].size(); }
+                int rc = leann_cuda_bm25_build(ptrs.data(), lens.data(), texts.size(), s->device, &s->bm25, err, errlen);
+                if (rc != LEANN_OK) throw Error(rc, err ? std::string(err) : std::string("bm25 build failed"));
+            }
+        }
+        const char* qs[1] = {query};
+        size_t ql[1] = {query_bytes};
+        int rc = leann_cuda_bm25_search(s->bm25, qs, ql, 1, top_k, idx, scores, count, err, errlen);
+        if (rc != LEANN_OK) throw Error(rc, err ? std::string(err) : std::string("bm25 search failed"));
+    });
+}
+
+int leann_cuda_searcher_set_honor_complexity(leann_cuda_searcher* s, int on) {
+    if (!s) return LEANN_ERR_INVALID_ARG;
+    s->honor_complexity = on != 0;
+    return LEANN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+"""GPU parity of K3/K3f (BM25 scoring, BM25 top-k, hybrid fusion, post-filter walk) and of the
+IndexSearcher glue against the text oracle: scores must be bit-identical f32, ids identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_data
+from oracle import text_oracle as T
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "text_golden.json")))
+
+
+def test_bm25_golden_bits(pkg):
+    for case in GOLD["bm25"]:
+        sc = pkg.Bm25Scorer.build(case["docs"])
+        st = sc.stats()
+        assert st["num_docs"] == len(case["docs"])
+        assert np.float32(st["avg_doc_len"]).view(np.uint32) == case["avg_doc_len_bits"]
+        for q, want, top in zip(case["queries"], case["scores_bits"], case["top5"]):
+            assert sc.score_query(q).view(np.uint32).tolist() == want, q
+            got = sc.search(q, 5)
+            assert [[i, int(np.float32(s).view(np.uint32))] for i, s in got] == top, q
+
+
+def test_bm25_reference_unit_tests_on_gpu(pkg):
+    """bm25.rs:199-280 assertions, through the GPU path."""
+    fox = ["the quick brown fox jumps over the lazy dog", "a quick brown dog outpaces a swift fox", "the dog chases the fox around the yard"]
+    r = pkg.Bm25Scorer.build(fox).search("quick fox", 3)
+    assert r and len(r) <= 3
+    s = pkg.Bm25Scorer.build(["rust rust rust programming", "rust programming"]).score_query("rust")
+    assert s[0] > s[1]
+    s = pkg.Bm25Scorer.build(["common rare", "common", "common"]).score_query("rare")
+    assert s[0] > 0 and s[1] == 0 and s[2] == 0
+    assert pkg.Bm25Scorer.build(["hello world"]).score_query("")[0] == 0
+    assert pkg.Bm25Scorer.build(["hello world"]).search("xyz", 5) == []
+    r = pkg.Bm25Scorer.build(["apple banana", "apple cherry", "banana cherry", "apple apple apple"]).search("apple", 2)
+    assert len(r) == 2 and r[0][0] == 3 and r[1][0] == 0
+
+
+def test_hybrid_rerank_golden_bits(pkg):
+    for h in GOLD["hybrid"]:
+        r = pkg.hybrid_rerank([(i, s) for i, s in h["vec"]], np.asarray(h["bm25"], dtype=np.float32), h["alpha"])
+        assert [[i, int(np.float32(s).view(np.uint32))] for i, s in r] == h["result"]
+
+
+def _corpus(n, seed, vocab=3000):
+    rng = np.random.default_rng(seed)
+    words = np.array([f"t{i}" for i in range(vocab)])
+    p = 1.0 / np.arange(1, vocab + 1) ** 1.07
+    p /= p.sum()
+    docs = [" ".join(words[rng.choice(vocab, size=int(rng.integers(8, 60)), p=p)]) for _ in range(n)]
+    queries = [" ".join(words[rng.choice(vocab, size=int(rng.integers(1, 6)), p=p)]) for _ in range(64)]
+    return docs, queries
+
+
+def test_bm25_medium_corpus_bits_and_topk(pkg):
+    docs, queries = _corpus(20000, 3)
+    queries += ["", "zzz unknown", "t0 t0 t0", "t1"]
+    ref = T.Bm25Scorer(docs)
+    sc = pkg.Bm25Scorer.build(docs)
+    for q in queries[:12] + queries[-4:]:
+        assert np.array_equal(sc.score_query(q).view(np.uint32), ref.score_query_fast(q).view(np.uint32)), q
+    idx, scores, cnt = sc.search_batch(queries, 50)
+    for i, q in enumerate(queries):
+        want = ref.search(q, 50, fast=True)
+        assert int(cnt[i]) == len(want)
+        assert idx[i, :len(want)].tolist() == [d for d, _ in want], q
+        assert scores[i, :len(want)].view(np.uint32).tolist() == [int(np.float32(s).view(np.uint32)) for _, s in want]
+    # a very common term exercises the in-kernel prune (more positives than the shared buffer holds)
+    big = sc.search("t0", 1000)
+    want = ref.search("t0", 1000, fast=True)
+    assert [d for d, _ in big] == [d for d, _ in want]
+
+
+def _fixture_dir(tmp_path, orc, n=3000, d=64, missing=(), with_ids=True, seed=13):
+    x, q = make_data(n, d, seed, nq=40)
+    g = orc.Hnsw.build(x, M=8, ef_add=32, seed=seed)
+    base = str(tmp_path / "documents.leann")
+    stem = base[: -len(".leann")]
+    g.save(stem + ".index")
+    docs, queries = _corpus(n, seed, vocab=800)
+    rng = np.random.default_rng(seed)
+    metas, offsets, pos = [], {}, 0
+    exts = ["rs", "py", "md", "txt"]
+    with open(stem + ".passages.jsonl", "wb") as f:
+        for i in range(n):
+            md = {"source": f"dir{i % 100}/f{i}.{exts[i % 4]}", "chunk_index": i % 7, "chunk_type": ["simple", "ast", "context"][i % 3],
+                  "lines": int(rng.integers(1, 500))}
+            metas.append(md)
+            if i in missing:
+                continue
+            line = json.dumps({"id": f"p{i}", "text": docs[i], "metadata": md}).encode() + b"\n"
+            offsets[f"p{i}"] = pos
+            f.write(line)
+            pos += len(line)
+    json.dump(offsets, open(stem + ".passages.idx.json", "w"))
+    if with_ids:
+        open(stem + ".ids.txt", "w").write("\n".join(f"p{i}" for i in range(n)) + "\n")
+    return base, x, q, g, docs, queries, metas
+
+
+def test_hybrid_search_matches_reference_glue(orc, pkg, tmp_path):
+    base, x, q, g, docs, queries, metas = _fixture_dir(tmp_path, orc)
+    n, d, k = len(docs), x.shape[1], 10
+    s = pkg.HnswSearcher.load(base, d)
+    bm = pkg.Bm25Scorer.build(docs)
+    ref_bm = T.Bm25Scorer(docs)
+    texts = queries[: len(q)]
+    filt = T.parse_filter("chunk_type=ast,lines>100")
+    passes_bits = np.array([T.filter_matches(filt, m) for m in metas])
+    fmask = pkg.MetadataFilter.parse("chunk_type=ast,lines>100").mask(metas)
+    assert np.array_equal(fmask, pkg.pack_mask(passes_bits))
+    for hybrid, use_filter, alpha in [(True, False, 0.5), (True, True, 0.7), (False, True, 0.7), (False, False, 0.7), (True, False, 1.0), (True, False, 0.0)]:
+        fk = T.fetch_k(k, use_filter, hybrid)
+        bk, bd, bc = s.search_batch(q, fk, 64)            # what backend.search returns (parity-checked elsewhere)
+        idx, sc, cnt = pkg.text.hybrid_search(s, bm, q, texts if hybrid else None, k, 64, hybrid, alpha, fmask if use_filter else None)
+        for i in range(len(q)):
+            want = T.search_with_options(bk[i, :bc[i]].tolist(), bd[i, :bc[i]].tolist(), k, ref_bm, texts[i], hybrid, alpha,
+                                         (lambda j: bool(passes_bits[j])) if use_filter else (lambda j: True), fk, fast=True)
+            assert int(cnt[i]) == len(want), (hybrid, use_filter, i)
+            assert idx[i, :len(want)].tolist() == [a for a, _ in want], (hybrid, use_filter, alpha, i)
+            assert sc[i, :len(want)].view(np.uint32).tolist() == [int(np.float32(b).view(np.uint32)) for _, b in want]
+
+
+def test_index_searcher_end_to_end(orc, pkg, tmp_path):
+    missing = {5, 17, 1234}
+    base, x, q, g, docs, queries, metas = _fixture_dir(tmp_path, orc, missing=missing)
+    d, k = x.shape[1], 5
+    s = pkg.IndexSearcher.load(base, "hnsw", d)
+    assert len(s) == len(docs)
+    ref_docs = ["" if i in missing else docs[i] for i in range(len(docs))]   # get_all_texts: missing -> empty (searcher.rs:219)
+    ref_bm = T.Bm25Scorer(ref_docs)
+    lanes = pkg.reduction_lanes(d)
+    for filt_expr, hybrid in [(None, False), ("source:*.rs", False), ("lines>=400", True), (None, True)]:
+        filt = T.parse_filter(filt_expr) if filt_expr else None
+        opts = pkg.SearchOptions.new(k, 999)
+        if filt_expr:
+            opts = opts.with_filter(filt_expr)
+        fk = T.fetch_k(k, filt is not None, hybrid)
+        ok, od, oc, _ = g.search(q, fk, 64, lanes=lanes, next_cap=max(64, fk))   # HNSW ignores complexity: ef = 64
+        idx, sc, cnt = s.search_batch(q, opts if not hybrid else opts.with_hybrid("unused", 0.6), queries[: len(q)] if hybrid else None)
+        passes = lambda j: (j not in missing) and j < len(metas) and (filt is None or T.filter_matches(filt, metas[j]))
+        for i in range(len(q)):
+            want = T.search_with_options(ok[i, :oc[i]].astype(np.int64).tolist(), od[i, :oc[i]].tolist(), k, ref_bm, queries[i], hybrid, 0.6,
+                                         passes, fk, fast=True)
+            assert idx[i, :cnt[i]].tolist() == [a for a, _ in want], (filt_expr, hybrid, i)
+            assert sc[i, :cnt[i]].view(np.uint32).tolist() == [int(np.float32(b).view(np.uint32)) for _, b in want]
+    # single-query reference-shaped calls
+    res = s.search(q[0], 3, 64)
+    assert len(res) == 3 and res[0].id.startswith("p") and res[0].text and "source" in res[0].metadata
+    hits = s.bm25_search(queries[0], 5)
+    want = ref_bm.search(queries[0], 5, fast=True)
+    assert hits == [ref_docs[i] for i, _ in want]
+    with pytest.raises(pkg.LeannCudaError) as e:
+        s.search_batch(q, pkg.SearchOptions.new(k, 64).with_filter("nonsense"))
+    assert e.value.code == pkg.ERR_PARSE
+    with pytest.raises(pkg.LeannCudaError) as e:
+        pkg.IndexSearcher.load(base, "faiss", d)
+    assert "Unknown backend" in e.value.message
