@@ -56,11 +56,12 @@ class ShardedSearcher:
         keys = torch.where(invalid, keys, keys + self.row_offset)
         if self.world == 1:
             return keys, dists
-        gk = torch.empty((self.world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
-        gd = torch.empty((self.world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
+        nq, k = keys.shape
+        gk = torch.empty((self.world * nq, k), dtype=keys.dtype, device=keys.device)
+        gd = torch.empty((self.world * nq, k), dtype=dists.dtype, device=dists.device)
         self.dist.all_gather_into_tensor(gk, keys.contiguous(), group=self.group)
         self.dist.all_gather_into_tensor(gd, dists.contiguous(), group=self.group)
-        return self.merge_fn(gk, gd, self.descending)
+        return self.merge_fn(gk.view(self.world, nq, k), gd.view(self.world, nq, k), self.descending)
 
 
 class ReplicaSearcher:
@@ -81,10 +82,11 @@ class ReplicaSearcher:
         pk = torch.full((per, k), -1, dtype=keys.dtype, device=keys.device)
         pd = torch.full((per, k), float("inf"), dtype=dists.dtype, device=dists.device)
         pk[: hi - lo], pd[: hi - lo] = keys, dists
-        gk = torch.empty((self.world, per, k), dtype=keys.dtype, device=keys.device)
-        gd = torch.empty((self.world, per, k), dtype=dists.dtype, device=dists.device)
+        gk = torch.empty((self.world * per, k), dtype=keys.dtype, device=keys.device)
+        gd = torch.empty((self.world * per, k), dtype=dists.dtype, device=dists.device)
         self.dist.all_gather_into_tensor(gk, pk, group=self.group)
         self.dist.all_gather_into_tensor(gd, pd, group=self.group)
+        gk, gd = gk.view(self.world, per, k), gd.view(self.world, per, k)
         outk, outd = [], []
         for r in range(self.world):
             a, b = shard_bounds(nq, self.world, r)
