@@ -1,0 +1,179 @@
+//! leann-cuda — `BackendSearcher` implementations backed by libleann_cuda (sm_100a).
+//!
+//! SOURCE ONLY (no Rust toolchain in the build image). Mirrors include/leann_cuda.h one to one.
+//! Drop-in points in leann-rs:
+//!   * `src/backend/mod.rs:23-45`  `BackendType::load_searcher` -> `CudaSearcher::load`
+//!   * `src/backend/traits.rs:11-30` `trait BackendSearcher`     -> `impl BackendSearcher for CudaSearcher`
+//!   * `src/index/searcher.rs:123-210` hybrid path               -> `CudaSearcher::hybrid_search`
+use std::ffi::{c_char, c_float, c_int, c_void, CString};
+use std::path::Path;
+
+#[repr(C)]
+pub struct LeannCudaIndex {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct LeannCudaBm25 {
+    _p: [u8; 0],
+}
+
+pub const BACKEND_HNSW: c_int = 0;
+pub const BACKEND_VAMANA: c_int = 1;
+pub const BACKEND_FLAT: c_int = 2;
+pub const METRIC_DEFAULT: c_int = -1;
+
+extern "C" {
+    fn leann_cuda_open(base_path: *const c_char, backend: c_int, dims: usize, metric: c_int, device: c_int,
+                       out: *mut *mut LeannCudaIndex, err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_len(index: *const LeannCudaIndex) -> usize;
+    fn leann_cuda_search(index: *const LeannCudaIndex, queries: *const c_float, nq: usize, k: usize, ef: usize,
+                         mask_bits: *const u64, mask_mode: c_int, keys: *mut u64, dists: *mut c_float,
+                         counts: *mut u32, err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_close(index: *mut LeannCudaIndex);
+    fn leann_cuda_bm25_build(docs: *const *const c_char, doc_bytes: *const usize, n_docs: usize, device: c_int,
+                             out: *mut *mut LeannCudaBm25, err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_bm25_free(b: *mut LeannCudaBm25);
+    fn leann_cuda_hybrid_search(index: *const LeannCudaIndex, bm25: *const LeannCudaBm25, queries: *const c_float,
+                                query_texts: *const *const c_char, query_text_bytes: *const usize, nq: usize,
+                                top_k: usize, ef: usize, hybrid: c_int, alpha: c_float, filter_mask: *const u64,
+                                idx: *mut u64, scores: *mut c_float, counts: *mut u32, err: *mut c_char,
+                                errlen: usize) -> c_int;
+}
+
+/// The trait of leann-rs (`src/backend/traits.rs:11-30`), repeated so the crate is self-contained.
+pub trait BackendSearcher: Send + Sync {
+    fn search(&self, query: &[f32], top_k: usize, complexity: usize) -> anyhow::Result<(Vec<u64>, Vec<f32>)>;
+    fn len(&self) -> usize;
+    fn is_empty(&self) -> bool {
+        self.len() == 0
+    }
+}
+
+pub struct CudaSearcher {
+    handle: *mut LeannCudaIndex,
+    dims: usize,
+    /// HnswSearcher ignores `complexity` and always runs expansion_search = 64 (hnsw.rs:49,83).
+    fixed_ef: Option<usize>,
+}
+// The library serialises concurrent calls on one handle internally (see include/leann_cuda.h).
+unsafe impl Send for CudaSearcher {}
+unsafe impl Sync for CudaSearcher {}
+
+fn check(rc: c_int, err: &[u8]) -> anyhow::Result<()> {
+    if rc == 0 {
+        return Ok(());
+    }
+    let end = err.iter().position(|&b| b == 0).unwrap_or(err.len());
+    anyhow::bail!("{}", String::from_utf8_lossy(&err[..end]))
+}
+
+impl CudaSearcher {
+    /// `index_path` is the extension-less base, exactly what `load_searcher` receives.
+    pub fn load(index_path: &Path, dimensions: usize, backend_name: &str, device: i32) -> anyhow::Result<Self> {
+        let (backend, fixed_ef) = match backend_name {
+            "hnsw" => (BACKEND_HNSW, Some(64)),
+            "diskann" => (BACKEND_VAMANA, None),
+            "flat" => (BACKEND_FLAT, None),
+            other => anyhow::bail!("Unknown backend: {}", other),
+        };
+        let base = CString::new(index_path.to_string_lossy().as_bytes())?;
+        let mut handle = std::ptr::null_mut();
+        let mut err = [0u8; 1024];
+        let rc = unsafe {
+            leann_cuda_open(base.as_ptr(), backend, dimensions, METRIC_DEFAULT, device, &mut handle,
+                            err.as_mut_ptr() as *mut c_char, err.len())
+        };
+        check(rc, &err)?;
+        Ok(Self { handle, dims: dimensions, fixed_ef })
+    }
+
+    /// Batched form: `queries` is nq x dims row-major. Returns (keys, dists, counts), nq x k each.
+    pub fn search_batch(&self, queries: &[f32], top_k: usize, ef: usize) -> anyhow::Result<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        let nq = queries.len() / self.dims;
+        let mut keys = vec![u64::MAX; nq * top_k];
+        let mut dists = vec![f32::INFINITY; nq * top_k];
+        let mut counts = vec![0u32; nq];
+        let mut err = [0u8; 1024];
+        let rc = unsafe {
+            leann_cuda_search(self.handle, queries.as_ptr(), nq, top_k, ef, std::ptr::null(), 0, keys.as_mut_ptr(),
+                              dists.as_mut_ptr(), counts.as_mut_ptr(), err.as_mut_ptr() as *mut c_char, err.len())
+        };
+        check(rc, &err)?;
+        Ok((keys, dists, counts))
+    }
+}
+
+impl BackendSearcher for CudaSearcher {
+    fn search(&self, query: &[f32], top_k: usize, complexity: usize) -> anyhow::Result<(Vec<u64>, Vec<f32>)> {
+        let ef = self.fixed_ef.unwrap_or(complexity);
+        let (mut keys, mut dists, counts) = self.search_batch(query, top_k, ef)?;
+        keys.truncate(counts[0] as usize);
+        dists.truncate(counts[0] as usize);
+        Ok((keys, dists))
+    }
+    fn len(&self) -> usize {
+        unsafe { leann_cuda_len(self.handle) }
+    }
+}
+
+impl Drop for CudaSearcher {
+    fn drop(&mut self) {
+        unsafe { leann_cuda_close(self.handle) }
+    }
+}
+
+/// BM25 index built once (the reference rebuilds it per query, searcher.rs:149-150).
+pub struct CudaBm25(*mut LeannCudaBm25);
+unsafe impl Send for CudaBm25 {}
+unsafe impl Sync for CudaBm25 {}
+
+impl CudaBm25 {
+    pub fn build(documents: &[String], device: i32) -> anyhow::Result<Self> {
+        let ptrs: Vec<*const c_char> = documents.iter().map(|d| d.as_ptr() as *const c_char).collect();
+        let lens: Vec<usize> = documents.iter().map(|d| d.len()).collect();
+        let mut h = std::ptr::null_mut();
+        let mut err = [0u8; 1024];
+        let rc = unsafe {
+            leann_cuda_bm25_build(ptrs.as_ptr(), lens.as_ptr(), documents.len(), device, &mut h,
+                                  err.as_mut_ptr() as *mut c_char, err.len())
+        };
+        check(rc, &err)?;
+        Ok(Self(h))
+    }
+}
+impl Drop for CudaBm25 {
+    fn drop(&mut self) {
+        unsafe { leann_cuda_bm25_free(self.0) }
+    }
+}
+
+impl CudaSearcher {
+    /// The arithmetic of `IndexSearcher::search_with_options` (searcher.rs:123-210) for a batch.
+    /// `filter_mask`: bit i set = passage i loads and passes `MetadataFilter::matches`.
+    #[allow(clippy::too_many_arguments)]
+    pub fn hybrid_search(&self, bm25: Option<&CudaBm25>, queries: &[f32], texts: Option<&[String]>, top_k: usize,
+                         complexity: usize, alpha: f32, filter_mask: Option<&[u64]>)
+                         -> anyhow::Result<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        let nq = queries.len() / self.dims;
+        let tptr: Vec<*const c_char> = texts.map(|t| t.iter().map(|s| s.as_ptr() as *const c_char).collect()).unwrap_or_default();
+        let tlen: Vec<usize> = texts.map(|t| t.iter().map(|s| s.len()).collect()).unwrap_or_default();
+        let mut idx = vec![u64::MAX; nq * top_k];
+        let mut scores = vec![0f32; nq * top_k];
+        let mut counts = vec![0u32; nq];
+        let mut err = [0u8; 1024];
+        let rc = unsafe {
+            leann_cuda_hybrid_search(
+                self.handle, bm25.map_or(std::ptr::null(), |b| b.0 as *const _), queries.as_ptr(),
+                if texts.is_some() { tptr.as_ptr() } else { std::ptr::null() },
+                if texts.is_some() { tlen.as_ptr() } else { std::ptr::null() },
+                nq, top_k, self.fixed_ef.unwrap_or(complexity), texts.is_some() as c_int, alpha,
+                filter_mask.map_or(std::ptr::null(), |m| m.as_ptr()), idx.as_mut_ptr(), scores.as_mut_ptr(),
+                counts.as_mut_ptr(), err.as_mut_ptr() as *mut c_char, err.len())
+        };
+        check(rc, &err)?;
+        Ok((idx, scores, counts))
+    }
+}
+
+#[allow(dead_code)]
+fn _unused(_: *const c_void) {}
