@@ -1,10 +1,11 @@
 // api.cu — the C ABI of the vector path (include/leann_cuda.h): open/build/save/search/merge/close.
 // Host logic only; kernels live in graph_search.cu, exact_scan.cu, hnsw_build.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 
-#include "internal.h"
+#include "scan_common.h"
 
 using namespace leann;
 
@@ -149,8 +150,24 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
             ix->scan_scratch_bytes = need;
         }
         FlatView f{ix->vecs, (uint32_t)ix->n, (uint32_t)ix->d, ix->d4, ix->metric};
+        TcIndexView tv{};
+        const TcIndexView* tvp = nullptr;
+        static const bool tc_env_off = getenv("LEANN_CUDA_DISABLE_TC") != nullptr;  // A/B switch for benchmarks
+        if (!tc_env_off && !ix->tc_disabled && exact_scan_tc_supported(f, (uint32_t)nq)) {
+            uint32_t dp8 = (uint32_t)((ix->d + 7) / 8 * 8);
+            if (!ix->tc_bf16) {
+                LEANN_CUDA_CHECK(cudaMalloc(&ix->tc_bf16, ix->n * (size_t)dp8 * 2));
+                LEANN_CUDA_CHECK(cudaMalloc(&ix->tc_norms, ix->n * 4));
+                LEANN_CUDA_CHECK(cudaMalloc(&ix->tc_xmax, 256));
+                exact_scan_tc_prepare(ix->vecs, ix->n, ix->d4, dp8, ix->tc_bf16, ix->tc_norms, ix->tc_xmax, stream);
+            }
+            tv.x_bf16 = ix->tc_bf16; tv.xmax_bits = ix->tc_xmax; tv.dp8 = dp8;
+            tvp = &tv;
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
         launch_exact_scan(f, d_queries, (uint32_t)nq, (uint32_t)k, d_mask, d_keys, d_dists, d_counts, ix->scan_scratch,
-                          ix->scan_scratch_bytes, stream);
+                          ix->scan_scratch_bytes, stream, tvp, sms);
         if (d_stats) LEANN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, nq * 4 * sizeof(uint64_t), stream));
         return;
     }
@@ -446,7 +463,7 @@ void leann_cuda_close(leann_cuda_index* ix) {
     cudaFree(ws.visited); cudaFree(ws.epochs); cudaFree(ws.counter); cudaFree(ws.d_queries); cudaFree(ws.d_keys);
     cudaFree(ws.d_dists); cudaFree(ws.d_counts); cudaFree(ws.d_mask);
     if (ws.stream) cudaStreamDestroy(ws.stream);
-    cudaFree(ix->scan_scratch);
+    cudaFree(ix->scan_scratch); cudaFree(ix->tc_bf16); cudaFree(ix->tc_norms); cudaFree(ix->tc_xmax);
     cudaGetLastError();
     if (prev >= 0) cudaSetDevice(prev);
     delete ix;

@@ -14,7 +14,7 @@
 
 #include <algorithm>
 
-#include "internal.h"
+#include "scan_common.h"
 
 namespace leann {
 
@@ -30,16 +30,6 @@ __device__ __forceinline__ float unorder_f32(uint32_t u) {
     u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
     return __uint_as_float(u);
 }
-
-struct ScanScratch {
-    unsigned long long* cand;      // [nq][cap]
-    uint32_t* cand_cnt;            // [nq]
-    unsigned long long* best;      // [nq][kpad]
-    uint32_t* best_cnt;            // [nq]
-    unsigned long long* thr;       // [nq]
-    uint32_t* overflow;            // [1]
-    float4* qpad;                  // [nq][d4]
-};
 
 // One 128x128 tile of scores, K-loop over the padded dimension, threshold epilogue.
 template <int METRIC>
@@ -310,13 +300,16 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
     uint32_t kpad = (k + 31) & ~31u;
     size_t d4max = d4;
+    size_t dp8 = ((size_t)d4 * 4 + 7) / 8 * 8;
     return align256((size_t)nq * SCAN_CAP * 8) + align256((size_t)nq * 4) + align256((size_t)nq * kpad * 8) +
-           align256((size_t)nq * 4) + align256((size_t)nq * 8) + 256 + align256((size_t)nq * d4max * 16);
+           align256((size_t)nq * 4) + align256((size_t)nq * 8) + 256 + align256((size_t)nq * d4max * 16) +
+           // tensor path: bf16 queries, |q|, dot thresholds, candidate row ids
+           align256((size_t)nq * dp8 * 2) + align256((size_t)nq * 4) + align256((size_t)nq * 4) + align256((size_t)nq * SCAN_CAP * 4);
 }
 
 void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
                        uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const TcIndexView* tv, int sms) {
     if (k == 0 || k > 1024) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: k must be in 1..1024");
     if (nq == 0) return;
     const uint32_t kpad = (k + 31) & ~31u;
@@ -329,10 +322,19 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     s.thr = (unsigned long long*)p; p += align256((size_t)nq * 8);
     s.overflow = (uint32_t*)p; p += 256;
     s.qpad = (float4*)p; p += align256((size_t)nq * f.d4 * 16);
+    TcScratch ts{};
+    const bool use_tc = tv != nullptr && exact_scan_tc_supported(f, nq);
+    if (use_tc) {
+        ts.q_bf16 = p; p += align256((size_t)nq * tv->dp8 * 2);
+        ts.qnorm = (float*)p; p += align256((size_t)nq * 4);
+        ts.thr_dot = (float*)p; p += align256((size_t)nq * 4);
+        ts.cand_ids = (uint32_t*)p; p += align256((size_t)nq * SCAN_CAP * 4);
+    }
     if ((size_t)(p - (unsigned char*)scratch) > scratch_bytes) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: scratch too small");
 
     scan_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.cand_cnt, s.best_cnt, s.thr, nq, s.overflow);
     launch_pad_rows(d_queries, s.qpad, nq, f.d, f.d4, stream);
+    if (use_tc) exact_scan_tc_queries(s.qpad, nq, f.d4, tv->dp8, ts, stream);
 
     const uint32_t growth = std::max<uint32_t>(2u, SCAN_CAP / (8u * k));
     uint32_t r0 = 0;
@@ -345,6 +347,10 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
             uint32_t r1 = (uint32_t)std::min<uint64_t>(f.n, (uint64_t)r0 + want);
             for (int attempt = 0;; ++attempt) {
                 dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);
+                if (use_tc && done_rows > 0) {
+                    // tensor-core pass + fp32 re-rank for every chunk after the first
+                    exact_scan_tc_round(f, *tv, s, ts, nq, r0, r1, d_mask, SCAN_CAP, sms, stream);
+                } else
                 switch (f.metric) {
                     case LEANN_METRIC_L2SQ:
                         scan_tile_kernel<LEANN_METRIC_L2SQ><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);

@@ -1,0 +1,408 @@
+// exact_scan_tc.cu — K2 on the 5th-generation tensor cores: the dense Q·Xᵀ contraction of the exact
+// scan (leann-rs src/index/recompute.rs:96-103) as a tcgen05.mma kernel fed by TMA, followed by K2r, the
+// fp32 re-rank of the surviving candidates (recompute.rs:137-139 arithmetic, f32 throughout).
+//
+//   pass 1 (this kernel): bf16 copies of Q and X, UMMA 128x256x16 (kind::f16, f32 accumulate in TMEM),
+//        operands staged by TMA into 128B-swizzled shared memory, 4-stage mbarrier pipeline, two
+//        TMEM accumulator stages so the epilogue of tile t overlaps the MMAs of tile t+1.
+//        Epilogue: tcgen05.ld, one thread per query row, compares every score with the query's
+//        threshold  T_q = (exact k-th best so far) - eps_q  and appends the row id of the few survivors.
+//        eps_q = 1.25 * 2^-8 * |q| * max|x| + 1e-6 bounds |bf16 score - f32 score| rigorously
+//        (round-to-nearest bf16 on both operands + f32 accumulation), so no true top-k row is dropped.
+//   pass 2 (rerank_kernel): exact f32 dot for each survivor -> packed rank key -> select_kernel.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31). Persistent CTAs walk a static
+// schedule of (query tile, group of database tiles) items ordered so that concurrently running CTAs
+// read the same database tiles (L2 reuse across query tiles).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "scan_common.h"
+
+namespace leann {
+
+namespace {
+
+constexpr int TC_M = 128;        // queries per tile (UMMA M)
+constexpr int TC_N = 256;        // database rows per tile (UMMA N)
+constexpr int TC_K = 64;         // bf16 elements per k-block = 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_M * TC_K * 2;   // 16 KB
+constexpr int TC_B_BYTES = TC_N * TC_K * 2;   // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_GROUP = 8;      // database tiles per schedule item
+constexpr int TC_THREADS = 256;
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups 1024 B apart.
+// SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO [16,30) unused for K-major
+// swizzled layouts, SBO>>4 [32,46) = 64, version [46,48) = 1, layout_type [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major both,
+// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct TcParams {
+    uint32_t nq, r0, r1, kblocks, n_qtiles, n_groups, tiles_total;
+    const float* thr_dot;          // [nq] candidate threshold in dot space (-inf = everything)
+    const uint64_t* mask;          // nullable
+    uint32_t* cand_ids;            // [nq][cap]
+    uint32_t* cand_cnt;            // [nq]
+    uint32_t cap;
+    uint32_t* overflow;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [TC_STAGES]
+    uint64_t* empty_bar = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
+    uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t n_items = p.n_qtiles * p.n_groups;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t qtile = item % p.n_qtiles, grp = item / p.n_qtiles;
+                const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
+                for (uint32_t t = t0; t < t1; ++t)
+                    for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        unsigned char* sa = smem + (size_t)stage * TC_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                        tma_load_2d(sa, &map_q, &full_bar[stage], (int)(kb * TC_K), (int)(qtile * TC_M));
+                        tma_load_2d(sa + TC_A_BYTES, &map_x, &full_bar[stage], (int)(kb * TC_K), (int)(p.r0 + t * TC_N));
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t grp = item / p.n_qtiles;
+                const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TC_N;
+                    for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
+                        const uint64_t da = umma_desc(sa), db = umma_desc(sa + TC_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_K / 16; ++k)  // advance 16 bf16 = 32 B inside the swizzle row
+                            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                        tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(&tmem_full[acc]);         // accumulator ready for the epilogue
+                    acc ^= 1u;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: one thread per query row =====
+        const uint32_t quad = (uint32_t)(warp & 3);
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const uint32_t qtile = item % p.n_qtiles, grp = item / p.n_qtiles;
+            const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
+            const uint32_t q = qtile * TC_M + quad * 32 + lane;
+            const float T = q < p.nq ? p.thr_dot[q] : CUDART_INF_F;
+            for (uint32_t t = t0; t < t1; ++t) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t row_base = p.r0 + t * TC_N;
+#pragma unroll 1
+                for (int c = 0; c < TC_N; c += 32) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((quad * 32u) << 16) + acc * TC_N + (uint32_t)c, r);
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) any |= (__uint_as_float(r[j]) >= T);
+                    if (any) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (__uint_as_float(r[j]) >= T) {
+                                uint32_t row = row_base + (uint32_t)c + (uint32_t)j;
+                                if (row < p.r1 && (!p.mask || ((p.mask[row >> 6] >> (row & 63u)) & 1ull))) {
+                                    uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
+                                    if (pos < p.cap) p.cand_ids[(size_t)q * p.cap + pos] = row;
+                                    else *p.overflow = 1u;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+                acc ^= 1u;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// f32 -> bf16 (round to nearest even) rows padded to dp8 elements; also |row| (f32) for eps.
+__global__ void to_bf16_kernel(const float4* __restrict__ src, uint32_t d4, __nv_bfloat16* __restrict__ dst, uint32_t dp8,
+                               size_t n, float* __restrict__ norms) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float ss = 0.f;
+    for (uint32_t i = lane; i < dp8 / 4; i += 32) {
+        float4 v = i < d4 ? src[row * d4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[i * 2] = a;
+        reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[i * 2 + 1] = b;
+    }
+    for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+    if (lane == 0 && norms) norms[row] = sqrtf(ss) * 1.0000005f;  // rounded up a hair: used only as an upper bound
+}
+
+__global__ void max_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ out_bits) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, v[i]);
+    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+// thr key (packed rank key of the exact k-th best, or ~0) -> dot-space candidate threshold.
+__global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr, const float* __restrict__ qnorm, const uint32_t* xmax_bits,
+                                     uint32_t nq, int metric, float* __restrict__ thr_dot) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long key = thr[q];
+    if (key == ~0ull) { thr_dot[q] = -CUDART_INF_F; return; }
+    uint32_t ok = (uint32_t)(key >> 32);
+    float dotk;
+    if (metric == LEANN_METRIC_DOT_DESC) dotk = scan_unorder_f32(~ok);
+    else dotk = 1.0f - scan_unorder_f32(ok);   // IP / IP_CLAMP: distance = 1 - dot (clamped at 0: dot >= 1 stays conservative)
+    const float xmax = __uint_as_float(*xmax_bits);
+    const float eps = 1.25f * 0.00390625f * qnorm[q] * xmax + 1e-6f;
+    thr_dot[q] = dotk - eps - fabsf(dotk) * 1e-6f;
+}
+
+// K2r: exact f32 score of every survivor -> packed rank key in cand[q][i].
+__global__ void __launch_bounds__(256)
+rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32_t d4, uint32_t nq, int metric,
+              const uint32_t* __restrict__ cand_ids, const uint32_t* __restrict__ cand_cnt, uint32_t cap,
+              unsigned long long* __restrict__ cand) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t n = cand_cnt[q];
+    if (n > cap) n = cap;
+    for (uint32_t i = warp; i < n; i += blockDim.x >> 5) {
+        const uint32_t row = cand_ids[(size_t)q * cap + i];
+        const float4* x = X + (size_t)row * d4;
+        const float4* qq = Q + (size_t)q * d4;
+        float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+        for (uint32_t j = lane; j < d4; j += 32) {
+            float4 a = qq[j], b = __ldg(&x[j]);
+            ax = fmaf(a.x, b.x, ax); ay = fmaf(a.y, b.y, ay); az = fmaf(a.z, b.z, az); aw = fmaf(a.w, b.w, aw);
+        }
+        float s = (ax + ay) + (az + aw);
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+        if (lane == 0) {
+            uint32_t ok;
+            if (metric == LEANN_METRIC_DOT_DESC) ok = ~scan_order_f32(s);
+            else {
+                float dd = 1.0f - s;
+                if (metric == LEANN_METRIC_IP_CLAMP) dd = dd < 0.f ? 0.f : dd;
+                ok = scan_order_f32(dd);
+            }
+            cand[(size_t)q * cap + i] = ((unsigned long long)ok << 32) | row;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !p) throw Error(LEANN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+CUtensorMap make_map(const void* base, uint64_t rows, uint32_t dp8, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {dp8, rows};
+    cuuint64_t strides[1] = {(cuuint64_t)dp8 * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(LEANN_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+}  // namespace
+
+bool exact_scan_tc_supported(const FlatView& f, uint32_t nq) {
+    return (f.metric == LEANN_METRIC_DOT_DESC || f.metric == LEANN_METRIC_IP || f.metric == LEANN_METRIC_IP_CLAMP) && nq >= 64 &&
+           f.d >= 64 && f.n >= 16384;
+}
+
+size_t exact_scan_tc_bf16_bytes(size_t n, uint32_t d) { return n * (size_t)((d + 7) / 8 * 8) * 2 + n * 4 + 256; }
+
+// Builds the bf16 copy + row norms + max norm of a database (called once per index).
+void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t dp8, void* bf16_rows, float* norms,
+                           uint32_t* xmax_bits, cudaStream_t s) {
+    LEANN_CUDA_CHECK(cudaMemsetAsync(xmax_bits, 0, 4, s));
+    if (!n) return;
+    to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(vecs, d4, (__nv_bfloat16*)bf16_rows, dp8, n, norms);
+    max_kernel<<<296, 256, 0, s>>>(norms, n, xmax_bits);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+// One round over rows [r0, r1): tensor pass -> re-rank. `s.thr` must hold the current exact thresholds;
+// on return s.cand / s.cand_cnt hold exact packed keys ready for select_kernel.
+void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq,
+                         uint32_t r0, uint32_t r1, const uint64_t* d_mask, uint32_t cap, int sms, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        attr = true;
+    }
+    dot_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.thr, ts.qnorm, tv.xmax_bits, nq, f.metric, ts.thr_dot);
+    CUtensorMap mq = make_map(ts.q_bf16, nq, tv.dp8, TC_M);
+    CUtensorMap mx = make_map(tv.x_bf16, f.n, tv.dp8, TC_N);
+    TcParams p;
+    p.nq = nq; p.r0 = r0; p.r1 = r1;
+    p.kblocks = (tv.dp8 + TC_K - 1) / TC_K;
+    p.n_qtiles = (nq + TC_M - 1) / TC_M;
+    p.tiles_total = (r1 - r0 + TC_N - 1) / TC_N;
+    p.n_groups = (p.tiles_total + TC_GROUP - 1) / TC_GROUP;
+    p.thr_dot = ts.thr_dot; p.mask = d_mask; p.cand_ids = ts.cand_ids; p.cand_cnt = s.cand_cnt; p.cap = cap; p.overflow = s.overflow;
+    uint32_t items = p.n_qtiles * p.n_groups;
+    int grid = (int)std::min<uint32_t>((uint32_t)sms, items);
+    scan_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(mq, mx, p);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+    rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_t dp8, const TcScratch& ts, cudaStream_t stream) {
+    to_bf16_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(qpad, d4, (__nv_bfloat16*)ts.q_bf16, dp8, nq, ts.qnorm);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace leann

@@ -115,3 +115,44 @@ def test_topk_merge(pkg):
     dd[np.isinf(dd)] = -np.inf
     mk2, md2, _ = pkg.topk_merge_device(torch.from_numpy(keys).cuda(), torch.from_numpy(dd).cuda(), descending=True)
     assert np.array_equal(mk2.cpu().numpy(), mk)
+
+
+# ---- tensor-core path (tcgen05 first pass + fp32 re-rank): n >= 16384, nq >= 64, d >= 64 -----------------
+@pytest.mark.parametrize("metric_name,k,d,n,nq", [("dot", 100, 384, 50000, 200), ("dot", 10, 768, 30000, 130), ("ip", 10, 100, 40000, 96),
+                                                   ("dot", 1, 64, 20000, 64), ("dot", 1000, 128, 70000, 257)])
+def test_exact_scan_tensor_path_parity(orc, pkg, metric_name, k, d, n, nq):
+    x, q = make_data(n, d, 17, nq=nq)
+    pm = {"dot": pkg.METRIC_DOT_DESC, "ip": pkg.METRIC_IP}[metric_name]
+    om = {"dot": 0, "ip": 2}[metric_name]
+    s = pkg.FlatSearcher.from_vectors(x, metric=pm)
+    keys, scores, counts = s.search_batch(q, k, 0)
+    oi, osc, oc = orc.exact_scan(q, x, k, metric=om, nthreads=8)
+    assert np.array_equal(counts, oc)
+    _check_topk(keys, scores, oi, osc, metric_name == "dot")
+    # second call reuses the bf16 copy
+    keys2, scores2, _ = s.search_batch(q, k, 0)
+    assert np.array_equal(keys, keys2) and np.array_equal(scores, scores2)
+
+
+def test_exact_scan_tensor_path_unnormalised_mask_and_sorted(orc, pkg):
+    # un-normalised vectors with widely varying norms: the error margin scales with |q| * max|x|
+    x, q = make_data(30000, 128, 23, nq=80, normalize=False)
+    x *= np.linspace(0.1, 30.0, 30000, dtype=np.float32)[:, None]
+    rng = np.random.default_rng(5)
+    bits = rng.random(30000) < 0.03
+    s = pkg.FlatSearcher.from_vectors(x)
+    keys, scores, counts = s.search_batch(q, 20, 0, mask=pkg.pack_mask(bits))
+    oi, osc, oc = orc.exact_scan(q, x, 20, metric=0, mask=orc.pack_mask(bits), nthreads=8)
+    assert np.array_equal(counts, oc)
+    _check_topk(keys, scores, oi, osc, True)
+    # rows sorted by ascending similarity: every later chunk beats the threshold (overflow re-run on the tensor path)
+    d, n = 64, 80000
+    qv = rng.standard_normal(d).astype(np.float32)
+    qv /= np.linalg.norm(qv)
+    t = np.linspace(-1, 1, n, dtype=np.float32)[:, None]
+    xs = (t * qv[None, :] + 0.001 * rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
+    qs = np.repeat(qv[None, :], 64, axis=0) + 0.01 * rng.standard_normal((64, d)).astype(np.float32)
+    s2 = pkg.FlatSearcher.from_vectors(xs)
+    keys, scores, counts = s2.search_batch(qs, 10, 0)
+    oi, osc, oc = orc.exact_scan(qs, xs, 10, metric=0, nthreads=8)
+    _check_topk(keys, scores, oi, osc, True)
