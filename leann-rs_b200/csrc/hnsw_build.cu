@@ -40,6 +40,8 @@ struct BuildParams {
     uint32_t next_cap, next_capp;
     uint8_t* visited; uint32_t* epochs; uint32_t* counter; size_t n_pad; int n_warps;
     uint32_t* overflow;  // [0]: edge buffer overflow, [1]: extra overflow (dropped links)
+    const uint32_t* order;  // nullable: insertion sequence (node = order[first + i]); identity when null
+    int vamana; float alpha;
 };
 
 __device__ __forceinline__ void carve(unsigned char* base, uint32_t top_cap, uint32_t next_capp, WarpLists& w) {
@@ -56,10 +58,14 @@ __host__ __device__ inline size_t build_smem_per_warp(uint32_t top_cap, uint32_t
 
 // usearch refine_: `top` ascending by distance to the owner; keeps candidate x unless an already
 // kept neighbour is closer to x than the owner is. Returns the new size.
+// vamana != 0 switches to DiskANN's alpha-robust prune (drop x when alpha * d(kept, x) <= d(owner, x);
+// always applied), restating diskann-rs build_index_with_params (diskann.rs:87-100, alpha = 1.2).
 template <int LPV, int VPL, int U>
-__device__ __forceinline__ int refine_heuristic(const GraphView& g, WarpLists& w, int needed, int lane) {
+__device__ __forceinline__ int refine_heuristic(const GraphView& g, WarpLists& w, int needed, int lane, int vamana = 0,
+                                                float alpha = 1.0f) {
     int total = w.top_size;
-    if (total < needed) return total;
+    if (total == 0) return 0;
+    if (!vamana && total < needed) return total;
     int submitted = 1;
     for (int consumed = 1; consumed < total && submitted < needed; ++consumed) {
         uint32_t x = w.top_s[consumed];
@@ -79,7 +85,7 @@ __device__ __forceinline__ int refine_heuristic(const GraphView& g, WarpLists& w
         for (int b = 0; b < submitted && good; b += 8) {
             int c = submitted - b < 8 ? submitted - b : 8;
             eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, qx, w.top_s + b, w.st_dist, c, lane);
-            bool closer = lane < c && w.st_dist[lane] < xd;
+            bool closer = lane < c && (vamana ? (alpha * w.st_dist[lane] <= xd) : (w.st_dist[lane] < xd));
             if (__any_sync(FULL, closer)) good = false;
             __syncwarp();
         }
@@ -111,8 +117,8 @@ insert_search_kernel(const GraphView g, const BuildParams p) {
         if (lane == 0) bi = atomicAdd(p.counter, 1u);
         bi = __shfl_sync(FULL, bi, 0);
         if (bi >= p.count) break;
-        const uint32_t node = p.first + bi;
-        const int node_level = p.levels[node];
+        const uint32_t node = p.order ? p.order[p.first + bi] : p.first + bi;
+        const int node_level = p.levels ? p.levels[node] : 0;
         float4 q[VPL];
         {
             const int lig = lane % LPV;
@@ -137,7 +143,7 @@ insert_search_kernel(const GraphView g, const BuildParams p) {
             LevelAdj adj{g.adj0, g.adjU, g.upper_base, level == 0 ? g.deg0 : g.degU, level};
             beam_level<LPV, VPL, U>(g, adj, q, w, (int)p.ef_add, (int)p.next_cap, (int)p.next_capp - 1, 0, nullptr,
                                     vis, tag, cur, cur_d, c, lane);
-            int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)p.M, lane);
+            int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)p.M, lane, p.vamana, p.alpha);
             // forward links of the new node (its rows are pre-filled with SENT)
             uint32_t* myrow = level == 0 ? p.adj0 + (size_t)node * p.M0
                                          : p.adjU + ((size_t)p.upper_base[node] + (uint32_t)(level - 1)) * p.M;
@@ -233,7 +239,7 @@ prune_kernel(const GraphView g, const BuildParams p) {
             __syncwarp();
             sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, STAGE, 0, 0, dj, sj, lane);
         }
-        int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)cap, lane);
+        int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)cap, lane, p.vamana, p.alpha);
         for (int j = lane; j < (int)cap; j += 32) row[j] = j < kept ? w.top_s[j] : SENT;
         if (lane == 0) { p.cnt[list_id] = (uint32_t)kept; p.flag[list_id] = 0u; }
         __syncwarp();
@@ -356,6 +362,7 @@ void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed
         p.M = (uint32_t)M; p.M0 = (uint32_t)M0; p.ef_add = (uint32_t)ef_add; p.n = (uint32_t)n;
         p.next_cap = (uint32_t)ef_add;
         p.next_capp = 1; while (p.next_capp < p.next_cap) p.next_capp <<= 1;
+        p.order = nullptr; p.vamana = 0; p.alpha = 1.0f;
         int max_warps = graph_search_max_warps(ix->device);
         p.n_pad = (n + 127) & ~(size_t)127;
         {
@@ -393,6 +400,139 @@ void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed
         LEANN_CUDA_CHECK(cudaMemcpyAsync(h_over, p.overflow, 8, cudaMemcpyDeviceToHost, stream));
         LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
         if (h_over[0]) throw Error(LEANN_ERR_CUDA, "hnsw build: reverse-edge buffer overflow");
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+
+namespace {
+
+__global__ void colsum_kernel(const float4* __restrict__ vecs, uint32_t d4, size_t n, float* __restrict__ sums) {
+    // grid.x = column groups of float4, grid.y = row slices
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d4) return;
+    size_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+    size_t r0 = (size_t)blockIdx.y * rows_per, r1 = r0 + rows_per < n ? r0 + rows_per : n;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t r = r0; r < r1; ++r) {
+        float4 v = vecs[r * d4 + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(&sums[c * 4 + 0], acc.x); atomicAdd(&sums[c * 4 + 1], acc.y);
+    atomicAdd(&sums[c * 4 + 2], acc.z); atomicAdd(&sums[c * 4 + 3], acc.w);
+}
+
+// medoid = row nearest (L2) to the centroid; packed (ordered distance, row) atomicMin.
+__global__ void medoid_kernel(const float4* __restrict__ vecs, uint32_t d4, size_t n, const float* __restrict__ sums,
+                              unsigned long long* __restrict__ best) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float inv = 1.0f / (float)n;
+    float s = 0.f;
+    for (uint32_t i = lane; i < d4; i += 32) {
+        float4 v = vecs[row * d4 + i];
+        float a = v.x - sums[i * 4] * inv, b = v.y - sums[i * 4 + 1] * inv, c = v.z - sums[i * 4 + 2] * inv, d = v.w - sums[i * 4 + 3] * inv;
+        s += a * a + b * b + c * c + d * d;
+    }
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+    if (lane == 0) atomicMin(best, ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)row);
+}
+
+}  // namespace
+
+// Vamana construction (diskann-rs build_index_with_params, diskann.rs:70-105): medoid entry point,
+// greedy search with beam L = `complexity`, alpha-robust prune to R, reverse edges with re-prune.
+// Batched insertion (ParlayANN-style prefix doubling) replaces the rayon-parallel passes of the crate;
+// the file written by leann_cuda_save is the same `.diskann` layout.
+void gpu_vamana_build(leann_cuda_index* ix, size_t R, size_t L, float alpha, uint64_t seed) {
+    (void)seed;
+    const size_t n = ix->n;
+    ix->M = (uint32_t)R; ix->M0 = (uint32_t)R;
+    ix->max_level = 0; ix->entry = 0; ix->identity_keys = true; ix->n_upper_lists = 0;
+    cudaStream_t stream = nullptr;
+    LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    std::vector<void*> temps;
+    auto cleanup = [&]() { for (void* t : temps) cudaFree(t); cudaStreamDestroy(stream); };
+    try {
+        ix->adj0 = dmalloc<uint32_t>(n * R);
+        LEANN_CUDA_CHECK(cudaMemset(ix->adj0, 0xFF, std::max<size_t>(n * R, 1) * 4));
+        if (n <= 1) { cleanup(); return; }
+        // ---- medoid ----
+        float* sums = dmalloc<float>(ix->d4 * 4); temps.push_back(sums);
+        unsigned long long* best = dmalloc<unsigned long long>(1); temps.push_back(best);
+        LEANN_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)ix->d4 * 16, stream));
+        LEANN_CUDA_CHECK(cudaMemsetAsync(best, 0xFF, 8, stream));
+        dim3 cg((ix->d4 + 63) / 64, (unsigned)std::min<size_t>(1024, (n + 255) / 256));
+        colsum_kernel<<<cg, 64, 0, stream>>>(ix->vecs, ix->d4, n, sums);
+        medoid_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(ix->vecs, ix->d4, n, sums, best);
+        unsigned long long h_best = 0;
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(&h_best, best, 8, cudaMemcpyDeviceToHost, stream));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const uint32_t medoid = (uint32_t)(h_best & 0xFFFFFFFFull);
+        // insertion order: medoid first, then slot order
+        std::vector<uint32_t> order(n);
+        order[0] = medoid;
+        for (size_t i = 0, o = 1; i < n; ++i) if (i != medoid) order[o++] = (uint32_t)i;
+        uint32_t* d_order = dmalloc<uint32_t>(n); temps.push_back(d_order);
+        LEANN_CUDA_CHECK(cudaMemcpy(d_order, order.data(), n * 4, cudaMemcpyHostToDevice));
+
+        const uint32_t MAXB = 16384;
+        BuildParams p{};
+        p.adj0 = ix->adj0; p.adjU = nullptr; p.upper_base = nullptr; p.levels = nullptr;
+        p.cnt = dmalloc<uint32_t>(n); temps.push_back(p.cnt);
+        p.flag = dmalloc<uint32_t>(n); temps.push_back(p.flag);
+        p.extra = dmalloc<uint32_t>(n * EXTRA); temps.push_back(p.extra);
+        LEANN_CUDA_CHECK(cudaMemset(p.cnt, 0, n * 4));
+        LEANN_CUDA_CHECK(cudaMemset(p.flag, 0, n * 4));
+        p.max_edges = (uint32_t)std::min<size_t>((size_t)MAXB * R + 1024, (size_t)0x7FFFFFFF);
+        p.edges = dmalloc<uint2>(p.max_edges); temps.push_back(p.edges);
+        p.edge_level = dmalloc<uint32_t>(p.max_edges); temps.push_back(p.edge_level);
+        p.work = dmalloc<uint2>(p.max_edges); temps.push_back(p.work);
+        uint32_t* ctrs = dmalloc<uint32_t>(8); temps.push_back(ctrs);
+        LEANN_CUDA_CHECK(cudaMemset(ctrs, 0, 32));
+        p.edge_count = ctrs; p.work_count = ctrs + 1; p.work_cursor = ctrs + 2; p.counter = ctrs + 3; p.overflow = ctrs + 4;
+        p.M = (uint32_t)R; p.M0 = (uint32_t)R; p.ef_add = (uint32_t)std::max(L, R); p.n = (uint32_t)n;
+        p.next_cap = p.ef_add;
+        p.next_capp = 1; while (p.next_capp < p.next_cap) p.next_capp <<= 1;
+        p.order = d_order; p.vamana = 1; p.alpha = alpha;
+        int max_warps = graph_search_max_warps(ix->device);
+        p.n_pad = (n + 127) & ~(size_t)127;
+        {
+            size_t free_b = 0, total_b = 0;
+            LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            while (max_warps > 64 && (size_t)max_warps * p.n_pad > free_b / 4) max_warps /= 2;
+        }
+        max_warps = (int)std::min<size_t>((size_t)max_warps, (size_t)MAXB);
+        p.visited = dmalloc<uint8_t>((size_t)max_warps * p.n_pad); temps.push_back(p.visited);
+        p.epochs = dmalloc<uint32_t>(max_warps); temps.push_back(p.epochs);
+        LEANN_CUDA_CHECK(cudaMemset(p.visited, 0, (size_t)max_warps * p.n_pad));
+        LEANN_CUDA_CHECK(cudaMemset(p.epochs, 0, (size_t)max_warps * 4));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+        ix->entry = medoid;  // searches during the build start from the medoid, as they will afterwards
+        size_t inserted = 1;
+        while (inserted < n) {
+            uint32_t b = (uint32_t)std::min<size_t>(std::min<size_t>(n - inserted, MAXB), std::max<size_t>(1, inserted / 16));
+            p.first = (uint32_t)inserted; p.count = b;
+            p.n_warps = (int)std::min<uint32_t>((uint32_t)max_warps, (b + 3u) & ~3u);
+            GraphView g = ix->view();
+            LEANN_CUDA_CHECK(cudaMemsetAsync(ctrs, 0, 16, stream));
+            dispatch_dims((uint32_t)ix->d, ix->d4, LaunchA{g, p, stream});
+            uint32_t max_e = std::min<uint32_t>(p.max_edges, b * (uint32_t)R);
+            reverse_append_kernel<<<(max_e + 255) / 256, 256, 0, stream>>>(p);
+            LEANN_CUDA_CHECK(cudaGetLastError());
+            int pblocks = (int)std::min<uint32_t>((uint32_t)sms * 3u, (max_e + 3u) / 4u);
+            dispatch_dims((uint32_t)ix->d, ix->d4, LaunchC{g, p, stream, std::max(pblocks, 1)});
+            inserted += b;
+        }
+        uint32_t h_over[2] = {0, 0};
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(h_over, p.overflow, 8, cudaMemcpyDeviceToHost, stream));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (h_over[0]) throw Error(LEANN_ERR_CUDA, "vamana build: reverse-edge buffer overflow");
     } catch (...) {
         cleanup();
         throw;

@@ -51,3 +51,30 @@ def test_gpu_hnsw_build_tiny_and_device_input(orc, pkg):
     s = pkg.HnswSearcher.build(torch.from_numpy(x).cuda(), graph_degree=32, complexity=64)
     gt = orc.exact_f64(q, x, 10)
     assert _recall(s.search_batch(q, 10, 64)[0], gt, 10) > 0.9
+
+
+def test_gpu_vamana_build_quality_and_file(orc, pkg, tmp_path):
+    n, d, R, L, k = 20000, 96, 32, 64, 10
+    x, q = make_data(n, d, 41, nq=300)
+    s = pkg.DiskAnnSearcher.build(x, graph_degree=R, complexity=L, alpha=1.2)
+    info = s.info()
+    assert info["n"] == n and info["M0"] == R and info["max_level"] == 0
+    gt = orc.exact_f64(q, x, k)
+    keys, dists, counts = s.search_batch(q, k, L)
+    r_gpu = _recall(keys, gt, k)
+    g_cpu = orc.Vamana.build(x[:6000], R=R, L=L, alpha=1.2, seed=3)     # CPU reference build is slow: smaller set
+    r_cpu = _recall(g_cpu.search(q, k, L)[0], orc.exact_f64(q, x[:6000], k), k)
+    assert r_gpu > 0.9 and r_gpu > r_cpu - 0.05, (r_gpu, r_cpu)
+    base = str(tmp_path / "documents.leann")
+    s.save(base)
+    g = orc.Vamana.load(base.replace(".leann", ".diskann"))      # checks header + size equation
+    assert g.info() == {"n": n, "d": d, "R": R, "medoid": info["entry"]}
+    ok, od, oc, _ = g.search(q, k, L, lanes=pkg.reduction_lanes(d), next_cap=L)
+    assert np.array_equal(keys, ok) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
+    s2 = pkg.DiskAnnSearcher.load(base, d)
+    assert np.array_equal(s2.search_batch(q, k, L)[0], keys)
+    # L2 metric on un-normalised data (BASELINE C4)
+    x2, q2 = make_data(n, d, 42, nq=200, normalize=False)
+    s3 = pkg.DiskAnnSearcher.build(x2, graph_degree=R, complexity=L, metric=pkg.METRIC_L2SQ)
+    gt2 = orc.exact_f64(q2, x2, k, metric=1)
+    assert _recall(s3.search_batch(q2, k, L)[0], gt2, k) > 0.9
