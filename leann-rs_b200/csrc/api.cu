@@ -105,11 +105,13 @@ leann_cuda_index* from_vamana(HostVamana& h, int device, int metric) {
     return ix.release();
 }
 
-void ensure_workspace(const leann_cuda_index* ix, size_t nq) {
+void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 12) {
     SearchWorkspace& ws = ix->ws;
     if (!ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
     if (ix->backend == LEANN_BACKEND_FLAT) return;
-    int max_warps = graph_search_max_warps(ix->device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+    int max_warps = sms * std::max(warps_per_sm, 4);
     size_t n_pad = (ix->n + 127) & ~(size_t)127;
     // bound the visited workspace to ~1/8 of device memory
     size_t free_b = 0, total_b = 0;
@@ -140,8 +142,8 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
     if (nq == 0) return;
     if (k == 0) throw Error(LEANN_ERR_INVALID_ARG, "k must be > 0");
     if (mask_mode == LEANN_MASK_NONE) d_mask = nullptr;
-    ensure_workspace(ix, nq);
     if (ix->backend == LEANN_BACKEND_FLAT) {
+        ensure_workspace(ix, nq);
         size_t need = exact_scan_scratch_bytes(ix->d4, (uint32_t)nq, (uint32_t)k);
         if (ix->scan_scratch_bytes < need) {
             if (ix->scan_scratch) cudaFree(ix->scan_scratch);
@@ -179,6 +181,7 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
     p.nq = (uint32_t)nq; p.k = (uint32_t)k; p.ef = (uint32_t)eff;
     p.next_cap = (uint32_t)leann_cuda_queue_capacity(eff, d_mask != nullptr);
     p.next_capp = next_pow2(p.next_cap);
+    ensure_workspace(ix, nq, graph_search_warps_per_sm(ix->view(), p.ef, p.next_capp));
     p.mask = d_mask;
     p.nonstrict_term = ix->backend == LEANN_BACKEND_VAMANA ? 1 : 0;
     p.out_keys = d_keys; p.out_dists = d_dists; p.out_counts = d_counts; p.out_stats = d_stats;

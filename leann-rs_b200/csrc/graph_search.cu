@@ -12,8 +12,8 @@
 
 namespace leann {
 
-template <int LPV, int VPL, int U>
-__global__ void __launch_bounds__(128)
+template <int LPV, int VPL, int U, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 graph_search_kernel(const GraphView g, const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -97,45 +97,60 @@ size_t graph_search_smem_per_warp(uint32_t ef, uint32_t next_capp) {
 int graph_search_max_warps(int device) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return sms * 12;  // 3 CTAs x 4 warps per SM (register-bound, see -Xptxas -v)
+    return sms * 12;  // builder kernels: 3 CTAs x 4 warps per SM (register-bound, see -Xptxas -v)
 }
 
 namespace {
-template <int LPV, int VPL, int U>
-void launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream) {
+// op 0: launch; op 1: report resident warps per SM for this instantiation and shared-memory size.
+template <int LPV, int VPL, int U, int MINB>
+int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
     const int warps_per_block = 4;
     size_t smem = graph_search_smem_per_warp(p.ef, p.next_capp) * warps_per_block;
-    auto kern = graph_search_kernel<LPV, VPL, U>;
+    auto kern = graph_search_kernel<LPV, VPL, U, MINB>;
     if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (op == 1) {
+        int blocks_per_sm = 0;
+        LEANN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, warps_per_block * 32, smem));
+        return blocks_per_sm * warps_per_block;
+    }
     int blocks = (p.n_warps + warps_per_block - 1) / warps_per_block;
     LEANN_CUDA_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), stream));
     kern<<<blocks, warps_per_block * 32, smem, stream>>>(g, p);
     LEANN_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
-}  // namespace
 
-void launch_graph_search(const GraphView& g, const SearchParams& p, cudaStream_t stream) {
+int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
     if (g.deg0 > (uint32_t)MAX_DEG || g.degU > (uint32_t)MAX_DEG)
         throw Error(LEANN_ERR_INVALID_ARG, "graph degree exceeds MAX_DEG (128)");
     if (p.ef > (uint32_t)MAX_EF) throw Error(LEANN_ERR_INVALID_ARG, "ef exceeds 1024");
     const uint32_t d4 = g.d4;
     if (reduction_lanes(g.d) == 8) {
+        // small rows: the traversal is instruction-latency bound, so favour resident warps over unroll depth
         uint32_t vpl = (d4 + 7) / 8;
-        if (vpl <= 2) launch_t<8, 2, 8>(g, p, stream);
-        else if (vpl <= 3) launch_t<8, 3, 8>(g, p, stream);
-        else if (vpl <= 4) launch_t<8, 4, 4>(g, p, stream);
-        else launch_t<8, 8, 2>(g, p, stream);
-    } else {
-        uint32_t vpl = (d4 + 31) / 32;
-        if (vpl <= 3) launch_t<32, 3, 8>(g, p, stream);
-        else if (vpl <= 4) launch_t<32, 4, 4>(g, p, stream);
-        else if (vpl <= 6) launch_t<32, 6, 4>(g, p, stream);
-        else if (vpl <= 8) launch_t<32, 8, 2>(g, p, stream);
-        else if (vpl <= 12) launch_t<32, 12, 2>(g, p, stream);
-        else if (vpl <= 16) launch_t<32, 16, 1>(g, p, stream);
-        else if (vpl <= 32) launch_t<32, 32, 1>(g, p, stream);
-        else throw Error(LEANN_ERR_INVALID_ARG, "dimension above 4096 is not supported");
+        if (vpl <= 2) return launch_t<8, 2, 4, 6>(g, p, stream, op);
+        if (vpl <= 3) return launch_t<8, 3, 4, 5>(g, p, stream, op);
+        if (vpl <= 4) return launch_t<8, 4, 4, 4>(g, p, stream, op);
+        return launch_t<8, 8, 2, 3>(g, p, stream, op);
     }
+    uint32_t vpl = (d4 + 31) / 32;
+    if (vpl <= 3) return launch_t<32, 3, 8, 3>(g, p, stream, op);
+    if (vpl <= 4) return launch_t<32, 4, 4, 4>(g, p, stream, op);
+    if (vpl <= 6) return launch_t<32, 6, 4, 3>(g, p, stream, op);
+    if (vpl <= 8) return launch_t<32, 8, 2, 3>(g, p, stream, op);
+    if (vpl <= 12) return launch_t<32, 12, 2, 2>(g, p, stream, op);
+    if (vpl <= 16) return launch_t<32, 16, 1, 3>(g, p, stream, op);
+    if (vpl <= 32) return launch_t<32, 32, 1, 2>(g, p, stream, op);
+    throw Error(LEANN_ERR_INVALID_ARG, "dimension above 4096 is not supported");
 }
+}  // namespace
+
+int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp) {
+    SearchParams p{};
+    p.ef = ef; p.next_capp = next_capp;
+    return dispatch_search(g, p, nullptr, 1);
+}
+
+void launch_graph_search(const GraphView& g, const SearchParams& p, cudaStream_t stream) { dispatch_search(g, p, stream, 0); }
 
 }  // namespace leann

@@ -250,8 +250,8 @@ template <typename F>
 void dispatch_dims(uint32_t d, uint32_t d4, F&& f) {
     if (reduction_lanes(d) == 8) {
         uint32_t vpl = (d4 + 7) / 8;
-        if (vpl <= 2) f.template operator()<8, 2, 8>();
-        else if (vpl <= 3) f.template operator()<8, 3, 8>();
+        if (vpl <= 2) f.template operator()<8, 2, 4>();
+        else if (vpl <= 3) f.template operator()<8, 3, 4>();
         else if (vpl <= 4) f.template operator()<8, 4, 4>();
         else f.template operator()<8, 8, 2>();
     } else {

@@ -102,6 +102,7 @@ int reduction_lanes(size_t dims);
 void launch_graph_search(const GraphView& g, const SearchParams& p, cudaStream_t stream);
 size_t graph_search_smem_per_warp(uint32_t ef, uint32_t next_capp);
 int graph_search_max_warps(int device);
+int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp);
 
 // Exact scan (K2 + K2r)
 struct FlatView { const float4* vecs; uint32_t n, d, d4; int metric; };
