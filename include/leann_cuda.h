@@ -107,6 +107,13 @@ int leann_cuda_search(const leann_cuda_index* index, const float* queries, size_
                       size_t ef, const uint64_t* mask_bits, int mask_mode, uint64_t* keys,
                       float* dists, uint32_t* counts, char* err, size_t errlen);
 
+/* Request coalescing. The reference API is one query per call and `leann serve` issues
+ * those calls concurrently on one shared searcher (src/cli/serve.rs:84,260-311). With max_batch > 1, calls
+ * with nq == 1 (no mask) arriving within max_wait_us of each other are merged into one batched launch; each
+ * caller still gets exactly its own result. max_batch <= 1 disables (default). */
+int leann_cuda_set_coalescing(leann_cuda_index* index, size_t max_batch, unsigned max_wait_us);
+int leann_cuda_coalescing_stats(const leann_cuda_index* index, uint64_t* batches, uint64_t* requests);
+
 /* Same, all pointers in device memory of the index's device, enqueued on `cuda_stream`
  * (a cudaStream_t; NULL = default stream) without host synchronisation.
  * d_stats: nullable, nq x 4 u64 = (distance evaluations, level-0 hops, upper-level hops, queue drops). */

@@ -66,6 +66,8 @@ def lib():
         "leann_cuda_search_device": (C.c_int, [vp, vp, sz, sz, sz, vp, C.c_int, vp, vp, vp, vp, vp, cp, sz]),
         "leann_cuda_topk_merge_device": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, vp, vp, vp, vp, cp, sz]),
         "leann_cuda_close": (None, [vp]),
+        "leann_cuda_set_coalescing": (C.c_int, [vp, sz, C.c_uint]),
+        "leann_cuda_coalescing_stats": (C.c_int, [vp, u64p, u64p]),
         "leann_cuda_device_count": (C.c_int, []),
         "leann_cuda_version": (cp, []),
         "leann_cuda_bm25_build": (C.c_int, [cpp, szp, sz, C.c_int, pp, cp, sz]),
@@ -239,6 +241,15 @@ class BackendSearcher:
             C.c_void_p(keys.data_ptr()), C.c_void_p(dists.data_ptr()), C.c_void_p(counts.data_ptr()),
             None if stats is None else C.c_void_p(stats.data_ptr()), C.c_void_p(st), e, 1024), e)
         return keys, dists, counts
+
+    def set_coalescing(self, max_batch: int, max_wait_us: int = 200):
+        """Merge concurrent single-query `search` calls into batched launches (serve.rs traffic)."""
+        lib().leann_cuda_set_coalescing(self._h, max_batch, max_wait_us)
+
+    def coalescing_stats(self):
+        b, r = C.c_uint64(), C.c_uint64()
+        lib().leann_cuda_coalescing_stats(self._h, C.byref(b), C.byref(r))
+        return int(b.value), int(r.value)
 
     def save(self, base_path: str):
         e = _err()

@@ -1,6 +1,7 @@
 // api.cu — the C ABI of the vector path (include/leann_cuda.h): open/build/save/search/merge/close.
 // Host logic only; kernels live in graph_search.cu, exact_scan.cu, hnsw_build.cu.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <functional>
 #include <memory>
@@ -407,6 +408,88 @@ int leann_cuda_search_device(const leann_cuda_index* ix, const float* d_queries,
     });
 }
 
+static void search_host_locked(const leann_cuda_index* ix, const float* queries, size_t nq, size_t k, size_t ef,
+                               const uint64_t* mask_bits, int mask_mode, uint64_t* keys, float* dists, uint32_t* counts) {
+    DeviceGuard dg(ix->device);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ensure_workspace(ix, nq);
+    SearchWorkspace& ws = ix->ws;
+    ensure_buf(ws.d_queries, ws.cap_q, nq * ix->d);
+    size_t out_need = nq * k;
+    if (ws.cap_out < out_need) {
+        if (ws.d_keys) cudaFree(ws.d_keys);
+        if (ws.d_dists) cudaFree(ws.d_dists);
+        ws.d_keys = nullptr; ws.d_dists = nullptr; ws.cap_out = 0;
+        LEANN_CUDA_CHECK(cudaMalloc(&ws.d_keys, out_need * 8));
+        LEANN_CUDA_CHECK(cudaMalloc(&ws.d_dists, out_need * 4));
+        ws.cap_out = out_need;
+    }
+    ensure_buf(ws.d_counts, ws.cap_counts, nq);
+    uint32_t* d_counts = ws.d_counts;
+    const uint64_t* d_mask = nullptr;
+    if (mask_bits && mask_mode != LEANN_MASK_NONE) {
+        size_t words = (ix->n + 63) / 64;
+        ensure_buf(ws.d_mask, ws.cap_mask, words);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(ws.d_mask, mask_bits, words * 8, cudaMemcpyHostToDevice, ws.stream));
+        d_mask = ws.d_mask;
+    }
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(ws.d_queries, queries, nq * ix->d * 4, cudaMemcpyHostToDevice, ws.stream));
+    search_device_impl(ix, ws.d_queries, nq, k, ef, d_mask, mask_mode, ws.d_keys, ws.d_dists, d_counts, nullptr, ws.stream);
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(keys, ws.d_keys, out_need * 8, cudaMemcpyDeviceToHost, ws.stream));
+    LEANN_CUDA_CHECK(cudaMemcpyAsync(dists, ws.d_dists, out_need * 4, cudaMemcpyDeviceToHost, ws.stream));
+    if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts, nq * 4, cudaMemcpyDeviceToHost, ws.stream));
+    LEANN_CUDA_CHECK(cudaStreamSynchronize(ws.stream));
+}
+
+// One query from one thread, coalescing enabled: join (or lead) a batch.
+static void search_coalesced(const leann_cuda_index* ix, const float* query, size_t k, size_t ef, uint64_t* keys, float* dists,
+                             uint32_t* count) {
+    Coalescer& c = ix->coalescer;
+    CoalesceReq r{query, k, ef, keys, dists, count};
+    std::unique_lock<std::mutex> lk(c.m);
+    c.queue.push_back(&r);
+    c.cv_leader.notify_one();
+    while (!r.done) {
+        if (c.leader_active) { c.cv_done.wait(lk); continue; }
+        c.leader_active = true;
+        auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(c.max_wait_us);
+        while (c.queue.size() < c.max_batch)
+            if (c.cv_leader.wait_until(lk, deadline) == std::cv_status::timeout) break;
+        // the batch = every queued request with this thread's (k, ef), in arrival order
+        std::vector<CoalesceReq*> batch, rest;
+        for (CoalesceReq* q : c.queue) ((q->k == r.k && q->ef == r.ef && batch.size() < c.max_batch) ? batch : rest).push_back(q);
+        c.queue.swap(rest);
+        c.leader_active = false;
+        c.batches++; c.requests += batch.size();
+        c.cv_done.notify_all();   // another waiter may lead the remaining requests while this batch runs
+        lk.unlock();
+        const size_t nb = batch.size(), d = ix->d;
+        std::vector<float> qbuf(nb * d);
+        std::vector<uint64_t> kbuf(nb * k);
+        std::vector<float> dbuf(nb * k);
+        std::vector<uint32_t> cbuf(nb);
+        for (size_t i = 0; i < nb; ++i) memcpy(&qbuf[i * d], batch[i]->query, d * 4);
+        int rc = 0;
+        std::string msg;
+        try {
+            search_host_locked(ix, qbuf.data(), nb, k, ef, nullptr, LEANN_MASK_NONE, kbuf.data(), dbuf.data(), cbuf.data());
+        } catch (const Error& e) { rc = e.code; msg = e.what(); }
+        catch (const std::exception& e) { rc = LEANN_ERR_INVALID_ARG; msg = e.what(); }
+        lk.lock();
+        for (size_t i = 0; i < nb; ++i) {
+            CoalesceReq* q = batch[i];
+            if (rc == 0) {
+                memcpy(q->keys, &kbuf[i * k], k * 8);
+                memcpy(q->dists, &dbuf[i * k], k * 4);
+                if (q->count) *q->count = cbuf[i];
+            }
+            q->rc = rc; q->err = msg; q->done = true;
+        }
+        c.cv_done.notify_all();
+    }
+    if (r.rc != 0) throw Error(r.rc, r.err);
+}
+
 int leann_cuda_search(const leann_cuda_index* ix, const float* queries, size_t nq, size_t k, size_t ef,
                       const uint64_t* mask_bits, int mask_mode, uint64_t* keys, float* dists, uint32_t* counts,
                       char* err, size_t errlen) {
@@ -414,36 +497,29 @@ int leann_cuda_search(const leann_cuda_index* ix, const float* queries, size_t n
         if (!ix) throw Error(LEANN_ERR_INVALID_ARG, "null index");
         if (nq == 0) return;
         if (!queries || !keys || !dists) throw Error(LEANN_ERR_INVALID_ARG, "null buffer");
-        DeviceGuard dg(ix->device);
-        std::lock_guard<std::mutex> lk(ix->mu);
-        ensure_workspace(ix, nq);
-        SearchWorkspace& ws = ix->ws;
-        ensure_buf(ws.d_queries, ws.cap_q, nq * ix->d);
-        size_t out_need = nq * k;
-        if (ws.cap_out < out_need) {
-            if (ws.d_keys) cudaFree(ws.d_keys);
-            if (ws.d_dists) cudaFree(ws.d_dists);
-            ws.d_keys = nullptr; ws.d_dists = nullptr; ws.cap_out = 0;
-            LEANN_CUDA_CHECK(cudaMalloc(&ws.d_keys, out_need * 8));
-            LEANN_CUDA_CHECK(cudaMalloc(&ws.d_dists, out_need * 4));
-            ws.cap_out = out_need;
+        if (k == 0) throw Error(LEANN_ERR_INVALID_ARG, "k must be > 0");
+        const bool masked = mask_bits && mask_mode != LEANN_MASK_NONE;
+        if (nq == 1 && !masked && ix->coalescer.max_batch > 1) {
+            search_coalesced(ix, queries, k, ef, keys, dists, counts);
+            return;
         }
-        ensure_buf(ws.d_counts, ws.cap_counts, nq);
-        uint32_t* d_counts = ws.d_counts;
-        const uint64_t* d_mask = nullptr;
-        if (mask_bits && mask_mode != LEANN_MASK_NONE) {
-            size_t words = (ix->n + 63) / 64;
-            ensure_buf(ws.d_mask, ws.cap_mask, words);
-            LEANN_CUDA_CHECK(cudaMemcpyAsync(ws.d_mask, mask_bits, words * 8, cudaMemcpyHostToDevice, ws.stream));
-            d_mask = ws.d_mask;
-        }
-        LEANN_CUDA_CHECK(cudaMemcpyAsync(ws.d_queries, queries, nq * ix->d * 4, cudaMemcpyHostToDevice, ws.stream));
-        search_device_impl(ix, ws.d_queries, nq, k, ef, d_mask, mask_mode, ws.d_keys, ws.d_dists, d_counts, nullptr, ws.stream);
-        LEANN_CUDA_CHECK(cudaMemcpyAsync(keys, ws.d_keys, out_need * 8, cudaMemcpyDeviceToHost, ws.stream));
-        LEANN_CUDA_CHECK(cudaMemcpyAsync(dists, ws.d_dists, out_need * 4, cudaMemcpyDeviceToHost, ws.stream));
-        if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts, nq * 4, cudaMemcpyDeviceToHost, ws.stream));
-        LEANN_CUDA_CHECK(cudaStreamSynchronize(ws.stream));
+        search_host_locked(ix, queries, nq, k, ef, mask_bits, mask_mode, keys, dists, counts);
     });
+}
+
+int leann_cuda_set_coalescing(leann_cuda_index* ix, size_t max_batch, unsigned max_wait_us) {
+    if (!ix) return LEANN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ix->coalescer.m);
+    ix->coalescer.max_batch = max_batch;
+    ix->coalescer.max_wait_us = max_wait_us;
+    return LEANN_OK;
+}
+int leann_cuda_coalescing_stats(const leann_cuda_index* ix, uint64_t* batches, uint64_t* requests) {
+    if (!ix) return LEANN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ix->coalescer.m);
+    if (batches) *batches = ix->coalescer.batches;
+    if (requests) *requests = ix->coalescer.requests;
+    return LEANN_OK;
 }
 
 int leann_cuda_topk_merge_device(const uint64_t* d_keys_in, const float* d_dists_in, size_t n_shards, size_t nq,

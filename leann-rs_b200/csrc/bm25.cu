@@ -9,6 +9,8 @@
 // Arithmetic is f32 with the reference's operation order and no FMA contraction, so scores are
 // bit-identical: per document the contributions are added in query-token order (tokens are
 // processed one after another; inside one token every posting is a distinct document).
+// The per-posting contribution idf*(tf*(K1+1))/(tf+K1*norm) does not depend on the query, so it is
+// computed once at build time (host, same f32 operation order) and the kernels only stream and add.
 // Bound: HBM (postings stream). Algorithmic bytes per query = sum_t df_t * 8.
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -32,22 +34,12 @@ __device__ __forceinline__ float unorder_f32(uint32_t u) {
     return __uint_as_float(u);
 }
 
-// bm25.rs:97-100 with norm precomputed: score = idf * (tf * (K1 + 1)) / (tf + K1 * norm)
-__device__ __forceinline__ float bm25_term(float idf, float tf, float norm) {
-    const float K1 = 1.2f;
-    const float K1P1 = __fadd_rn(K1, 1.0f);
-    float num = __fmul_rn(idf, __fmul_rn(tf, K1P1));
-    float den = __fadd_rn(tf, __fmul_rn(K1, norm));
-    return __fdiv_rn(num, den);
-}
-
 __global__ void bm25_token_dense_kernel(Bm25Dev b, uint32_t term, float* __restrict__ scores) {
     uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
     uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
     uint32_t doc = b.post_doc[p];
-    float s = bm25_term(b.idf[term], (float)b.post_tf[p], b.norm[doc]);
-    scores[doc] = __fadd_rn(scores[doc], s);
+    scores[doc] = __fadd_rn(scores[doc], b.post_score[p]);
 }
 
 __device__ void block_sort_4096(unsigned long long* keys) {
@@ -101,12 +93,18 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
         // ---- pass 1: accumulate, tokens in query order (duplicates counted again, bm25.rs:81) ----
         for (uint64_t t = t0; t < t1; ++t) {
             const uint32_t term = qtok_term[t];
-            const float idf = b.idf[term];
             const uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
-            for (uint64_t p = p0 + tid; p < p1; p += BM_THREADS) {
+            // postings are doc-ascending and distinct inside a term: plain read-modify-write, 4 in flight per thread
+            uint64_t p = p0 + tid;
+            for (; p + 3 * BM_THREADS < p1; p += 4 * BM_THREADS) {
+                uint32_t d0 = b.post_doc[p], d1 = b.post_doc[p + BM_THREADS], d2 = b.post_doc[p + 2 * BM_THREADS], d3 = b.post_doc[p + 3 * BM_THREADS];
+                float s0 = b.post_score[p], s1 = b.post_score[p + BM_THREADS], s2 = b.post_score[p + 2 * BM_THREADS], s3 = b.post_score[p + 3 * BM_THREADS];
+                float a0 = acc[d0], a1 = acc[d1], a2 = acc[d2], a3 = acc[d3];
+                acc[d0] = __fadd_rn(a0, s0); acc[d1] = __fadd_rn(a1, s1); acc[d2] = __fadd_rn(a2, s2); acc[d3] = __fadd_rn(a3, s3);
+            }
+            for (; p < p1; p += BM_THREADS) {
                 uint32_t doc = b.post_doc[p];
-                float s = bm25_term(idf, (float)b.post_tf[p], b.norm[doc]);
-                acc[doc] = __fadd_rn(acc[doc], s);
+                acc[doc] = __fadd_rn(acc[doc], b.post_score[p]);
             }
             __syncthreads();
         }

@@ -9,9 +9,7 @@ struct Bm25Dev {
     uint32_t n_docs;
     const uint64_t* term_off;  // [n_terms + 1]
     const uint32_t* post_doc;  // [n_postings] ascending inside a term
-    const uint32_t* post_tf;   // [n_postings]
-    const float* idf;          // [n_terms]
-    const float* norm;         // [n_docs]
+    const float* post_score;   // [n_postings] per-posting BM25 contribution (query independent)
 };
 
 void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
@@ -39,14 +37,12 @@ struct leann_cuda_bm25 {
     leann::Bm25Host host;
     uint64_t* d_term_off = nullptr;
     uint32_t* d_post_doc = nullptr;
-    uint32_t* d_post_tf = nullptr;
-    float* d_idf = nullptr;
-    float* d_norm = nullptr;
+    float* d_post_score = nullptr;
     // per-handle workspace
     mutable std::mutex mu;
     mutable float* d_acc = nullptr;   // [n_ctas][n_docs], zero between calls
     mutable int n_ctas = 0;
     mutable uint32_t* d_qcounter = nullptr;
     mutable cudaStream_t stream = nullptr;
-    leann::Bm25Dev view() const { return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_tf, d_idf, d_norm}; }
+    leann::Bm25Dev view() const { return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_score}; }
 };

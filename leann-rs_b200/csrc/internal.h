@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -119,6 +120,26 @@ void launch_pad_rows(const float* src, float4* dst, size_t n, uint32_t d, uint32
 
 }  // namespace leann
 
+namespace leann {
+// Request coalescing: concurrent nq=1 callers of one handle (the axum handlers of
+// src/cli/serve.rs:260-311 share one searcher) are merged into one batched launch by a leader/follower
+// scheme; no background thread.
+struct CoalesceReq {
+    const float* query; size_t k, ef;
+    uint64_t* keys; float* dists; uint32_t* count;
+    int rc = 0; std::string err; bool done = false;
+};
+struct Coalescer {
+    std::mutex m;
+    std::condition_variable cv_leader, cv_done;
+    bool leader_active = false;
+    size_t max_batch = 0;        // 0 = disabled
+    unsigned max_wait_us = 0;
+    std::vector<CoalesceReq*> queue;
+    uint64_t batches = 0, requests = 0;
+};
+}  // namespace leann
+
 struct leann_cuda_index {
     int backend = LEANN_BACKEND_HNSW;
     int device = 0;
@@ -148,6 +169,7 @@ struct leann_cuda_index {
     mutable float* tc_norms = nullptr;
     mutable uint32_t* tc_xmax = nullptr;
     mutable bool tc_disabled = false;
+    mutable leann::Coalescer coalescer;
     leann::GraphView view() const {
         leann::GraphView g;
         g.vecs = vecs; g.adj0 = adj0; g.upper_base = upper_base; g.adjU = adjU;

@@ -262,6 +262,21 @@ void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_
         volatile float base = 1.0f - B;
         o.norm[d] = base + m;
     }
+    // bm25.rs:100  score = idf * (tf * (K1 + 1.0)) / (tf + K1 * norm)  — per (term, doc), independent of the query
+    o.post_score.resize(o.post_doc.size());
+    const float K1f = 1.2f;
+    volatile float k1p1 = K1f + 1.0f;
+    for (size_t t = 0; t < nt; ++t) {
+        const float idf = o.idf[t];
+        for (uint64_t pp = o.term_off[t]; pp < o.term_off[t + 1]; ++pp) {
+            const float tf = (float)o.post_tf[pp];
+            volatile float a = tf * k1p1;
+            volatile float num = idf * a;
+            volatile float kn = K1f * o.norm[o.post_doc[pp]];
+            volatile float den = tf + kn;
+            o.post_score[pp] = num / den;
+        }
+    }
 }
 
 // ================================= filter =================================

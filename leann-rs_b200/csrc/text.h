@@ -47,6 +47,7 @@ struct Bm25Host {
     std::vector<uint64_t> term_off;   // n_terms + 1
     std::vector<uint32_t> post_doc;   // ascending doc id inside a term
     std::vector<uint32_t> post_tf;
+    std::vector<float> post_score;    // idf * (tf * (K1 + 1)) / (tf + K1 * norm): query independent, f32 as bm25.rs:88-100
     std::vector<float> idf;           // per term, f32 exactly as bm25.rs:88
     std::vector<float> norm;          // per doc: 1 - B + B * (len / avg), bm25.rs:97
     std::vector<uint32_t> doc_len;

@@ -198,9 +198,7 @@ int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size
         DevGuard dg(device);
         b->d_term_off = upload_vec(b->host.term_off);
         b->d_post_doc = upload_vec(b->host.post_doc);
-        b->d_post_tf = upload_vec(b->host.post_tf);
-        b->d_idf = upload_vec(b->host.idf);
-        b->d_norm = upload_vec(b->host.norm);
+        b->d_post_score = upload_vec(b->host.post_score);
         *out = b.release();
     });
 }
@@ -227,7 +225,7 @@ void leann_cuda_bm25_free(leann_cuda_bm25* b) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(b->device);
-    cudaFree(b->d_term_off); cudaFree(b->d_post_doc); cudaFree(b->d_post_tf); cudaFree(b->d_idf); cudaFree(b->d_norm);
+    cudaFree(b->d_term_off); cudaFree(b->d_post_doc); cudaFree(b->d_post_score);
     cudaFree(b->d_acc); cudaFree(b->d_qcounter);
     if (b->stream) cudaStreamDestroy(b->stream);
     cudaGetLastError();

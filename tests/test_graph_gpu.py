@@ -112,3 +112,31 @@ def test_vamana_parity(orc, pkg, tmp_path):
     ok, od, oc, _ = g2.search(q2, k, 64, lanes=lanes, next_cap=64)
     keys, dists, counts = s2.search_batch(q2, k, 64)
     assert np.array_equal(keys, ok) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
+
+
+def test_request_coalescing_concurrent_single_queries(orc, pkg, tmp_path):
+    """serve.rs shares one searcher between request threads; coalesced nq=1 calls must return exactly what
+    the batched call returns, while running in far fewer launches."""
+    import threading
+    n, d, k = 5000, 128, 10
+    x, q = make_data(n, d, 19, nq=512)
+    g = orc.Hnsw.build(x, M=16, ef_add=64, seed=19)
+    base = str(tmp_path / "documents.leann")
+    g.save(base.replace(".leann", ".index"))
+    s = pkg.HnswSearcher.load(base, d)
+    want_k, want_d, _ = s.search_batch(q, k, 64)
+    s.set_coalescing(256, 500)
+    got = [None] * len(q)
+    def worker(lo, hi):
+        for i in range(lo, hi):
+            got[i] = s.search(q[i], k, 64)
+    threads = [threading.Thread(target=worker, args=(t * 16, (t + 1) * 16)) for t in range(32)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for i in range(len(q)):
+        assert got[i][0] == [int(v) for v in want_k[i]]
+        assert np.array_equal(np.asarray(got[i][1], dtype=np.float32), want_d[i])
+    batches, requests = s.coalescing_stats()
+    assert requests == len(q) and batches < requests / 2, (batches, requests)
+    s.set_coalescing(0, 0)
+    assert s.search(q[0], k, 64)[0] == [int(v) for v in want_k[0]]
