@@ -114,14 +114,17 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
     int max_warps = sms * std::max(warps_per_sm, 4);
     size_t n_pad = (ix->n + 127) & ~(size_t)127;
-    // bound the visited workspace to ~1/8 of device memory
-    size_t free_b = 0, total_b = 0;
-    LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = total_b / 8;
-    while (max_warps > 64 && (size_t)max_warps * n_pad > budget) max_warps /= 2;
     int want = (int)std::min<size_t>((size_t)max_warps, std::max<size_t>(nq, 1));
     want = (want + 3) & ~3;
-    if (ws.n_warps >= want && ws.n_pad == n_pad) return;
+    if (ws.n_warps >= want && ws.n_pad == n_pad) return;   // fast path: no driver queries
+    if (ws.warp_cap && ws.n_warps >= ws.warp_cap && ws.n_pad == n_pad) return;  // already at the memory-bounded maximum
+    // bound the visited workspace to ~1/3 of device memory
+    size_t free_b = 0, total_b = 0;
+    LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = total_b / 3;
+    while (max_warps > 64 && (size_t)max_warps * n_pad > budget) max_warps /= 2;
+    ws.warp_cap = max_warps;
+    want = std::min(want, max_warps);
     if (ws.visited) cudaFree(ws.visited);
     if (ws.epochs) cudaFree(ws.epochs);
     if (!ws.counter) ws.counter = dalloc<uint32_t>(1);
@@ -450,14 +453,15 @@ static void search_coalesced(const leann_cuda_index* ix, const float* query, siz
     c.queue.push_back(&r);
     c.cv_leader.notify_one();
     while (!r.done) {
-        if (c.leader_active) { c.cv_done.wait(lk); continue; }
+        if (r.taken || c.leader_active) { c.cv_done.wait(lk); continue; }
         c.leader_active = true;
         auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(c.max_wait_us);
         while (c.queue.size() < c.max_batch)
             if (c.cv_leader.wait_until(lk, deadline) == std::cv_status::timeout) break;
         // the batch = every queued request with this thread's (k, ef), in arrival order
         std::vector<CoalesceReq*> batch, rest;
-        for (CoalesceReq* q : c.queue) ((q->k == r.k && q->ef == r.ef && batch.size() < c.max_batch) ? batch : rest).push_back(q);
+        for (CoalesceReq* q : c.queue) ((q->k == r.k && q->ef == r.ef && (q == &r || batch.size() + 1 < c.max_batch)) ? batch : rest).push_back(q);
+        for (CoalesceReq* q : batch) q->taken = true;
         c.queue.swap(rest);
         c.leader_active = false;
         c.batches++; c.requests += batch.size();

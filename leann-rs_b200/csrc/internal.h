@@ -80,6 +80,7 @@ struct SearchWorkspace {
     uint32_t* epochs = nullptr;  // [n_warps]
     uint32_t* counter = nullptr; // dynamic query scheduler
     int n_warps = 0;
+    int warp_cap = 0;            // memory-bounded maximum pool size (0 = not computed yet)
     size_t n_pad = 0;
     cudaStream_t stream = nullptr;  // private stream for host-pointer calls
     float* d_queries = nullptr; uint64_t* d_keys = nullptr; float* d_dists = nullptr; uint32_t* d_counts = nullptr;
@@ -128,6 +129,7 @@ struct CoalesceReq {
     const float* query; size_t k, ef;
     uint64_t* keys; float* dists; uint32_t* count;
     int rc = 0; std::string err; bool done = false;
+    bool taken = false;   // already part of a batch some leader is running
 };
 struct Coalescer {
     std::mutex m;

@@ -114,29 +114,23 @@ def test_vamana_parity(orc, pkg, tmp_path):
     assert np.array_equal(keys, ok) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
 
 
-def test_request_coalescing_concurrent_single_queries(orc, pkg, tmp_path):
-    """serve.rs shares one searcher between request threads; coalesced nq=1 calls must return exactly what
-    the batched call returns, while running in far fewer launches."""
-    import threading
-    n, d, k = 5000, 128, 10
-    x, q = make_data(n, d, 19, nq=512)
-    g = orc.Hnsw.build(x, M=16, ef_add=64, seed=19)
+def test_request_coalescing_native_threads(orc, pkg, tmp_path):
+    """serve.rs shares one searcher between request threads (src/cli/serve.rs:84,260-311). A native driver
+    (tests/native/coalesce_driver.cpp, plain C ABI) issues concurrent nq=1 calls on one handle: every answer
+    must equal the batched call, and with coalescing on they must run in far fewer launches."""
+    import json, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "coalesce_driver")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests/native/coalesce_driver.cpp"), "-o", exe,
+                           "-L" + os.path.dirname(pkg.LIB_PATH), "-lleann_cuda", "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH)])
+    n, d = 20000, 128
+    x, _ = make_data(n, d, 19)
+    s = pkg.HnswSearcher.build(x, graph_degree=16, complexity=64)
     base = str(tmp_path / "documents.leann")
-    g.save(base.replace(".leann", ".index"))
-    s = pkg.HnswSearcher.load(base, d)
-    want_k, want_d, _ = s.search_batch(q, k, 64)
-    s.set_coalescing(256, 500)
-    got = [None] * len(q)
-    def worker(lo, hi):
-        for i in range(lo, hi):
-            got[i] = s.search(q[i], k, 64)
-    threads = [threading.Thread(target=worker, args=(t * 16, (t + 1) * 16)) for t in range(32)]
-    [t.start() for t in threads]
-    [t.join() for t in threads]
-    for i in range(len(q)):
-        assert got[i][0] == [int(v) for v in want_k[i]]
-        assert np.array_equal(np.asarray(got[i][1], dtype=np.float32), want_d[i])
-    batches, requests = s.coalescing_stats()
-    assert requests == len(q) and batches < requests / 2, (batches, requests)
-    s.set_coalescing(0, 0)
-    assert s.search(q[0], k, 64)[0] == [int(v) for v in want_k[0]]
+    s.save(base)
+    out = subprocess.check_output([exe, base, str(d), "64", "32"], text=True, timeout=240)
+    r = json.loads(out.strip().splitlines()[-1])
+    assert r["mismatch_or_fail"] == 0 and r["coalesced_requests"] == r["requests"]
+    assert r["batches"] < r["requests"] / 4, r
+    assert r["qps_coalesced"] > r["qps_uncoalesced"], r
+    print(r)
