@@ -172,8 +172,9 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
         }
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+        if (!ix->scan_pinned) LEANN_CUDA_CHECK(cudaMallocHost(&ix->scan_pinned, 64));
         launch_exact_scan(f, d_queries, (uint32_t)nq, (uint32_t)k, d_mask, d_keys, d_dists, d_counts, ix->scan_scratch,
-                          ix->scan_scratch_bytes, stream, tvp, sms);
+                          ix->scan_scratch_bytes, stream, tvp, sms, ix->scan_pinned);
         if (d_stats) LEANN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, nq * 4 * sizeof(uint64_t), stream));
         return;
     }
@@ -546,6 +547,7 @@ void leann_cuda_close(leann_cuda_index* ix) {
     cudaFree(ws.visited); cudaFree(ws.epochs); cudaFree(ws.counter); cudaFree(ws.d_queries); cudaFree(ws.d_keys);
     cudaFree(ws.d_dists); cudaFree(ws.d_counts); cudaFree(ws.d_mask);
     if (ws.stream) cudaStreamDestroy(ws.stream);
+    if (ix->scan_pinned) cudaFreeHost(ix->scan_pinned);
     cudaFree(ix->scan_scratch); cudaFree(ix->tc_bf16); cudaFree(ix->tc_norms); cudaFree(ix->tc_xmax);
     cudaGetLastError();
     if (prev >= 0) cudaSetDevice(prev);

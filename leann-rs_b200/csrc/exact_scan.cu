@@ -13,6 +13,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "scan_common.h"
 
@@ -200,8 +201,13 @@ select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand
 __global__ void scan_init_kernel(uint32_t* cand_cnt, uint32_t* best_cnt, unsigned long long* thr, uint32_t nq, uint32_t* overflow) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) { cand_cnt[i] = 0; best_cnt[i] = 0; thr[i] = ~0ull; }
-    if (i == 0) *overflow = 0;
+    if (i == 0) { overflow[0] = 0; overflow[1] = 0xFFFFFFFFu; }
 }
+// overflow[0]: set by a scoring kernel that had to drop a survivor; overflow[1]: first round where that happened.
+__global__ void note_overflow_kernel(uint32_t* overflow, uint32_t round) {
+    if (overflow[0] && overflow[1] == 0xFFFFFFFFu) overflow[1] = round;
+}
+__global__ void scan_reset_overflow_kernel(uint32_t* overflow) { overflow[0] = 0; overflow[1] = 0xFFFFFFFFu; }
 
 __global__ void scan_finish_kernel(const unsigned long long* __restrict__ best, const uint32_t* __restrict__ best_cnt,
                                    uint32_t k, uint32_t kpad, uint32_t nq, int metric, uint64_t* __restrict__ keys,
@@ -309,7 +315,7 @@ size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
 
 void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
                        uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
-                       cudaStream_t stream, const TcIndexView* tv, int sms) {
+                       cudaStream_t stream, const TcIndexView* tv, int sms, uint32_t* h_flag) {
     if (k == 0 || k > 1024) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: k must be in 1..1024");
     if (nq == 0) return;
     const uint32_t kpad = (k + 31) & ~31u;
@@ -336,59 +342,60 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     launch_pad_rows(d_queries, s.qpad, nq, f.d, f.d4, stream);
     if (use_tc) exact_scan_tc_queries(s.qpad, nq, f.d4, tv->dp8, ts, stream);
 
+    // Round boundaries: the first chunk holds SCAN_CAP rows (cannot overflow), later ones grow geometrically so
+    // that the expected number of survivors per query and round stays near growth * k.
     const uint32_t growth = std::max<uint32_t>(2u, SCAN_CAP / (8u * k));
-    uint32_t r0 = 0;
-    uint32_t done_rows = 0;
-    uint32_t* h_over = nullptr;
-    LEANN_CUDA_CHECK(cudaMallocHost(&h_over, sizeof(uint32_t)));
-    try {
-        while (r0 < f.n) {
-            uint64_t want = done_rows == 0 ? SCAN_CAP : (uint64_t)done_rows * growth;
-            uint32_t r1 = (uint32_t)std::min<uint64_t>(f.n, (uint64_t)r0 + want);
-            for (int attempt = 0;; ++attempt) {
-                dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);
-                if (use_tc && done_rows > 0) {
-                    // tensor-core pass + fp32 re-rank for every chunk after the first
-                    exact_scan_tc_round(f, *tv, s, ts, nq, r0, r1, d_mask, SCAN_CAP, sms, stream);
-                } else
-                switch (f.metric) {
-                    case LEANN_METRIC_L2SQ:
-                        scan_tile_kernel<LEANN_METRIC_L2SQ><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                        break;
-                    case LEANN_METRIC_IP_CLAMP:
-                        scan_tile_kernel<LEANN_METRIC_IP_CLAMP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                        break;
-                    case LEANN_METRIC_DOT_DESC:
-                        scan_tile_kernel<LEANN_METRIC_DOT_DESC><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                        break;
-                    default:
-                        scan_tile_kernel<LEANN_METRIC_IP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                }
-                LEANN_CUDA_CHECK(cudaGetLastError());
-                size_t smem = (size_t)2 * SCAN_CAP * 8;  // best (<=1024) + cand (<=4096) rounded to 8192 keys
-                static bool attr_set = false;
-                if (!attr_set) {
-                    LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_set = true;
-                }
-                select_kernel<<<nq, 256, smem, stream>>>(s.cand, s.cand_cnt, SCAN_CAP, s.best, s.best_cnt, k, kpad, s.thr, nq);
-                LEANN_CUDA_CHECK(cudaGetLastError());
-                LEANN_CUDA_CHECK(cudaMemcpyAsync(h_over, s.overflow, 4, cudaMemcpyDeviceToHost, stream));
-                LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
-                if (*h_over == 0) break;
-                // A candidate list overflowed: the threshold is tighter now; re-run the same chunk
-                // (duplicates of rows already kept are removed by the select kernel).
-                LEANN_CUDA_CHECK(cudaMemsetAsync(s.overflow, 0, 4, stream));
-                if (attempt > 64) throw Error(LEANN_ERR_CUDA, "exact scan: candidate overflow did not converge");
-            }
-            done_rows = r1;
-            r0 = r1;
-        }
-    } catch (...) {
-        cudaFreeHost(h_over);
-        throw;
+    std::vector<std::pair<uint32_t, uint32_t>> rounds;
+    for (uint32_t r0 = 0; r0 < f.n;) {
+        uint64_t want = r0 == 0 ? SCAN_CAP : (uint64_t)r0 * growth;
+        uint32_t r1 = (uint32_t)std::min<uint64_t>(f.n, (uint64_t)r0 + want);
+        rounds.emplace_back(r0, r1);
+        r0 = r1;
     }
-    cudaFreeHost(h_over);
+    static bool attr_set = false;
+    const size_t sel_smem = (size_t)2 * SCAN_CAP * 8;  // best (<=1024) + cand (<=4096) rounded to 8192 keys
+    if (!attr_set) {
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+        attr_set = true;
+    }
+    auto run_round = [&](size_t ri) {
+        const uint32_t r0 = rounds[ri].first, r1 = rounds[ri].second;
+        dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);
+        if (use_tc && ri > 0) {
+            // tensor-core pass + fp32 re-rank for every chunk after the first
+            exact_scan_tc_round(f, *tv, s, ts, nq, r0, r1, d_mask, SCAN_CAP, sms, stream);
+        } else
+        switch (f.metric) {
+            case LEANN_METRIC_L2SQ:
+                scan_tile_kernel<LEANN_METRIC_L2SQ><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                break;
+            case LEANN_METRIC_IP_CLAMP:
+                scan_tile_kernel<LEANN_METRIC_IP_CLAMP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                break;
+            case LEANN_METRIC_DOT_DESC:
+                scan_tile_kernel<LEANN_METRIC_DOT_DESC><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+                break;
+            default:
+                scan_tile_kernel<LEANN_METRIC_IP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+        }
+        LEANN_CUDA_CHECK(cudaGetLastError());
+        select_kernel<<<nq, 256, sel_smem, stream>>>(s.cand, s.cand_cnt, SCAN_CAP, s.best, s.best_cnt, k, kpad, s.thr, nq);
+        note_overflow_kernel<<<1, 1, 0, stream>>>(s.overflow, (uint32_t)ri);
+        LEANN_CUDA_CHECK(cudaGetLastError());
+    };
+    // All rounds are enqueued back to back; the device records the first round whose candidate list
+    // overflowed (s.overflow[1]). One synchronisation at the end; if a round overflowed, that round and the ones
+    // after it are repeated with the tightened thresholds (rows already kept are deduplicated by select_kernel).
+    size_t first = 0;
+    for (int attempt = 0;; ++attempt) {
+        for (size_t ri = first; ri < rounds.size(); ++ri) run_round(ri);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(h_flag, s.overflow, 8, cudaMemcpyDeviceToHost, stream));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (h_flag[1] == 0xFFFFFFFFu) break;
+        first = h_flag[1];
+        if (attempt > 64) throw Error(LEANN_ERR_CUDA, "exact scan: candidate overflow did not converge");
+        scan_reset_overflow_kernel<<<1, 1, 0, stream>>>(s.overflow);
+    }
     uint32_t tot = nq * k;
     scan_finish_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(s.best, s.best_cnt, k, kpad, nq, f.metric, d_keys, d_dists, d_counts);
     LEANN_CUDA_CHECK(cudaGetLastError());

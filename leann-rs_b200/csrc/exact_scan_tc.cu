@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "scan_common.h"
 
@@ -37,7 +38,8 @@ constexpr int TC_B_BYTES = TC_N * TC_K * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_GROUP = 8;      // database tiles per schedule item
 constexpr int TC_THREADS = 256;
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_QBUF = 32;      // survivors buffered per query row before one slot reservation
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 128 * TC_QBUF * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,6 +122,7 @@ struct TcParams {
     uint32_t* cand_cnt;            // [nq]
     uint32_t cap;
     uint32_t* overflow;
+    int direct_append;             // A/B switch: 1 = one atomic per survivor (no shared-memory batching)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -132,6 +135,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
     uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+    uint32_t* s_qbuf = reinterpret_cast<uint32_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES + 256);  // [128][TC_QBUF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -210,6 +214,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
             const uint32_t q = qtile * TC_M + quad * 32 + lane;
             const float T = q < p.nq ? p.thr_dot[q] : CUDART_INF_F;
+            // survivors are buffered per thread and appended with ONE slot reservation per TC_QBUF rows
+            uint32_t* myq = s_qbuf + (quad * 32 + lane);   // [TC_QBUF][128] layout: slot i at myq[i * 128], conflict-free
+            int nbuf = 0;
+            auto flush = [&]() {
+                if (nbuf == 0) return;
+                uint32_t pos = atomicAdd(&p.cand_cnt[q], (uint32_t)nbuf);
+                for (int i = 0; i < nbuf; ++i) {
+                    if (pos + i < p.cap) p.cand_ids[(size_t)q * p.cap + pos + i] = myq[i * 128];
+                    else *p.overflow = 1u;
+                }
+                nbuf = 0;
+            };
             for (uint32_t t = t0; t < t1; ++t) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -227,9 +243,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                             if (__uint_as_float(r[j]) >= T) {
                                 uint32_t row = row_base + (uint32_t)c + (uint32_t)j;
                                 if (row < p.r1 && (!p.mask || ((p.mask[row >> 6] >> (row & 63u)) & 1ull))) {
-                                    uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
-                                    if (pos < p.cap) p.cand_ids[(size_t)q * p.cap + pos] = row;
-                                    else *p.overflow = 1u;
+                                    if (p.direct_append) {
+                                        uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
+                                        if (pos < p.cap) p.cand_ids[(size_t)q * p.cap + pos] = row;
+                                        else *p.overflow = 1u;
+                                    } else {
+                                        myq[(nbuf++) * 128] = row;
+                                        if (nbuf == TC_QBUF) flush();
+                                    }
                                 }
                             }
                         }
@@ -240,6 +261,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
             }
+            flush();
         }
     }
     tc_fence_before();
@@ -391,6 +413,8 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
     p.n_qtiles = (nq + TC_M - 1) / TC_M;
     p.tiles_total = (r1 - r0 + TC_N - 1) / TC_N;
     p.n_groups = (p.tiles_total + TC_GROUP - 1) / TC_GROUP;
+    static const int direct = getenv("LEANN_TC_DIRECT_APPEND") ? 1 : 0;
+    p.direct_append = direct;
     p.thr_dot = ts.thr_dot; p.mask = d_mask; p.cand_ids = ts.cand_ids; p.cand_cnt = s.cand_cnt; p.cap = cap; p.overflow = s.overflow;
     uint32_t items = p.n_qtiles * p.n_groups;
     int grid = (int)std::min<uint32_t>((uint32_t)sms, items);

@@ -111,7 +111,7 @@ struct FlatView { const float4* vecs; uint32_t n, d, d4; int metric; };
 struct TcIndexView;
 void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
                        uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
-                       cudaStream_t stream, const TcIndexView* tv, int sms);
+                       cudaStream_t stream, const TcIndexView* tv, int sms, uint32_t* h_flag /*pinned, 2 words*/);
 size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k);
 
 void launch_topk_merge(const uint64_t* keys_in, const float* dists_in, uint32_t n_shards, uint32_t nq, uint32_t k,
@@ -166,6 +166,7 @@ struct leann_cuda_index {
     mutable leann::SearchWorkspace ws;
     mutable void* scan_scratch = nullptr;
     mutable size_t scan_scratch_bytes = 0;
+    mutable uint32_t* scan_pinned = nullptr;   // 2 pinned words for the overflow read-back
     // tensor-path copy of a flat database (bf16 rows, row norms, max norm), built on first use
     mutable void* tc_bf16 = nullptr;
     mutable float* tc_norms = nullptr;

@@ -1,0 +1,240 @@
+// leann_cuda.hpp — header-only C++ host layer above the C ABI (include/leann_cuda.h), mirroring the
+// reference's Rust interfaces one to one (the reference is compiled code and its toolchain is absent
+// from this image, so the host side is written in C++; rust/leann-cuda/ holds the same thing as a crate):
+//   trait BackendSearcher                 src/backend/traits.rs:11-30
+//   HnswSearcher / DiskAnnSearcher        src/backend/hnsw.rs:12-93, src/backend/diskann.rs:12-66
+//   BackendType::load_searcher            src/backend/mod.rs:16-45
+//   Bm25Scorer, hybrid_rerank             src/index/bm25.rs:17-170
+//   MetadataFilter                        src/index/filter.rs:35-39,52-134,319-325
+//   SearchOptions, IndexSearcher          src/index/searcher.rs:25-63,66-257
+// Errors surface as leann::Error (anyhow::Result in the reference). Nothing here computes.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/leann_cuda.h"
+
+namespace leann {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc, const char* err) {
+    if (rc != LEANN_OK) throw Error(rc, err);
+}
+
+// ---- src/backend/traits.rs ------------------------------------------------------------------------
+class BackendSearcher {
+public:
+    virtual ~BackendSearcher() = default;
+    /// (indices, distances) for one query; ascending distance, length <= top_k.
+    virtual std::pair<std::vector<uint64_t>, std::vector<float>> search(const std::vector<float>& query, size_t top_k,
+                                                                        size_t complexity) const = 0;
+    virtual size_t len() const = 0;
+    bool is_empty() const { return len() == 0; }
+};
+
+class CudaSearcher : public BackendSearcher {
+public:
+    CudaSearcher(const std::string& index_path, int backend, size_t dimensions, int device, std::optional<size_t> fixed_ef)
+        : dims_(dimensions), fixed_ef_(fixed_ef) {
+        char err[1024];
+        check(leann_cuda_open(index_path.c_str(), backend, dimensions, LEANN_METRIC_DEFAULT, device, &h_, err, sizeof err), err);
+    }
+    ~CudaSearcher() override { leann_cuda_close(h_); }
+    CudaSearcher(const CudaSearcher&) = delete;
+    CudaSearcher& operator=(const CudaSearcher&) = delete;
+
+    std::pair<std::vector<uint64_t>, std::vector<float>> search(const std::vector<float>& query, size_t top_k,
+                                                                size_t complexity) const override {
+        std::vector<uint64_t> keys(top_k);
+        std::vector<float> dists(top_k);
+        uint32_t count = 0;
+        char err[1024];
+        check(leann_cuda_search(h_, query.data(), 1, top_k, fixed_ef_.value_or(complexity), nullptr, LEANN_MASK_NONE, keys.data(),
+                                dists.data(), &count, err, sizeof err), err);
+        keys.resize(count);
+        dists.resize(count);
+        return {std::move(keys), std::move(dists)};
+    }
+    /// Batched form (new): queries is nq x dims row-major; outputs nq x top_k, counts per query.
+    void search_batch(const float* queries, size_t nq, size_t top_k, size_t ef, uint64_t* keys, float* dists, uint32_t* counts,
+                      const uint64_t* mask_bits = nullptr) const {
+        char err[1024];
+        check(leann_cuda_search(h_, queries, nq, top_k, ef, mask_bits, mask_bits ? LEANN_MASK_INLINE : LEANN_MASK_NONE, keys, dists,
+                                counts, err, sizeof err), err);
+    }
+    size_t len() const override { return leann_cuda_len(h_); }
+    size_t dims() const { return dims_; }
+    /// Merge concurrent single-query calls (the axum handlers of serve.rs) into batched launches.
+    void set_coalescing(size_t max_batch, unsigned max_wait_us) { leann_cuda_set_coalescing(h_, max_batch, max_wait_us); }
+    const leann_cuda_index* handle() const { return h_; }
+
+protected:
+    leann_cuda_index* h_ = nullptr;
+    size_t dims_;
+    std::optional<size_t> fixed_ef_;
+};
+
+/// src/backend/hnsw.rs: `complexity` is ignored, expansion_search is 64 (hnsw.rs:49,83).
+class HnswSearcher : public CudaSearcher {
+public:
+    static std::unique_ptr<HnswSearcher> load(const std::string& index_path, size_t dimensions, int device = 0) {
+        return std::unique_ptr<HnswSearcher>(new HnswSearcher(index_path, dimensions, device));
+    }
+private:
+    HnswSearcher(const std::string& p, size_t d, int dev) : CudaSearcher(p, LEANN_BACKEND_HNSW, d, dev, 64) {}
+};
+/// src/backend/diskann.rs: beam = max(complexity, top_k) (diskann.rs:54).
+class DiskAnnSearcher : public CudaSearcher {
+public:
+    static std::unique_ptr<DiskAnnSearcher> load(const std::string& index_path, size_t dimensions, int device = 0) {
+        return std::unique_ptr<DiskAnnSearcher>(new DiskAnnSearcher(index_path, dimensions, device));
+    }
+private:
+    DiskAnnSearcher(const std::string& p, size_t d, int dev) : CudaSearcher(p, LEANN_BACKEND_VAMANA, d, dev, std::nullopt) {}
+};
+
+// ---- src/backend/mod.rs:16-45 -------------------------------------------------------------------------
+enum class BackendType { Hnsw, DiskAnn };
+inline std::unique_ptr<BackendSearcher> load_searcher(BackendType t, const std::string& index_path, size_t dimensions, int device = 0) {
+    if (t == BackendType::Hnsw) return HnswSearcher::load(index_path, dimensions, device);
+    return DiskAnnSearcher::load(index_path, dimensions, device);
+}
+
+// ---- src/index/filter.rs ---------------------------------------------------------------------------------
+class MetadataFilter {
+public:
+    /// nullopt where the reference returns None.
+    static std::optional<MetadataFilter> parse(const std::string& filter_str) {
+        leann_cuda_filter* f = nullptr;
+        char err[1024];
+        int rc = leann_cuda_filter_parse(filter_str.c_str(), &f, err, sizeof err);
+        if (rc == LEANN_ERR_PARSE) return std::nullopt;
+        check(rc, err);
+        return MetadataFilter(f);
+    }
+    bool matches(const std::string& metadata_json) const {
+        int r = 0;
+        char err[1024];
+        check(leann_cuda_filter_matches(f_.get(), metadata_json.data(), metadata_json.size(), &r, err, sizeof err), err);
+        return r != 0;
+    }
+    std::vector<uint64_t> mask(const std::vector<std::string>& metadata_json) const {
+        std::vector<const char*> p(metadata_json.size());
+        std::vector<size_t> n(metadata_json.size());
+        for (size_t i = 0; i < p.size(); ++i) { p[i] = metadata_json[i].data(); n[i] = metadata_json[i].size(); }
+        std::vector<uint64_t> out((p.size() + 63) / 64);
+        char err[1024];
+        check(leann_cuda_filter_mask(f_.get(), p.data(), n.data(), p.size(), out.data(), err, sizeof err), err);
+        return out;
+    }
+private:
+    explicit MetadataFilter(leann_cuda_filter* f) : f_(f, leann_cuda_filter_free) {}
+    std::shared_ptr<leann_cuda_filter> f_;
+};
+
+// ---- src/index/bm25.rs -------------------------------------------------------------------------------------
+class Bm25Scorer {
+public:
+    static Bm25Scorer build(const std::vector<std::string>& documents, int device = 0) {
+        std::vector<const char*> p(documents.size());
+        std::vector<size_t> n(documents.size());
+        for (size_t i = 0; i < p.size(); ++i) { p[i] = documents[i].data(); n[i] = documents[i].size(); }
+        leann_cuda_bm25* b = nullptr;
+        char err[1024];
+        check(leann_cuda_bm25_build(p.data(), n.data(), p.size(), device, &b, err, sizeof err), err);
+        return Bm25Scorer(b);
+    }
+    std::vector<float> score_query(const std::string& query) const {
+        std::vector<float> s(leann_cuda_bm25_len(b_.get()));
+        char err[1024];
+        check(leann_cuda_bm25_score(b_.get(), query.data(), query.size(), s.data(), err, sizeof err), err);
+        return s;
+    }
+    std::vector<std::pair<size_t, float>> search(const std::string& query, size_t top_k) const {
+        std::vector<uint64_t> idx(top_k);
+        std::vector<float> sc(top_k);
+        uint32_t cnt = 0;
+        const char* q = query.data();
+        size_t n = query.size();
+        char err[1024];
+        check(leann_cuda_bm25_search(b_.get(), &q, &n, 1, top_k, idx.data(), sc.data(), &cnt, err, sizeof err), err);
+        std::vector<std::pair<size_t, float>> out;
+        for (uint32_t i = 0; i < cnt; ++i) out.emplace_back((size_t)idx[i], sc[i]);
+        return out;
+    }
+    const leann_cuda_bm25* handle() const { return b_.get(); }
+private:
+    explicit Bm25Scorer(leann_cuda_bm25* b) : b_(b, leann_cuda_bm25_free) {}
+    std::shared_ptr<leann_cuda_bm25> b_;
+};
+
+inline std::vector<std::pair<size_t, float>> hybrid_rerank(const std::vector<std::pair<size_t, float>>& vector_results,
+                                                           const std::vector<float>& bm25_scores, float alpha, int device = 0) {
+    std::vector<uint64_t> idx(vector_results.size()), oi(vector_results.size());
+    std::vector<float> vs(vector_results.size()), os(vector_results.size());
+    for (size_t i = 0; i < idx.size(); ++i) { idx[i] = vector_results[i].first; vs[i] = vector_results[i].second; }
+    char err[1024];
+    check(leann_cuda_hybrid_rerank(idx.data(), vs.data(), idx.size(), bm25_scores.data(), bm25_scores.size(), alpha, device, oi.data(),
+                                   os.data(), err, sizeof err), err);
+    std::vector<std::pair<size_t, float>> out;
+    for (size_t i = 0; i < oi.size(); ++i) out.emplace_back((size_t)oi[i], os[i]);
+    return out;
+}
+
+// ---- src/index/searcher.rs -----------------------------------------------------------------------------------
+struct SearchOptions {
+    size_t top_k = 0, complexity = 0;
+    std::optional<std::string> filter;
+    bool hybrid = false;
+    float hybrid_alpha = 0.7f;  // searcher.rs:47
+    std::optional<std::string> query_text;
+    static SearchOptions make(size_t top_k, size_t complexity) { SearchOptions o; o.top_k = top_k; o.complexity = complexity; return o; }
+    SearchOptions& with_filter(std::string f) { filter = std::move(f); return *this; }
+    SearchOptions& with_hybrid(std::string text, float alpha) { hybrid = true; hybrid_alpha = alpha; query_text = std::move(text); return *this; }
+};
+struct SearchHit { std::string id; uint64_t ordinal; float score; };
+
+class IndexSearcher {
+public:
+    static IndexSearcher load(const std::string& index_path, const std::string& backend_name, size_t dimensions, int device = 0) {
+        leann_cuda_searcher* s = nullptr;
+        char err[1024];
+        check(leann_cuda_searcher_load(index_path.c_str(), backend_name.c_str(), dimensions, device, &s, err, sizeof err), err);
+        return IndexSearcher(s);
+    }
+    std::vector<SearchHit> search_with_options(const std::vector<float>& query_embedding, const SearchOptions& o) const {
+        std::vector<uint64_t> idx(o.top_k);
+        std::vector<float> sc(o.top_k);
+        uint32_t cnt = 0;
+        const char* t = o.query_text ? o.query_text->data() : nullptr;
+        size_t tn = o.query_text ? o.query_text->size() : 0;
+        char err[1024];
+        check(leann_cuda_searcher_search(s_.get(), query_embedding.data(), t ? &t : nullptr, t ? &tn : nullptr, 1, o.top_k, o.complexity,
+                                         o.filter ? o.filter->c_str() : nullptr, o.hybrid ? 1 : 0, o.hybrid_alpha, idx.data(), sc.data(),
+                                         &cnt, err, sizeof err), err);
+        std::vector<SearchHit> out;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            char id[512];
+            leann_cuda_searcher_id(s_.get(), idx[i], id, sizeof id);
+            out.push_back({id, idx[i], sc[i]});
+        }
+        return out;
+    }
+    std::vector<SearchHit> search(const std::vector<float>& q, size_t top_k, size_t complexity) const {
+        return search_with_options(q, SearchOptions::make(top_k, complexity));
+    }
+    size_t len() const { return leann_cuda_searcher_len(s_.get()); }
+private:
+    explicit IndexSearcher(leann_cuda_searcher* s) : s_(s, leann_cuda_searcher_close) {}
+    std::shared_ptr<leann_cuda_searcher> s_;
+};
+
+}  // namespace leann

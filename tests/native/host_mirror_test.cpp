@@ -1,0 +1,60 @@
+// Exercises the C++ host mirror (leann-rs_b200/host/leann_cuda.hpp) the way the reference's own unit tests
+// exercise the Rust types: bm25.rs:264-329 and filter.rs:446-551 assertions, plus one BackendSearcher::search
+// call whose result is printed for the Python side to compare. Usage: host_mirror_test <base_path> <dims>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../leann-rs_b200/host/leann_cuda.hpp"
+
+#define REQUIRE(c) do { if (!(c)) { fprintf(stderr, "REQUIRE failed line %d: %s\n", __LINE__, #c); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    using namespace leann;
+    if (argc < 3) return 2;
+    try {
+        // --- bm25.rs:264-280 test_bm25_search_top_k
+        auto scorer = Bm25Scorer::build({"apple banana", "apple cherry", "banana cherry", "apple apple apple"});
+        auto r = scorer.search("apple", 2);
+        REQUIRE(r.size() == 2 && r[0].first == 3 && r[1].first == 0);
+        auto dense = scorer.score_query("apple");
+        REQUIRE(dense.size() == 4 && dense[2] == 0.0f && dense[3] == r[0].second && dense[0] == dense[1]);
+        REQUIRE(Bm25Scorer::build({"hello world"}).search("xyz", 5).empty());            // bm25.rs:255-262
+        // --- bm25.rs:282-329 hybrid_rerank
+        auto h = hybrid_rerank({{0, 0.9f}, {1, 0.8f}, {2, 0.7f}}, {0.5f, 0.9f, 0.3f}, 0.5f);
+        REQUIRE(h.size() == 3 && h[0].first == 1 && h[1].first == 0 && h[2].first == 2 && h[2].second == 0.0f);
+        REQUIRE(hybrid_rerank({{0, 0.9f}, {1, 0.5f}}, {0.1f, 0.9f}, 1.0f)[0].first == 0);
+        REQUIRE(hybrid_rerank({{0, 0.9f}, {1, 0.5f}}, {0.1f, 0.9f}, 0.0f)[0].first == 1);
+        // --- filter.rs:446-551
+        const char* md = "{\"source\": \"main.rs\", \"type\": \"code\", \"lines\": 100}";
+        REQUIRE(MetadataFilter::parse("source:*.rs")->matches(md));
+        REQUIRE(MetadataFilter::parse("type=code,lines>50")->matches(md));
+        REQUIRE(!MetadataFilter::parse("type=code,lines>200")->matches(md));
+        REQUIRE(MetadataFilter::parse("type in [code,text,doc]")->matches(md));
+        REQUIRE(!MetadataFilter::parse("type not_in [code,text]")->matches(md));
+        REQUIRE(MetadataFilter::parse("type=text OR type=code")->matches(md));
+        REQUIRE(!MetadataFilter::parse("missing?")->matches(md));
+        REQUIRE(!MetadataFilter::parse("nonsense").has_value());
+        // --- BackendType::load_searcher + BackendSearcher::search (traits.rs:16-21)
+        size_t d = (size_t)atol(argv[2]);
+        auto s = load_searcher(BackendType::Hnsw, argv[1], d);
+        REQUIRE(!s->is_empty());
+        std::vector<float> q(d);
+        for (size_t i = 0; i < d; ++i) q[i] = std::sin(0.37f * (float)(i + 1));
+        auto res = s->search(q, 5, 999);   // complexity ignored for HNSW (hnsw.rs:83)
+        REQUIRE(res.first.size() == 5 && res.second.size() == 5);
+        for (size_t i = 1; i < 5; ++i) REQUIRE(res.second[i - 1] <= res.second[i]);
+        printf("KEYS");
+        for (auto k : res.first) printf(" %llu", (unsigned long long)k);
+        printf("\n");
+        try {
+            HnswSearcher::load("/nonexistent/documents.leann", d);
+            REQUIRE(false);
+        } catch (const Error& e) { REQUIRE(e.code == LEANN_ERR_NOT_FOUND); }
+    } catch (const std::exception& e) {
+        fprintf(stderr, "exception: %s\n", e.what());
+        return 1;
+    }
+    printf("OK\n");
+    return 0;
+}

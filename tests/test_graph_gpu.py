@@ -134,3 +134,24 @@ def test_request_coalescing_native_threads(orc, pkg, tmp_path):
     assert r["batches"] < r["requests"] / 4, r
     assert r["qps_coalesced"] > r["qps_uncoalesced"], r
     print(r)
+
+
+def test_cpp_host_mirror(orc, pkg, tmp_path):
+    """The header-only C++ host layer (leann-rs_b200/host/leann_cuda.hpp) mirrors the reference's Rust types; a
+    native program runs the reference's bm25/filter unit-test assertions and a trait-level search through it."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_mirror_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", os.path.join(root, "tests/native/host_mirror_test.cpp"), "-o", exe,
+                           "-L" + os.path.dirname(pkg.LIB_PATH), "-lleann_cuda", "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH)])
+    n, d = 3000, 128
+    x, _ = make_data(n, d, 5)
+    g = orc.Hnsw.build(x, M=16, ef_add=64, seed=5)
+    base = str(tmp_path / "documents.leann")
+    g.save(base.replace(".leann", ".index"))
+    out = subprocess.check_output([exe, base, str(d)], text=True, timeout=120)
+    assert out.strip().endswith("OK")
+    keys = [int(t) for t in [l for l in out.splitlines() if l.startswith("KEYS")][0].split()[1:]]
+    q = np.sin(0.37 * np.arange(1, d + 1, dtype=np.float32)).astype(np.float32)
+    ok, _, _, _ = g.search(q[None, :], 5, 64, lanes=pkg.reduction_lanes(d), next_cap=64)
+    assert keys == [int(v) for v in ok[0]]
