@@ -1,6 +1,6 @@
 // Exercises the C++ host mirror (leann-rs_b200/host/leann_cuda.hpp) the way the reference's own unit tests
 // exercise the Rust types: bm25.rs:264-329 and filter.rs:446-551 assertions, plus one BackendSearcher::search
-// call whose result is printed for the Python side to compare. Usage: host_mirror_test <base_path> <dims>
+// call whose result is printed for the Python side to compare. Usage: host_mirror_test <base_path> <dims> <query.f32>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -11,7 +11,7 @@
 
 int main(int argc, char** argv) {
     using namespace leann;
-    if (argc < 3) return 2;
+    if (argc < 4) return 2;
     try {
         // --- bm25.rs:264-280 test_bm25_search_top_k
         auto scorer = Bm25Scorer::build({"apple banana", "apple cherry", "banana cherry", "apple apple apple"});
@@ -40,7 +40,11 @@ int main(int argc, char** argv) {
         auto s = load_searcher(BackendType::Hnsw, argv[1], d);
         REQUIRE(!s->is_empty());
         std::vector<float> q(d);
-        for (size_t i = 0; i < d; ++i) q[i] = std::sin(0.37f * (float)(i + 1));
+        {
+            FILE* f = fopen(argv[3], "rb");   // raw f32 query written by the caller
+            REQUIRE(f && fread(q.data(), 4, d, f) == d);
+            fclose(f);
+        }
         auto res = s->search(q, 5, 999);   // complexity ignored for HNSW (hnsw.rs:83)
         REQUIRE(res.first.size() == 5 && res.second.size() == 5);
         for (size_t i = 1; i < 5; ++i) REQUIRE(res.second[i - 1] <= res.second[i]);

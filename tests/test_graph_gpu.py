@@ -149,9 +149,10 @@ def test_cpp_host_mirror(orc, pkg, tmp_path):
     g = orc.Hnsw.build(x, M=16, ef_add=64, seed=5)
     base = str(tmp_path / "documents.leann")
     g.save(base.replace(".leann", ".index"))
-    out = subprocess.check_output([exe, base, str(d)], text=True, timeout=120)
+    q = np.sin(0.37 * np.arange(1, d + 1, dtype=np.float32)).astype(np.float32)
+    q.tofile(str(tmp_path / "query.f32"))
+    out = subprocess.check_output([exe, base, str(d), str(tmp_path / "query.f32")], text=True, timeout=120)
     assert out.strip().endswith("OK")
     keys = [int(t) for t in [l for l in out.splitlines() if l.startswith("KEYS")][0].split()[1:]]
-    q = np.sin(0.37 * np.arange(1, d + 1, dtype=np.float32)).astype(np.float32)
     ok, _, _, _ = g.search(q[None, :], 5, 64, lanes=pkg.reduction_lanes(d), next_cap=64)
     assert keys == [int(v) for v in ok[0]]
