@@ -29,28 +29,44 @@ namespace leann {
 
 namespace {
 
-constexpr int TC_M = 128;        // queries per tile (UMMA M)
-constexpr int TC_N = 256;        // database rows per tile (UMMA N)
+constexpr int TC_M = 128;        // queries per CTA; the CTA pair issues UMMA M = 256
+constexpr int TC_N = 256;        // database rows per pair tile (UMMA N); each CTA stages TC_N / 2 of them
+constexpr int TC_NH = TC_N / 2;
 constexpr int TC_K = 64;         // bf16 elements per k-block = 128 B = one swizzle row
-constexpr int TC_STAGES = 4;
-constexpr int TC_A_BYTES = TC_M * TC_K * 2;   // 16 KB
-constexpr int TC_B_BYTES = TC_N * TC_K * 2;   // 32 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_GROUP = 8;      // database tiles per schedule item
+constexpr int TC_A_BYTES = TC_M * TC_K * 2;    // 16 KB: one k-block of this CTA's query tile
+constexpr int TC_B_BYTES = TC_NH * TC_K * 2;   // 16 KB: one k-block of this CTA's half of the database tile
+constexpr int TC_MAX_RES_KB = 7;  // query tile stays resident in shared memory up to 7 k-blocks (d <= 448)
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 256;
 constexpr int TC_QBUF = 32;      // survivors buffered per query row before one slot reservation
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 128 * TC_QBUF * 4;
+constexpr int TC_BAR_BYTES = 256;
+constexpr size_t TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// arrive on a barrier of another CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -65,23 +81,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+// TMA tile load issued by either CTA of the pair: data lands in this CTA's shared memory, the byte count is
+// credited to the barrier at `bar_cluster_addr` (the leader CTA's, where the MMA issuer waits).
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// arrives (once all MMAs issued so far retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -111,79 +133,117 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return d;
 }
 // InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major both,
-// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29). M = 256: the pair's two 128-row halves.
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)((2 * TC_M) >> 4) << 24);
 
 struct TcParams {
-    uint32_t nq, r0, r1, kblocks, n_qtiles, n_groups, tiles_total;
-    const float* thr_dot;          // [nq] candidate threshold in dot space (-inf = everything)
+    uint32_t nq, r0, r1, kblocks, n_qpairs, n_groups, tiles_total, group, stages;
+    const float* thr_dot;          // [nq] strict candidate threshold in dot space (-inf = everything)
     const uint64_t* mask;          // nullable
     uint32_t* cand_ids;            // [nq][cap]
     uint32_t* cand_cnt;            // [nq]
     uint32_t cap;
     uint32_t* overflow;
-    int direct_append;             // A/B switch: 1 = one atomic per survivor (no shared-memory batching)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// One CTA pair (two SMs of a TPC) per cluster. Work item = (256-query pair tile, group of database tiles);
+// items are dealt round-robin so that concurrently running pairs read the same database tiles out of L2.
+//   RESIDENT: the CTA's 128 x d query tile is loaded once per item and stays in shared memory; the ring
+//             streams only this CTA's half of each database tile (16 KB per k-block).
+//   !RESIDENT (d > 448): query k-blocks travel through the ring beside the database k-blocks.
+template <bool RESIDENT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* full_bar = bars;                    // [TC_STAGES]
-    uint64_t* empty_bar = bars + TC_STAGES;       // [TC_STAGES]
-    uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
-    uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
-    uint32_t* s_qbuf = reinterpret_cast<uint32_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES + 256);  // [128][TC_QBUF]
+    constexpr uint32_t STAGE_BYTES = RESIDENT ? TC_B_BYTES : TC_A_BYTES + TC_B_BYTES;
+    unsigned char* a_res = smem;                                                        // RESIDENT: [kblocks][16 KB]
+    unsigned char* ring = smem + (RESIDENT ? (size_t)p.kblocks * TC_A_BYTES : 0);      // [stages][STAGE_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * STAGE_BYTES);
+    uint64_t* full_bar = bars;                            // [8]  leader's copy is the one waited on
+    uint64_t* empty_bar = bars + TC_MAX_STAGES;           // [8]  one per CTA (multicast commit)
+    uint64_t* tmem_full = bars + 2 * TC_MAX_STAGES;       // [2]  one per CTA (multicast commit)
+    uint64_t* tmem_empty = bars + 2 * TC_MAX_STAGES + 2;  // [2]  leader's copy: 8 epilogue warps arrive
+    uint64_t* a_full = bars + 2 * TC_MAX_STAGES + 4;      // leader's copy
+    uint64_t* a_empty = bars + 2 * TC_MAX_STAGES + 5;     // one per CTA (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
+    uint32_t* s_qbuf = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + TC_BAR_BYTES);  // [TC_QBUF][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t n_items = p.n_qtiles * p.n_groups;
+    const uint32_t n_items = p.n_qpairs * p.n_groups;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== ring producer (one thread per CTA) =====
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const uint32_t qtile = item % p.n_qtiles, grp = item / p.n_qtiles;
-                const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
-                for (uint32_t t = t0; t < t1; ++t)
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = pair; item < n_items; item += n_pairs) {
+                const uint32_t qpair = item % p.n_qpairs, grp = item / p.n_qpairs;
+                const uint32_t t0 = grp * p.group, t1 = min(t0 + p.group, p.tiles_total);
+                const int qrow = (int)(qpair * (2 * TC_M) + rank * TC_M);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    const int xrow = (int)(p.r0 + t * TC_N + rank * TC_NH);
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        unsigned char* sa = smem + (size_t)stage * TC_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-                        tma_load_2d(sa, &map_q, &full_bar[stage], (int)(kb * TC_K), (int)(qtile * TC_M));
-                        tma_load_2d(sa + TC_A_BYTES, &map_x, &full_bar[stage], (int)(kb * TC_K), (int)(p.r0 + t * TC_N));
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * STAGE_BYTES);
+                        const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        unsigned char* dst = ring + (size_t)stage * STAGE_BYTES;
+                        if (!RESIDENT) {
+                            tma_load_2d_pair(dst, &map_q, bar, (int)(kb * TC_K), qrow);
+                            dst += TC_A_BYTES;
+                        }
+                        tma_load_2d_pair(dst, &map_x, bar, (int)(kb * TC_K), xrow);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== resident query tile producer (one thread per CTA) =====
+        if (RESIDENT && lane == 0) {
+            uint32_t a_phase = 0;
+            for (uint32_t item = pair; item < n_items; item += n_pairs) {
+                const uint32_t qpair = item % p.n_qpairs;
+                const int qrow = (int)(qpair * (2 * TC_M) + rank * TC_M);
+                mbar_wait(a_empty, a_phase ^ 1u);   // every MMA of the previous item has retired
+                if (rank == 0) mbar_arrive_expect_tx(a_full, 2u * p.kblocks * TC_A_BYTES);
+                const uint32_t bar = mapa_u32(smem_u32(a_full), 0);
+                for (uint32_t kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_2d_pair(a_res + (size_t)kb * TC_A_BYTES, &map_q, bar, (int)(kb * TC_K), qrow);
+                a_phase ^= 1u;
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const uint32_t grp = item / p.n_qtiles;
-                const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
+        if (rank == 0 && lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
+            for (uint32_t item = pair; item < n_items; item += n_pairs) {
+                const uint32_t grp = item / p.n_qpairs;
+                const uint32_t t0 = grp * p.group, t1 = min(t0 + p.group, p.tiles_total);
+                if (RESIDENT) {
+                    mbar_wait(a_full, a_phase);
+                    tc_fence_after();
+                }
                 for (uint32_t t = t0; t < t1; ++t) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                     tc_fence_after();
@@ -191,31 +251,38 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
-                        const uint64_t da = umma_desc(sa), db = umma_desc(sa + TC_A_BYTES);
+                        const uint32_t sr = smem_u32(ring + (size_t)stage * STAGE_BYTES);
+                        const uint32_t sa = RESIDENT ? smem_u32(a_res + (size_t)kb * TC_A_BYTES) : sr;
+                        const uint32_t sb = RESIDENT ? sr : sr + TC_A_BYTES;
+                        const uint64_t da = umma_desc(sa), db = umma_desc(sb);
 #pragma unroll
                         for (int k = 0; k < TC_K / 16; ++k)  // advance 16 bf16 = 32 B inside the swizzle row
-                            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, (kb | (uint32_t)k) ? 1u : 0u);
-                        tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                            tc_mma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                        tc_commit_pair(&empty_bar[stage]);   // frees the slot in both CTAs once these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit(&tmem_full[acc]);         // accumulator ready for the epilogue
+                    tc_commit_pair(&tmem_full[acc]);         // accumulator halves ready in both CTAs
                     acc ^= 1u;
                     if (acc == 0) acc_phase ^= 1u;
+                }
+                if (RESIDENT) {
+                    tc_commit_pair(a_empty);                 // query tiles may be replaced in both CTAs
+                    a_phase ^= 1u;
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: one thread per query row =====
+        // ===== epilogue: one thread per query row of this CTA's half =====
         const uint32_t quad = (uint32_t)(warp & 3);
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const uint32_t qtile = item % p.n_qtiles, grp = item / p.n_qtiles;
-            const uint32_t t0 = grp * TC_GROUP, t1 = min(t0 + (uint32_t)TC_GROUP, p.tiles_total);
-            const uint32_t q = qtile * TC_M + quad * 32 + lane;
-            const float T = q < p.nq ? p.thr_dot[q] : CUDART_INF_F;
+        const uint32_t empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+        for (uint32_t item = pair; item < n_items; item += n_pairs) {
+            const uint32_t qpair = item % p.n_qpairs, grp = item / p.n_qpairs;
+            const uint32_t t0 = grp * p.group, t1 = min(t0 + p.group, p.tiles_total);
+            const uint32_t q = qpair * (2 * TC_M) + rank * TC_M + quad * 32 + lane;
+            const float T = q < p.nq ? p.thr_dot[q] : CUDART_INF_F;   // survivor <=> score > T
             // survivors are buffered per thread and appended with ONE slot reservation per TC_QBUF rows
-            uint32_t* myq = s_qbuf + (quad * 32 + lane);   // [TC_QBUF][128] layout: slot i at myq[i * 128], conflict-free
+            uint32_t* myq = s_qbuf + (quad * 32 + lane);   // slot i at myq[i * 128], conflict-free
             int nbuf = 0;
             auto flush = [&]() {
                 if (nbuf == 0) return;
@@ -234,41 +301,35 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 for (int c = 0; c < TC_N; c += 32) {
                     uint32_t r[32];
                     tc_ld32(tmem_base + ((quad * 32u) << 16) + acc * TC_N + (uint32_t)c, r);
-                    bool any = false;
+                    // bit j of m = sign(T - score_j): two instructions per score, no branches
+                    uint32_t m = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) any |= (__uint_as_float(r[j]) >= T);
-                    if (any) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (__uint_as_float(r[j]) >= T) {
-                                uint32_t row = row_base + (uint32_t)c + (uint32_t)j;
-                                if (row < p.r1 && (!p.mask || ((p.mask[row >> 6] >> (row & 63u)) & 1ull))) {
-                                    if (p.direct_append) {
-                                        uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
-                                        if (pos < p.cap) p.cand_ids[(size_t)q * p.cap + pos] = row;
-                                        else *p.overflow = 1u;
-                                    } else {
-                                        myq[(nbuf++) * 128] = row;
-                                        if (nbuf == TC_QBUF) flush();
-                                    }
-                                }
-                            }
+                    for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(T - __uint_as_float(r[j])), m, 1);
+                    while (m) {
+                        const uint32_t j = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t row = row_base + (uint32_t)c + j;
+                        if (row < p.r1 && (!p.mask || ((p.mask[row >> 6] >> (row & 63u)) & 1ull))) {
+                            myq[(nbuf++) * 128] = row;
+                            if (nbuf == TC_QBUF) flush();
                         }
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? empty1 : empty0);
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
             }
             flush();
         }
     }
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();   // neither CTA leaves (or frees TMEM) while its partner can still signal it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -310,7 +371,7 @@ __global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr,
     else dotk = 1.0f - scan_unorder_f32(ok);   // IP / IP_CLAMP: distance = 1 - dot (clamped at 0: dot >= 1 stays conservative)
     const float xmax = __uint_as_float(*xmax_bits);
     const float eps = 1.25f * 0.00390625f * qnorm[q] * xmax + 1e-6f;
-    thr_dot[q] = dotk - eps - fabsf(dotk) * 1e-6f;
+    thr_dot[q] = nextafterf(dotk - eps - fabsf(dotk) * 1e-6f, -CUDART_INF_F);   // strict: the kernel keeps score > thr_dot
 }
 
 // K2r: exact f32 score of every survivor -> packed rank key in cand[q][i].
@@ -399,26 +460,36 @@ void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t d
 // on return s.cand / s.cand_cnt hold exact packed keys ready for select_kernel.
 void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq,
                          uint32_t r0, uint32_t r1, const uint64_t* d_mask, uint32_t cap, int sms, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
-        LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        attr = true;
-    }
     dot_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.thr, ts.qnorm, tv.xmax_bits, nq, f.metric, ts.thr_dot);
     CUtensorMap mq = make_map(ts.q_bf16, nq, tv.dp8, TC_M);
-    CUtensorMap mx = make_map(tv.x_bf16, f.n, tv.dp8, TC_N);
+    CUtensorMap mx = make_map(tv.x_bf16, f.n, tv.dp8, TC_NH);
     TcParams p;
     p.nq = nq; p.r0 = r0; p.r1 = r1;
     p.kblocks = (tv.dp8 + TC_K - 1) / TC_K;
-    p.n_qtiles = (nq + TC_M - 1) / TC_M;
+    p.n_qpairs = (nq + 2 * TC_M - 1) / (2 * TC_M);
     p.tiles_total = (r1 - r0 + TC_N - 1) / TC_N;
-    p.n_groups = (p.tiles_total + TC_GROUP - 1) / TC_GROUP;
-    static const int direct = getenv("LEANN_TC_DIRECT_APPEND") ? 1 : 0;
-    p.direct_append = direct;
+    const bool resident = p.kblocks <= (uint32_t)TC_MAX_RES_KB;
+    const size_t a_bytes = resident ? (size_t)p.kblocks * TC_A_BYTES : 0;
+    const size_t stage_bytes = resident ? TC_B_BYTES : TC_A_BYTES + TC_B_BYTES;
+    const size_t fixed = 1024 /*align*/ + TC_BAR_BYTES + (size_t)128 * TC_QBUF * 4 + a_bytes;
+    p.stages = (uint32_t)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_MAX - fixed) / stage_bytes);
+    const size_t smem = fixed + (size_t)p.stages * stage_bytes;
+    const uint32_t max_pairs = (uint32_t)std::max(1, sms / 2);
+    // database tiles per work item: long enough to amortise the query-tile reload, short enough to balance
+    uint64_t want = (uint64_t)p.tiles_total * p.n_qpairs / ((uint64_t)max_pairs * 6u);
+    p.group = (uint32_t)std::min<uint64_t>(32u, std::max<uint64_t>(4u, want));
+    p.n_groups = (p.tiles_total + p.group - 1) / p.group;
     p.thr_dot = ts.thr_dot; p.mask = d_mask; p.cand_ids = ts.cand_ids; p.cand_cnt = s.cand_cnt; p.cap = cap; p.overflow = s.overflow;
-    uint32_t items = p.n_qtiles * p.n_groups;
-    int grid = (int)std::min<uint32_t>((uint32_t)sms, items);
-    scan_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(mq, mx, p);
+    const uint32_t items = p.n_qpairs * p.n_groups;
+    const int grid = 2 * (int)std::min<uint32_t>(max_pairs, items);
+    static bool attr = false;
+    if (!attr) {
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+        attr = true;
+    }
+    if (resident) scan_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mq, mx, p);
+    else scan_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(mq, mx, p);
     LEANN_CUDA_CHECK(cudaGetLastError());
     rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand);
     LEANN_CUDA_CHECK(cudaGetLastError());
