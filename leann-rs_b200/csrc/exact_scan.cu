@@ -33,7 +33,9 @@ __device__ __forceinline__ float unorder_f32(uint32_t u) {
 }
 
 // One 128x128 tile of scores, K-loop over the padded dimension, threshold epilogue.
-template <int METRIC>
+// DIRECT (first round: no threshold yet, every row is a candidate): the slot of a row is its offset in the chunk,
+// no atomics; masked-out rows leave the ~0 sentinel and the host presets cand_cnt = r1 - r0.
+template <int METRIC, bool DIRECT>
 __global__ void __launch_bounds__(256)
 scan_tile_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32_t d4, uint32_t nq,
                  uint32_t r0, uint32_t r1, const uint64_t* __restrict__ mask,
@@ -130,6 +132,11 @@ scan_tile_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uin
                 ok = order_f32(dd);
             }
             unsigned long long key = ((unsigned long long)ok << 32) | row;
+            if (DIRECT) {
+                const bool keep = !mask || ((mask[row >> 6] >> (row & 63u)) & 1ull);
+                cand[(size_t)qi * cap + (row - r0)] = keep ? key : ~0ull;
+                continue;
+            }
             if (key > th) continue;
             if (mask && !((mask[row >> 6] >> (row & 63u)) & 1ull)) continue;
             uint32_t pos = atomicAdd(&cand_cnt[qi], 1u);
@@ -156,51 +163,119 @@ __device__ void block_bitonic_sort(unsigned long long* keys, uint32_t n) {
     __syncthreads();
 }
 
+// The (kth+1)-th smallest of n 64-bit keys in shared memory: MSB-first radix select, 8 bits per pass.
+// All threads of the block call it; hist = 256 counters + 2 words in shared memory.
+__device__ unsigned long long block_kth_smallest(const unsigned long long* keys, uint32_t n, uint32_t kth, uint32_t* hist) {
+    unsigned long long prefix = 0;
+    uint32_t remaining = kth;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long v = keys[i];
+            if (pass == 0 || (v >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(uint32_t)(v >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t lane = threadIdx.x;
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; sum += c[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= (uint32_t)off) incl += t;
+            }
+            const uint32_t before = incl - sum;
+            if (remaining >= before && remaining < incl) {   // exactly one lane
+                uint32_t acc = before;
+                int j = 0;
+                while (j < 7 && remaining >= acc + c[j]) { acc += c[j]; ++j; }
+                hist[256] = lane * 8 + (uint32_t)j;
+                hist[257] = acc;
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)hist[256] << shift;
+        remaining -= hist[257];
+        __syncthreads();
+    }
+    return prefix;
+}
+
 // Merge (running best) + (candidates) -> new best, dedupe, new threshold. One block per query.
+// A row can appear twice (once in best, once re-appended by a chunk re-run after overflow), never more, so the
+// 2k smallest keys with multiplicity always hold the k smallest distinct ones: a radix select cuts the working
+// set to those before the sort.
 __global__ void __launch_bounds__(256)
 select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand_cnt, uint32_t cap,
               unsigned long long* __restrict__ best, uint32_t* __restrict__ best_cnt, uint32_t k, uint32_t kpad,
-              unsigned long long* __restrict__ thr, uint32_t nq) {
-    extern __shared__ unsigned long long skeys[];
+              unsigned long long* __restrict__ thr, uint32_t nq, uint32_t sort_cap) {
+    extern __shared__ unsigned long long skeys[];   // [sort_cap] sort buffer, then [cap + kpad] staging
+    __shared__ uint32_t s_hist[258];
+    __shared__ uint32_t s_n;
     const uint32_t q = blockIdx.x;
     if (q >= nq) return;
     uint32_t nc = cand_cnt[q];
     if (nc > cap) nc = cap;
-    uint32_t nb = best_cnt[q];
+    const uint32_t nb = best_cnt[q];
     if (nc == 0) return;  // nothing new: best/thr unchanged
     uint32_t total = nc + nb;
-    uint32_t n2 = 1;
-    while (n2 < total) n2 <<= 1;
-    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-        unsigned long long v = ~0ull;
-        if (i < nb) v = best[(size_t)q * kpad + i];
-        else if (i < total) v = cand[(size_t)q * cap + (i - nb)];
-        skeys[i] = v;
+    unsigned long long* sortbuf = skeys;
+    if (total > 2 * k + 1 && total > 512) {
+        unsigned long long* stage = skeys + sort_cap;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x)
+            stage[i] = i < nb ? best[(size_t)q * kpad + i] : cand[(size_t)q * cap + (i - nb)];
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const unsigned long long cut = block_kth_smallest(stage, total, 2 * k - 1, s_hist);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const unsigned long long v = stage[i];
+            if (v <= cut && v != ~0ull) {
+                uint32_t pos = atomicAdd(&s_n, 1u);
+                if (pos < sort_cap) sortbuf[pos] = v;
+            }
+        }
+        __syncthreads();
+        total = min(s_n, sort_cap);   // <= 2k + 1 (the cut key itself may be duplicated once)
+        uint32_t n2 = 1;
+        while (n2 < total) n2 <<= 1;
+        for (uint32_t i = total + threadIdx.x; i < n2; i += blockDim.x) sortbuf[i] = ~0ull;
+        block_bitonic_sort(sortbuf, n2);
+    } else {
+        uint32_t n2 = 1;
+        while (n2 < total) n2 <<= 1;
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+            unsigned long long v = ~0ull;
+            if (i < nb) v = best[(size_t)q * kpad + i];
+            else if (i < total) v = cand[(size_t)q * cap + (i - nb)];
+            sortbuf[i] = v;
+        }
+        block_bitonic_sort(sortbuf, n2);
     }
-    block_bitonic_sort(skeys, n2);
-    // dedupe adjacent equal keys (a chunk re-run after overflow re-appends rows already kept);
-    // single thread compaction of at most k survivors.
-    __shared__ uint32_t s_out;
+    // dedupe adjacent equal keys; single thread compaction of at most k survivors.
     if (threadIdx.x == 0) {
         uint32_t o = 0;
         unsigned long long prev = ~0ull;
         for (uint32_t i = 0; i < total && o < k; ++i) {
-            unsigned long long v = skeys[i];
+            unsigned long long v = sortbuf[i];
             if (v == ~0ull) break;
             if (i > 0 && v == prev) continue;
             best[(size_t)q * kpad + o++] = v;
             prev = v;
         }
-        s_out = o;
         best_cnt[q] = o;
         thr[q] = (o == k) ? best[(size_t)q * kpad + k - 1] : ~0ull;
         cand_cnt[q] = 0;
     }
 }
 
-__global__ void scan_init_kernel(uint32_t* cand_cnt, uint32_t* best_cnt, unsigned long long* thr, uint32_t nq, uint32_t* overflow) {
+__global__ void scan_init_kernel(uint32_t* cand_cnt, uint32_t* best_cnt, unsigned long long* thr, uint32_t nq, uint32_t* overflow,
+                                 uint32_t first_rows) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq) { cand_cnt[i] = 0; best_cnt[i] = 0; thr[i] = ~0ull; }
+    if (i < nq) { cand_cnt[i] = first_rows; best_cnt[i] = 0; thr[i] = ~0ull; }
     if (i == 0) { overflow[0] = 0; overflow[1] = 0xFFFFFFFFu; }
 }
 // overflow[0]: set by a scoring kernel that had to drop a survivor; overflow[1]: first round where that happened.
@@ -338,7 +413,8 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     }
     if ((size_t)(p - (unsigned char*)scratch) > scratch_bytes) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: scratch too small");
 
-    scan_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.cand_cnt, s.best_cnt, s.thr, nq, s.overflow);
+    scan_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.cand_cnt, s.best_cnt, s.thr, nq, s.overflow,
+                                                           (uint32_t)std::min<uint64_t>(f.n, SCAN_CAP));
     launch_pad_rows(d_queries, s.qpad, nq, f.d, f.d4, stream);
     if (use_tc) exact_scan_tc_queries(s.qpad, nq, f.d4, tv->dp8, ts, stream);
 
@@ -353,33 +429,37 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         r0 = r1;
     }
     static bool attr_set = false;
-    const size_t sel_smem = (size_t)2 * SCAN_CAP * 8;  // best (<=1024) + cand (<=4096) rounded to 8192 keys
+    uint32_t sort_cap = 512;   // sort buffer: the 2k + 1 keys a radix select keeps, or a short list sorted whole
+    while (sort_cap < 2 * k + 1) sort_cap <<= 1;
+    const size_t sel_smem = ((size_t)sort_cap + SCAN_CAP + kpad) * 8;
     if (!attr_set) {
-        LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)4096 + SCAN_CAP + 1024) * 8)));
         attr_set = true;
     }
-    auto run_round = [&](size_t ri) {
+    auto run_round = [&](size_t ri, int attempt) {
         const uint32_t r0 = rounds[ri].first, r1 = rounds[ri].second;
         dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);
         if (use_tc && ri > 0) {
             // tensor-core pass + fp32 re-rank for every chunk after the first
             exact_scan_tc_round(f, *tv, s, ts, nq, r0, r1, d_mask, SCAN_CAP, sms, stream);
         } else
-        switch (f.metric) {
-            case LEANN_METRIC_L2SQ:
-                scan_tile_kernel<LEANN_METRIC_L2SQ><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                break;
-            case LEANN_METRIC_IP_CLAMP:
-                scan_tile_kernel<LEANN_METRIC_IP_CLAMP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                break;
-            case LEANN_METRIC_DOT_DESC:
-                scan_tile_kernel<LEANN_METRIC_DOT_DESC><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
-                break;
-            default:
-                scan_tile_kernel<LEANN_METRIC_IP><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand, s.cand_cnt, SCAN_CAP, s.overflow);
+        {
+            const bool direct = ri == 0 && attempt == 0;   // no threshold yet: slot = row offset, cand_cnt preset by scan_init
+#define LEANN_TILE(M)                                                                                                          \
+    (direct ? scan_tile_kernel<M, true><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand,      \
+                                                                   s.cand_cnt, SCAN_CAP, s.overflow)                            \
+            : scan_tile_kernel<M, false><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand,     \
+                                                                    s.cand_cnt, SCAN_CAP, s.overflow))
+            switch (f.metric) {
+                case LEANN_METRIC_L2SQ: LEANN_TILE(LEANN_METRIC_L2SQ); break;
+                case LEANN_METRIC_IP_CLAMP: LEANN_TILE(LEANN_METRIC_IP_CLAMP); break;
+                case LEANN_METRIC_DOT_DESC: LEANN_TILE(LEANN_METRIC_DOT_DESC); break;
+                default: LEANN_TILE(LEANN_METRIC_IP);
+            }
+#undef LEANN_TILE
         }
         LEANN_CUDA_CHECK(cudaGetLastError());
-        select_kernel<<<nq, 256, sel_smem, stream>>>(s.cand, s.cand_cnt, SCAN_CAP, s.best, s.best_cnt, k, kpad, s.thr, nq);
+        select_kernel<<<nq, 256, sel_smem, stream>>>(s.cand, s.cand_cnt, SCAN_CAP, s.best, s.best_cnt, k, kpad, s.thr, nq, sort_cap);
         note_overflow_kernel<<<1, 1, 0, stream>>>(s.overflow, (uint32_t)ri);
         LEANN_CUDA_CHECK(cudaGetLastError());
     };
@@ -388,7 +468,7 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     // after it are repeated with the tightened thresholds (rows already kept are deduplicated by select_kernel).
     size_t first = 0;
     for (int attempt = 0;; ++attempt) {
-        for (size_t ri = first; ri < rounds.size(); ++ri) run_round(ri);
+        for (size_t ri = first; ri < rounds.size(); ++ri) run_round(ri, attempt);
         LEANN_CUDA_CHECK(cudaMemcpyAsync(h_flag, s.overflow, 8, cudaMemcpyDeviceToHost, stream));
         LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
         if (h_flag[1] == 0xFFFFFFFFu) break;

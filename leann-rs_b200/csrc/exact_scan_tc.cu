@@ -39,7 +39,7 @@ constexpr int TC_MAX_RES_KB = 7;  // query tile stays resident in shared memory 
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 256;
 constexpr int TC_QBUF = 32;      // survivors buffered per query row before one slot reservation
-constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_BAR_BYTES = 512;
 constexpr size_t TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,9 +164,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t* empty_bar = bars + TC_MAX_STAGES;           // [8]  one per CTA (multicast commit)
     uint64_t* tmem_full = bars + 2 * TC_MAX_STAGES;       // [2]  one per CTA (multicast commit)
     uint64_t* tmem_empty = bars + 2 * TC_MAX_STAGES + 2;  // [2]  leader's copy: 8 epilogue warps arrive
-    uint64_t* a_full = bars + 2 * TC_MAX_STAGES + 4;      // leader's copy
-    uint64_t* a_empty = bars + 2 * TC_MAX_STAGES + 5;     // one per CTA (multicast commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
+    uint64_t* a_full = bars + 2 * TC_MAX_STAGES + 4;      // [7] per resident k-block; leader's copy
+    uint64_t* a_empty = a_full + TC_MAX_RES_KB;           // [7] one per CTA (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + TC_MAX_RES_KB);
     uint32_t* s_qbuf = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + TC_BAR_BYTES);  // [TC_QBUF][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -179,8 +179,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        for (int kb = 0; kb < TC_MAX_RES_KB; ++kb) { mbar_init(&a_full[kb], 1); mbar_init(&a_empty[kb], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -225,11 +224,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             for (uint32_t item = pair; item < n_items; item += n_pairs) {
                 const uint32_t qpair = item % p.n_qpairs;
                 const int qrow = (int)(qpair * (2 * TC_M) + rank * TC_M);
-                mbar_wait(a_empty, a_phase ^ 1u);   // every MMA of the previous item has retired
-                if (rank == 0) mbar_arrive_expect_tx(a_full, 2u * p.kblocks * TC_A_BYTES);
-                const uint32_t bar = mapa_u32(smem_u32(a_full), 0);
-                for (uint32_t kb = 0; kb < p.kblocks; ++kb)
-                    tma_load_2d_pair(a_res + (size_t)kb * TC_A_BYTES, &map_q, bar, (int)(kb * TC_K), qrow);
+                // k-block kb of the tile is replaced as soon as the previous item's last MMAs on it retire,
+                // while that item's remaining k-blocks are still running
+                for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&a_empty[kb], a_phase ^ 1u);
+                    if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2u * TC_A_BYTES);
+                    tma_load_2d_pair(a_res + (size_t)kb * TC_A_BYTES, &map_q, mapa_u32(smem_u32(&a_full[kb]), 0), (int)(kb * TC_K), qrow);
+                }
                 a_phase ^= 1u;
             }
         }
@@ -240,15 +241,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             for (uint32_t item = pair; item < n_items; item += n_pairs) {
                 const uint32_t grp = item / p.n_qpairs;
                 const uint32_t t0 = grp * p.group, t1 = min(t0 + p.group, p.tiles_total);
-                if (RESIDENT) {
-                    mbar_wait(a_full, a_phase);
-                    tc_fence_after();
-                }
                 for (uint32_t t = t0; t < t1; ++t) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TC_N;
                     for (uint32_t kb = 0; kb < p.kblocks; ++kb) {
+                        if (RESIDENT && t == t0) mbar_wait(&a_full[kb], a_phase);
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint32_t sr = smem_u32(ring + (size_t)stage * STAGE_BYTES);
@@ -259,16 +257,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         for (int k = 0; k < TC_K / 16; ++k)  // advance 16 bf16 = 32 B inside the swizzle row
                             tc_mma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, (kb | (uint32_t)k) ? 1u : 0u);
                         tc_commit_pair(&empty_bar[stage]);   // frees the slot in both CTAs once these MMAs retire
+                        if (RESIDENT && t + 1 == t1) tc_commit_pair(&a_empty[kb]);   // query k-block may be replaced
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit_pair(&tmem_full[acc]);         // accumulator halves ready in both CTAs
                     acc ^= 1u;
                     if (acc == 0) acc_phase ^= 1u;
                 }
-                if (RESIDENT) {
-                    tc_commit_pair(a_empty);                 // query tiles may be replaced in both CTAs
-                    a_phase ^= 1u;
-                }
+                a_phase ^= 1u;
             }
         }
     } else if (warp >= 4) {
