@@ -24,6 +24,8 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Per-warp shared-memory state.
 struct WarpLists {
     float* top_d; uint32_t* top_s;    // ascending, size <= ef
@@ -211,7 +213,7 @@ __device__ __forceinline__ void greedy_descend(const GraphView& g, const float4 
 //   nonstrict == 0 : stop when cand.d >  radius   (usearch)
 //   nonstrict == 1 : stop when cand.d >= radius   (diskann-rs; only reachable when top is full)
 // mask: nullable; nodes failing it are traversed but never enter `top` (usearch predicate shape).
-template <int LPV, int VPL, int U>
+template <int LPV, int VPL, int U, bool PREFETCH = false>
 __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL],
                                            WarpLists& w, int ef, int next_cap, int next_mask, int nonstrict,
                                            const uint64_t* __restrict__ mask, uint8_t* vis, uint8_t tag,
@@ -233,6 +235,11 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
         if (adj.level == 0) c.n_hops0++; else c.n_hops_upper++;
         // ---- adjacency row -> unvisited neighbours, list order preserved ----
         const uint32_t* row = adj.row(cs);
+        if (PREFETCH && adj.level == 0 && w.next_size > 0) {
+            // the most likely next pop is the new head of the queue: pull its adjacency row into L2 now
+            const uint32_t nh = w.next_s[w.next_head & next_mask];
+            if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
+        }
         int cnt = 0;
         for (uint32_t base = 0; base < adj.deg; base += 32) {
             uint32_t j = base + lane;
@@ -247,6 +254,16 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
         }
         __syncwarp();
         c.n_dist += cnt;
+        if (PREFETCH) {
+            // rows beyond the first register batch are requested from HBM now, so that the later batches of
+            // eval_distances find them in L2 (one DRAM latency per hop instead of one per batch)
+            constexpr int BATCH = U * (32 / LPV);
+            const uint32_t lines = (g.d4 * 16u + 127u) >> 7;
+            for (int j = BATCH + lane; j < cnt; j += 32) {
+                const char* r = reinterpret_cast<const char*>(g.vecs + (size_t)w.st_slot[j] * g.d4);
+                for (uint32_t l = 0; l < lines; ++l) prefetch_l2(r + l * 128u);
+            }
+        }
         eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
         // ---- replay the inserts in list order ----
         for (int base = 0; base < cnt; base += 32) {

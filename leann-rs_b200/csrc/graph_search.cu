@@ -57,7 +57,7 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         if (g.max_level > 0) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, 0, c, lane);
 
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
-        beam_level<LPV, VPL, U>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
+        beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
                                 p.mask, vis, tag, cur, cur_d, c, lane);
 
         // results: ascending, truncated to k; tail = UINT64_MAX / +inf
