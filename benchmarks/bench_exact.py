@@ -11,7 +11,7 @@ import leann_rs_b200 as P
 from leann_rs_b200 import shards as S
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=10_000_000); ap.add_argument("--d", type=int, default=384)
+ap.add_argument("--n", "--rows", dest="n", type=int, default=10_000_000); ap.add_argument("--d", type=int, default=384)
 ap.add_argument("--k", type=int, default=100); ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--steps", type=int, default=3); ap.add_argument("--check", type=int, default=256)
 a = ap.parse_args()
@@ -50,7 +50,7 @@ if rank == 0:
     tf = 2.0 * a.n * a.d * a.nq / (ms / 1e3) / 1e12
     print(json.dumps({"bench": "exact_scan", "n": a.n, "d": a.d, "k": a.k, "nq": a.nq, "gpus": world, "ms_per_batch": round(ms, 2),
                       "qps": round(a.nq / ms * 1e3, 1), "step_ms": [round(v, 1) for v in step_ms], "tflops_algorithmic": round(tf, 1),
-                      "frac_of_bf16_sustained_peak": round(tf / peaks.get("bf16_tflops_sustained", 1395.4), 4),
+                      "frac_of_bf16_sustained_peak_per_gpu": round(tf / world / peaks.get("bf16_tflops_sustained", 1395.4), 4),
                       "tc_path": os.environ.get("LEANN_CUDA_DISABLE_TC") is None,
                       "checksum": int(keys.sum().item()) & 0xFFFFFFFF, "score_sum": float(sc.double().sum().item())}))
 if world > 1: dist.destroy_process_group()
