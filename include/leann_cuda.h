@@ -75,6 +75,13 @@ int leann_cuda_flat_from_device(const float* d_vectors, size_t n, size_t dims, i
 int leann_cuda_hnsw_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
                           size_t graph_degree, size_t complexity, int metric, uint64_t seed, int device,
                           leann_cuda_index** out, char* err, size_t errlen);
+/* hnsw::add_to_index (backend/hnsw.rs:142-191, called from cli/update.rs:221-232): appends `m` vectors to a
+ * GPU-resident HNSW index with keys start_id .. start_id + m - 1, as `index.add(id, embedding)` after
+ * `index.load`. Connectivity is the index's; `complexity` is expansion_add (the reference passes 64).
+ * Follow with leann_cuda_save to write the updated `.index`. Must not run concurrently with a search on
+ * the same handle. */
+int leann_cuda_hnsw_add(leann_cuda_index* index, const float* vectors, int vectors_on_device, size_t m,
+                        uint64_t start_id, size_t complexity, uint64_t seed, char* err, size_t errlen);
 /* diskann::build_index (backend/diskann.rs:70-105), alpha as DiskAnnParams.alpha (:91). */
 int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
                             size_t graph_degree, size_t complexity, float alpha, int metric,

@@ -55,6 +55,7 @@ def lib():
         "leann_cuda_flat_from_host": (C.c_int, [vp, sz, sz, C.c_int, C.c_int, pp, cp, sz]),
         "leann_cuda_flat_from_device": (C.c_int, [vp, sz, sz, C.c_int, C.c_int, pp, cp, sz]),
         "leann_cuda_hnsw_build": (C.c_int, [vp, C.c_int, sz, sz, sz, sz, C.c_int, C.c_uint64, C.c_int, pp, cp, sz]),
+        "leann_cuda_hnsw_add": (C.c_int, [vp, vp, C.c_int, sz, C.c_uint64, sz, C.c_uint64, cp, sz]),
         "leann_cuda_vamana_build": (C.c_int, [vp, C.c_int, sz, sz, sz, sz, C.c_float, C.c_int, C.c_uint64, C.c_int, pp, cp, sz]),
         "leann_cuda_save": (C.c_int, [vp, cp, cp, sz]),
         "leann_cuda_len": (sz, [vp]),
@@ -285,6 +286,32 @@ class HnswSearcher(BackendSearcher):
         _check(lib().leann_cuda_hnsw_build(ptr, on_dev, n, d, graph_degree, complexity, metric, seed, device,
                                            C.byref(h), e, 1024), e)
         return cls(h.value)
+
+
+    def add(self, embeddings, start_id: int = None, complexity: int = 64, seed: int = 1):
+        """hnsw::add_to_index (hnsw.rs:142-191) on the resident index: keys start_id .. start_id+m-1
+        (default: continue from len(), as cli/update.rs:221-232 does with passage_count)."""
+        e = _err()
+        if start_id is None:
+            start_id = len(self)
+        if isinstance(embeddings, np.ndarray):
+            x = np.ascontiguousarray(embeddings, dtype=np.float32)
+            ptr, on_dev, m = _np_ptr(x), 0, x.shape[0]
+        else:
+            assert embeddings.is_cuda and embeddings.is_contiguous()
+            ptr, on_dev, m = C.c_void_p(embeddings.data_ptr()), 1, embeddings.shape[0]
+        _check(lib().leann_cuda_hnsw_add(self._h, ptr, on_dev, m, start_id, complexity, seed, e, 1024), e)
+        return self
+
+
+def add_to_index(embeddings, index_path: str, dimensions: int, start_id: int, device: int = 0) -> None:
+    """hnsw::add_to_index (hnsw.rs:142-191): load `<index_path>.index`, append, save it back."""
+    s = HnswSearcher.load(index_path, dimensions, device)
+    try:
+        s.add(embeddings, start_id, complexity=64)
+        s.save(index_path)
+    finally:
+        s.close()
 
 
 class DiskAnnSearcher(BackendSearcher):

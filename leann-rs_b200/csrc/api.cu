@@ -15,6 +15,7 @@ int guard_impl(char* err, size_t errlen, const std::function<void()>& f);
 // builders (hnsw_build.cu / vamana_build.cu)
 void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed);
 void gpu_vamana_build(leann_cuda_index* ix, size_t R, size_t L, float alpha, uint64_t seed);
+void gpu_hnsw_add(leann_cuda_index* ix, const float4* new_rows, size_t m, uint64_t start_id, size_t ef_add, uint64_t seed);
 }  // namespace leann
 
 namespace {
@@ -337,6 +338,43 @@ int leann_cuda_hnsw_build(const float* vectors, int vectors_on_device, size_t n,
         upload_vectors(ix.get(), vectors, vectors_on_device != 0);
         gpu_hnsw_build(ix.get(), graph_degree, complexity, seed);
         *out = ix.release();
+    });
+}
+
+int leann_cuda_hnsw_add(leann_cuda_index* ix, const float* vectors, int vectors_on_device, size_t m, uint64_t start_id,
+                        size_t complexity, uint64_t seed, char* err, size_t errlen) {
+    GUARD({
+        if (!ix || (!vectors && m)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        if (ix->backend != LEANN_BACKEND_HNSW) throw Error(LEANN_ERR_INVALID_ARG, "add_to_index is defined for the HNSW backend only (hnsw.rs:142)");
+        if (complexity == 0 || complexity > (size_t)MAX_EF) throw Error(LEANN_ERR_INVALID_ARG, "complexity must be in 1..1024");
+        if (m == 0) return;
+        DeviceGuard dg(ix->device);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        // padded device copy of the new rows
+        float4* rows = dalloc<float4>(m * ix->d4);
+        try {
+            if (vectors_on_device) {
+                launch_pad_rows(vectors, rows, m, (uint32_t)ix->d, ix->d4, nullptr);
+            } else {
+                float* tmp = dalloc<float>(m * ix->d);
+                cudaError_t e = cudaMemcpy(tmp, vectors, m * ix->d * 4, cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) launch_pad_rows(tmp, rows, m, (uint32_t)ix->d, ix->d4, nullptr);
+                cudaDeviceSynchronize();
+                cudaFree(tmp);
+                LEANN_CUDA_CHECK(e);
+            }
+            LEANN_CUDA_CHECK(cudaDeviceSynchronize());
+            gpu_hnsw_add(ix, rows, m, start_id, complexity, seed);
+        } catch (...) {
+            cudaFree(rows);
+            throw;
+        }
+        cudaFree(rows);
+        // the traversal workspace is sized by n: drop it, the next search re-creates it
+        SearchWorkspace& ws = ix->ws;
+        if (ws.visited) cudaFree(ws.visited);
+        if (ws.epochs) cudaFree(ws.epochs);
+        ws.visited = nullptr; ws.epochs = nullptr; ws.n_warps = 0; ws.warp_cap = 0; ws.n_pad = 0;
     });
 }
 

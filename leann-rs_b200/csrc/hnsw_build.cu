@@ -296,50 +296,45 @@ T* dmalloc(size_t count) {
 
 }  // namespace
 
-void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed) {
-    const size_t n = ix->n, M0 = 2 * M;
-    ix->M = (uint32_t)M; ix->M0 = (uint32_t)M0;
-    ix->identity_keys = true;
-    // --- levels: usearch choose_random_level_ = floor(-ln(U) * 1/ln(connectivity)) ---
-    std::vector<uint8_t> lv8(n);
-    ix->h_levels.resize(n);
-    std::vector<uint32_t> upper_base(n);
+namespace {
+
+// entries per list of an existing graph (lists are packed at the front and SENT-padded)
+__global__ void count_lists_kernel(const uint32_t* __restrict__ adj0, const uint32_t* __restrict__ adjU, uint32_t n, uint32_t n_upper,
+                                   uint32_t M, uint32_t M0, uint32_t* __restrict__ cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + n_upper) return;
+    const uint32_t cap = i < n ? M0 : M;
+    const uint32_t* row = i < n ? adj0 + (size_t)i * M0 : adjU + (size_t)(i - n) * M;
+    uint32_t c = 0;
+    while (c < cap && row[c] != SENT) ++c;
+    cnt[i] = c;
+}
+
+// usearch choose_random_level_ = floor(-ln(U) * 1/ln(connectivity)) for slots [first, first + count)
+void draw_levels(size_t count, size_t M, uint64_t seed, std::vector<uint8_t>& out) {
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> uni(0.0, 1.0);
     const double inv_log = 1.0 / std::log((double)M);
-    size_t n_upper = 0;
-    for (size_t i = 0; i < n; ++i) {
+    out.resize(count);
+    for (size_t i = 0; i < count; ++i) {
         double u = uni(rng);
         if (u <= 0.0) u = 1e-300;
         int l = (int)(-std::log(u) * inv_log);
-        if (l > 15) l = 15;
-        lv8[i] = (uint8_t)l;
-        ix->h_levels[i] = (int16_t)l;
-        upper_base[i] = (uint32_t)n_upper;
-        n_upper += (size_t)l;
+        out[i] = (uint8_t)(l > 15 ? 15 : l);
     }
-    ix->n_upper_lists = n_upper;
+}
+
+// Inserts slots [first, n) into the graph held by `ix` (arrays sized for n nodes, rows of the new slots
+// SENT-filled, ix->entry / max_level describing the graph over [0, first)). Batched insertion as described
+// at the top of this file; `lv8` holds the level of every slot.
+void insert_range(leann_cuda_index* ix, const std::vector<uint8_t>& lv8, size_t first, size_t ef_add) {
+    const size_t n = ix->n, M = ix->M, M0 = ix->M0, n_upper = ix->n_upper_lists;
+    if (first >= n) return;
     cudaStream_t stream = nullptr;
     LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     std::vector<void*> temps;
     auto cleanup = [&]() { for (void* t : temps) cudaFree(t); cudaStreamDestroy(stream); };
     try {
-        ix->adj0 = dmalloc<uint32_t>(n * M0);
-        ix->adjU = dmalloc<uint32_t>(n_upper * M);
-        ix->upper_base = dmalloc<uint32_t>(n);
-        ix->keys = dmalloc<uint64_t>(n);
-        LEANN_CUDA_CHECK(cudaMemset(ix->adj0, 0xFF, std::max<size_t>(n * M0, 1) * 4));
-        LEANN_CUDA_CHECK(cudaMemset(ix->adjU, 0xFF, std::max<size_t>(n_upper * M, 1) * 4));
-        if (n) LEANN_CUDA_CHECK(cudaMemcpy(ix->upper_base, upper_base.data(), n * 4, cudaMemcpyHostToDevice));
-        {
-            std::vector<uint64_t> keys(n);
-            for (size_t i = 0; i < n; ++i) keys[i] = i;
-            if (n) LEANN_CUDA_CHECK(cudaMemcpy(ix->keys, keys.data(), n * 8, cudaMemcpyHostToDevice));
-        }
-        ix->entry = 0;
-        ix->max_level = n ? lv8[0] : 0;
-        if (n <= 1) { cleanup(); return; }
-
         const uint32_t MAXB = 16384;
         const size_t n_lists = n + n_upper;
         BuildParams p{};
@@ -350,14 +345,16 @@ void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed
         p.cnt = dmalloc<uint32_t>(n_lists); temps.push_back(p.cnt);
         p.flag = dmalloc<uint32_t>(n_lists); temps.push_back(p.flag);
         p.extra = dmalloc<uint32_t>(n_lists * EXTRA); temps.push_back(p.extra);
-        LEANN_CUDA_CHECK(cudaMemset(p.cnt, 0, n_lists * 4));
-        LEANN_CUDA_CHECK(cudaMemset(p.flag, 0, n_lists * 4));
+        count_lists_kernel<<<(unsigned)((n_lists + 255) / 256), 256, 0, stream>>>(ix->adj0, ix->adjU, (uint32_t)n, (uint32_t)n_upper,
+                                                                                (uint32_t)M, (uint32_t)M0, p.cnt);
+        LEANN_CUDA_CHECK(cudaGetLastError());
+        LEANN_CUDA_CHECK(cudaMemsetAsync(p.flag, 0, n_lists * 4, stream));
         p.max_edges = (uint32_t)std::min<size_t>((size_t)MAXB * M * 3, (size_t)0x7FFFFFFF);
         p.edges = dmalloc<uint2>(p.max_edges); temps.push_back(p.edges);
         p.edge_level = dmalloc<uint32_t>(p.max_edges); temps.push_back(p.edge_level);
         p.work = dmalloc<uint2>(p.max_edges); temps.push_back(p.work);
         uint32_t* ctrs = dmalloc<uint32_t>(8); temps.push_back(ctrs);
-        LEANN_CUDA_CHECK(cudaMemset(ctrs, 0, 32));
+        LEANN_CUDA_CHECK(cudaMemsetAsync(ctrs, 0, 32, stream));
         p.edge_count = ctrs; p.work_count = ctrs + 1; p.work_cursor = ctrs + 2; p.counter = ctrs + 3; p.overflow = ctrs + 4;
         p.M = (uint32_t)M; p.M0 = (uint32_t)M0; p.ef_add = (uint32_t)ef_add; p.n = (uint32_t)n;
         p.next_cap = (uint32_t)ef_add;
@@ -373,12 +370,12 @@ void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed
         max_warps = (int)std::min<size_t>((size_t)max_warps, (size_t)MAXB);
         p.visited = dmalloc<uint8_t>((size_t)max_warps * p.n_pad); temps.push_back(p.visited);
         p.epochs = dmalloc<uint32_t>(max_warps); temps.push_back(p.epochs);
-        LEANN_CUDA_CHECK(cudaMemset(p.visited, 0, (size_t)max_warps * p.n_pad));
-        LEANN_CUDA_CHECK(cudaMemset(p.epochs, 0, (size_t)max_warps * 4));
+        LEANN_CUDA_CHECK(cudaMemsetAsync(p.visited, 0, (size_t)max_warps * p.n_pad, stream));
+        LEANN_CUDA_CHECK(cudaMemsetAsync(p.epochs, 0, (size_t)max_warps * 4, stream));
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
 
-        size_t inserted = 1;
+        size_t inserted = first;
         while (inserted < n) {
             uint32_t b = (uint32_t)std::min<size_t>(std::min<size_t>(n - inserted, MAXB), std::max<size_t>(1, inserted / 16));
             p.first = (uint32_t)inserted; p.count = b;
@@ -407,6 +404,95 @@ void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed
     cleanup();
 }
 
+// cudaMalloc a larger array, keep the first `old_count` elements, fill the rest with the byte `fill`.
+template <typename T>
+void grow(T*& ptr, size_t old_count, size_t new_count, int fill) {
+    T* np = dmalloc<T>(new_count);
+    if (old_count) LEANN_CUDA_CHECK(cudaMemcpy(np, ptr, old_count * sizeof(T), cudaMemcpyDeviceToDevice));
+    if (new_count > old_count) LEANN_CUDA_CHECK(cudaMemset(np + old_count, fill, (new_count - old_count) * sizeof(T)));
+    cudaFree(ptr);
+    ptr = np;
+}
+
+}  // namespace
+
+void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed) {
+    const size_t n = ix->n, M0 = 2 * M;
+    ix->M = (uint32_t)M; ix->M0 = (uint32_t)M0;
+    ix->identity_keys = true;
+    std::vector<uint8_t> lv8;
+    draw_levels(n, M, seed, lv8);
+    ix->h_levels.resize(n);
+    std::vector<uint32_t> upper_base(n);
+    size_t n_upper = 0;
+    for (size_t i = 0; i < n; ++i) {
+        ix->h_levels[i] = (int16_t)lv8[i];
+        upper_base[i] = (uint32_t)n_upper;
+        n_upper += (size_t)lv8[i];
+    }
+    ix->n_upper_lists = n_upper;
+    ix->adj0 = dmalloc<uint32_t>(n * M0);
+    ix->adjU = dmalloc<uint32_t>(n_upper * M);
+    ix->upper_base = dmalloc<uint32_t>(n);
+    ix->keys = dmalloc<uint64_t>(n);
+    LEANN_CUDA_CHECK(cudaMemset(ix->adj0, 0xFF, std::max<size_t>(n * M0, 1) * 4));
+    LEANN_CUDA_CHECK(cudaMemset(ix->adjU, 0xFF, std::max<size_t>(n_upper * M, 1) * 4));
+    if (n) LEANN_CUDA_CHECK(cudaMemcpy(ix->upper_base, upper_base.data(), n * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint64_t> keys(n);
+        for (size_t i = 0; i < n; ++i) keys[i] = i;
+        if (n) LEANN_CUDA_CHECK(cudaMemcpy(ix->keys, keys.data(), n * 8, cudaMemcpyHostToDevice));
+    }
+    ix->entry = 0;
+    ix->max_level = n ? lv8[0] : 0;
+    insert_range(ix, lv8, 1, ef_add);
+}
+
+// hnsw::add_to_index (leann-rs src/backend/hnsw.rs:142-191): `m` more vectors (already padded
+// device rows) are appended to a resident index with keys start_id + i, as `index.add(id, embedding)` does after
+// `index.load`. Connectivity comes from the index; the new slots draw their levels from `seed`.
+void gpu_hnsw_add(leann_cuda_index* ix, const float4* new_rows, size_t m, uint64_t start_id, size_t ef_add, uint64_t seed) {
+    if (m == 0) return;
+    const size_t n_old = ix->n, n_new = n_old + m, M = ix->M, M0 = ix->M0;
+    if (n_new > 0xFFFFFFF0ull) throw Error(LEANN_ERR_INVALID_ARG, "index would exceed 2^32 slots");
+    std::vector<uint8_t> lv_new;
+    draw_levels(m, M, seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(n_old + 1)), lv_new);
+    std::vector<uint8_t> lv8(n_new);
+    for (size_t i = 0; i < n_old; ++i) lv8[i] = (uint8_t)std::min<int>(15, std::max<int>(0, ix->h_levels[i]));
+    std::vector<uint32_t> ub_new(m);
+    size_t n_upper = ix->n_upper_lists;
+    for (size_t i = 0; i < m; ++i) {
+        lv8[n_old + i] = lv_new[i];
+        ub_new[i] = (uint32_t)n_upper;
+        n_upper += (size_t)lv_new[i];
+    }
+    grow(ix->vecs, n_old * ix->d4, n_new * ix->d4, 0);
+    LEANN_CUDA_CHECK(cudaMemcpy(ix->vecs + n_old * ix->d4, new_rows, m * (size_t)ix->d4 * 16, cudaMemcpyDeviceToDevice));
+    grow(ix->adj0, n_old * M0, n_new * M0, 0xFF);
+    grow(ix->adjU, ix->n_upper_lists * M, n_upper * M, 0xFF);
+    grow(ix->upper_base, n_old, n_new, 0);
+    LEANN_CUDA_CHECK(cudaMemcpy(ix->upper_base + n_old, ub_new.data(), m * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint64_t> keys(m);
+        for (size_t i = 0; i < m; ++i) keys[i] = start_id + i;
+        if (!ix->keys) {   // indexes opened with key == slot keep no key array
+            std::vector<uint64_t> old(n_old);
+            for (size_t i = 0; i < n_old; ++i) old[i] = i;
+            ix->keys = dmalloc<uint64_t>(n_old);
+            if (n_old) LEANN_CUDA_CHECK(cudaMemcpy(ix->keys, old.data(), n_old * 8, cudaMemcpyHostToDevice));
+        }
+        grow(ix->keys, n_old, n_new, 0);
+        LEANN_CUDA_CHECK(cudaMemcpy(ix->keys + n_old, keys.data(), m * 8, cudaMemcpyHostToDevice));
+    }
+    if (start_id != n_old) ix->identity_keys = false;
+    ix->h_levels.resize(n_new);
+    for (size_t i = 0; i < m; ++i) ix->h_levels[n_old + i] = (int16_t)lv_new[i];
+    ix->n = n_new;
+    ix->n_upper_lists = n_upper;
+    size_t first = n_old;
+    if (n_old == 0) { ix->entry = 0; ix->max_level = lv8[0]; first = 1; }
+    insert_range(ix, lv8, first, ef_add);
+}
 
 namespace {
 

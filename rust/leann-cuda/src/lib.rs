@@ -30,6 +30,12 @@ extern "C" {
                          mask_bits: *const u64, mask_mode: c_int, keys: *mut u64, dists: *mut c_float,
                          counts: *mut u32, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_close(index: *mut LeannCudaIndex);
+    fn leann_cuda_hnsw_build(vectors: *const c_float, vectors_on_device: c_int, n: usize, dims: usize, graph_degree: usize,
+                             complexity: usize, metric: c_int, seed: u64, device: c_int, out: *mut *mut LeannCudaIndex,
+                             err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_hnsw_add(index: *mut LeannCudaIndex, vectors: *const c_float, vectors_on_device: c_int, m: usize,
+                           start_id: u64, complexity: usize, seed: u64, err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_save(index: *const LeannCudaIndex, base_path: *const c_char, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_bm25_build(docs: *const *const c_char, doc_bytes: *const usize, n_docs: usize, device: c_int,
                              out: *mut *mut LeannCudaBm25, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_bm25_free(b: *mut LeannCudaBm25);
@@ -177,3 +183,47 @@ impl CudaSearcher {
 
 #[allow(dead_code)]
 fn _unused(_: *const c_void) {}
+
+fn flatten(embeddings: &[Vec<f32>], dimensions: usize) -> anyhow::Result<Vec<f32>> {
+    let mut flat = Vec::with_capacity(embeddings.len() * dimensions);
+    for e in embeddings {
+        anyhow::ensure!(e.len() == dimensions, "Dimension mismatch: expected {}, got {}", dimensions, e.len());
+        flat.extend_from_slice(e);
+    }
+    Ok(flat)
+}
+
+/// Drop-in for `hnsw::build_index` (`src/backend/hnsw.rs:96-139`): same arguments, same `<base>.index` output.
+pub fn build_index(embeddings: &[Vec<f32>], _ids: &[String], index_path: &Path, dimensions: usize, graph_degree: usize,
+                   complexity: usize) -> anyhow::Result<()> {
+    let flat = flatten(embeddings, dimensions)?;
+    let base = CString::new(index_path.to_string_lossy().as_bytes())?;
+    let mut err = [0u8; 1024];
+    let mut h = std::ptr::null_mut();
+    unsafe {
+        check(leann_cuda_hnsw_build(flat.as_ptr(), 0, embeddings.len(), dimensions, graph_degree, complexity, METRIC_DEFAULT, 1, 0,
+                                    &mut h, err.as_mut_ptr() as *mut c_char, err.len()), &err)?;
+        let rc = leann_cuda_save(h, base.as_ptr(), err.as_mut_ptr() as *mut c_char, err.len());
+        leann_cuda_close(h);
+        check(rc, &err)
+    }
+}
+
+/// Drop-in for `hnsw::add_to_index` (`src/backend/hnsw.rs:142-191`): load, append with keys from `start_id`, save.
+pub fn add_to_index(embeddings: &[Vec<f32>], index_path: &Path, dimensions: usize, start_id: usize) -> anyhow::Result<()> {
+    let flat = flatten(embeddings, dimensions)?;
+    let base = CString::new(index_path.to_string_lossy().as_bytes())?;
+    let mut err = [0u8; 1024];
+    let mut h = std::ptr::null_mut();
+    unsafe {
+        check(leann_cuda_open(base.as_ptr(), BACKEND_HNSW, dimensions, METRIC_DEFAULT, 0, &mut h,
+                              err.as_mut_ptr() as *mut c_char, err.len()), &err)?;
+        let mut rc = leann_cuda_hnsw_add(h, flat.as_ptr(), 0, embeddings.len(), start_id as u64, 64, 1,
+                                         err.as_mut_ptr() as *mut c_char, err.len());
+        if rc == 0 {
+            rc = leann_cuda_save(h, base.as_ptr(), err.as_mut_ptr() as *mut c_char, err.len());
+        }
+        leann_cuda_close(h);
+        check(rc, &err)
+    }
+}

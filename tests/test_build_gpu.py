@@ -78,3 +78,42 @@ def test_gpu_vamana_build_quality_and_file(orc, pkg, tmp_path):
     s3 = pkg.DiskAnnSearcher.build(x2, graph_degree=R, complexity=L, metric=pkg.METRIC_L2SQ)
     gt2 = orc.exact_f64(q2, x2, k, metric=1)
     assert _recall(s3.search_batch(q2, k, L)[0], gt2, k) > 0.9
+
+
+def test_gpu_hnsw_add_to_index(orc, pkg, tmp_path):
+    """hnsw::add_to_index (hnsw.rs:142-191): append to a saved index, keys continue from start_id, the updated
+    file is a valid usearch `.index`, GPU search on it equals the oracle on the same file, and recall over the
+    whole set matches a one-shot build."""
+    n0, m, d, M, k = 12000, 8000, 128, 16, 10
+    x, q = make_data(n0 + m, d, 77, nq=300)
+    base = str(tmp_path / "documents.leann")
+    s0 = pkg.HnswSearcher.build(x[:n0], graph_degree=M, complexity=64, seed=3)
+    s0.save(base)
+    s0.close()
+    pkg.add_to_index(x[n0:], base, d, start_id=n0)          # load -> add -> save, as the reference does
+    s = pkg.HnswSearcher.load(base, d)
+    assert len(s) == n0 + m and s.info()["M"] == M
+    gt = orc.exact_f64(q, x, k)
+    keys, dists, counts = s.search_batch(q, k, 64)
+    r_add = _recall(keys, gt, k)
+    full = pkg.HnswSearcher.build(x, graph_degree=M, complexity=64, seed=3)
+    r_full = _recall(full.search_batch(q, k, 64)[0], gt, k)
+    assert r_add > 0.9 and r_add > r_full - 0.03, (r_add, r_full)
+    assert (keys[:, 0] < n0 + m).all() and (keys >= n0).any()           # appended rows are reachable
+    g = orc.Hnsw.load(base.replace(".leann", ".index"), d)                 # format + size equation
+    assert g.info()["n"] == n0 + m
+    ok, od, oc, _ = g.search(q, k, 64, lanes=pkg.reduction_lanes(d), next_cap=64)
+    assert np.array_equal(keys, ok) and np.array_equal(dists.view(np.uint32), od.view(np.uint32))
+    # non-contiguous keys: start_id beyond the current size
+    s.add(x[:100] * np.float32(2.0), start_id=10**6)      # dot with the doubled copy beats the original
+    k2, _, _ = s.search_batch(x[:20], 3, 64)
+    assert len(s) == n0 + m + 100 and (k2[:, 0] == 10**6 + np.arange(20)).mean() > 0.9
+    # adding to an empty-then-built tiny index and to a Vamana handle
+    t = pkg.HnswSearcher.build(x[:1], graph_degree=4, complexity=16)
+    t.add(x[1:40])
+    kk, _, cc = t.search_batch(q[:4], 5, 16)
+    assert len(t) == 40 and (cc == 5).all()
+    v = pkg.DiskAnnSearcher.build(x[:500], graph_degree=8, complexity=16)
+    with pytest.raises(pkg.LeannCudaError):
+        pkg.lib().leann_cuda_hnsw_add  # symbol exists
+        pkg.HnswSearcher.add(v, x[:3])
