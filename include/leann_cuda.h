@@ -53,6 +53,7 @@ extern "C" {
 typedef struct leann_cuda_index leann_cuda_index;
 typedef struct leann_cuda_bm25 leann_cuda_bm25;
 typedef struct leann_cuda_filter leann_cuda_filter;
+typedef struct leann_cuda_metacols leann_cuda_metacols;
 typedef struct leann_cuda_searcher leann_cuda_searcher;
 
 /* ---------------------------------------------------------------------------------------------
@@ -193,6 +194,19 @@ int leann_cuda_filter_matches(const leann_cuda_filter* f, const char* metadata_j
 int leann_cuda_filter_mask(const leann_cuda_filter* f, const char* const* metadata_json,
                            const size_t* bytes, size_t n, uint64_t* mask_bits, char* err, size_t errlen);
 void leann_cuda_filter_free(leann_cuda_filter* f);
+
+/* Columnar side-car of the passages' metadata. The reference opens the passage file and parses
+ * its JSON for every candidate a filter is tested on (index/passages.rs:90-105 + filter.rs:319-439); here each
+ * dotted field path becomes one typed column (kind / f64 / dictionary-coded string) built once, and a parsed
+ * filter is evaluated column-wise into the N-bit mask the kernels test. metadata_json[i] == NULL: passage i has
+ * no metadata. Results are identical to leann_cuda_filter_mask row by row. Host only. */
+int leann_cuda_metacols_build(const char* const* metadata_json, const size_t* bytes, size_t n,
+                              leann_cuda_metacols** out, char* err, size_t errlen);
+int leann_cuda_metacols_mask(const leann_cuda_metacols* cols, const leann_cuda_filter* f, uint64_t* mask_bits,
+                             char* err, size_t errlen);
+size_t leann_cuda_metacols_len(const leann_cuda_metacols* cols);
+size_t leann_cuda_metacols_fields(const leann_cuda_metacols* cols);
+void leann_cuda_metacols_free(leann_cuda_metacols* cols);
 
 /* ---------------------------------------------------------------------------------------------
  * IndexSearcher (index/searcher.rs:76-109 load; :123-210 search; :228-246 bm25_search):

@@ -85,6 +85,11 @@ def lib():
         "leann_cuda_filter_matches": (C.c_int, [vp, cp, sz, C.POINTER(C.c_int), cp, sz]),
         "leann_cuda_filter_mask": (C.c_int, [vp, cpp, szp, sz, vp, cp, sz]),
         "leann_cuda_filter_free": (None, [vp]),
+        "leann_cuda_metacols_build": (C.c_int, [cpp, szp, sz, pp, cp, sz]),
+        "leann_cuda_metacols_mask": (C.c_int, [vp, vp, vp, cp, sz]),
+        "leann_cuda_metacols_len": (sz, [vp]),
+        "leann_cuda_metacols_fields": (sz, [vp]),
+        "leann_cuda_metacols_free": (None, [vp]),
         "leann_cuda_searcher_load": (C.c_int, [cp, cp, sz, C.c_int, pp, cp, sz]),
         "leann_cuda_searcher_len": (sz, [vp]),
         "leann_cuda_searcher_id": (sz, [vp, C.c_uint64, cp, sz]),
@@ -399,4 +404,4 @@ def topk_merge_device(keys_in, dists_in, descending: bool = False):
 
 
 from . import text  # noqa: E402,F401
-from .text import Bm25Scorer, MetadataFilter, IndexSearcher, SearchOptions, SearchResult, hybrid_rerank, tokenize  # noqa: E402,F401
+from .text import Bm25Scorer, MetadataFilter, MetadataColumns, IndexSearcher, SearchOptions, SearchResult, hybrid_rerank, tokenize  # noqa: E402,F401

@@ -424,8 +424,8 @@ int compare_values(const Json& a, const Json& b) {  // filter.rs:402-418
     if (a.kind == Json::Str && b.kind == Json::Str) { int c = a.str.compare(b.str); return c < 0 ? -1 : (c > 0 ? 1 : 0); }
     return 0;
 }
-bool cond_matches(const FilterNode& c, const Json& md) {  // filter.rs:329-373
-    const Json* fv = nested(md, c.field);
+// filter.rs:329-373 on an already resolved field value (nullptr = field missing)
+bool cond_on_value(const FilterNode& c, const Json* fv) {
     auto pat = [&]() -> const std::string& { static const std::string empty; return c.value.kind == Json::Str ? c.value.str : empty; };
     switch (c.op) {
         case FilterOp::Exists: return fv != nullptr;
@@ -453,6 +453,7 @@ bool cond_matches(const FilterNode& c, const Json& md) {  // filter.rs:329-373
     }
     return false;
 }
+bool cond_matches(const FilterNode& c, const Json& md) { return cond_on_value(c, nested(md, c.field)); }
 const char* op_name(FilterOp op) {
     switch (op) {
         case FilterOp::Eq: return "eq"; case FilterOp::Ne: return "ne"; case FilterOp::Gt: return "gt";
@@ -526,6 +527,101 @@ std::string filter_describe(const FilterNode& f) {
     for (size_t i = 0; i < f.children.size(); ++i) { if (i) o += ','; o += filter_describe(f.children[i]); }
     o += "]}";
     return o;
+}
+
+// ---- MetaColumns ---------------------------------------------------------------------------------------------
+void MetaColumns::resize(size_t rows) {
+    n = rows;
+    for (auto& kv : cols) {
+        kv.second.kind.resize(n, MetaColumn::Missing);
+        kv.second.sid.resize(n, 0);
+        if (!kv.second.num.empty()) kv.second.num.resize(n, 0.0);
+    }
+}
+
+namespace {
+void put_value(MetaColumns& mc, const std::string& path, size_t row, const Json& v) {
+    MetaColumn& c = mc.cols[path];
+    if (c.kind.size() < mc.n) { c.kind.resize(mc.n, MetaColumn::Missing); c.sid.resize(mc.n, 0); }
+    switch (v.kind) {
+        case Json::Null: c.kind[row] = MetaColumn::Null; break;
+        case Json::Bool: c.kind[row] = v.b ? MetaColumn::True : MetaColumn::False; break;
+        case Json::Num:
+            if (c.num.size() < mc.n) c.num.resize(mc.n, 0.0);
+            c.kind[row] = MetaColumn::Num; c.num[row] = v.num; break;
+        case Json::Str: {
+            auto it = c.dict_ids.find(v.str);
+            if (it == c.dict_ids.end()) { it = c.dict_ids.emplace(v.str, (uint32_t)c.dict.size()).first; c.dict.push_back(v.str); }
+            c.kind[row] = MetaColumn::Str; c.sid[row] = it->second; break;
+        }
+        default: c.kind[row] = MetaColumn::Other;
+    }
+}
+// Every path `nested` can resolve: keys joined by '.', keys that themselves contain '.' are unreachable
+// (filter.rs:376 splits the field on '.'), duplicate keys resolve as Json::get does.
+void flatten(MetaColumns& mc, const std::string& prefix, bool top, size_t row, const Json& obj) {
+    for (auto& kv : obj.obj) {
+        if (kv.first.find('.') != std::string::npos) continue;
+        const Json* v = obj.get(kv.first);
+        const std::string path = top ? kv.first : prefix + "." + kv.first;
+        put_value(mc, path, row, *v);
+        if (v->kind == Json::Obj) flatten(mc, path, false, row, *v);
+    }
+}
+}  // namespace
+
+void MetaColumns::add_row(size_t row, const Json& metadata) {
+    if (row >= n) resize(row + 1);
+    if (metadata.kind == Json::Obj) flatten(*this, "", true, row, metadata);
+}
+
+void MetaColumns::eval(const FilterNode& f, std::vector<uint64_t>& mask) const {
+    const size_t words = (n + 63) / 64;
+    if (f.kind != FilterNode::Condition) {
+        const bool is_and = f.kind == FilterNode::And;
+        mask.assign(words, is_and ? ~0ull : 0ull);
+        std::vector<uint64_t> m;
+        for (auto& ch : f.children) {
+            eval(ch, m);
+            for (size_t w = 0; w < words; ++w) mask[w] = is_and ? (mask[w] & m[w]) : (mask[w] | m[w]);
+        }
+        if (words && (n & 63)) mask[words - 1] &= (1ull << (n & 63)) - 1ull;
+        return;
+    }
+    mask.assign(words, 0ull);
+    // a field path with an empty segment in the middle ("a..b") or one the flattening never produced is missing everywhere
+    auto it = cols.find(f.field);
+    const bool when_missing = cond_on_value(f, nullptr);
+    if (it == cols.end()) {
+        if (when_missing) {
+            for (size_t w = 0; w < words; ++w) mask[w] = ~0ull;
+            if (words && (n & 63)) mask[words - 1] &= (1ull << (n & 63)) - 1ull;
+        }
+        return;
+    }
+    const MetaColumn& c = it->second;
+    // one evaluation per distinct non-numeric value, one per row for numbers
+    Json probe;
+    bool by_kind[7];
+    by_kind[MetaColumn::Missing] = when_missing;
+    probe.kind = Json::Null; by_kind[MetaColumn::Null] = cond_on_value(f, &probe);
+    probe.kind = Json::Bool; probe.b = false; by_kind[MetaColumn::False] = cond_on_value(f, &probe);
+    probe.b = true; by_kind[MetaColumn::True] = cond_on_value(f, &probe);
+    probe = Json(); probe.kind = Json::Arr; by_kind[MetaColumn::Other] = cond_on_value(f, &probe);   // arrays/objects: only kind matters
+    std::vector<uint8_t> str_ok(c.dict.size());
+    probe = Json(); probe.kind = Json::Str;
+    for (size_t i = 0; i < c.dict.size(); ++i) { probe.str = c.dict[i]; str_ok[i] = cond_on_value(f, &probe) ? 1 : 0; }
+    probe = Json(); probe.kind = Json::Num;
+    const size_t rows = std::min(n, c.kind.size());
+    for (size_t i = 0; i < rows; ++i) {
+        bool ok;
+        const uint8_t k = c.kind[i];
+        if (k == MetaColumn::Str) ok = str_ok[c.sid[i]] != 0;
+        else if (k == MetaColumn::Num) { probe.num = c.num[i]; ok = cond_on_value(f, &probe); }
+        else ok = by_kind[k];
+        if (ok) mask[i >> 6] |= 1ull << (i & 63);
+    }
+    if (when_missing) for (size_t i = rows; i < n; ++i) mask[i >> 6] |= 1ull << (i & 63);
 }
 
 }  // namespace leann

@@ -38,6 +38,26 @@ bool filter_parse(const std::string& s, FilterNode& out);             // Metadat
 bool filter_matches(const FilterNode& f, const Json& metadata);       // MetadataFilter::matches
 std::string filter_describe(const FilterNode& f);
 
+// ---- columnar side-car of the passages' metadata -------------------------------------------
+// Every dotted field path a filter can reach (filter.rs:376-388 splits on '.') becomes one typed column;
+// a parsed filter is then evaluated column-wise into an N-bit mask without touching JSON again. The per-row
+// semantics are exactly those of filter_matches (the condition code is shared).
+struct MetaColumn {
+    enum : uint8_t { Missing = 0, Null = 1, False = 2, True = 3, Num = 4, Str = 5, Other = 6 };
+    std::vector<uint8_t> kind;        // per row
+    std::vector<double> num;          // per row, valid when kind == Num (empty while the column holds no number)
+    std::vector<uint32_t> sid;        // per row, dictionary id, valid when kind == Str
+    std::vector<std::string> dict;
+    std::unordered_map<std::string, uint32_t> dict_ids;
+};
+struct MetaColumns {
+    size_t n = 0;
+    std::unordered_map<std::string, MetaColumn> cols;
+    void resize(size_t rows);
+    void add_row(size_t row, const Json& metadata);                 // metadata of passage `row` (any JSON value)
+    void eval(const FilterNode& f, std::vector<uint64_t>& mask) const;   // mask: ceil(n/64) words
+};
+
 // ---- index/bm25.rs:17-74: inverted (CSR) form of Bm25Scorer ------------------------------------------------
 struct Bm25Host {
     size_t num_docs = 0;

@@ -20,6 +20,9 @@ struct leann_cuda_filter {
     leann::FilterNode root;
     std::string expr;
 };
+struct leann_cuda_metacols {
+    leann::MetaColumns cols;
+};
 
 namespace {
 
@@ -167,6 +170,7 @@ struct leann_cuda_searcher {
     std::string jsonl;                     // whole <base>.passages.jsonl
     std::vector<uint64_t> line_off;        // per ordinal: byte offset of its passage line, or ~0 when missing
     std::vector<uint64_t> exists_mask;     // passages.get(id) succeeds
+    MetaColumns meta;                      // typed columns of every passage's metadata (built once at load)
     std::unordered_map<std::string, std::vector<uint64_t>> mask_cache;
     bool honor_complexity = false;
     std::mutex mu;
@@ -376,6 +380,36 @@ int leann_cuda_filter_mask(const leann_cuda_filter* f, const char* const* metada
 }
 void leann_cuda_filter_free(leann_cuda_filter* f) { delete f; }
 
+// ------------------------------------------------------------------ metadata columns (host only)
+int leann_cuda_metacols_build(const char* const* metadata_json, const size_t* bytes, size_t n, leann_cuda_metacols** out,
+                              char* err, size_t errlen) {
+    GUARD({
+        if (!out || (n && (!metadata_json || !bytes))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        std::unique_ptr<leann_cuda_metacols> mc(new leann_cuda_metacols());
+        mc->cols.resize(n);
+        Json md;
+        std::string e;
+        for (size_t i = 0; i < n; ++i) {
+            if (!metadata_json[i]) continue;   // passage without metadata: every field missing
+            if (!json_parse(metadata_json[i], bytes[i], md, e)) throw Error(LEANN_ERR_BAD_FORMAT, "metadata " + std::to_string(i) + " is not valid JSON: " + e);
+            mc->cols.add_row(i, md);
+        }
+        *out = mc.release();
+    });
+}
+int leann_cuda_metacols_mask(const leann_cuda_metacols* mc, const leann_cuda_filter* f, uint64_t* mask_bits, char* err, size_t errlen) {
+    GUARD({
+        if (!mc || !f || (mc->cols.n && !mask_bits)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        std::vector<uint64_t> m;
+        mc->cols.eval(f->root, m);
+        for (size_t w = 0; w < m.size(); ++w) mask_bits[w] = m[w];
+    });
+}
+size_t leann_cuda_metacols_len(const leann_cuda_metacols* mc) { return mc ? mc->cols.n : 0; }
+size_t leann_cuda_metacols_fields(const leann_cuda_metacols* mc) { return mc ? mc->cols.cols.size() : 0; }
+void leann_cuda_metacols_free(leann_cuda_metacols* mc) { delete mc; }
+
 // ------------------------------------------------------------------ IndexSearcher
 int leann_cuda_searcher_load(const char* base_path, const char* backend_name, size_t dims, int device,
                              leann_cuda_searcher** out, char* err, size_t errlen) {
@@ -428,9 +462,12 @@ int leann_cuda_searcher_load(const char* base_path, const char* backend_name, si
             if (it == off.end() || it->second >= s->jsonl.size()) continue;
             s->line_off[i] = it->second;
             Json p;
-            if (s->passage(i, p)) s->exists_mask[i >> 6] |= 1ull << (i & 63);
-            else s->line_off[i] = ~0ull;
+            if (s->passage(i, p)) {
+                s->exists_mask[i >> 6] |= 1ull << (i & 63);
+                if (const Json* md = p.get("metadata")) s->meta.add_row(i, *md);
+            } else s->line_off[i] = ~0ull;
         }
+        s->meta.resize(s->id_map.size());
         int rc = leann_cuda_open(base_path, backend, dims, LEANN_METRIC_DEFAULT, device, &s->backend, err, errlen);
         if (rc != LEANN_OK) throw Error(rc, err ? std::string(err) : std::string("backend open failed"));
         *out = s.release();
@@ -470,14 +507,10 @@ int leann_cuda_searcher_search(const leann_cuda_searcher* cs, const float* queri
                 if (it == s->mask_cache.end()) {
                     FilterNode root;
                     if (!filter_parse(filter_expr, root)) throw Error(LEANN_ERR_PARSE, std::string("cannot parse filter: ") + filter_expr);
-                    std::vector<uint64_t> m(words, 0);
-                    Json p;
-                    static const Json null_json;
-                    for (size_t i = 0; i < s->id_map.size(); ++i) {
-                        if (!s->passage(i, p)) continue;
-                        const Json* md = p.get("metadata");
-                        if (filter_matches(root, md ? *md : null_json)) m[i >> 6] |= 1ull << (i & 63);
-                    }
+                    // column-wise over the side-car (rows whose passage is missing are cleared by exists_mask below)
+                    std::vector<uint64_t> m;
+                    s->meta.eval(root, m);
+                    m.resize(words, 0);
                     it = s->mask_cache.emplace(filter_expr, std::move(m)).first;
                 }
                 use = &it->second;

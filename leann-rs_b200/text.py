@@ -186,6 +186,45 @@ class MetadataFilter:
             pass
 
 
+class MetadataColumns:
+    """Columnar side-car of the passages' metadata: built once from one JSON document per
+    passage (None = no metadata); `mask(filter)` evaluates a parsed MetadataFilter column-wise into the
+    N-bit mask, bit-identical to MetadataFilter.mask (filter.rs:319-439 row by row)."""
+
+    def __init__(self, metadata_docs: Sequence[Any]):
+        L = _core().lib()
+        n = len(metadata_docs)
+        enc = [None if m is None else (m if isinstance(m, bytes) else (m if isinstance(m, str) else json.dumps(m)).encode())
+               for m in metadata_docs]
+        arr = (C.c_char_p * max(n, 1))(*enc) if n else (C.c_char_p * 1)()
+        lens = (C.c_size_t * max(n, 1))(*[0 if b is None else len(b) for b in enc]) if n else (C.c_size_t * 1)()
+        h = C.c_void_p()
+        e = _err()
+        _check(L.leann_cuda_metacols_build(arr, lens, n, C.byref(h), e, 1024), e)
+        self._h, self.n = h, n
+
+    @property
+    def fields(self) -> int:
+        return int(_core().lib().leann_cuda_metacols_fields(self._h))
+
+    def mask(self, flt: "MetadataFilter") -> np.ndarray:
+        out = np.zeros((self.n + 63) // 64, dtype=np.uint64)
+        e = _err()
+        _check(_core().lib().leann_cuda_metacols_mask(self._h, flt._h, C.c_void_p(out.ctypes.data), e, 1024), e)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _core().lib().leann_cuda_metacols_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 @dataclass
 class SearchOptions:
     """index/searcher.rs:25-63."""

@@ -90,6 +90,65 @@ def test_filter_matches_oracle(expr):
         assert f.matches(md) == T.filter_matches(ref, md), (expr, md)
 
 
+def _bits(words, n):
+    return [bool((int(words[i // 64]) >> (i % 64)) & 1) for i in range(n)]
+
+
+_MD_COLS = _MD + [None, {"a": {"b": "x", "c": {"d": 1}}, "a.b": 7, "": {"": 3}}, {"a": 5, "lines": [1, 2], "source": {"k": 1}},
+                  {"lines": -3, "flag": False, "type": None}, {"type": "code", "lines": 5.0000000000000001, "x": "abc"},
+                  "not an object", 17, {"source": "main.rs", "lines": 9007199254740993}]
+
+
+def test_metadata_columns_golden(pkg):
+    """Column-wise evaluation over the side-car == MetadataFilter.matches row by row on the golden metadata."""
+    cols = pkg.MetadataColumns(GOLD["metadata"])
+    assert cols.fields >= 3
+    for c in GOLD["filters"]:
+        if c["tree"] is None:
+            continue
+        f = pkg.MetadataFilter.parse(c["expr"])
+        assert _bits(cols.mask(f), len(GOLD["metadata"])) == c["matches"], c["expr"]
+
+
+@settings(max_examples=400, deadline=None)
+@given(_expr())
+def test_metadata_columns_match_rowwise_and_oracle(expr):
+    import leann_rs_b200 as P
+    ref = T.parse_filter(expr)
+    f = P.MetadataFilter.parse(expr)
+    if ref is None:
+        assert f is None
+        return
+    cols = _cols_cache.setdefault("c", P.MetadataColumns([None if m is None else json.dumps(m) for m in _MD_COLS]))
+    got = _bits(cols.mask(f), len(_MD_COLS))
+    want = [T.filter_matches(ref, md) for md in _MD_COLS]     # passages without metadata are matched against null
+    assert got == want, (expr, got, want)
+    rows = _bits(f.mask(["null" if m is None else json.dumps(m) for m in _MD_COLS]), len(_MD_COLS))
+    assert got == rows, expr
+
+
+_cols_cache = {}
+
+
+def test_metadata_columns_paths_and_sizes(pkg):
+    f = pkg.MetadataFilter.parse
+    cols = pkg.MetadataColumns([None if m is None else json.dumps(m) for m in _MD_COLS])
+    n = len(_MD_COLS)
+    pick = lambda e: [i for i, b in enumerate(_bits(cols.mask(f(e)), n)) if b]
+    assert pick("a.c.d=1") == [5] and pick("a.b=x") == [5] and pick("a.b=5") == [0]
+    assert pick("a?") == [0, 5, 6] and pick("nosuch?") == [] and pick("nosuch!=1") == list(range(n))
+    assert pick("lines>=5") == [i for i, m in enumerate(_MD_COLS) if isinstance(m, dict) and "lines" in m and not (isinstance(m["lines"], (int, float)) and not isinstance(m["lines"], bool) and m["lines"] < 5)]
+    # ragged sizes around the word boundary, empty set
+    for k in (0, 1, 63, 64, 65, 130):
+        docs = [{"i": i, "s": "v%d" % (i % 7)} for i in range(k)]
+        c = pkg.MetadataColumns(docs)
+        w = c.mask(f("i>=10,s!=v3"))
+        assert len(w) == (k + 63) // 64
+        assert _bits(w, k) == [i >= 10 and i % 7 != 3 for i in range(k)]
+        if k % 64:
+            assert int(w[-1]) >> (k % 64) == 0       # no stray bits beyond n
+
+
 def test_text_path_fails_loudly_without_gpu(pkg):
     if pkg.device_count() > 0:
         pytest.skip("GPU present")
