@@ -159,6 +159,9 @@ int leann_cuda_bm25_score(const leann_cuda_bm25* bm25, const char* query, size_t
 int leann_cuda_bm25_search(const leann_cuda_bm25* bm25, const char* const* queries,
                            const size_t* query_bytes, size_t nq, size_t top_k, uint64_t* idx,
                            float* scores, uint32_t* counts, char* err, size_t errlen);
+/* Measurement of the last leann_cuda_bm25_search batch on this handle: postings covered by its query tokens
+ * (algorithmic bytes of K3 = postings * 8) and the device time of the query kernel (CUDA events). */
+int leann_cuda_bm25_last_batch(const leann_cuda_bm25* bm25, uint64_t* postings, float* kernel_ms);
 /* hybrid_rerank (bm25.rs:135-170) for one candidate list, evaluated on the device. bm25_scores is
  * the dense host vector of n_docs scores. Output has n entries, stable descending. */
 int leann_cuda_hybrid_rerank(const uint64_t* idx, const float* vec_scores, size_t n,

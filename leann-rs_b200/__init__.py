@@ -77,6 +77,7 @@ def lib():
         "leann_cuda_tokenize": (sz, [cp, sz, cp, sz]),
         "leann_cuda_bm25_score": (C.c_int, [vp, cp, sz, vp, cp, sz]),
         "leann_cuda_bm25_search": (C.c_int, [vp, cpp, szp, sz, sz, vp, vp, vp, cp, sz]),
+        "leann_cuda_bm25_last_batch": (C.c_int, [vp, u64p, f32p]),
         "leann_cuda_hybrid_rerank": (C.c_int, [vp, vp, sz, vp, sz, C.c_float, C.c_int, vp, vp, cp, sz]),
         "leann_cuda_bm25_free": (None, [vp]),
         "leann_cuda_hybrid_search": (C.c_int, [vp, vp, vp, cpp, szp, sz, sz, sz, C.c_int, C.c_float, vp, vp, vp, vp, cp, sz]),

@@ -22,8 +22,11 @@ namespace leann {
 namespace {
 
 constexpr int BM_THREADS = 256;
-constexpr int BM_CAP = 4096;      // candidate keys held in shared memory between prunes
-constexpr int BM_CHUNK = 1024;    // postings examined per block step (4 per thread)
+constexpr int BM_TILE = 8192;     // documents per shared-memory accumulator tile (32 KB of f32)
+constexpr int BM_CAP = 2048;      // candidate keys held in shared memory between prunes
+constexpr int BM_BOUNDS = 2048;   // entries of the (token, tile boundary) -> posting offset table (16 KB)
+constexpr int BM_SPARSE = 1024;   // tiles holding fewer postings are collected by re-walking them instead of a full scan
+constexpr size_t BM_SMEM = (size_t)BM_TILE * 4 + (size_t)BM_CAP * 8 + (size_t)BM_BOUNDS * 8;
 
 __device__ __forceinline__ uint32_t order_f32(float f) {
     uint32_t u = __float_as_uint(f);
@@ -42,7 +45,7 @@ __global__ void bm25_token_dense_kernel(Bm25Dev b, uint32_t term, float* __restr
     scores[doc] = __fadd_rn(scores[doc], b.post_score[p]);
 }
 
-__device__ void block_sort_4096(unsigned long long* keys) {
+__device__ void block_sort_cap(unsigned long long* keys) {
     const uint32_t n = BM_CAP;
     for (uint32_t size = 2; size <= n; size <<= 1)
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -57,25 +60,32 @@ __device__ void block_sort_4096(unsigned long long* keys) {
     __syncthreads();
 }
 
-// One CTA per query (persistent). acc: this CTA's dense f32 accumulator [n_docs], all zero on entry
-// and restored to zero on exit.
-__global__ void __launch_bounds__(BM_THREADS)
+// One CTA per query (persistent pool, dynamic scheduling). The dense score vector of the reference
+// (bm25.rs:77-106) is never materialised in HBM: documents are walked in tiles of BM_TILE, each tile's scores
+// are accumulated in shared memory token by token (postings are doc-ascending, so a tile is a contiguous slice
+// of every posting list; the slice boundaries come from one parallel binary search per query), then the tile is
+// scanned for positives, which feed the running top-K, the positive count and the min/max of hybrid_rerank.
+// Every posting is read once, coalesced; no global read-modify-write.
+__global__ void __launch_bounds__(BM_THREADS, 3)
 bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32_t* __restrict__ qtok_term,
-                  uint32_t nq, uint32_t K, float* __restrict__ acc_all, const uint64_t* __restrict__ cand_idx,
+                  uint32_t nq, uint32_t K, const uint64_t* __restrict__ cand_idx,
                   const uint32_t* __restrict__ cand_cnt, uint32_t fk, float* __restrict__ cand_bm,
                   uint64_t* __restrict__ top_idx, float* __restrict__ top_score, uint32_t* __restrict__ top_cnt,
                   float* __restrict__ bmax, float* __restrict__ bmin, uint32_t* __restrict__ qcounter) {
-    __shared__ unsigned long long buf[BM_CAP];
+    extern __shared__ __align__(16) unsigned char bm_smem[];
+    float* acc = reinterpret_cast<float*>(bm_smem);                                                  // [BM_TILE], zero between tiles
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(bm_smem + (size_t)BM_TILE * 4);   // [BM_CAP]
+    unsigned long long* bounds = buf + BM_CAP;                                                         // [T][S + 1] absolute posting offsets
     __shared__ uint32_t s_cnt, s_q, s_pos, s_minbits;
     __shared__ unsigned long long s_thr;
-    float* acc = acc_all + (size_t)blockIdx.x * b.n_docs;
     const int tid = threadIdx.x;
+    for (int i = tid; i < BM_TILE; i += BM_THREADS) acc[i] = 0.0f;
 
     auto prune = [&]() {  // all threads; keeps the K best keys and tightens the threshold
         __syncthreads();
         uint32_t c = s_cnt;
         for (uint32_t i = c + tid; i < BM_CAP; i += BM_THREADS) buf[i] = ~0ull;
-        block_sort_4096(buf);
+        block_sort_cap(buf);
         if (tid == 0) {
             uint32_t keep = c < K ? c : K;
             s_cnt = keep;
@@ -83,68 +93,113 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
         }
         __syncthreads();
     };
+    uint32_t my_pos = 0, my_min = 0xFFFFFFFFu;
+    auto collect = [&](uint32_t doc, float v, unsigned long long thr) {   // v != 0
+        if (v > 0.0f) {   // bm25.rs:115
+            my_pos++;
+            uint32_t o = order_f32(v);
+            my_min = o < my_min ? o : my_min;
+            unsigned long long key = ((unsigned long long)(~o) << 32) | doc;
+            if (key <= thr) buf[atomicAdd(&s_cnt, 1u)] = key;
+        }
+    };
 
     for (;;) {
-        if (tid == 0) s_q = atomicAdd(qcounter, 1u);
+        __syncthreads();
+        if (tid == 0) { s_q = atomicAdd(qcounter, 1u); s_cnt = 0; s_thr = ~0ull; s_pos = 0; s_minbits = 0xFFFFFFFFu; }
         __syncthreads();
         const uint32_t q = s_q;
         if (q >= nq) break;
-        const uint64_t t0 = qtok_off[q], t1 = qtok_off[q + 1];
-        // ---- pass 1: accumulate, tokens in query order (duplicates counted again, bm25.rs:81) ----
-        for (uint64_t t = t0; t < t1; ++t) {
-            const uint32_t term = qtok_term[t];
-            const uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
-            // postings are doc-ascending and distinct inside a term: plain read-modify-write, 4 in flight per thread
-            uint64_t p = p0 + tid;
-            for (; p + 3 * BM_THREADS < p1; p += 4 * BM_THREADS) {
-                uint32_t d0 = b.post_doc[p], d1 = b.post_doc[p + BM_THREADS], d2 = b.post_doc[p + 2 * BM_THREADS], d3 = b.post_doc[p + 3 * BM_THREADS];
-                float s0 = b.post_score[p], s1 = b.post_score[p + BM_THREADS], s2 = b.post_score[p + 2 * BM_THREADS], s3 = b.post_score[p + 3 * BM_THREADS];
-                float a0 = acc[d0], a1 = acc[d1], a2 = acc[d2], a3 = acc[d3];
-                acc[d0] = __fadd_rn(a0, s0); acc[d1] = __fadd_rn(a1, s1); acc[d2] = __fadd_rn(a2, s2); acc[d3] = __fadd_rn(a3, s3);
-            }
-            for (; p < p1; p += BM_THREADS) {
-                uint32_t doc = b.post_doc[p];
-                acc[doc] = __fadd_rn(acc[doc], b.post_score[p]);
+        const uint64_t t0 = qtok_off[q];
+        const uint32_t T = (uint32_t)(qtok_off[q + 1] - t0);     // <= BM_BOUNDS / 2 (checked by the host)
+        const uint32_t nc = cand_idx ? cand_cnt[q] : 0u;
+        for (uint32_t j = tid; j < nc; j += BM_THREADS) cand_bm[(size_t)q * fk + j] = 0.0f;   // bm25.rs:160 unwrap_or(0.0) / untouched tiles
+        my_pos = 0; my_min = 0xFFFFFFFFu;
+        const uint32_t n_tiles = (b.n_docs + BM_TILE - 1) / BM_TILE;
+        const uint32_t S = T ? max(1u, (uint32_t)BM_BOUNDS / T - 1u) : n_tiles;   // tiles per boundary table
+        for (uint32_t sb0 = 0; sb0 < n_tiles && T; sb0 += S) {
+            const uint32_t sbt = min(S, n_tiles - sb0);
+            // ---- slice boundaries: lower_bound(first doc of tile) in every token's posting list ----
+            __syncthreads();
+            for (uint32_t e = tid; e < T * (sbt + 1); e += BM_THREADS) {
+                const uint32_t t = e / (sbt + 1), i = e % (sbt + 1);
+                const uint32_t term = qtok_term[t0 + t];
+                uint64_t lo = b.term_off[term], hi = b.term_off[term + 1];
+                const uint64_t target = (uint64_t)(sb0 + i) * BM_TILE;
+                if (target >= b.n_docs) lo = hi;
+                while (lo < hi) {
+                    uint64_t mid = (lo + hi) >> 1;
+                    if (b.post_doc[mid] < target) lo = mid + 1; else hi = mid;
+                }
+                bounds[e] = lo;
             }
             __syncthreads();
-        }
-        // ---- BM25 score of the vector candidates (bm25_scores.get(idx).unwrap_or(0.0), bm25.rs:160) ----
-        if (cand_idx) {
-            uint32_t nc = cand_cnt[q];
-            for (uint32_t j = tid; j < nc; j += BM_THREADS) {
-                uint64_t idx = cand_idx[(size_t)q * fk + j];
-                cand_bm[(size_t)q * fk + j] = idx < b.n_docs ? acc[idx] : 0.0f;
-            }
-        }
-        if (tid == 0) { s_cnt = 0; s_thr = ~0ull; s_pos = 0; s_minbits = 0xFFFFFFFFu; }
-        __syncthreads();
-        // ---- pass 2: collect positives (score > 0, bm25.rs:115), zero the accumulator ----
-        uint32_t my_pos = 0, my_min = 0xFFFFFFFFu;
-        for (uint64_t t = t0; t < t1; ++t) {
-            const uint32_t term = qtok_term[t];
-            const uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
-            for (uint64_t base = p0; base < p1; base += BM_CHUNK) {
-                if (s_cnt > BM_CAP - BM_CHUNK) prune();
-                const unsigned long long thr = s_thr;
+            for (uint32_t tile = 0; tile < sbt; ++tile) {
+                const uint32_t base = (sb0 + tile) * BM_TILE;
+                // ---- accumulate, tokens in query order (duplicates counted again, bm25.rs:81) ----
+                uint64_t in_tile = 0;
+                for (uint32_t t = 0; t < T; ++t) {
+                    const uint64_t lo = bounds[t * (sbt + 1) + tile], hi = bounds[t * (sbt + 1) + tile + 1];
+                    if (lo >= hi) continue;
+                    in_tile += hi - lo;
+                    // documents inside one token are distinct: plain shared-memory read-modify-write, 8 postings in flight per thread
+                    uint64_t p = lo + tid;
+                    for (; p + 7 * BM_THREADS < hi; p += 8 * BM_THREADS) {
+                        uint32_t d[8]; float sc[8];
 #pragma unroll
-                for (int i = 0; i < BM_CHUNK / BM_THREADS; ++i) {
-                    uint64_t p = base + tid + (uint64_t)i * BM_THREADS;
-                    if (p < p1) {
-                        uint32_t doc = b.post_doc[p];
-                        float v = acc[doc];
-                        if (v != 0.0f) {
-                            acc[doc] = 0.0f;
-                            if (v > 0.0f) {
-                                my_pos++;
-                                uint32_t o = order_f32(v);
-                                my_min = o < my_min ? o : my_min;
-                                unsigned long long key = ((unsigned long long)(~o) << 32) | doc;
-                                if (key <= thr) buf[atomicAdd(&s_cnt, 1u)] = key;
-                            }
-                        }
+                        for (int u = 0; u < 8; ++u) { d[u] = __ldg(b.post_doc + p + u * BM_THREADS); sc[u] = __ldg(b.post_score + p + u * BM_THREADS); }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc[d[u] - base] = __fadd_rn(acc[d[u] - base], sc[u]);
                     }
+                    for (; p < hi; p += BM_THREADS) {
+                        const uint32_t doc = __ldg(b.post_doc + p);
+                        acc[doc - base] = __fadd_rn(acc[doc - base], __ldg(b.post_score + p));
+                    }
+                    __syncthreads();
+                }
+                if (in_tile == 0) continue;
+                // ---- BM25 score of the vector candidates that live in this tile (bm25.rs:160) ----
+                for (uint32_t j = tid; j < nc; j += BM_THREADS) {
+                    const uint64_t idx = cand_idx[(size_t)q * fk + j];
+                    if (idx >= base && idx < (uint64_t)base + BM_TILE && idx < b.n_docs) cand_bm[(size_t)q * fk + j] = acc[idx - base];
                 }
                 __syncthreads();
+                if (in_tile < (uint64_t)BM_SPARSE) {
+                    // ---- few postings: collect by re-walking them (the first visit of a document takes and clears its score) ----
+                    for (uint32_t t = 0; t < T; ++t) {
+                        const uint64_t lo = bounds[t * (sbt + 1) + tile], hi = bounds[t * (sbt + 1) + tile + 1];
+                        if (lo >= hi) continue;
+                        const uint32_t c = s_cnt;
+                        __syncthreads();   // everyone has read the count before anyone appends: the decision is uniform
+                        if (c > BM_CAP - BM_SPARSE) prune();
+                        const unsigned long long thr = s_thr;
+                        for (uint64_t p = lo + tid; p < hi; p += BM_THREADS) {
+                            const uint32_t doc = __ldg(b.post_doc + p);
+                            const float v = acc[doc - base];
+                            if (v != 0.0f) { acc[doc - base] = 0.0f; collect(doc, v, thr); }
+                        }
+                        __syncthreads();
+                    }
+                } else {
+                    // ---- scan the tile: collect positives, clear the accumulator ----
+                    for (int it = 0; it < BM_TILE / (4 * BM_THREADS); ++it) {
+                        const uint32_t c = s_cnt;
+                        __syncthreads();   // everyone has read the count before anyone appends: the decision is uniform
+                        if (c > BM_CAP - 4 * BM_THREADS) prune();
+                        const unsigned long long thr = s_thr;
+                        const int i4 = it * BM_THREADS + tid;
+                        float4 v = reinterpret_cast<float4*>(acc)[i4];
+                        if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
+                            reinterpret_cast<float4*>(acc)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const uint32_t doc = base + (uint32_t)i4 * 4u;
+                            if (v.x != 0.0f) collect(doc, v.x, thr);
+                            if (v.y != 0.0f) collect(doc + 1, v.y, thr);
+                            if (v.z != 0.0f) collect(doc + 2, v.z, thr);
+                            if (v.w != 0.0f) collect(doc + 3, v.w, thr);
+                        }
+                        __syncthreads();
+                    }
+                }
             }
         }
         atomicAdd(&s_pos, my_pos);
@@ -171,7 +226,6 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
             bmax[q] = mx;
             bmin[q] = mn;
         }
-        __syncthreads();
     }
 }
 
@@ -313,15 +367,22 @@ void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* 
 }
 
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
-                       float* acc_all, int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
+                       int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
                        float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,
                        uint32_t* qcounter, cudaStream_t s) {
     if (K == 0 || K > 1024) throw Error(LEANN_ERR_INVALID_ARG, "bm25: top_k must be in 1..1024");
+    static bool attr = false;
+    if (!attr) {
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(bm25_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BM_SMEM));
+        attr = true;
+    }
     LEANN_CUDA_CHECK(cudaMemsetAsync(qcounter, 0, 4, s));
-    bm25_query_kernel<<<n_ctas, BM_THREADS, 0, s>>>(b, qtok_off, qtok_term, nq, K, acc_all, cand_idx, cand_cnt, fk, cand_bm,
-                                                     top_idx, top_score, top_cnt, bmax, bmin, qcounter);
+    bm25_query_kernel<<<n_ctas, BM_THREADS, BM_SMEM, s>>>(b, qtok_off, qtok_term, nq, K, cand_idx, cand_cnt, fk, cand_bm,
+                                                          top_idx, top_score, top_cnt, bmax, bmin, qcounter);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
+
+size_t bm25_max_query_tokens() { return BM_BOUNDS / 2; }
 
 void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, uint32_t fk, const float* cand_bm,
                         const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, uint32_t bm_k,

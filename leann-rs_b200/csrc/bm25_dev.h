@@ -14,8 +14,9 @@ struct Bm25Dev {
 
 void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
                        cudaStream_t s);
+size_t bm25_max_query_tokens();   // longest query (known tokens, duplicates included) the query kernel takes
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
-                       float* acc_all, int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
+                       int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
                        float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,
                        uint32_t* qcounter, cudaStream_t s);
 void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, uint32_t fk, const float* cand_bm,
@@ -40,9 +41,13 @@ struct leann_cuda_bm25 {
     float* d_post_score = nullptr;
     // per-handle workspace
     mutable std::mutex mu;
-    mutable float* d_acc = nullptr;   // [n_ctas][n_docs], zero between calls
+    mutable float* d_acc = nullptr;   // [n_docs] dense score vector of score_query, zero between calls
     mutable int n_ctas = 0;
     mutable uint32_t* d_qcounter = nullptr;
     mutable cudaStream_t stream = nullptr;
+    // measurement of the last leann_cuda_bm25_search batch: postings its tokens cover, device time of the query kernel
+    mutable cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    mutable uint64_t last_postings = 0;
+    mutable float last_kernel_ms = 0.0f;
     leann::Bm25Dev view() const { return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_score}; }
 };

@@ -68,16 +68,12 @@ void bm25_ensure_ws(const leann_cuda_bm25* b, size_t nq) {
     if (!b->d_qcounter) LEANN_CUDA_CHECK(cudaMalloc(&b->d_qcounter, 16));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
-    int want = (int)std::min<size_t>((size_t)sms * 2, std::max<size_t>(nq, 1));
-    // bound the accumulators to 8 GB
+    (void)nq;
+    b->n_ctas = sms * 3;   // persistent pool of the query kernel: 3 CTAs of 64 KB shared memory per SM
+    if (b->d_acc) return;
     size_t per = std::max<size_t>(b->host.num_docs, 1) * 4;
-    while (want > 1 && (size_t)want * per > ((size_t)8 << 30)) want /= 2;
-    if (b->n_ctas >= want) return;
-    if (b->d_acc) cudaFree(b->d_acc);
-    b->d_acc = nullptr; b->n_ctas = 0;
-    LEANN_CUDA_CHECK(cudaMalloc(&b->d_acc, (size_t)want * per));
-    LEANN_CUDA_CHECK(cudaMemset(b->d_acc, 0, (size_t)want * per));
-    b->n_ctas = want;
+    LEANN_CUDA_CHECK(cudaMalloc(&b->d_acc, per));
+    LEANN_CUDA_CHECK(cudaMemset(b->d_acc, 0, per));
 }
 
 // query texts -> CSR of known term ids (unknown terms contribute nothing: bm25.rs:82-85)
@@ -94,6 +90,8 @@ void tokenize_queries(const leann_cuda_bm25* b, const char* const* texts, const 
                 if (it != b->host.dict.end()) terms.push_back(it->second);
             }
         }
+        if (terms.size() - off[i] > bm25_max_query_tokens())
+            throw Error(LEANN_ERR_INVALID_ARG, "bm25: query " + std::to_string(i) + " has more than " + std::to_string(bm25_max_query_tokens()) + " indexed tokens");
         off[i + 1] = terms.size();
     }
 }
@@ -134,7 +132,7 @@ void hybrid_search_impl(const leann_cuda_index* ix, const leann_cuda_bm25* bm, c
         LEANN_CUDA_CHECK(cudaMemcpyAsync(qo->p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
         if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt->p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
         LEANN_CUDA_CHECK(cudaStreamSynchronize(s));  // off/terms are stack-owned host vectors
-        launch_bm25_query(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, (uint32_t)fk, bm->d_acc, bm->n_ctas,
+        launch_bm25_query(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, (uint32_t)fk, bm->n_ctas,
                           vk.as<uint64_t>(), vc.as<uint32_t>(), (uint32_t)fk, cb->as<float>(), bi->as<uint64_t>(), bs->as<float>(),
                           bc->as<uint32_t>(), bx->as<float>(), bn->as<float>(), bm->d_qcounter, s);
     }
@@ -231,6 +229,7 @@ void leann_cuda_bm25_free(leann_cuda_bm25* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_term_off); cudaFree(b->d_post_doc); cudaFree(b->d_post_score);
     cudaFree(b->d_acc); cudaFree(b->d_qcounter);
+    if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
     if (b->stream) cudaStreamDestroy(b->stream);
     cudaGetLastError();
     if (prev >= 0) cudaSetDevice(prev);
@@ -279,14 +278,26 @@ int leann_cuda_bm25_search(const leann_cuda_bm25* b, const char* const* queries,
         DevBuf qo(off.size() * 8), qt(terms.size() * 4), bi(nq * top_k * 8), bs(nq * top_k * 4), bc(nq * 4), bx(nq * 4), bn(nq * 4);
         LEANN_CUDA_CHECK(cudaMemcpyAsync(qo.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
         if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt.p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
-        launch_bm25_query(b->view(), qo.as<uint64_t>(), qt.as<uint32_t>(), (uint32_t)nq, (uint32_t)top_k, b->d_acc, b->n_ctas,
+        if (!b->ev0) { LEANN_CUDA_CHECK(cudaEventCreate(&b->ev0)); LEANN_CUDA_CHECK(cudaEventCreate(&b->ev1)); }
+        LEANN_CUDA_CHECK(cudaEventRecord(b->ev0, s));
+        launch_bm25_query(b->view(), qo.as<uint64_t>(), qt.as<uint32_t>(), (uint32_t)nq, (uint32_t)top_k, b->n_ctas,
                           nullptr, nullptr, 0, nullptr, bi.as<uint64_t>(), bs.as<float>(), bc.as<uint32_t>(), bx.as<float>(),
                           bn.as<float>(), b->d_qcounter, s);
+        LEANN_CUDA_CHECK(cudaEventRecord(b->ev1, s));
+        b->last_postings = 0;
+        for (uint32_t t : terms) b->last_postings += b->host.term_off[t + 1] - b->host.term_off[t];
         LEANN_CUDA_CHECK(cudaMemcpyAsync(idx, bi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
         LEANN_CUDA_CHECK(cudaMemcpyAsync(scores, bs.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
         if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, bc.p, nq * 4, cudaMemcpyDeviceToHost, s));
         LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
+        LEANN_CUDA_CHECK(cudaEventElapsedTime(&b->last_kernel_ms, b->ev0, b->ev1));
     });
+}
+int leann_cuda_bm25_last_batch(const leann_cuda_bm25* b, uint64_t* postings, float* kernel_ms) {
+    if (!b) return LEANN_ERR_INVALID_ARG;
+    if (postings) *postings = b->last_postings;
+    if (kernel_ms) *kernel_ms = b->last_kernel_ms;
+    return LEANN_OK;
 }
 
 int leann_cuda_hybrid_rerank(const uint64_t* idx, const float* vec_scores, size_t n, const float* bm25_scores,

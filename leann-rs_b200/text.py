@@ -100,6 +100,12 @@ class Bm25Scorer:
                                         C.c_void_p(cnt.ctypes.data), e, 1024), e)
         return idx, sc, cnt
 
+    def last_batch(self):
+        """(postings covered by the last search_batch's tokens, device ms of its query kernel)."""
+        n, ms = C.c_uint64(), C.c_float()
+        _core().lib().leann_cuda_bm25_last_batch(self._h, C.byref(n), C.byref(ms))
+        return int(n.value), float(ms.value)
+
     def close(self):
         if getattr(self, "_h", None):
             _core().lib().leann_cuda_bm25_free(self._h)

@@ -73,6 +73,17 @@ def test_bm25_medium_corpus_bits_and_topk(pkg):
     big = sc.search("t0", 1000)
     want = ref.search("t0", 1000, fast=True)
     assert [d for d, _ in big] == [d for d, _ in want]
+    # long queries (duplicates included): the tile-boundary table is rebuilt every few tiles; every document scores
+    rng = np.random.default_rng(11)
+    longq = [" ".join(f"t{int(i)}" for i in rng.integers(0, 3000, size=m)) for m in (300, 700, 1024)]
+    idx, scores, cnt = sc.search_batch(longq, 100)
+    for i, q in enumerate(longq):
+        want = ref.search(q, 100, fast=True)
+        assert int(cnt[i]) == len(want) and idx[i, :len(want)].tolist() == [d for d, _ in want], len(q)
+        assert scores[i, :len(want)].view(np.uint32).tolist() == [int(np.float32(s).view(np.uint32)) for _, s in want]
+    with pytest.raises(pkg.LeannCudaError) as e:
+        sc.search(" ".join(["t1"] * 1025), 5)
+    assert "indexed tokens" in e.value.message
 
 
 def _fixture_dir(tmp_path, orc, n=3000, d=64, missing=(), with_ids=True, seed=13):
