@@ -36,13 +36,59 @@ struct DevGuard {
     ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Scoped device scratch of the synchronous host-pointer entry points. Blocks come from a small per-device cache
+// (power-of-two buckets, at most 1 GiB kept): steady-state calls make no cudaMalloc / cudaFree, whose implicit
+// device synchronisation and page (un)mapping showed up as 100+ ms outliers in batch latency.
+class ScratchCache {
+public:
+    static ScratchCache& get() { static ScratchCache c; return c; }
+    void* take(size_t& bytes) {
+        size_t b = 256;
+        while (b < bytes) b <<= 1;
+        bytes = b;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            auto& fl = free_[key(dev, b)];
+            if (!fl.empty()) { void* p = fl.back(); fl.pop_back(); cached_ -= b; return p; }
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) { trim(); LEANN_CUDA_CHECK(cudaMalloc(&p, b)); }
+        return p;
+    }
+    void give(void* p, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (cached_ + bytes <= ((size_t)1 << 30)) { free_[key(dev, bytes)].push_back(p); cached_ += bytes; return; }
+        }
+        cudaFree(p);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& kv : free_) for (void* p : kv.second) cudaFree(p);
+        free_.clear();
+        cached_ = 0;
+        cudaGetLastError();
+    }
+private:
+    static uint64_t key(int dev, size_t b) { return ((uint64_t)dev << 56) | (uint64_t)b; }
+    std::mutex mu_;
+    std::unordered_map<uint64_t, std::vector<void*>> free_;
+    size_t cached_ = 0;
+};
+
 struct DevBuf {  // scoped device allocation
     void* p = nullptr;
+    size_t bytes = 0;
     DevBuf() = default;
-    explicit DevBuf(size_t bytes) { LEANN_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16))); }
+    explicit DevBuf(size_t n) : bytes(std::max<size_t>(n, 16)) { p = ScratchCache::get().take(bytes); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) ScratchCache::get().give(p, bytes); }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
