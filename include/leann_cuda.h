@@ -177,6 +177,33 @@ void leann_cuda_bm25_free(leann_cuda_bm25* bm25);
  * ef: the backend `complexity` (pass 64 for HNSW to reproduce hnsw.rs:49,83).
  * Outputs nq x top_k (host): passage ordinals and the score searcher.rs returns (distance, or fused
  * score when hybrid). */
+/* Document-range shards of the BM25 / hybrid path. Every shard indexes its own documents with the
+ * corpus-wide N, total token count and per-term document frequency, so idf (bm25.rs:88), avg_doc_len (:61-65) and
+ * each posting's score are bit-identical to the unsharded index. The statistics travel between ranks as opaque
+ * blobs (all_gather of bytes): shard_stats on every rank -> stats_merge of all blobs -> build_sharded.
+ * Sizing call: out == NULL returns the byte count in *needed. */
+int leann_cuda_bm25_shard_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, unsigned char* out,
+                                size_t cap, size_t* needed, char* err, size_t errlen);
+int leann_cuda_bm25_stats_merge(const unsigned char* const* blobs, const size_t* blob_bytes, size_t n_blobs,
+                                unsigned char* out, size_t cap, size_t* needed, char* err, size_t errlen);
+int leann_cuda_bm25_build_sharded(const char* const* docs, const size_t* doc_bytes, size_t n_docs,
+                                  const unsigned char* global_stats, size_t stats_bytes, int device,
+                                  leann_cuda_bm25** out, char* err, size_t errlen);
+/* One shard's part of search_with_options' hybrid step (searcher.rs:146-167) for a batch: BM25 top-k of the shard
+ * (ids + doc_offset), BM25 score of the global vector candidates the shard owns (0 elsewhere), min / max of the
+ * shard's dense score vector (bm25.rs:152-153). Reduce over shards: top lists -> leann_cuda_topk_merge_device
+ * (descending), cand_bm -> sum, bmax -> max, bmin -> min; then leann_cuda_hybrid_fuse. cand_idx may be NULL. */
+int leann_cuda_bm25_search_shard(const leann_cuda_bm25* bm25, const char* const* queries, const size_t* query_bytes,
+                                 size_t nq, size_t top_k, uint64_t doc_offset, const uint64_t* cand_idx,
+                                 const uint32_t* cand_cnt, size_t fk, uint64_t* top_idx, float* top_score,
+                                 uint32_t* top_cnt, float* cand_bm, float* bmax, float* bmin, char* err, size_t errlen);
+/* Batched hybrid_rerank (bm25.rs:135-170) + BM25-only additions (searcher.rs:156-165) + post-filter walk
+ * (searcher.rs:174-207) over gathered inputs; host pointers. vkeys/vdists: nq x fk vector results; bm_*: nq x bm_k. */
+int leann_cuda_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, size_t nq, size_t fk,
+                           const float* cand_bm, const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt,
+                           size_t bm_k, const float* bmax, const float* bmin, int hybrid, float alpha,
+                           const uint64_t* mask, size_t mask_bits, size_t top_k, int device, uint64_t* out_idx,
+                           float* out_score, uint32_t* out_cnt, char* err, size_t errlen);
 int leann_cuda_hybrid_search(const leann_cuda_index* index, const leann_cuda_bm25* bm25,
                              const float* queries, const char* const* query_texts,
                              const size_t* query_text_bytes, size_t nq, size_t top_k, size_t ef,

@@ -77,6 +77,12 @@ def lib():
         "leann_cuda_tokenize": (sz, [cp, sz, cp, sz]),
         "leann_cuda_bm25_score": (C.c_int, [vp, cp, sz, vp, cp, sz]),
         "leann_cuda_bm25_search": (C.c_int, [vp, cpp, szp, sz, sz, vp, vp, vp, cp, sz]),
+        "leann_cuda_bm25_shard_stats": (C.c_int, [cpp, szp, sz, vp, sz, szp, cp, sz]),
+        "leann_cuda_bm25_stats_merge": (C.c_int, [vp, szp, sz, vp, sz, szp, cp, sz]),
+        "leann_cuda_bm25_build_sharded": (C.c_int, [cpp, szp, sz, vp, sz, C.c_int, pp, cp, sz]),
+        "leann_cuda_bm25_search_shard": (C.c_int, [vp, cpp, szp, sz, sz, C.c_uint64, vp, vp, sz, vp, vp, vp, vp, vp, vp, cp, sz]),
+        "leann_cuda_hybrid_fuse": (C.c_int, [vp, vp, vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, C.c_int, C.c_float, vp, sz, sz, C.c_int,
+                                             vp, vp, vp, cp, sz]),
         "leann_cuda_bm25_last_batch": (C.c_int, [vp, u64p, f32p]),
         "leann_cuda_hybrid_rerank": (C.c_int, [vp, vp, sz, vp, sz, C.c_float, C.c_int, vp, vp, cp, sz]),
         "leann_cuda_bm25_free": (None, [vp]),
@@ -405,4 +411,4 @@ def topk_merge_device(keys_in, dists_in, descending: bool = False):
 
 
 from . import text  # noqa: E402,F401
-from .text import Bm25Scorer, MetadataFilter, MetadataColumns, IndexSearcher, SearchOptions, SearchResult, hybrid_rerank, tokenize  # noqa: E402,F401
+from .text import Bm25Scorer, MetadataFilter, MetadataColumns, IndexSearcher, SearchOptions, SearchResult, hybrid_rerank, hybrid_fuse, tokenize  # noqa: E402,F401

@@ -195,7 +195,60 @@ void tokenize(const char* text, size_t n, std::vector<std::string>& out) {
 }
 
 // ================================= BM25 build =================================
-void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& o) {
+void bm25_local_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25GlobalStats& g) {
+    g = Bm25GlobalStats();
+    g.num_docs = n_docs;
+    std::vector<std::string> toks;
+    for (size_t d = 0; d < n_docs; ++d) {
+        tokenize(docs[d], doc_bytes[d], toks);
+        g.total_tokens += toks.size();
+        std::sort(toks.begin(), toks.end());
+        for (size_t i = 0; i < toks.size(); ++i)
+            if (i == 0 || toks[i] != toks[i - 1]) g.df[toks[i]]++;
+    }
+}
+void Bm25GlobalStats::merge(const Bm25GlobalStats& o) {
+    num_docs += o.num_docs;
+    total_tokens += o.total_tokens;
+    for (auto& kv : o.df) df[kv.first] += kv.second;
+}
+std::string Bm25GlobalStats::encode() const {
+    std::string out;
+    auto put64 = [&](uint64_t v) { out.append(reinterpret_cast<const char*>(&v), 8); };
+    put64(0x314D42534E41454Cull);  // "LEANSBM1"
+    put64(num_docs); put64(total_tokens); put64(df.size());
+    std::vector<const std::pair<const std::string, uint64_t>*> order;
+    order.reserve(df.size());
+    for (auto& kv : df) order.push_back(&kv);
+    std::sort(order.begin(), order.end(), [](auto* a, auto* b) { return a->first < b->first; });   // deterministic bytes
+    for (auto* kv : order) {
+        uint32_t len = (uint32_t)kv->first.size();
+        out.append(reinterpret_cast<const char*>(&len), 4);
+        out.append(kv->first);
+        put64(kv->second);
+    }
+    return out;
+}
+bool Bm25GlobalStats::decode(const unsigned char* p, size_t n) {
+    *this = Bm25GlobalStats();
+    size_t o = 0;
+    auto get64 = [&](uint64_t& v) { if (o + 8 > n) return false; memcpy(&v, p + o, 8); o += 8; return true; };
+    uint64_t magic = 0, nt = 0;
+    if (!get64(magic) || magic != 0x314D42534E41454Cull || !get64(num_docs) || !get64(total_tokens) || !get64(nt)) return false;
+    for (uint64_t i = 0; i < nt; ++i) {
+        uint32_t len = 0;
+        if (o + 4 > n) return false;
+        memcpy(&len, p + o, 4); o += 4;
+        if (o + len > n) return false;
+        std::string term(reinterpret_cast<const char*>(p + o), len); o += len;
+        uint64_t v = 0;
+        if (!get64(v)) return false;
+        df[term] += v;
+    }
+    return o == n;
+}
+
+void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& o, const Bm25GlobalStats* glob) {
     const float K1 = 1.2f, B = 0.75f;
     (void)K1;
     o = Bm25Host();
@@ -228,8 +281,16 @@ void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_
         }
         doc_off[d + 1] = doc_terms.size();
     }
-    // bm25.rs:61-65
-    o.avg_doc_len = n_docs > 0 ? (float)o.total_tokens / (float)n_docs : 1.0f;
+    // bm25.rs:61-65 (over the whole corpus when this is one document-range shard of it)
+    const uint64_t N_all = glob ? glob->num_docs : (uint64_t)n_docs;
+    const uint64_t tokens_all = glob ? glob->total_tokens : o.total_tokens;
+    o.avg_doc_len = N_all > 0 ? (float)tokens_all / (float)N_all : 1.0f;
+    std::vector<uint64_t> df_all(df.begin(), df.end());
+    if (glob)
+        for (auto& kv : o.dict) {
+            auto it = glob->df.find(kv.first);
+            if (it != glob->df.end()) df_all[kv.second] = it->second;
+        }
     size_t nt = df.size();
     o.term_off.assign(nt + 1, 0);
     for (size_t t = 0; t < nt; ++t) o.term_off[t + 1] = o.term_off[t] + df[t];
@@ -244,9 +305,9 @@ void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_
         }
     // bm25.rs:88  idf = ((N - df + 0.5) / (df + 0.5) + 1.0).ln()   — all f32
     o.idf.resize(nt);
-    const float Nf = (float)n_docs;
+    const float Nf = (float)N_all;
     for (size_t t = 0; t < nt; ++t) {
-        float dff = (float)df[t];
+        float dff = (float)df_all[t];
         volatile float a = Nf - dff;
         volatile float num = a + 0.5f;
         volatile float den = dff + 0.5f;

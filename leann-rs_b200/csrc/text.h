@@ -72,6 +72,17 @@ struct Bm25Host {
     std::vector<float> norm;          // per doc: 1 - B + B * (len / avg), bm25.rs:97
     std::vector<uint32_t> doc_len;
 };
-void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& out);
+// Corpus-wide statistics of a document-range sharded corpus: N, total tokens and df per term are
+// global, so idf (bm25.rs:88), avg_doc_len (:61-65) and every per-posting score equal the unsharded ones bit for bit.
+struct Bm25GlobalStats {
+    uint64_t num_docs = 0, total_tokens = 0;
+    std::unordered_map<std::string, uint64_t> df;
+    std::string encode() const;                          // blob exchanged between ranks
+    bool decode(const unsigned char* p, size_t n);
+    void merge(const Bm25GlobalStats& other);
+};
+void bm25_local_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25GlobalStats& out);
+void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& out,
+                     const Bm25GlobalStats* global = nullptr);
 
 }  // namespace leann

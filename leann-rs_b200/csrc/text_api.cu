@@ -250,6 +250,58 @@ int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size
         *out = b.release();
     });
 }
+// ---- document-range shards: global statistics exchanged as opaque blobs ----
+static int copy_blob(const std::string& blob, unsigned char* out, size_t cap, size_t* needed) {
+    if (needed) *needed = blob.size();
+    if (!out || cap < blob.size()) return out ? LEANN_ERR_INVALID_ARG : LEANN_OK;   // sizing call: out == NULL
+    memcpy(out, blob.data(), blob.size());
+    return LEANN_OK;
+}
+int leann_cuda_bm25_shard_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, unsigned char* out, size_t cap,
+                                size_t* needed, char* err, size_t errlen) {
+    int rc = LEANN_OK;
+    int g = leann::guard_impl(err, errlen, [&]() {
+        if (n_docs && (!docs || !doc_bytes)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        Bm25GlobalStats st;
+        bm25_local_stats(docs, doc_bytes, n_docs, st);
+        rc = copy_blob(st.encode(), out, cap, needed);
+        if (rc != LEANN_OK) throw Error(rc, "stats buffer too small");
+    });
+    return g;
+}
+int leann_cuda_bm25_stats_merge(const unsigned char* const* blobs, const size_t* blob_bytes, size_t n_blobs, unsigned char* out,
+                                size_t cap, size_t* needed, char* err, size_t errlen) {
+    GUARD({
+        if (n_blobs && (!blobs || !blob_bytes)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        Bm25GlobalStats all;
+        for (size_t i = 0; i < n_blobs; ++i) {
+            Bm25GlobalStats one;
+            if (!one.decode(blobs[i], blob_bytes[i])) throw Error(LEANN_ERR_BAD_FORMAT, "BM25 statistics blob " + std::to_string(i) + " is malformed");
+            all.merge(one);
+        }
+        int rc = copy_blob(all.encode(), out, cap, needed);
+        if (rc != LEANN_OK) throw Error(rc, "stats buffer too small");
+    });
+}
+int leann_cuda_bm25_build_sharded(const char* const* docs, const size_t* doc_bytes, size_t n_docs, const unsigned char* global_stats,
+                                  size_t stats_bytes, int device, leann_cuda_bm25** out, char* err, size_t errlen) {
+    GUARD({
+        if (!out || !global_stats || (n_docs && (!docs || !doc_bytes))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        *out = nullptr;
+        require_device(device);
+        Bm25GlobalStats g;
+        if (!g.decode(global_stats, stats_bytes)) throw Error(LEANN_ERR_BAD_FORMAT, "BM25 statistics blob is malformed");
+        if (g.num_docs < n_docs) throw Error(LEANN_ERR_INVALID_ARG, "global statistics cover fewer documents than this shard holds");
+        std::unique_ptr<leann_cuda_bm25> b(new leann_cuda_bm25());
+        b->device = device;
+        bm25_build_host(docs, doc_bytes, n_docs, b->host, &g);
+        DevGuard dg(device);
+        b->d_term_off = upload_vec(b->host.term_off);
+        b->d_post_doc = upload_vec(b->host.post_doc);
+        b->d_post_score = upload_vec(b->host.post_score);
+        *out = b.release();
+    });
+}
 size_t leann_cuda_bm25_len(const leann_cuda_bm25* b) { return b ? b->host.num_docs : 0; }
 int leann_cuda_bm25_stats(const leann_cuda_bm25* b, uint64_t* st, float* avg) {
     if (!b || !st) return LEANN_ERR_INVALID_ARG;
@@ -374,6 +426,100 @@ int leann_cuda_hybrid_rerank(const uint64_t* idx, const float* vec_scores, size_
                                (uint32_t)n, oi.as<uint64_t>(), os.as<float>(), oc.as<uint32_t>(), 1, s);
             LEANN_CUDA_CHECK(cudaMemcpyAsync(out_idx, oi.p, n * 8, cudaMemcpyDeviceToHost, s));
             LEANN_CUDA_CHECK(cudaMemcpyAsync(out_scores, os.p, n * 4, cudaMemcpyDeviceToHost, s));
+            LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        cudaStreamDestroy(s);
+    });
+}
+
+// One document-range shard's part of the hybrid step: BM25 top-k of the shard (ids made global with doc_offset),
+// the BM25 score of the (already merged, global) vector candidates this shard owns, and the shard's min / max of
+// its dense score vector. The caller reduces over shards: top lists -> top-k merge, cand_bm -> sum (only the owner
+// is non-zero), bmax -> max, bmin -> min; then leann_cuda_hybrid_fuse.
+int leann_cuda_bm25_search_shard(const leann_cuda_bm25* b, const char* const* queries, const size_t* query_bytes, size_t nq,
+                                 size_t top_k, uint64_t doc_offset, const uint64_t* cand_idx, const uint32_t* cand_cnt, size_t fk,
+                                 uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* cand_bm, float* bmax, float* bmin,
+                                 char* err, size_t errlen) {
+    GUARD({
+        if (!b || (nq && (!queries || !top_idx || !top_score || !top_cnt || !bmax || !bmin))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        if (cand_idx && (!cand_cnt || !cand_bm || fk == 0)) throw Error(LEANN_ERR_INVALID_ARG, "candidate list without counts / output");
+        if (nq == 0) return;
+        DevGuard dg(b->device);
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> terms;
+        tokenize_queries(b, queries, query_bytes, nq, off, terms);
+        std::lock_guard<std::mutex> lk(b->mu);
+        bm25_ensure_ws(b, nq);
+        cudaStream_t s = b->stream;
+        const size_t n_local = b->host.num_docs;
+        std::vector<uint64_t> local;
+        if (cand_idx) {
+            local.resize(nq * fk);
+            for (size_t i = 0; i < nq * fk; ++i) {
+                const uint64_t g = cand_idx[i];
+                local[i] = (g >= doc_offset && g - doc_offset < n_local) ? g - doc_offset : ~0ull;
+            }
+        }
+        DevBuf qo(off.size() * 8), qt(terms.size() * 4), bi(nq * top_k * 8), bs(nq * top_k * 4), bc(nq * 4), bx(nq * 4), bn(nq * 4);
+        DevBuf ci(cand_idx ? nq * fk * 8 : 16), cc(cand_idx ? nq * 4 : 16), cb(cand_idx ? nq * fk * 4 : 16);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(qo.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+        if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt.p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
+        if (cand_idx) {
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(ci.p, local.data(), nq * fk * 8, cudaMemcpyHostToDevice, s));
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(cc.p, cand_cnt, nq * 4, cudaMemcpyHostToDevice, s));
+        }
+        launch_bm25_query(b->view(), qo.as<uint64_t>(), qt.as<uint32_t>(), (uint32_t)nq, (uint32_t)top_k, b->n_ctas,
+                          cand_idx ? ci.as<uint64_t>() : nullptr, cand_idx ? cc.as<uint32_t>() : nullptr, (uint32_t)fk,
+                          cand_idx ? cb.as<float>() : nullptr, bi.as<uint64_t>(), bs.as<float>(), bc.as<uint32_t>(), bx.as<float>(),
+                          bn.as<float>(), b->d_qcounter, s);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(top_idx, bi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(top_score, bs.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(top_cnt, bc.p, nq * 4, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(bmax, bx.p, nq * 4, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(bmin, bn.p, nq * 4, cudaMemcpyDeviceToHost, s));
+        if (cand_idx) LEANN_CUDA_CHECK(cudaMemcpyAsync(cand_bm, cb.p, nq * fk * 4, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < nq * top_k; ++i) if (top_idx[i] != ~0ull) top_idx[i] += doc_offset;
+    });
+}
+
+// Batched hybrid_rerank + post-filter walk (bm25.rs:135-170, searcher.rs:156-207) on already gathered inputs.
+int leann_cuda_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, size_t nq, size_t fk,
+                           const float* cand_bm, const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, size_t bm_k,
+                           const float* bmax, const float* bmin, int hybrid, float alpha, const uint64_t* mask, size_t mask_bits,
+                           size_t top_k, int device, uint64_t* out_idx, float* out_score, uint32_t* out_cnt, char* err, size_t errlen) {
+    GUARD({
+        if (nq && (!vkeys || !vdists || !vcnt || !out_idx || !out_score || !out_cnt)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        if (hybrid && (!cand_bm || !bm_idx || !bm_score || !bm_cnt || !bmax || !bmin)) throw Error(LEANN_ERR_INVALID_ARG, "hybrid fuse needs the BM25 inputs");
+        if (nq == 0) return;
+        if (top_k == 0 || fk == 0) throw Error(LEANN_ERR_INVALID_ARG, "top_k and fetch_k must be > 0");
+        require_device(device);
+        DevGuard dg(device);
+        cudaStream_t s = nullptr;
+        LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        try {
+            const size_t mw = mask ? (mask_bits + 63) / 64 : 0;
+            DevBuf vk(nq * fk * 8), vd(nq * fk * 4), vc(nq * 4), cb(hybrid ? nq * fk * 4 : 16), bi(hybrid ? nq * bm_k * 8 : 16),
+                bs(hybrid ? nq * bm_k * 4 : 16), bc(hybrid ? nq * 4 : 16), bx(hybrid ? nq * 4 : 16), bn(hybrid ? nq * 4 : 16),
+                dm(mask ? mw * 8 : 16), oi(nq * top_k * 8), os(nq * top_k * 4), oc(nq * 4);
+            auto up = [&](DevBuf& d, const void* h, size_t bytes) { LEANN_CUDA_CHECK(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, s)); };
+            up(vk, vkeys, nq * fk * 8); up(vd, vdists, nq * fk * 4); up(vc, vcnt, nq * 4);
+            if (hybrid) {
+                up(cb, cand_bm, nq * fk * 4); up(bi, bm_idx, nq * bm_k * 8); up(bs, bm_score, nq * bm_k * 4);
+                up(bc, bm_cnt, nq * 4); up(bx, bmax, nq * 4); up(bn, bmin, nq * 4);
+            }
+            if (mask) up(dm, mask, mw * 8);
+            launch_hybrid_fuse(vk.as<uint64_t>(), vd.as<float>(), vc.as<uint32_t>(), (uint32_t)fk, hybrid ? cb.as<float>() : nullptr,
+                               hybrid ? bi.as<uint64_t>() : nullptr, hybrid ? bs.as<float>() : nullptr, hybrid ? bc.as<uint32_t>() : nullptr,
+                               (uint32_t)(hybrid ? bm_k : 0), hybrid ? bx.as<float>() : nullptr, hybrid ? bn.as<float>() : nullptr, hybrid,
+                               alpha, mask ? dm.as<uint64_t>() : nullptr, (uint64_t)mask_bits, (uint32_t)top_k, oi.as<uint64_t>(),
+                               os.as<float>(), oc.as<uint32_t>(), (uint32_t)nq, s);
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(out_idx, oi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(out_score, os.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(out_cnt, oc.p, nq * 4, cudaMemcpyDeviceToHost, s));
             LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
         } catch (...) {
             cudaStreamDestroy(s);

@@ -64,6 +64,67 @@ class Bm25Scorer:
         _check(L.leann_cuda_bm25_build(arr, lens, len(documents), device, C.byref(h), e, 1024), e)
         return cls(h.value)
 
+    # ---- document-range shards: corpus-wide N / token count / df travel as opaque blobs ----
+    @staticmethod
+    def shard_stats(documents: Sequence[str]) -> bytes:
+        L = _core().lib()
+        keep, arr, lens = _strs(documents)
+        need = C.c_size_t()
+        e = _err()
+        _check(L.leann_cuda_bm25_shard_stats(arr, lens, len(documents), None, 0, C.byref(need), e, 1024), e)
+        buf = (C.c_ubyte * max(need.value, 1))()
+        _check(L.leann_cuda_bm25_shard_stats(arr, lens, len(documents), buf, need.value, C.byref(need), e, 1024), e)
+        return bytes(buf[: need.value])
+
+    @staticmethod
+    def merge_stats(blobs: Sequence[bytes]) -> bytes:
+        L = _core().lib()
+        n = len(blobs)
+        bufs = [(C.c_ubyte * max(len(b), 1)).from_buffer_copy(b if b else b"\0") for b in blobs]
+        arr = (C.POINTER(C.c_ubyte) * max(n, 1))(*[C.cast(b, C.POINTER(C.c_ubyte)) for b in bufs])
+        lens = (C.c_size_t * max(n, 1))(*[len(b) for b in blobs])
+        need = C.c_size_t()
+        e = _err()
+        _check(L.leann_cuda_bm25_stats_merge(arr, lens, n, None, 0, C.byref(need), e, 1024), e)
+        out = (C.c_ubyte * max(need.value, 1))()
+        _check(L.leann_cuda_bm25_stats_merge(arr, lens, n, out, need.value, C.byref(need), e, 1024), e)
+        return bytes(out[: need.value])
+
+    @classmethod
+    def build_sharded(cls, documents: Sequence[str], global_stats: bytes, device: int = 0) -> "Bm25Scorer":
+        """This rank's documents indexed with the corpus-wide statistics: scores equal the unsharded index bit for bit."""
+        L = _core().lib()
+        keep, arr, lens = _strs(documents)
+        st = (C.c_ubyte * max(len(global_stats), 1)).from_buffer_copy(global_stats or b"\0")
+        h = C.c_void_p()
+        e = _err()
+        _check(L.leann_cuda_bm25_build_sharded(arr, lens, len(documents), st, len(global_stats), device, C.byref(h), e, 1024), e)
+        return cls(h.value)
+
+    def search_shard(self, queries: Sequence[str], top_k: int, doc_offset: int, cand_idx=None, cand_cnt=None):
+        """One shard's BM25 part of the hybrid step. Returns (top_idx[nq,k] global ids, top_score, top_cnt, cand_bm or None,
+        bmax[nq], bmin[nq]); reduce over shards with top-k merge / sum / max / min."""
+        L = _core().lib()
+        keep, arr, lens = _strs(queries)
+        nq = len(queries)
+        ti = np.empty((nq, top_k), dtype=np.uint64)
+        ts = np.empty((nq, top_k), dtype=np.float32)
+        tc = np.zeros(nq, dtype=np.uint32)
+        bx = np.zeros(nq, dtype=np.float32)
+        bn = np.zeros(nq, dtype=np.float32)
+        ci = cc = cb = None
+        fk = 0
+        if cand_idx is not None:
+            ci = np.ascontiguousarray(cand_idx, dtype=np.uint64)
+            cc = np.ascontiguousarray(cand_cnt, dtype=np.uint32)
+            fk = ci.shape[1]
+            cb = np.zeros((nq, fk), dtype=np.float32)
+        ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        e = _err()
+        _check(L.leann_cuda_bm25_search_shard(self._h, arr, lens, nq, top_k, doc_offset, ptr(ci), ptr(cc), fk, ptr(ti), ptr(ts), ptr(tc),
+                                              ptr(cb), ptr(bx), ptr(bn), e, 1024), e)
+        return ti, ts, tc, cb, bx, bn
+
     def __len__(self):
         return int(_core().lib().leann_cuda_bm25_len(self._h))
 
@@ -282,6 +343,30 @@ def hybrid_search(index, bm25: Optional[Bm25Scorer], queries, query_texts: Optio
                                       top_k, ef, 1 if hybrid else 0, C.c_float(alpha),
                                       None if m is None else C.c_void_p(m.ctypes.data), C.c_void_p(idx.ctypes.data),
                                       C.c_void_p(sc.ctypes.data), C.c_void_p(cnt.ctypes.data), e, 1024), e)
+    return idx, sc, cnt
+
+
+def hybrid_fuse(vkeys, vdists, vcnt, top_k: int, hybrid: bool, alpha: float, cand_bm=None, bm_idx=None, bm_score=None, bm_cnt=None,
+                bmax=None, bmin=None, filter_mask: Optional[np.ndarray] = None, mask_bits: int = 0, device: int = 0):
+    """Batched hybrid_rerank + BM25-only additions + post-filter walk (bm25.rs:135-170, searcher.rs:156-207) over gathered
+    inputs (C ABI leann_cuda_hybrid_fuse). vkeys/vdists [nq, fetch_k]; bm_* [nq, bm_k]."""
+    L = _core().lib()
+    vk = np.ascontiguousarray(vkeys, dtype=np.uint64)
+    vd = np.ascontiguousarray(vdists, dtype=np.float32)
+    vc = np.ascontiguousarray(vcnt, dtype=np.uint32)
+    nq, fk = vk.shape
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=t) for a, t in
+            ((cand_bm, np.float32), (bm_idx, np.uint64), (bm_score, np.float32), (bm_cnt, np.uint32), (bmax, np.float32), (bmin, np.float32))]
+    m = None if filter_mask is None else np.ascontiguousarray(filter_mask, dtype=np.uint64)
+    idx = np.empty((nq, top_k), dtype=np.uint64)
+    sc = np.empty((nq, top_k), dtype=np.float32)
+    cnt = np.zeros(nq, dtype=np.uint32)
+    ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    e = _err()
+    _check(L.leann_cuda_hybrid_fuse(ptr(vk), ptr(vd), ptr(vc), nq, fk, ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]),
+                                    0 if arrs[1] is None else arrs[1].shape[1], ptr(arrs[4]), ptr(arrs[5]), 1 if hybrid else 0,
+                                    C.c_float(alpha), ptr(m), mask_bits if m is not None else 0, top_k, device, ptr(idx), ptr(sc), ptr(cnt),
+                                    e, 1024), e)
     return idx, sc, cnt
 
 

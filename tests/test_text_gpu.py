@@ -171,3 +171,44 @@ def test_index_searcher_end_to_end(orc, pkg, tmp_path):
     with pytest.raises(pkg.LeannCudaError) as e:
         pkg.IndexSearcher.load(base, "faiss", d)
     assert "Unknown backend" in e.value.message
+
+
+def test_sharded_bm25_and_fuse_equal_unsharded(orc, pkg, tmp_path):
+    """two document-range shards built with the merged corpus statistics, reduced the way the
+    collectives of ShardedHybridSearcher reduce them, reproduce the unsharded BM25 top-k and the unsharded hybrid
+    result bit for bit."""
+    import torch
+    base, x, q, g, docs, queries, metas = _fixture_dir(tmp_path, orc)
+    n, d, k = len(docs), x.shape[1], 10
+    fk = 5 * k
+    s = pkg.HnswSearcher.load(base, d)
+    full = pkg.Bm25Scorer.build(docs)
+    cut = 1234
+    st = pkg.Bm25Scorer.merge_stats([pkg.Bm25Scorer.shard_stats(docs[:cut]), pkg.Bm25Scorer.shard_stats(docs[cut:])])
+    assert st == pkg.Bm25Scorer.shard_stats(docs)
+    sh = [pkg.Bm25Scorer.build_sharded(docs[:cut], st), pkg.Bm25Scorer.build_sharded(docs[cut:], st)]
+    assert len(sh[0]) == cut and len(sh[1]) == n - cut
+    assert np.float32(sh[0].stats()["avg_doc_len"]).view(np.uint32) == np.float32(full.stats()["avg_doc_len"]).view(np.uint32)
+    texts = queries[: len(q)]
+    vk, vd, vc = s.search_batch(q, fk, 64)
+    parts = [sh[0].search_shard(texts, fk, 0, vk, vc), sh[1].search_shard(texts, fk, cut, vk, vc)]
+    gk = torch.from_numpy(np.stack([p[0].view(np.int64) for p in parts])).cuda()
+    gs = torch.from_numpy(np.stack([p[1] for p in parts])).cuda()
+    mk, ms, mc = pkg.topk_merge_device(gk, gs, descending=True)
+    mk, ms, mc = mk.cpu().numpy(), ms.cpu().numpy(), mc.cpu().numpy()
+    fi, fs, fc = full.search_batch(texts, fk)
+    for i in range(len(texts)):
+        c = int(fc[i])
+        assert int(mc[i]) == c and mk[i, :c].tolist() == fi[i, :c].astype(np.int64).tolist(), texts[i]
+        assert ms[i, :c].view(np.uint32).tolist() == fs[i, :c].view(np.uint32).tolist()
+        dense = full.score_query(texts[i])
+        cb = parts[0][3][i] + parts[1][3][i]
+        assert np.array_equal(cb[: vc[i]].view(np.uint32), dense[vk[i, : vc[i]].astype(np.int64)].view(np.uint32))
+        assert max(parts[0][4][i], parts[1][4][i]) == dense.max() and min(parts[0][5][i], parts[1][5][i]) == dense.min()
+    cb = parts[0][3] + parts[1][3]
+    bx, bn = np.maximum(parts[0][4], parts[1][4]), np.minimum(parts[0][5], parts[1][5])
+    bits = np.array([m["chunk_type"] == "ast" for m in metas])
+    for hybrid, mask in ((True, None), (True, pkg.pack_mask(bits)), (False, pkg.pack_mask(bits))):
+        idx, sc, cnt = pkg.hybrid_fuse(vk, vd, vc, k, hybrid, 0.5, cb, mk.view(np.uint64), ms, mc.astype(np.uint32), bx, bn, mask, n)
+        ridx, rsc, rcnt = pkg.text.hybrid_search(s, full, q, texts if hybrid else None, k, 64, hybrid, 0.5, mask)
+        assert np.array_equal(cnt, rcnt) and np.array_equal(idx, ridx) and np.array_equal(sc.view(np.uint32), rsc.view(np.uint32))
