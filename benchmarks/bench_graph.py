@@ -61,14 +61,18 @@ for ef in a.ef:
     tot = st.sum(0).tolist()
     byts = tot[0] * ((a.d + 3) // 4) * 16 + tot[1] * info["M0"] * 4 + tot[2] * info["M"] * 4
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3): eng.search(q, a.k, ef)          # warm-up
     if world > 1: dist.barrier()
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(a.steps): eng.search(q, a.k, ef)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    evs[0].record()
+    for i in range(a.steps): eng.search(q, a.k, ef); evs[i + 1].record()
+    torch.cuda.synchronize()
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(a.steps)]
+    ms = sorted(step_ms)[a.steps // 2]
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
-    rows.append({"ef": ef, "recall": round(rec, 4), "qps": round(a.nq / ms * 1e3), "ms": round(ms, 3), "n_dist": round(tot[0] / a.nq, 1),
+    rows.append({"ef": ef, "recall": round(rec, 4), "qps": round(a.nq / ms * 1e3), "ms": round(ms, 3), "step_ms": [round(v, 2) for v in step_ms], "n_dist": round(tot[0] / a.nq, 1),
                  "hops": round(tot[1] / a.nq, 1), "algorithmic_GBps": round(byts / ms / 1e6, 1), "frac_of_hbm_peak": round(byts / ms / 1e6 / peak / world, 4)})
 if world > 1: dist.destroy_process_group()
 if rank == 0: print(json.dumps({"bench": "graph", "gpus": world, "backend": a.backend, "n": a.n, "d": a.d, "metric": a.metric, "degree": a.deg, "L_build": a.L, "k": a.k,
