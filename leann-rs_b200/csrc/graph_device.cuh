@@ -240,27 +240,41 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
             const uint32_t nh = w.next_s[w.next_head & next_mask];
             if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
         }
-        // the visited tags of the whole row are requested together (one memory round trip per hop, not one per 32
-        // neighbours); membership is decided per lane, the compaction keeps list order
-        constexpr int NCH = MAX_DEG / 32;
-        uint32_t sv[NCH];
-        uint8_t tg[NCH];
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            const uint32_t j = (uint32_t)ch * 32u + lane;
-            sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
-        }
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vis[sv[ch]] : tag;
         int cnt = 0;
+        if (PREFETCH) {
+            // short rows (latency-bound): the visited tags of the whole row are requested together, one memory round trip per
+            // hop instead of one per 32 neighbours; membership is decided per lane, the compaction keeps list order
+            constexpr int NCH = MAX_DEG / 32;
+            uint32_t sv[NCH];
+            uint8_t tg[NCH];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            if ((uint32_t)ch * 32u >= adj.deg) break;
-            const bool fresh = tg[ch] != tag;
-            if (fresh) vis[sv[ch]] = tag;
-            unsigned b = __ballot_sync(FULL, fresh);
-            if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = sv[ch];
-            cnt += __popc(b);
+            for (int ch = 0; ch < NCH; ++ch) {
+                const uint32_t j = (uint32_t)ch * 32u + lane;
+                sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
+            }
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vis[sv[ch]] : tag;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                if ((uint32_t)ch * 32u >= adj.deg) break;
+                const bool fresh = tg[ch] != tag;
+                if (fresh) vis[sv[ch]] = tag;
+                unsigned b = __ballot_sync(FULL, fresh);
+                if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = sv[ch];
+                cnt += __popc(b);
+            }
+        } else {
+            for (uint32_t base = 0; base < adj.deg; base += 32) {
+                uint32_t j = base + lane;
+                uint32_t s = j < adj.deg ? __ldg(row + j) : SENT;
+                bool fresh = false;
+                if (s != SENT) {
+                    if (vis[s] != tag) { vis[s] = tag; fresh = true; }
+                }
+                unsigned b = __ballot_sync(FULL, fresh);
+                if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = s;
+                cnt += __popc(b);
+            }
         }
         __syncwarp();
         c.n_dist += cnt;
