@@ -194,6 +194,12 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
     p.visited = ix->ws.visited; p.epochs = ix->ws.epochs; p.counter = ix->ws.counter;
     p.n_pad = ix->ws.n_pad;
     p.n_warps = (int)std::min<size_t>((size_t)ix->ws.n_warps, (nq + 3) & ~(size_t)3);
+    // batches of at most two queries per SM leave most of the machine idle with one warp per query: give each query a CTA
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+        p.coop_ctas = (nq <= (size_t)sms * 2 && ix->coop_small_batches) ? (int)std::min<size_t>(nq, (size_t)ix->ws.n_warps) : 0;
+    }
     launch_graph_search(ix->view(), p, stream);
 }
 

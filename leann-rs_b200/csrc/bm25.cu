@@ -364,6 +364,16 @@ __global__ void gather_kernel(const float* __restrict__ dense, uint32_t n, const
 
 }  // namespace
 
+// cudaFuncSetAttribute is per device: remember which devices of this process already have it.
+static bool first_use_on_device(unsigned long long& seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
                        cudaStream_t s) {
     for (size_t i = 0; i < n_tokens; ++i) {
@@ -379,11 +389,9 @@ void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_
                        float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,
                        uint32_t* qcounter, cudaStream_t s) {
     if (K == 0 || K > 1024) throw Error(LEANN_ERR_INVALID_ARG, "bm25: top_k must be in 1..1024");
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long seen = 0;
+    if (first_use_on_device(seen))
         LEANN_CUDA_CHECK(cudaFuncSetAttribute(bm25_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BM_SMEM));
-        attr = true;
-    }
     LEANN_CUDA_CHECK(cudaMemsetAsync(qcounter, 0, 4, s));
     bm25_query_kernel<<<n_ctas, BM_THREADS, BM_SMEM, s>>>(b, qtok_off, qtok_term, nq, K, cand_idx, cand_cnt, fk, cand_bm,
                                                           top_idx, top_score, top_cnt, bmax, bmin, qcounter);

@@ -369,6 +369,16 @@ constexpr uint32_t SCAN_CAP = 4096;
 
 }  // namespace
 
+// cudaFuncSetAttribute is per device: remember which devices of this process already have it.
+static bool first_use_on_device(unsigned long long& seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 void launch_pad_rows(const float* src, float4* dst, size_t n, uint32_t d, uint32_t d4, cudaStream_t stream) {
     size_t total = n * d4;
     if (!total) return;
@@ -428,14 +438,12 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         rounds.emplace_back(r0, r1);
         r0 = r1;
     }
-    static bool attr_set = false;
+    static unsigned long long attr_seen = 0;
     uint32_t sort_cap = 512;   // sort buffer: the 2k + 1 keys a radix select keeps, or a short list sorted whole
     while (sort_cap < 2 * k + 1) sort_cap <<= 1;
     const size_t sel_smem = ((size_t)sort_cap + SCAN_CAP + kpad) * 8;
-    if (!attr_set) {
+    if (first_use_on_device(attr_seen))
         LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)4096 + SCAN_CAP + 1024) * 8)));
-        attr_set = true;
-    }
     auto run_round = [&](size_t ri, int attempt) {
         const uint32_t r0 = rounds[ri].first, r1 = rounds[ri].second;
         dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);

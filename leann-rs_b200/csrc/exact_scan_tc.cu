@@ -478,11 +478,16 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
     p.thr_dot = ts.thr_dot; p.mask = d_mask; p.cand_ids = ts.cand_ids; p.cand_cnt = s.cand_cnt; p.cap = cap; p.overflow = s.overflow;
     const uint32_t items = p.n_qpairs * p.n_groups;
     const int grid = 2 * (int)std::min<uint32_t>(max_pairs, items);
-    static bool attr = false;
-    if (!attr) {
-        LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-        LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
-        attr = true;
+    static unsigned long long attr_seen = 0;   // cudaFuncSetAttribute is per device
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (!(attr_seen & bit)) {
+            LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+            LEANN_CUDA_CHECK(cudaFuncSetAttribute(scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX));
+            attr_seen |= bit;
+        }
     }
     if (resident) scan_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mq, mx, p);
     else scan_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(mq, mx, p);

@@ -73,14 +73,17 @@ __device__ __forceinline__ float finish_distance(float s, int metric) {
 // Distances from the register-resident query to st_slot[0..cnt) -> st_dist[0..cnt).
 // 32/LPV vectors are evaluated side by side, U deep: U*VPL independent 16-byte loads per lane are
 // in flight before the first FMA.
+// `first` / `stride` (in entries, multiples of the batch size) let several warps share one list: every entry is
+// still evaluated by exactly one warp with the same lane mapping, so the bits do not depend on the split.
 template <int LPV, int VPL, int U>
 __device__ __forceinline__ void eval_distances(const float4* __restrict__ vecs, uint32_t d4, int metric,
                                                const float4 (&q)[VPL], const uint32_t* st_slot,
-                                               float* st_dist, int cnt, int lane) {
+                                               float* st_dist, int cnt, int lane, int first = 0,
+                                               int stride = U * (32 / LPV)) {
     constexpr int GROUPS = 32 / LPV;
     constexpr int BATCH = U * GROUPS;
     const int gid = lane / LPV, lig = lane % LPV;
-    for (int b = 0; b < cnt; b += BATCH) {
+    for (int b = first; b < cnt; b += stride) {
         float4 x[U][VPL];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -116,6 +119,46 @@ __device__ __forceinline__ void load_query(const float* __restrict__ qrow, uint3
         q[i].z = j + 2 < d ? qrow[j + 2] : 0.f;
         q[i].w = j + 3 < d ? qrow[j + 3] : 0.f;
     }
+}
+
+// Several warps of one CTA can serve ONE query (small batches: the reference's API is one query per call): warp 0 runs
+// the traversal and owns the lists, the other warps only evaluate their share of every staged neighbour list.
+// Protocol: warp 0 publishes the list length (or -1 = query finished) and both sides meet at two named barriers.
+struct Coop {
+    int* cmd;      // shared-memory command word (nullptr: single-warp mode)
+    int warp, nwarps;
+};
+__device__ __forceinline__ void coop_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+template <int LPV, int VPL, int U>
+__device__ __forceinline__ void coop_eval(const Coop& cp, const float4* __restrict__ vecs, uint32_t d4, int metric,
+                                          const float4 (&q)[VPL], const uint32_t* st_slot, float* st_dist, int cnt, int lane) {
+    if (cp.cmd == nullptr) {
+        eval_distances<LPV, VPL, U>(vecs, d4, metric, q, st_slot, st_dist, cnt, lane);
+        return;
+    }
+    constexpr int BATCH = U * (32 / LPV);
+    if (lane == 0) *cp.cmd = cnt;
+    coop_bar(cp.nwarps * 32);
+    eval_distances<LPV, VPL, U>(vecs, d4, metric, q, st_slot, st_dist, cnt, lane, 0, cp.nwarps * BATCH);
+    coop_bar(cp.nwarps * 32);
+}
+// helper warps: serve evaluation requests until warp 0 signals the end of the query
+template <int LPV, int VPL, int U>
+__device__ __forceinline__ void coop_serve(const Coop& cp, const float4* __restrict__ vecs, uint32_t d4, int metric,
+                                           const float4 (&q)[VPL], const uint32_t* st_slot, float* st_dist, int lane) {
+    constexpr int BATCH = U * (32 / LPV);
+    for (;;) {
+        coop_bar(cp.nwarps * 32);
+        const int cnt = *reinterpret_cast<volatile int*>(cp.cmd);
+        if (cnt < 0) break;
+        eval_distances<LPV, VPL, U>(vecs, d4, metric, q, st_slot, st_dist, cnt, lane, cp.warp * BATCH, cp.nwarps * BATCH);
+        coop_bar(cp.nwarps * 32);
+    }
+}
+__device__ __forceinline__ void coop_finish(const Coop& cp, int lane) {   // warp 0, after the last evaluation of a query
+    if (cp.cmd == nullptr) return;
+    if (lane == 0) *cp.cmd = -1;
+    coop_bar(cp.nwarps * 32);
 }
 
 // Sorted insert into an ascending (optionally ring-indexed) array.
@@ -172,7 +215,7 @@ struct Counters { uint32_t n_dist, n_hops0, n_hops_upper, dropped; };
 template <int LPV, int VPL, int U>
 __device__ __forceinline__ void greedy_descend(const GraphView& g, const float4 (&q)[VPL], WarpLists& w,
                                                uint32_t& cur, float& cur_d, int from_level, int to_level,
-                                               Counters& c, int lane) {
+                                               Counters& c, int lane, const Coop cp = Coop{nullptr, 0, 1}) {
     for (int level = from_level; level > to_level; --level) {
         bool changed;
         do {
@@ -190,7 +233,7 @@ __device__ __forceinline__ void greedy_descend(const GraphView& g, const float4 
             __syncwarp();
             c.n_hops_upper++;
             c.n_dist += cnt;
-            eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+            coop_eval<LPV, VPL, U>(cp, g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
             float bd = CUDART_INF_F; int bj = 0x7fffffff;
             for (int j = lane; j < cnt; j += 32) {
                 float dj = w.st_dist[j];
@@ -217,7 +260,8 @@ template <int LPV, int VPL, int U, bool PREFETCH = false>
 __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL],
                                            WarpLists& w, int ef, int next_cap, int next_mask, int nonstrict,
                                            const uint64_t* __restrict__ mask, uint8_t* vis, uint8_t tag,
-                                           uint32_t start, float start_d, Counters& c, int lane) {
+                                           uint32_t start, float start_d, Counters& c, int lane,
+                                           const Coop cp = Coop{nullptr, 0, 1}) {
     auto passes = [&](uint32_t s) { return mask == nullptr || ((mask[s >> 6] >> (s & 63u)) & 1ull); };
     w.top_size = 0; w.next_size = 0; w.next_head = 0;
     float radius = CUDART_INF_F;
@@ -288,7 +332,7 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
                 for (uint32_t l = 0; l < lines; ++l) prefetch_l2(r + l * 128u);
             }
         }
-        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+        coop_eval<LPV, VPL, U>(cp, g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
         // ---- replay the inserts in list order ----
         for (int base = 0; base < cnt; base += 32) {
             int j = base + lane;

@@ -86,6 +86,81 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
     }
 }
 
+// Small batches (nq <= about two per SM): one CTA of COOP_WARPS warps per query. Warp 0 runs the same traversal as above and
+// owns the lists; all warps evaluate the distances of each staged neighbour list (coop_eval / coop_serve), which is where a
+// single-warp traversal spends most of a hop at d = 768. Results are bit-identical to the warp-per-query kernel.
+constexpr int COOP_WARPS = 4;
+template <int LPV, int VPL, int U, int MINB>
+__global__ void __launch_bounds__(COOP_WARPS * 32, MINB)
+graph_search_coop_kernel(const GraphView g, const SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_cmd;
+    __shared__ uint32_t s_qi;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t ef_pad = (p.ef + 31u) & ~31u;
+    WarpLists w;
+    w.top_d = reinterpret_cast<float*>(smem_raw);
+    w.top_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ef_pad * 4);
+    w.next_d = reinterpret_cast<float*>(smem_raw + (size_t)ef_pad * 8);
+    w.next_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ef_pad * 8 + (size_t)p.next_capp * 4);
+    w.st_slot = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8);
+    w.st_dist = reinterpret_cast<float*>(smem_raw + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 4);
+    uint8_t* vis = p.visited + (size_t)blockIdx.x * p.n_pad;
+    uint32_t* epoch_slot = p.epochs + blockIdx.x;
+    const Coop cp{&s_cmd, warp, COOP_WARPS};
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_qi = atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const uint32_t qi = s_qi;
+        if (qi >= p.nq) break;
+        float4 q[VPL];
+        load_query<LPV, VPL>(p.queries + (size_t)qi * g.d, g.d, q, lane);
+        if (warp != 0) {
+            coop_serve<LPV, VPL, U>(cp, g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, lane);
+            continue;
+        }
+        const uint8_t tag = next_epoch(epoch_slot, vis, p.n_pad, lane);
+        Counters c{0u, 0u, 0u, 0u};
+        uint32_t cur = g.entry;
+        if (lane == 0) w.st_slot[0] = cur;
+        __syncwarp();
+        coop_eval<LPV, VPL, U>(cp, g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, 1, lane);
+        float cur_d = w.st_dist[0];
+        c.n_dist = 1;
+        __syncwarp();
+        if (g.max_level > 0) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, 0, c, lane, cp);
+        LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
+        beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
+                                            p.mask, vis, tag, cur, cur_d, c, lane, cp);
+        coop_finish(cp, lane);
+        const int cnt = w.top_size < (int)p.k ? w.top_size : (int)p.k;
+        for (uint32_t i = lane; i < p.k; i += 32) {
+            uint64_t key = ~0ull;
+            float dd = CUDART_INF_F;
+            if ((int)i < cnt) {
+                uint32_t s = w.top_s[i];
+                key = g.keys ? g.keys[s] : (uint64_t)s;
+                dd = w.top_d[i];
+            }
+            p.out_keys[(size_t)qi * p.k + i] = key;
+            p.out_dists[(size_t)qi * p.k + i] = dd;
+        }
+        if (lane == 0) {
+            if (p.out_counts) p.out_counts[qi] = (uint32_t)cnt;
+            if (p.out_stats) {
+                p.out_stats[(size_t)qi * 4 + 0] = c.n_dist;
+                p.out_stats[(size_t)qi * 4 + 1] = c.n_hops0;
+                p.out_stats[(size_t)qi * 4 + 2] = c.n_hops_upper;
+                p.out_stats[(size_t)qi * 4 + 3] = c.dropped;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Lanes cooperating on one distance: 8 for d <= 256 (four vectors side by side), else 32.
 int reduction_lanes(size_t dims) { return dims <= 256 ? 8 : 32; }
 
@@ -113,8 +188,17 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
         LEANN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, warps_per_block * 32, smem));
         return blocks_per_sm * warps_per_block;
     }
-    int blocks = (p.n_warps + warps_per_block - 1) / warps_per_block;
     LEANN_CUDA_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), stream));
+    if (p.coop_ctas > 0) {
+        // small batch: one CTA of COOP_WARPS warps per query (visited slices are indexed by CTA, so coop_ctas <= n_warps)
+        auto ck = graph_search_coop_kernel<LPV, VPL, U, MINB>;
+        const size_t csmem = graph_search_smem_per_warp(p.ef, p.next_capp);
+        if (csmem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        ck<<<p.coop_ctas, COOP_WARPS * 32, csmem, stream>>>(g, p);
+        LEANN_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    int blocks = (p.n_warps + warps_per_block - 1) / warps_per_block;
     kern<<<blocks, warps_per_block * 32, smem, stream>>>(g, p);
     LEANN_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -97,6 +97,7 @@ struct SearchParams {
     uint8_t* visited; uint32_t* epochs; uint32_t* counter;
     size_t n_pad;
     int n_warps;
+    int coop_ctas;   // > 0: small batch, launch this many multi-warp CTAs (one query each at a time) instead of the warp pool
 };
 
 int reduction_lanes(size_t dims);
@@ -173,6 +174,7 @@ struct leann_cuda_index {
     mutable uint32_t* tc_xmax = nullptr;
     mutable bool tc_disabled = false;
     mutable leann::Coalescer coalescer;
+    bool coop_small_batches = true;   // CTA-per-query kernel for nq <= 2 per SM
     leann::GraphView view() const {
         leann::GraphView g;
         g.vecs = vecs; g.adj0 = adj0; g.upper_base = upper_base; g.adjU = adjU;

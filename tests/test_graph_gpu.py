@@ -156,3 +156,29 @@ def test_cpp_host_mirror(orc, pkg, tmp_path):
     keys = [int(t) for t in [l for l in out.splitlines() if l.startswith("KEYS")][0].split()[1:]]
     ok, _, _, _ = g.search(q[None, :], 5, 64, lanes=pkg.reduction_lanes(d), next_cap=64)
     assert keys == [int(v) for v in ok[0]]
+
+
+def test_small_batch_cta_per_query_matches_pool_and_oracle(orc, pkg, tmp_path):
+    """Batches of at most two queries per SM run one 4-warp CTA per query (distance evaluations split across the warps);
+    larger batches run one warp per query. Both must give the oracle's ids, distance bits and work counters."""
+    import torch
+    for d, M in ((768, 16), (96, 16)):
+        n, k, ef = 5000, 10, 64
+        x, q = make_data(n, d, 23, nq=900)
+        g = orc.Hnsw.build(x, M=M, ef_add=64, seed=9)
+        base = str(tmp_path / f"documents{d}.leann")
+        g.save(base.replace(".leann", ".index"))
+        s = pkg.HnswSearcher.load(base, d)
+        ok, od, oc, ost = g.search(q, k, ef, lanes=pkg.reduction_lanes(d), next_cap=pkg.queue_capacity(ef, False))
+        qt = torch.from_numpy(q).cuda()
+        for lo, hi in ((0, 900), (0, 1), (1, 8), (8, 150), (150, 446)):     # pool kernel, then CTA-per-query batches
+            st = torch.zeros((hi - lo, 4), dtype=torch.int64, device="cuda")
+            keys, dists, counts = s.search_device(qt[lo:hi].contiguous(), k, ef, stats=st)
+            assert np.array_equal(keys.cpu().numpy().view(np.uint64), ok[lo:hi]), (d, lo, hi)
+            assert np.array_equal(dists.cpu().numpy().view(np.uint32), od[lo:hi].view(np.uint32)), (d, lo, hi)
+            assert np.array_equal(st.cpu().numpy()[:, :3], ost[lo:hi, :3].astype(np.int64)), (d, lo, hi)
+        # inline mask on a small batch
+        bits = np.random.default_rng(1).random(n) < 0.3
+        mk, md, mc = s.search_batch(q[:50], k, ef, mask=pkg.pack_mask(bits))
+        wk, wd, wc, _ = g.search(q[:50], k, ef, lanes=pkg.reduction_lanes(d), mask=pkg.pack_mask(bits), next_cap=pkg.queue_capacity(ef, True))
+        assert np.array_equal(mk, wk) and np.array_equal(md.view(np.uint32), wd.view(np.uint32))
