@@ -199,6 +199,7 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
         p.coop_ctas = (nq <= (size_t)sms * 2 && ix->coop_small_batches) ? (int)std::min<size_t>(nq, (size_t)ix->ws.n_warps) : 0;
+        p.coop_warps = nq <= (size_t)sms ? 8 : 4;
     }
     launch_graph_search(ix->view(), p, stream);
 }

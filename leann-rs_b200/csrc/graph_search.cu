@@ -86,12 +86,12 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
     }
 }
 
-// Small batches (nq <= about two per SM): one CTA of COOP_WARPS warps per query. Warp 0 runs the same traversal as above and
+// Small batches (nq <= two per SM): one CTA of COOP_WARPS warps per query. Warp 0 runs the same traversal as above and
 // owns the lists; all warps evaluate the distances of each staged neighbour list (coop_eval / coop_serve), which is where a
 // single-warp traversal spends most of a hop at d = 768. Results are bit-identical to the warp-per-query kernel.
-constexpr int COOP_WARPS = 4;
-template <int LPV, int VPL, int U, int MINB>
-__global__ void __launch_bounds__(COOP_WARPS * 32, MINB)
+// COOP_WARPS = 8 while every query gets an SM to itself (nq <= SM count), 4 up to two queries per SM.
+template <int LPV, int VPL, int U, int MINB, int COOP_WARPS>
+__global__ void __launch_bounds__(COOP_WARPS * 32, (COOP_WARPS == 4 ? MINB : 1))
 graph_search_coop_kernel(const GraphView g, const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_cmd;
@@ -191,10 +191,11 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
     LEANN_CUDA_CHECK(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), stream));
     if (p.coop_ctas > 0) {
         // small batch: one CTA of COOP_WARPS warps per query (visited slices are indexed by CTA, so coop_ctas <= n_warps)
-        auto ck = graph_search_coop_kernel<LPV, VPL, U, MINB>;
+        const int cw = p.coop_warps == 8 ? 8 : 4;
+        auto ck = cw == 8 ? graph_search_coop_kernel<LPV, VPL, U, MINB, 8> : graph_search_coop_kernel<LPV, VPL, U, MINB, 4>;
         const size_t csmem = graph_search_smem_per_warp(p.ef, p.next_capp);
         if (csmem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        ck<<<p.coop_ctas, COOP_WARPS * 32, csmem, stream>>>(g, p);
+        ck<<<p.coop_ctas, cw * 32, csmem, stream>>>(g, p);
         LEANN_CUDA_CHECK(cudaGetLastError());
         return 0;
     }

@@ -97,6 +97,7 @@ struct SearchParams {
     uint8_t* visited; uint32_t* epochs; uint32_t* counter;
     size_t n_pad;
     int n_warps;
+    int coop_warps;  // 4 or 8 warps per CTA of the small-batch kernel
     int coop_ctas;   // > 0: small batch, launch this many multi-warp CTAs (one query each at a time) instead of the warp pool
 };
 
