@@ -181,9 +181,10 @@ void leann_cuda_bm25_free(leann_cuda_bm25* bm25);
  * corpus-wide N, total token count and per-term document frequency, so idf (bm25.rs:88), avg_doc_len (:61-65) and
  * each posting's score are bit-identical to the unsharded index. The statistics travel between ranks as opaque
  * blobs (all_gather of bytes): shard_stats on every rank -> stats_merge of all blobs -> build_sharded.
- * Sizing call: out == NULL returns the byte count in *needed. */
-int leann_cuda_bm25_shard_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, unsigned char* out,
-                                size_t cap, size_t* needed, char* err, size_t errlen);
+ * Sizing call: out == NULL returns the byte count in *needed (shard_stats tokenises on `device` during the sizing call
+ * and hands the same blob to the fill call that follows on the calling thread). */
+int leann_cuda_bm25_shard_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, int device,
+                                unsigned char* out, size_t cap, size_t* needed, char* err, size_t errlen);
 int leann_cuda_bm25_stats_merge(const unsigned char* const* blobs, const size_t* blob_bytes, size_t n_blobs,
                                 unsigned char* out, size_t cap, size_t* needed, char* err, size_t errlen);
 int leann_cuda_bm25_build_sharded(const char* const* docs, const size_t* doc_bytes, size_t n_docs,

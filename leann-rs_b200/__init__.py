@@ -77,7 +77,7 @@ def lib():
         "leann_cuda_tokenize": (sz, [cp, sz, cp, sz]),
         "leann_cuda_bm25_score": (C.c_int, [vp, cp, sz, vp, cp, sz]),
         "leann_cuda_bm25_search": (C.c_int, [vp, cpp, szp, sz, sz, vp, vp, vp, cp, sz]),
-        "leann_cuda_bm25_shard_stats": (C.c_int, [cpp, szp, sz, vp, sz, szp, cp, sz]),
+        "leann_cuda_bm25_shard_stats": (C.c_int, [cpp, szp, sz, C.c_int, vp, sz, szp, cp, sz]),
         "leann_cuda_bm25_stats_merge": (C.c_int, [vp, szp, sz, vp, sz, szp, cp, sz]),
         "leann_cuda_bm25_build_sharded": (C.c_int, [cpp, szp, sz, vp, sz, C.c_int, pp, cp, sz]),
         "leann_cuda_bm25_search_shard": (C.c_int, [vp, cpp, szp, sz, sz, C.c_uint64, vp, vp, sz, vp, vp, vp, vp, vp, vp, cp, sz]),

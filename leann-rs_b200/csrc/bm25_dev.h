@@ -26,6 +26,10 @@ void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32
 void launch_dense_minmax_gather(const float* dense, uint32_t n, const uint64_t* idx, uint32_t m, float* cand_bm, float* bmax,
                                 float* bmin, uint32_t* scratch2, cudaStream_t s);
 
+// GPU index construction (bm25_build.cu). stats_only: fill `stats` (N, token count, per-term df) and return.
+void bm25_build_device(const char* const* docs, const size_t* doc_bytes, size_t n_docs, const Bm25GlobalStats* glob,
+                       leann_cuda_bm25* out, Bm25GlobalStats* stats, bool stats_only);
+
 // search entry shared between api.cu and text_api.cu: enqueue a backend search with device buffers
 void backend_search_device(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
                            const uint64_t* d_mask, uint64_t* d_keys, float* d_dists, uint32_t* d_counts, cudaStream_t stream);
@@ -35,7 +39,7 @@ cudaStream_t backend_stream(const leann_cuda_index* ix);
 
 struct leann_cuda_bm25 {
     int device = 0;
-    leann::Bm25Host host;
+    leann::Bm25Host host;   // dictionary, term offsets, idf, counters (the postings live on the device only)
     uint64_t* d_term_off = nullptr;
     uint32_t* d_post_doc = nullptr;
     float* d_post_score = nullptr;

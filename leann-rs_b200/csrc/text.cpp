@@ -194,19 +194,7 @@ void tokenize(const char* text, size_t n, std::vector<std::string>& out) {
     }
 }
 
-// ================================= BM25 build =================================
-void bm25_local_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25GlobalStats& g) {
-    g = Bm25GlobalStats();
-    g.num_docs = n_docs;
-    std::vector<std::string> toks;
-    for (size_t d = 0; d < n_docs; ++d) {
-        tokenize(docs[d], doc_bytes[d], toks);
-        g.total_tokens += toks.size();
-        std::sort(toks.begin(), toks.end());
-        for (size_t i = 0; i < toks.size(); ++i)
-            if (i == 0 || toks[i] != toks[i - 1]) g.df[toks[i]]++;
-    }
-}
+// ================================= BM25 statistics blobs =================================
 void Bm25GlobalStats::merge(const Bm25GlobalStats& o) {
     num_docs += o.num_docs;
     total_tokens += o.total_tokens;
@@ -246,98 +234,6 @@ bool Bm25GlobalStats::decode(const unsigned char* p, size_t n) {
         df[term] += v;
     }
     return o == n;
-}
-
-void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& o, const Bm25GlobalStats* glob) {
-    const float K1 = 1.2f, B = 0.75f;
-    (void)K1;
-    o = Bm25Host();
-    o.num_docs = n_docs;
-    o.doc_len.resize(n_docs);
-    std::vector<uint32_t> df;
-    std::vector<std::pair<uint32_t, uint32_t>> doc_terms;  // flattened (term, tf) per doc
-    std::vector<uint64_t> doc_off(n_docs + 1, 0);
-    std::vector<std::string> toks;
-    std::vector<uint32_t> ids;
-    for (size_t d = 0; d < n_docs; ++d) {
-        tokenize(docs[d], doc_bytes[d], toks);
-        o.doc_len[d] = (uint32_t)toks.size();
-        o.total_tokens += toks.size();
-        ids.clear();
-        for (auto& t : toks) {
-            auto it = o.dict.find(t);
-            uint32_t id;
-            if (it == o.dict.end()) { id = (uint32_t)o.dict.size(); o.dict.emplace(t, id); df.push_back(0); }
-            else id = it->second;
-            ids.push_back(id);
-        }
-        std::sort(ids.begin(), ids.end());
-        for (size_t i = 0; i < ids.size();) {
-            size_t j = i;
-            while (j < ids.size() && ids[j] == ids[i]) ++j;
-            doc_terms.emplace_back(ids[i], (uint32_t)(j - i));
-            df[ids[i]]++;
-            i = j;
-        }
-        doc_off[d + 1] = doc_terms.size();
-    }
-    // bm25.rs:61-65 (over the whole corpus when this is one document-range shard of it)
-    const uint64_t N_all = glob ? glob->num_docs : (uint64_t)n_docs;
-    const uint64_t tokens_all = glob ? glob->total_tokens : o.total_tokens;
-    o.avg_doc_len = N_all > 0 ? (float)tokens_all / (float)N_all : 1.0f;
-    std::vector<uint64_t> df_all(df.begin(), df.end());
-    if (glob)
-        for (auto& kv : o.dict) {
-            auto it = glob->df.find(kv.first);
-            if (it != glob->df.end()) df_all[kv.second] = it->second;
-        }
-    size_t nt = df.size();
-    o.term_off.assign(nt + 1, 0);
-    for (size_t t = 0; t < nt; ++t) o.term_off[t + 1] = o.term_off[t] + df[t];
-    o.post_doc.resize(doc_terms.size());
-    o.post_tf.resize(doc_terms.size());
-    std::vector<uint64_t> cur(o.term_off.begin(), o.term_off.end() - 1);
-    for (size_t d = 0; d < n_docs; ++d)
-        for (uint64_t i = doc_off[d]; i < doc_off[d + 1]; ++i) {
-            uint64_t pos = cur[doc_terms[i].first]++;
-            o.post_doc[pos] = (uint32_t)d;
-            o.post_tf[pos] = doc_terms[i].second;
-        }
-    // bm25.rs:88  idf = ((N - df + 0.5) / (df + 0.5) + 1.0).ln()   — all f32
-    o.idf.resize(nt);
-    const float Nf = (float)N_all;
-    for (size_t t = 0; t < nt; ++t) {
-        float dff = (float)df_all[t];
-        volatile float a = Nf - dff;
-        volatile float num = a + 0.5f;
-        volatile float den = dff + 0.5f;
-        volatile float r = num / den;
-        volatile float s = r + 1.0f;
-        o.idf[t] = logf(s);
-    }
-    // bm25.rs:96-97  norm = 1.0 - B + B * (doc_len / avg_doc_len)
-    o.norm.resize(n_docs);
-    for (size_t d = 0; d < n_docs; ++d) {
-        volatile float ratio = (float)o.doc_len[d] / o.avg_doc_len;
-        volatile float m = B * ratio;
-        volatile float base = 1.0f - B;
-        o.norm[d] = base + m;
-    }
-    // bm25.rs:100  score = idf * (tf * (K1 + 1.0)) / (tf + K1 * norm)  — per (term, doc), independent of the query
-    o.post_score.resize(o.post_doc.size());
-    const float K1f = 1.2f;
-    volatile float k1p1 = K1f + 1.0f;
-    for (size_t t = 0; t < nt; ++t) {
-        const float idf = o.idf[t];
-        for (uint64_t pp = o.term_off[t]; pp < o.term_off[t + 1]; ++pp) {
-            const float tf = (float)o.post_tf[pp];
-            volatile float a = tf * k1p1;
-            volatile float num = idf * a;
-            volatile float kn = K1f * o.norm[o.post_doc[pp]];
-            volatile float den = tf + kn;
-            o.post_score[pp] = num / den;
-        }
-    }
 }
 
 // ================================= filter =================================

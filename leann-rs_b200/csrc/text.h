@@ -62,15 +62,13 @@ struct MetaColumns {
 struct Bm25Host {
     size_t num_docs = 0;
     uint64_t total_tokens = 0;
+    uint64_t n_postings = 0;
     float avg_doc_len = 1.0f;
     std::unordered_map<std::string, uint32_t> dict;  // term -> term id
     std::vector<uint64_t> term_off;   // n_terms + 1
-    std::vector<uint32_t> post_doc;   // ascending doc id inside a term
-    std::vector<uint32_t> post_tf;
-    std::vector<float> post_score;    // idf * (tf * (K1 + 1)) / (tf + K1 * norm): query independent, f32 as bm25.rs:88-100
-    std::vector<float> idf;           // per term, f32 exactly as bm25.rs:88
-    std::vector<float> norm;          // per doc: 1 - B + B * (len / avg), bm25.rs:97
-    std::vector<uint32_t> doc_len;
+    std::vector<float> idf;           // per term, f32 exactly as bm25.rs:88 (libm logf on the host)
+    // device only: post_doc (ascending doc id inside a term) and post_score = idf * (tf * (K1 + 1)) / (tf + K1 * norm),
+    // query independent, f32 as bm25.rs:88-100
 };
 // Corpus-wide statistics of a document-range sharded corpus: N, total tokens and df per term are
 // global, so idf (bm25.rs:88), avg_doc_len (:61-65) and every per-posting score equal the unsharded ones bit for bit.
@@ -81,8 +79,6 @@ struct Bm25GlobalStats {
     bool decode(const unsigned char* p, size_t n);
     void merge(const Bm25GlobalStats& other);
 };
-void bm25_local_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25GlobalStats& out);
-void bm25_build_host(const char* const* docs, const size_t* doc_bytes, size_t n_docs, Bm25Host& out,
-                     const Bm25GlobalStats* global = nullptr);
+// The index itself is built on the device (bm25_build.cu); the host keeps the dictionary, the term offsets and idf.
 
 }  // namespace leann

@@ -242,11 +242,8 @@ int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size
         if (n_docs > 0xFFFFFFF0ull) throw Error(LEANN_ERR_INVALID_ARG, "too many documents");
         std::unique_ptr<leann_cuda_bm25> b(new leann_cuda_bm25());
         b->device = device;
-        bm25_build_host(docs, doc_bytes, n_docs, b->host);
         DevGuard dg(device);
-        b->d_term_off = upload_vec(b->host.term_off);
-        b->d_post_doc = upload_vec(b->host.post_doc);
-        b->d_post_score = upload_vec(b->host.post_score);
+        bm25_build_device(docs, doc_bytes, n_docs, nullptr, b.get(), nullptr, false);
         *out = b.release();
     });
 }
@@ -257,17 +254,26 @@ static int copy_blob(const std::string& blob, unsigned char* out, size_t cap, si
     memcpy(out, blob.data(), blob.size());
     return LEANN_OK;
 }
-int leann_cuda_bm25_shard_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, unsigned char* out, size_t cap,
-                                size_t* needed, char* err, size_t errlen) {
-    int rc = LEANN_OK;
-    int g = leann::guard_impl(err, errlen, [&]() {
+int leann_cuda_bm25_shard_stats(const char* const* docs, const size_t* doc_bytes, size_t n_docs, int device, unsigned char* out,
+                                size_t cap, size_t* needed, char* err, size_t errlen) {
+    GUARD({
         if (n_docs && (!docs || !doc_bytes)) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
-        Bm25GlobalStats st;
-        bm25_local_stats(docs, doc_bytes, n_docs, st);
-        rc = copy_blob(st.encode(), out, cap, needed);
+        // the sizing call (out == NULL) runs the device pipeline and keeps the blob for the fill call that follows on this thread
+        thread_local std::string cached;
+        thread_local const void* cached_key = nullptr;
+        thread_local size_t cached_n = 0;
+        if (!(out && cached_key == (const void*)docs && cached_n == n_docs && !cached.empty())) {
+            require_device(device);
+            DevGuard dg(device);
+            Bm25GlobalStats st;
+            bm25_build_device(docs, doc_bytes, n_docs, nullptr, nullptr, &st, true);
+            cached = st.encode();
+            cached_key = docs; cached_n = n_docs;
+        }
+        int rc = copy_blob(cached, out, cap, needed);
+        if (out) { cached.clear(); cached_key = nullptr; }
         if (rc != LEANN_OK) throw Error(rc, "stats buffer too small");
     });
-    return g;
 }
 int leann_cuda_bm25_stats_merge(const unsigned char* const* blobs, const size_t* blob_bytes, size_t n_blobs, unsigned char* out,
                                 size_t cap, size_t* needed, char* err, size_t errlen) {
@@ -294,18 +300,15 @@ int leann_cuda_bm25_build_sharded(const char* const* docs, const size_t* doc_byt
         if (g.num_docs < n_docs) throw Error(LEANN_ERR_INVALID_ARG, "global statistics cover fewer documents than this shard holds");
         std::unique_ptr<leann_cuda_bm25> b(new leann_cuda_bm25());
         b->device = device;
-        bm25_build_host(docs, doc_bytes, n_docs, b->host, &g);
         DevGuard dg(device);
-        b->d_term_off = upload_vec(b->host.term_off);
-        b->d_post_doc = upload_vec(b->host.post_doc);
-        b->d_post_score = upload_vec(b->host.post_score);
+        bm25_build_device(docs, doc_bytes, n_docs, &g, b.get(), nullptr, false);
         *out = b.release();
     });
 }
 size_t leann_cuda_bm25_len(const leann_cuda_bm25* b) { return b ? b->host.num_docs : 0; }
 int leann_cuda_bm25_stats(const leann_cuda_bm25* b, uint64_t* st, float* avg) {
     if (!b || !st) return LEANN_ERR_INVALID_ARG;
-    st[0] = b->host.num_docs; st[1] = b->host.idf.size(); st[2] = b->host.post_doc.size(); st[3] = b->host.total_tokens;
+    st[0] = b->host.num_docs; st[1] = b->host.idf.size(); st[2] = b->host.n_postings; st[3] = b->host.total_tokens;
     if (avg) *avg = b->host.avg_doc_len;
     return LEANN_OK;
 }

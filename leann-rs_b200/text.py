@@ -66,14 +66,14 @@ class Bm25Scorer:
 
     # ---- document-range shards: corpus-wide N / token count / df travel as opaque blobs ----
     @staticmethod
-    def shard_stats(documents: Sequence[str]) -> bytes:
+    def shard_stats(documents: Sequence[str], device: int = 0) -> bytes:
         L = _core().lib()
         keep, arr, lens = _strs(documents)
         need = C.c_size_t()
         e = _err()
-        _check(L.leann_cuda_bm25_shard_stats(arr, lens, len(documents), None, 0, C.byref(need), e, 1024), e)
+        _check(L.leann_cuda_bm25_shard_stats(arr, lens, len(documents), device, None, 0, C.byref(need), e, 1024), e)
         buf = (C.c_ubyte * max(need.value, 1))()
-        _check(L.leann_cuda_bm25_shard_stats(arr, lens, len(documents), buf, need.value, C.byref(need), e, 1024), e)
+        _check(L.leann_cuda_bm25_shard_stats(arr, lens, len(documents), device, buf, need.value, C.byref(need), e, 1024), e)
         return bytes(buf[: need.value])
 
     @staticmethod
