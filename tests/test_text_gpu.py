@@ -212,3 +212,27 @@ def test_sharded_bm25_and_fuse_equal_unsharded(orc, pkg, tmp_path):
         idx, sc, cnt = pkg.hybrid_fuse(vk, vd, vc, k, hybrid, 0.5, cb, mk.view(np.uint64), ms, mc.astype(np.uint32), bx, bn, mask, n)
         ridx, rsc, rcnt = pkg.text.hybrid_search(s, full, q, texts if hybrid else None, k, 64, hybrid, 0.5, mask)
         assert np.array_equal(cnt, rcnt) and np.array_equal(idx, ridx) and np.array_equal(sc.view(np.uint32), rsc.view(np.uint32))
+
+
+def test_gpu_index_build_edge_cases(pkg):
+    """The device tokenizer / index builder against the oracle on awkward inputs: empty and one-letter passages, non-ASCII
+    bytes, mixed case, tokens that straddle the 4096-byte scan chunks, one very long token, an empty corpus."""
+    rng = np.random.default_rng(3)
+    words = ["rust", "Rust", "RUST", "x", "ab", "a1", "42", "é東京", "naïve", "foo_bar", "C++", "zz" * 300]
+    docs = ["", "a", "a b c", "é 東 京", "Rust RUST rust x ab", "ab" + "_" * 4093 + "cd ef", "q" * 4095 + " tail end", "w" * 10000,
+            "x" * 4094 + " ab cd", "ends with token zz", " " * 5000 + "late token"]
+    docs += [" ".join(rng.choice(words, size=int(rng.integers(0, 40)))) for _ in range(300)]
+    docs += ["pad " * 1000 + "needle"]          # > one chunk of ordinary text
+    ref = T.Bm25Scorer(docs)
+    sc = pkg.Bm25Scorer.build(docs)
+    st = sc.stats()
+    assert st["num_docs"] == len(docs)
+    assert st["total_tokens"] == int(sum(ref.doc_lengths)) and st["n_terms"] == len(ref.doc_freq)
+    assert st["n_postings"] == int(sum(ref.doc_freq.values()))
+    assert np.float32(st["avg_doc_len"]).view(np.uint32) == np.float32(ref.avg_doc_len).view(np.uint32)
+    for q in ["rust", "RUST ab", "zz" * 300, "q" * 4095, "w" * 10000, "tail end cd ef", "needle pad", "42 a1", "x", "", "東京", "naïve", "ve na"]:
+        assert np.array_equal(sc.score_query(q).view(np.uint32), ref.score_query_fast(q).view(np.uint32)), q[:20]
+    empty = pkg.Bm25Scorer.build([])
+    assert len(empty) == 0 and empty.search("anything", 3) == []
+    blank = pkg.Bm25Scorer.build(["", " ", "a b"])
+    assert blank.stats()["n_terms"] == 0 and blank.search("a b", 3) == [] and blank.score_query("ab").tolist() == [0.0, 0.0, 0.0]
