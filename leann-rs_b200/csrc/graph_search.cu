@@ -214,7 +214,7 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
         // small rows: the traversal is instruction-latency bound, so favour resident warps over unroll depth
         uint32_t vpl = (d4 + 7) / 8;
         if (vpl <= 2) return launch_t<8, 2, 4, 6>(g, p, stream, op);
-        if (vpl <= 3) return launch_t<8, 3, 4, 5>(g, p, stream, op);
+        if (vpl <= 3) return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
         if (vpl <= 4) return launch_t<8, 4, 4, 4>(g, p, stream, op);
         return launch_t<8, 8, 2, 3>(g, p, stream, op);
     }
