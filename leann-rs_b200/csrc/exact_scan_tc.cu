@@ -436,7 +436,7 @@ CUtensorMap make_map(const void* base, uint64_t rows, uint32_t dp8, uint32_t box
 }  // namespace
 
 bool exact_scan_tc_supported(const FlatView& f, uint32_t nq) {
-    return (f.metric == LEANN_METRIC_DOT_DESC || f.metric == LEANN_METRIC_IP || f.metric == LEANN_METRIC_IP_CLAMP) && nq >= 64 &&
+    return (f.metric == LEANN_METRIC_DOT_DESC || f.metric == LEANN_METRIC_IP || f.metric == LEANN_METRIC_IP_CLAMP) && nq >= 1 &&
            f.d >= 64 && f.n >= 16384;
 }
 

@@ -117,11 +117,13 @@ def test_topk_merge(pkg):
     assert np.array_equal(mk2.cpu().numpy(), mk)
 
 
-# ---- tensor-core path (tcgen05 first pass + fp32 re-rank): n >= 16384, nq >= 64, d >= 64 -----------------
+# ---- tensor-core path (tcgen05 first pass + fp32 re-rank): n >= 16384, d >= 64, any batch size -----------------
 @pytest.mark.parametrize("metric_name,k,d,n,nq", [("dot", 100, 384, 50000, 200), ("dot", 10, 768, 30000, 130), ("ip", 10, 100, 40000, 96),
                                                    ("dot", 1, 64, 20000, 64), ("dot", 1000, 128, 70000, 257),
                                                    # query tile resident up to 7 k-blocks (d <= 448), streamed beyond; ragged query pairs
-                                                   ("dot", 10, 448, 30000, 300), ("ip", 10, 450, 30000, 513), ("dot", 5, 520, 20000, 64)])
+                                                   ("dot", 10, 448, 30000, 300), ("ip", 10, 450, 30000, 513), ("dot", 5, 520, 20000, 64),
+                                                   # single query and a handful: the query tile is mostly TMA zero fill
+                                                   ("dot", 100, 384, 40000, 1), ("ip", 10, 768, 30000, 3), ("dot", 7, 128, 20000, 17)])
 def test_exact_scan_tensor_path_parity(orc, pkg, metric_name, k, d, n, nq):
     x, q = make_data(n, d, 17, nq=nq)
     pm = {"dot": pkg.METRIC_DOT_DESC, "ip": pkg.METRIC_IP}[metric_name]
