@@ -67,6 +67,17 @@ for name, mask in [("hybrid", None)] + [("hybrid+filter " + e, m) for e, m in ma
     dt = sorted(ts)[len(ts) // 2]
     rows.append({"mode": name, "pass_frac": None if mask is None else round(float(np.unpackbits(mask.view(np.uint8)).sum()) / a.n, 4),
                  "ms_per_batch_e2e": round(dt * 1e3, 2), "step_ms": [round(t * 1e3, 1) for t in ts], "qps_e2e": round(a.nq / dt), "mean_results": round(float(cnt.mean()), 2)})
+# small batches: the reference API is one query per call (IndexSearcher::search_with_options)
+small = []
+for m in (1, 16, 128):
+    ts = []
+    for i in range(24):
+        lo = (i * m) % (a.nq - m)
+        t0 = time.time()
+        P.text.hybrid_search(index, bm, q[lo:lo + m], texts[lo:lo + m], a.k, 64, True, 0.5, masks["source:*.rs"])
+        ts.append(time.time() - t0)
+    ts = sorted(ts[4:])
+    small.append({"nq": m, "p50_ms": round(ts[len(ts) // 2] * 1e3, 3), "p90_ms": round(ts[int(len(ts) * 0.9)] * 1e3, 3)})
 # BM25-only batched top-50 (Bm25Scorer::search) and consistency with the dense score_query path
 k3 = []
 for _ in range(4):
@@ -82,5 +93,5 @@ for i in range(16):
     ok &= bi[i, :bc[i]].tolist() == order.tolist() and np.array_equal(bs[i, :bc[i]], dense[order])
 print(json.dumps({"bench": "hybrid", "n": a.n, "nq": a.nq, "k": a.k, "alpha": 0.5, "bm25_stats": st, "corpus_s": round(t_corpus, 1),
                   "bm25_build_s": round(t_bm, 1), "filter_masks_rowwise_s": round(t_mask, 2), "metadata_columns_build_s": round(t_cols, 2), "filter_mask_columnar_ms": t_eval, "hnsw_build_s": round(t_idx, 2),
-                  "bm25_top50_batch_ms": round(t_bm25 * 1e3, 1), "bm25_top50_qps": round(a.nq / t_bm25), "k3_batches": k3,
+                  "bm25_top50_batch_ms": round(t_bm25 * 1e3, 1), "bm25_top50_qps": round(a.nq / t_bm25), "k3_batches": k3, "hybrid_filter_small_batches": small,
                   "dense_vs_topk_consistent": bool(ok), "results": rows}))
