@@ -237,6 +237,36 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
     }
 }
 
+// BM25 score of given (query, document) pairs straight from the postings (bm25_scores.get(idx).unwrap_or(0.0), bm25.rs:160): per
+// document the contributions of the query's tokens are added in token order, starting from 0.0f, exactly like the dense
+// accumulation, so the bits are the same. Lets the vector search and the BM25 top-k kernel run concurrently: neither needs
+// the other's output, only this small kernel and the fusion do.
+__global__ void __launch_bounds__(64)
+bm25_cand_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32_t* __restrict__ qtok_term, uint32_t nq,
+                 const uint64_t* __restrict__ cand_idx, const uint32_t* __restrict__ cand_cnt, uint32_t fk, float* __restrict__ cand_bm) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const uint32_t nc = cand_cnt[q];
+    const uint64_t t0 = qtok_off[q], t1 = qtok_off[q + 1];
+    for (uint32_t j = threadIdx.x; j < fk; j += blockDim.x) {
+        float acc = 0.0f;
+        const uint64_t doc = j < nc ? cand_idx[(size_t)q * fk + j] : ~0ull;
+        if (doc < b.n_docs) {
+            for (uint64_t t = t0; t < t1; ++t) {
+                const uint32_t term = qtok_term[t];
+                uint64_t lo = b.term_off[term], hi = b.term_off[term + 1];
+                const uint64_t end = hi;
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (b.post_doc[mid] < (uint32_t)doc) lo = mid + 1; else hi = mid;
+                }
+                if (lo < end && b.post_doc[lo] == (uint32_t)doc) acc = __fadd_rn(acc, b.post_score[lo]);
+            }
+        }
+        cand_bm[(size_t)q * fk + j] = acc;
+    }
+}
+
 // searcher.rs:146-207 + bm25.rs:135-170 for one query per block.
 __global__ void __launch_bounds__(128)
 hybrid_fuse_kernel(const uint64_t* __restrict__ vkeys, const float* __restrict__ vdists, const uint32_t* __restrict__ vcnt,
@@ -399,6 +429,13 @@ void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_
 }
 
 size_t bm25_max_query_tokens() { return BM_BOUNDS / 2; }
+
+void launch_bm25_candidates(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, const uint64_t* cand_idx,
+                            const uint32_t* cand_cnt, uint32_t fk, float* cand_bm, cudaStream_t s) {
+    if (nq == 0 || fk == 0) return;
+    bm25_cand_kernel<<<nq, 64, 0, s>>>(b, qtok_off, qtok_term, nq, cand_idx, cand_cnt, fk, cand_bm);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
 
 void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, uint32_t fk, const float* cand_bm,
                         const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, uint32_t bm_k,

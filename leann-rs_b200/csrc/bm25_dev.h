@@ -19,6 +19,8 @@ void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_
                        int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
                        float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,
                        uint32_t* qcounter, cudaStream_t s);
+void launch_bm25_candidates(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, const uint64_t* cand_idx,
+                            const uint32_t* cand_cnt, uint32_t fk, float* cand_bm, cudaStream_t s);
 void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32_t* vcnt, uint32_t fk, const float* cand_bm,
                         const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, uint32_t bm_k,
                         const float* bmax, const float* bmin, int hybrid, float alpha, const uint64_t* mask, uint64_t mask_bits,
@@ -51,6 +53,7 @@ struct leann_cuda_bm25 {
     mutable cudaStream_t stream = nullptr;
     // measurement of the last leann_cuda_bm25_search batch: postings its tokens cover, device time of the query kernel
     mutable cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    mutable cudaEvent_t ev_join = nullptr;   // BM25 top-k kernel done (joins the vector search's stream in the hybrid path)
     mutable uint64_t last_postings = 0;
     mutable float last_kernel_ms = 0.0f;
     leann::Bm25Dev view() const { return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_score}; }

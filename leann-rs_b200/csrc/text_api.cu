@@ -175,12 +175,20 @@ void hybrid_search_impl(const leann_cuda_index* ix, const leann_cuda_bm25* bm, c
         qo.reset(new DevBuf(off.size() * 8)); qt.reset(new DevBuf(terms.size() * 4));
         cb.reset(new DevBuf(nq * fk * 4)); bi.reset(new DevBuf(nq * fk * 8)); bs.reset(new DevBuf(nq * fk * 4));
         bc.reset(new DevBuf(nq * 4)); bx.reset(new DevBuf(nq * 4)); bn.reset(new DevBuf(nq * 4));
-        LEANN_CUDA_CHECK(cudaMemcpyAsync(qo->p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
-        if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt->p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
-        LEANN_CUDA_CHECK(cudaStreamSynchronize(s));  // off/terms are stack-owned host vectors
+        // The BM25 top-k kernel runs on the BM25 handle's own stream, concurrently with the vector search on `s`: neither needs
+        // the other's output. The scores of the vector candidates are then read straight from the postings on `s`.
+        cudaStream_t sb = bm->stream;
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(qo->p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, sb));
+        if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt->p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, sb));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(sb));  // off/terms are stack-owned host vectors; nothing else is queued on sb
         launch_bm25_query(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, (uint32_t)fk, bm->n_ctas,
-                          vk.as<uint64_t>(), vc.as<uint32_t>(), (uint32_t)fk, cb->as<float>(), bi->as<uint64_t>(), bs->as<float>(),
-                          bc->as<uint32_t>(), bx->as<float>(), bn->as<float>(), bm->d_qcounter, s);
+                          nullptr, nullptr, (uint32_t)fk, nullptr, bi->as<uint64_t>(), bs->as<float>(),
+                          bc->as<uint32_t>(), bx->as<float>(), bn->as<float>(), bm->d_qcounter, sb);
+        if (!bm->ev_join) LEANN_CUDA_CHECK(cudaEventCreateWithFlags(&bm->ev_join, cudaEventDisableTiming));
+        LEANN_CUDA_CHECK(cudaEventRecord(bm->ev_join, sb));
+        launch_bm25_candidates(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, vk.as<uint64_t>(), vc.as<uint32_t>(),
+                               (uint32_t)fk, cb->as<float>(), s);
+        LEANN_CUDA_CHECK(cudaStreamWaitEvent(s, bm->ev_join, 0));
     }
     launch_hybrid_fuse(vk.as<uint64_t>(), vd.as<float>(), vc.as<uint32_t>(), (uint32_t)fk, hybrid ? cb->as<float>() : nullptr,
                        hybrid ? bi->as<uint64_t>() : nullptr, hybrid ? bs->as<float>() : nullptr,
@@ -331,6 +339,7 @@ void leann_cuda_bm25_free(leann_cuda_bm25* b) {
     cudaFree(b->d_term_off); cudaFree(b->d_post_doc); cudaFree(b->d_post_score);
     cudaFree(b->d_acc); cudaFree(b->d_qcounter);
     if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream) cudaStreamDestroy(b->stream);
     cudaGetLastError();
     if (prev >= 0) cudaSetDevice(prev);
