@@ -143,21 +143,25 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     if (lo >= hi) continue;
                     in_tile += hi - lo;
                     // documents inside one token are distinct: plain shared-memory read-modify-write, 8 postings in flight per thread
-                    uint64_t p = lo + tid;
-                    for (; p + 7 * BM_THREADS < hi; p += 8 * BM_THREADS) {
+                    // 32-bit index inside the slice: one address computation per 8 loads, the rest are immediate offsets
+                    const uint32_t* __restrict__ pd = b.post_doc + lo;
+                    const float* __restrict__ ps = b.post_score + lo;
+                    const uint32_t len = (uint32_t)(hi - lo);
+                    uint32_t i = tid;
+                    for (; i + 7 * BM_THREADS < len; i += 8 * BM_THREADS) {
                         uint32_t d[8]; float sc[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) { d[u] = __ldg(b.post_doc + p + u * BM_THREADS); sc[u] = __ldg(b.post_score + p + u * BM_THREADS); }
+                        for (int u = 0; u < 8; ++u) { d[u] = __ldg(pd + i + u * BM_THREADS); sc[u] = __ldg(ps + i + u * BM_THREADS); }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) acc[d[u] - base] = __fadd_rn(acc[d[u] - base], sc[u]);
                     }
-                    if (p < hi) {   // remainder (and short slices): its loads are issued together as well
+                    if (i < len) {   // remainder (and short slices): its loads are issued together as well
                         uint32_t d[7]; float sc[7];
 #pragma unroll
                         for (int u = 0; u < 7; ++u) {
-                            const bool ok = p + (uint64_t)u * BM_THREADS < hi;
-                            d[u] = ok ? __ldg(b.post_doc + p + u * BM_THREADS) : 0xFFFFFFFFu;
-                            sc[u] = ok ? __ldg(b.post_score + p + u * BM_THREADS) : 0.0f;
+                            const bool ok = i + (uint32_t)u * BM_THREADS < len;
+                            d[u] = ok ? __ldg(pd + i + u * BM_THREADS) : 0xFFFFFFFFu;
+                            sc[u] = ok ? __ldg(ps + i + u * BM_THREADS) : 0.0f;
                         }
 #pragma unroll
                         for (int u = 0; u < 7; ++u)
