@@ -160,3 +160,34 @@ def test_exact_scan_tensor_path_unnormalised_mask_and_sorted(orc, pkg):
     keys, scores, counts = s2.search_batch(qs, 10, 0)
     oi, osc, oc = orc.exact_scan(qs, xs, 10, metric=0, nthreads=8)
     _check_topk(keys, scores, oi, osc, True)
+
+
+def test_randomised_exact_scan_matches_oracle(orc, pkg):
+    """Seeded sweep: sizes on both sides of every path switch (f32 tiles below 16384 rows or d < 64, tensor path with the query
+    tile resident up to d = 448 and streamed beyond), ragged batches, k up to several hundred, all metrics, pre-filter masks,
+    exact duplicate rows (ties resolve by ascending index)."""
+    rng = np.random.default_rng(77)
+    dims = [8, 64, 70, 128, 384, 448, 456, 1000]
+    for trial in range(12):
+        d = int(dims[trial % len(dims)])
+        n = int(rng.choice([150, 5000, 16383, 16384, 40000, 70000]))
+        nq = int(rng.choice([1, 5, 64, 129, 300]))
+        k = int(rng.integers(1, 200))
+        metric_name = ["dot", "ip", "l2"][trial % 3]
+        x, q = make_data(n, d, 300 + trial, nq=nq, normalize=(metric_name != "l2"))
+        x[rng.integers(0, n, size=n // 20)] = x[rng.integers(0, n, size=n // 20)]
+        bits = (rng.random(n) < 0.2) if trial % 4 == 3 else None
+        pm = {"dot": pkg.METRIC_DOT_DESC, "l2": pkg.METRIC_L2SQ, "ip": pkg.METRIC_IP}[metric_name]
+        om = {"dot": 0, "l2": 1, "ip": 2}[metric_name]
+        s = pkg.FlatSearcher.from_vectors(x, metric=pm)
+        keys, scores, counts = s.search_batch(q, k, 0, mask=None if bits is None else pkg.pack_mask(bits))
+        oi, osc, oc = orc.exact_scan(q, x, k, metric=om, mask=None if bits is None else orc.pack_mask(bits), nthreads=8)
+        ctx = (trial, d, n, nq, k, metric_name, bits is not None)
+        assert np.array_equal(counts, oc), ctx
+        valid = np.arange(k)[None, :] < oc[:, None]
+        assert np.array_equal(keys[~valid], oi[~valid]), ctx
+        kk, ss, ok_, os_ = keys.copy(), scores.copy(), oi.copy(), osc.copy()
+        for i in range(nq):                      # compare only the filled part of each row
+            c = int(oc[i])
+            _check_topk(kk[i:i + 1, :c], ss[i:i + 1, :c], ok_[i:i + 1, :c], os_[i:i + 1, :c], metric_name == "dot")
+        s.close()

@@ -182,3 +182,45 @@ def test_small_batch_cta_per_query_matches_pool_and_oracle(orc, pkg, tmp_path):
         mk, md, mc = s.search_batch(q[:50], k, ef, mask=pkg.pack_mask(bits))
         wk, wd, wc, _ = g.search(q[:50], k, ef, lanes=pkg.reduction_lanes(d), mask=pkg.pack_mask(bits), next_cap=pkg.queue_capacity(ef, True))
         assert np.array_equal(mk, wk) and np.array_equal(md.view(np.uint32), wd.view(np.uint32))
+
+
+def test_randomised_configs_match_oracle(orc, pkg, tmp_path):
+    """Seeded sweep over shapes the fixed cases do not hit: odd dimensions on both sides of the 8-lane / 32-lane split, tiny
+    and large degrees, ef below and above the queue sizes, k = 1 .. ef, iid data, exact duplicate vectors (distance ties),
+    batch sizes on both sides of the CTA-per-query / warp-pool switch, inline masks, both backends and all three metrics."""
+    rng = np.random.default_rng(2024)
+    dims = [24, 64, 96, 200, 256, 260, 384, 1000]
+    for trial in range(10):
+        d = int(dims[trial % len(dims)])
+        n = int(rng.integers(600, 4000))
+        nq = int(rng.choice([1, 7, 120, 310, 500]))
+        ef = int(rng.integers(8, 260))
+        k = int(rng.integers(1, min(ef, 40) + 1))
+        x, q = make_data(n, d, 100 + trial, kind="iid" if trial % 3 == 0 else "lowrank", nq=nq, normalize=trial % 4 != 1)
+        dup = rng.integers(0, n, size=n // 10)
+        x[rng.integers(0, n, size=n // 10)] = x[dup]                      # exact duplicates: equal distances
+        mask_bits = (rng.random(n) < 0.35) if trial % 2 else None
+        mask = None if mask_bits is None else pkg.pack_mask(mask_bits)
+        base = str(tmp_path / f"t{trial}.leann")
+        if trial % 2 == 0:
+            M = int(rng.choice([4, 8, 16, 32]))
+            g = orc.Hnsw.build(x, M=M, ef_add=int(rng.integers(16, 80)), seed=trial)
+            g.save(base.replace(".leann", ".index"))
+            s = pkg.HnswSearcher.load(base, d)
+        else:
+            R = int(rng.choice([8, 24, 64]))
+            metric_o, metric_p = [(orc.METRIC_IP_CLAMP, pkg.METRIC_DEFAULT), (orc.METRIC_L2SQ, pkg.METRIC_L2SQ)][trial % 4 == 1]
+            g = orc.Vamana.build(x, R=R, L=int(rng.integers(R, 90)), alpha=1.2, seed=trial, metric=metric_o)
+            g.save(base.replace(".leann", ".diskann"))
+            s = pkg.DiskAnnSearcher.load(base, d, metric=metric_p)
+            g.set_metric(metric_o)
+        cap = pkg.queue_capacity(max(ef, k), mask is not None)
+        ok, od, oc, ost = g.search(q, k, ef, lanes=pkg.reduction_lanes(d), mask=mask, next_cap=cap)
+        keys, dists, counts = s.search_batch(q, k, ef, mask=mask)
+        ctx = (trial, d, n, nq, ef, k, mask is not None)
+        assert np.array_equal(counts, oc), ctx
+        assert np.array_equal(keys, ok), ctx
+        assert np.array_equal(dists.view(np.uint32), od.view(np.uint32)), ctx
+        if mask_bits is not None:
+            valid = keys != np.uint64(2**64 - 1)
+            assert mask_bits[keys[valid].astype(np.int64)].all(), ctx
