@@ -119,6 +119,12 @@ int leann_cuda_search(const leann_cuda_index* index, const float* queries, size_
  * those calls concurrently on one shared searcher (src/cli/serve.rs:84,260-311). With max_batch > 1, calls
  * with nq == 1 (no mask) arriving within max_wait_us of each other are merged into one batched launch; each
  * caller still gets exactly its own result. max_batch <= 1 disables (default). */
+/* Visited set of the graph traversal. By default every resident warp owns a byte map over the n nodes (exact, never cleared);
+ * when n * resident warps would not fit in a third of device memory (tens of millions of short vectors per GPU) the library
+ * switches to per-warp hash tables of about 2 * ef * degree node ids with a small shared pool of byte maps for traversals
+ * that outgrow theirs. capacity 0 = automatic, 1 = byte maps only (fewer warps on large indexes), >= 1024 = force hash
+ * tables of this size (tests use a tiny table to exercise the spill). Results never depend on the choice. */
+int leann_cuda_set_visited_hash(leann_cuda_index* index, size_t capacity);
 int leann_cuda_set_coalescing(leann_cuda_index* index, size_t max_batch, unsigned max_wait_us);
 int leann_cuda_coalescing_stats(const leann_cuda_index* index, uint64_t* batches, uint64_t* requests);
 

@@ -67,6 +67,7 @@ def lib():
         "leann_cuda_search_device": (C.c_int, [vp, vp, sz, sz, sz, vp, C.c_int, vp, vp, vp, vp, vp, cp, sz]),
         "leann_cuda_topk_merge_device": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, vp, vp, vp, vp, cp, sz]),
         "leann_cuda_close": (None, [vp]),
+        "leann_cuda_set_visited_hash": (C.c_int, [vp, sz]),
         "leann_cuda_set_coalescing": (C.c_int, [vp, sz, C.c_uint]),
         "leann_cuda_coalescing_stats": (C.c_int, [vp, u64p, u64p]),
         "leann_cuda_device_count": (C.c_int, []),
@@ -258,6 +259,12 @@ class BackendSearcher:
     def set_coalescing(self, max_batch: int, max_wait_us: int = 200):
         """Merge concurrent single-query `search` calls into batched launches (serve.rs traffic)."""
         lib().leann_cuda_set_coalescing(self._h, max_batch, max_wait_us)
+
+    def set_visited_hash(self, capacity: int):
+        """Visited set of the traversal: 0 auto, 1 byte maps only, >= 1024 force per-warp hash tables of this capacity."""
+        rc = lib().leann_cuda_set_visited_hash(self._h, capacity)
+        if rc != 0:
+            raise LeannCudaError(rc, "invalid visited-hash capacity")
 
     def coalescing_stats(self):
         b, r = C.c_uint64(), C.c_uint64()

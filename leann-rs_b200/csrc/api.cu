@@ -107,7 +107,44 @@ leann_cuda_index* from_vamana(HostVamana& h, int device, int metric) {
     return ix.release();
 }
 
-void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 12) {
+uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+// Large-index mode of the traversal workspace: one byte map per resident warp would not fit (n * warps bytes), so every warp
+// gets a visited hash table sized from ef * degree instead, and a small pool of byte maps serves the traversals that outgrow
+// their table (graph_device.cuh VisitedSet).
+void ensure_workspace_large(const leann_cuda_index* ix, int want, size_t n_pad, size_t budget, size_t ef) {
+    SearchWorkspace& ws = ix->ws;
+    uint32_t cap = ix->vhash_mode >= 1024 ? next_pow2((uint32_t)std::min<size_t>(ix->vhash_mode, (size_t)1 << 22))
+                                         : std::max<uint32_t>(1024u, next_pow2((uint32_t)std::min<size_t>(2 * ef * ix->M0, (size_t)1 << 22)));
+    if (!ws.large_mode || ws.n_pad != n_pad) {   // (re)create the byte-map pool
+        if (ws.visited) cudaFree(ws.visited);
+        if (ws.epochs) cudaFree(ws.epochs);
+        if (ws.pool_locks) cudaFree(ws.pool_locks);
+        ws.visited = nullptr; ws.epochs = nullptr; ws.pool_locks = nullptr; ws.n_warps = 0;
+        uint32_t slots = (uint32_t)std::min<size_t>(64, std::max<size_t>(1, budget / 2 / std::max<size_t>(n_pad, 1)));
+        ws.visited = dalloc<uint8_t>((size_t)slots * n_pad);
+        ws.epochs = dalloc<uint32_t>(slots);
+        ws.pool_locks = dalloc<uint32_t>(slots);
+        LEANN_CUDA_CHECK(cudaMemset(ws.visited, 0, (size_t)slots * n_pad));
+        LEANN_CUDA_CHECK(cudaMemset(ws.epochs, 0, (size_t)slots * 4));
+        LEANN_CUDA_CHECK(cudaMemset(ws.pool_locks, 0, (size_t)slots * 4));
+        ws.pool_slots = slots;
+        ws.n_pad = n_pad;
+        ws.large_mode = true;
+    }
+    if (!ws.counter) ws.counter = dalloc<uint32_t>(1);
+    ws.n_warps = std::max(ws.n_warps, want);
+    const size_t words = (size_t)cap * (size_t)ws.n_warps;
+    if (ws.vhash_words < words) {
+        if (ws.vhash) cudaFree(ws.vhash);
+        ws.vhash = nullptr; ws.vhash_words = 0;
+        ws.vhash = dalloc<uint32_t>(words);
+        ws.vhash_words = words;
+    }
+    ws.vhash_cap = cap;
+}
+
+void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 12, size_t ef = 64) {
     SearchWorkspace& ws = ix->ws;
     if (!ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
     if (ix->backend == LEANN_BACKEND_FLAT) return;
@@ -117,6 +154,20 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
     size_t n_pad = (ix->n + 127) & ~(size_t)127;
     int want = (int)std::min<size_t>((size_t)max_warps, std::max<size_t>(nq, 1));
     want = (want + 3) & ~3;
+    if (ix->vhash_mode != 1) {
+        // byte maps for the full pool of resident warps must fit in a third of device memory, else: large-index mode
+        if (!ws.mem_total) { size_t f = 0; LEANN_CUDA_CHECK(cudaMemGetInfo(&f, &ws.mem_total)); }
+        const size_t budget = ws.mem_total / 3;
+        if (ix->vhash_mode >= 1024 || (size_t)max_warps * n_pad > budget) {
+            ensure_workspace_large(ix, want, n_pad, budget, ef);
+            return;
+        }
+    }
+    if (ws.large_mode) {   // leaving large-index mode (tuning hook): start over with per-warp byte maps
+        if (ws.visited) cudaFree(ws.visited);
+        if (ws.epochs) cudaFree(ws.epochs);
+        ws.visited = nullptr; ws.epochs = nullptr; ws.n_warps = 0; ws.warp_cap = 0; ws.n_pad = 0; ws.large_mode = false;
+    }
     if (ws.n_warps >= want && ws.n_pad == n_pad) return;   // fast path: no driver queries
     if (ws.warp_cap && ws.n_warps >= ws.warp_cap && ws.n_pad == n_pad) return;  // already at the memory-bounded maximum
     // bound the visited workspace to ~1/3 of device memory
@@ -137,8 +188,6 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
     LEANN_CUDA_CHECK(cudaMemset(ws.visited, 0, (size_t)want * n_pad));
     LEANN_CUDA_CHECK(cudaMemset(ws.epochs, 0, (size_t)want * 4));
 }
-
-uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
                         const uint64_t* d_mask, int mask_mode, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
@@ -187,13 +236,16 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
     p.nq = (uint32_t)nq; p.k = (uint32_t)k; p.ef = (uint32_t)eff;
     p.next_cap = (uint32_t)leann_cuda_queue_capacity(eff, d_mask != nullptr);
     p.next_capp = next_pow2(p.next_cap);
-    ensure_workspace(ix, nq, graph_search_warps_per_sm(ix->view(), p.ef, p.next_capp));
+    ensure_workspace(ix, nq, graph_search_warps_per_sm(ix->view(), p.ef, p.next_capp), p.ef);
     p.mask = d_mask;
     p.nonstrict_term = ix->backend == LEANN_BACKEND_VAMANA ? 1 : 0;
     p.out_keys = d_keys; p.out_dists = d_dists; p.out_counts = d_counts; p.out_stats = d_stats;
     p.visited = ix->ws.visited; p.epochs = ix->ws.epochs; p.counter = ix->ws.counter;
     p.n_pad = ix->ws.n_pad;
     p.n_warps = (int)std::min<size_t>((size_t)ix->ws.n_warps, (nq + 3) & ~(size_t)3);
+    p.vhash = ix->ws.large_mode ? ix->ws.vhash : nullptr;
+    p.vhash_cap = ix->ws.large_mode ? ix->ws.vhash_cap : 1024u;
+    p.pool_locks = ix->ws.pool_locks; p.pool_slots = ix->ws.large_mode ? ix->ws.pool_slots : 1u;
     // batches of at most two queries per SM leave most of the machine idle with one warp per query: give each query a CTA
     {
         int sms = 148;
@@ -381,8 +433,17 @@ int leann_cuda_hnsw_add(leann_cuda_index* ix, const float* vectors, int vectors_
         SearchWorkspace& ws = ix->ws;
         if (ws.visited) cudaFree(ws.visited);
         if (ws.epochs) cudaFree(ws.epochs);
-        ws.visited = nullptr; ws.epochs = nullptr; ws.n_warps = 0; ws.warp_cap = 0; ws.n_pad = 0;
+        if (ws.pool_locks) cudaFree(ws.pool_locks);
+        ws.visited = nullptr; ws.epochs = nullptr; ws.pool_locks = nullptr; ws.n_warps = 0; ws.warp_cap = 0; ws.n_pad = 0;
+        ws.large_mode = false;
     });
+}
+
+int leann_cuda_set_visited_hash(leann_cuda_index* ix, size_t capacity) {
+    if (!ix || (capacity > 1 && capacity < 1024)) return LEANN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->vhash_mode = capacity;
+    return LEANN_OK;
 }
 
 int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t n, size_t dims,
@@ -589,7 +650,8 @@ void leann_cuda_close(leann_cuda_index* ix) {
     cudaSetDevice(ix->device);
     cudaFree(ix->vecs); cudaFree(ix->adj0); cudaFree(ix->upper_base); cudaFree(ix->adjU); cudaFree(ix->keys);
     SearchWorkspace& ws = ix->ws;
-    cudaFree(ws.visited); cudaFree(ws.epochs); cudaFree(ws.counter); cudaFree(ws.d_queries); cudaFree(ws.d_keys);
+    cudaFree(ws.visited); cudaFree(ws.epochs); cudaFree(ws.counter); cudaFree(ws.vhash); cudaFree(ws.pool_locks);
+    cudaFree(ws.d_queries); cudaFree(ws.d_keys);
     cudaFree(ws.d_dists); cudaFree(ws.d_counts); cudaFree(ws.d_mask);
     if (ws.stream) cudaStreamDestroy(ws.stream);
     if (ix->scan_pinned) cudaFreeHost(ix->scan_pinned);

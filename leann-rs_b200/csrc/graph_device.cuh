@@ -251,6 +251,90 @@ __device__ __forceinline__ void greedy_descend(const GraphView& g, const float4 
     }
 }
 
+// Epoch handling of the visited byte map: tag in [1,255]; the map is wiped when the tag wraps.
+__device__ __forceinline__ uint8_t next_epoch(uint32_t* epoch_slot, uint8_t* vis, size_t n_pad, int lane) {
+    uint32_t e = *epoch_slot;
+    __syncwarp();
+    if (e != 0 && e % 255u == 0) {
+        uint4* v4 = reinterpret_cast<uint4*>(vis);
+        for (size_t i = lane; i < n_pad / 16; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (lane == 0) *epoch_slot = e + 1;
+    return (uint8_t)(e % 255u + 1u);
+}
+
+
+// Exact visited set of one traversal.
+//  * Byte map in HBM, one epoch tag per node, no clearing between queries: the default, one map per resident warp.
+//  * Large indexes (n * resident warps would not fit in memory): an open-addressing table of node ids per warp, sized
+//    from ef * degree and independent of n, cleared per query. A traversal that outgrows its table (count > limit) takes
+//    one byte map from a small shared pool, replays the table into it and continues there, so the set stays exact for
+//    any query; the pool slot goes back at the end of the query.
+constexpr uint32_t VIS_EMPTY = 0xFFFFFFFFu;
+struct VisitedSet {
+    uint8_t* vis; uint8_t tag; uint32_t* epoch_slot; size_t n_pad;       // byte map in use (own map, or a pool slot after a spill)
+    uint32_t* tbl; uint32_t shift, cap_mask, limit, count; bool hashed;  // hash table (nullptr: byte map only)
+    uint8_t* pool_vis; uint32_t* pool_epochs; uint32_t* pool_locks; uint32_t n_slots; int slot;   // spill pool
+};
+__device__ __forceinline__ void visited_begin(VisitedSet& v, int lane) {
+    v.count = 0;
+    v.slot = -1;
+    v.hashed = v.tbl != nullptr;
+    if (v.hashed) {
+        uint4* t4 = reinterpret_cast<uint4*>(v.tbl);
+        for (uint32_t i = lane; i <= v.cap_mask / 4; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+        __syncwarp();
+    } else {
+        v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
+    }
+}
+// per lane: true when `s` was not in the set (and now is). v.hashed is warp-uniform.
+__device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t s) {
+    if (v.hashed) {
+        uint32_t h = (s * 0x9E3779B1u) >> v.shift;
+        for (;;) {
+            const uint32_t old = atomicCAS(v.tbl + h, VIS_EMPTY, s);
+            if (old == VIS_EMPTY) return true;
+            if (old == s) return false;
+            h = (h + 1u) & v.cap_mask;
+        }
+    }
+    if (v.vis[s] != v.tag) { v.vis[s] = v.tag; return true; }
+    return false;
+}
+// warp: account for `added` new members; when the table passes its limit, move to a pooled byte map
+__device__ __forceinline__ void visited_added(VisitedSet& v, uint32_t added, uint32_t warp_id, int lane) {
+    v.count += added;
+    if (v.hashed && v.count > v.limit) {
+        int slot = 0;
+        if (lane == 0) {
+            uint32_t i = warp_id % v.n_slots;
+            while (atomicCAS(v.pool_locks + i, 0u, 1u) != 0u) { i = (i + 1u) % v.n_slots; __nanosleep(64); }
+            __threadfence();
+            slot = (int)i;
+        }
+        slot = __shfl_sync(FULL, slot, 0);
+        v.slot = slot;
+        v.vis = v.pool_vis + (size_t)slot * v.n_pad;
+        v.epoch_slot = v.pool_epochs + slot;
+        v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
+        for (uint32_t i = lane; i <= v.cap_mask; i += 32) {
+            const uint32_t s = __ldcg(v.tbl + i);
+            if (s != VIS_EMPTY) v.vis[s] = v.tag;
+        }
+        __syncwarp();
+        v.hashed = false;
+    }
+}
+__device__ __forceinline__ void visited_end(VisitedSet& v, int lane) {
+    if (v.slot >= 0) {
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicExch(v.pool_locks + v.slot, 0u); }
+        v.slot = -1;
+    }
+}
+
 // Beam search on one level (usearch search_to_find_in_base_ / search_to_insert_, diskann-rs
 // search_with_dists). radius = worst distance in `top` once it holds `ef` entries, +inf before.
 //   nonstrict == 0 : stop when cand.d >  radius   (usearch)
@@ -259,14 +343,15 @@ __device__ __forceinline__ void greedy_descend(const GraphView& g, const float4 
 template <int LPV, int VPL, int U, bool PREFETCH = false>
 __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL],
                                            WarpLists& w, int ef, int next_cap, int next_mask, int nonstrict,
-                                           const uint64_t* __restrict__ mask, uint8_t* vis, uint8_t tag,
+                                           const uint64_t* __restrict__ mask, VisitedSet& vs, uint32_t warp_id,
                                            uint32_t start, float start_d, Counters& c, int lane,
                                            const Coop cp = Coop{nullptr, 0, 1}) {
     auto passes = [&](uint32_t s) { return mask == nullptr || ((mask[s >> 6] >> (s & 63u)) & 1ull); };
     w.top_size = 0; w.next_size = 0; w.next_head = 0;
     float radius = CUDART_INF_F;
     sorted_insert<true, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, start_d, start, lane);
-    if (lane == 0) vis[start] = tag;
+    if (lane == 0) visited_test_and_set(vs, start);
+    visited_added(vs, 1u, warp_id, lane);
     if (passes(start)) sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, start_d, start, lane);
     if (w.top_size == ef) radius = w.top_d[ef - 1];
     __syncwarp();
@@ -296,13 +381,40 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
                 const uint32_t j = (uint32_t)ch * 32u + lane;
                 sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
             }
+            bool fr[NCH];
+            if (vs.hashed) {
+                // table probes of the whole row run as interleaved CAS chains
+                uint32_t h[NCH];
+                bool act[NCH];
+                bool any = false;
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vis[sv[ch]] : tag;
+                for (int ch = 0; ch < NCH; ++ch) { h[ch] = (sv[ch] * 0x9E3779B1u) >> vs.shift; act[ch] = sv[ch] != SENT; fr[ch] = false; any |= act[ch]; }
+                while (any) {
+                    uint32_t old[NCH];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) if (act[ch]) old[ch] = atomicCAS(vs.tbl + h[ch], VIS_EMPTY, sv[ch]);
+                    any = false;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (act[ch]) {
+                            if (old[ch] == VIS_EMPTY) { fr[ch] = true; act[ch] = false; }
+                            else if (old[ch] == sv[ch]) act[ch] = false;
+                            else { h[ch] = (h[ch] + 1u) & vs.cap_mask; any = true; }
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vs.vis[sv[ch]] : vs.tag;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    fr[ch] = tg[ch] != vs.tag;
+                    if (fr[ch]) vs.vis[sv[ch]] = vs.tag;
+                }
+            }
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 if ((uint32_t)ch * 32u >= adj.deg) break;
-                const bool fresh = tg[ch] != tag;
-                if (fresh) vis[sv[ch]] = tag;
+                const bool fresh = fr[ch];
                 unsigned b = __ballot_sync(FULL, fresh);
                 if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = sv[ch];
                 cnt += __popc(b);
@@ -311,10 +423,7 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
             for (uint32_t base = 0; base < adj.deg; base += 32) {
                 uint32_t j = base + lane;
                 uint32_t s = j < adj.deg ? __ldg(row + j) : SENT;
-                bool fresh = false;
-                if (s != SENT) {
-                    if (vis[s] != tag) { vis[s] = tag; fresh = true; }
-                }
+                const bool fresh = s != SENT && visited_test_and_set(vs, s);
                 unsigned b = __ballot_sync(FULL, fresh);
                 if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = s;
                 cnt += __popc(b);
@@ -322,6 +431,7 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
         }
         __syncwarp();
         c.n_dist += cnt;
+        visited_added(vs, (uint32_t)cnt, warp_id, lane);
         if (PREFETCH) {
             // rows beyond the first register batch are requested from HBM now, so that the later batches of
             // eval_distances find them in L2 (one DRAM latency per hop instead of one per batch)
@@ -354,19 +464,6 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
         }
         __syncwarp();
     }
-}
-
-// Epoch handling of the visited byte map: tag in [1,255]; the map is wiped when the tag wraps.
-__device__ __forceinline__ uint8_t next_epoch(uint32_t* epoch_slot, uint8_t* vis, size_t n_pad, int lane) {
-    uint32_t e = *epoch_slot;
-    __syncwarp();
-    if (e != 0 && e % 255u == 0) {
-        uint4* v4 = reinterpret_cast<uint4*>(vis);
-        for (size_t i = lane; i < n_pad / 16; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
-    if (lane == 0) *epoch_slot = e + 1;
-    return (uint8_t)(e % 255u + 1u);
 }
 
 }  // namespace leann

@@ -32,8 +32,16 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
     w.st_slot = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8);
     w.st_dist = reinterpret_cast<float*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 4);
 
-    uint8_t* vis = p.visited + (size_t)warp_global * p.n_pad;
-    uint32_t* epoch_slot = p.epochs + warp_global;
+    VisitedSet vs;
+    vs.n_pad = p.n_pad;
+    vs.tbl = p.vhash ? p.vhash + (size_t)warp_global * p.vhash_cap : nullptr;
+    vs.cap_mask = p.vhash_cap - 1u;
+    vs.shift = 32u - (uint32_t)__ffs((int)p.vhash_cap) + 1u;
+    vs.limit = p.vhash_cap / 4u * 3u;
+    vs.pool_vis = p.visited; vs.pool_epochs = p.epochs; vs.pool_locks = p.pool_locks; vs.n_slots = p.pool_slots;
+    vs.vis = p.vhash ? nullptr : p.visited + (size_t)warp_global * p.n_pad;
+    vs.epoch_slot = p.vhash ? nullptr : p.epochs + warp_global;
+    vs.tag = 0; vs.slot = -1;
 
     for (;;) {
         uint32_t qi = 0;
@@ -43,7 +51,7 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
 
         float4 q[VPL];
         load_query<LPV, VPL>(p.queries + (size_t)qi * g.d, g.d, q, lane);
-        const uint8_t tag = next_epoch(epoch_slot, vis, p.n_pad, lane);
+        visited_begin(vs, lane);
         Counters c{0u, 0u, 0u, 0u};
 
         // entry point distance
@@ -58,7 +66,8 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
 
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
         beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
-                                p.mask, vis, tag, cur, cur_d, c, lane);
+                                p.mask, vs, (uint32_t)warp_global, cur, cur_d, c, lane);
+        visited_end(vs, lane);
 
         // results: ascending, truncated to k; tail = UINT64_MAX / +inf
         const int cnt = w.top_size < (int)p.k ? w.top_size : (int)p.k;
@@ -106,8 +115,16 @@ graph_search_coop_kernel(const GraphView g, const SearchParams p) {
     w.next_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ef_pad * 8 + (size_t)p.next_capp * 4);
     w.st_slot = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8);
     w.st_dist = reinterpret_cast<float*>(smem_raw + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 4);
-    uint8_t* vis = p.visited + (size_t)blockIdx.x * p.n_pad;
-    uint32_t* epoch_slot = p.epochs + blockIdx.x;
+    VisitedSet vs;
+    vs.n_pad = p.n_pad;
+    vs.tbl = p.vhash ? p.vhash + (size_t)blockIdx.x * p.vhash_cap : nullptr;
+    vs.cap_mask = p.vhash_cap - 1u;
+    vs.shift = 32u - (uint32_t)__ffs((int)p.vhash_cap) + 1u;
+    vs.limit = p.vhash_cap / 4u * 3u;
+    vs.pool_vis = p.visited; vs.pool_epochs = p.epochs; vs.pool_locks = p.pool_locks; vs.n_slots = p.pool_slots;
+    vs.vis = p.vhash ? nullptr : p.visited + (size_t)blockIdx.x * p.n_pad;
+    vs.epoch_slot = p.vhash ? nullptr : p.epochs + blockIdx.x;
+    vs.tag = 0; vs.slot = -1;
     const Coop cp{&s_cmd, warp, COOP_WARPS};
 
     for (;;) {
@@ -122,7 +139,7 @@ graph_search_coop_kernel(const GraphView g, const SearchParams p) {
             coop_serve<LPV, VPL, U>(cp, g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, lane);
             continue;
         }
-        const uint8_t tag = next_epoch(epoch_slot, vis, p.n_pad, lane);
+        visited_begin(vs, lane);
         Counters c{0u, 0u, 0u, 0u};
         uint32_t cur = g.entry;
         if (lane == 0) w.st_slot[0] = cur;
@@ -134,7 +151,8 @@ graph_search_coop_kernel(const GraphView g, const SearchParams p) {
         if (g.max_level > 0) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, 0, c, lane, cp);
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
         beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
-                                            p.mask, vis, tag, cur, cur_d, c, lane, cp);
+                                            p.mask, vs, (uint32_t)blockIdx.x, cur, cur_d, c, lane, cp);
+        visited_end(vs, lane);
         coop_finish(cp, lane);
         const int cnt = w.top_size < (int)p.k ? w.top_size : (int)p.k;
         for (uint32_t i = lane; i < p.k; i += 32) {

@@ -109,8 +109,11 @@ insert_search_kernel(const GraphView g, const BuildParams p) {
     const uint32_t top_cap = (p.ef_add + 31u) & ~31u;
     WarpLists w;
     carve(smem_raw + build_smem_per_warp(top_cap, p.next_capp) * wib, top_cap, p.next_capp, w);
-    uint8_t* vis = p.visited + (size_t)warp_global * p.n_pad;
-    uint32_t* epoch_slot = p.epochs + warp_global;
+    VisitedSet vs{};   // byte map only
+    vs.vis = p.visited + (size_t)warp_global * p.n_pad;
+    vs.epoch_slot = p.epochs + warp_global;
+    vs.n_pad = p.n_pad;
+    vs.slot = -1;
 
     for (;;) {
         uint32_t bi = 0;
@@ -139,10 +142,10 @@ insert_search_kernel(const GraphView g, const BuildParams p) {
         if (g.max_level > node_level) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, node_level, c, lane);
         const int top_level = node_level < g.max_level ? node_level : g.max_level;
         for (int level = top_level; level >= 0; --level) {
-            const uint8_t tag = next_epoch(epoch_slot, vis, p.n_pad, lane);
+            visited_begin(vs, lane);
             LevelAdj adj{g.adj0, g.adjU, g.upper_base, level == 0 ? g.deg0 : g.degU, level};
             beam_level<LPV, VPL, U>(g, adj, q, w, (int)p.ef_add, (int)p.next_cap, (int)p.next_capp - 1, 0, nullptr,
-                                    vis, tag, cur, cur_d, c, lane);
+                                    vs, (uint32_t)warp_global, cur, cur_d, c, lane);
             int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)p.M, lane, p.vamana, p.alpha);
             // forward links of the new node (its rows are pre-filled with SENT)
             uint32_t* myrow = level == 0 ? p.adj0 + (size_t)node * p.M0

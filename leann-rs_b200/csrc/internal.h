@@ -79,6 +79,11 @@ struct SearchWorkspace {
     uint8_t* visited = nullptr;  // [n_warps][n_pad] epoch tags
     uint32_t* epochs = nullptr;  // [n_warps]
     uint32_t* counter = nullptr; // dynamic query scheduler
+    // large-index mode: visited hash tables [n_warps][vhash_cap]; `visited` / `epochs` then hold a small pool of byte maps
+    uint32_t* vhash = nullptr; size_t vhash_words = 0; uint32_t vhash_cap = 0;
+    uint32_t* pool_locks = nullptr; uint32_t pool_slots = 0;
+    bool large_mode = false;
+    size_t mem_total = 0;        // device memory size (queried once)
     int n_warps = 0;
     int warp_cap = 0;            // memory-bounded maximum pool size (0 = not computed yet)
     size_t n_pad = 0;
@@ -97,6 +102,8 @@ struct SearchParams {
     uint8_t* visited; uint32_t* epochs; uint32_t* counter;
     size_t n_pad;
     int n_warps;
+    uint32_t* vhash; uint32_t vhash_cap;              // nullable: per-warp visited hash tables (large-index mode)
+    uint32_t* pool_locks; uint32_t pool_slots;        // byte-map spill pool of the large-index mode (maps in `visited`)
     int coop_warps;  // 4 or 8 warps per CTA of the small-batch kernel
     int coop_ctas;   // > 0: small batch, launch this many multi-warp CTAs (one query each at a time) instead of the warp pool
 };
@@ -176,6 +183,7 @@ struct leann_cuda_index {
     mutable bool tc_disabled = false;
     mutable leann::Coalescer coalescer;
     bool coop_small_batches = true;   // CTA-per-query kernel for nq <= 2 per SM
+    size_t vhash_mode = 0;   // visited set: 0 auto (byte maps unless they would not fit), 1 byte maps only, >= 1024 force hash tables of this capacity
     leann::GraphView view() const {
         leann::GraphView g;
         g.vecs = vecs; g.adj0 = adj0; g.upper_base = upper_base; g.adjU = adjU;

@@ -224,3 +224,33 @@ def test_randomised_configs_match_oracle(orc, pkg, tmp_path):
         if mask_bits is not None:
             valid = keys != np.uint64(2**64 - 1)
             assert mask_bits[keys[valid].astype(np.int64)].all(), ctx
+
+
+def test_visited_set_modes_are_equivalent(orc, pkg, tmp_path):
+    """The traversal's exact visited set has two representations: per-warp byte maps (default) and, for indexes whose byte
+    maps would not fit, per-warp hash tables with a pooled byte-map spill. Forced through the tuning hook on a small index:
+    a tiny table (every traversal spills through the pool), a roomy table, byte maps only — all must reproduce the oracle
+    (ids, distance bits, work counters), for the warp pool and the CTA-per-query kernel, short and long rows."""
+    import torch
+    for d in (96, 768):
+        n, k = 30000, 10
+        x, q = make_data(n, d, 19, nq=500, normalize=False)
+        base = str(tmp_path / f"v{d}.leann")
+        pkg.DiskAnnSearcher.build(x, graph_degree=64, complexity=100, metric=pkg.METRIC_L2SQ).save(base)   # CPU build of this size is slow
+        g = orc.Vamana.load(base.replace(".leann", ".diskann"))
+        g.set_metric(orc.METRIC_L2SQ)
+        s = pkg.DiskAnnSearcher.load(base, d, metric=pkg.METRIC_L2SQ)
+        qt = torch.from_numpy(q).cuda()
+        for ef in (32, 200):
+            ok, od, oc, ost = g.search(q, k, ef, lanes=pkg.reduction_lanes(d), next_cap=pkg.queue_capacity(ef, False))
+            for mode in (0, 1024, 1, 65536):
+                s.set_visited_hash(mode)
+                for lo, hi in ((0, 500), (0, 40)):            # warp pool, CTA per query
+                    stats = torch.zeros((hi - lo, 4), dtype=torch.int64, device="cuda")
+                    keys, dists, counts = s.search_device(qt[lo:hi].contiguous(), k, ef, stats=stats)
+                    assert np.array_equal(keys.cpu().numpy().view(np.uint64), ok[lo:hi]), (d, ef, mode, hi)
+                    assert np.array_equal(dists.cpu().numpy().view(np.uint32), od[lo:hi].view(np.uint32)), (d, ef, mode, hi)
+                    assert np.array_equal(stats.cpu().numpy()[:, :3], ost[lo:hi, :3].astype(np.int64)), (d, ef, mode, hi)
+        assert ost[:, 0].max() > 768          # the 1024-slot tables did have to spill
+        with pytest.raises(pkg.LeannCudaError):
+            s.set_visited_hash(100)
