@@ -15,6 +15,7 @@
 // follows usearch index_gt::add. Level assignment: floor(-ln(U) / ln(M)) as in usearch.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <random>
 
 #include "graph_device.cuh"
@@ -39,6 +40,7 @@ struct BuildParams {
     uint32_t M, M0, ef_add, n;
     uint32_t next_cap, next_capp;
     uint8_t* visited; uint32_t* epochs; uint32_t* counter; size_t n_pad; int n_warps;
+    uint32_t* vhash; uint32_t vhash_cap; uint32_t* pool_locks; uint32_t pool_slots;   // large-index mode (see VisitedSet)
     uint32_t* overflow;  // [0]: edge buffer overflow, [1]: extra overflow (dropped links)
     const uint32_t* order;  // nullable: insertion sequence (node = order[first + i]); identity when null
     int vamana; float alpha;
@@ -109,11 +111,19 @@ insert_search_kernel(const GraphView g, const BuildParams p) {
     const uint32_t top_cap = (p.ef_add + 31u) & ~31u;
     WarpLists w;
     carve(smem_raw + build_smem_per_warp(top_cap, p.next_capp) * wib, top_cap, p.next_capp, w);
-    VisitedSet vs{};   // byte map only
-    vs.vis = p.visited + (size_t)warp_global * p.n_pad;
-    vs.epoch_slot = p.epochs + warp_global;
+    VisitedSet vs{};
     vs.n_pad = p.n_pad;
     vs.slot = -1;
+    if (p.vhash) {   // large-index mode: per-warp hash table, pooled byte maps for the spill
+        vs.tbl = p.vhash + (size_t)warp_global * p.vhash_cap;
+        vs.cap_mask = p.vhash_cap - 1u;
+        vs.shift = 32u - (uint32_t)__ffs((int)p.vhash_cap) + 1u;
+        vs.limit = p.vhash_cap / 4u * 3u;
+        vs.pool_vis = p.visited; vs.pool_epochs = p.epochs; vs.pool_locks = p.pool_locks; vs.n_slots = p.pool_slots;
+    } else {
+        vs.vis = p.visited + (size_t)warp_global * p.n_pad;
+        vs.epoch_slot = p.epochs + warp_global;
+    }
 
     for (;;) {
         uint32_t bi = 0;
@@ -146,6 +156,7 @@ insert_search_kernel(const GraphView g, const BuildParams p) {
             LevelAdj adj{g.adj0, g.adjU, g.upper_base, level == 0 ? g.deg0 : g.degU, level};
             beam_level<LPV, VPL, U>(g, adj, q, w, (int)p.ef_add, (int)p.next_cap, (int)p.next_capp - 1, 0, nullptr,
                                     vs, (uint32_t)warp_global, cur, cur_d, c, lane);
+            visited_end(vs, lane);
             int kept = refine_heuristic<LPV, VPL, U>(g, w, (int)p.M, lane, p.vamana, p.alpha);
             // forward links of the new node (its rows are pre-filled with SENT)
             uint32_t* myrow = level == 0 ? p.adj0 + (size_t)node * p.M0
@@ -297,6 +308,37 @@ T* dmalloc(size_t count) {
     return p;
 }
 
+// Visited workspace of the builders: one byte map per warp when that fits in a quarter of the free memory, else per-warp
+// hash tables of 2 * ef_add * degree ids with a pool of byte maps for the spill (the traversal's large-index mode).
+void alloc_build_visited(BuildParams& p, int& max_warps, uint32_t MAXB, size_t n, uint32_t ef_add, uint32_t deg, std::vector<void*>& temps,
+                         cudaStream_t stream) {
+    p.n_pad = (n + 127) & ~(size_t)127;
+    size_t free_b = 0, total_b = 0;
+    LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    max_warps = (int)std::min<size_t>((size_t)max_warps, (size_t)MAXB);
+    p.vhash = nullptr; p.vhash_cap = 1024; p.pool_locks = nullptr; p.pool_slots = 1;
+    const bool force_large = getenv("LEANN_CUDA_FORCE_LARGE_INDEX_MODE") != nullptr;   // test hook: exercise the large-index mode on small data
+    if (!force_large && (size_t)max_warps * p.n_pad <= free_b / 4) {
+        p.visited = dmalloc<uint8_t>((size_t)max_warps * p.n_pad); temps.push_back(p.visited);
+        p.epochs = dmalloc<uint32_t>(max_warps); temps.push_back(p.epochs);
+        LEANN_CUDA_CHECK(cudaMemsetAsync(p.visited, 0, (size_t)max_warps * p.n_pad, stream));
+        LEANN_CUDA_CHECK(cudaMemsetAsync(p.epochs, 0, (size_t)max_warps * 4, stream));
+        return;
+    }
+    uint32_t cap = 1024;
+    while (cap < 2u * ef_add * deg && cap < (1u << 22)) cap <<= 1;
+    const uint32_t slots = (uint32_t)std::min<size_t>(64, std::max<size_t>(1, free_b / 8 / p.n_pad));
+    p.vhash = dmalloc<uint32_t>((size_t)max_warps * cap); temps.push_back(p.vhash);
+    p.vhash_cap = cap;
+    p.visited = dmalloc<uint8_t>((size_t)slots * p.n_pad); temps.push_back(p.visited);
+    p.epochs = dmalloc<uint32_t>(slots); temps.push_back(p.epochs);
+    p.pool_locks = dmalloc<uint32_t>(slots); temps.push_back(p.pool_locks);
+    p.pool_slots = slots;
+    LEANN_CUDA_CHECK(cudaMemsetAsync(p.visited, 0, (size_t)slots * p.n_pad, stream));
+    LEANN_CUDA_CHECK(cudaMemsetAsync(p.epochs, 0, (size_t)slots * 4, stream));
+    LEANN_CUDA_CHECK(cudaMemsetAsync(p.pool_locks, 0, (size_t)slots * 4, stream));
+}
+
 }  // namespace
 
 namespace {
@@ -364,17 +406,7 @@ void insert_range(leann_cuda_index* ix, const std::vector<uint8_t>& lv8, size_t 
         p.next_capp = 1; while (p.next_capp < p.next_cap) p.next_capp <<= 1;
         p.order = nullptr; p.vamana = 0; p.alpha = 1.0f;
         int max_warps = graph_search_max_warps(ix->device);
-        p.n_pad = (n + 127) & ~(size_t)127;
-        {
-            size_t free_b = 0, total_b = 0;
-            LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-            while (max_warps > 64 && (size_t)max_warps * p.n_pad > free_b / 4) max_warps /= 2;
-        }
-        max_warps = (int)std::min<size_t>((size_t)max_warps, (size_t)MAXB);
-        p.visited = dmalloc<uint8_t>((size_t)max_warps * p.n_pad); temps.push_back(p.visited);
-        p.epochs = dmalloc<uint32_t>(max_warps); temps.push_back(p.epochs);
-        LEANN_CUDA_CHECK(cudaMemsetAsync(p.visited, 0, (size_t)max_warps * p.n_pad, stream));
-        LEANN_CUDA_CHECK(cudaMemsetAsync(p.epochs, 0, (size_t)max_warps * 4, stream));
+        alloc_build_visited(p, max_warps, MAXB, n, p.ef_add, (uint32_t)M0, temps, stream);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
 
@@ -589,17 +621,7 @@ void gpu_vamana_build(leann_cuda_index* ix, size_t R, size_t L, float alpha, uin
         p.next_capp = 1; while (p.next_capp < p.next_cap) p.next_capp <<= 1;
         p.order = d_order; p.vamana = 1; p.alpha = alpha;
         int max_warps = graph_search_max_warps(ix->device);
-        p.n_pad = (n + 127) & ~(size_t)127;
-        {
-            size_t free_b = 0, total_b = 0;
-            LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-            while (max_warps > 64 && (size_t)max_warps * p.n_pad > free_b / 4) max_warps /= 2;
-        }
-        max_warps = (int)std::min<size_t>((size_t)max_warps, (size_t)MAXB);
-        p.visited = dmalloc<uint8_t>((size_t)max_warps * p.n_pad); temps.push_back(p.visited);
-        p.epochs = dmalloc<uint32_t>(max_warps); temps.push_back(p.epochs);
-        LEANN_CUDA_CHECK(cudaMemset(p.visited, 0, (size_t)max_warps * p.n_pad));
-        LEANN_CUDA_CHECK(cudaMemset(p.epochs, 0, (size_t)max_warps * 4));
+        alloc_build_visited(p, max_warps, MAXB, n, p.ef_add, (uint32_t)R, temps, stream);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
         ix->entry = medoid;  // searches during the build start from the medoid, as they will afterwards
