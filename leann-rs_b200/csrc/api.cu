@@ -179,14 +179,37 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
     want = std::min(want, max_warps);
     if (ws.visited) cudaFree(ws.visited);
     if (ws.epochs) cudaFree(ws.epochs);
+    if (ws.pool_locks) cudaFree(ws.pool_locks);
     if (!ws.counter) ws.counter = dalloc<uint32_t>(1);
     // allocate for the full pool once a large batch has been seen, else just what is needed
     ws.n_warps = want;
     ws.n_pad = n_pad;
     ws.visited = dalloc<uint8_t>((size_t)want * n_pad);
     ws.epochs = dalloc<uint32_t>(want);
+    ws.pool_locks = dalloc<uint32_t>(want);   // the per-warp maps double as the spill pool of the L2-resident hash mode
+    ws.pool_slots = (uint32_t)want;
     LEANN_CUDA_CHECK(cudaMemset(ws.visited, 0, (size_t)want * n_pad));
     LEANN_CUDA_CHECK(cudaMemset(ws.epochs, 0, (size_t)want * 4));
+    LEANN_CUDA_CHECK(cudaMemset(ws.pool_locks, 0, (size_t)want * 4));
+}
+
+// Small traversals on long rows: hash tables of 8192 ids for all resident warps stay in L2 (<= 64 MB), which measured 4-6 %
+// faster than the byte maps (no DRAM traffic for the visited set). Chosen only when the expected number of visited nodes
+// (about 0.7 * ef * degree) leaves the table under 40 % full, so spills into the byte maps stay exceptional.
+constexpr uint32_t L2_HASH_CAP = 8192;
+bool prefer_l2_hash(const leann_cuda_index* ix, size_t ef) {
+    const SearchWorkspace& ws = ix->ws;
+    return ix->vhash_mode == 0 && !ws.large_mode && ws.n_warps > 0 && (size_t)ws.n_warps * L2_HASH_CAP * 4 <= ((size_t)64 << 20) &&
+           7 * ef * ix->M0 <= 4 * (size_t)L2_HASH_CAP;
+}
+void ensure_l2_hash(const leann_cuda_index* ix) {
+    SearchWorkspace& ws = ix->ws;
+    const size_t words = (size_t)ws.n_warps * L2_HASH_CAP;
+    if (ws.vhash_words >= words) return;
+    if (ws.vhash) cudaFree(ws.vhash);
+    ws.vhash = nullptr; ws.vhash_words = 0;
+    ws.vhash = dalloc<uint32_t>(words);
+    ws.vhash_words = words;
 }
 
 void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
@@ -245,13 +268,18 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
     p.n_warps = (int)std::min<size_t>((size_t)ix->ws.n_warps, (nq + 3) & ~(size_t)3);
     p.vhash = ix->ws.large_mode ? ix->ws.vhash : nullptr;
     p.vhash_cap = ix->ws.large_mode ? ix->ws.vhash_cap : 1024u;
-    p.pool_locks = ix->ws.pool_locks; p.pool_slots = ix->ws.large_mode ? ix->ws.pool_slots : 1u;
+    p.pool_locks = ix->ws.pool_locks; p.pool_slots = std::max<uint32_t>(ix->ws.pool_slots, 1u);
     // batches of at most two queries per SM leave most of the machine idle with one warp per query: give each query a CTA
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
         p.coop_ctas = (nq <= (size_t)sms * 2 && ix->coop_small_batches) ? (int)std::min<size_t>(nq, (size_t)ix->ws.n_warps) : 0;
         p.coop_warps = nq <= (size_t)sms ? 8 : 4;
+    }
+    // throughput batches only: a latency-bound single traversal pays more for the CAS round trips than it saves (measured +20 %)
+    if (p.coop_ctas == 0 && prefer_l2_hash(ix, p.ef)) {
+        ensure_l2_hash(ix);
+        p.vhash = ix->ws.vhash; p.vhash_cap = L2_HASH_CAP;
     }
     launch_graph_search(ix->view(), p, stream);
 }
