@@ -254,3 +254,27 @@ def test_visited_set_modes_are_equivalent(orc, pkg, tmp_path):
         assert ost[:, 0].max() > 768          # the 1024-slot tables did have to spill
         with pytest.raises(pkg.LeannCudaError):
             s.set_visited_hash(100)
+
+
+def test_handmade_index_hand_traced_on_gpu(pkg, tmp_path):
+    """The hand-traced known answers of tests/handmade.py (file written byte by byte from the published usearch layout,
+    search traced by hand from the published loop) through the product: reader, descent, beam, counters."""
+    import torch
+    import handmade as H
+    vecs, keys, levels, adj, q = H.ring_case()
+    base = str(tmp_path / "ring.leann")
+    H.write_usearch_index(base.replace(".leann", ".index"), vecs, keys, levels, adj, M=2, M0=4, entry=0, max_level=1)
+    s = pkg.HnswSearcher.load(base, 2)
+    assert len(s) == 8 and s.info()["max_level"] == 1
+    qt = torch.from_numpy(np.repeat(q, 400, axis=0)).cuda()       # 400 copies: warp-pool kernel; 1 copy: CTA-per-query kernel
+    for ef, k, exp in ((2, 2, H.EXPECT_EF2), (1, 1, H.EXPECT_EF1)):
+        for nq in (400, 1):
+            st = torch.zeros((nq, 4), dtype=torch.int64, device="cuda")
+            kk, dd, cc = s.search_device(qt[:nq].contiguous(), k, ef, stats=st)
+            assert kk.cpu().numpy()[0].tolist() == exp["keys"] and (kk == kk[0]).all()
+            assert st.cpu().numpy()[0, :3].tolist() == [exp["n_dist"], exp["hops0"], exp["hops_upper"]]
+            want = 1.0 - np.cos(np.deg2rad(70.0 - 10.0 * (np.array(exp["keys"]) - 100)))
+            assert np.allclose(dd.cpu().numpy()[0], want, atol=1e-6)
+    # the trait call (hnsw.rs:79-88): complexity ignored, ef = max(64, k) -> every node is reached, nearest first
+    keys5, dists5 = s.search(q[0], 5, 1)
+    assert keys5 == [107, 106, 105, 104, 103]

@@ -175,3 +175,21 @@ def test_abi_open_error_paths(pkg, orc, small, tmp_path):
         with pytest.raises(pkg.LeannCudaError) as e:
             pkg.HnswSearcher.load(base, 96)
         assert e.value.code == pkg.ERR_CUDA and "no CPU fallback" in e.value.message
+
+
+def test_handmade_index_and_hand_traced_search(orc, tmp_path):
+    """Known-answer test derived by hand from the published usearch loop on a file written byte by byte from the published
+    layout (tests/handmade.py): pins the reader, the greedy descent, the level-0 beam, the bounded `top` and the counters."""
+    import handmade as H
+    vecs, keys, levels, adj, q = H.ring_case()
+    path = str(tmp_path / "ring.index")
+    H.write_usearch_index(path, vecs, keys, levels, adj, M=2, M0=4, entry=0, max_level=1)
+    g = orc.Hnsw.load(path, 2)
+    assert g.info()["n"] == 8 and g.info()["max_level"] == 1 and g.info()["entry"] == 0
+    for ef, k, exp in ((2, 2, H.EXPECT_EF2), (1, 1, H.EXPECT_EF1)):
+        for cap in (0, ef):                          # unbounded heap and the kernel's bounded queue
+            kk, dd, cc, st = g.search(q, k, ef, next_cap=cap)
+            assert kk[0].tolist() == exp["keys"] and int(cc[0]) == k
+            assert (int(st[0, 0]), int(st[0, 1]), int(st[0, 2])) == (exp["n_dist"], exp["hops0"], exp["hops_upper"])
+            want = 1.0 - np.cos(np.deg2rad(70.0 - 10.0 * (np.array(exp["keys"]) - 100)))
+            assert np.allclose(dd[0], want, atol=1e-6)
