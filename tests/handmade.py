@@ -61,3 +61,31 @@ EXPECT_EF2 = {"keys": [107, 106], "n_dist": 8, "hops0": 5, "hops_upper": 2}
 #   ef = 1 (k = 1): top = [3]; pop 3: 2: top full, d(2) > d(3) -> rejected; 4: d(4) < d(3) -> top = [4]; pop 4 -> 5; pop 5 -> 6; pop 6 -> 7;
 #   pop 7: nothing; next empty -> stop. hops 3,4,5,6,7 = 5; evaluations 2,4,5,6,7 = 5 -> n_dist = 8
 EXPECT_EF1 = {"keys": [107], "n_dist": 8, "hops0": 5, "hops_upper": 2}
+
+
+def write_diskann(path, vecs, adj, R, medoid, name=b"DistDot"):
+    """diskann-rs single-file layout: u64 metadata length, bincode metadata
+    {dim, n, max_degree u64; medoid u32; vectors_offset, adjacency_offset u64; distance name (u64 length + bytes)},
+    vectors, fixed-degree adjacency padded with u32::MAX."""
+    n, d = vecs.shape
+    meta_len = 52 + len(name)
+    voff = 8 + meta_len
+    aoff = voff + n * d * 4
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", meta_len))
+        f.write(struct.pack("<QQQIQQQ", d, n, R, medoid, voff, aoff, len(name)) + name)
+        f.write(np.ascontiguousarray(vecs, dtype="<f4").tobytes())
+        for i in range(n):
+            nb = list(adj[i])
+            f.write(np.asarray(nb + [0xFFFFFFFF] * (R - len(nb)), dtype="<u4").tobytes())
+
+
+# Hand trace of diskann-rs search_with_dists (Appendix A.3) on the chain 0-1-...-7 of ring_case (level-0 lists only, R = 2,
+# medoid 0), query at 70 degrees, beam L = max(complexity, k):
+#   L = 2: results = {0}; pop 0 (results not full): 1 is new, results = {0,1}; pop 1: full, d(1) < worst = d(0): go on;
+#          2 new, d(2) < d(0): results {0,1,2} -> drop worst -> {1,2}; ... each pop i reveals i+1 which replaces i-1 ...
+#          pop 7: d(7) < worst = d(6): go on; its only neighbour 6 is visited; queue empty -> stop.
+#          pops 0..7 = 8 hops, evaluations medoid + 1..7 = 8, answer [7, 6].
+VAMANA_L2 = {"keys": [7, 6], "n_dist": 8, "hops0": 8}
+#   L = 1: results = {0} is full at once; first pop: d(0) >= worst = d(0) -> the non-strict stop rule ends the search at the medoid.
+VAMANA_L1 = {"keys": [0], "n_dist": 1, "hops0": 0}

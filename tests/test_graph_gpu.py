@@ -278,3 +278,24 @@ def test_handmade_index_hand_traced_on_gpu(pkg, tmp_path):
     # the trait call (hnsw.rs:79-88): complexity ignored, ef = max(64, k) -> every node is reached, nearest first
     keys5, dists5 = s.search(q[0], 5, 1)
     assert keys5 == [107, 106, 105, 104, 103]
+
+
+def test_handmade_diskann_hand_traced_on_gpu(pkg, tmp_path):
+    """Hand-written `.diskann` file + hand-traced diskann-rs beam search (tests/handmade.py) through the product."""
+    import torch
+    import handmade as H
+    vecs, keys, levels, adj, q = H.ring_case()
+    base = str(tmp_path / "ring.leann")
+    H.write_diskann(base.replace(".leann", ".diskann"), vecs, [a[0] for a in adj], R=2, medoid=0)
+    s = pkg.DiskAnnSearcher.load(base, 2)
+    assert len(s) == 8
+    qt = torch.from_numpy(np.repeat(q, 400, axis=0)).cuda()
+    for L, k, exp in ((2, 2, H.VAMANA_L2), (1, 1, H.VAMANA_L1)):
+        for nq in (400, 1):
+            st = torch.zeros((nq, 4), dtype=torch.int64, device="cuda")
+            kk, dd, cc = s.search_device(qt[:nq].contiguous(), k, L, stats=st)
+            assert kk.cpu().numpy()[0].tolist() == exp["keys"] and (kk == kk[0]).all()
+            assert st.cpu().numpy()[0, :2].tolist() == [exp["n_dist"], exp["hops0"]]
+    # trait call (diskann.rs:47-62): beam = max(complexity, top_k)
+    k3, d3 = s.search(q[0], 3, 1)
+    assert k3 == [7, 6, 5]

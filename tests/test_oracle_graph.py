@@ -193,3 +193,19 @@ def test_handmade_index_and_hand_traced_search(orc, tmp_path):
             assert (int(st[0, 0]), int(st[0, 1]), int(st[0, 2])) == (exp["n_dist"], exp["hops0"], exp["hops_upper"])
             want = 1.0 - np.cos(np.deg2rad(70.0 - 10.0 * (np.array(exp["keys"]) - 100)))
             assert np.allclose(dd[0], want, atol=1e-6)
+
+
+def test_handmade_diskann_file_and_hand_traced_search(orc, tmp_path):
+    import handmade as H
+    vecs, keys, levels, adj, q = H.ring_case()
+    path = str(tmp_path / "ring.diskann")
+    H.write_diskann(path, vecs, [a[0] for a in adj], R=2, medoid=0)
+    g = orc.Vamana.load(path)
+    assert g.info() == {"n": 8, "d": 2, "R": 2, "medoid": 0}
+    for L, k, exp in ((2, 2, H.VAMANA_L2), (1, 1, H.VAMANA_L1)):
+        for cap in (0, L):
+            kk, dd, cc, st = g.search(q, k, L, next_cap=cap)
+            assert kk[0].tolist() == exp["keys"], (L, kk)
+            assert (int(st[0, 0]), int(st[0, 1])) == (exp["n_dist"], exp["hops0"]), (L, st[0])
+            want = np.maximum(0.0, 1.0 - np.cos(np.deg2rad(70.0 - 10.0 * np.array(exp["keys"]))))
+            assert np.allclose(dd[0], want, atol=1e-6)
