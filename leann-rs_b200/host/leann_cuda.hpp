@@ -4,6 +4,8 @@
 //   trait BackendSearcher                 src/backend/traits.rs:11-30
 //   HnswSearcher / DiskAnnSearcher        src/backend/hnsw.rs:12-93, src/backend/diskann.rs:12-66
 //   BackendType::load_searcher            src/backend/mod.rs:16-45
+//   hnsw::{build_index, add_to_index}     src/backend/hnsw.rs:96-191
+//   diskann::build_index                  src/backend/diskann.rs:70-105
 //   Bm25Scorer, hybrid_rerank             src/index/bm25.rs:17-170
 //   MetadataFilter                        src/index/filter.rs:35-39,52-134,319-325
 //   SearchOptions, IndexSearcher          src/index/searcher.rs:25-63,66-257
@@ -108,6 +110,59 @@ inline std::unique_ptr<BackendSearcher> load_searcher(BackendType t, const std::
     return DiskAnnSearcher::load(index_path, dimensions, device);
 }
 
+// ---- src/backend/hnsw.rs:96-191, src/backend/diskann.rs:70-105 -----------------------------------------
+namespace detail {
+inline std::vector<float> flatten(const std::vector<std::vector<float>>& embeddings, size_t dimensions) {
+    std::vector<float> flat;
+    flat.reserve(embeddings.size() * dimensions);
+    for (auto& e : embeddings) {
+        if (e.size() != dimensions) throw Error(LEANN_ERR_DIM_MISMATCH, "Dimension mismatch: expected " + std::to_string(dimensions) + ", got " + std::to_string(e.size()));
+        flat.insert(flat.end(), e.begin(), e.end());
+    }
+    return flat;
+}
+struct IndexHandle {   // closes on scope exit
+    leann_cuda_index* h = nullptr;
+    ~IndexHandle() { if (h) leann_cuda_close(h); }
+};
+}  // namespace detail
+
+namespace hnsw {
+/// hnsw.rs:96-139: same arguments, writes `<index_path>.index` (with_extension("index")).
+inline void build_index(const std::vector<std::vector<float>>& embeddings, const std::vector<std::string>& /*ids*/, const std::string& index_path,
+                        size_t dimensions, size_t graph_degree, size_t complexity, int device = 0) {
+    auto flat = detail::flatten(embeddings, dimensions);
+    detail::IndexHandle ix;
+    char err[1024];
+    check(leann_cuda_hnsw_build(flat.data(), 0, embeddings.size(), dimensions, graph_degree, complexity, LEANN_METRIC_DEFAULT, 1, device, &ix.h, err,
+                                sizeof err), err);
+    check(leann_cuda_save(ix.h, index_path.c_str(), err, sizeof err), err);
+}
+/// hnsw.rs:142-191: load, append with keys start_id.., save back (connectivity from the file, expansion_add 64).
+inline void add_to_index(const std::vector<std::vector<float>>& embeddings, const std::string& index_path, size_t dimensions, size_t start_id,
+                         int device = 0) {
+    auto flat = detail::flatten(embeddings, dimensions);
+    detail::IndexHandle ix;
+    char err[1024];
+    check(leann_cuda_open(index_path.c_str(), LEANN_BACKEND_HNSW, dimensions, LEANN_METRIC_DEFAULT, device, &ix.h, err, sizeof err), err);
+    check(leann_cuda_hnsw_add(ix.h, flat.data(), 0, embeddings.size(), start_id, 64, 1, err, sizeof err), err);
+    check(leann_cuda_save(ix.h, index_path.c_str(), err, sizeof err), err);
+}
+}  // namespace hnsw
+
+namespace diskann {
+/// diskann.rs:70-105: writes `<index_path>.diskann`; alpha = 1.2 (diskann.rs:91).
+inline void build_index(const std::vector<std::vector<float>>& embeddings, const std::vector<std::string>& /*ids*/, const std::string& index_path,
+                        size_t dimensions, size_t graph_degree, size_t complexity, int device = 0) {
+    auto flat = detail::flatten(embeddings, dimensions);
+    detail::IndexHandle ix;
+    char err[1024];
+    check(leann_cuda_vamana_build(flat.data(), 0, embeddings.size(), dimensions, graph_degree, complexity, 1.2f, LEANN_METRIC_DEFAULT, 1, device,
+                                  &ix.h, err, sizeof err), err);
+    check(leann_cuda_save(ix.h, index_path.c_str(), err, sizeof err), err);
+}
+}  // namespace diskann
+
 // ---- src/index/filter.rs ---------------------------------------------------------------------------------
 class MetadataFilter {
 public:
@@ -135,9 +190,34 @@ public:
         check(leann_cuda_filter_mask(f_.get(), p.data(), n.data(), p.size(), out.data(), err, sizeof err), err);
         return out;
     }
+    const leann_cuda_filter* handle() const { return f_.get(); }
 private:
     explicit MetadataFilter(leann_cuda_filter* f) : f_(f, leann_cuda_filter_free) {}
     std::shared_ptr<leann_cuda_filter> f_;
+};
+
+/// Typed columns of the passages' metadata: any parsed filter -> N-bit mask without touching JSON again
+/// (replaces the per-candidate passages.get + filter.matches of searcher.rs:186-194).
+class MetadataColumns {
+public:
+    explicit MetadataColumns(const std::vector<std::string>& metadata_json) : n_(metadata_json.size()) {
+        std::vector<const char*> p(n_);
+        std::vector<size_t> n(n_);
+        for (size_t i = 0; i < n_; ++i) { p[i] = metadata_json[i].data(); n[i] = metadata_json[i].size(); }
+        leann_cuda_metacols* c = nullptr;
+        char err[1024];
+        check(leann_cuda_metacols_build(p.data(), n.data(), n_, &c, err, sizeof err), err);
+        c_.reset(c, leann_cuda_metacols_free);
+    }
+    std::vector<uint64_t> mask(const MetadataFilter& f) const {
+        std::vector<uint64_t> out((n_ + 63) / 64);
+        char err[1024];
+        check(leann_cuda_metacols_mask(c_.get(), f.handle(), out.data(), err, sizeof err), err);
+        return out;
+    }
+private:
+    size_t n_;
+    std::shared_ptr<leann_cuda_metacols> c_;
 };
 
 // ---- src/index/bm25.rs -------------------------------------------------------------------------------------
@@ -232,6 +312,17 @@ public:
         return search_with_options(q, SearchOptions::make(top_k, complexity));
     }
     size_t len() const { return leann_cuda_searcher_len(s_.get()); }
+    /// searcher.rs:228-246: BM25-only top-k ordinals and scores (the reference returns the passages' texts).
+    std::vector<std::pair<size_t, float>> bm25_search(const std::string& query, size_t top_k) const {
+        std::vector<uint64_t> idx(top_k);
+        std::vector<float> sc(top_k);
+        uint32_t cnt = 0;
+        char err[1024];
+        check(leann_cuda_searcher_bm25_search(s_.get(), query.data(), query.size(), top_k, idx.data(), sc.data(), &cnt, err, sizeof err), err);
+        std::vector<std::pair<size_t, float>> out;
+        for (uint32_t i = 0; i < cnt; ++i) out.emplace_back((size_t)idx[i], sc[i]);
+        return out;
+    }
 private:
     explicit IndexSearcher(leann_cuda_searcher* s) : s_(s, leann_cuda_searcher_close) {}
     std::shared_ptr<leann_cuda_searcher> s_;

@@ -1,6 +1,6 @@
 // Exercises the C++ host mirror (leann-rs_b200/host/leann_cuda.hpp) the way the reference's own unit tests
 // exercise the Rust types: bm25.rs:264-329 and filter.rs:446-551 assertions, plus one BackendSearcher::search
-// call whose result is printed for the Python side to compare. Usage: host_mirror_test <base_path> <dims> <query.f32>
+// call whose result is printed for the Python side to compare. Usage: host_mirror_test <base_path> <dims> <query.f32> [scratch_base]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +51,31 @@ int main(int argc, char** argv) {
         printf("KEYS");
         for (auto k : res.first) printf(" %llu", (unsigned long long)k);
         printf("\n");
+        // --- hnsw::build_index + hnsw::add_to_index (hnsw.rs:96-191) on a scratch base path, then load and search
+        if (argc > 4) {
+            const std::string base = argv[4];
+            std::vector<std::vector<float>> first, more;
+            for (int i = 0; i < 300; ++i) {
+                std::vector<float> v(8);
+                for (int j = 0; j < 8; ++j) v[j] = std::sin(0.37f * (float)(i + 1) * (float)(j + 1));
+                (i < 200 ? first : more).push_back(v);
+            }
+            hnsw::build_index(first, {}, base, 8, 8, 32);
+            REQUIRE(HnswSearcher::load(base, 8)->len() == 200);
+            hnsw::add_to_index(more, base, 8, 200);
+            auto grown = HnswSearcher::load(base, 8);
+            REQUIRE(grown->len() == 300);
+            auto hit = grown->search(more[42], 1, 64);            // an appended vector finds itself under its key start_id + i
+            REQUIRE(hit.first.size() == 1 && hit.first[0] == 242);
+            try { hnsw::add_to_index({{1.0f, 2.0f}}, base, 8, 300); REQUIRE(false); } catch (const Error& e) { REQUIRE(e.code == LEANN_ERR_DIM_MISMATCH); }
+            // --- MetadataColumns == MetadataFilter::mask
+            std::vector<std::string> metas = {"{\"lines\": 5, \"type\": \"code\"}", "{\"lines\": 500}", "{}", "{\"type\": \"doc\", \"lines\": 7}"};
+            MetadataColumns cols(metas);
+            for (const char* expr : {"lines>6", "type=code", "type!=code", "lines>=5,type?", "type=doc OR lines<6"}) {
+                auto f = MetadataFilter::parse(expr);
+                REQUIRE(f.has_value() && cols.mask(*f) == f->mask(metas));
+            }
+        }
         try {
             HnswSearcher::load("/nonexistent/documents.leann", d);
             REQUIRE(false);

@@ -151,8 +151,8 @@ def test_cpp_host_mirror(orc, pkg, tmp_path):
     g.save(base.replace(".leann", ".index"))
     q = np.sin(0.37 * np.arange(1, d + 1, dtype=np.float32)).astype(np.float32)
     q.tofile(str(tmp_path / "query.f32"))
-    out = subprocess.check_output([exe, base, str(d), str(tmp_path / "query.f32")], text=True, timeout=120)
-    assert out.strip().endswith("OK")
+    out = subprocess.check_output([exe, base, str(d), str(tmp_path / "query.f32"), str(tmp_path / "scratch.leann")], text=True, timeout=120)
+    assert out.strip().endswith("OK")       # includes hnsw::build_index / add_to_index and MetadataColumns through the C++ mirror
     keys = [int(t) for t in [l for l in out.splitlines() if l.startswith("KEYS")][0].split()[1:]]
     ok, _, _, _ = g.search(q[None, :], 5, 64, lanes=pkg.reduction_lanes(d), next_cap=64)
     assert keys == [int(v) for v in ok[0]]
