@@ -159,3 +159,27 @@ def test_text_path_fails_loudly_without_gpu(pkg):
         pkg.hybrid_rerank([(0, 0.9)], [0.1], 0.5)
     with pytest.raises(pkg.LeannCudaError):
         pkg.FlatSearcher.from_vectors(__import__("numpy").zeros((4, 8), dtype="float32"))
+
+
+def _stats_blob(num_docs, total_tokens, df):
+    import struct
+    out = struct.pack("<QQQQ", 0x314D42534E41454C, num_docs, total_tokens, len(df))
+    for term in sorted(df):
+        t = term.encode()
+        out += struct.pack("<I", len(t)) + t + struct.pack("<Q", df[term])
+    return out
+
+
+def test_bm25_shard_statistics_merge(pkg):
+    """Corpus-wide BM25 statistics of document-range shards travel as blobs: merging is a host-side sum over
+    N, token count and per-term document frequency, deterministic in its byte output, and rejects malformed input."""
+    a = _stats_blob(3, 17, {"fox": 2, "quick": 1, "the": 3})
+    b = _stats_blob(2, 9, {"dog": 1, "the": 2, "zebra": 1})
+    want = _stats_blob(5, 26, {"fox": 2, "quick": 1, "the": 5, "dog": 1, "zebra": 1})
+    assert pkg.Bm25Scorer.merge_stats([a, b]) == want == pkg.Bm25Scorer.merge_stats([b, a])
+    assert pkg.Bm25Scorer.merge_stats([a]) == a
+    assert pkg.Bm25Scorer.merge_stats([]) == _stats_blob(0, 0, {})
+    for bad in (a[:-3], b"\x00" * 32, a + b"x"):
+        with pytest.raises(pkg.LeannCudaError) as e:
+            pkg.Bm25Scorer.merge_stats([a, bad])
+        assert e.value.code == pkg.ERR_BAD_FORMAT
