@@ -193,18 +193,20 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
     LEANN_CUDA_CHECK(cudaMemset(ws.pool_locks, 0, (size_t)want * 4));
 }
 
-// Small traversals on long rows: hash tables of 8192 ids for all resident warps stay in L2 (<= 64 MB), which measured 4-6 %
-// faster than the byte maps (no DRAM traffic for the visited set). Chosen only when the expected number of visited nodes
-// (about 0.7 * ef * degree) leaves the table under 40 % full, so spills into the byte maps stay exceptional.
-constexpr uint32_t L2_HASH_CAP = 8192;
-bool prefer_l2_hash(const leann_cuda_index* ix, size_t ef) {
+// Throughput batches on long rows: when the hash tables of all resident warps fit in (most of) L2 they beat the byte maps, which
+// cost one DRAM burst per neighbour test: 8192-entry tables (64 MB for 12 warps per SM) measured 4-7 % faster at ef = 64, 16384-entry
+// tables 1.7 % faster at ef = 148 on 1M x 768. Chosen only when the expected number of visited nodes (about 0.7 * ef * degree) leaves
+// the table under 41 % full, so that spills into the byte maps (limit 75 %) stay exceptional. Returns the capacity, 0 = byte maps.
+uint32_t l2_hash_capacity(const leann_cuda_index* ix, size_t ef) {
     const SearchWorkspace& ws = ix->ws;
-    return ix->vhash_mode == 0 && !ws.large_mode && ws.n_warps > 0 && (size_t)ws.n_warps * L2_HASH_CAP * 4 <= ((size_t)64 << 20) &&
-           7 * ef * ix->M0 <= 4 * (size_t)L2_HASH_CAP;
+    if (ix->vhash_mode != 0 || ws.large_mode || ws.n_warps <= 0) return 0;
+    for (uint32_t cap : {8192u, 16384u})
+        if (70 * ef * ix->M0 <= 41 * (size_t)cap && (size_t)ws.n_warps * cap * 4 <= ((size_t)128 << 20)) return cap;
+    return 0;
 }
-void ensure_l2_hash(const leann_cuda_index* ix) {
+void ensure_l2_hash(const leann_cuda_index* ix, uint32_t cap) {
     SearchWorkspace& ws = ix->ws;
-    const size_t words = (size_t)ws.n_warps * L2_HASH_CAP;
+    const size_t words = (size_t)ws.n_warps * cap;
     if (ws.vhash_words >= words) return;
     if (ws.vhash) cudaFree(ws.vhash);
     ws.vhash = nullptr; ws.vhash_words = 0;
@@ -277,9 +279,11 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
         p.coop_warps = nq <= (size_t)sms ? 8 : 4;
     }
     // throughput batches only: a latency-bound single traversal pays more for the CAS round trips than it saves (measured +20 %)
-    if (p.coop_ctas == 0 && prefer_l2_hash(ix, p.ef)) {
-        ensure_l2_hash(ix);
-        p.vhash = ix->ws.vhash; p.vhash_cap = L2_HASH_CAP;
+    if (p.coop_ctas == 0) {
+        if (const uint32_t cap = l2_hash_capacity(ix, p.ef)) {
+            ensure_l2_hash(ix, cap);
+            p.vhash = ix->ws.vhash; p.vhash_cap = cap;
+        }
     }
     launch_graph_search(ix->view(), p, stream);
 }
