@@ -23,9 +23,11 @@
 //     diskann.rs:54   beam = max(complexity, top_k);  diskann.rs:91 alpha = 1.2
 // The exact scan IS pinned by in-repo source: src/index/recompute.rs:96-110,137-139.
 //
-// Self-checks that stand in for golden vectors: recall against f64 brute force,
-// strict file-size equations in both readers, bounded-queue == unbounded-queue
-// equality, and two independent reduction orders.
+// Self-checks that stand in for golden vectors: hand-traced known answers on files
+// written byte by byte from the published layouts (tests/handmade.py: ids, distances,
+// evaluation and hop counts of an 8-node graph derived by hand from the published
+// loops), recall against f64 brute force, strict file-size equations in both readers,
+// bounded-queue == unbounded-queue equality, and two independent reduction orders.
 // =============================================================================
 #include <algorithm>
 #include <atomic>
