@@ -16,6 +16,14 @@ pub struct LeannCudaIndex {
 pub struct LeannCudaBm25 {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct LeannCudaFilter {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct LeannCudaMetacols {
+    _p: [u8; 0],
+}
 
 pub const BACKEND_HNSW: c_int = 0;
 pub const BACKEND_VAMANA: c_int = 1;
@@ -39,6 +47,13 @@ extern "C" {
     fn leann_cuda_bm25_build(docs: *const *const c_char, doc_bytes: *const usize, n_docs: usize, device: c_int,
                              out: *mut *mut LeannCudaBm25, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_bm25_free(b: *mut LeannCudaBm25);
+    fn leann_cuda_filter_parse(expr: *const c_char, out: *mut *mut LeannCudaFilter, err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_filter_free(f: *mut LeannCudaFilter);
+    fn leann_cuda_metacols_build(metadata_json: *const *const c_char, bytes: *const usize, n: usize,
+                                 out: *mut *mut LeannCudaMetacols, err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_metacols_mask(cols: *const LeannCudaMetacols, f: *const LeannCudaFilter, mask_bits: *mut u64,
+                                err: *mut c_char, errlen: usize) -> c_int;
+    fn leann_cuda_metacols_free(cols: *mut LeannCudaMetacols);
     fn leann_cuda_hybrid_search(index: *const LeannCudaIndex, bm25: *const LeannCudaBm25, queries: *const c_float,
                                 query_texts: *const *const c_char, query_text_bytes: *const usize, nq: usize,
                                 top_k: usize, ef: usize, hybrid: c_int, alpha: c_float, filter_mask: *const u64,
@@ -178,6 +193,51 @@ impl CudaSearcher {
         };
         check(rc, &err)?;
         Ok((idx, scores, counts))
+    }
+}
+
+/// Typed columns of every passage's metadata, built once when the index is opened; `mask(filter)` evaluates a filter
+/// string (`MetadataFilter::parse` grammar, filter.rs:52-134) into the N-bit mask `hybrid_search` takes, replacing the
+/// per-candidate `passages.get` + `filter.matches` of searcher.rs:186-194. `Ok(None)` where `parse` returns `None`.
+pub struct CudaMetadataColumns {
+    handle: *mut LeannCudaMetacols,
+    n: usize,
+}
+unsafe impl Send for CudaMetadataColumns {}
+unsafe impl Sync for CudaMetadataColumns {}
+
+impl CudaMetadataColumns {
+    pub fn build(metadata_json: &[String]) -> anyhow::Result<Self> {
+        let ptrs: Vec<*const c_char> = metadata_json.iter().map(|d| d.as_ptr() as *const c_char).collect();
+        let lens: Vec<usize> = metadata_json.iter().map(|d| d.len()).collect();
+        let mut h = std::ptr::null_mut();
+        let mut err = [0u8; 1024];
+        let rc = unsafe {
+            leann_cuda_metacols_build(ptrs.as_ptr(), lens.as_ptr(), metadata_json.len(), &mut h, err.as_mut_ptr() as *mut c_char, err.len())
+        };
+        check(rc, &err)?;
+        Ok(Self { handle: h, n: metadata_json.len() })
+    }
+    pub fn mask(&self, filter_str: &str) -> anyhow::Result<Option<Vec<u64>>> {
+        const LEANN_ERR_PARSE: c_int = -8;
+        let expr = CString::new(filter_str)?;
+        let mut f = std::ptr::null_mut();
+        let mut err = [0u8; 1024];
+        let rc = unsafe { leann_cuda_filter_parse(expr.as_ptr(), &mut f, err.as_mut_ptr() as *mut c_char, err.len()) };
+        if rc == LEANN_ERR_PARSE {
+            return Ok(None);
+        }
+        check(rc, &err)?;
+        let mut bits = vec![0u64; (self.n + 63) / 64];
+        let rc = unsafe { leann_cuda_metacols_mask(self.handle, f, bits.as_mut_ptr(), err.as_mut_ptr() as *mut c_char, err.len()) };
+        unsafe { leann_cuda_filter_free(f) };
+        check(rc, &err)?;
+        Ok(Some(bits))
+    }
+}
+impl Drop for CudaMetadataColumns {
+    fn drop(&mut self) {
+        unsafe { leann_cuda_metacols_free(self.handle) }
     }
 }
 
