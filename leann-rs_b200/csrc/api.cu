@@ -200,6 +200,7 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
 uint32_t l2_hash_capacity(const leann_cuda_index* ix, size_t ef) {
     const SearchWorkspace& ws = ix->ws;
     if (ix->vhash_mode != 0 || ws.large_mode || ws.n_warps <= 0) return 0;
+    if ((size_t)ws.n_warps * ws.n_pad <= ((size_t)64 << 20)) return 0;   // small index: the byte maps themselves live in L2
     for (uint32_t cap : {8192u, 16384u})
         if (70 * ef * ix->M0 <= 41 * (size_t)cap && (size_t)ws.n_warps * cap * 4 <= ((size_t)128 << 20)) return cap;
     return 0;
