@@ -233,8 +233,8 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
         uint32_t vpl = (d4 + 7) / 8;
         if (vpl <= 2) return launch_t<8, 2, 4, 6>(g, p, stream, op);
         if (vpl <= 3) return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
-        if (vpl <= 4) return launch_t<8, 4, 4, 4>(g, p, stream, op);
-        return launch_t<8, 8, 2, 3>(g, p, stream, op);
+        if (vpl <= 4) return launch_t<8, 4, 2, 6>(g, p, stream, op);   // d = 128: +10-15 % over <8,4,4,4>
+        return launch_t<8, 8, 2, 4>(g, p, stream, op);                  // d = 256: +6-7 % over <8,8,2,3>
     }
     uint32_t vpl = (d4 + 31) / 32;
     // occupancy / unroll per row length from sweeps on 1M-vector HNSW indexes (d = 384: +13 %, d = 512: +7 % over deeper unrolls)
