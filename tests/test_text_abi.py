@@ -183,3 +183,10 @@ def test_bm25_shard_statistics_merge(pkg):
         with pytest.raises(pkg.LeannCudaError) as e:
             pkg.Bm25Scorer.merge_stats([a, bad])
         assert e.value.code == pkg.ERR_BAD_FORMAT
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/leann_cuda.h must compile as C99 (no C++ or torch types in the signatures)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "include/leann_cuda.h"\nint main(void) { return leann_cuda_device_count() < 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-c", str(src), "-I", ROOT, "-o", str(tmp_path / "abi.o")])
