@@ -7,8 +7,10 @@
  * Nothing here aborts or throws across the ABI. There is NO CPU fallback: every search entry point
  * returns LEANN_ERR_CUDA when no sm_100 device is usable.
  *
- * Threading: `*_search*` calls are re-entrant on one handle (src/cli/serve.rs:84,289 shares one
- * searcher behind read locks); open/build/close must not race with searches on the same handle.
+ * Threading: `*_search*` calls may be issued concurrently on one handle from any number of threads
+ * (src/cli/serve.rs:84,289 shares one searcher behind read locks); the library serialises the launches of a
+ * handle and merges concurrent single-query calls (see leann_cuda_set_coalescing). open/build/close must not
+ * race with searches on the same handle.
  */
 #ifndef LEANN_CUDA_H
 #define LEANN_CUDA_H
@@ -116,9 +118,11 @@ int leann_cuda_search(const leann_cuda_index* index, const float* queries, size_
                       float* dists, uint32_t* counts, char* err, size_t errlen);
 
 /* Request coalescing. The reference API is one query per call and `leann serve` issues
- * those calls concurrently on one shared searcher (src/cli/serve.rs:84,260-311). With max_batch > 1, calls
- * with nq == 1 (no mask) arriving within max_wait_us of each other are merged into one batched launch; each
- * caller still gets exactly its own result. max_batch <= 1 disables (default). */
+ * those calls concurrently on one shared searcher (src/cli/serve.rs:84,260-311). Calls with nq == 1 (no mask)
+ * that arrive while another launch of the same handle is running are merged into one batched launch; each
+ * caller still gets exactly its own result. Default: max_batch = 256, max_wait_us = 0 — a lone caller never
+ * waits, concurrent callers batch naturally. max_wait_us > 0 makes a leader wait that long for company;
+ * max_batch <= 1 disables coalescing (calls then serialise on the handle). */
 /* Visited set of the graph traversal. By default every resident warp owns a byte map over the n nodes (exact, never cleared);
  * when n * resident warps would not fit in a third of device memory (tens of millions of short vectors per GPU) the library
  * switches to per-warp hash tables of about 2 * ef * degree node ids with a small shared pool of byte maps for traversals
@@ -127,9 +131,15 @@ int leann_cuda_search(const leann_cuda_index* index, const float* queries, size_
 int leann_cuda_set_visited_hash(leann_cuda_index* index, size_t capacity);
 int leann_cuda_set_coalescing(leann_cuda_index* index, size_t max_batch, unsigned max_wait_us);
 int leann_cuda_coalescing_stats(const leann_cuda_index* index, uint64_t* batches, uint64_t* requests);
+/* stats[0] = (re)allocations of the traversal workspace so far, [1] = its bytes, [2] = 1 in large-index mode,
+ * [3] = warps it is sized for. A repeated identical search must not change stats[0]. */
+int leann_cuda_workspace_stats(const leann_cuda_index* index, uint64_t* stats4);
 
 /* Same, all pointers in device memory of the index's device, enqueued on `cuda_stream`
- * (a cudaStream_t; NULL = default stream) without host synchronisation.
+ * (a cudaStream_t; NULL = default stream). Graph backends return without host synchronisation; the exact scan
+ * (FLAT) synchronises the stream once per call to read its overflow flag. Launches on one handle share one
+ * workspace: the library orders them itself (each call's stream first waits for the previous call's work on
+ * this handle), so calls from different streams or threads are safe but do not overlap each other.
  * d_stats: nullable, nq x 4 u64 = (distance evaluations, level-0 hops, upper-level hops, queue drops). */
 int leann_cuda_search_device(const leann_cuda_index* index, const float* d_queries, size_t nq,
                              size_t k, size_t ef, const uint64_t* d_mask_bits, int mask_mode,

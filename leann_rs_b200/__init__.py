@@ -70,6 +70,7 @@ def lib():
         "leann_cuda_set_visited_hash": (C.c_int, [vp, sz]),
         "leann_cuda_set_coalescing": (C.c_int, [vp, sz, C.c_uint]),
         "leann_cuda_coalescing_stats": (C.c_int, [vp, u64p, u64p]),
+        "leann_cuda_workspace_stats": (C.c_int, [vp, u64p]),
         "leann_cuda_device_count": (C.c_int, []),
         "leann_cuda_version": (cp, []),
         "leann_cuda_bm25_build": (C.c_int, [cpp, szp, sz, C.c_int, pp, cp, sz]),
@@ -265,6 +266,11 @@ class BackendSearcher:
         rc = lib().leann_cuda_set_visited_hash(self._h, capacity)
         if rc != 0:
             raise LeannCudaError(rc, "invalid visited-hash capacity")
+
+    def workspace_stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        lib().leann_cuda_workspace_stats(self._h, out)
+        return dict(zip(["reallocs", "bytes", "large_mode", "n_warps"], [int(x) for x in out]))
 
     def coalescing_stats(self):
         b, r = C.c_uint64(), C.c_uint64()

@@ -117,6 +117,7 @@ void ensure_workspace_large(const leann_cuda_index* ix, int want, size_t n_pad, 
     uint32_t cap = ix->vhash_mode >= 1024 ? next_pow2((uint32_t)std::min<size_t>(ix->vhash_mode, (size_t)1 << 22))
                                          : std::max<uint32_t>(1024u, next_pow2((uint32_t)std::min<size_t>(2 * ef * ix->M0, (size_t)1 << 22)));
     if (!ws.large_mode || ws.n_pad != n_pad) {   // (re)create the byte-map pool
+        ws.reallocs++;
         if (ws.visited) cudaFree(ws.visited);
         if (ws.epochs) cudaFree(ws.epochs);
         if (ws.pool_locks) cudaFree(ws.pool_locks);
@@ -136,6 +137,7 @@ void ensure_workspace_large(const leann_cuda_index* ix, int want, size_t n_pad, 
     ws.n_warps = std::max(ws.n_warps, want);
     const size_t words = (size_t)cap * (size_t)ws.n_warps;
     if (ws.vhash_words < words) {
+        ws.reallocs++;
         if (ws.vhash) cudaFree(ws.vhash);
         ws.vhash = nullptr; ws.vhash_words = 0;
         ws.vhash = dalloc<uint32_t>(words);
@@ -144,9 +146,15 @@ void ensure_workspace_large(const leann_cuda_index* ix, int want, size_t n_pad, 
     ws.vhash_cap = cap;
 }
 
-void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 12, size_t ef = 64) {
+void ensure_stream(const leann_cuda_index* ix) {
+    if (!ix->ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->ws.stream, cudaStreamNonBlocking));
+}
+
+// Sizes the traversal workspace for a launch of `nq` queries with the kernel's real resident-warp count and ef. Called
+// from exactly one place (search_device_impl): the byte-map / large-index decision depends on warps_per_sm, so a second
+// caller with other defaults would flip the mode back and forth (free + malloc + memset of GBs per call).
+void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm, size_t ef) {
     SearchWorkspace& ws = ix->ws;
-    if (!ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
     if (ix->backend == LEANN_BACKEND_FLAT) return;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
@@ -164,6 +172,7 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
         }
     }
     if (ws.large_mode) {   // leaving large-index mode (tuning hook): start over with per-warp byte maps
+        ws.reallocs++;
         if (ws.visited) cudaFree(ws.visited);
         if (ws.epochs) cudaFree(ws.epochs);
         ws.visited = nullptr; ws.epochs = nullptr; ws.n_warps = 0; ws.warp_cap = 0; ws.n_pad = 0; ws.large_mode = false;
@@ -177,6 +186,7 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm = 
     while (max_warps > 64 && (size_t)max_warps * n_pad > budget) max_warps /= 2;
     ws.warp_cap = max_warps;
     want = std::min(want, max_warps);
+    ws.reallocs++;
     if (ws.visited) cudaFree(ws.visited);
     if (ws.epochs) cudaFree(ws.epochs);
     if (ws.pool_locks) cudaFree(ws.pool_locks);
@@ -209,11 +219,30 @@ void ensure_l2_hash(const leann_cuda_index* ix, uint32_t cap) {
     SearchWorkspace& ws = ix->ws;
     const size_t words = (size_t)ws.n_warps * cap;
     if (ws.vhash_words >= words) return;
+    ws.reallocs++;
     if (ws.vhash) cudaFree(ws.vhash);
     ws.vhash = nullptr; ws.vhash_words = 0;
     ws.vhash = dalloc<uint32_t>(words);
     ws.vhash_words = words;
 }
+
+// All launches on one handle share the traversal workspace (query counter, visited maps, hash tables), the exact-scan
+// scratch and the lazily built bf16 copy. Calls arrive under ix->mu, but they may name different streams: each call
+// first makes its stream wait for the previous call's work (an event recorded after the last enqueue), so launches
+// on one handle execute in call order whatever streams carry them.
+void chain_begin(const leann_cuda_index* ix, cudaStream_t stream) {
+    if (ix->chain_valid && ix->chain_stream != stream) LEANN_CUDA_CHECK(cudaStreamWaitEvent(stream, ix->chain_ev, 0));
+}
+void chain_end(const leann_cuda_index* ix, cudaStream_t stream) {
+    if (!ix->chain_ev) LEANN_CUDA_CHECK(cudaEventCreateWithFlags(&ix->chain_ev, cudaEventDisableTiming));
+    LEANN_CUDA_CHECK(cudaEventRecord(ix->chain_ev, stream));
+    ix->chain_stream = stream;
+    ix->chain_valid = true;
+}
+
+void search_device_launch(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
+                          const uint64_t* d_mask, int mask_mode, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
+                          uint64_t* d_stats, cudaStream_t stream);
 
 void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
                         const uint64_t* d_mask, int mask_mode, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
@@ -221,9 +250,16 @@ void search_device_impl(const leann_cuda_index* ix, const float* d_queries, size
     if (!ix) throw Error(LEANN_ERR_INVALID_ARG, "null index");
     if (nq == 0) return;
     if (k == 0) throw Error(LEANN_ERR_INVALID_ARG, "k must be > 0");
+    chain_begin(ix, stream);
+    search_device_launch(ix, d_queries, nq, k, ef, d_mask, mask_mode, d_keys, d_dists, d_counts, d_stats, stream);
+    chain_end(ix, stream);
+}
+
+void search_device_launch(const leann_cuda_index* ix, const float* d_queries, size_t nq, size_t k, size_t ef,
+                          const uint64_t* d_mask, int mask_mode, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
+                          uint64_t* d_stats, cudaStream_t stream) {
     if (mask_mode == LEANN_MASK_NONE) d_mask = nullptr;
     if (ix->backend == LEANN_BACKEND_FLAT) {
-        ensure_workspace(ix, nq);
         size_t need = exact_scan_scratch_bytes(ix->d4, (uint32_t)nq, (uint32_t)k);
         if (ix->scan_scratch_bytes < need) {
             if (ix->scan_scratch) cudaFree(ix->scan_scratch);
@@ -307,7 +343,7 @@ void backend_search_device(const leann_cuda_index* ix, const float* d_queries, s
                        nullptr, stream);
 }
 cudaStream_t backend_stream(const leann_cuda_index* ix) {
-    if (!ix->ws.stream) LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->ws.stream, cudaStreamNonBlocking));
+    ensure_stream(ix);
     return ix->ws.stream;
 }
 int guard_impl(char* err, size_t errlen, const std::function<void()>& f) {
@@ -555,7 +591,7 @@ static void search_host_locked(const leann_cuda_index* ix, const float* queries,
                                const uint64_t* mask_bits, int mask_mode, uint64_t* keys, float* dists, uint32_t* counts) {
     DeviceGuard dg(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
-    ensure_workspace(ix, nq);
+    ensure_stream(ix);   // the traversal workspace is sized once, by search_device_impl, with the kernel's real parameters
     SearchWorkspace& ws = ix->ws;
     ensure_buf(ws.d_queries, ws.cap_q, nq * ix->d);
     size_t out_need = nq * k;
@@ -584,7 +620,9 @@ static void search_host_locked(const leann_cuda_index* ix, const float* queries,
     LEANN_CUDA_CHECK(cudaStreamSynchronize(ws.stream));
 }
 
-// One query from one thread, coalescing enabled: join (or lead) a batch.
+// One query from one thread, coalescing enabled: join (or lead) a batch. One batch is in flight per handle at a time
+// (launches on a handle are serialised anyway): requests that arrive while it runs queue up and the next leader takes all
+// of them, so a lone caller pays no waiting time (max_wait_us = 0, the default) and concurrent callers batch naturally.
 static void search_coalesced(const leann_cuda_index* ix, const float* query, size_t k, size_t ef, uint64_t* keys, float* dists,
                              uint32_t* count) {
     Coalescer& c = ix->coalescer;
@@ -595,40 +633,65 @@ static void search_coalesced(const leann_cuda_index* ix, const float* query, siz
     while (!r.done) {
         if (r.taken || c.leader_active) { c.cv_done.wait(lk); continue; }
         c.leader_active = true;
-        auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(c.max_wait_us);
-        while (c.queue.size() < c.max_batch)
-            if (c.cv_leader.wait_until(lk, deadline) == std::cv_status::timeout) break;
-        // the batch = every queued request with this thread's (k, ef), in arrival order
+        if (c.max_wait_us > 0) {
+            auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(c.max_wait_us);
+            while (c.queue.size() < c.max_batch)
+                if (c.cv_leader.wait_until(lk, deadline) == std::cv_status::timeout) break;
+        }
+        // the batch = queued requests with this thread's (k, ef), in arrival order, at most max_batch (this one included)
         std::vector<CoalesceReq*> batch, rest;
-        for (CoalesceReq* q : c.queue) ((q->k == r.k && q->ef == r.ef && (q == &r || batch.size() + 1 < c.max_batch)) ? batch : rest).push_back(q);
-        for (CoalesceReq* q : batch) q->taken = true;
-        c.queue.swap(rest);
-        c.leader_active = false;
-        c.batches++; c.requests += batch.size();
-        c.cv_done.notify_all();   // another waiter may lead the remaining requests while this batch runs
+        try {
+            batch.reserve(c.queue.size()); rest.reserve(c.queue.size());
+            batch.push_back(&r);
+            for (CoalesceReq* q : c.queue) {
+                if (q == &r) continue;
+                ((q->k == r.k && q->ef == r.ef && batch.size() < c.max_batch) ? batch : rest).push_back(q);
+            }
+        } catch (...) {   // out of memory while forming the batch: run alone
+            batch.clear(); rest.clear();
+            r.taken = true;
+            c.queue.erase(std::find(c.queue.begin(), c.queue.end(), &r));
+        }
+        if (!batch.empty()) {
+            for (CoalesceReq* q : batch) q->taken = true;
+            c.queue.swap(rest);
+        }
+        c.batches++; c.requests += batch.empty() ? 1 : batch.size();
         lk.unlock();
-        const size_t nb = batch.size(), d = ix->d;
-        std::vector<float> qbuf(nb * d);
-        std::vector<uint64_t> kbuf(nb * k);
-        std::vector<float> dbuf(nb * k);
-        std::vector<uint32_t> cbuf(nb);
-        for (size_t i = 0; i < nb; ++i) memcpy(&qbuf[i * d], batch[i]->query, d * 4);
         int rc = 0;
         std::string msg;
+        const size_t nb = batch.empty() ? 1 : batch.size(), d = ix->d;
         try {
-            search_host_locked(ix, qbuf.data(), nb, k, ef, nullptr, LEANN_MASK_NONE, kbuf.data(), dbuf.data(), cbuf.data());
-        } catch (const Error& e) { rc = e.code; msg = e.what(); }
-        catch (const std::exception& e) { rc = LEANN_ERR_INVALID_ARG; msg = e.what(); }
-        lk.lock();
-        for (size_t i = 0; i < nb; ++i) {
-            CoalesceReq* q = batch[i];
-            if (rc == 0) {
-                memcpy(q->keys, &kbuf[i * k], k * 8);
-                memcpy(q->dists, &dbuf[i * k], k * 4);
-                if (q->count) *q->count = cbuf[i];
+            if (nb == 1) {
+                search_host_locked(ix, query, 1, k, ef, nullptr, LEANN_MASK_NONE, keys, dists, count);
+            } else {
+                std::vector<float> qbuf(nb * d);
+                std::vector<uint64_t> kbuf(nb * k);
+                std::vector<float> dbuf(nb * k);
+                std::vector<uint32_t> cbuf(nb);
+                for (size_t i = 0; i < nb; ++i) memcpy(&qbuf[i * d], batch[i]->query, d * 4);
+                search_host_locked(ix, qbuf.data(), nb, k, ef, nullptr, LEANN_MASK_NONE, kbuf.data(), dbuf.data(), cbuf.data());
+                for (size_t i = 0; i < nb; ++i) {
+                    CoalesceReq* q = batch[i];
+                    memcpy(q->keys, &kbuf[i * k], k * 8);
+                    memcpy(q->dists, &dbuf[i * k], k * 4);
+                    if (q->count) *q->count = cbuf[i];
+                }
             }
-            q->rc = rc; q->err = msg; q->done = true;
+        } catch (const Error& e) { rc = e.code; msg = e.what(); }
+        catch (const std::bad_alloc&) { rc = LEANN_ERR_INVALID_ARG; msg = "out of host memory"; }
+        catch (const std::exception& e) { rc = LEANN_ERR_INVALID_ARG; msg = e.what(); }
+        catch (...) { rc = LEANN_ERR_INVALID_ARG; msg = "unknown error"; }
+        // every request of the batch is completed (with the error code, if any) whatever happened above: a follower
+        // left without done = true would wait forever
+        lk.lock();
+        if (batch.empty()) { r.rc = rc; r.done = true; }
+        for (CoalesceReq* q : batch) {
+            q->rc = rc;
+            if (rc != 0) { try { q->err = msg; } catch (...) {} }
+            q->done = true;
         }
+        c.leader_active = false;
         c.cv_done.notify_all();
     }
     if (r.rc != 0) throw Error(r.rc, r.err);
@@ -656,6 +719,16 @@ int leann_cuda_set_coalescing(leann_cuda_index* ix, size_t max_batch, unsigned m
     std::lock_guard<std::mutex> lk(ix->coalescer.m);
     ix->coalescer.max_batch = max_batch;
     ix->coalescer.max_wait_us = max_wait_us;
+    return LEANN_OK;
+}
+int leann_cuda_workspace_stats(const leann_cuda_index* ix, uint64_t* stats4) {
+    if (!ix || !stats4) return LEANN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const SearchWorkspace& ws = ix->ws;
+    stats4[0] = ws.reallocs;
+    stats4[1] = ws.large_mode ? (uint64_t)ws.pool_slots * ws.n_pad + ws.vhash_words * 4 : (uint64_t)ws.n_warps * ws.n_pad + ws.vhash_words * 4;
+    stats4[2] = ws.large_mode ? 1 : 0;
+    stats4[3] = (uint64_t)ws.n_warps;
     return LEANN_OK;
 }
 int leann_cuda_coalescing_stats(const leann_cuda_index* ix, uint64_t* batches, uint64_t* requests) {
@@ -687,6 +760,7 @@ void leann_cuda_close(leann_cuda_index* ix) {
     cudaFree(ws.d_queries); cudaFree(ws.d_keys);
     cudaFree(ws.d_dists); cudaFree(ws.d_counts); cudaFree(ws.d_mask);
     if (ws.stream) cudaStreamDestroy(ws.stream);
+    if (ix->chain_ev) cudaEventDestroy(ix->chain_ev);
     if (ix->scan_pinned) cudaFreeHost(ix->scan_pinned);
     cudaFree(ix->scan_scratch); cudaFree(ix->tc_bf16); cudaFree(ix->tc_norms); cudaFree(ix->tc_xmax);
     cudaGetLastError();

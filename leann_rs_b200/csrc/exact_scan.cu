@@ -395,7 +395,7 @@ size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
     return align256((size_t)nq * SCAN_CAP * 8) + align256((size_t)nq * 4) + align256((size_t)nq * kpad * 8) +
            align256((size_t)nq * 4) + align256((size_t)nq * 8) + 256 + align256((size_t)nq * d4max * 16) +
            // tensor path: bf16 queries, |q|, dot thresholds, candidate row ids
-           align256((size_t)nq * dp8 * 2) + align256((size_t)nq * 4) + align256((size_t)nq * 4) + align256((size_t)nq * SCAN_CAP * 4);
+           align256((size_t)nq * dp8 * 2) + 3 * align256((size_t)nq * 4) + align256((size_t)nq * SCAN_CAP * 4);
 }
 
 void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
@@ -418,6 +418,7 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     if (use_tc) {
         ts.q_bf16 = p; p += align256((size_t)nq * tv->dp8 * 2);
         ts.qnorm = (float*)p; p += align256((size_t)nq * 4);
+        ts.qres = (float*)p; p += align256((size_t)nq * 4);
         ts.thr_dot = (float*)p; p += align256((size_t)nq * 4);
         ts.cand_ids = (uint32_t*)p; p += align256((size_t)nq * SCAN_CAP * 4);
     }

@@ -2,19 +2,28 @@
 // scan (leann-rs src/index/recompute.rs:96-103) as a tcgen05.mma kernel fed by TMA, followed by K2r, the
 // fp32 re-rank of the surviving candidates (recompute.rs:137-139 arithmetic, f32 throughout).
 //
-//   pass 1 (this kernel): bf16 copies of Q and X, UMMA 128x256x16 (kind::f16, f32 accumulate in TMEM),
-//        operands staged by TMA into 128B-swizzled shared memory, 4-stage mbarrier pipeline, two
-//        TMEM accumulator stages so the epilogue of tile t overlaps the MMAs of tile t+1.
-//        Epilogue: tcgen05.ld, one thread per query row, compares every score with the query's
-//        threshold  T_q = (exact k-th best so far) - eps_q  and appends the row id of the few survivors.
-//        eps_q = 1.25 * 2^-8 * |q| * max|x| + 1e-6 bounds |bf16 score - f32 score| rigorously
-//        (round-to-nearest bf16 on both operands + f32 accumulation), so no true top-k row is dropped.
+//   pass 1 (scan_tc_kernel): bf16 copies of Q and X. One CTA pair (two SMs of a TPC, cta_group::2) per work
+//        item = (256 queries, group of <= 32 database tiles of 256 rows); UMMA 256x256x16 (kind::f16, f32
+//        accumulate in TMEM) issued by one thread of the leader CTA. Each CTA keeps its 128 x d query tile
+//        resident in 128B-swizzled shared memory (d <= 448; streamed through the ring above that) and streams
+//        its 128-row half of every database tile through a TMA ring of up to 8 stages; the peer's TMA
+//        completes on the leader's mbarrier, tcgen05.commit multicast frees ring slots in both CTAs; two
+//        256-column TMEM accumulator stages so the epilogue of tile t overlaps the MMAs of tile t+1.
+//        Epilogue: tcgen05.ld 32x32b.x32, one thread per query row, survivor bitmask by sign(T_q - score),
+//        row ids of the survivors appended in batches of TC_QBUF.
+//        T_q = (exact k-th best so far) - eps_q, and eps_q bounds |bf16 score - f32 score| rigorously:
+//          |q^.x^ - q.x| = |(q^-q).x + q^.(x^-x)| <= |q^-q| |x| + |q^| |x^-x|          (Cauchy-Schwarz)
+//        with the ACTUAL rounding residuals |q^-q| (per query) and max_rows |x^-x|, max_rows |x| measured when
+//        the bf16 copies are made (to_bf16_kernel), plus dp8 * 2^-22 |q^||x^| for the f32 accumulation inside the
+//        tensor core. (The worst case of the residual is 2^-8 relative per operand, i.e. (2^-7 + 2^-16)|q||x| in
+//        total; the round-1 constant 1.25 * 2^-8 was below that and could drop a true top-k row on low-mantissa
+//        inputs such as (1 + 2^-8) c — tests/test_exact_gpu.py::test_tc_prefilter_tie_point_rows.)
 //   pass 2 (rerank_kernel): exact f32 dot for each survivor -> packed rank key -> select_kernel.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31). Persistent CTAs walk a static
-// schedule of (query tile, group of database tiles) items ordered so that concurrently running CTAs
-// read the same database tiles (L2 reuse across query tiles).
+// Warp roles (256 threads per CTA): warp 0 = ring producer (TMA), warp 1 = MMA issuer (leader CTA only),
+// warp 2 = TMEM allocator, warp 3 = resident query tile producer, warps 4..7 = epilogue (warp w reads TMEM
+// lanes 32*(w%4)..+31). Persistent pairs walk a static schedule of (query pair tile, group of database tiles)
+// items ordered so that concurrently running pairs read the same database tiles (L2 reuse across query tiles).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -329,34 +338,63 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
-// f32 -> bf16 (round to nearest even) rows padded to dp8 elements; also |row| (f32) for eps.
+// f32 -> bf16 (round to nearest even) rows padded to dp8 elements. Per row: |x| and the rounding residual |x^ - x|
+// (both rounded up: they are only used as upper bounds), optionally stored, optionally folded into two global maxima
+// (max_bits[0] = max |x|, max_bits[1] = max |x^ - x|; non-negative floats order as their bit patterns).
 __global__ void to_bf16_kernel(const float4* __restrict__ src, uint32_t d4, __nv_bfloat16* __restrict__ dst, uint32_t dp8,
-                               size_t n, float* __restrict__ norms) {
+                               size_t n, float* __restrict__ norms, float* __restrict__ resid, uint32_t* __restrict__ max_bits) {
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    float ss = 0.f;
-    for (uint32_t i = lane; i < dp8 / 4; i += 32) {
-        float4 v = i < d4 ? src[row * d4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-        reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[i * 2] = a;
-        reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[i * 2 + 1] = b;
+    float ss = 0.f, rr = 0.f;
+    if (row < n) {
+        for (uint32_t i = lane; i < dp8 / 4; i += 32) {
+            float4 v = i < d4 ? src[row * d4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+            const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+            const float ex = fa.x - v.x, ey = fa.y - v.y, ez = fb.x - v.z, ew = fb.y - v.w;   // exact in f32
+            rr += ex * ex + ey * ey + ez * ez + ew * ew;
+            reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[i * 2] = a;
+            reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[i * 2 + 1] = b;
+        }
     }
-    for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
-    if (lane == 0 && norms) norms[row] = sqrtf(ss) * 1.0000005f;  // rounded up a hair: used only as an upper bound
+    for (int off = 16; off; off >>= 1) {
+        ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
+        rr += __shfl_xor_sync(0xFFFFFFFFu, rr, off);
+    }
+    // 1 + 1e-4 covers the f32 rounding of the sums of squares (<= d * 2^-24 relative, d <= 4096) and of sqrtf
+    const float nrm = sqrtf(ss) * 1.0001f, res = sqrtf(rr) * 1.0001f;
+    if (row < n && lane == 0) {
+        if (norms) norms[row] = nrm;
+        if (resid) resid[row] = res;
+    }
+    if (max_bits) {
+        __shared__ float s_n[32], s_r[32];
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (lane == 0) { s_n[w] = row < n ? nrm : 0.f; s_r[w] = row < n ? res : 0.f; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float mn = 0.f, mr = 0.f;
+            for (int i = 0; i < nw; ++i) { mn = fmaxf(mn, s_n[i]); mr = fmaxf(mr, s_r[i]); }
+            atomicMax(&max_bits[0], __float_as_uint(mn));
+            atomicMax(&max_bits[1], __float_as_uint(mr));
+        }
+    }
 }
 
-__global__ void max_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ out_bits) {
-    float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, v[i]);
-    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
-    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
+// Rigorous bound on |bf16 tensor-core score - f32 score| of query q against any database row (header comment):
+// |q^-q| max|x|  +  |q^| max|x^-x|  +  dp8 * 2^-22 |q^| max|x^|, with |q^| <= |q| (1 + 2^-8), |x^| <= |x| (1 + 2^-8).
+__device__ __forceinline__ float tc_eps(float qnorm, float qres, const uint32_t* xmax_bits, uint32_t dp8) {
+    const float xmax = __uint_as_float(xmax_bits[0]), xres = __uint_as_float(xmax_bits[1]);
+    const float qhat = qnorm * 1.00390625f;
+    const float acc = (float)dp8 * 2.3841858e-7f * qhat * (xmax * 1.00390625f);
+    return (qres * xmax + qhat * xres + acc) * 1.0001f + 1e-30f;
 }
 
 // thr key (packed rank key of the exact k-th best, or ~0) -> dot-space candidate threshold.
-__global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr, const float* __restrict__ qnorm, const uint32_t* xmax_bits,
-                                     uint32_t nq, int metric, float* __restrict__ thr_dot) {
+__global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr, const float* __restrict__ qnorm,
+                                     const float* __restrict__ qres, const uint32_t* xmax_bits, uint32_t dp8, uint32_t nq, int metric,
+                                     float* __restrict__ thr_dot) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     unsigned long long key = thr[q];
@@ -365,9 +403,7 @@ __global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr,
     float dotk;
     if (metric == LEANN_METRIC_DOT_DESC) dotk = scan_unorder_f32(~ok);
     else dotk = 1.0f - scan_unorder_f32(ok);   // IP / IP_CLAMP: distance = 1 - dot (clamped at 0: dot >= 1 stays conservative)
-    const float xmax = __uint_as_float(*xmax_bits);
-    const float eps = 1.25f * 0.00390625f * qnorm[q] * xmax + 1e-6f;
-    thr_dot[q] = nextafterf(dotk - eps - fabsf(dotk) * 1e-6f, -CUDART_INF_F);   // strict: the kernel keeps score > thr_dot
+    thr_dot[q] = nextafterf(dotk - tc_eps(qnorm[q], qres[q], xmax_bits, dp8) - fabsf(dotk) * 1e-6f, -CUDART_INF_F);   // strict: the kernel keeps score > thr_dot
 }
 
 // K2r: exact f32 score of every survivor -> packed rank key in cand[q][i].
@@ -442,13 +478,13 @@ bool exact_scan_tc_supported(const FlatView& f, uint32_t nq) {
 
 size_t exact_scan_tc_bf16_bytes(size_t n, uint32_t d) { return n * (size_t)((d + 7) / 8 * 8) * 2 + n * 4 + 256; }
 
-// Builds the bf16 copy + row norms + max norm of a database (called once per index).
+// Builds the bf16 copy of a database (called once per index) with its row norms (f32, kept for the L2 form of the
+// tensor path) and the two maxima tc_eps needs: xmax_bits[0] = max |x|, xmax_bits[1] = max |x^ - x|.
 void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t dp8, void* bf16_rows, float* norms,
                            uint32_t* xmax_bits, cudaStream_t s) {
-    LEANN_CUDA_CHECK(cudaMemsetAsync(xmax_bits, 0, 4, s));
+    LEANN_CUDA_CHECK(cudaMemsetAsync(xmax_bits, 0, 8, s));
     if (!n) return;
-    to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(vecs, d4, (__nv_bfloat16*)bf16_rows, dp8, n, norms);
-    max_kernel<<<296, 256, 0, s>>>(norms, n, xmax_bits);
+    to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(vecs, d4, (__nv_bfloat16*)bf16_rows, dp8, n, norms, nullptr, xmax_bits);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -456,7 +492,7 @@ void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t d
 // on return s.cand / s.cand_cnt hold exact packed keys ready for select_kernel.
 void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq,
                          uint32_t r0, uint32_t r1, const uint64_t* d_mask, uint32_t cap, int sms, cudaStream_t stream) {
-    dot_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.thr, ts.qnorm, tv.xmax_bits, nq, f.metric, ts.thr_dot);
+    dot_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.thr, ts.qnorm, ts.qres, tv.xmax_bits, tv.dp8, nq, f.metric, ts.thr_dot);
     CUtensorMap mq = make_map(ts.q_bf16, nq, tv.dp8, TC_M);
     CUtensorMap mx = make_map(tv.x_bf16, f.n, tv.dp8, TC_NH);
     TcParams p;
@@ -497,7 +533,7 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
 }
 
 void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_t dp8, const TcScratch& ts, cudaStream_t stream) {
-    to_bf16_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(qpad, d4, (__nv_bfloat16*)ts.q_bf16, dp8, nq, ts.qnorm);
+    to_bf16_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(qpad, d4, (__nv_bfloat16*)ts.q_bf16, dp8, nq, ts.qnorm, ts.qres, nullptr);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -6,8 +6,10 @@
 // Both graph formats are third-party serialisations recalled from upstream; every header field and
 // the exact file-size equation are verified so a mismatch fails loudly instead of mis-reading.
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <fstream>
 
 #include "internal.h"
@@ -49,6 +51,35 @@ struct Reader {
         if (pos + bytes > size || fread(dst, 1, bytes, f) != bytes)
             throw Error(LEANN_ERR_BAD_FORMAT, path + ": truncated while reading " + what);
         pos += bytes;
+    }
+};
+// Writes go to `<path>.tmp`; every fwrite is checked, the file is flushed to disk and renamed over the target only
+// when complete, so a short write (ENOSPC, crash) never truncates the only copy of an index (hnsw::add_to_index
+// overwrites `.index` in place, hnsw.rs:183).
+struct Writer {
+    FILE* f;
+    std::string path, tmp;
+    explicit Writer(const std::string& p) : f(nullptr), path(p), tmp(p + ".tmp") {
+        f = fopen(tmp.c_str(), "wb");
+        if (!f) throw Error(LEANN_ERR_NOT_FOUND, "cannot create " + tmp + ": " + strerror(errno));
+    }
+    ~Writer() { if (f) { fclose(f); remove(tmp.c_str()); } }
+    void write(const void* src, size_t size, size_t count) {
+        if (count == 0 || size == 0) return;
+        if (fwrite(src, size, count, f) != count) {
+            const std::string why = strerror(errno);
+            throw Error(LEANN_ERR_BAD_FORMAT, "write failed: " + tmp + ": " + why);
+        }
+    }
+    void commit() {
+        bool ok = fflush(f) == 0 && fsync(fileno(f)) == 0;
+        ok = (fclose(f) == 0) && ok;
+        f = nullptr;
+        if (!ok || rename(tmp.c_str(), path.c_str()) != 0) {
+            const std::string why = strerror(errno);
+            remove(tmp.c_str());
+            throw Error(LEANN_ERR_BAD_FORMAT, "write failed: " + path + ": " + why);
+        }
     }
 };
 }  // namespace
@@ -151,11 +182,10 @@ void read_usearch_index(const std::string& path, size_t dims, HostHnsw& g) {
 }
 
 void write_usearch_index(const std::string& path, const HostHnsw& g) {
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) throw Error(LEANN_ERR_NOT_FOUND, "cannot create " + path);
+    Writer w(path);
     uint32_t rc[2] = {(uint32_t)g.n, (uint32_t)(g.d * 4)};
-    fwrite(rc, 4, 2, f);
-    fwrite(g.vecs.data(), 4, g.n * g.d, f);
+    w.write(rc, 4, 2);
+    w.write(g.vecs.data(), 4, g.n * g.d);
     UsearchDenseHead h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, "usearch", 7);
@@ -163,10 +193,10 @@ void write_usearch_index(const std::string& path, const HostHnsw& g) {
     h.kind_metric = g.metric == LEANN_METRIC_L2SQ ? 'e' : 'i';
     h.kind_scalar = KIND_F32; h.kind_key = KIND_U64; h.kind_slot = KIND_U32;
     h.count_present = g.n; h.count_deleted = 0; h.dimensions = g.d; h.multi = 0;
-    fwrite(&h, sizeof h, 1, f);
+    w.write(&h, sizeof h, 1);
     UsearchGraphHead gh{g.n, g.M, g.M0, (uint64_t)g.max_level, g.entry};
-    fwrite(&gh, sizeof gh, 1, f);
-    fwrite(g.levels.data(), 2, g.n, f);
+    w.write(&gh, sizeof gh, 1);
+    w.write(g.levels.data(), 2, g.n);
     std::vector<uint32_t> node;
     for (size_t i = 0; i < g.n; ++i) {
         int lv = g.levels[i];
@@ -183,11 +213,11 @@ void write_usearch_index(const std::string& path, const HostHnsw& g) {
         }
         uint64_t key = g.keys.empty() ? (uint64_t)i : g.keys[i];
         int16_t lv16 = (int16_t)lv;
-        fwrite(&key, 8, 1, f);
-        fwrite(&lv16, 2, 1, f);
-        fwrite(node.data(), 4, node.size(), f);
+        w.write(&key, 8, 1);
+        w.write(&lv16, 2, 1);
+        w.write(node.data(), 4, node.size());
     }
-    if (fclose(f) != 0) throw Error(LEANN_ERR_BAD_FORMAT, "write failed: " + path);
+    w.commit();
 }
 
 // bincode 1 (fixint, little endian): usize -> u64, String -> u64 length + bytes.
@@ -229,16 +259,15 @@ void write_diskann(const std::string& path, const HostVamana& g) {
     for (int i = 0; i < 4; ++i) m.push_back((unsigned char)(g.medoid >> (8 * i)));
     p64(voff); p64(aoff); p64(name.size());
     m.insert(m.end(), name.begin(), name.end());
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) throw Error(LEANN_ERR_NOT_FOUND, "cannot create " + path);
+    Writer w(path);
     uint64_t ml = m.size();
-    fwrite(&ml, 8, 1, f);
-    fwrite(m.data(), 1, m.size(), f);
+    w.write(&ml, 8, 1);
+    w.write(m.data(), 1, m.size());
     std::vector<unsigned char> z(voff - 8 - m.size(), 0);
-    fwrite(z.data(), 1, z.size(), f);
-    fwrite(g.vecs.data(), 4, g.n * g.d, f);
-    fwrite(g.adj.data(), 4, g.n * g.R, f);
-    if (fclose(f) != 0) throw Error(LEANN_ERR_BAD_FORMAT, "write failed: " + path);
+    w.write(z.data(), 1, z.size());
+    w.write(g.vecs.data(), 4, g.n * g.d);
+    w.write(g.adj.data(), 4, g.n * g.R);
+    w.commit();
 }
 
 void read_embeddings(const std::string& path, size_t dims, std::vector<float>& out, size_t& n) {
@@ -251,10 +280,9 @@ void read_embeddings(const std::string& path, size_t dims, std::vector<float>& o
 }
 
 void write_embeddings(const std::string& path, const float* v, size_t n, size_t dims) {
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) throw Error(LEANN_ERR_NOT_FOUND, "cannot create " + path);
-    fwrite(v, 4, n * dims, f);
-    if (fclose(f) != 0) throw Error(LEANN_ERR_BAD_FORMAT, "write failed: " + path);
+    Writer w(path);
+    w.write(v, 4, n * dims);
+    w.commit();
 }
 
 }  // namespace leann

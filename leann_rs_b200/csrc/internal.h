@@ -84,6 +84,7 @@ struct SearchWorkspace {
     uint32_t* pool_locks = nullptr; uint32_t pool_slots = 0;
     bool large_mode = false;
     size_t mem_total = 0;        // device memory size (queried once)
+    uint64_t reallocs = 0;       // (re)allocations of the traversal workspace so far (leann_cuda_workspace_stats)
     int n_warps = 0;
     int warp_cap = 0;            // memory-bounded maximum pool size (0 = not computed yet)
     size_t n_pad = 0;
@@ -144,8 +145,8 @@ struct Coalescer {
     std::mutex m;
     std::condition_variable cv_leader, cv_done;
     bool leader_active = false;
-    size_t max_batch = 0;        // 0 = disabled
-    unsigned max_wait_us = 0;
+    size_t max_batch = 256;      // <= 1 = disabled
+    unsigned max_wait_us = 0;    // 0: never wait for company, only merge what queued up while the previous batch ran
     std::vector<CoalesceReq*> queue;
     uint64_t batches = 0, requests = 0;
 };
@@ -182,6 +183,10 @@ struct leann_cuda_index {
     mutable uint32_t* tc_xmax = nullptr;
     mutable bool tc_disabled = false;
     mutable leann::Coalescer coalescer;
+    // stream chaining: event recorded after the last enqueue on this handle, and the stream it was recorded on
+    mutable cudaEvent_t chain_ev = nullptr;
+    mutable cudaStream_t chain_stream = nullptr;
+    mutable bool chain_valid = false;
     bool coop_small_batches = true;   // CTA-per-query kernel for nq <= 2 per SM
     size_t vhash_mode = 0;   // visited set: 0 auto (byte maps unless they would not fit), 1 byte maps only, >= 1024 force hash tables of this capacity
     leann::GraphView view() const {

@@ -25,12 +25,13 @@ struct ScanScratch {
 
 struct TcIndexView {               // per-index tensor-path data (built once)
     const void* x_bf16;            // [n][dp8] bf16
-    const uint32_t* xmax_bits;     // max row norm (f32 bits)
+    const uint32_t* xmax_bits;     // [0] max row norm |x|, [1] max bf16 rounding residual |x^ - x| (f32 bits)
     uint32_t dp8;
 };
 struct TcScratch {                 // per-call tensor-path scratch
     void* q_bf16;                  // [nq][dp8] bf16
-    float* qnorm;                  // [nq]
+    float* qnorm;                  // [nq] |q|
+    float* qres;                   // [nq] |q^ - q| (bf16 rounding residual)
     float* thr_dot;                // [nq]
     uint32_t* cand_ids;            // [nq][cap]
 };

@@ -5,7 +5,7 @@ use std::{env, path::PathBuf, process::Command};
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
-    let csrc = root.join("leann-rs_b200/csrc");
+    let csrc = root.join("leann_rs_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libleann_cuda.so");
     let mut sources = Vec::new();

@@ -1,11 +1,11 @@
-// Exercises the C++ host mirror (leann-rs_b200/host/leann_cuda.hpp) the way the reference's own unit tests
+// Exercises the C++ host mirror (leann_rs_b200/host/leann_cuda.hpp) the way the reference's own unit tests
 // exercise the Rust types: bm25.rs:264-329 and filter.rs:446-551 assertions, plus one BackendSearcher::search
 // call whose result is printed for the Python side to compare. Usage: host_mirror_test <base_path> <dims> <query.f32> [scratch_base]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
-#include "../../leann-rs_b200/host/leann_cuda.hpp"
+#include "../../leann_rs_b200/host/leann_cuda.hpp"
 
 #define REQUIRE(c) do { if (!(c)) { fprintf(stderr, "REQUIRE failed line %d: %s\n", __LINE__, #c); return 1; } } while (0)
 

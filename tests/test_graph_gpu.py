@@ -137,7 +137,7 @@ def test_request_coalescing_native_threads(orc, pkg, tmp_path):
 
 
 def test_cpp_host_mirror(orc, pkg, tmp_path):
-    """The header-only C++ host layer (leann-rs_b200/host/leann_cuda.hpp) mirrors the reference's Rust types; a
+    """The header-only C++ host layer (leann_rs_b200/host/leann_cuda.hpp) mirrors the reference's Rust types; a
     native program runs the reference's bm25/filter unit-test assertions and a trait-level search through it."""
     import os, subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,4 +1,4 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic in leann-rs_b200/shards.py: the sharded
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic in leann_rs_b200/shards.py: the sharded
 layout (every rank searches all queries in its rows, all_gather, per-query merge, global keys) and the
 replica layout (queries split, results all_gathered) must both equal a single-process search."""
 import os
