@@ -53,6 +53,7 @@ extern "C" {
 #define LEANN_MASK_INLINE 1 /* bit i set = passage i may be returned; tested inside the traversal */
 
 typedef struct leann_cuda_index leann_cuda_index;
+typedef struct leann_cuda_shards leann_cuda_shards;
 typedef struct leann_cuda_bm25 leann_cuda_bm25;
 typedef struct leann_cuda_filter leann_cuda_filter;
 typedef struct leann_cuda_metacols leann_cuda_metacols;
@@ -154,6 +155,51 @@ int leann_cuda_topk_merge_device(const uint64_t* d_keys_in, const float* d_dists
                                  char* err, size_t errlen);
 
 void leann_cuda_close(leann_cuda_index* index);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sharded backend (BASELINE north_star): the database and graph are split into sub-indexes, one per
+ * GPU; every shard searches all queries, the per-shard top-k lists are exchanged and merged per query (K4).
+ * What BackendType::load_searcher (backend/mod.rs:23-45) returns for an index that spans several GPUs;
+ * `search` keeps the contract of BackendSearcher::search (backend/traits.rs:16-21). Returned keys are global:
+ * shard key + key_offsets[shard] (key_offsets == NULL: running sum of the shard lengths, i.e. the shards are
+ * consecutive row ranges of one corpus). At most 16 shards.
+ *
+ * One host process, several devices: leann_cuda_shards_open / leann_cuda_shards_from_indexes. `exchange`:
+ *   0 automatic (peer memory when every pair of devices can map each other: the merge kernel on the first device
+ *     reads the shards' result blocks directly over NVLink, no collective launch; otherwise NCCL),
+ *   1 ncclCommInitAll + ncclAllGather + merge,   2 peer memory or fail.
+ * One process per GPU (torchrun-style): rank 0 calls leann_cuda_comm_unique_id, the caller broadcasts the 128 bytes
+ * with its own plumbing, every rank calls leann_cuda_shards_join with its local index (ncclCommInitRank inside);
+ * every rank then issues the same searches and every rank receives the merged answer.
+ * libnccl.so.2 is loaded with dlopen on first use (LEANN_CUDA_NCCL_LIB overrides the path); failures are
+ * LEANN_ERR_NCCL.
+ * ------------------------------------------------------------------------------------------- */
+int leann_cuda_shards_open(const char* const* base_paths, size_t n_shards, int backend, size_t dims, int metric,
+                           const int* devices, const uint64_t* key_offsets, int exchange, leann_cuda_shards** out,
+                           char* err, size_t errlen);
+/* Same over already opened / built handles (one per device). take_ownership != 0: shards_close closes them. */
+int leann_cuda_shards_from_indexes(leann_cuda_index* const* shards, size_t n_shards, const uint64_t* key_offsets,
+                                   int take_ownership, int exchange, leann_cuda_shards** out, char* err, size_t errlen);
+int leann_cuda_comm_unique_id(unsigned char* id, size_t id_bytes /* >= 128 */, char* err, size_t errlen);
+int leann_cuda_shards_join(leann_cuda_index* local, int take_ownership, const unsigned char* id, size_t id_bytes,
+                           int rank, int n_ranks, uint64_t key_offset, leann_cuda_shards** out, char* err, size_t errlen);
+/* BackendSearcher::len over all shards / number of shards. */
+size_t leann_cuda_shards_len(const leann_cuda_shards* shards);
+size_t leann_cuda_shards_count(const leann_cuda_shards* shards);
+/* info[0] = shards, [1] = exchange in use (0 none, 1 NCCL all_gather, 2 peer-memory merge),
+ * [2] = exchange steps so far, [3] = bytes moved between GPUs by them. */
+int leann_cuda_shards_info(const leann_cuda_shards* shards, uint64_t* info4);
+/* Host buffers, as leann_cuda_search. shard_masks: nullable; one entry per LOCAL shard (nullable each), bits indexed
+ * by the shard's own slots, tested inside the traversal (LEANN_MASK_INLINE). */
+int leann_cuda_shards_search(leann_cuda_shards* shards, const float* queries, size_t nq, size_t k, size_t ef,
+                             const uint64_t* const* shard_masks, uint64_t* keys, float* dists, uint32_t* counts,
+                             char* err, size_t errlen);
+/* Device buffers on the local shard's device, everything (search, all_gather, merge) enqueued on `cuda_stream`;
+ * handles with exactly one local shard (the process-per-GPU layout). */
+int leann_cuda_shards_search_device(leann_cuda_shards* shards, const float* d_queries, size_t nq, size_t k, size_t ef,
+                                    const uint64_t* d_mask_bits, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
+                                    void* cuda_stream, char* err, size_t errlen);
+void leann_cuda_shards_close(leann_cuda_shards* shards);
 
 /* ---------------------------------------------------------------------------------------------
  * BM25: replaces Bm25Scorer::{build,score_query,search} (index/bm25.rs:33-122), tokenize (:127-132)

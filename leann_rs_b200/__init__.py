@@ -67,6 +67,16 @@ def lib():
         "leann_cuda_search_device": (C.c_int, [vp, vp, sz, sz, sz, vp, C.c_int, vp, vp, vp, vp, vp, cp, sz]),
         "leann_cuda_topk_merge_device": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, vp, vp, vp, vp, cp, sz]),
         "leann_cuda_close": (None, [vp]),
+        "leann_cuda_shards_open": (C.c_int, [cpp, sz, C.c_int, sz, C.c_int, C.POINTER(C.c_int), u64p, C.c_int, pp, cp, sz]),
+        "leann_cuda_shards_from_indexes": (C.c_int, [pp, sz, u64p, C.c_int, C.c_int, pp, cp, sz]),
+        "leann_cuda_comm_unique_id": (C.c_int, [vp, sz, cp, sz]),
+        "leann_cuda_shards_join": (C.c_int, [vp, C.c_int, vp, sz, C.c_int, C.c_int, C.c_uint64, pp, cp, sz]),
+        "leann_cuda_shards_len": (sz, [vp]),
+        "leann_cuda_shards_count": (sz, [vp]),
+        "leann_cuda_shards_info": (C.c_int, [vp, u64p]),
+        "leann_cuda_shards_search": (C.c_int, [vp, vp, sz, sz, sz, pp, vp, vp, vp, cp, sz]),
+        "leann_cuda_shards_search_device": (C.c_int, [vp, vp, sz, sz, sz, vp, vp, vp, vp, vp, cp, sz]),
+        "leann_cuda_shards_close": (None, [vp]),
         "leann_cuda_set_visited_hash": (C.c_int, [vp, sz]),
         "leann_cuda_set_coalescing": (C.c_int, [vp, sz, C.c_uint]),
         "leann_cuda_coalescing_stats": (C.c_int, [vp, u64p, u64p]),
@@ -387,6 +397,119 @@ class FlatSearcher(BackendSearcher):
             _check(lib().leann_cuda_flat_from_device(C.c_void_p(vectors.data_ptr()), vectors.shape[0], vectors.shape[1],
                                                      metric, device, C.byref(h), e, 1024), e)
         return cls(h.value)
+
+
+EXCHANGE_AUTO, EXCHANGE_NCCL, EXCHANGE_PEER = 0, 1, 2
+
+
+class ShardedBackend:
+    """A BackendSearcher (src/backend/traits.rs:11-30) over sub-indexes on several GPUs (`leann_cuda_shards_*`):
+    every shard searches all queries, the per-shard lists are exchanged (NCCL all_gather, or peer-memory loads inside the
+    merge kernel when one process owns all devices) and merged per query on the device. Keys are global."""
+
+    def __init__(self, handle: int, parts=()):
+        self._h = C.c_void_p(handle)
+        self._parts = list(parts)   # keeps the shard searchers alive when the handle does not own them
+
+    @classmethod
+    def open(cls, base_paths: Sequence[str], backend: int, dimensions: int, devices: Sequence[int],
+             metric: int = METRIC_DEFAULT, key_offsets=None, exchange: int = EXCHANGE_AUTO):
+        _, arr, _ = _strs([os.fsencode(p) for p in base_paths])
+        devs = (C.c_int * len(devices))(*devices)
+        offs = None if key_offsets is None else (C.c_uint64 * len(key_offsets))(*key_offsets)
+        h, e = C.c_void_p(), _err()
+        _check(lib().leann_cuda_shards_open(arr, len(base_paths), backend, dimensions, metric, devs, offs, exchange,
+                                            C.byref(h), e, 1024), e)
+        return cls(h.value)
+
+    @classmethod
+    def from_searchers(cls, parts: Sequence[BackendSearcher], key_offsets=None, exchange: int = EXCHANGE_AUTO):
+        """One process, one already built/opened searcher per device."""
+        hs = (C.c_void_p * len(parts))(*[p._h for p in parts])
+        offs = None if key_offsets is None else (C.c_uint64 * len(key_offsets))(*key_offsets)
+        h, e = C.c_void_p(), _err()
+        _check(lib().leann_cuda_shards_from_indexes(hs, len(parts), offs, 0, exchange, C.byref(h), e, 1024), e)
+        return cls(h.value, parts)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf, e = C.create_string_buffer(128), _err()
+        _check(lib().leann_cuda_comm_unique_id(buf, 128, e, 1024), e)
+        return buf.raw
+
+    @classmethod
+    def join(cls, local: BackendSearcher, unique_id: bytes, rank: int, n_ranks: int, key_offset: int):
+        """One process per GPU: every rank joins with its own shard (ncclCommInitRank inside the library)."""
+        h, e = C.c_void_p(), _err()
+        idb = C.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().leann_cuda_shards_join(local._h, 0, idb, 128, rank, n_ranks, key_offset, C.byref(h), e, 1024), e)
+        return cls(h.value, [local])
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().leann_cuda_shards_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(lib().leann_cuda_shards_len(self._h))
+
+    def len(self) -> int:
+        return len(self)
+
+    def is_empty(self) -> bool:
+        return len(self) == 0
+
+    def info(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        lib().leann_cuda_shards_info(self._h, out)
+        return {"shards": int(out[0]), "exchange": {0: "none", 1: "nccl_all_gather", 2: "peer_memory_merge"}[int(out[1])],
+                "exchanges": int(out[2]), "exchange_bytes": int(out[3])}
+
+    def search(self, query, top_k: int, complexity: int = 64):
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(1, -1)
+        keys, dists, counts = self.search_batch(q, top_k, complexity)
+        c = int(counts[0])
+        return [int(x) for x in keys[0, :c]], [float(x) for x in dists[0, :c]]
+
+    def search_batch(self, queries, top_k: int, ef: int, shard_masks=None):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        keys = np.empty((nq, top_k), dtype=np.uint64)
+        dists = np.empty((nq, top_k), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.uint32)
+        mp = None
+        if shard_masks is not None:
+            ms = [None if m is None else np.ascontiguousarray(m, dtype=np.uint64) for m in shard_masks]
+            mp = (C.c_void_p * len(ms))(*[None if m is None else m.ctypes.data for m in ms])
+        e = _err()
+        _check(lib().leann_cuda_shards_search(self._h, _np_ptr(q), nq, top_k, ef, mp, _np_ptr(keys), _np_ptr(dists),
+                                              _np_ptr(counts), e, 1024), e)
+        return keys, dists, counts
+
+    def search_device(self, queries, top_k: int, ef: int, mask=None, out=None, stream=None):
+        """torch CUDA tensors on the local shard's device; search + exchange + merge on torch's current stream."""
+        import torch
+
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        nq = queries.shape[0]
+        if out is None:
+            keys = torch.empty((nq, top_k), dtype=torch.int64, device=queries.device)
+            dists = torch.empty((nq, top_k), dtype=torch.float32, device=queries.device)
+            counts = torch.empty((nq,), dtype=torch.int32, device=queries.device)
+        else:
+            keys, dists, counts = out
+        st = stream if stream is not None else torch.cuda.current_stream(queries.device).cuda_stream
+        e = _err()
+        _check(lib().leann_cuda_shards_search_device(
+            self._h, C.c_void_p(queries.data_ptr()), nq, top_k, ef, None if mask is None else C.c_void_p(mask.data_ptr()),
+            C.c_void_p(keys.data_ptr()), C.c_void_p(dists.data_ptr()), C.c_void_p(counts.data_ptr()), C.c_void_p(st), e, 1024), e)
+        return keys, dists, counts
 
 
 class BackendType:

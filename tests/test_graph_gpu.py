@@ -299,3 +299,41 @@ def test_handmade_diskann_hand_traced_on_gpu(pkg, tmp_path):
     # trait call (diskann.rs:47-62): beam = max(complexity, top_k)
     k3, d3 = s.search(q[0], 3, 1)
     assert k3 == [7, 6, 5]
+
+
+def test_workspace_sized_once_and_streams_chain(orc, pkg):
+    """(i) the host-buffer path must not size the traversal workspace with other parameters than the launch
+    (a repeated identical search performs no reallocation); (ii) device-pointer calls on different streams of one handle
+    share that workspace and must execute in call order (the library chains them with an event)."""
+    import torch
+    n, d, k, ef = 6000, 96, 10, 64
+    x, q = make_data(n, d, 21, nq=3000)
+    s = pkg.HnswSearcher.build(x, graph_degree=16, complexity=64, seed=3)
+    k0, d0, c0 = s.search_batch(q, k, ef)
+    r0 = s.workspace_stats()["reallocs"]
+    assert r0 >= 1
+    for _ in range(3):
+        k1, d1, _ = s.search_batch(q, k, ef)
+        assert np.array_equal(k1, k0) and np.array_equal(d1.view(np.uint32), d0.view(np.uint32))
+    assert s.workspace_stats()["reallocs"] == r0
+    # forced large-index mode (hash tables): same rule
+    s.set_visited_hash(4096)
+    s.search_batch(q, k, ef)
+    r1 = s.workspace_stats()["reallocs"]
+    assert s.workspace_stats()["large_mode"] == 1
+    k2, _, _ = s.search_batch(q, k, ef)
+    assert s.workspace_stats()["reallocs"] == r1 and np.array_equal(k2, k0)
+    s.set_visited_hash(0)
+    # two streams, interleaved launches, no host synchronisation in between
+    qt = torch.from_numpy(q).cuda()
+    st = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    torch.cuda.synchronize()
+    for i in range(6):
+        with torch.cuda.stream(st[i % 2]):
+            outs.append(s.search_device(qt, k, ef))
+    torch.cuda.synchronize()
+    for kk, dd, cc in outs:
+        assert np.array_equal(kk.cpu().numpy().astype(np.uint64), k0)
+        assert np.array_equal(dd.cpu().numpy().view(np.uint32), d0.view(np.uint32))
+    s.close()
