@@ -4,16 +4,26 @@
 Metric (BASELINE.json): QPS at recall@10 >= 0.95 on 1M x 768 cosine HNSW (M=32), 10k-query batches,
 plus the achieved HBM GB/s of the traversal kernel against the measured B200 peak.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--layout replica|shard]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-secondary]
 
 A step = one batch of 10 000 queries per GPU through the K1 graph-search kernel.
-`value`   : whole-job QPS with the queries already resident in HBM (CUDA events, max over ranks).
-`e2e`     : the same through the host-buffer C-ABI call (`leann_cuda_search`), pinned host
-            queries -> H2D -> kernel -> D2H of keys/distances inside the timed region.
-`roofline`: algorithmic bytes the kernel itself counted (distance evaluations x row bytes +
-            adjacency rows read) / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline` / `--impl reference`: the CPU oracle (port of the usearch search loop the
-            reference calls, hnsw.rs:85) on the box's host cores, same index file, same ef.
+`value`    : whole-job QPS with the queries already resident in HBM (CUDA events, max over ranks). For N > 1 this is
+             the REPLICA layout (index on every GPU, queries split; no data-path collective).
+`shard`    : (N > 1) the north star's database-sharded layout measured in the same run through the library's own
+             sharded handle (`leann_cuda_shards_*`): every rank owns a different 1M-row sub-index, all queries visit
+             every shard, ONE ncclAllGather of the packed (keys, dists) blocks + the K4 merge kernel per batch, all
+             inside the timed region. QPS stays that of one GPU while the database is N times larger.
+`e2e`      : the same through the host-buffer C-ABI call (`leann_cuda_search`), pinned host queries -> H2D ->
+             kernel -> D2H of keys/distances inside the timed region.
+`roofline` : algorithmic bytes the kernel itself counted (distance evaluations x row bytes + adjacency rows read) /
+             average launch duration, against MEASURED_PEAKS.json hbm_gbs.
+`secondary`: (N = 1) BASELINE configs[2..4] — exact scan 10M x 384 top-100 (tensor roofline), one 12.5M x 96 L2 Vamana
+             shard (HBM roofline), hybrid BM25 + filter over 1M passages (e2e) — each with its oracle agreement on a sample
+             (benchmarks/secondary.py).
+`cpu_baseline` / `--impl reference`: the CPU oracle (port of the usearch search loop the reference calls,
+             hnsw.rs:85) on the box's host cores, same index file, same ef: all host threads, and one thread with one
+             query per call (the reference's actual execution model, hnsw.rs:79-88). The reference arm's TIMED process
+             maps only oracle/liborc.so: the index file, queries and ground truth are produced by a child process.
 Data is synthetic (no embedding service offline): unit-normalised low-intrinsic-dimension
 embeddings x = normalise(z W + 0.3 g), z in R^32 (seeded); queries are fresh draws.
 """
@@ -38,6 +48,16 @@ RECALL_TARGET = 0.95
 EF_SWEEP = (64, 96, 128, 160, 192, 256)
 N_QUERY_BATCHES = 4
 DB_SEED, Q_SEED = 1234, 4321
+METRIC_NAME = "QPS at recall@10>=0.95, 1Mx768 cosine HNSW"
+
+
+def workload_config(n, nq):
+    """Identical in both arms (the driver compares the two `config` dicts)."""
+    return {"workload": "configs[1]: 1Mx768 cosine HNSW (usearch format), M=32, ef_add=64, top-10, 10k-query batches",
+            "n": n, "dim": DIM, "M": M_DEG, "M0": 2 * M_DEG, "ef_add": EF_ADD, "top_k": TOP_K, "queries_per_batch": nq,
+            "recall_target": RECALL_TARGET, "ef": "smallest multiple of 4 with recall@10 >= target on every cycled batch",
+            "generator": "x = normalise(z W + 0.3 g), z~N(0,I_32); DB seed 1234, query seeds 4321..",
+            "l2": "inputs larger than L2: 3.07 GB of vectors, ~190 GB gathered per 10k-query step"}
 
 
 def parse():
@@ -45,12 +65,17 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layout", default="replica", choices=["replica", "shard"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-setup"])
     ap.add_argument("--n", type=int, default=N_DB, help="database rows per index (default = the named config)")
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--cpu-sample", type=int, default=4000, help="queries in the CPU baseline sample")
+    ap.add_argument("--cpu-single", type=int, default=200, help="queries of the one-thread, one-query-per-call baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2..4] records of the N = 1 line")
+    ap.add_argument("--secondary", default="c3,c4,c5")
+    ap.add_argument("--secondary-budget-s", type=float, default=420.0, help="no new secondary record starts after this many seconds")
+    ap.add_argument("--no-shard", action="store_true", help="N > 1: skip the database-sharded layout")
+    ap.add_argument("--out", default=None, help="(reference-setup) directory for the index file, queries and ground truth")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -131,91 +156,20 @@ def recall_at_k(keys, gt):
     return (keys.unsqueeze(2) == gt.unsqueeze(1)).any(2).float().mean().item()
 
 
-def load_measured_peak():
+def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+            j = json.load(open(p))
+            float(j["hbm_gbs"])
+            return j, "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         except Exception:
             pass
-    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1395.4}, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def load_ncu_traffic(ef):
-    p = os.path.join(ROOT, "profiles", "k1_ncu_summary.json")
-    try:
-        j = json.load(open(p))
-        if j.get("n") == N_DB and j.get("dim") == DIM and j.get("ef") == ef:
-            return j.get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    return None
-
-
-def cpu_oracle_qps(index, queries_np, ef, steps, warmup, tmpdir):
-    """Times the CPU oracle (port of the reference's usearch search) on the same index file."""
-    import oracle
-    base = os.path.join(tmpdir, "documents.leann")
-    index.save(base)
-    g = oracle.Hnsw.load(base.replace(".leann", ".index"), DIM)
-    os.remove(base.replace(".leann", ".index"))
-    cores = oracle.hardware_threads()
-    times = []
-    for s in range(warmup + steps):
-        t0 = time.perf_counter()
-        keys, dists, counts, stats = g.search(queries_np, TOP_K, ef, lanes=-1, next_cap=0, nthreads=cores)
-        t1 = time.perf_counter()
-        if s >= warmup:
-            times.append(t1 - t0)
-    return queries_np.shape[0] * len(times) / sum(times), cores, keys
-
-
-def main():
-    a = parse()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.impl == "reference" and rank != 0:
-        return 0
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import leann_rs_b200 as P
-    from leann_rs_b200 import shards as S  # noqa
-
-    if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
-        return 2
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    use_dist = world > 1 and a.impl == "ours"
-    if use_dist:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    n, nq = a.n, a.nq
-    layout = a.layout if world > 1 else "single"
-
-    # ---- data + index (setup, untimed) ------------------------------------------------------------
-    W = make_W(DIM, dev)
-    db_seed = DB_SEED + (rank if layout == "shard" else 0)   # shard layout: every rank owns different rows
-    t0 = time.time()
-    x = gen_lowrank(n, DIM, db_seed, dev, W)
-    qb = [gen_lowrank(nq, DIM, Q_SEED + i, dev, W) for i in range(N_QUERY_BATCHES)]
-    torch.cuda.synchronize()
-    t_gen = time.time() - t0
-    t0 = time.time()
-    index = P.HnswSearcher.build(x, graph_degree=M_DEG, complexity=EF_ADD, seed=DB_SEED)
-    torch.cuda.synchronize()
-    t_build = time.time() - t0
-    flat = P.FlatSearcher.from_vectors(x, metric=P.METRIC_IP)
-    gts = [flat.search_device(q, TOP_K, 0)[0] for q in qb]
-    torch.cuda.synchronize()
-    flat.close()
-    del flat
-    torch.cuda.empty_cache()
-
-    # ---- recall sweep: smallest ef with recall@10 >= 0.95 (untimed) ----------------------------------
+def ef_for_recall(index, qb, gts, nq, torch):
+    """Smallest ef (multiple of 4) whose recall@10 meets the target on every cycled batch; also the published grid."""
     sweep, ef_star, rec_star = [], None, None
 
     def probe(ef):
@@ -239,8 +193,7 @@ def main():
     if ef_star is None:
         ef_star, rec_star = EF_SWEEP[-1], sweep[-1]["recall_at_10"]
     elif prev is not None:
-        # refine between the last failing and the first passing grid point (multiples of 4)
-        lo, hi = prev, ef_star
+        lo, hi = prev, ef_star   # refine between the last failing and the first passing grid point (multiples of 4)
         while hi - lo > 4:
             mid = (lo + hi) // 8 * 4
             if mid <= lo:
@@ -254,35 +207,172 @@ def main():
         if all(e["ef"] != ef for e in sweep):
             probe(ef)
     sweep.sort(key=lambda e: e["ef"])
-    # the timed region must meet the target on every cycled batch, not only on batch 0
     while ef_star < EF_SWEEP[-1] and min(recall_at_k(index.search_device(q, TOP_K, ef_star)[0], g) for q, g in zip(qb, gts)) < RECALL_TARGET:
         ef_star += 4
         rec_star = probe(ef_star)
+    return ef_star, rec_star, sweep
 
-    tmpdir = tempfile.mkdtemp(prefix="leann_bench_")
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: the TIMED process loads oracle/liborc.so only
+# ----------------------------------------------------------------------------------------------------------------
+def reference_setup(a):
+    """Child process of the reference arm: synthetic data, index file (usearch format, written by the GPU builder as
+    untimed setup — a sequential CPU build of 1M x 768 takes hours), exact ground truth and the ef that meets the
+    recall target. Writes documents.index, queries.npy, gt.npy, setup.json into --out."""
+    import numpy as np
+    import torch
+
+    import leann_rs_b200 as P
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    W = make_W(DIM, dev)
+    x = gen_lowrank(a.n, DIM, DB_SEED, dev, W)
+    qb = [gen_lowrank(a.nq, DIM, Q_SEED + i, dev, W) for i in range(N_QUERY_BATCHES)]
+    index = P.HnswSearcher.build(x, graph_degree=M_DEG, complexity=EF_ADD, seed=DB_SEED)
+    flat = P.FlatSearcher.from_vectors(x, metric=P.METRIC_IP)
+    gts = [flat.search_device(q, TOP_K, 0)[0] for q in qb]
+    torch.cuda.synchronize()
+    flat.close()
+    ef_star, rec_star, sweep = ef_for_recall(index, qb, gts, a.nq, torch)
+    index.save(os.path.join(a.out, "documents.leann"))
+    np.save(os.path.join(a.out, "queries.npy"), qb[0][: a.cpu_sample].cpu().numpy())
+    np.save(os.path.join(a.out, "gt.npy"), gts[0][: a.cpu_sample].cpu().numpy())
+    json.dump({"ef": ef_star, "recall_gpu": rec_star}, open(os.path.join(a.out, "setup.json"), "w"))
+    return 0
+
+
+def cpu_oracle_times(index_file, queries_np, ef, steps, warmup, single_n):
+    """(all-threads QPS, threads, keys, one-thread one-query-per-call QPS) of the CPU oracle on the same index file."""
+    import oracle
+    g = oracle.Hnsw.load(index_file, DIM)
+    cores = oracle.hardware_threads()
+    times, keys = [], None
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        keys, dists, counts, stats = g.search(queries_np, TOP_K, ef, lanes=-1, next_cap=0, nthreads=cores)
+        t1 = time.perf_counter()
+        if s >= warmup:
+            times.append(t1 - t0)
+    qps = queries_np.shape[0] * len(times) / sum(times)
+    single = None
+    if single_n:
+        m = min(single_n, queries_np.shape[0])
+        t0 = time.perf_counter()
+        for i in range(m):   # hnsw.rs:79-88: one query per call, one thread
+            g.search(queries_np[i:i + 1], TOP_K, ef, lanes=-1, next_cap=0, nthreads=1)
+        single = m / (time.perf_counter() - t0)
+    return qps, cores, keys, single
+
+
+def reference_arm(a):
+    import numpy as np
+    tmp = tempfile.mkdtemp(prefix="leann_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
-        if a.impl == "reference":
-            sample = qb[0][: a.cpu_sample].cpu().numpy()
-            qps, cores, ckeys = cpu_oracle_qps(index, sample, ef_star, a.steps, a.warmup, tmpdir)
-            crec = recall_at_k(torch.from_numpy(ckeys.astype(np.int64)).to(dev), gts[0][: a.cpu_sample])
-            line = {
-                "impl": "reference", "metric": "QPS at recall@10>=0.95, 1Mx768 cosine HNSW", "value": round(qps, 1),
-                "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": round(a.cpu_sample / qps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[1]: 1Mx768 cosine HNSW, M=32, ef_add=64, top-10", "n": n, "dim": DIM, "M": M_DEG,
-                           "ef": ef_star, "recall_at_10": round(crec, 4), "queries_per_step": a.cpu_sample,
-                           "note": "CPU oracle = port of usearch's search loop (reference: hnsw.rs:85); the index file "
-                                   "was written by the GPU builder as untimed setup because a sequential CPU build of 1M x 768 "
-                                   "takes hours; search itself runs only oracle code on host threads"},
-                "cpu_baseline": {"value": round(qps, 1), "unit": "queries/s", "cores": cores, "kind": "port",
-                                 "sample": f"{a.cpu_sample} queries of batch 0 per step, all host threads, SIMD-shaped f32 dot"},
-                "e2e": {"value": round(qps, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0,
-            }
-            print(json.dumps(line))
-            return 0
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-setup", "--out", tmp, "--n", str(a.n), "--nq", str(a.nq),
+               "--cpu-sample", str(a.cpu_sample)]
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE")}
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            print(json.dumps({"impl": "reference", "error": "setup child failed", "stderr": r.stderr[-2000:]}))
+            return 1
+        st = json.load(open(os.path.join(tmp, "setup.json")))
+        q = np.load(os.path.join(tmp, "queries.npy"))
+        gt = np.load(os.path.join(tmp, "gt.npy"))
+        ef = int(st["ef"])
+        qps, cores, keys, single = cpu_oracle_times(os.path.join(tmp, "documents.index"), q, ef, a.steps, a.warmup, a.cpu_single)
+        rec = float(np.mean((keys.astype(np.int64)[:, :, None] == gt[:, None, :]).any(2)))
+        mapped = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ln.rstrip().endswith(".so") and
+                         ("leann" in ln or "liborc" in ln or "libcuda" in ln or "libtorch" in ln)})
+        line = {
+            "impl": "reference", "metric": METRIC_NAME, "value": round(qps, 1), "unit": "queries/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(q.shape[0] / qps * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a.n, a.nq),
+            "operating_point": {"ef": ef, "recall_at_10": round(rec, 4), "recall_at_10_gpu_same_ef": st.get("recall_gpu")},
+            "cpu_baseline": {"value": round(qps, 1), "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": f"{q.shape[0]} queries of batch 0 per step, all host threads, SIMD-shaped f32 dot",
+                             "single_thread": {"value": None if single is None else round(single, 1), "unit": "queries/s", "cores": 1,
+                                               "sample": f"{min(a.cpu_single, q.shape[0])} queries, one query per call on one thread "
+                                                         "(the reference's execution model, hnsw.rs:79-88)"},
+                             "build_flags": "-O3 -mavx2 -mfma (oracle/Makefile; the .so is built in the container and travels)"},
+            "e2e": {"value": round(qps, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU oracle = port of usearch's search loop (reference: hnsw.rs:85). The index file, queries and ground truth "
+                    "come from a child process (GPU builder, untimed setup); this timed process maps: " + ", ".join(os.path.basename(m) for m in mapped),
+        }
+        print(json.dumps(line))
+        return 0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference-setup":
+        return reference_setup(a)
+    if a.impl == "reference":
+        return reference_arm(a) if rank == 0 else 0
+    t_start = time.time()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import leann_rs_b200 as P
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    use_dist = world > 1
+    if use_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, nq = a.n, a.nq
+    peaks, peak_src = load_peaks()
+    peak = float(peaks["hbm_gbs"])
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(vals):
+        if not use_dist:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    # ---- data + index (setup, untimed) ------------------------------------------------------------
+    W = make_W(DIM, dev)
+    t0 = time.time()
+    x = gen_lowrank(n, DIM, DB_SEED, dev, W)
+    qb = [gen_lowrank(nq, DIM, Q_SEED + i, dev, W) for i in range(N_QUERY_BATCHES)]
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    index = P.HnswSearcher.build(x, graph_degree=M_DEG, complexity=EF_ADD, seed=DB_SEED)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    flat = P.FlatSearcher.from_vectors(x, metric=P.METRIC_IP)
+    gts = [flat.search_device(q, TOP_K, 0)[0] for q in qb]
+    torch.cuda.synchronize()
+    flat.close()
+    del flat, x
+    torch.cuda.empty_cache()
+    ef_star, rec_star, sweep = ef_for_recall(index, qb, gts, nq, torch)
+    if use_dist:   # every rank runs the same ef (graphs differ slightly between ranks: GPU build order)
+        t = torch.tensor([ef_star], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ef_star = int(t.item())
+
+    tmpdir = tempfile.mkdtemp(prefix="leann_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
         # ---- algorithmic bytes per batch, counted by the kernel ------------------------------------------
         info = index.info()
         row_bytes = ((DIM + 3) // 4) * 16
@@ -295,25 +385,8 @@ def main():
             bytes_per_batch.append(tot[0] * row_bytes + tot[1] * info["M0"] * 4 + tot[2] * info["M"] * 4)
             ndist_mean.append(tot[0] / nq)
 
-        # ---- the search callable of this layout -------------------------------------------------------------
-        def local_search(q, k, ef):
-            kk, dd, _ = index.search_device(q, k, ef)
-            return kk, dd
-
-        if layout == "shard":
-            eng = S.ShardedSearcher(local_search, rank * n, world, rank, False,
-                                    lambda gk, gd, desc: P.topk_merge_device(gk, gd, desc)[:2], dist)
-            step_fn = lambda i: eng.search(qb[i % N_QUERY_BATCHES], TOP_K, ef_star)
-            queries_per_step_job = nq
-        else:
-            step_fn = lambda i: local_search(qb[i % N_QUERY_BATCHES], TOP_K, ef_star)
-            queries_per_step_job = nq * world
-
-        def barrier():
-            if use_dist:
-                dist.barrier()
-            torch.cuda.synchronize()
-
+        # ---- timed region: value (replica layout for N > 1: this rank's 10k queries on its own copy) ------
+        step_fn = lambda i: index.search_device(qb[i % N_QUERY_BATCHES], TOP_K, ef_star)
         for i in range(a.warmup):
             step_fn(i)
         barrier()
@@ -358,18 +431,16 @@ def main():
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop()
         e2e_rec = recall_at_k(hk.to(dev), gts[(a.steps - 1) % N_QUERY_BATCHES])
+        total_ms, e2e_s = max_over_ranks([total_ms, e2e_s])
+        value = nq * world * a.steps / (total_ms / 1e3)
+        e2e_value = nq * world * a.steps / e2e_s
 
-        if use_dist:
-            t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms, e2e_s = t.tolist()
-        value = queries_per_step_job * a.steps / (total_ms / 1e3)
-        e2e_value = (nq * world if layout != "shard" else nq) * a.steps / e2e_s
-        if layout == "shard":
-            e2e_value = None  # the host-buffer call is per rank; the sharded merge runs on device tensors
+        # ---- N > 1: the database-sharded layout through the library's sharded handle ------------------------
+        shard = None
+        if use_dist and not a.no_shard:
+            shard = shard_layout(P, torch, dist, dev, rank, world, n, nq, W, qb, ef_star, a, max_over_ranks, barrier, hq)
 
         # ---- roofline of the dominant kernel (K1) --------------------------------------------------------------
-        peak, peak_src = load_measured_peak()
         mean_bytes = sum(bytes_per_batch[i % N_QUERY_BATCHES] for i in range(a.steps)) / a.steps
         mean_ms = sum(step_ms) / len(step_ms)
         achieved = mean_bytes / (mean_ms / 1e3) / 1e9
@@ -377,46 +448,143 @@ def main():
         cpu = None
         if rank == 0 and world == 1 and not a.no_cpu_baseline:
             sample = qb[0][: a.cpu_sample].cpu().numpy()
-            qps, cores, ckeys = cpu_oracle_qps(index, sample, ef_star, 1, 0, tmpdir)
+            index.save(os.path.join(tmpdir, "documents.leann"))
+            qps, cores, ckeys, single = cpu_oracle_times(os.path.join(tmpdir, "documents.index"), sample, ef_star, 1, 0, a.cpu_single)
+            os.remove(os.path.join(tmpdir, "documents.index"))
             same = float((torch.from_numpy(ckeys.astype(np.int64)).to(dev) == index.search_device(qb[0][: a.cpu_sample].contiguous(), TOP_K, ef_star)[0]).float().mean().item())
             cpu = {"value": round(qps, 1), "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": f"{a.cpu_sample} queries of batch 0, one pass, all host threads, same index file and ef; "
-                             f"id agreement with the GPU result {same:.4f} (different f32 summation order)"}
+                             f"id agreement with the GPU result {same:.4f} (different f32 summation order)",
+                   "single_thread": {"value": None if single is None else round(single, 1), "unit": "queries/s", "cores": 1,
+                                     "sample": f"{min(a.cpu_single, a.cpu_sample)} queries, one query per call on one thread "
+                                               "(the reference's execution model, hnsw.rs:79-88)"},
+                   "build_flags": "-O3 -mavx2 -mfma (oracle/Makefile; the .so is built in the container and travels)"}
 
+        line = None
         if rank == 0:
+            cfg = workload_config(n, nq)
             line = {
-                "metric": "QPS at recall@10>=0.95, 1Mx768 cosine HNSW", "value": round(value, 1), "unit": "queries/s",
+                "metric": METRIC_NAME, "value": round(value, 1), "unit": "queries/s",
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(total_ms / a.steps, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {
-                    "workload": "configs[1]: 1Mx768 cosine HNSW (usearch format), M=32, ef_add=64, top-10, 10k-query batches",
-                    "n": n, "dim": DIM, "M": M_DEG, "M0": info["M0"], "ef": ef_star, "recall_at_10": round(rec_star, 4),
-                    "recall_target": RECALL_TARGET, "queries_per_step_per_gpu": nq, "query_batches_cycled": N_QUERY_BATCHES,
-                    "parallelism": {"single": "1 GPU", "replica": f"replica x{world}: index replicated, queries split, no data-path collective",
-                                    "shard": f"db-shard x{world}: {n} rows per GPU, all queries on every shard, NCCL all_gather + top-k merge kernel"}[layout],
-                    "l2": "inputs larger than L2: 3.07 GB of vectors, ~%.0f GB gathered per step" % (mean_bytes / 1e9),
-                    "generator": "x = normalise(z W + 0.3 g), z~N(0,I_32); DB seed 1234, query seeds 4321..",
-                    "index_build_s": round(t_build, 2), "datagen_s": round(t_gen, 2),
-                    "mean_distance_evals_per_query": round(sum(ndist_mean) / len(ndist_mean), 1),
-                },
+                "config": cfg,
+                "operating_point": {"ef": ef_star, "recall_at_10": round(rec_star, 4), "index_build_s": round(t_build, 2),
+                                    "datagen_s": round(t_gen, 2), "query_batches_cycled": N_QUERY_BATCHES,
+                                    "mean_distance_evals_per_query": round(sum(ndist_mean) / len(ndist_mean), 1)},
+                "parallelism": "1 GPU" if world == 1 else
+                               f"value = replica x{world}: the index on every GPU, {nq} queries per GPU per step, no data-path collective "
+                               f"(weak scaling in queries); 'shard' = database-sharded x{world} with ncclAllGather + merge kernel in the timed region",
                 "recall_sweep": sweep,
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": load_ncu_traffic(ef_star),
-                             "peak_source": peak_src, "kernel": "graph_search_kernel<32,6,4>",
+                             "frac": round(achieved / peak, 4), "traffic": None,
+                             "traffic_note": "not measured in this run; ncu capture of the same kernel: profiles/ (dram bytes / algorithmic = 1.03)",
+                             "peak_source": peak_src, "kernel": "graph_search_kernel<32,6,4,3> (LPV=32 lanes/vector, VPL=6 float4/lane, unroll 4, 3 CTAs/SM)",
                              "algorithmic_bytes_per_launch": int(mean_bytes), "launch_ms": round(mean_ms, 4)},
                 "cpu_baseline": cpu,
-                "e2e": {"value": None if e2e_value is None else round(e2e_value, 1), "unit": "queries/s",
+                "e2e": {"value": round(e2e_value, 1), "unit": "queries/s",
                         "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * TOP_K * 12 + nq * 4,
-                        "recall_at_10": round(e2e_rec, 4)},
-                "gpu_launches": a.steps * (2 if layout == "shard" else 1),
+                        "recall_at_10": round(e2e_rec, 4), "api": "leann_cuda_search (host buffers, pinned)"},
+                "gpu_launches": a.steps,
                 "clocks": clocks,
             }
+            if shard is not None:
+                line["shard"] = shard
+
+        # ---- N = 1: secondary records (configs[2..4]) ----------------------------------------------------------
+        if rank == 0 and world == 1 and not a.no_secondary:
+            import oracle
+            oracle.build()
+            from benchmarks import secondary as S2
+            sec = {}
+            wanted = [s.strip() for s in a.secondary.split(",") if s.strip()]
+            # c5 first: it reuses the 1M x 768 index of the headline; then the index is released
+            for name in [w for w in ("c5", "c3", "c4") if w in wanted]:
+                if time.time() - t_start > a.secondary_budget_s:
+                    sec[name] = {"skipped": f"time budget ({a.secondary_budget_s:.0f} s) reached before this record started"}
+                    continue
+                t0 = time.time()
+                try:
+                    if name == "c5":
+                        sec[name] = S2.run_c5(P, torch, dev, oracle, peaks, index, qb[0])
+                        index.close()
+                        torch.cuda.empty_cache()
+                    elif name == "c3":
+                        sec[name] = S2.run_c3(P, torch, dev, oracle, peaks)
+                    else:
+                        sec[name] = S2.run_c4(P, torch, dev, oracle, peaks)
+                    sec[name]["wall_s"] = round(time.time() - t0, 1)
+                except Exception as ex:   # a secondary record must never lose the headline
+                    sec[name] = {"error": f"{type(ex).__name__}: {ex}"[:500]}
+            line["secondary"] = {k: sec[k] for k in ("c3", "c4", "c5") if k in sec}
+        if rank == 0:
+            line["wall_s"] = round(time.time() - t_start, 1)
             print(json.dumps(line))
     finally:
         shutil.rmtree(tmpdir, ignore_errors=True)
         if use_dist:
             dist.destroy_process_group()
     return 0
+
+
+def shard_layout(P, torch, dist, dev, rank, world, n, nq, W, qb, ef, a, max_over_ranks, barrier, hq):
+    """North-star multi-GPU layout: rank r owns rows [r*n, (r+1)*n) of an (n * world)-row database as its own HNSW
+    sub-index; every rank searches all queries; per batch ONE ncclAllGather of packed (keys, dists) + the K4 merge,
+    all inside `leann_cuda_shards_search_device` on one stream. Ground truth = exact scan shards through the same handle."""
+    t0 = time.time()
+    xs = gen_lowrank(n, DIM, DB_SEED + 1000 + rank, dev, W)
+    part = P.HnswSearcher.build(xs, graph_degree=M_DEG, complexity=EF_ADD, seed=DB_SEED + rank)
+    flat = P.FlatSearcher.from_vectors(xs, metric=P.METRIC_IP)
+    del xs
+
+    def joined(local):
+        uid = [P.ShardedBackend.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        return P.ShardedBackend.join(local, uid[0], rank, world, rank * n)
+
+    gsh = joined(flat)
+    gts = [gsh.search_device(q, TOP_K, 0)[0] for q in qb]
+    torch.cuda.synchronize()
+    gsh.close()
+    flat.close()
+    torch.cuda.empty_cache()
+    sh = joined(part)
+    t_setup = time.time() - t0
+    step = lambda i: sh.search_device(qb[i % N_QUERY_BATCHES], TOP_K, ef)
+    local = lambda i: part.search_device(qb[i % N_QUERY_BATCHES], TOP_K, ef)
+
+    def timed(fn):
+        for i in range(a.warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    ms_shard = timed(step)
+    ms_local = timed(local)
+    rec = min(recall_at_k(sh.search_device(q, TOP_K, ef)[0], g) for q, g in zip(qb, gts))
+    # host buffers end to end through leann_cuda_shards_search
+    hk = sh.search_batch(hq[0].numpy(), TOP_K, ef)[0]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        sh.search_batch(hq[i % N_QUERY_BATCHES].numpy(), TOP_K, ef)
+    e2e_s = time.perf_counter() - t0
+    info = sh.info()
+    ms_shard, ms_local, e2e_s = max_over_ranks([ms_shard, ms_local, e2e_s])
+    out = {"value": round(nq * a.steps / (ms_shard / 1e3), 1), "unit": "queries/s", "ms_per_step": round(ms_shard / a.steps, 4),
+           "local_search_ms": round(ms_local / a.steps, 4), "merge_ms": round((ms_shard - ms_local) / a.steps, 4),
+           "allgather_bytes": int(world * ((nq * TOP_K * 12 + 255) // 256 * 256)), "exchange": info["exchange"],
+           "recall_at_10": round(rec, 4), "ef": ef, "database_rows": n * world, "rows_per_gpu": n, "scaling": "weak (capacity x N at ~constant QPS)",
+           "e2e_value": round(nq * a.steps / e2e_s, 1), "api": "leann_cuda_shards_join + leann_cuda_shards_search_device (ncclAllGather + topk_merge_ptr_kernel)",
+           "gpu_launches": 2 * a.steps, "setup_s": round(t_setup, 1)}
+    sh.close()
+    part.close()
+    return out
 
 
 if __name__ == "__main__":
