@@ -1,0 +1,43 @@
+"""A/B harness for K1 on short rows (C4 shard: Vamana n x 96 L2, R = 64): one index, several kernel instantiations selected
+through LEANN_K1_TUNE / LEANN_CUDA_DISABLE_REG_LISTS, results compared bit for bit with the shared-memory-list kernel."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import leann_rs_b200 as P
+from benchmarks import secondary as S2
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=12_500_000); ap.add_argument("--d", type=int, default=96)
+ap.add_argument("--nq", type=int, default=10_000); ap.add_argument("--variants", default="base,4,6;4,5;3,6;3,5;2,6;2,7;2,8;4,4")
+ap.add_argument("--efs", default="50,100"); ap.add_argument("--steps", type=int, default=5)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+W = S2._make_W(torch, dev, 16, a.d)
+x = S2._gen(torch, dev, a.n, a.d, 1234, W, normalize=False)
+q = S2._gen(torch, dev, a.nq, a.d, 4321, W, normalize=False)
+t0 = time.time()
+idx = P.DiskAnnSearcher.build(x, graph_degree=64, complexity=100, alpha=1.2, metric=P.METRIC_L2SQ)
+torch.cuda.synchronize()
+print("build_s", round(time.time() - t0, 1), flush=True)
+del x
+info = idx.info()
+rows = []
+ref = {}
+variants = [v for v in a.variants.replace("base,", "base;").split(";") if v]
+for v in variants:
+    if v == "base":
+        os.environ["LEANN_CUDA_DISABLE_REG_LISTS"] = "1"; os.environ.pop("LEANN_K1_TUNE", None)
+    else:
+        os.environ.pop("LEANN_CUDA_DISABLE_REG_LISTS", None); os.environ["LEANN_K1_TUNE"] = v
+    for ef in [int(e) for e in a.efs.split(",")]:
+        st = torch.zeros((a.nq, 4), dtype=torch.int64, device=dev)
+        keys, dists, _ = idx.search_device(q, 10, ef, stats=st)
+        torch.cuda.synchronize()
+        if v == "base":
+            ref[ef] = (keys.clone(), dists.clone(), st.clone())
+        same = bool(torch.equal(keys, ref[ef][0]) and torch.equal(dists.view(torch.int32), ref[ef][1].view(torch.int32)) and torch.equal(st, ref[ef][2])) if ef in ref else None
+        tot = st.sum(0).tolist()
+        byts = tot[0] * ((a.d + 3) // 4) * 16 + tot[1] * info["M0"] * 4
+        ms, step_ms = S2._timed(torch, lambda: idx.search_device(q, 10, ef), a.steps, 3)
+        rows.append({"variant": v, "ef": ef, "ms": round(ms, 3), "qps": round(a.nq / ms * 1e3), "frac": round(byts / ms / 1e6 / 6538.0, 4), "identical_to_base": same})
+        print(json.dumps(rows[-1]), flush=True)

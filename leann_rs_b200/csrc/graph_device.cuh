@@ -466,4 +466,197 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident lists (short rows). At d <= 256 a hop moves little data and the traversal is bound by issued
+// instructions: the shared-memory sorted inserts above (rank scan + shift loop, two __syncwarp per 32 entries) were
+// about two thirds of all instructions of a hop at d = 96. Here `top` and `next` live in registers, EPL entries per
+// lane in blocked layout (entry i = lane i / EPL, register i % EPL), ascending, unused entries = +inf:
+//   rank    = EPL compares per lane + one ballot + one shuffle,
+//   insert  = one shuffle per array (carry from the previous lane) + predicated moves,
+//   pop     = one shuffle per array.
+// Semantics are those of sorted_insert<UPPER, ...> (usearch sorted_buffer_gt::insert with a bounded size): identical
+// results, bit for bit. Used when ef and the queue capacity fit in 32 * EPL entries and no inline mask is set.
+template <int EPL>
+struct RegList {
+    float d[EPL];
+    uint32_t s[EPL];
+    int size;
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) { d[j] = CUDART_INF_F; s[j] = SENT; }
+        size = 0;
+    }
+    // #entries < dd (UPPER: <= dd). Entries are sorted, so lanes whose EPL entries all count form a prefix.
+    template <bool UPPER>
+    __device__ __forceinline__ int rank(float dd) const {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) c += (UPPER ? (d[j] <= dd) : (d[j] < dd)) ? 1 : 0;
+        const int full = __popc(__ballot_sync(FULL, c == EPL));
+        const int rem = __shfl_sync(FULL, c, full & 31);
+        return full == 32 ? 32 * EPL : full * EPL + rem;
+    }
+    // insert at `pos` (< limit), dropping the last entry when the list already holds `limit`
+    __device__ __forceinline__ void insert_at(int pos, float dd, uint32_t ss, int limit, int lane) {
+        const int lp = pos / EPL, rp = pos % EPL;
+        const float cd = __shfl_up_sync(FULL, d[EPL - 1], 1);
+        const uint32_t cs = __shfl_up_sync(FULL, s[EPL - 1], 1);
+        if (lane > lp) {
+#pragma unroll
+            for (int j = EPL - 1; j >= 1; --j) { d[j] = d[j - 1]; s[j] = s[j - 1]; }
+            d[0] = cd; s[0] = cs;
+        } else if (lane == lp) {
+#pragma unroll
+            for (int j = EPL - 1; j >= 1; --j)
+                if (j > rp) { d[j] = d[j - 1]; s[j] = s[j - 1]; }
+#pragma unroll
+            for (int j = 0; j < EPL; ++j)
+                if (j == rp) { d[j] = dd; s[j] = ss; }
+        }
+        if (size == limit) {
+            if (limit < 32 * EPL && lane == limit / EPL) {   // the entry pushed past the bound is dropped
+#pragma unroll
+                for (int j = 0; j < EPL; ++j)
+                    if (j == limit % EPL) { d[j] = CUDART_INF_F; s[j] = SENT; }
+            }
+        } else {
+            size++;
+        }
+    }
+    template <bool UPPER>
+    __device__ __forceinline__ bool insert(float dd, uint32_t ss, int limit, int lane) {
+        const int pos = rank<UPPER>(dd);
+        if (pos >= limit) return false;
+        insert_at(pos, dd, ss, limit, lane);
+        return true;
+    }
+    __device__ __forceinline__ float dist_at(int i) const {
+        float v = d[0];
+#pragma unroll
+        for (int j = 1; j < EPL; ++j)
+            if (j == i % EPL) v = d[j];
+        return __shfl_sync(FULL, v, i / EPL);
+    }
+    __device__ __forceinline__ void pop_front(int lane) {
+        const float nd = __shfl_down_sync(FULL, d[0], 1);
+        const uint32_t ns = __shfl_down_sync(FULL, s[0], 1);
+#pragma unroll
+        for (int j = 0; j + 1 < EPL; ++j) { d[j] = d[j + 1]; s[j] = s[j + 1]; }
+        d[EPL - 1] = lane == 31 ? CUDART_INF_F : nd;
+        s[EPL - 1] = lane == 31 ? SENT : ns;
+        size--;
+    }
+};
+
+// beam_level with register lists: same loop as beam_level<..., PREFETCH = true> without a mask.
+template <int LPV, int VPL, int U, int EPL>
+__device__ __forceinline__ void beam_level_regs(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL], WarpLists& w,
+                                                RegList<EPL>& top, RegList<EPL>& next, int ef, int next_cap, int nonstrict,
+                                                VisitedSet& vs, uint32_t warp_id, uint32_t start, float start_d,
+                                                Counters& c, int lane) {
+    top.clear();
+    next.clear();
+    float radius = CUDART_INF_F;
+    next.template insert<true>(start_d, start, next_cap, lane);
+    if (lane == 0) visited_test_and_set(vs, start);
+    visited_added(vs, 1u, warp_id, lane);
+    top.template insert<false>(start_d, start, ef, lane);
+    if (top.size == ef) radius = top.dist_at(ef - 1);
+    while (next.size > 0) {
+        const float cd = __shfl_sync(FULL, next.d[0], 0);
+        const uint32_t cs = __shfl_sync(FULL, next.s[0], 0);
+        if (nonstrict ? (cd >= radius) : (cd > radius)) break;
+        next.pop_front(lane);
+        if (adj.level == 0) c.n_hops0++; else c.n_hops_upper++;
+        const uint32_t* row = adj.row(cs);
+        if (adj.level == 0 && next.size > 0) {
+            // the most likely next pop is the new head of the queue: pull its adjacency row into L2 now
+            const uint32_t nh = __shfl_sync(FULL, next.s[0], 0);
+            if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
+        }
+        int cnt = 0;
+        constexpr int NCH = MAX_DEG / 32;
+        uint32_t sv[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const uint32_t j = (uint32_t)ch * 32u + lane;
+            sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
+        }
+        bool fr[NCH];
+        if (vs.hashed) {
+            uint32_t h[NCH];
+            bool act[NCH];
+            bool any = false;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) { h[ch] = (sv[ch] * 0x9E3779B1u) >> vs.shift; act[ch] = sv[ch] != SENT; fr[ch] = false; any |= act[ch]; }
+            while (any) {
+                uint32_t old[NCH];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) if (act[ch]) old[ch] = atomicCAS(vs.tbl + h[ch], VIS_EMPTY, sv[ch]);
+                any = false;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+                    if (act[ch]) {
+                        if (old[ch] == VIS_EMPTY) { fr[ch] = true; act[ch] = false; }
+                        else if (old[ch] == sv[ch]) act[ch] = false;
+                        else { h[ch] = (h[ch] + 1u) & vs.cap_mask; any = true; }
+                    }
+            }
+        } else {
+            uint8_t tg[NCH];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vs.vis[sv[ch]] : vs.tag;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                fr[ch] = tg[ch] != vs.tag;
+                if (fr[ch]) vs.vis[sv[ch]] = vs.tag;
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            if ((uint32_t)ch * 32u >= adj.deg) break;
+            const bool fresh = fr[ch];
+            const unsigned b = __ballot_sync(FULL, fresh);
+            if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = sv[ch];
+            cnt += __popc(b);
+        }
+        __syncwarp();
+        c.n_dist += cnt;
+        visited_added(vs, (uint32_t)cnt, warp_id, lane);
+        {
+            constexpr int BATCH = U * (32 / LPV);
+            const uint32_t lines = (g.d4 * 16u + 127u) >> 7;
+            for (int j = BATCH + lane; j < cnt; j += 32) {
+                const char* r = reinterpret_cast<const char*>(g.vecs + (size_t)w.st_slot[j] * g.d4);
+                for (uint32_t l = 0; l < lines; ++l) prefetch_l2(r + l * 128u);
+            }
+        }
+        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+        // ---- replay the inserts in list order (usearch loop), lists in registers ----
+        for (int base = 0; base < cnt; base += 32) {
+            const int j = base + lane;
+            const float dj = j < cnt ? w.st_dist[j] : CUDART_INF_F;
+            const uint32_t sj = j < cnt ? w.st_slot[j] : SENT;
+            unsigned m = __ballot_sync(FULL, j < cnt && (top.size < ef || dj < radius));
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const float dd = __shfl_sync(FULL, dj, l);
+                if (top.size < ef || dd < radius) {
+                    const uint32_t ss = __shfl_sync(FULL, sj, l);
+                    if (next.size == next_cap) c.dropped = 1;
+                    next.template insert<true>(dd, ss, next_cap, lane);
+                    top.template insert<false>(dd, ss, ef, lane);
+                    if (top.size == ef) {
+                        radius = top.dist_at(ef - 1);
+                        m &= __ballot_sync(FULL, dj < radius);   // later entries that can no longer pass are skipped now
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace leann

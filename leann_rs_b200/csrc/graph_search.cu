@@ -8,11 +8,16 @@
 // Bound: HBM gather bandwidth. Algorithmic bytes per query =
 //     n_dist * d4*16  +  n_hops0 * deg0*4  +  n_hops_upper * degU*4      
 // all three counted by the kernel itself (out_stats) and by the oracle.
+#include <cstdlib>
+#include <string>
+
 #include "graph_device.cuh"
 
 namespace leann {
 
-template <int LPV, int VPL, int U, int MINB>
+// EPL > 0: `top` / `next` live in registers (RegList<EPL>, graph_device.cuh); the host picks that instantiation for short
+// rows when max(ef, queue capacity) <= 32 * EPL and no mask is set. Shared memory then holds only the staging row.
+template <int LPV, int VPL, int U, int MINB, int EPL>
 __global__ void __launch_bounds__(128, MINB)
 graph_search_kernel(const GraphView g, const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -21,16 +26,17 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
     if (warp_global >= p.n_warps) return;
 
-    const uint32_t ef_pad = (p.ef + 31u) & ~31u;
-    const size_t per_warp = (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 8;
+    const uint32_t ef_pad = EPL > 0 ? 0u : ((p.ef + 31u) & ~31u);
+    const uint32_t ncapp = EPL > 0 ? 0u : p.next_capp;
+    const size_t per_warp = (size_t)ef_pad * 8 + (size_t)ncapp * 8 + (size_t)MAX_DEG * 8;
     unsigned char* base = smem_raw + per_warp * warp_in_block;
     WarpLists w;
     w.top_d = reinterpret_cast<float*>(base);
     w.top_s = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 4);
     w.next_d = reinterpret_cast<float*>(base + (size_t)ef_pad * 8);
-    w.next_s = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 4);
-    w.st_slot = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8);
-    w.st_dist = reinterpret_cast<float*>(base + (size_t)ef_pad * 8 + (size_t)p.next_capp * 8 + (size_t)MAX_DEG * 4);
+    w.next_s = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)ncapp * 4);
+    w.st_slot = reinterpret_cast<uint32_t*>(base + (size_t)ef_pad * 8 + (size_t)ncapp * 8);
+    w.st_dist = reinterpret_cast<float*>(base + (size_t)ef_pad * 8 + (size_t)ncapp * 8 + (size_t)MAX_DEG * 4);
 
     VisitedSet vs;
     vs.n_pad = p.n_pad;
@@ -65,22 +71,39 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         if (g.max_level > 0) greedy_descend<LPV, VPL, U>(g, q, w, cur, cur_d, g.max_level, 0, c, lane);
 
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
-        beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
-                                p.mask, vs, (uint32_t)warp_global, cur, cur_d, c, lane);
-        visited_end(vs, lane);
-
-        // results: ascending, truncated to k; tail = UINT64_MAX / +inf
-        const int cnt = w.top_size < (int)p.k ? w.top_size : (int)p.k;
-        for (uint32_t i = lane; i < p.k; i += 32) {
-            uint64_t key = ~0ull;
-            float dd = CUDART_INF_F;
-            if ((int)i < cnt) {
-                uint32_t s = w.top_s[i];
-                key = g.keys ? g.keys[s] : (uint64_t)s;
-                dd = w.top_d[i];
+        int cnt;
+        if constexpr (EPL > 0) {
+            RegList<EPL> top, next;
+            beam_level_regs<LPV, VPL, U, EPL>(g, adj, q, w, top, next, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
+                                              (uint32_t)warp_global, cur, cur_d, c, lane);
+            visited_end(vs, lane);
+            cnt = top.size < (int)p.k ? top.size : (int)p.k;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const uint32_t i = (uint32_t)(lane * EPL + j);
+                if (i < p.k) {
+                    const bool ok = (int)i < cnt;
+                    p.out_keys[(size_t)qi * p.k + i] = ok ? (g.keys ? g.keys[top.s[j]] : (uint64_t)top.s[j]) : ~0ull;
+                    p.out_dists[(size_t)qi * p.k + i] = ok ? top.d[j] : CUDART_INF_F;
+                }
             }
-            p.out_keys[(size_t)qi * p.k + i] = key;
-            p.out_dists[(size_t)qi * p.k + i] = dd;
+        } else {
+            beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
+                                                p.mask, vs, (uint32_t)warp_global, cur, cur_d, c, lane);
+            visited_end(vs, lane);
+            // results: ascending, truncated to k; tail = UINT64_MAX / +inf
+            cnt = w.top_size < (int)p.k ? w.top_size : (int)p.k;
+            for (uint32_t i = lane; i < p.k; i += 32) {
+                uint64_t key = ~0ull;
+                float dd = CUDART_INF_F;
+                if ((int)i < cnt) {
+                    uint32_t s = w.top_s[i];
+                    key = g.keys ? g.keys[s] : (uint64_t)s;
+                    dd = w.top_d[i];
+                }
+                p.out_keys[(size_t)qi * p.k + i] = key;
+                p.out_dists[(size_t)qi * p.k + i] = dd;
+            }
         }
         if (lane == 0) {
             if (p.out_counts) p.out_counts[qi] = (uint32_t)cnt;
@@ -195,11 +218,21 @@ int graph_search_max_warps(int device) {
 
 namespace {
 // op 0: launch; op 1: report resident warps per SM for this instantiation and shared-memory size.
-template <int LPV, int VPL, int U, int MINB>
+constexpr int REG_EPL = 4;   // register lists: up to 128 entries
+inline bool use_reg_lists(const SearchParams& p) {
+    return p.mask == nullptr && p.ef <= 32u * REG_EPL && p.next_cap <= 32u * REG_EPL && p.k <= 32u * REG_EPL;
+}
+
+template <int LPV, int VPL, int U, int MINB, int EPL = 0>
 int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
+    if constexpr (EPL == 0 && LPV < 32) {
+        // short rows: the register-list instantiation when the lists fit (small batches keep the cooperative kernel)
+        const bool off = getenv("LEANN_CUDA_DISABLE_REG_LISTS") != nullptr;   // A/B switch for benchmarks
+        if (!off && p.coop_ctas == 0 && use_reg_lists(p)) return launch_t<LPV, VPL, U, MINB, REG_EPL>(g, p, stream, op);
+    }
     const int warps_per_block = 4;
-    size_t smem = graph_search_smem_per_warp(p.ef, p.next_capp) * warps_per_block;
-    auto kern = graph_search_kernel<LPV, VPL, U, MINB>;
+    size_t smem = (EPL > 0 ? (size_t)MAX_DEG * 8 : graph_search_smem_per_warp(p.ef, p.next_capp)) * warps_per_block;
+    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL>;
     if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (op == 1) {
         int blocks_per_sm = 0;
@@ -210,6 +243,7 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
     if (p.coop_ctas > 0) {
         // small batch: one CTA of COOP_WARPS warps per query (visited slices are indexed by CTA, so coop_ctas <= n_warps)
         const int cw = p.coop_warps == 8 ? 8 : 4;
+        if constexpr (EPL > 0) throw Error(LEANN_ERR_INVALID_ARG, "internal: register lists are not used by the cooperative kernel");
         auto ck = cw == 8 ? graph_search_coop_kernel<LPV, VPL, U, MINB, 8> : graph_search_coop_kernel<LPV, VPL, U, MINB, 4>;
         const size_t csmem = graph_search_smem_per_warp(p.ef, p.next_capp);
         if (csmem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
@@ -232,7 +266,21 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
         // small rows: the traversal is instruction-latency bound, so favour resident warps over unroll depth
         uint32_t vpl = (d4 + 7) / 8;
         if (vpl <= 2) return launch_t<8, 2, 4, 6>(g, p, stream, op);
-        if (vpl <= 3) return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
+        if (vpl <= 3) {
+            // TUNING (temporary): LEANN_K1_TUNE=U,MINB picks a register-list instantiation
+            const char* tune = getenv("LEANN_K1_TUNE");
+            if (tune && p.coop_ctas == 0 && use_reg_lists(p)) {
+                const std::string t(tune);
+                if (t == "4,5") return launch_t<8, 3, 4, 5, REG_EPL>(g, p, stream, op);
+                if (t == "2,6") return launch_t<8, 3, 2, 6, REG_EPL>(g, p, stream, op);
+                if (t == "3,6") return launch_t<8, 3, 3, 6, REG_EPL>(g, p, stream, op);
+                if (t == "3,5") return launch_t<8, 3, 3, 5, REG_EPL>(g, p, stream, op);
+                if (t == "2,8") return launch_t<8, 3, 2, 8, REG_EPL>(g, p, stream, op);
+                if (t == "2,7") return launch_t<8, 3, 2, 7, REG_EPL>(g, p, stream, op);
+                if (t == "4,4") return launch_t<8, 3, 4, 4, REG_EPL>(g, p, stream, op);
+            }
+            return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
+        }
         if (vpl <= 4) return launch_t<8, 4, 2, 6>(g, p, stream, op);   // d = 128: +10-15 % over <8,4,4,4>
         return launch_t<8, 8, 2, 4>(g, p, stream, op);                  // d = 256: +6-7 % over <8,8,2,3>
     }
