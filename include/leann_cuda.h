@@ -40,7 +40,8 @@ extern "C" {
 /* Distance / score conventions.
  *  IP        1 - <q,x>, ascending     usearch MetricKind::IP            (hnsw.rs:45)
  *  L2SQ      |q-x|^2,   ascending     BASELINE config C4
- *  IP_CLAMP  max(0, 1 - <q,x>)        anndists DistDot                  (diskann.rs:16,36)
+ *  IP_CLAMP  max(0, 1 - <q,x>)        anndists DistDot                  (diskann.rs:16,36); deviation: anndists
+ *                                     asserts 1 - <q,x> >= -2e-6 and panics on non-unit vectors, this library clamps
  *  DOT_DESC  <q,x>,     descending    RecomputeSearcher score           (recompute.rs:96-106)
  * LEANN_METRIC_DEFAULT takes the metric recorded in the file / the reference default of the backend. */
 #define LEANN_METRIC_DEFAULT (-1)
@@ -329,6 +330,11 @@ void leann_cuda_searcher_close(leann_cuda_searcher* s);
 /* Library / device probe: returns the CUDA device count usable by the library (0 = none). */
 int leann_cuda_device_count(void);
 const char* leann_cuda_version(void);
+/* The recalled third-party behaviours the traversal kernels were compiled with (leann_rs_b200/csrc/compat.h):
+ * bit 0 usearch stop rule is strict (cand.d > radius), bit 1 diskann-rs stop rule is strict, bit 2 a newcomer enters
+ * `top` before equal distances, bit 3 equal distances leave the candidate queue in arrival order, bit 4 DistDot clamps
+ * at zero (the anndists assert on 1 - dot < -2e-6 is NOT reproduced: non-unit vectors are clamped, not rejected). */
+unsigned leann_cuda_compat_flags(void);
 
 #ifdef __cplusplus
 }

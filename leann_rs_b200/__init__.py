@@ -83,6 +83,7 @@ def lib():
         "leann_cuda_workspace_stats": (C.c_int, [vp, u64p]),
         "leann_cuda_device_count": (C.c_int, []),
         "leann_cuda_version": (cp, []),
+        "leann_cuda_compat_flags": (C.c_uint, []),
         "leann_cuda_bm25_build": (C.c_int, [cpp, szp, sz, C.c_int, pp, cp, sz]),
         "leann_cuda_bm25_len": (sz, [vp]),
         "leann_cuda_bm25_stats": (C.c_int, [vp, u64p, f32p]),

@@ -6,6 +6,7 @@
 #include <functional>
 #include <memory>
 
+#include "compat.h"
 #include "scan_common.h"
 
 using namespace leann;
@@ -300,7 +301,7 @@ void search_device_launch(const leann_cuda_index* ix, const float* d_queries, si
     p.next_capp = next_pow2(p.next_cap);
     ensure_workspace(ix, nq, graph_search_warps_per_sm(ix->view(), p.ef, p.next_capp), p.ef);
     p.mask = d_mask;
-    p.nonstrict_term = ix->backend == LEANN_BACKEND_VAMANA ? 1 : 0;
+    p.nonstrict_term = (ix->backend == LEANN_BACKEND_VAMANA ? compat::DISKANN_STOP_STRICT : compat::USEARCH_STOP_STRICT) ? 0 : 1;
     p.out_keys = d_keys; p.out_dists = d_dists; p.out_counts = d_counts; p.out_stats = d_stats;
     p.visited = ix->ws.visited; p.epochs = ix->ws.epochs; p.counter = ix->ws.counter;
     p.n_pad = ix->ws.n_pad;
@@ -377,6 +378,7 @@ int leann_cuda_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+unsigned leann_cuda_compat_flags(void) { return compat::FLAGS; }
 const char* leann_cuda_version(void) { return "leann-cuda 0.1.0 (sm_100a)"; }
 int leann_cuda_reduction_lanes(size_t dims) { return reduction_lanes(dims); }
 size_t leann_cuda_queue_capacity(size_t ef, int masked) { return masked ? std::min<size_t>(4 * ef, 2048) : ef; }

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "compat.h"
 #include "internal.h"
 
 namespace leann {
@@ -66,7 +67,7 @@ __device__ __forceinline__ float group_reduce(float v) {
 __device__ __forceinline__ float finish_distance(float s, int metric) {
     if (metric == LEANN_METRIC_L2SQ) return s;
     float r = __fsub_rn(1.0f, s);
-    if (metric == LEANN_METRIC_IP_CLAMP) r = r < 0.0f ? 0.0f : r;
+    if (compat::DISTDOT_CLAMP_AT_ZERO && metric == LEANN_METRIC_IP_CLAMP) r = r < 0.0f ? 0.0f : r;
     return r;
 }
 
@@ -349,10 +350,10 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
     auto passes = [&](uint32_t s) { return mask == nullptr || ((mask[s >> 6] >> (s & 63u)) & 1ull); };
     w.top_size = 0; w.next_size = 0; w.next_head = 0;
     float radius = CUDART_INF_F;
-    sorted_insert<true, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, start_d, start, lane);
+    sorted_insert<compat::NEXT_FIFO_AMONG_EQUALS, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, start_d, start, lane);
     if (lane == 0) visited_test_and_set(vs, start);
     visited_added(vs, 1u, warp_id, lane);
-    if (passes(start)) sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, start_d, start, lane);
+    if (passes(start)) sorted_insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, start_d, start, lane);
     if (w.top_size == ef) radius = w.top_d[ef - 1];
     __syncwarp();
     while (w.next_size > 0) {
@@ -456,8 +457,8 @@ __device__ __forceinline__ void beam_level(const GraphView& g, const LevelAdj ad
                 if (w.top_size < ef || dd < radius) {
                     uint32_t ss = w.st_slot[base + l];
                     if (w.next_size == next_cap) c.dropped = 1;
-                    sorted_insert<true, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, dd, ss, lane);
-                    if (passes(ss)) sorted_insert<false, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, dd, ss, lane);
+                    sorted_insert<compat::NEXT_FIFO_AMONG_EQUALS, true>(w.next_d, w.next_s, w.next_size, next_cap, w.next_head, next_mask, dd, ss, lane);
+                    if (passes(ss)) sorted_insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, false>(w.top_d, w.top_s, w.top_size, ef, 0, 0, dd, ss, lane);
                     radius = w.top_size == ef ? w.top_d[ef - 1] : CUDART_INF_F;
                 }
             }
@@ -497,32 +498,31 @@ struct RegList {
         const int rem = __shfl_sync(FULL, c, full & 31);
         return full == 32 ? 32 * EPL : full * EPL + rem;
     }
-    // insert at `pos` (< limit), dropping the last entry when the list already holds `limit`
+    // insert at `pos` (< limit), dropping the last entry when the list already holds `limit`.
+    // Written with value selects only: conditional stores into d[j] / s[j] get merged by the compiler into one store
+    // through a computed address, which sends the arrays to local memory.
     __device__ __forceinline__ void insert_at(int pos, float dd, uint32_t ss, int limit, int lane) {
         const int lp = pos / EPL, rp = pos % EPL;
         const float cd = __shfl_up_sync(FULL, d[EPL - 1], 1);
         const uint32_t cs = __shfl_up_sync(FULL, s[EPL - 1], 1);
-        if (lane > lp) {
+        const bool after = lane > lp, here = lane == lp;
+        const bool full = size == limit;
+        const int ll = limit / EPL, rl = limit % EPL;
 #pragma unroll
-            for (int j = EPL - 1; j >= 1; --j) { d[j] = d[j - 1]; s[j] = s[j - 1]; }
-            d[0] = cd; s[0] = cs;
-        } else if (lane == lp) {
-#pragma unroll
-            for (int j = EPL - 1; j >= 1; --j)
-                if (j > rp) { d[j] = d[j - 1]; s[j] = s[j - 1]; }
-#pragma unroll
-            for (int j = 0; j < EPL; ++j)
-                if (j == rp) { d[j] = dd; s[j] = ss; }
+        for (int j = EPL - 1; j >= 0; --j) {
+            const bool shift = after || (here && j > rp);
+            const float pd = j == 0 ? cd : d[j > 0 ? j - 1 : 0];
+            const uint32_t ps = j == 0 ? cs : s[j > 0 ? j - 1 : 0];
+            float nd = shift ? pd : d[j];
+            uint32_t ns = shift ? ps : s[j];
+            const bool ins = here && j == rp;
+            nd = ins ? dd : nd;
+            ns = ins ? ss : ns;
+            const bool drop = full && limit < 32 * EPL && lane == ll && j == rl;   // the entry pushed past the bound
+            d[j] = drop ? CUDART_INF_F : nd;
+            s[j] = drop ? SENT : ns;
         }
-        if (size == limit) {
-            if (limit < 32 * EPL && lane == limit / EPL) {   // the entry pushed past the bound is dropped
-#pragma unroll
-                for (int j = 0; j < EPL; ++j)
-                    if (j == limit % EPL) { d[j] = CUDART_INF_F; s[j] = SENT; }
-            }
-        } else {
-            size++;
-        }
+        size += full ? 0 : 1;
     }
     template <bool UPPER>
     __device__ __forceinline__ bool insert(float dd, uint32_t ss, int limit, int lane) {
@@ -532,10 +532,10 @@ struct RegList {
         return true;
     }
     __device__ __forceinline__ float dist_at(int i) const {
+        const int r = i % EPL;
         float v = d[0];
 #pragma unroll
-        for (int j = 1; j < EPL; ++j)
-            if (j == i % EPL) v = d[j];
+        for (int j = 1; j < EPL; ++j) v = (r == j) ? d[j] : v;
         return __shfl_sync(FULL, v, i / EPL);
     }
     __device__ __forceinline__ void pop_front(int lane) {
@@ -551,17 +551,18 @@ struct RegList {
 
 // beam_level with register lists: same loop as beam_level<..., PREFETCH = true> without a mask.
 template <int LPV, int VPL, int U, int EPL>
-__device__ __forceinline__ void beam_level_regs(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL], WarpLists& w,
-                                                RegList<EPL>& top, RegList<EPL>& next, int ef, int next_cap, int nonstrict,
-                                                VisitedSet& vs, uint32_t warp_id, uint32_t start, float start_d,
-                                                Counters& c, int lane) {
+__device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL], WarpLists& w,
+                                               int ef, int next_cap, int nonstrict, VisitedSet& vs, uint32_t warp_id,
+                                               uint32_t start, float start_d, Counters& c, int lane,
+                                               uint32_t k, uint64_t* __restrict__ out_keys, float* __restrict__ out_dists) {
+    RegList<EPL> top, next;
     top.clear();
     next.clear();
     float radius = CUDART_INF_F;
-    next.template insert<true>(start_d, start, next_cap, lane);
+    next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(start_d, start, next_cap, lane);
     if (lane == 0) visited_test_and_set(vs, start);
     visited_added(vs, 1u, warp_id, lane);
-    top.template insert<false>(start_d, start, ef, lane);
+    top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS>(start_d, start, ef, lane);
     if (top.size == ef) radius = top.dist_at(ef - 1);
     while (next.size > 0) {
         const float cd = __shfl_sync(FULL, next.d[0], 0);
@@ -576,50 +577,53 @@ __device__ __forceinline__ void beam_level_regs(const GraphView& g, const LevelA
             if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
         }
         int cnt = 0;
-        constexpr int NCH = MAX_DEG / 32;
-        uint32_t sv[NCH];
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            const uint32_t j = (uint32_t)ch * 32u + lane;
-            sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
-        }
-        bool fr[NCH];
-        if (vs.hashed) {
-            uint32_t h[NCH];
-            bool act[NCH];
-            bool any = false;
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) { h[ch] = (sv[ch] * 0x9E3779B1u) >> vs.shift; act[ch] = sv[ch] != SENT; fr[ch] = false; any |= act[ch]; }
-            while (any) {
-                uint32_t old[NCH];
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) if (act[ch]) old[ch] = atomicCAS(vs.tbl + h[ch], VIS_EMPTY, sv[ch]);
-                any = false;
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch)
-                    if (act[ch]) {
-                        if (old[ch] == VIS_EMPTY) { fr[ch] = true; act[ch] = false; }
-                        else if (old[ch] == sv[ch]) act[ch] = false;
-                        else { h[ch] = (h[ch] + 1u) & vs.cap_mask; any = true; }
-                    }
-            }
-        } else {
-            uint8_t tg[NCH];
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vs.vis[sv[ch]] : vs.tag;
+        // the row is handled 64 neighbours at a time (one pass for the usual degrees M0 = 64 / R = 64): the visited tags of a
+        // pass are requested together, membership is decided per lane, the compaction keeps list order
+        constexpr int NCH = 2;
+        for (uint32_t c0 = 0; c0 < adj.deg; c0 += 32u * NCH) {
+            uint32_t sv[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                fr[ch] = tg[ch] != vs.tag;
-                if (fr[ch]) vs.vis[sv[ch]] = vs.tag;
+                const uint32_t j = c0 + (uint32_t)ch * 32u + lane;
+                sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
             }
-        }
+            bool fr[NCH];
+            if (vs.hashed) {
+                uint32_t h[NCH];
+                bool act[NCH];
+                bool any = false;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            if ((uint32_t)ch * 32u >= adj.deg) break;
-            const bool fresh = fr[ch];
-            const unsigned b = __ballot_sync(FULL, fresh);
-            if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = sv[ch];
-            cnt += __popc(b);
+                for (int ch = 0; ch < NCH; ++ch) { h[ch] = (sv[ch] * 0x9E3779B1u) >> vs.shift; act[ch] = sv[ch] != SENT; fr[ch] = false; any |= act[ch]; }
+                while (any) {
+                    uint32_t old[NCH];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) if (act[ch]) old[ch] = atomicCAS(vs.tbl + h[ch], VIS_EMPTY, sv[ch]);
+                    any = false;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (act[ch]) {
+                            if (old[ch] == VIS_EMPTY) { fr[ch] = true; act[ch] = false; }
+                            else if (old[ch] == sv[ch]) act[ch] = false;
+                            else { h[ch] = (h[ch] + 1u) & vs.cap_mask; any = true; }
+                        }
+                }
+            } else {
+                uint8_t tg[NCH];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vs.vis[sv[ch]] : vs.tag;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    fr[ch] = tg[ch] != vs.tag;
+                    if (fr[ch]) vs.vis[sv[ch]] = vs.tag;
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const bool fresh = fr[ch];
+                const unsigned b = __ballot_sync(FULL, fresh);
+                if (fresh) w.st_slot[cnt + __popc(b & ((1u << lane) - 1u))] = sv[ch];
+                cnt += __popc(b);
+            }
         }
         __syncwarp();
         c.n_dist += cnt;
@@ -646,8 +650,8 @@ __device__ __forceinline__ void beam_level_regs(const GraphView& g, const LevelA
                 if (top.size < ef || dd < radius) {
                     const uint32_t ss = __shfl_sync(FULL, sj, l);
                     if (next.size == next_cap) c.dropped = 1;
-                    next.template insert<true>(dd, ss, next_cap, lane);
-                    top.template insert<false>(dd, ss, ef, lane);
+                    next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(dd, ss, next_cap, lane);
+                    top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS>(dd, ss, ef, lane);
                     if (top.size == ef) {
                         radius = top.dist_at(ef - 1);
                         m &= __ballot_sync(FULL, dj < radius);   // later entries that can no longer pass are skipped now
@@ -657,6 +661,18 @@ __device__ __forceinline__ void beam_level_regs(const GraphView& g, const LevelA
         }
         __syncwarp();
     }
+    // results: ascending, truncated to k; tail = UINT64_MAX / +inf (entry i = lane i / EPL, register i % EPL)
+    const int cnt = top.size < (int)k ? top.size : (int)k;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        const uint32_t i = (uint32_t)(lane * EPL + j);
+        if (i < k) {
+            const bool ok = (int)i < cnt;
+            out_keys[i] = ok ? (g.keys ? g.keys[top.s[j]] : (uint64_t)top.s[j]) : ~0ull;
+            out_dists[i] = ok ? top.d[j] : CUDART_INF_F;
+        }
+    }
+    return cnt;
 }
 
 }  // namespace leann

@@ -73,20 +73,10 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
         int cnt;
         if constexpr (EPL > 0) {
-            RegList<EPL> top, next;
-            beam_level_regs<LPV, VPL, U, EPL>(g, adj, q, w, top, next, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
-                                              (uint32_t)warp_global, cur, cur_d, c, lane);
+            cnt = beam_level_regs<LPV, VPL, U, EPL>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
+                                                    (uint32_t)warp_global, cur, cur_d, c, lane, p.k,
+                                                    p.out_keys + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k);
             visited_end(vs, lane);
-            cnt = top.size < (int)p.k ? top.size : (int)p.k;
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const uint32_t i = (uint32_t)(lane * EPL + j);
-                if (i < p.k) {
-                    const bool ok = (int)i < cnt;
-                    p.out_keys[(size_t)qi * p.k + i] = ok ? (g.keys ? g.keys[top.s[j]] : (uint64_t)top.s[j]) : ~0ull;
-                    p.out_dists[(size_t)qi * p.k + i] = ok ? top.d[j] : CUDART_INF_F;
-                }
-            }
         } else {
             beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
                                                 p.mask, vs, (uint32_t)warp_global, cur, cur_d, c, lane);

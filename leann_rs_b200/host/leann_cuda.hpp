@@ -103,6 +103,49 @@ private:
     DiskAnnSearcher(const std::string& p, size_t d, int dev) : CudaSearcher(p, LEANN_BACKEND_VAMANA, d, dev, std::nullopt) {}
 };
 
+/// A BackendSearcher over sub-indexes on several GPUs of one box (`leann_cuda_shards_*`): what load_searcher returns
+/// when the index directory holds `<base>.shardNN.index` files. One host process owns all devices; the per-shard
+/// top-k lists are merged on the first device (peer-memory loads inside the merge kernel, or NCCL all_gather).
+class ShardedSearcher : public BackendSearcher {
+public:
+    ShardedSearcher(const std::vector<std::string>& base_paths, int backend, size_t dimensions, const std::vector<int>& devices,
+                    std::optional<size_t> fixed_ef, int exchange = 0)
+        : dims_(dimensions), fixed_ef_(fixed_ef) {
+        if (base_paths.size() != devices.size()) throw Error(LEANN_ERR_INVALID_ARG, "one device per shard");
+        std::vector<const char*> paths;
+        for (auto& p : base_paths) paths.push_back(p.c_str());
+        char err[1024];
+        check(leann_cuda_shards_open(paths.data(), paths.size(), backend, dimensions, LEANN_METRIC_DEFAULT, devices.data(), nullptr,
+                                     exchange, &h_, err, sizeof err), err);
+    }
+    ~ShardedSearcher() override { leann_cuda_shards_close(h_); }
+    ShardedSearcher(const ShardedSearcher&) = delete;
+    ShardedSearcher& operator=(const ShardedSearcher&) = delete;
+    std::pair<std::vector<uint64_t>, std::vector<float>> search(const std::vector<float>& query, size_t top_k,
+                                                                size_t complexity) const override {
+        std::vector<uint64_t> keys(top_k);
+        std::vector<float> dists(top_k);
+        uint32_t count = 0;
+        char err[1024];
+        check(leann_cuda_shards_search(h_, query.data(), 1, top_k, fixed_ef_.value_or(complexity), nullptr, keys.data(), dists.data(),
+                                       &count, err, sizeof err), err);
+        keys.resize(count);
+        dists.resize(count);
+        return {std::move(keys), std::move(dists)};
+    }
+    void search_batch(const float* queries, size_t nq, size_t top_k, size_t ef, uint64_t* keys, float* dists, uint32_t* counts) const {
+        char err[1024];
+        check(leann_cuda_shards_search(h_, queries, nq, top_k, ef, nullptr, keys, dists, counts, err, sizeof err), err);
+    }
+    size_t len() const override { return leann_cuda_shards_len(h_); }
+    size_t shards() const { return leann_cuda_shards_count(h_); }
+
+private:
+    leann_cuda_shards* h_ = nullptr;
+    size_t dims_;
+    std::optional<size_t> fixed_ef_;
+};
+
 // ---- src/backend/mod.rs:16-45 -------------------------------------------------------------------------
 enum class BackendType { Hnsw, DiskAnn };
 inline std::unique_ptr<BackendSearcher> load_searcher(BackendType t, const std::string& index_path, size_t dimensions, int device = 0) {

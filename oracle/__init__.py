@@ -63,6 +63,10 @@ def lib():
         L.orc_distance.restype = C.c_float
         L.orc_distance.argtypes = [f32p, f32p, sz, C.c_int, C.c_int]
         L.orc_hardware_threads.restype = C.c_int
+        L.orc_compat_flags.restype = C.c_uint32
+        L.orc_compat_default.restype = C.c_uint32
+        L.orc_set_compat.argtypes = [C.c_uint32]
+        L.orc_set_compat.restype = None
         _LIB = L
     return _LIB
 
@@ -215,3 +219,22 @@ def distance(a, b, metric=0, lanes=0) -> float:
 
 def hardware_threads() -> int:
     return int(lib().orc_hardware_threads())
+
+
+# Recalled third-party behaviours behind named switches (graph_oracle.cpp CompatBits; the product mirrors them in
+# leann_rs_b200/csrc/compat.h and reports them through leann_cuda_compat_flags()).
+COMPAT_BITS = {"usearch_stop_strict": 1, "diskann_stop_strict": 2, "top_newcomer_before_equals": 4,
+               "next_fifo_among_equals": 8, "distdot_clamp_at_zero": 16}
+
+
+def compat_flags() -> int:
+    return int(lib().orc_compat_flags())
+
+
+def compat_default() -> int:
+    return int(lib().orc_compat_default())
+
+
+def set_compat(flags: int) -> None:
+    """Tests only; not thread-safe (set between searches)."""
+    lib().orc_set_compat(int(flags))

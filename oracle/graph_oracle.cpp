@@ -47,6 +47,23 @@
 namespace {
 
 enum Metric { METRIC_IP = 0, METRIC_L2SQ = 1, METRIC_IP_CLAMP = 2 };
+
+// Every behaviour of the third-party engines that is RECALLED rather than read from source under /root/reference
+//  sits behind one named switch. The defaults are what the restatement believes;
+// the product reports its own compile-time choice through leann_cuda_compat_flags() (same bit layout) and a test
+// asserts the two agree. When tests/golden/graph_golden.json has been produced on a machine with usearch 2.23.0
+// (oracle/pin_graph_golden.py) and disagrees, tests/test_graph_golden.py names the switch combination that
+// reproduces it: flip it here (orc_set_compat) and in leann_rs_b200/csrc/compat.h.
+enum CompatBits : uint32_t {
+    USEARCH_STOP_STRICT = 1u << 0,          // search_to_find_in_base_: stop when cand.d >  radius (clear: >=)
+    DISKANN_STOP_STRICT = 1u << 1,          // search_with_dists: stop when full && best.d > worst (clear: >=)
+    TOP_NEWCOMER_BEFORE_EQUALS = 1u << 2,   // sorted_buffer_gt::insert = lower_bound (clear: upper_bound)
+    NEXT_FIFO_AMONG_EQUALS = 1u << 3,       // order of equal distances in the candidate queue (clear: LIFO)
+    DISTDOT_CLAMP_AT_ZERO = 1u << 4,        // anndists DistDot::eval = max(0, 1 - dot) (clear: plain 1 - dot)
+};
+constexpr uint32_t COMPAT_DEFAULT = USEARCH_STOP_STRICT | TOP_NEWCOMER_BEFORE_EQUALS | NEXT_FIFO_AMONG_EQUALS | DISTDOT_CLAMP_AT_ZERO;
+uint32_t g_compat = COMPAT_DEFAULT;
+inline bool compat(uint32_t bit) { return (g_compat & bit) != 0; }
 // Reduction order of one distance evaluation.
 //   lanes == 0 : plain sequential f32 fold, mul then add (recompute.rs:137-139; anndists DistDot)
 //   lanes  > 0 : bit-exact model of the CUDA kernel: float4 index i belongs to lane i % lanes,
@@ -68,7 +85,7 @@ inline float dist_seq(const float* q, const float* x, size_t d, int metric) {
     }
     for (size_t i = 0; i < d; ++i) s += q[i] * x[i];
     float r = 1.0f - s;
-    if (metric == METRIC_IP_CLAMP && r < 0.0f) r = 0.0f;  // anndists DistDot::eval clamps at 0
+    if (metric == METRIC_IP_CLAMP && r < 0.0f && compat(DISTDOT_CLAMP_AT_ZERO)) r = 0.0f;  // anndists DistDot::eval clamps at 0
     return r;
 }
 
@@ -99,7 +116,7 @@ inline float dist_lanes(const float* q, const float* x, size_t d, int metric, in
     float s = v[0];
     if (metric == METRIC_L2SQ) return s;
     float r = 1.0f - s;
-    if (metric == METRIC_IP_CLAMP && r < 0.0f) r = 0.0f;
+    if (metric == METRIC_IP_CLAMP && r < 0.0f && compat(DISTDOT_CLAMP_AT_ZERO)) r = 0.0f;
     return r;
 }
 
@@ -122,7 +139,7 @@ inline float dist_simd(const float* q, const float* x, size_t d, int metric) {
     for (int w = 8; w >= 1; w >>= 1) for (int j = 0; j < w; ++j) acc[j] += acc[j + w];
     if (metric == METRIC_L2SQ) return acc[0];
     float r = 1.0f - acc[0];
-    if (metric == METRIC_IP_CLAMP && r < 0.0f) r = 0.0f;
+    if (metric == METRIC_IP_CLAMP && r < 0.0f && compat(DISTDOT_CLAMP_AT_ZERO)) r = 0.0f;
     return r;
 }
 
@@ -146,7 +163,8 @@ inline bool top_insert(std::vector<Cand>& top, Cand e, size_t limit) {
         size_t lo = 0, hi = n;
         while (lo < hi) {
             size_t mid = (lo + hi) / 2;
-            if (top[mid].d < e.d) lo = mid + 1; else hi = mid;
+            const bool before = compat(TOP_NEWCOMER_BEFORE_EQUALS) ? top[mid].d < e.d : top[mid].d <= e.d;
+            if (before) lo = mid + 1; else hi = mid;
         }
         pos = lo;
     }
@@ -172,7 +190,8 @@ struct NextQueue {
         size_t lo = 0, hi = v.size();
         while (lo < hi) {
             size_t mid = (lo + hi) / 2;
-            if (v[mid].d <= e.d) lo = mid + 1; else hi = mid;
+            const bool before = compat(NEXT_FIFO_AMONG_EQUALS) ? v[mid].d <= e.d : v[mid].d < e.d;
+            if (before) lo = mid + 1; else hi = mid;
         }
         if (cap && v.size() == cap) {
             dropped = true;
@@ -260,8 +279,10 @@ void beam_level(const Hnsw& g, const float* q, DistCfg dc, uint32_t start, float
         Cand c = next.front();
         // Equivalent to usearch's `cand.d > radius` for the unfiltered case: while top is not full
         // every queued candidate is also in top, so the test can never fire.
-        if (c.d > radius) break;
+        // insert_variant (search_to_insert_, the builder's call): usearch additionally requires `top` to be full, which is
+        // implied here because radius is +inf until then.
         (void)insert_variant;
+        if (compat(USEARCH_STOP_STRICT) ? (c.d > radius) : (c.d >= radius)) break;
         next.pop();
         const uint32_t* l = g.list(c.s, level);
         uint32_t cnt = l[0];
@@ -536,7 +557,7 @@ size_t vamana_search_one(const Vamana& g, const float* q, size_t k, size_t beam,
     float radius = top.size() == beam ? top.back().d : INF;
     while (!next.empty()) {
         Cand c = next.front();
-        if (top.size() >= beam && c.d >= radius) break;
+        if (top.size() >= beam && (compat(DISKANN_STOP_STRICT) ? (c.d > radius) : (c.d >= radius))) break;
         next.pop();
         st.n_hops0++;
         const uint32_t* l = &g.adj[(size_t)c.s * g.R];
@@ -856,6 +877,9 @@ void orc_exact_f64(const float* queries, size_t nq, const float* db, size_t n, s
 }
 
 float orc_distance(const float* a, const float* b, size_t d, int metric, int lanes) { return dist(a, b, d, DistCfg{metric, lanes}); }
+uint32_t orc_compat_flags() { return g_compat; }
+uint32_t orc_compat_default() { return COMPAT_DEFAULT; }
+void orc_set_compat(uint32_t flags) { g_compat = flags; }   // not thread-safe: set between searches (tests only)
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -51,6 +51,13 @@ int main(int argc, char** argv) {
         printf("KEYS");
         for (auto k : res.first) printf(" %llu", (unsigned long long)k);
         printf("\n");
+        // --- the sharded BackendSearcher over the same file as a one-shard index: identical answer through the merge kernel
+        {
+            ShardedSearcher sh({argv[1]}, LEANN_BACKEND_HNSW, d, {0}, 64);
+            REQUIRE(sh.len() == s->len() && sh.shards() == 1);
+            auto rs = sh.search(q, 5, 999);
+            REQUIRE(rs.first == res.first && rs.second == res.second);
+        }
         // --- hnsw::build_index + hnsw::add_to_index (hnsw.rs:96-191) on a scratch base path, then load and search
         if (argc > 4) {
             const std::string base = argv[4];

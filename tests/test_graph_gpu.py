@@ -337,3 +337,25 @@ def test_workspace_sized_once_and_streams_chain(orc, pkg):
         assert np.array_equal(kk.cpu().numpy().astype(np.uint64), k0)
         assert np.array_equal(dd.cpu().numpy().view(np.uint32), d0.view(np.uint32))
     s.close()
+
+
+def test_reduction_orders_agree_at_100k(orc, pkg, tmp_path):
+    """The graph parity tests run the oracle in `lanes` mode (a bit-exact model of the kernel's reduction tree). The
+    reference's usearch uses SimSIMD's order instead; the two differ in the last ulp of a distance, which can only swap
+    near-ties. On a 100k-vector index the ids under both orders (and under the plain sequential fold) must agree >= 0.999."""
+    n, d, k, ef = 100_000, 128, 10, 64
+    x, q = make_data(n, d, 41, nq=2000)
+    s = pkg.HnswSearcher.build(x, graph_degree=16, complexity=64, seed=4)
+    base = str(tmp_path / "documents.leann")
+    s.save(base)
+    g = orc.Hnsw.load(base.replace(".leann", ".index"), d)
+    lanes = pkg.reduction_lanes(d)
+    kl, dl, _, _ = g.search(q, k, ef, lanes=lanes, next_cap=pkg.queue_capacity(ef, False), nthreads=8)
+    gk, gd, _ = s.search_batch(q, k, ef)
+    assert np.array_equal(gk, kl) and np.array_equal(gd.view(np.uint32), dl.view(np.uint32))
+    for other in (-1, 0):     # SimSIMD-shaped, sequential
+        ko, do_, _, _ = g.search(q, k, ef, lanes=other, next_cap=0, nthreads=8)
+        agree = float(np.mean(ko == kl))
+        assert agree >= 0.999, (other, agree)
+        assert float(np.max(np.abs(do_ - dl))) < 1e-6
+    s.close()

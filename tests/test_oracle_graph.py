@@ -209,3 +209,32 @@ def test_handmade_diskann_file_and_hand_traced_search(orc, tmp_path):
             assert (int(st[0, 0]), int(st[0, 1])) == (exp["n_dist"], exp["hops0"]), (L, st[0])
             want = np.maximum(0.0, 1.0 - np.cos(np.deg2rad(70.0 - 10.0 * np.array(exp["keys"]))))
             assert np.allclose(dd[0], want, atol=1e-6)
+
+
+def test_compat_switches_change_only_tie_handling(orc):
+    """The recalled behaviours sit behind named switches (graph_oracle.cpp CompatBits). On data with exact duplicate rows the
+    tie switches reorder equal-distance results and nothing else; on duplicate-free data they change nothing."""
+    x, q = make_data(1500, 32, 3, nq=120)
+    xd = x.copy()
+    xd[500:1000] = xd[:500]                       # every one of 500 rows twice: equal distances everywhere
+    base = orc.compat_default()
+    try:
+        for data, expect_change in ((xd, True), (x, False)):
+            g = orc.Hnsw.build(data, M=8, ef_add=32, seed=3)
+            orc.set_compat(base)
+            k0, d0, _, _ = g.search(q, 10, 32)
+            changed = False
+            for bit in (orc.COMPAT_BITS["top_newcomer_before_equals"], orc.COMPAT_BITS["next_fifo_among_equals"]):
+                orc.set_compat(base ^ bit)
+                k1, d1, _, _ = g.search(q, 10, 32)
+                changed |= not np.array_equal(k0, k1)
+                assert np.mean(np.sort(d0, axis=1) == np.sort(d1, axis=1)) > 0.97   # only the order inside tie groups moves
+            assert changed == expect_change
+            # the stop rule (> vs >=) decides whether the current worst entry of `top` is still expanded: it may move a
+            # boundary result even without ties, but never more than a few
+            orc.set_compat(base ^ orc.COMPAT_BITS["usearch_stop_strict"])
+            k1, d1, _, _ = g.search(q, 10, 32)
+            assert np.mean(k0 == k1) > 0.95
+    finally:
+        orc.set_compat(base)
+    assert orc.compat_flags() == base
