@@ -95,6 +95,17 @@ int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t 
  * EmbeddingsWriter (index/embeddings.rs:126-147). Writes the reference's on-disk formats. */
 int leann_cuda_save(const leann_cuda_index* index, const char* base_path, char* err, size_t errlen);
 
+/* Cached device layout. leann_cuda_open streams the vectors block of `.index` / `.diskann` /
+ * `.embeddings` files from disk to HBM through pinned staging buffers and parses the usearch node block on host threads
+ * meanwhile. write_layout_cache stores the parsed, fixed-stride adjacency of an HNSW handle as `<base>.cuda-layout`, bound to
+ * the `.index` file at the same base by (size, mtime, hash of its headers); a later leann_cuda_open finds it, verifies the
+ * binding and streams it instead of reading and parsing the node block (a stale or foreign cache file is ignored).
+ * The environment variable LEANN_CUDA_LAYOUT_CACHE=1 makes leann_cuda_open write the file after a parse;
+ * LEANN_CUDA_NO_LAYOUT_CACHE=1 makes it ignore an existing one. */
+int leann_cuda_write_layout_cache(const leann_cuda_index* index, const char* base_path, char* err, size_t errlen);
+/* 1 when this handle's adjacency was loaded from `<base>.cuda-layout`. */
+int leann_cuda_layout_cache_used(const leann_cuda_index* index);
+
 /* BackendSearcher::len (backend/traits.rs:24). */
 size_t leann_cuda_len(const leann_cuda_index* index);
 size_t leann_cuda_dims(const leann_cuda_index* index);

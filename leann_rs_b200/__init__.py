@@ -58,6 +58,8 @@ def lib():
         "leann_cuda_hnsw_add": (C.c_int, [vp, vp, C.c_int, sz, C.c_uint64, sz, C.c_uint64, cp, sz]),
         "leann_cuda_vamana_build": (C.c_int, [vp, C.c_int, sz, sz, sz, sz, C.c_float, C.c_int, C.c_uint64, C.c_int, pp, cp, sz]),
         "leann_cuda_save": (C.c_int, [vp, cp, cp, sz]),
+        "leann_cuda_write_layout_cache": (C.c_int, [vp, cp, cp, sz]),
+        "leann_cuda_layout_cache_used": (C.c_int, [vp]),
         "leann_cuda_len": (sz, [vp]),
         "leann_cuda_dims": (sz, [vp]),
         "leann_cuda_info": (C.c_int, [vp, u64p]),
@@ -291,6 +293,15 @@ class BackendSearcher:
     def save(self, base_path: str):
         e = _err()
         _check(lib().leann_cuda_save(self._h, os.fsencode(base_path), e, 1024), e)
+
+    def write_layout_cache(self, base_path: str):
+        """Persist the parsed adjacency as `<base>.cuda-layout` (bound to the `.index` at the same base) so later opens skip the parse."""
+        e = _err()
+        _check(lib().leann_cuda_write_layout_cache(self._h, os.fsencode(base_path), e, 1024), e)
+
+    @property
+    def layout_cache_used(self) -> bool:
+        return bool(lib().leann_cuda_layout_cache_used(self._h))
 
 
 class HnswSearcher(BackendSearcher):

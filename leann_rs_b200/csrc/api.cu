@@ -17,6 +17,11 @@ int guard_impl(char* err, size_t errlen, const std::function<void()>& f);
 void gpu_hnsw_build(leann_cuda_index* ix, size_t M, size_t ef_add, uint64_t seed);
 void gpu_vamana_build(leann_cuda_index* ix, size_t R, size_t L, float alpha, uint64_t seed);
 void gpu_hnsw_add(leann_cuda_index* ix, const float4* new_rows, size_t m, uint64_t start_id, size_t ef_add, uint64_t seed);
+// file -> HBM loaders (open_stream.cu)
+leann_cuda_index* open_hnsw_streamed(const std::string& base, size_t dims, int device, int metric, bool* used_cache);
+leann_cuda_index* open_vamana_streamed(const std::string& base, size_t dims, int device, int metric);
+leann_cuda_index* open_flat_streamed(const std::string& base, size_t dims, int device, int metric);
+void write_layout_cache(const leann_cuda_index* ix, const std::string& base);
 }  // namespace leann
 
 namespace {
@@ -396,29 +401,31 @@ int leann_cuda_open(const char* base_path, int backend, size_t dims, int metric,
                             "This index was built with Python LEANN (FAISS format).\nRust LEANN uses usearch which has a different binary format.\n\n"
                             "To use this index with Rust LEANN, you need to rebuild it:\n  leann build <name> --docs <path> --force\n\n"
                             "The passages and metadata files are compatible and will be preserved.");
-            HostHnsw h;
-            read_usearch_index(file, dims, h);
+            usearch_probe(file, dims);   // header / format / dimension errors are reported before the device is touched
             require_gpu(device);
             DeviceGuard dg(device);
-            *out = from_hnsw(h, device, metric);
+            bool used_cache = false;
+            *out = open_hnsw_streamed(base, dims, device, metric, &used_cache);
+            (*out)->layout_cache_used = used_cache;
+            // LEANN_CUDA_LAYOUT_CACHE=1: leave <base>.cuda-layout behind after a parse so the next open skips it
+            if (!used_cache && getenv("LEANN_CUDA_LAYOUT_CACHE") != nullptr) {
+                try { write_layout_cache(*out, base); } catch (const Error&) {}   // read-only index directory: not an error
+            }
         } else if (backend == LEANN_BACKEND_VAMANA) {
-            HostVamana h;
-            read_diskann(with_extension(base, "diskann"), dims, h);
+            diskann_probe(with_extension(base, "diskann"), dims);
             require_gpu(device);
             DeviceGuard dg(device);
-            *out = from_vamana(h, device, metric);
+            *out = open_vamana_streamed(base, dims, device, metric);
         } else if (backend == LEANN_BACKEND_FLAT) {
-            std::vector<float> v;
-            size_t n = 0;
-            read_embeddings(with_extension(base, "embeddings"), dims, v, n);
+            if (dims == 0) throw Error(LEANN_ERR_INVALID_ARG, "embeddings: dimensions must be given (the file has no header)");
+            {
+                FILE* probe = fopen(with_extension(base, "embeddings").c_str(), "rb");
+                if (!probe) throw Error(LEANN_ERR_NOT_FOUND, "Embeddings file not found: " + with_extension(base, "embeddings"));
+                fclose(probe);
+            }
             require_gpu(device);
             DeviceGuard dg(device);
-            std::unique_ptr<leann_cuda_index> ix(new leann_cuda_index());
-            ix->backend = LEANN_BACKEND_FLAT; ix->device = device;
-            ix->metric = metric == LEANN_METRIC_DEFAULT ? LEANN_METRIC_DOT_DESC : metric;
-            ix->n = n; ix->d = dims;
-            upload_vectors(ix.get(), v.data(), false);
-            *out = ix.release();
+            *out = open_flat_streamed(base, dims, device, metric);
         } else {
             throw Error(LEANN_ERR_INVALID_ARG, "Unknown backend");  // searcher.rs:98
         }
@@ -537,6 +544,15 @@ int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t 
         *out = ix.release();
     });
 }
+
+int leann_cuda_write_layout_cache(const leann_cuda_index* ix, const char* base_path, char* err, size_t errlen) {
+    GUARD({
+        if (!ix || !base_path) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        DeviceGuard dg(ix->device);
+        write_layout_cache(ix, base_path);
+    });
+}
+int leann_cuda_layout_cache_used(const leann_cuda_index* ix) { return ix && ix->layout_cache_used ? 1 : 0; }
 
 int leann_cuda_save(const leann_cuda_index* ix, const char* base_path, char* err, size_t errlen) {
     GUARD({

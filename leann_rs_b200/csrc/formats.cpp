@@ -105,17 +105,33 @@ bool is_faiss_index(const std::string& index_file) {
     return false;
 }
 
-void read_usearch_index(const std::string& path, size_t dims, HostHnsw& g) {
+uint64_t fnv1a64(const void* data, size_t bytes, uint64_t h) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 0x100000001B3ull; }
+    return h;
+}
+
+void usearch_layout(const UsearchPlan& pl, const std::string& path, const int16_t* levels, std::vector<uint32_t>& upper_base,
+                    std::vector<uint64_t>& node_off, size_t& n_upper);
+
+// Header pass over a usearch `.index`: every header field is verified, the byte ranges of the three blocks are returned.
+// The vectors block and the node block are NOT read here (leann_cuda_open streams them, open_stream.cu).
+UsearchPlan usearch_probe(const std::string& path, size_t dims) {
     Reader r(path);
     if (!r.f) throw Error(LEANN_ERR_NOT_FOUND, "Index file not found: " + path + "\nRun 'leann build' to create an index first.");
+    UsearchPlan pl;
+    pl.file_size = r.size;
+    struct stat st;
+    pl.mtime_ns = stat(path.c_str(), &st) == 0 ? (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec : 0;
     uint32_t rc[2];
     r.read(rc, 8, "matrix shape");
     size_t rows = rc[0], cols = rc[1];
     if (cols == 0 || cols % 4 != 0) throw Error(LEANN_ERR_BAD_FORMAT, path + ": vector byte width is not a multiple of 4 (not an f32 usearch index)");
     if (8 + rows * cols + sizeof(UsearchDenseHead) + sizeof(UsearchGraphHead) > r.size)
         throw Error(LEANN_ERR_BAD_FORMAT, path + ": vectors block larger than file (incompatible format / header)");
-    g.vecs.resize(rows * (cols / 4));
-    r.read(g.vecs.data(), rows * cols, "vectors");
+    pl.vec_off = 8; pl.vec_bytes = rows * cols;
+    if (fseek(r.f, (long)(8 + rows * cols), SEEK_SET) != 0) throw Error(LEANN_ERR_BAD_FORMAT, path + ": seek failed");
+    r.pos = 8 + rows * cols;
     UsearchDenseHead h;
     r.read(&h, sizeof h, "dense head");
     if (memcmp(h.magic, "usearch", 7) != 0) throw Error(LEANN_ERR_BAD_FORMAT, path + ": bad magic (not a usearch index)");
@@ -134,51 +150,105 @@ void read_usearch_index(const std::string& path, size_t dims, HostHnsw& g) {
     if (gh.connectivity == 0 || gh.connectivity_base < gh.connectivity || gh.connectivity_base > (uint64_t)MAX_DEG)
         throw Error(LEANN_ERR_BAD_FORMAT, path + ": connectivity out of range (max " + std::to_string(MAX_DEG) + ")");
     if (rows && gh.entry_slot >= rows) throw Error(LEANN_ERR_BAD_FORMAT, path + ": entry slot out of range");
-    g.n = rows; g.d = h.dimensions; g.M = gh.connectivity; g.M0 = gh.connectivity_base;
-    g.max_level = (int64_t)gh.max_level; g.entry = gh.entry_slot;
-    g.metric = h.kind_metric == 'e' ? LEANN_METRIC_L2SQ : LEANN_METRIC_IP;
-    g.levels.resize(rows);
-    r.read(g.levels.data(), rows * 2, "levels");
-    g.keys.resize(rows);
-    g.upper_base.assign(rows, 0);
-    size_t n_upper = 0;
-    for (size_t i = 0; i < rows; ++i) {
-        if (g.levels[i] < 0 || g.levels[i] > g.max_level) throw Error(LEANN_ERR_BAD_FORMAT, path + ": node level out of range");
-        g.upper_base[i] = (uint32_t)n_upper;
-        n_upper += (size_t)g.levels[i];
+    pl.n = rows; pl.d = h.dimensions; pl.M = gh.connectivity; pl.M0 = gh.connectivity_base;
+    pl.max_level = (int64_t)gh.max_level; pl.entry = gh.entry_slot;
+    pl.metric = h.kind_metric == 'e' ? LEANN_METRIC_L2SQ : LEANN_METRIC_IP;
+    pl.levels_off = r.pos;
+    pl.nodes_off = pl.levels_off + rows * 2;
+    if (pl.nodes_off > r.size) throw Error(LEANN_ERR_BAD_FORMAT, path + ": truncated while reading levels");
+    pl.head_hash = fnv1a64(&gh, sizeof gh, fnv1a64(&h, sizeof h, fnv1a64(rc, 8, 0xCBF29CE484222325ull)));
+    // the level table is small (2 bytes per node): verify the file-size equation here, before any device work
+    {
+        std::vector<int16_t> levels(rows);
+        r.read(levels.data(), rows * 2, "levels");
+        std::vector<uint32_t> upper;
+        std::vector<uint64_t> node_off;
+        size_t n_upper = 0;
+        usearch_layout(pl, path, levels.data(), upper, node_off, n_upper);
     }
+    return pl;
+}
+
+// Levels table -> per-node upper-list base and byte offset inside the node block; verifies the file-size equation.
+void usearch_layout(const UsearchPlan& pl, const std::string& path, const int16_t* levels, std::vector<uint32_t>& upper_base,
+                    std::vector<uint64_t>& node_off, size_t& n_upper) {
+    upper_base.assign(pl.n, 0);
+    node_off.resize(pl.n + 1);
+    n_upper = 0;
+    uint64_t off = 0;
+    for (size_t i = 0; i < pl.n; ++i) {
+        if (levels[i] < 0 || levels[i] > pl.max_level) throw Error(LEANN_ERR_BAD_FORMAT, path + ": node level out of range");
+        upper_base[i] = (uint32_t)n_upper;
+        node_off[i] = off;
+        n_upper += (size_t)levels[i];
+        off += 10 + 4 * ((1 + pl.M0) + (uint64_t)levels[i] * (1 + pl.M));
+    }
+    node_off[pl.n] = off;
     if (n_upper > 0xFFFFFFF0ull) throw Error(LEANN_ERR_BAD_FORMAT, path + ": too many upper-level lists");
-    g.adj0.assign(rows * g.M0, SENT);
-    g.adjU.assign(n_upper * g.M, SENT);
-    std::vector<uint32_t> node;
-    for (size_t i = 0; i < rows; ++i) {
-        int lv = g.levels[i];
-        size_t words = (1 + g.M0) + (size_t)lv * (1 + g.M);
-        unsigned char head[10];
-        r.read(head, 10, "node head");
-        memcpy(&g.keys[i], head, 8);
+    if (pl.nodes_off + off != pl.file_size) {
+        if (pl.nodes_off + off > pl.file_size) throw Error(LEANN_ERR_BAD_FORMAT, path + ": truncated while reading node links");
+        throw Error(LEANN_ERR_BAD_FORMAT, path + ": file size equation violated (" + std::to_string(pl.file_size - pl.nodes_off - off) + " trailing bytes)");
+    }
+}
+
+// Nodes [i0, i1) of the node block -> fixed-stride adjacency (SENT padded, list order kept) + keys. Thread-safe on disjoint ranges.
+void usearch_parse_nodes(const UsearchPlan& pl, const std::string& path, const unsigned char* nodes, const uint64_t* node_off,
+                         const int16_t* levels, const uint32_t* upper_base, size_t i0, size_t i1, uint64_t* keys, uint32_t* adj0,
+                         uint32_t* adjU) {
+    const size_t rows = pl.n, M0 = pl.M0, M = pl.M;
+    for (size_t i = i0; i < i1; ++i) {
+        const unsigned char* p = nodes + node_off[i];
+        const int lv = levels[i];
+        memcpy(&keys[i], p, 8);
         int16_t lv2;
-        memcpy(&lv2, head + 8, 2);
+        memcpy(&lv2, p + 8, 2);
         if (lv2 != lv) throw Error(LEANN_ERR_BAD_FORMAT, path + ": node level disagrees with the level table");
-        node.resize(words);
-        r.read(node.data(), words * 4, "node links");
-        uint32_t c0 = node[0];
-        if (c0 > g.M0) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour count exceeds connectivity_base");
-        for (uint32_t j = 0; j < c0; ++j) {
-            if (node[1 + j] >= rows) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour slot out of range");
-            g.adj0[i * g.M0 + j] = node[1 + j];
-        }
-        for (int l = 1; l <= lv; ++l) {
-            const uint32_t* p = &node[(1 + g.M0) + (size_t)(l - 1) * (1 + g.M)];
-            if (p[0] > g.M) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour count exceeds connectivity");
-            uint32_t* dst = &g.adjU[((size_t)g.upper_base[i] + (l - 1)) * g.M];
-            for (uint32_t j = 0; j < p[0]; ++j) {
-                if (p[1 + j] >= rows) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour slot out of range");
-                dst[j] = p[1 + j];
-            }
+        uint32_t cnt;
+        const unsigned char* l = p + 10;
+        memcpy(&cnt, l, 4);
+        if (cnt > M0) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour count exceeds connectivity_base");
+        uint32_t* dst = adj0 + i * M0;
+        memcpy(dst, l + 4, (size_t)cnt * 4);
+        for (uint32_t j = 0; j < cnt; ++j)
+            if (dst[j] >= rows) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour slot out of range");
+        for (size_t j = cnt; j < M0; ++j) dst[j] = SENT;
+        l += 4 * (1 + M0);
+        for (int lev = 1; lev <= lv; ++lev, l += 4 * (1 + M)) {
+            memcpy(&cnt, l, 4);
+            if (cnt > M) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour count exceeds connectivity");
+            uint32_t* du = adjU + ((size_t)upper_base[i] + (size_t)(lev - 1)) * M;
+            memcpy(du, l + 4, (size_t)cnt * 4);
+            for (uint32_t j = 0; j < cnt; ++j)
+                if (du[j] >= rows) throw Error(LEANN_ERR_BAD_FORMAT, path + ": neighbour slot out of range");
+            for (size_t j = cnt; j < M; ++j) du[j] = SENT;
         }
     }
-    if (r.pos != r.size) throw Error(LEANN_ERR_BAD_FORMAT, path + ": file size equation violated (" + std::to_string(r.size - r.pos) + " trailing bytes)");
+}
+
+// Whole-file reader into host memory (tools and tests; leann_cuda_open streams instead).
+void read_usearch_index(const std::string& path, size_t dims, HostHnsw& g) {
+    UsearchPlan pl = usearch_probe(path, dims);
+    Reader r(path);
+    if (!r.f) throw Error(LEANN_ERR_NOT_FOUND, "Index file not found: " + path);
+    g.n = pl.n; g.d = pl.d; g.M = pl.M; g.M0 = pl.M0; g.max_level = pl.max_level; g.entry = pl.entry; g.metric = pl.metric;
+    fseek(r.f, (long)pl.vec_off, SEEK_SET);
+    r.pos = pl.vec_off;
+    g.vecs.resize(pl.n * pl.d);
+    r.read(g.vecs.data(), pl.vec_bytes, "vectors");
+    fseek(r.f, (long)pl.levels_off, SEEK_SET);
+    r.pos = pl.levels_off;
+    g.levels.resize(pl.n);
+    r.read(g.levels.data(), pl.n * 2, "levels");
+    std::vector<uint64_t> node_off;
+    size_t n_upper = 0;
+    usearch_layout(pl, path, g.levels.data(), g.upper_base, node_off, n_upper);
+    std::vector<unsigned char> nodes(node_off[pl.n]);
+    r.read(nodes.data(), nodes.size(), "node links");
+    g.keys.resize(pl.n);
+    g.adj0.resize(pl.n * pl.M0);
+    g.adjU.resize(n_upper * pl.M);
+    usearch_parse_nodes(pl, path, nodes.data(), node_off.data(), g.levels.data(), g.upper_base.data(), 0, pl.n, g.keys.data(),
+                        g.adj0.data(), g.adjU.data());
 }
 
 void write_usearch_index(const std::string& path, const HostHnsw& g) {
@@ -220,10 +290,11 @@ void write_usearch_index(const std::string& path, const HostHnsw& g) {
     w.commit();
 }
 
-// bincode 1 (fixint, little endian): usize -> u64, String -> u64 length + bytes.
-void read_diskann(const std::string& path, size_t dims, HostVamana& g) {
+// bincode 1 (fixint, little endian): usize -> u64, String -> u64 length + bytes. Header pass only.
+DiskannPlan diskann_probe(const std::string& path, size_t dims) {
     Reader r(path);
     if (!r.f) throw Error(LEANN_ERR_NOT_FOUND, "DiskANN index not found: " + path + "\nRun 'leann build' with --backend-name diskann to create an index first.");
+    DiskannPlan g;
     uint64_t meta_len;
     r.read(&meta_len, 8, "meta length");
     if (meta_len < 52 || meta_len > 4096) throw Error(LEANN_ERR_BAD_FORMAT, path + ": implausible metadata length");
@@ -240,8 +311,16 @@ void read_diskann(const std::string& path, size_t dims, HostVamana& g) {
     if (voff < 8 + meta_len || aoff != voff + (uint64_t)g.n * g.d * 4 || r.size != aoff + (uint64_t)g.n * g.R * 4)
         throw Error(LEANN_ERR_BAD_FORMAT, path + ": file size equation violated");
     if (g.n && g.medoid >= g.n) throw Error(LEANN_ERR_BAD_FORMAT, path + ": medoid out of range");
-    fseek(r.f, (long)voff, SEEK_SET);
-    r.pos = voff;
+    g.vec_off = voff; g.adj_off = aoff; g.file_size = r.size;
+    return g;
+}
+
+void read_diskann(const std::string& path, size_t dims, HostVamana& g) {
+    DiskannPlan pl = diskann_probe(path, dims);
+    Reader r(path);
+    g.n = pl.n; g.d = pl.d; g.R = pl.R; g.medoid = pl.medoid; g.distance_name = pl.distance_name;
+    fseek(r.f, (long)pl.vec_off, SEEK_SET);
+    r.pos = pl.vec_off;
     g.vecs.resize(g.n * g.d);
     r.read(g.vecs.data(), g.n * g.d * 4, "vectors");
     g.adj.resize(g.n * g.R);

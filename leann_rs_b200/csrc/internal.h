@@ -53,6 +53,32 @@ struct HostVamana {  // diskann-rs `.diskann` (diskann.rs:34-37,94-99), Appendix
     std::vector<uint32_t> adj;  // n*R, SENT padded
 };
 
+// Header-only passes (formats.cpp): every header field verified, byte ranges of the blocks returned; the blocks themselves
+// are streamed to the device by open_stream.cu.
+struct UsearchPlan {
+    size_t n = 0, d = 0, M = 0, M0 = 0;
+    int64_t max_level = 0;
+    uint64_t entry = 0;
+    int metric = LEANN_METRIC_IP;
+    size_t vec_off = 0, vec_bytes = 0, levels_off = 0, nodes_off = 0, file_size = 0;
+    int64_t mtime_ns = 0;
+    uint64_t head_hash = 0;   // FNV-1a of (matrix shape, dense head, graph header)
+};
+struct DiskannPlan {
+    size_t n = 0, d = 0, R = 0;
+    uint32_t medoid = 0;
+    std::string distance_name;
+    size_t vec_off = 0, adj_off = 0, file_size = 0;
+};
+UsearchPlan usearch_probe(const std::string& path, size_t dims);
+void usearch_layout(const UsearchPlan& pl, const std::string& path, const int16_t* levels, std::vector<uint32_t>& upper_base,
+                    std::vector<uint64_t>& node_off, size_t& n_upper);
+void usearch_parse_nodes(const UsearchPlan& pl, const std::string& path, const unsigned char* nodes, const uint64_t* node_off,
+                         const int16_t* levels, const uint32_t* upper_base, size_t i0, size_t i1, uint64_t* keys, uint32_t* adj0,
+                         uint32_t* adjU);
+DiskannPlan diskann_probe(const std::string& path, size_t dims);
+uint64_t fnv1a64(const void* data, size_t bytes, uint64_t h);
+
 bool is_faiss_index(const std::string& index_file);                       // backend/compat.rs:15-38
 void read_usearch_index(const std::string& path, size_t dims, HostHnsw& out);   // throws Error
 void write_usearch_index(const std::string& path, const HostHnsw& g);
@@ -171,6 +197,7 @@ struct leann_cuda_index {
     int max_level = 0;
     uint32_t entry = 0;
     bool identity_keys = true;
+    bool layout_cache_used = false;   // adjacency came from <base>.cuda-layout (open_stream.cu)
     // workspaces (guarded by mu: concurrent callers serialise on the GPU queue)
     mutable std::mutex mu;
     mutable leann::SearchWorkspace ws;
