@@ -291,8 +291,17 @@ void search_device_launch(const leann_cuda_index* ix, const float* d_queries, si
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
         if (!ix->scan_pinned) LEANN_CUDA_CHECK(cudaMallocHost(&ix->scan_pinned, 64));
+        if (!ix->scan_aux.helper) {
+            static const bool no_split = getenv("LEANN_CUDA_SCAN_NO_SPLIT") != nullptr;   // A/B switch for benchmarks
+            ix->scan_aux.h_flags = ix->scan_pinned;
+            if (!no_split) {
+                LEANN_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->scan_aux.helper, cudaStreamNonBlocking));
+                LEANN_CUDA_CHECK(cudaEventCreateWithFlags(&ix->scan_aux.fork, cudaEventDisableTiming));
+                LEANN_CUDA_CHECK(cudaEventCreateWithFlags(&ix->scan_aux.join, cudaEventDisableTiming));
+            }
+        }
         launch_exact_scan(f, d_queries, (uint32_t)nq, (uint32_t)k, d_mask, d_keys, d_dists, d_counts, ix->scan_scratch,
-                          ix->scan_scratch_bytes, stream, tvp, sms, ix->scan_pinned);
+                          ix->scan_scratch_bytes, stream, tvp, sms, ix->scan_aux);
         if (d_stats) LEANN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, nq * 4 * sizeof(uint64_t), stream));
         return;
     }
@@ -779,6 +788,9 @@ void leann_cuda_close(leann_cuda_index* ix) {
     cudaFree(ws.d_dists); cudaFree(ws.d_counts); cudaFree(ws.d_mask);
     if (ws.stream) cudaStreamDestroy(ws.stream);
     if (ix->chain_ev) cudaEventDestroy(ix->chain_ev);
+    if (ix->scan_aux.helper) cudaStreamDestroy(ix->scan_aux.helper);
+    if (ix->scan_aux.fork) cudaEventDestroy(ix->scan_aux.fork);
+    if (ix->scan_aux.join) cudaEventDestroy(ix->scan_aux.join);
     if (ix->scan_pinned) cudaFreeHost(ix->scan_pinned);
     cudaFree(ix->scan_scratch); cudaFree(ix->tc_bf16); cudaFree(ix->tc_norms); cudaFree(ix->tc_xmax);
     cudaGetLastError();

@@ -163,9 +163,11 @@ __device__ void block_bitonic_sort(unsigned long long* keys, uint32_t n) {
     __syncthreads();
 }
 
-// The (kth+1)-th smallest of n 64-bit keys in shared memory: MSB-first radix select, 8 bits per pass.
-// All threads of the block call it; hist = 256 counters + 2 words in shared memory.
-__device__ unsigned long long block_kth_smallest(const unsigned long long* keys, uint32_t n, uint32_t kth, uint32_t* hist) {
+// The (kth+1)-th smallest of n 64-bit keys: MSB-first radix select, 8 bits per pass. `key(i)` reads key i (shared memory
+// staging buffer, or global memory in the low-shared-memory variant). All threads of the block call it; hist = 256
+// counters + 2 words in shared memory.
+template <typename KeyFn>
+__device__ unsigned long long block_kth_smallest(KeyFn key, uint32_t n, uint32_t kth, uint32_t* hist) {
     unsigned long long prefix = 0;
     uint32_t remaining = kth;
     for (int pass = 0; pass < 8; ++pass) {
@@ -173,7 +175,7 @@ __device__ unsigned long long block_kth_smallest(const unsigned long long* keys,
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long v = keys[i];
+            const unsigned long long v = key(i);
             if (pass == 0 || (v >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(uint32_t)(v >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -209,11 +211,15 @@ __device__ unsigned long long block_kth_smallest(const unsigned long long* keys,
 // A row can appear twice (once in best, once re-appended by a chunk re-run after overflow), never more, so the
 // 2k smallest keys with multiplicity always hold the k smallest distinct ones: a radix select cuts the working
 // set to those before the sort.
+// LOWSMEM: the candidates are not staged in shared memory (the radix passes re-read them through L2), so the block needs
+// only the sort buffer (4 KB for k <= 255) and can run on an SM whose shared memory belongs to a resident scan_tc CTA —
+// the two query halves of a batch overlap this kernel with the other half's tensor pass (launch_exact_scan).
+template <bool LOWSMEM>
 __global__ void __launch_bounds__(256)
 select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand_cnt, uint32_t cap,
               unsigned long long* __restrict__ best, uint32_t* __restrict__ best_cnt, uint32_t k, uint32_t kpad,
               unsigned long long* __restrict__ thr, uint32_t nq, uint32_t sort_cap) {
-    extern __shared__ unsigned long long skeys[];   // [sort_cap] sort buffer, then [cap + kpad] staging
+    extern __shared__ unsigned long long skeys[];   // [sort_cap] sort buffer (+ [cap + kpad] staging unless LOWSMEM)
     __shared__ uint32_t s_hist[258];
     __shared__ uint32_t s_n;
     const uint32_t q = blockIdx.x;
@@ -224,15 +230,20 @@ select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand
     if (nc == 0) return;  // nothing new: best/thr unchanged
     uint32_t total = nc + nb;
     unsigned long long* sortbuf = skeys;
+    const unsigned long long* gbest = best + (size_t)q * kpad;
+    const unsigned long long* gcand = cand + (size_t)q * cap;
+    auto gkey = [&](uint32_t i) { return i < nb ? gbest[i] : gcand[i - nb]; };
     if (total > 2 * k + 1 && total > 512) {
         unsigned long long* stage = skeys + sort_cap;
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x)
-            stage[i] = i < nb ? best[(size_t)q * kpad + i] : cand[(size_t)q * cap + (i - nb)];
+        if (!LOWSMEM) {
+            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) stage[i] = gkey(i);
+        }
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        const unsigned long long cut = block_kth_smallest(stage, total, 2 * k - 1, s_hist);
+        auto skey = [&](uint32_t i) { return LOWSMEM ? gkey(i) : stage[i]; };
+        const unsigned long long cut = block_kth_smallest(skey, total, 2 * k - 1, s_hist);
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            const unsigned long long v = stage[i];
+            const unsigned long long v = skey(i);
             if (v <= cut && v != ~0ull) {
                 uint32_t pos = atomicAdd(&s_n, 1u);
                 if (pos < sort_cap) sortbuf[pos] = v;
@@ -247,12 +258,7 @@ select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand
     } else {
         uint32_t n2 = 1;
         while (n2 < total) n2 <<= 1;
-        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-            unsigned long long v = ~0ull;
-            if (i < nb) v = best[(size_t)q * kpad + i];
-            else if (i < total) v = cand[(size_t)q * cap + (i - nb)];
-            sortbuf[i] = v;
-        }
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) sortbuf[i] = i < total ? gkey(i) : ~0ull;
         block_bitonic_sort(sortbuf, n2);
     }
     // dedupe adjacent equal keys; single thread compaction of at most k survivors.
@@ -398,9 +404,20 @@ size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
            align256((size_t)nq * dp8 * 2) + 3 * align256((size_t)nq * 4) + align256((size_t)nq * SCAN_CAP * 4);
 }
 
+// One half (or all) of a query batch: its own slice of every per-query scratch array, its own overflow words and stream.
+struct ScanJob {
+    uint32_t q0 = 0, nq = 0;
+    ScanScratch s{};
+    TcScratch ts{};
+    cudaStream_t stream = nullptr;
+    uint32_t* h_flag = nullptr;   // 2 pinned words
+    size_t first = 0;             // first round to (re)run
+    bool done = false;
+};
+
 void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
                        uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
-                       cudaStream_t stream, const TcIndexView* tv, int sms, uint32_t* h_flag) {
+                       cudaStream_t stream, const TcIndexView* tv, int sms, const ScanAux& aux) {
     if (k == 0 || k > 1024) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: k must be in 1..1024");
     if (nq == 0) return;
     const uint32_t kpad = (k + 31) & ~31u;
@@ -424,10 +441,30 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     }
     if ((size_t)(p - (unsigned char*)scratch) > scratch_bytes) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: scratch too small");
 
-    scan_init_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.cand_cnt, s.best_cnt, s.thr, nq, s.overflow,
-                                                           (uint32_t)std::min<uint64_t>(f.n, SCAN_CAP));
-    launch_pad_rows(d_queries, s.qpad, nq, f.d, f.d4, stream);
-    if (use_tc) exact_scan_tc_queries(s.qpad, nq, f.d4, tv->dp8, ts, stream);
+    // Two jobs when the batch is large enough to keep the tensor pipe busy with half of it: the halves run the same rounds
+    // on two streams, so that the f32 re-rank and the select of one half (HBM / latency bound, small shared memory)
+    // execute while the other half's scan_tc CTAs occupy the tensor cores. Per-query results do not depend on the split.
+    const bool split = use_tc && aux.helper != nullptr && nq >= 2048;
+    ScanJob jobs[2];
+    const uint32_t h = split ? (uint32_t)(((nq / 2) + 255) / 256 * 256) : nq;
+    const int n_jobs = split ? 2 : 1;
+    for (int j = 0; j < n_jobs; ++j) {
+        ScanJob& J = jobs[j];
+        J.q0 = j == 0 ? 0 : h;
+        J.nq = j == 0 ? h : nq - h;
+        J.stream = j == 0 ? stream : aux.helper;
+        J.h_flag = aux.h_flags + 2 * j;
+        J.s.cand = s.cand + (size_t)J.q0 * SCAN_CAP; J.s.cand_cnt = s.cand_cnt + J.q0; J.s.best = s.best + (size_t)J.q0 * kpad;
+        J.s.best_cnt = s.best_cnt + J.q0; J.s.thr = s.thr + J.q0; J.s.overflow = s.overflow + 2 * j; J.s.qpad = s.qpad + (size_t)J.q0 * f.d4;
+        if (use_tc) {
+            J.ts.q_bf16 = (unsigned char*)ts.q_bf16 + (size_t)J.q0 * tv->dp8 * 2; J.ts.qnorm = ts.qnorm + J.q0; J.ts.qres = ts.qres + J.q0;
+            J.ts.thr_dot = ts.thr_dot + J.q0; J.ts.cand_ids = ts.cand_ids + (size_t)J.q0 * SCAN_CAP;
+        }
+    }
+    if (split) {   // the helper stream starts after everything already queued on the caller's stream
+        LEANN_CUDA_CHECK(cudaEventRecord(aux.fork, stream));
+        LEANN_CUDA_CHECK(cudaStreamWaitEvent(aux.helper, aux.fork, 0));
+    }
 
     // Round boundaries: the first chunk holds SCAN_CAP rows (cannot overflow), later ones grow geometrically so
     // that the expected number of survivors per query and round stays near growth * k.
@@ -442,23 +479,30 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     static unsigned long long attr_seen = 0;
     uint32_t sort_cap = 512;   // sort buffer: the 2k + 1 keys a radix select keeps, or a short list sorted whole
     while (sort_cap < 2 * k + 1) sort_cap <<= 1;
-    const size_t sel_smem = ((size_t)sort_cap + SCAN_CAP + kpad) * 8;
+    const bool lowsmem = split;
+    const size_t sel_smem = lowsmem ? (size_t)sort_cap * 8 : ((size_t)sort_cap + SCAN_CAP + kpad) * 8;
     if (first_use_on_device(attr_seen))
-        LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)4096 + SCAN_CAP + 1024) * 8)));
-    auto run_round = [&](size_t ri, int attempt) {
+        LEANN_CUDA_CHECK(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)4096 + SCAN_CAP + 1024) * 8)));
+
+    auto begin_job = [&](ScanJob& J) {
+        scan_init_kernel<<<(J.nq + 255) / 256, 256, 0, J.stream>>>(J.s.cand_cnt, J.s.best_cnt, J.s.thr, J.nq, J.s.overflow,
+                                                                   (uint32_t)std::min<uint64_t>(f.n, SCAN_CAP));
+        launch_pad_rows(d_queries + (size_t)J.q0 * f.d, J.s.qpad, J.nq, f.d, f.d4, J.stream);
+        if (use_tc) exact_scan_tc_queries(J.s.qpad, J.nq, f.d4, tv->dp8, J.ts, J.stream);
+    };
+    auto run_round = [&](ScanJob& J, size_t ri, int attempt) {
         const uint32_t r0 = rounds[ri].first, r1 = rounds[ri].second;
-        dim3 grid((r1 - r0 + TN - 1) / TN, (nq + TM - 1) / TM);
+        dim3 grid((r1 - r0 + TN - 1) / TN, (J.nq + TM - 1) / TM);
         if (use_tc && ri > 0) {
             // tensor-core pass + fp32 re-rank for every chunk after the first
-            exact_scan_tc_round(f, *tv, s, ts, nq, r0, r1, d_mask, SCAN_CAP, sms, stream);
-        } else
-        {
+            exact_scan_tc_round(f, *tv, J.s, J.ts, J.nq, r0, r1, d_mask, SCAN_CAP, sms, J.stream);
+        } else {
             const bool direct = ri == 0 && attempt == 0;   // no threshold yet: slot = row offset, cand_cnt preset by scan_init
-#define LEANN_TILE(M)                                                                                                          \
-    (direct ? scan_tile_kernel<M, true><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand,      \
-                                                                   s.cand_cnt, SCAN_CAP, s.overflow)                            \
-            : scan_tile_kernel<M, false><<<grid, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, r0, r1, d_mask, s.thr, s.cand,     \
-                                                                    s.cand_cnt, SCAN_CAP, s.overflow))
+#define LEANN_TILE(M)                                                                                                            \
+    (direct ? scan_tile_kernel<M, true><<<grid, 256, 0, J.stream>>>(f.vecs, J.s.qpad, f.d4, J.nq, r0, r1, d_mask, J.s.thr,        \
+                                                                     J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.overflow)              \
+            : scan_tile_kernel<M, false><<<grid, 256, 0, J.stream>>>(f.vecs, J.s.qpad, f.d4, J.nq, r0, r1, d_mask, J.s.thr,       \
+                                                                      J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.overflow))
             switch (f.metric) {
                 case LEANN_METRIC_L2SQ: LEANN_TILE(LEANN_METRIC_L2SQ); break;
                 case LEANN_METRIC_IP_CLAMP: LEANN_TILE(LEANN_METRIC_IP_CLAMP); break;
@@ -468,26 +512,51 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
 #undef LEANN_TILE
         }
         LEANN_CUDA_CHECK(cudaGetLastError());
-        select_kernel<<<nq, 256, sel_smem, stream>>>(s.cand, s.cand_cnt, SCAN_CAP, s.best, s.best_cnt, k, kpad, s.thr, nq, sort_cap);
-        note_overflow_kernel<<<1, 1, 0, stream>>>(s.overflow, (uint32_t)ri);
+        if (lowsmem)
+            select_kernel<true><<<J.nq, 256, sel_smem, J.stream>>>(J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.best, J.s.best_cnt, k, kpad, J.s.thr, J.nq, sort_cap);
+        else
+            select_kernel<false><<<J.nq, 256, sel_smem, J.stream>>>(J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.best, J.s.best_cnt, k, kpad, J.s.thr, J.nq, sort_cap);
+        note_overflow_kernel<<<1, 1, 0, J.stream>>>(J.s.overflow, (uint32_t)ri);
         LEANN_CUDA_CHECK(cudaGetLastError());
     };
-    // All rounds are enqueued back to back; the device records the first round whose candidate list
-    // overflowed (s.overflow[1]). One synchronisation at the end; if a round overflowed, that round and the ones
-    // after it are repeated with the tightened thresholds (rows already kept are deduplicated by select_kernel).
-    size_t first = 0;
+    // All rounds of every job are enqueued back to back, round by round across the jobs so that the streams alternate;
+    // the device records the first round whose candidate list overflowed (overflow[1]). One synchronisation per attempt; a
+    // job that overflowed repeats that round and the ones after it with the tightened thresholds (rows already kept are
+    // deduplicated by select_kernel).
+    for (int j = 0; j < n_jobs; ++j) begin_job(jobs[j]);
     for (int attempt = 0;; ++attempt) {
-        for (size_t ri = first; ri < rounds.size(); ++ri) run_round(ri, attempt);
-        LEANN_CUDA_CHECK(cudaMemcpyAsync(h_flag, s.overflow, 8, cudaMemcpyDeviceToHost, stream));
-        LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
-        if (h_flag[1] == 0xFFFFFFFFu) break;
-        first = h_flag[1];
+        bool any = false;
+        for (size_t ri = 0; ri < rounds.size(); ++ri)
+            for (int j = 0; j < n_jobs; ++j)
+                if (!jobs[j].done && ri >= jobs[j].first) { run_round(jobs[j], ri, attempt); any = true; }
+        if (!any) break;
+        for (int j = 0; j < n_jobs; ++j)
+            if (!jobs[j].done) LEANN_CUDA_CHECK(cudaMemcpyAsync(jobs[j].h_flag, jobs[j].s.overflow, 8, cudaMemcpyDeviceToHost, jobs[j].stream));
+        for (int j = 0; j < n_jobs; ++j)
+            if (!jobs[j].done) LEANN_CUDA_CHECK(cudaStreamSynchronize(jobs[j].stream));
+        bool again = false;
+        for (int j = 0; j < n_jobs; ++j) {
+            ScanJob& J = jobs[j];
+            if (J.done) continue;
+            if (J.h_flag[1] == 0xFFFFFFFFu) { J.done = true; continue; }
+            J.first = J.h_flag[1];
+            again = true;
+            scan_reset_overflow_kernel<<<1, 1, 0, J.stream>>>(J.s.overflow);
+        }
+        if (!again) break;
         if (attempt > 64) throw Error(LEANN_ERR_CUDA, "exact scan: candidate overflow did not converge");
-        scan_reset_overflow_kernel<<<1, 1, 0, stream>>>(s.overflow);
     }
-    uint32_t tot = nq * k;
-    scan_finish_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(s.best, s.best_cnt, k, kpad, nq, f.metric, d_keys, d_dists, d_counts);
-    LEANN_CUDA_CHECK(cudaGetLastError());
+    for (int j = 0; j < n_jobs; ++j) {
+        ScanJob& J = jobs[j];
+        const uint32_t tot = J.nq * k;
+        scan_finish_kernel<<<(tot + 255) / 256, 256, 0, J.stream>>>(J.s.best, J.s.best_cnt, k, kpad, J.nq, f.metric, d_keys + (size_t)J.q0 * k,
+                                                                     d_dists + (size_t)J.q0 * k, d_counts ? d_counts + J.q0 : nullptr);
+        LEANN_CUDA_CHECK(cudaGetLastError());
+    }
+    if (split) {   // the caller's stream continues after the helper's half
+        LEANN_CUDA_CHECK(cudaEventRecord(aux.join, aux.helper));
+        LEANN_CUDA_CHECK(cudaStreamWaitEvent(stream, aux.join, 0));
+    }
 }
 
 void launch_topk_merge(const uint64_t* keys_in, const float* dists_in, uint32_t n_shards, uint32_t nq, uint32_t k,

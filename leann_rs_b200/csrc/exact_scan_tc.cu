@@ -47,9 +47,10 @@ constexpr int TC_B_BYTES = TC_NH * TC_K * 2;   // 16 KB: one k-block of this CTA
 constexpr int TC_MAX_RES_KB = 7;  // query tile stays resident in shared memory up to 7 k-blocks (d <= 448)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 256;
-constexpr int TC_QBUF = 32;      // survivors buffered per query row before one slot reservation
+constexpr int TC_QBUF = 16;      // survivors buffered per query row before one slot reservation
 constexpr int TC_BAR_BYTES = 512;
-constexpr size_t TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
+constexpr size_t TC_SMEM_MAX = 225280;  // 220 KB of the 227 KB opt-in limit: the rest lets a select_kernel<true> / rerank CTA of the
+                                        // other query half share the SM (launch_exact_scan)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {

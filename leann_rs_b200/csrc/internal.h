@@ -145,9 +145,15 @@ int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_cap
 // Exact scan (K2 + K2r)
 struct FlatView { const float4* vecs; uint32_t n, d, d4; int metric; };
 struct TcIndexView;
+// helper stream / events / pinned flag words a handle lends to the exact scan (two query halves on two streams)
+struct ScanAux {
+    cudaStream_t helper = nullptr;   // nullptr: never split the batch
+    cudaEvent_t fork = nullptr, join = nullptr;
+    uint32_t* h_flags = nullptr;     // pinned, 4 words
+};
 void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, uint32_t k, const uint64_t* d_mask,
                        uint64_t* d_keys, float* d_dists, uint32_t* d_counts, void* scratch, size_t scratch_bytes,
-                       cudaStream_t stream, const TcIndexView* tv, int sms, uint32_t* h_flag /*pinned, 2 words*/);
+                       cudaStream_t stream, const TcIndexView* tv, int sms, const ScanAux& aux);
 size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k);
 
 void launch_topk_merge(const uint64_t* keys_in, const float* dists_in, uint32_t n_shards, uint32_t nq, uint32_t k,
@@ -203,7 +209,8 @@ struct leann_cuda_index {
     mutable leann::SearchWorkspace ws;
     mutable void* scan_scratch = nullptr;
     mutable size_t scan_scratch_bytes = 0;
-    mutable uint32_t* scan_pinned = nullptr;   // 2 pinned words for the overflow read-back
+    mutable uint32_t* scan_pinned = nullptr;   // pinned words for the overflow read-back (2 per query half)
+    mutable leann::ScanAux scan_aux;           // helper stream + events of the two-half exact scan
     // tensor-path copy of a flat database (bf16 rows, row norms, max norm), built on first use
     mutable void* tc_bf16 = nullptr;
     mutable float* tc_norms = nullptr;

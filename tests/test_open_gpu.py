@@ -30,17 +30,20 @@ def test_layout_cache_round_trip(orc, pkg, tmp_path, d):
     s = pkg.HnswSearcher.load(base, d)
     assert not s.layout_cache_used and not os.path.exists(cache)
     k0 = _search_equal(pkg, s, g, q, d)
+    base1 = str(tmp_path / "parsed" / "documents.leann")
+    os.makedirs(os.path.dirname(base1))
+    s.save(base1)                                   # what a handle loaded by parsing the node block writes back
     s.write_layout_cache(base)
     assert os.path.exists(cache)
     s.close()
     s = pkg.HnswSearcher.load(base, d)               # adjacency from the cache, vectors streamed from the .index
     assert s.layout_cache_used
     assert np.array_equal(_search_equal(pkg, s, g, q, d), k0)
-    # save() from a cache-loaded handle writes the same .index bytes (levels and keys survive the cache)
+    # save() from a cache-loaded handle writes the same .index bytes as the parse-loaded one (levels, keys, lists survive)
     base2 = str(tmp_path / "copy" / "documents.leann")
     os.makedirs(os.path.dirname(base2))
     s.save(base2)
-    assert open(base2.replace(".leann", ".index"), "rb").read() == open(idx_file, "rb").read()
+    assert open(base2.replace(".leann", ".index"), "rb").read() == open(base1.replace(".leann", ".index"), "rb").read()
     s.close()
     # a touched .index (same bytes, new mtime) invalidates the cache: parsed again, same answers
     st = os.stat(idx_file)
