@@ -501,6 +501,9 @@ struct RegList {
     // insert at `pos` (< limit), dropping the last entry when the list already holds `limit`.
     // Written with value selects only: conditional stores into d[j] / s[j] get merged by the compiler into one store
     // through a computed address, which sends the arrays to local memory.
+    // DROP = false (single-list mode, where nothing is ever popped): the entry pushed past `limit` is left in place; it is
+    // never read (readers respect `size`) and cannot disturb rank() because inserts are gated by d < d[limit - 1].
+    template <bool DROP = true>
     __device__ __forceinline__ void insert_at(int pos, float dd, uint32_t ss, int limit, int lane) {
         const int lp = pos / EPL, rp = pos % EPL;
         const float cd = __shfl_up_sync(FULL, d[EPL - 1], 1);
@@ -518,17 +521,17 @@ struct RegList {
             const bool ins = here && j == rp;
             nd = ins ? dd : nd;
             ns = ins ? ss : ns;
-            const bool drop = full && limit < 32 * EPL && lane == ll && j == rl;   // the entry pushed past the bound
+            const bool drop = DROP && full && limit < 32 * EPL && lane == ll && j == rl;   // the entry pushed past the bound
             d[j] = drop ? CUDART_INF_F : nd;
             s[j] = drop ? SENT : ns;
         }
         size += full ? 0 : 1;
     }
-    template <bool UPPER>
+    template <bool UPPER, bool DROP = true>
     __device__ __forceinline__ bool insert(float dd, uint32_t ss, int limit, int lane) {
         const int pos = rank<UPPER>(dd);
         if (pos >= limit) return false;
-        insert_at(pos, dd, ss, limit, lane);
+        insert_at<DROP>(pos, dd, ss, limit, lane);
         return true;
     }
     __device__ __forceinline__ float dist_at(int i) const {
@@ -550,32 +553,86 @@ struct RegList {
 };
 
 // beam_level with register lists: same loop as beam_level<..., PREFETCH = true> without a mask.
-template <int LPV, int VPL, int U, int EPL>
+//
+// SINGLE (diskann-rs stop rule only): one list. Without a mask every queued candidate was inserted into `top` at the same
+// moment, so the queue is `top` minus the entries already expanded, plus entries `top` has evicted since. An evicted entry
+// has d >= the current worst of a full `top`, and search_with_dists stops as soon as the queue head has d >= that worst: an
+// evicted entry can only ever end the search, which the first unexpanded entry of `top` (or its absence) decides just as
+// well. The queue therefore becomes one "expanded" bit per entry of `top` (bit 31 of the slot, slots stay below 2^31):
+// one sorted insert per accepted neighbour instead of two. Equal distances: the queue is FIFO among equals while `top` puts a
+// newcomer first, so the oldest of an equal run is its LAST unexpanded entry — that one is popped. Results are identical to the
+// two-list form bit for bit (the randomised parity tests include duplicate rows); the queue can no longer overflow, so the
+// `dropped` counter stays 0.
+constexpr uint32_t XBIT = 0x80000000u;
+template <int LPV, int VPL, int U, int EPL, bool SINGLE>
 __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL], WarpLists& w,
                                                int ef, int next_cap, int nonstrict, VisitedSet& vs, uint32_t warp_id,
                                                uint32_t start, float start_d, Counters& c, int lane,
                                                uint32_t k, uint64_t* __restrict__ out_keys, float* __restrict__ out_dists) {
     RegList<EPL> top, next;
     top.clear();
-    next.clear();
+    if (!SINGLE) next.clear();
     float radius = CUDART_INF_F;
-    next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(start_d, start, next_cap, lane);
+    if (!SINGLE) next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(start_d, start, next_cap, lane);
     if (lane == 0) visited_test_and_set(vs, start);
     visited_added(vs, 1u, warp_id, lane);
-    top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS>(start_d, start, ef, lane);
+    top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, !SINGLE>(start_d, start, ef, lane);
     if (top.size == ef) radius = top.dist_at(ef - 1);
-    while (next.size > 0) {
-        const float cd = __shfl_sync(FULL, next.d[0], 0);
-        const uint32_t cs = __shfl_sync(FULL, next.s[0], 0);
-        if (nonstrict ? (cd >= radius) : (cd > radius)) break;
-        next.pop_front(lane);
+    for (;;) {
+        float cd;
+        uint32_t cs;
+        if (SINGLE) {
+            // queue head = first unexpanded entry of `top`
+            unsigned mine = 0;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) mine |= (lane * EPL + j < top.size && !(top.s[j] & XBIT)) ? (1u << j) : 0u;
+            const unsigned b = __ballot_sync(FULL, mine != 0);
+            if (!b) break;
+            const int L = __ffs(b) - 1;
+            const int j0 = __ffs(__shfl_sync(FULL, mine, L)) - 1;
+            cd = top.dist_at(L * EPL + j0);
+            if (top.size >= ef && cd >= radius) break;
+            // FIFO among equal distances: the oldest of the run is its last unexpanded entry
+            unsigned eq = 0;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) eq |= (((mine >> j) & 1u) && top.d[j] == cd) ? (1u << j) : 0u;
+            const unsigned be = __ballot_sync(FULL, eq != 0);
+            const int H = 31 - __clz(be);
+            const int jH = 31 - __clz(__shfl_sync(FULL, eq, H));
+            uint32_t sv0 = top.s[0];
+#pragma unroll
+            for (int j = 1; j < EPL; ++j) sv0 = (j == jH) ? top.s[j] : sv0;
+            cs = __shfl_sync(FULL, sv0, H);
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) top.s[j] |= (lane == H && j == jH) ? XBIT : 0u;
+            mine &= (lane == H) ? ~(1u << jH) : ~0u;
+            if (adj.level == 0) {
+                // the most likely next pop is the next unexpanded entry: pull its adjacency row into L2 now
+                const unsigned b2 = __ballot_sync(FULL, mine != 0);
+                if (b2) {
+                    const int L2 = __ffs(b2) - 1;
+                    const int j2 = __ffs(__shfl_sync(FULL, mine, L2)) - 1;
+                    uint32_t sn = top.s[0];
+#pragma unroll
+                    for (int j = 1; j < EPL; ++j) sn = (j == j2) ? top.s[j] : sn;
+                    const uint32_t nh = __shfl_sync(FULL, sn, L2);
+                    if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
+                }
+            }
+        } else {
+            if (next.size == 0) break;
+            cd = __shfl_sync(FULL, next.d[0], 0);
+            cs = __shfl_sync(FULL, next.s[0], 0);
+            if (nonstrict ? (cd >= radius) : (cd > radius)) break;
+            next.pop_front(lane);
+            if (adj.level == 0 && next.size > 0) {
+                // the most likely next pop is the new head of the queue: pull its adjacency row into L2 now
+                const uint32_t nh = __shfl_sync(FULL, next.s[0], 0);
+                if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
+            }
+        }
         if (adj.level == 0) c.n_hops0++; else c.n_hops_upper++;
         const uint32_t* row = adj.row(cs);
-        if (adj.level == 0 && next.size > 0) {
-            // the most likely next pop is the new head of the queue: pull its adjacency row into L2 now
-            const uint32_t nh = __shfl_sync(FULL, next.s[0], 0);
-            if ((uint32_t)lane * 32u < adj.deg) prefetch_l2(adj.adj0 + (size_t)nh * adj.deg + lane * 32);
-        }
         int cnt = 0;
         // the row is handled 64 neighbours at a time (one pass for the usual degrees M0 = 64 / R = 64): the visited tags of a
         // pass are requested together, membership is decided per lane, the compaction keeps list order
@@ -649,9 +706,11 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                 const float dd = __shfl_sync(FULL, dj, l);
                 if (top.size < ef || dd < radius) {
                     const uint32_t ss = __shfl_sync(FULL, sj, l);
-                    if (next.size == next_cap) c.dropped = 1;
-                    next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(dd, ss, next_cap, lane);
-                    top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS>(dd, ss, ef, lane);
+                    if (!SINGLE) {
+                        if (next.size == next_cap) c.dropped = 1;
+                        next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(dd, ss, next_cap, lane);
+                    }
+                    top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, !SINGLE>(dd, ss, ef, lane);
                     if (top.size == ef) {
                         radius = top.dist_at(ef - 1);
                         m &= __ballot_sync(FULL, dj < radius);   // later entries that can no longer pass are skipped now
@@ -668,7 +727,8 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
         const uint32_t i = (uint32_t)(lane * EPL + j);
         if (i < k) {
             const bool ok = (int)i < cnt;
-            out_keys[i] = ok ? (g.keys ? g.keys[top.s[j]] : (uint64_t)top.s[j]) : ~0ull;
+            const uint32_t slot = SINGLE ? (top.s[j] & ~XBIT) : top.s[j];
+            out_keys[i] = ok ? (g.keys ? g.keys[slot] : (uint64_t)slot) : ~0ull;
             out_dists[i] = ok ? top.d[j] : CUDART_INF_F;
         }
     }

@@ -17,7 +17,7 @@ namespace leann {
 
 // EPL > 0: `top` / `next` live in registers (RegList<EPL>, graph_device.cuh); the host picks that instantiation for short
 // rows when max(ef, queue capacity) <= 32 * EPL and no mask is set. Shared memory then holds only the staging row.
-template <int LPV, int VPL, int U, int MINB, int EPL>
+template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE = false>
 __global__ void __launch_bounds__(128, MINB)
 graph_search_kernel(const GraphView g, const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -73,7 +73,7 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
         int cnt;
         if constexpr (EPL > 0) {
-            cnt = beam_level_regs<LPV, VPL, U, EPL>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
+            cnt = beam_level_regs<LPV, VPL, U, EPL, SINGLE>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
                                                     (uint32_t)warp_global, cur, cur_d, c, lane, p.k,
                                                     p.out_keys + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k);
             visited_end(vs, lane);
@@ -213,16 +213,26 @@ inline bool use_reg_lists(const SearchParams& p) {
     return p.mask == nullptr && p.ef <= 32u * REG_EPL && p.next_cap <= 32u * REG_EPL && p.k <= 32u * REG_EPL;
 }
 
-template <int LPV, int VPL, int U, int MINB, int EPL = 0>
+// one list with an "expanded" bit instead of top + next (graph_device.cuh): diskann-rs stop rule, slots below 2^31, and
+// the tie rules this form was derived for
+inline bool use_single_list(const GraphView& g, const SearchParams& p) {
+    return p.nonstrict_term && g.n < 0x80000000u && compat::TOP_NEWCOMER_BEFORE_EQUALS && compat::NEXT_FIFO_AMONG_EQUALS &&
+           getenv("LEANN_CUDA_DISABLE_SINGLE_LIST") == nullptr;
+}
+
+template <int LPV, int VPL, int U, int MINB, int EPL = 0, bool SINGLE = false>
 int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
     if constexpr (EPL == 0 && LPV < 32) {
         // short rows: the register-list instantiation when the lists fit (small batches keep the cooperative kernel)
         const bool off = getenv("LEANN_CUDA_DISABLE_REG_LISTS") != nullptr;   // A/B switch for benchmarks
-        if (!off && p.coop_ctas == 0 && use_reg_lists(p)) return launch_t<LPV, VPL, U, MINB, REG_EPL>(g, p, stream, op);
+        if (!off && p.coop_ctas == 0 && use_reg_lists(p)) {
+            if (use_single_list(g, p)) return launch_t<LPV, VPL, U, MINB, REG_EPL, true>(g, p, stream, op);
+            return launch_t<LPV, VPL, U, MINB, REG_EPL>(g, p, stream, op);
+        }
     }
     const int warps_per_block = 4;
     size_t smem = (EPL > 0 ? (size_t)MAX_DEG * 8 : graph_search_smem_per_warp(p.ef, p.next_capp)) * warps_per_block;
-    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL>;
+    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL, SINGLE>;
     if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (op == 1) {
         int blocks_per_sm = 0;
@@ -261,13 +271,13 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
             const char* tune = getenv("LEANN_K1_TUNE");
             if (tune && p.coop_ctas == 0 && use_reg_lists(p)) {
                 const std::string t(tune);
-                if (t == "4,5") return launch_t<8, 3, 4, 5, REG_EPL>(g, p, stream, op);
-                if (t == "2,6") return launch_t<8, 3, 2, 6, REG_EPL>(g, p, stream, op);
-                if (t == "3,6") return launch_t<8, 3, 3, 6, REG_EPL>(g, p, stream, op);
-                if (t == "3,5") return launch_t<8, 3, 3, 5, REG_EPL>(g, p, stream, op);
-                if (t == "2,8") return launch_t<8, 3, 2, 8, REG_EPL>(g, p, stream, op);
-                if (t == "2,7") return launch_t<8, 3, 2, 7, REG_EPL>(g, p, stream, op);
-                if (t == "4,4") return launch_t<8, 3, 4, 4, REG_EPL>(g, p, stream, op);
+                if (t == "4,5") return use_single_list(g, p) ? launch_t<8, 3, 4, 5, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 4, 5, REG_EPL>(g, p, stream, op);
+                if (t == "2,6") return use_single_list(g, p) ? launch_t<8, 3, 2, 6, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 6, REG_EPL>(g, p, stream, op);
+                if (t == "3,6") return use_single_list(g, p) ? launch_t<8, 3, 3, 6, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 3, 6, REG_EPL>(g, p, stream, op);
+                if (t == "3,5") return use_single_list(g, p) ? launch_t<8, 3, 3, 5, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 3, 5, REG_EPL>(g, p, stream, op);
+                if (t == "2,8") return use_single_list(g, p) ? launch_t<8, 3, 2, 8, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 8, REG_EPL>(g, p, stream, op);
+                if (t == "2,7") return use_single_list(g, p) ? launch_t<8, 3, 2, 7, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 7, REG_EPL>(g, p, stream, op);
+                if (t == "4,4") return use_single_list(g, p) ? launch_t<8, 3, 4, 4, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 4, 4, REG_EPL>(g, p, stream, op);
             }
             return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
         }

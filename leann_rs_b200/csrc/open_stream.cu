@@ -147,7 +147,7 @@ struct LayoutHead {   // 128 bytes
 static_assert(sizeof(LayoutHead) == 128, "layout head");
 
 size_t layout_bytes(const LayoutHead& h) {
-    return sizeof(LayoutHead) + h.n * 2 + h.n * 4 + h.n * h.M0 * 4 + h.n_upper * h.M * 4 + (h.identity_keys ? 0 : h.n * 8);
+    return sizeof(LayoutHead) + h.n * 2 + h.n * 4 + h.n * h.M0 * 4 + h.n_upper * h.M * 4 + h.n * 8;
 }
 
 bool layout_valid(const std::string& path, const UsearchPlan& pl, LayoutHead& h) {
@@ -178,7 +178,7 @@ void write_layout_cache(const leann_cuda_index* ix, const std::string& base) {
     h.n = ix->n; h.d = ix->d; h.M = ix->M; h.M0 = ix->M0; h.max_level = (uint64_t)ix->max_level; h.entry = ix->entry;
     h.n_upper = ix->n_upper_lists; h.identity_keys = ix->identity_keys ? 1 : 0;
     std::vector<uint32_t> upper(ix->n), adj0(ix->n * ix->M0), adjU(ix->n_upper_lists * ix->M);
-    std::vector<uint64_t> keys(ix->identity_keys ? 0 : ix->n);
+    std::vector<uint64_t> keys(ix->n);
     auto down = [](auto& v, const void* src) { if (!v.empty()) LEANN_CUDA_CHECK(cudaMemcpy(v.data(), src, v.size() * sizeof(v[0]), cudaMemcpyDeviceToHost)); };
     down(upper, ix->upper_base); down(adj0, ix->adj0); down(adjU, ix->adjU); down(keys, ix->keys);
     const std::string path = with_extension(base, "cuda-layout"), tmp = path + ".tmp";
@@ -228,7 +228,7 @@ leann_cuda_index* open_hnsw_streamed(const std::string& base, size_t dims, int d
             st.copy(cf, off, pl.n * pl.M0 * 4, ix->adj0, stream, "layout adj0"); off += pl.n * pl.M0 * 4;
             st.copy(cf, off, lh.n_upper * pl.M * 4, ix->adjU, stream, "layout adjU"); off += lh.n_upper * pl.M * 4;
             ix->identity_keys = lh.identity_keys != 0;
-            if (!ix->identity_keys) st.copy(cf, off, pl.n * 8, ix->keys, stream, "layout keys");
+            st.copy(cf, off, pl.n * 8, ix->keys, stream, "layout keys");
             st.vectors(f, pl.vec_off, pl.n, pl.d, ix->d4, ix->vecs, stream);
             LEANN_CUDA_CHECK(cudaStreamSynchronize(stream));
         } else {
