@@ -35,7 +35,9 @@ for v in variants:
         torch.cuda.synchronize()
         if v == "base":
             ref[ef] = (keys.clone(), dists.clone(), st.clone())
-        same = bool(torch.equal(keys, ref[ef][0]) and torch.equal(dists.view(torch.int32), ref[ef][1].view(torch.int32)) and torch.equal(st, ref[ef][2])) if ef in ref else None
+        same = None
+        if ef in ref:   # ids, distance bits and the work counters (evaluations, hops); the queue-drop flag is 0 by construction in single-list mode
+            same = bool(torch.equal(keys, ref[ef][0]) and torch.equal(dists.view(torch.int32), ref[ef][1].view(torch.int32)) and torch.equal(st[:, :3], ref[ef][2][:, :3]))
         tot = st.sum(0).tolist()
         byts = tot[0] * ((a.d + 3) // 4) * 16 + tot[1] * info["M0"] * 4
         ms, step_ms = S2._timed(torch, lambda: idx.search_device(q, 10, ef), a.steps, 3)
