@@ -209,16 +209,22 @@ void ensure_workspace(const leann_cuda_index* ix, size_t nq, int warps_per_sm, s
     LEANN_CUDA_CHECK(cudaMemset(ws.pool_locks, 0, (size_t)want * 4));
 }
 
-// Throughput batches on long rows: when the hash tables of all resident warps fit in (most of) L2 they beat the byte maps, which
-// cost one DRAM burst per neighbour test: 8192-entry tables (64 MB for 12 warps per SM) measured 4-7 % faster at ef = 64, 16384-entry
-// tables 1.7 % faster at ef = 148 on 1M x 768. Chosen only when the expected number of visited nodes (about 0.7 * ef * degree) leaves
-// the table under 41 % full, so that spills into the byte maps (limit 75 %) stay exceptional. Returns the capacity, 0 = byte maps.
+// Throughput batches: per-warp visited hash tables that (mostly) stay in L2 instead of byte maps in HBM, which cost one DRAM
+// burst per neighbour test plus the write-back. Long rows (d > 256): 8192-entry tables (64 MB for 12 warps per SM) measured
+// 4-7 % faster at ef = 64, 16384-entry tables 1.7 % faster at ef = 148 on 1M x 768; allowed while all tables fit in 128 MB.
+// Short rows (d <= 256, register-list kernels): the traversal is bound by DRAM transactions, a third of which are visited
+// tags; on the 12.5M x 96 Vamana shard 16384-entry tables (232 MB for 24 warps per SM, about half of it L2-resident)
+// measured 5.54 -> 4.98 ms at L = 100 and 8192-entry tables 2.57 ms at L = 50 (benchmarks/k1_visited_ab.py), so up to
+// 256 MB of tables are allowed there. A capacity is chosen only when the expected number of visited nodes (about
+// 0.7 * ef * degree) leaves the table under 41 % full, so that spills into the byte maps (limit 75 %) stay exceptional.
+// Returns the capacity, 0 = byte maps.
 uint32_t l2_hash_capacity(const leann_cuda_index* ix, size_t ef) {
     const SearchWorkspace& ws = ix->ws;
     if (ix->vhash_mode != 0 || ws.large_mode || ws.n_warps <= 0) return 0;
     if ((size_t)ws.n_warps * ws.n_pad <= ((size_t)64 << 20)) return 0;   // small index: the byte maps themselves live in L2
+    const size_t budget = reduction_lanes(ix->d) == 8 ? ((size_t)256 << 20) : ((size_t)128 << 20);
     for (uint32_t cap : {8192u, 16384u})
-        if (70 * ef * ix->M0 <= 41 * (size_t)cap && (size_t)ws.n_warps * cap * 4 <= ((size_t)128 << 20)) return cap;
+        if (70 * ef * ix->M0 <= 41 * (size_t)cap && (size_t)ws.n_warps * cap * 4 <= budget) return cap;
     return 0;
 }
 void ensure_l2_hash(const leann_cuda_index* ix, uint32_t cap) {

@@ -279,6 +279,10 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
                 if (t == "2,7") return use_single_list(g, p) ? launch_t<8, 3, 2, 7, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 7, REG_EPL>(g, p, stream, op);
                 if (t == "4,4") return use_single_list(g, p) ? launch_t<8, 3, 4, 4, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 4, 4, REG_EPL>(g, p, stream, op);
             }
+            // d <= 96. Register lists (r2): <U = 3, 6 CTAs per SM> measured best of {4,6; 4,5; 3,6; 3,5; 2,6; 2,7; 2,8; 4,4}
+            // on the 12.5M x 96 Vamana shard (profiles/r2_k1_tune*.log); shared-memory lists (ef > 128, masks): <4, 6>.
+            if (p.coop_ctas == 0 && use_reg_lists(p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr)
+                return use_single_list(g, p) ? launch_t<8, 3, 3, 6, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 3, 6, REG_EPL>(g, p, stream, op);
             return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
         }
         if (vpl <= 4) return launch_t<8, 4, 2, 6>(g, p, stream, op);   // d = 128: +10-15 % over <8,4,4,4>
