@@ -227,6 +227,32 @@ uint32_t l2_hash_capacity(const leann_cuda_index* ix, size_t ef) {
         if (70 * ef * ix->M0 <= 41 * (size_t)cap && (size_t)ws.n_warps * cap * 4 <= budget) return cap;
     return 0;
 }
+// Modular inverse of the table's hash multiplier 0x9E3779B1 (mod 2^32): reconstructs a slot from a quotiented entry.
+constexpr uint32_t inv_mod32(uint32_t a) { uint32_t x = a; for (int i = 0; i < 5; ++i) x *= 2u - a * x; return x; }
+constexpr uint32_t Q_HASH_INV = inv_mod32(0x9E3779B1u);
+static_assert(Q_HASH_INV * 0x9E3779B1u == 1u, "hash multiplier inverse");
+
+// q16 table for the register-list kernels: `slots` 16-bit entries per warp in buckets of 8. Sized for <= ~33 % load at
+// the expected 0.7 * ef * degree visited nodes; the slot space must split into bucket bits + at most 14 remainder bits.
+bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* rem_bits, uint32_t* key_bits) {
+    static const bool off = getenv("LEANN_CUDA_DISABLE_Q16") != nullptr;   // A/B switch for benchmarks
+    const SearchWorkspace& ws = ix->ws;
+    if (off || ix->vhash_mode == 1 || ws.n_warps <= 0 || ix->n < 2) return false;
+    if (!ws.large_mode && ix->vhash_mode == 0 && (size_t)ws.n_warps * ws.n_pad <= ((size_t)64 << 20)) return false;   // byte maps already live in L2
+    uint32_t B = 1;
+    while (B < 32 && ((uint64_t)1 << B) < ix->n) ++B;
+    uint32_t S = 8192;
+    while ((size_t)S * 10 < 21 * ef * ix->M0 && S < 65536) S <<= 1;          // S >= 3 * 0.7 * ef * degree
+    if (ix->vhash_mode >= 1024) S = std::max<uint32_t>(1024u, std::min<uint32_t>(65536u, next_pow2((uint32_t)std::min<size_t>(ix->vhash_mode, 65536))));   // tests: tiny tables exercise the spill
+    auto bucket_bits = [](uint32_t s) { uint32_t b = 0; while ((8u << b) < s) ++b; return b; };
+    while (B > bucket_bits(S) + 14 && S < 65536) S <<= 1;
+    const uint32_t bb = bucket_bits(S);
+    if (B <= bb || B > bb + 14) return false;
+    if ((size_t)ws.n_warps * S * 2 > ((size_t)256 << 20) && !ws.large_mode && ix->vhash_mode == 0) return false;
+    *slots = S; *rem_bits = B - bb; *key_bits = B;
+    return true;
+}
+
 void ensure_l2_hash(const leann_cuda_index* ix, uint32_t cap) {
     SearchWorkspace& ws = ix->ws;
     const size_t words = (size_t)ws.n_warps * cap;
@@ -337,10 +363,18 @@ void search_device_launch(const leann_cuda_index* ix, const float* d_queries, si
         p.coop_warps = nq <= (size_t)sms ? 8 : 4;
     }
     // throughput batches only: a latency-bound single traversal pays more for the CAS round trips than it saves (measured +20 %)
+    p.vhash16 = 0; p.q_rem_bits = 0; p.q_key_bits = 32; p.q_inv = 0;
     if (p.coop_ctas == 0) {
-        if (const uint32_t cap = l2_hash_capacity(ix, p.ef)) {
-            ensure_l2_hash(ix, cap);
-            p.vhash = ix->ws.vhash; p.vhash_cap = cap;
+        uint32_t q16_slots = 0;
+        if (graph_search_uses_reg_lists(ix->view(), p) && q16_plan(ix, p.ef, &q16_slots, &p.q_rem_bits, &p.q_key_bits)) {
+            // short rows: bucketed table of 16-bit quotiented entries (graph_device.cuh), L2-resident for all resident warps
+            ensure_l2_hash(ix, q16_slots / 2);   // words per warp
+            p.vhash = ix->ws.vhash; p.vhash_cap = q16_slots; p.vhash16 = 1; p.q_inv = Q_HASH_INV;
+        } else if (!ix->ws.large_mode) {
+            if (const uint32_t cap = l2_hash_capacity(ix, p.ef)) {
+                ensure_l2_hash(ix, cap);
+                p.vhash = ix->ws.vhash; p.vhash_cap = cap;
+            }
         }
     }
     launch_graph_search(ix->view(), p, stream);

@@ -297,20 +297,112 @@ struct VisitedSet {
     uint8_t* vis; uint8_t tag; uint32_t* epoch_slot; size_t n_pad;       // byte map in use (own map, or a pool slot after a spill)
     uint32_t* tbl; uint32_t shift, cap_mask, limit, count; bool hashed;  // hash table (nullptr: byte map only)
     uint8_t* pool_vis; uint32_t* pool_epochs; uint32_t* pool_locks; uint32_t n_slots; int slot;   // spill pool
+    // q16: `tbl` holds 16-bit quotiented entries in buckets of 8 (one 16-byte load tests a key against a whole bucket)
+    bool q16; uint32_t q_rem_bits, q_bmask, q_kmask, q_inv;
 };
+
+// ---- q16: bucketed, quotiented visited table --------------------------------------------------------------------------
+// The u32 table above is open addressing with linear probing: one atomicCAS per probed slot, and a warp that tests the 64
+// neighbours of a hop waits for the LONGEST probe chain among them (3-4 dependent L2 / DRAM round trips at 28 % load; 33 % of
+// all stall samples of the d = 96 traversal in profiles/r2_k1_d96_single_ncu_summary.json). Here:
+//   * h = (slot * odd) mod 2^B is a bijection on the B-bit slot space; home bucket = top bits of h, remainder = the rest.
+//     A 16-bit entry (remainder << 2 | displacement) in bucket `home + displacement` identifies the slot exactly, so the
+//     table is exact at 2 bytes per entry: 32 KB per warp for 16384 entries — all resident warps together fit in L2.
+//   * one 16-byte load reads the 8 entries of a bucket: a visited neighbour is recognised in one round trip, a fresh one
+//     takes one more (a 16-bit atomicCAS on the first empty entry; a lost race retries on the next empty entry of the same
+//     snapshot, the racing keys are different neighbours). A key moves to the next bucket only when its bucket is full, at
+//     most 3 buckets away; beyond that (or above 62 % load) the traversal moves to a pooled byte map as the u32 table does.
+constexpr uint32_t Q_EMPTY = 0xFFFFu;
+constexpr uint32_t Q_HASH_MUL = 0x9E3779B1u;
+__device__ __forceinline__ uint4 q_bucket(const VisitedSet& v, uint32_t b) { return __ldcg(reinterpret_cast<const uint4*>(v.tbl) + b); }
+// found: `want` is one of the 8 entries; empties: bit i set = entry i is empty
+__device__ __forceinline__ void q_scan(const uint4 w, uint32_t want, bool& found, uint32_t& empties) {
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+    found = false;
+    empties = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = x[i] & 0xFFFFu, hi = x[i] >> 16;
+        found |= (lo == want) | (hi == want);
+        empties |= (lo == Q_EMPTY ? 1u : 0u) << (2 * i) | (hi == Q_EMPTY ? 1u : 0u) << (2 * i + 1);
+    }
+}
+// One key, one thread (entry point of a traversal; the hop loop uses the interleaved form in beam_level_regs).
+// Returns 1 fresh (now inserted), 0 already present, -1 no room within 3 buckets (caller spills).
+__device__ __forceinline__ int q_test_and_set(VisitedSet& v, uint32_t s) {
+    const uint32_t h = (s * Q_HASH_MUL) & v.q_kmask;
+    const uint32_t home = h >> v.q_rem_bits, rem = h & ((1u << v.q_rem_bits) - 1u);
+    unsigned short* t16 = reinterpret_cast<unsigned short*>(v.tbl);
+    for (uint32_t disp = 0; disp < 4; ++disp) {
+        const uint32_t b = (home + disp) & v.q_bmask, want = (rem << 2) | disp;
+        bool found;
+        uint32_t empties;
+        q_scan(q_bucket(v, b), want, found, empties);
+        if (found) return 0;
+        while (empties) {
+            const int e = __ffs((int)empties) - 1;
+            empties &= empties - 1;
+            const unsigned short old = atomicCAS(t16 + b * 8 + e, (unsigned short)Q_EMPTY, (unsigned short)want);
+            if (old == Q_EMPTY) return 1;
+            if (old == want) return 0;
+        }
+    }
+    return -1;
+}
+
+// warp: take a byte map from the pool and replay the table into it (the set stays exact for any query)
+__device__ __forceinline__ void visited_spill(VisitedSet& v, uint32_t warp_id, int lane) {
+    int slot = 0;
+    if (lane == 0) {
+        uint32_t i = warp_id % v.n_slots;
+        while (atomicCAS(v.pool_locks + i, 0u, 1u) != 0u) { i = (i + 1u) % v.n_slots; __nanosleep(64); }
+        __threadfence();
+        slot = (int)i;
+    }
+    slot = __shfl_sync(FULL, slot, 0);
+    v.slot = slot;
+    v.vis = v.pool_vis + (size_t)slot * v.n_pad;
+    v.epoch_slot = v.pool_epochs + slot;
+    v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
+    if (v.q16) {
+        for (uint32_t b = lane; b <= v.q_bmask; b += 32) {
+            const uint4 w = q_bucket(v, b);
+            const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t e = (i & 1) ? (x[i >> 1] >> 16) : (x[i >> 1] & 0xFFFFu);
+                if (e != Q_EMPTY) {
+                    const uint32_t home = (b - (e & 3u)) & v.q_bmask;
+                    const uint32_t h = (home << v.q_rem_bits) | (e >> 2);
+                    v.vis[(h * v.q_inv) & v.q_kmask] = v.tag;
+                }
+            }
+        }
+    } else {
+        for (uint32_t i = lane; i <= v.cap_mask; i += 32) {
+            const uint32_t s = __ldcg(v.tbl + i);
+            if (s != VIS_EMPTY) v.vis[s] = v.tag;
+        }
+    }
+    __syncwarp();
+    v.hashed = false;
+}
+
 __device__ __forceinline__ void visited_begin(VisitedSet& v, int lane) {
     v.count = 0;
     v.slot = -1;
     v.hashed = v.tbl != nullptr;
     if (v.hashed) {
         uint4* t4 = reinterpret_cast<uint4*>(v.tbl);
-        for (uint32_t i = lane; i <= v.cap_mask / 4; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+        const uint32_t n16 = v.q16 ? v.q_bmask + 1u : v.cap_mask / 4 + 1u;   // 16-byte units to clear
+        for (uint32_t i = lane; i < n16; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
         __syncwarp();
     } else {
         v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
     }
 }
-// per lane: true when `s` was not in the set (and now is). v.hashed is warp-uniform.
+// per lane: true when `s` was not in the set (and now is). v.hashed is warp-uniform. (u32 table / byte map; the q16 table
+// goes through q_test_and_set.)
 __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t s) {
     if (v.hashed) {
         uint32_t h = (s * 0x9E3779B1u) >> v.shift;
@@ -327,26 +419,7 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t s) 
 // warp: account for `added` new members; when the table passes its limit, move to a pooled byte map
 __device__ __forceinline__ void visited_added(VisitedSet& v, uint32_t added, uint32_t warp_id, int lane) {
     v.count += added;
-    if (v.hashed && v.count > v.limit) {
-        int slot = 0;
-        if (lane == 0) {
-            uint32_t i = warp_id % v.n_slots;
-            while (atomicCAS(v.pool_locks + i, 0u, 1u) != 0u) { i = (i + 1u) % v.n_slots; __nanosleep(64); }
-            __threadfence();
-            slot = (int)i;
-        }
-        slot = __shfl_sync(FULL, slot, 0);
-        v.slot = slot;
-        v.vis = v.pool_vis + (size_t)slot * v.n_pad;
-        v.epoch_slot = v.pool_epochs + slot;
-        v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
-        for (uint32_t i = lane; i <= v.cap_mask; i += 32) {
-            const uint32_t s = __ldcg(v.tbl + i);
-            if (s != VIS_EMPTY) v.vis[s] = v.tag;
-        }
-        __syncwarp();
-        v.hashed = false;
-    }
+    if (v.hashed && v.count > v.limit) visited_spill(v, warp_id, lane);
 }
 __device__ __forceinline__ void visited_end(VisitedSet& v, int lane) {
     if (v.slot >= 0) {
@@ -594,7 +667,8 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
     if (!SINGLE) next.clear();
     float radius = CUDART_INF_F;
     if (!SINGLE) next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(start_d, start, next_cap, lane);
-    if (lane == 0) visited_test_and_set(vs, start);
+    if (lane == 0) { if (vs.hashed && vs.q16) q_test_and_set(vs, start); else visited_test_and_set(vs, start); }   // empty table: cannot fail
+    __syncwarp();
     visited_added(vs, 1u, warp_id, lane);
     top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, !SINGLE>(start_d, start, ef, lane);
     if (top.size == ef) radius = top.dist_at(ef - 1);
@@ -665,7 +739,73 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                 sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
             }
             bool fr[NCH];
-            if (vs.hashed) {
+            if (vs.hashed && vs.q16) {
+                // bucketed table: all probes of the pass advance together, one bucket load (or one CAS) per round
+                unsigned short* t16 = reinterpret_cast<unsigned short*>(vs.tbl);
+                uint32_t bk[NCH], want[NCH], emp[NCH], disp[NCH];
+                bool act[NCH], need_load[NCH];
+                bool any = false, failed = false;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const uint32_t h = (sv[ch] * Q_HASH_MUL) & vs.q_kmask;
+                    bk[ch] = h >> vs.q_rem_bits;
+                    want[ch] = (h & ((1u << vs.q_rem_bits) - 1u)) << 2;
+                    disp[ch] = 0; emp[ch] = 0;
+                    act[ch] = sv[ch] != SENT; need_load[ch] = true; fr[ch] = false;
+                    any |= act[ch];
+                }
+                while (any) {
+                    uint4 w[NCH];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) if (act[ch] && need_load[ch]) w[ch] = q_bucket(vs, bk[ch] & vs.q_bmask);
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (act[ch] && need_load[ch]) {
+                            bool found;
+                            q_scan(w[ch], want[ch] | disp[ch], found, emp[ch]);
+                            need_load[ch] = false;
+                            if (found) act[ch] = false;
+                        }
+                    unsigned short old[NCH];
+                    int e[NCH];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        e[ch] = -1;
+                        if (act[ch] && emp[ch]) {
+                            e[ch] = __ffs((int)emp[ch]) - 1;
+                            emp[ch] &= emp[ch] - 1;
+                            old[ch] = atomicCAS(t16 + (bk[ch] & vs.q_bmask) * 8 + e[ch], (unsigned short)Q_EMPTY, (unsigned short)(want[ch] | disp[ch]));
+                        }
+                    }
+                    any = false;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (act[ch]) {
+                            if (e[ch] >= 0) {
+                                if (old[ch] == Q_EMPTY) { fr[ch] = true; act[ch] = false; }
+                                else if (old[ch] == (want[ch] | disp[ch])) act[ch] = false;   // cannot happen with duplicate-free rows; harmless
+                            }
+                            if (act[ch] && emp[ch] == 0) {      // bucket full (now): the key lives in, or goes to, the next one
+                                if (disp[ch] == 3) { failed = true; act[ch] = false; }
+                                else { disp[ch]++; bk[ch]++; need_load[ch] = true; }
+                            }
+                            any |= act[ch];
+                        }
+                }
+                if (__any_sync(FULL, failed)) {
+                    // no room within 3 buckets for some key: continue this query on a pooled byte map. Keys already claimed in
+                    // this pass are in the table and therefore in the replay; the ones that failed are decided on the map.
+                    visited_spill(vs, warp_id, lane);
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch)
+                        if (failed && sv[ch] != SENT && !fr[ch] && vs.vis[sv[ch]] != vs.tag) {
+                            // (a lane may reach here for a key that was found in the table; the map agrees, nothing to do)
+                            vs.vis[sv[ch]] = vs.tag;
+                            fr[ch] = true;
+                        }
+                    __syncwarp();
+                }
+            } else if (vs.hashed) {
                 uint32_t h[NCH];
                 bool act[NCH];
                 bool any = false;

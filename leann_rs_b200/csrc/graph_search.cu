@@ -48,6 +48,13 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
     vs.vis = p.vhash ? nullptr : p.visited + (size_t)warp_global * p.n_pad;
     vs.epoch_slot = p.vhash ? nullptr : p.epochs + warp_global;
     vs.tag = 0; vs.slot = -1;
+    vs.q16 = EPL > 0 && p.vhash != nullptr && p.vhash16 != 0;
+    vs.q_rem_bits = p.q_rem_bits; vs.q_kmask = p.q_key_bits >= 32 ? 0xFFFFFFFFu : ((1u << p.q_key_bits) - 1u); vs.q_inv = p.q_inv;
+    vs.q_bmask = p.vhash_cap / 8u - 1u;
+    if (vs.q16) {   // 2 bytes per entry
+        vs.tbl = p.vhash + (size_t)warp_global * (p.vhash_cap / 2u);
+        vs.limit = p.vhash_cap / 8u * 5u;
+    }
 
     for (;;) {
         uint32_t qi = 0;
@@ -300,6 +307,10 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
     throw Error(LEANN_ERR_INVALID_ARG, "dimension above 4096 is not supported");
 }
 }  // namespace
+
+bool graph_search_uses_reg_lists(const GraphView& g, const SearchParams& p) {
+    return reduction_lanes(g.d) == 8 && p.coop_ctas == 0 && use_reg_lists(p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr;
+}
 
 int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp) {
     SearchParams p{};

@@ -76,6 +76,12 @@ public:
     size_t dims() const { return dims_; }
     /// Merge concurrent single-query calls (the axum handlers of serve.rs) into batched launches.
     void set_coalescing(size_t max_batch, unsigned max_wait_us) { leann_cuda_set_coalescing(h_, max_batch, max_wait_us); }
+    /// Persist the parsed adjacency as `<index_path>.cuda-layout` so later loads stream it instead of parsing the node block.
+    void write_layout_cache(const std::string& index_path) const {
+        char err[1024];
+        check(leann_cuda_write_layout_cache(h_, index_path.c_str(), err, sizeof err), err);
+    }
+    bool layout_cache_used() const { return leann_cuda_layout_cache_used(h_) != 0; }
     const leann_cuda_index* handle() const { return h_; }
 
 protected:

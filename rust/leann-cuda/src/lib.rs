@@ -63,6 +63,7 @@ extern "C" {
                                 err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_metacols_free(cols: *mut LeannCudaMetacols);
     fn leann_cuda_set_coalescing(index: *mut LeannCudaIndex, max_batch: usize, max_wait_us: u32) -> c_int;
+    fn leann_cuda_write_layout_cache(index: *const LeannCudaIndex, base_path: *const c_char, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_vamana_build(vectors: *const c_float, vectors_on_device: c_int, n: usize, dims: usize, graph_degree: usize,
                                complexity: usize, alpha: c_float, metric: c_int, seed: u64, device: c_int,
                                out: *mut *mut LeannCudaIndex, err: *mut c_char, errlen: usize) -> c_int;
@@ -164,6 +165,16 @@ impl CudaSearcher {
     /// `max_wait_us > 0` lets a leader wait for company, `max_batch <= 1` turns it off.
     pub fn set_coalescing(&mut self, max_batch: usize, max_wait_us: u32) {
         unsafe { leann_cuda_set_coalescing(self.handle, max_batch, max_wait_us) };
+    }
+
+    /// Writes `<index_path>.cuda-layout` (the parsed adjacency, bound to the `.index` file by size, mtime and header hash):
+    /// the next `load` of the same index streams it instead of parsing usearch's node records (`leann build` would call this
+    /// once after `index.save`, src/backend/hnsw.rs:134).
+    pub fn write_layout_cache(&self, index_path: &Path) -> anyhow::Result<()> {
+        let base = CString::new(index_path.to_string_lossy().as_bytes())?;
+        let mut err = [0u8; 1024];
+        let rc = unsafe { leann_cuda_write_layout_cache(self.handle, base.as_ptr(), err.as_mut_ptr() as *mut c_char, err.len()) };
+        check(rc, &err)
     }
 
     /// Exact scan over raw embeddings: the scoring + sort + take(k) of `RecomputeSearcher::search`
