@@ -298,7 +298,7 @@ struct VisitedSet {
     uint32_t* tbl; uint32_t shift, cap_mask, limit, count; bool hashed;  // hash table (nullptr: byte map only)
     uint8_t* pool_vis; uint32_t* pool_epochs; uint32_t* pool_locks; uint32_t n_slots; int slot;   // spill pool
     // q16: `tbl` holds 16-bit quotiented entries in buckets of 8 (one 16-byte load tests a key against a whole bucket)
-    bool q16; uint32_t q_rem_bits, q_bmask, q_kmask, q_inv;
+    bool q16 = false; uint32_t q_rem_bits = 0, q_bmask = 0, q_kmask = 0, q_inv = 0;
 };
 
 // ---- q16: bucketed, quotiented visited table --------------------------------------------------------------------------
@@ -657,7 +657,7 @@ struct RegList {
 // two-list form bit for bit (the randomised parity tests include duplicate rows); the queue can no longer overflow, so the
 // `dropped` counter stays 0.
 constexpr uint32_t XBIT = 0x80000000u;
-template <int LPV, int VPL, int U, int EPL, bool SINGLE>
+template <int LPV, int VPL, int U, int EPL, bool SINGLE, bool Q16>
 __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL], WarpLists& w,
                                                int ef, int next_cap, int nonstrict, VisitedSet& vs, uint32_t warp_id,
                                                uint32_t start, float start_d, Counters& c, int lane,
@@ -667,7 +667,7 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
     if (!SINGLE) next.clear();
     float radius = CUDART_INF_F;
     if (!SINGLE) next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(start_d, start, next_cap, lane);
-    if (lane == 0) { if (vs.hashed && vs.q16) q_test_and_set(vs, start); else visited_test_and_set(vs, start); }   // empty table: cannot fail
+    if (lane == 0) { if (Q16 && vs.hashed) q_test_and_set(vs, start); else visited_test_and_set(vs, start); }   // empty table: cannot fail
     __syncwarp();
     visited_added(vs, 1u, warp_id, lane);
     top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, !SINGLE>(start_d, start, ef, lane);
@@ -739,7 +739,7 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                 sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
             }
             bool fr[NCH];
-            if (vs.hashed && vs.q16) {
+            if (Q16 && vs.hashed) {
                 // bucketed table: all probes of the pass advance together, one bucket load (or one CAS) per round
                 unsigned short* t16 = reinterpret_cast<unsigned short*>(vs.tbl);
                 uint32_t bk[NCH], want[NCH], emp[NCH], disp[NCH];
@@ -805,7 +805,7 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                         }
                     __syncwarp();
                 }
-            } else if (vs.hashed) {
+            } else if (!Q16 && vs.hashed) {
                 uint32_t h[NCH];
                 bool act[NCH];
                 bool any = false;

@@ -17,7 +17,7 @@ namespace leann {
 
 // EPL > 0: `top` / `next` live in registers (RegList<EPL>, graph_device.cuh); the host picks that instantiation for short
 // rows when max(ef, queue capacity) <= 32 * EPL and no mask is set. Shared memory then holds only the staging row.
-template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE = false>
+template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE = false, bool Q16 = false>
 __global__ void __launch_bounds__(128, MINB)
 graph_search_kernel(const GraphView g, const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -48,7 +48,7 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
     vs.vis = p.vhash ? nullptr : p.visited + (size_t)warp_global * p.n_pad;
     vs.epoch_slot = p.vhash ? nullptr : p.epochs + warp_global;
     vs.tag = 0; vs.slot = -1;
-    vs.q16 = EPL > 0 && p.vhash != nullptr && p.vhash16 != 0;
+    vs.q16 = Q16 && p.vhash != nullptr;
     vs.q_rem_bits = p.q_rem_bits; vs.q_kmask = p.q_key_bits >= 32 ? 0xFFFFFFFFu : ((1u << p.q_key_bits) - 1u); vs.q_inv = p.q_inv;
     vs.q_bmask = p.vhash_cap / 8u - 1u;
     if (vs.q16) {   // 2 bytes per entry
@@ -80,7 +80,7 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
         int cnt;
         if constexpr (EPL > 0) {
-            cnt = beam_level_regs<LPV, VPL, U, EPL, SINGLE>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
+            cnt = beam_level_regs<LPV, VPL, U, EPL, SINGLE, Q16>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
                                                     (uint32_t)warp_global, cur, cur_d, c, lane, p.k,
                                                     p.out_keys + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k);
             visited_end(vs, lane);
@@ -227,19 +227,28 @@ inline bool use_single_list(const GraphView& g, const SearchParams& p) {
            getenv("LEANN_CUDA_DISABLE_SINGLE_LIST") == nullptr;
 }
 
-template <int LPV, int VPL, int U, int MINB, int EPL = 0, bool SINGLE = false>
+template <int LPV, int VPL, int U, int MINB, int EPL = 0, bool SINGLE = false, bool Q16 = false>
+int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op);
+
+// short rows: register-list instantiation (one or two lists, u32 / byte-map or q16 visited set)
+template <int LPV, int VPL, int U, int MINB>
+int launch_reg(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
+    const bool q16 = p.vhash != nullptr && p.vhash16 != 0;
+    if (use_single_list(g, p))
+        return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false>(g, p, stream, op);
+    return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, false, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, false, false>(g, p, stream, op);
+}
+
+template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE, bool Q16>
 int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
     if constexpr (EPL == 0 && LPV < 32) {
         // short rows: the register-list instantiation when the lists fit (small batches keep the cooperative kernel)
         const bool off = getenv("LEANN_CUDA_DISABLE_REG_LISTS") != nullptr;   // A/B switch for benchmarks
-        if (!off && p.coop_ctas == 0 && use_reg_lists(p)) {
-            if (use_single_list(g, p)) return launch_t<LPV, VPL, U, MINB, REG_EPL, true>(g, p, stream, op);
-            return launch_t<LPV, VPL, U, MINB, REG_EPL>(g, p, stream, op);
-        }
+        if (!off && p.coop_ctas == 0 && use_reg_lists(p)) return launch_reg<LPV, VPL, U, MINB>(g, p, stream, op);
     }
     const int warps_per_block = 4;
     size_t smem = (EPL > 0 ? (size_t)MAX_DEG * 8 : graph_search_smem_per_warp(p.ef, p.next_capp)) * warps_per_block;
-    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL, SINGLE>;
+    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL, SINGLE, Q16>;
     if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (op == 1) {
         int blocks_per_sm = 0;
@@ -278,18 +287,18 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
             const char* tune = getenv("LEANN_K1_TUNE");
             if (tune && p.coop_ctas == 0 && use_reg_lists(p)) {
                 const std::string t(tune);
-                if (t == "4,5") return use_single_list(g, p) ? launch_t<8, 3, 4, 5, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 4, 5, REG_EPL>(g, p, stream, op);
-                if (t == "2,6") return use_single_list(g, p) ? launch_t<8, 3, 2, 6, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 6, REG_EPL>(g, p, stream, op);
-                if (t == "3,6") return use_single_list(g, p) ? launch_t<8, 3, 3, 6, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 3, 6, REG_EPL>(g, p, stream, op);
-                if (t == "3,5") return use_single_list(g, p) ? launch_t<8, 3, 3, 5, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 3, 5, REG_EPL>(g, p, stream, op);
-                if (t == "2,8") return use_single_list(g, p) ? launch_t<8, 3, 2, 8, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 8, REG_EPL>(g, p, stream, op);
-                if (t == "2,7") return use_single_list(g, p) ? launch_t<8, 3, 2, 7, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 2, 7, REG_EPL>(g, p, stream, op);
-                if (t == "4,4") return use_single_list(g, p) ? launch_t<8, 3, 4, 4, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 4, 4, REG_EPL>(g, p, stream, op);
+                if (t == "4,5") return launch_reg<8, 3, 4, 5>(g, p, stream, op);
+                if (t == "2,6") return launch_reg<8, 3, 2, 6>(g, p, stream, op);
+                if (t == "3,6") return launch_reg<8, 3, 3, 6>(g, p, stream, op);
+                if (t == "3,5") return launch_reg<8, 3, 3, 5>(g, p, stream, op);
+                if (t == "2,8") return launch_reg<8, 3, 2, 8>(g, p, stream, op);
+                if (t == "2,7") return launch_reg<8, 3, 2, 7>(g, p, stream, op);
+                if (t == "4,4") return launch_reg<8, 3, 4, 4>(g, p, stream, op);
             }
-            // d <= 96. Register lists (r2): <U = 3, 6 CTAs per SM> measured best of {4,6; 4,5; 3,6; 3,5; 2,6; 2,7; 2,8; 4,4}
+            // d <= 96. Register lists (r2): <U = 2, 6 CTAs per SM> measured best of {4,6; 4,5; 3,6; 3,5; 2,6; 2,7; 2,8; 4,4}
             // on the 12.5M x 96 Vamana shard (profiles/r2_k1_tune*.log); shared-memory lists (ef > 128, masks): <4, 6>.
             if (p.coop_ctas == 0 && use_reg_lists(p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr)
-                return use_single_list(g, p) ? launch_t<8, 3, 3, 6, REG_EPL, true>(g, p, stream, op) : launch_t<8, 3, 3, 6, REG_EPL>(g, p, stream, op);
+                return launch_reg<8, 3, 2, 6>(g, p, stream, op);
             return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
         }
         if (vpl <= 4) return launch_t<8, 4, 2, 6>(g, p, stream, op);   // d = 128: +10-15 % over <8,4,4,4>
