@@ -1,5 +1,10 @@
-"""A/B harness for K1 on short rows (C4 shard: Vamana n x 96 L2, R = 64): one index, several kernel instantiations selected
-through LEANN_K1_TUNE / LEANN_CUDA_DISABLE_REG_LISTS, results compared bit for bit with the shared-memory-list kernel."""
+"""A/B harness for K1 on short rows (C4 shard: Vamana n x 96 L2, R = 64): one index, the round-2 changes switched off one by
+one through the library's A/B environment switches, results compared bit for bit with the round-1 kernel.
+  base     LEANN_CUDA_DISABLE_REG_LISTS      shared-memory top / next lists (round 1)
+  reg2     LEANN_CUDA_DISABLE_SINGLE_LIST    register lists, two lists, u32 / byte-map visited set
+  single   LEANN_CUDA_DISABLE_Q16            one list with an expanded bit, u32 hash / byte maps
+  default                                    + bucketed 16-bit quotiented visited tables
+(The (unroll, CTAs per SM) sweeps of profiles/r2_k1_tune*.log were made with a temporary LEANN_K1_TUNE switch.)"""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +13,7 @@ from benchmarks import secondary as S2
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=12_500_000); ap.add_argument("--d", type=int, default=96)
-ap.add_argument("--nq", type=int, default=10_000); ap.add_argument("--variants", default="base,4,6;4,5;3,6;3,5;2,6;2,7;2,8;4,4")
+ap.add_argument("--nq", type=int, default=10_000); ap.add_argument("--variants", default="base;reg2;single;default")
 ap.add_argument("--efs", default="50,100"); ap.add_argument("--steps", type=int, default=5)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -24,11 +29,12 @@ info = idx.info()
 rows = []
 ref = {}
 variants = [v for v in a.variants.replace("base,", "base;").split(";") if v]
+SW = {"base": ["LEANN_CUDA_DISABLE_REG_LISTS"], "reg2": ["LEANN_CUDA_DISABLE_SINGLE_LIST", "LEANN_CUDA_DISABLE_Q16"], "single": ["LEANN_CUDA_DISABLE_Q16"], "default": []}
 for v in variants:
-    if v == "base":
-        os.environ["LEANN_CUDA_DISABLE_REG_LISTS"] = "1"; os.environ.pop("LEANN_K1_TUNE", None)
-    else:
-        os.environ.pop("LEANN_CUDA_DISABLE_REG_LISTS", None); os.environ["LEANN_K1_TUNE"] = v
+    for k in ("LEANN_CUDA_DISABLE_REG_LISTS", "LEANN_CUDA_DISABLE_SINGLE_LIST", "LEANN_CUDA_DISABLE_Q16"):
+        os.environ.pop(k, None)
+    for k in SW[v]:
+        os.environ[k] = "1"
     for ef in [int(e) for e in a.efs.split(",")]:
         st = torch.zeros((a.nq, 4), dtype=torch.int64, device=dev)
         keys, dists, _ = idx.search_device(q, 10, ef, stats=st)

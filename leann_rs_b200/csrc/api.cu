@@ -235,7 +235,7 @@ static_assert(Q_HASH_INV * 0x9E3779B1u == 1u, "hash multiplier inverse");
 // q16 table for the register-list kernels: `slots` 16-bit entries per warp in buckets of 8. Sized for <= ~33 % load at
 // the expected 0.7 * ef * degree visited nodes; the slot space must split into bucket bits + at most 14 remainder bits.
 bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* rem_bits, uint32_t* key_bits) {
-    static const bool off = getenv("LEANN_CUDA_DISABLE_Q16") != nullptr;   // A/B switch for benchmarks
+    const bool off = getenv("LEANN_CUDA_DISABLE_Q16") != nullptr;   // A/B switch for benchmarks (read per launch)
     const SearchWorkspace& ws = ix->ws;
     if (off || ix->vhash_mode == 1 || ws.n_warps <= 0 || ix->n < 2) return false;
     if (!ws.large_mode && ix->vhash_mode == 0 && (size_t)ws.n_warps * ws.n_pad <= ((size_t)64 << 20)) return false;   // byte maps already live in L2

@@ -9,7 +9,6 @@
 //     n_dist * d4*16  +  n_hops0 * deg0*4  +  n_hops_upper * degU*4      
 // all three counted by the kernel itself (out_stats) and by the oracle.
 #include <cstdlib>
-#include <string>
 
 #include "graph_device.cuh"
 
@@ -283,18 +282,6 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
         uint32_t vpl = (d4 + 7) / 8;
         if (vpl <= 2) return launch_t<8, 2, 4, 6>(g, p, stream, op);
         if (vpl <= 3) {
-            // TUNING (temporary): LEANN_K1_TUNE=U,MINB picks a register-list instantiation
-            const char* tune = getenv("LEANN_K1_TUNE");
-            if (tune && p.coop_ctas == 0 && use_reg_lists(p)) {
-                const std::string t(tune);
-                if (t == "4,5") return launch_reg<8, 3, 4, 5>(g, p, stream, op);
-                if (t == "2,6") return launch_reg<8, 3, 2, 6>(g, p, stream, op);
-                if (t == "3,6") return launch_reg<8, 3, 3, 6>(g, p, stream, op);
-                if (t == "3,5") return launch_reg<8, 3, 3, 5>(g, p, stream, op);
-                if (t == "2,8") return launch_reg<8, 3, 2, 8>(g, p, stream, op);
-                if (t == "2,7") return launch_reg<8, 3, 2, 7>(g, p, stream, op);
-                if (t == "4,4") return launch_reg<8, 3, 4, 4>(g, p, stream, op);
-            }
             // d <= 96. Register lists (r2): <U = 2, 6 CTAs per SM> measured best of {4,6; 4,5; 3,6; 3,5; 2,6; 2,7; 2,8; 4,4}
             // on the 12.5M x 96 Vamana shard (profiles/r2_k1_tune*.log); shared-memory lists (ef > 128, masks): <4, 6>.
             if (p.coop_ctas == 0 && use_reg_lists(p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr)
