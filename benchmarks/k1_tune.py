@@ -1,7 +1,6 @@
 """A/B harness for K1 on short rows (C4 shard: Vamana n x 96 L2, R = 64): one index, the round-2 changes switched off one by
 one through the library's A/B environment switches, results compared bit for bit with the round-1 kernel.
   base     LEANN_CUDA_DISABLE_REG_LISTS      shared-memory top / next lists (round 1)
-  reg2     LEANN_CUDA_DISABLE_SINGLE_LIST    register lists, two lists, u32 / byte-map visited set
   single   LEANN_CUDA_DISABLE_Q16            one list with an expanded bit, u32 hash / byte maps
   default                                    + bucketed 16-bit quotiented visited tables
 (The (unroll, CTAs per SM) sweeps of profiles/r2_k1_tune*.log were made with a temporary LEANN_K1_TUNE switch.)"""
@@ -13,7 +12,7 @@ from benchmarks import secondary as S2
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=12_500_000); ap.add_argument("--d", type=int, default=96)
-ap.add_argument("--nq", type=int, default=10_000); ap.add_argument("--variants", default="base;reg2;single;default")
+ap.add_argument("--nq", type=int, default=10_000); ap.add_argument("--variants", default="base;single;default")
 ap.add_argument("--efs", default="50,100"); ap.add_argument("--steps", type=int, default=5)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -29,7 +28,7 @@ info = idx.info()
 rows = []
 ref = {}
 variants = [v for v in a.variants.replace("base,", "base;").split(";") if v]
-SW = {"base": ["LEANN_CUDA_DISABLE_REG_LISTS"], "reg2": ["LEANN_CUDA_DISABLE_SINGLE_LIST", "LEANN_CUDA_DISABLE_Q16"], "single": ["LEANN_CUDA_DISABLE_Q16"], "default": []}
+SW = {"base": ["LEANN_CUDA_DISABLE_REG_LISTS"], "single": ["LEANN_CUDA_DISABLE_Q16"], "default": []}
 for v in variants:
     for k in ("LEANN_CUDA_DISABLE_REG_LISTS", "LEANN_CUDA_DISABLE_SINGLE_LIST", "LEANN_CUDA_DISABLE_Q16"):
         os.environ.pop(k, None)

@@ -17,7 +17,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libleann_cuda.so")
+LIB_PATH = os.environ.get("LEANN_CUDA_LIB") or os.path.join(_HERE, "libleann_cuda.so")   # LEANN_CUDA_LIB: A/B builds of the same ABI
 
 OK = 0
 BACKEND_HNSW, BACKEND_VAMANA, BACKEND_FLAT = 0, 1, 2

@@ -21,9 +21,22 @@ namespace leann {
 
 namespace {
 
-constexpr int BM_THREADS = 256;
-constexpr int BM_TILE = 8192;     // documents per shared-memory accumulator tile (32 KB of f32)
-constexpr int BM_CAP = 2048;      // candidate keys held in shared memory between prunes
+// Tile geometry of the query kernel; overridable at compile time for A/B builds (benchmarks/k3_variants.sh).
+#ifndef LEANN_BM_THREADS
+#define LEANN_BM_THREADS 256
+#endif
+#ifndef LEANN_BM_TILE
+#define LEANN_BM_TILE 8192
+#endif
+#ifndef LEANN_BM_CAP
+#define LEANN_BM_CAP 2048
+#endif
+#ifndef LEANN_BM_MINB
+#define LEANN_BM_MINB 3
+#endif
+constexpr int BM_THREADS = LEANN_BM_THREADS;
+constexpr int BM_TILE = LEANN_BM_TILE;     // documents per shared-memory accumulator tile (32 KB of f32)
+constexpr int BM_CAP = LEANN_BM_CAP;       // candidate keys held in shared memory between prunes
 constexpr int BM_BOUNDS = 2048;   // entries of the (token, tile boundary) -> posting offset table (16 KB)
 constexpr int BM_SPARSE = 1024;   // tiles holding fewer postings are collected by re-walking them instead of a full scan
 constexpr size_t BM_SMEM = (size_t)BM_TILE * 4 + (size_t)BM_CAP * 8 + (size_t)BM_BOUNDS * 8;
@@ -66,7 +79,7 @@ __device__ void block_sort_cap(unsigned long long* keys) {
 // of every posting list; the slice boundaries come from one parallel binary search per query), then the tile is
 // scanned for positives, which feed the running top-K, the positive count and the min/max of hybrid_rerank.
 // Every posting is read once, coalesced; no global read-modify-write.
-__global__ void __launch_bounds__(BM_THREADS, 3)
+__global__ void __launch_bounds__(BM_THREADS, LEANN_BM_MINB)
 bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32_t* __restrict__ qtok_term,
                   uint32_t nq, uint32_t K, const uint64_t* __restrict__ cand_idx,
                   const uint32_t* __restrict__ cand_cnt, uint32_t fk, float* __restrict__ cand_bm,
@@ -417,6 +430,8 @@ void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* 
     }
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
+
+int bm25_query_ctas_per_sm() { return LEANN_BM_MINB; }
 
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
                        int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,

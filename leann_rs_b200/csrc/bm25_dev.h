@@ -15,6 +15,7 @@ struct Bm25Dev {
 void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
                        cudaStream_t s);
 size_t bm25_max_query_tokens();   // longest query (known tokens, duplicates included) the query kernel takes
+int bm25_query_ctas_per_sm();   // resident CTAs per SM the query kernel is built for (persistent pool size)
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
                        int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
                        float* cand_bm, uint64_t* top_idx, float* top_score, uint32_t* top_cnt, float* bmax, float* bmin,

@@ -229,13 +229,13 @@ inline bool use_single_list(const GraphView& g, const SearchParams& p) {
 template <int LPV, int VPL, int U, int MINB, int EPL = 0, bool SINGLE = false, bool Q16 = false>
 int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op);
 
-// short rows: register-list instantiation (one or two lists, u32 / byte-map or q16 visited set)
+// short rows, diskann-rs stop rule: register-list instantiation (one list with an expanded bit; u32 / byte-map or q16
+// visited set). The two-list register form (usearch stop rule) exists in graph_device.cuh but is not instantiated: on 1M x 128 /
+// 1M x 256 HNSW indexes it measured 3-9 % slower than the shared-memory lists (two sorted inserts per accepted neighbour).
 template <int LPV, int VPL, int U, int MINB>
 int launch_reg(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
     const bool q16 = p.vhash != nullptr && p.vhash16 != 0;
-    if (use_single_list(g, p))
-        return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false>(g, p, stream, op);
-    return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, false, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, false, false>(g, p, stream, op);
+    return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false>(g, p, stream, op);
 }
 
 template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE, bool Q16>
@@ -243,7 +243,7 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
     if constexpr (EPL == 0 && LPV < 32) {
         // short rows: the register-list instantiation when the lists fit (small batches keep the cooperative kernel)
         const bool off = getenv("LEANN_CUDA_DISABLE_REG_LISTS") != nullptr;   // A/B switch for benchmarks
-        if (!off && p.coop_ctas == 0 && use_reg_lists(p)) return launch_reg<LPV, VPL, U, MINB>(g, p, stream, op);
+        if (!off && p.coop_ctas == 0 && use_reg_lists(p) && use_single_list(g, p)) return launch_reg<LPV, VPL, U, MINB>(g, p, stream, op);
     }
     const int warps_per_block = 4;
     size_t smem = (EPL > 0 ? (size_t)MAX_DEG * 8 : graph_search_smem_per_warp(p.ef, p.next_capp)) * warps_per_block;
@@ -284,7 +284,7 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
         if (vpl <= 3) {
             // d <= 96. Register lists (r2): <U = 2, 6 CTAs per SM> measured best of {4,6; 4,5; 3,6; 3,5; 2,6; 2,7; 2,8; 4,4}
             // on the 12.5M x 96 Vamana shard (profiles/r2_k1_tune*.log); shared-memory lists (ef > 128, masks): <4, 6>.
-            if (p.coop_ctas == 0 && use_reg_lists(p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr)
+            if (p.coop_ctas == 0 && use_reg_lists(p) && use_single_list(g, p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr)
                 return launch_reg<8, 3, 2, 6>(g, p, stream, op);
             return launch_t<8, 3, 4, 6>(g, p, stream, op);   // d = 96: 6 CTAs per SM measured 6 % faster than 5, deeper unrolls slower
         }
@@ -305,7 +305,8 @@ int dispatch_search(const GraphView& g, const SearchParams& p, cudaStream_t stre
 }  // namespace
 
 bool graph_search_uses_reg_lists(const GraphView& g, const SearchParams& p) {
-    return reduction_lanes(g.d) == 8 && p.coop_ctas == 0 && use_reg_lists(p) && getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr;
+    return reduction_lanes(g.d) == 8 && p.coop_ctas == 0 && use_reg_lists(p) && use_single_list(g, p) &&
+           getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr;
 }
 
 int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp) {

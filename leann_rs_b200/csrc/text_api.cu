@@ -115,7 +115,7 @@ void bm25_ensure_ws(const leann_cuda_bm25* b, size_t nq) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
     (void)nq;
-    b->n_ctas = sms * 3;   // persistent pool of the query kernel: 3 CTAs of 64 KB shared memory per SM
+    b->n_ctas = sms * bm25_query_ctas_per_sm();   // persistent pool of the query kernel: 3 CTAs of 64 KB shared memory per SM
     if (b->d_acc) return;
     size_t per = std::max<size_t>(b->host.num_docs, 1) * 4;
     LEANN_CUDA_CHECK(cudaMalloc(&b->d_acc, per));
