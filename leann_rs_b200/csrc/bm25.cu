@@ -34,6 +34,9 @@ namespace {
 #ifndef LEANN_BM_MINB
 #define LEANN_BM_MINB 3
 #endif
+#ifndef LEANN_BM_PIPE
+#define LEANN_BM_PIPE 0   // software-pipelined accumulation: measured 33.4 ms vs 28.8 ms per 10k queries (profiles/r2_k3_variants.json): off
+#endif
 constexpr int BM_THREADS = LEANN_BM_THREADS;
 constexpr int BM_TILE = LEANN_BM_TILE;     // documents per shared-memory accumulator tile (32 KB of f32)
 constexpr int BM_CAP = LEANN_BM_CAP;       // candidate keys held in shared memory between prunes
@@ -151,6 +154,58 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                 const uint32_t base = (sb0 + tile) * BM_TILE;
                 // ---- accumulate, tokens in query order (duplicates counted again, bm25.rs:81) ----
                 uint64_t in_tile = 0;
+#if LEANN_BM_PIPE
+                // (A/B variant, off by default: slower than the plain loop below on B200 — the predicated loads and the register
+                // hand-over cost more than the overlapped latency buys at 24 resident warps per SM.)
+                // Software pipeline over the (token, chunk) sequence of this tile: the 16 loads of chunk c + 1 are issued before the
+                // shared-memory read-modify-writes of chunk c and before the barrier that separates two tokens, so that the load
+                // latency of every slice (and the barrier) overlaps the accumulation of the previous one. The sequence is the same
+                // for all threads of the block (slice bounds are block-uniform); inside one token every posting is a distinct
+                // document, so only the token boundary needs the barrier.
+                {
+                    constexpr uint32_t CH = 8u * BM_THREADS;
+                    uint32_t t = 0;
+                    auto slice = [&](uint32_t tt, const uint32_t*& pd, const float*& ps) -> uint32_t {
+                        const uint64_t lo = bounds[tt * (sbt + 1) + tile], hi = bounds[tt * (sbt + 1) + tile + 1];
+                        pd = b.post_doc + lo; ps = b.post_score + lo;
+                        return hi > lo ? (uint32_t)(hi - lo) : 0u;
+                    };
+                    auto next_token = [&](uint32_t tt, const uint32_t*& pd, const float*& ps, uint32_t& len) {   // first non-empty slice at or after tt
+                        len = 0;
+                        while (tt < T && (len = slice(tt, pd, ps)) == 0) ++tt;
+                        return tt;
+                    };
+                    auto load = [&](const uint32_t* pd, const float* ps, uint32_t len, uint32_t i0, uint32_t (&d)[8], float (&sc)[8]) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t i = i0 + tid + (uint32_t)u * BM_THREADS;
+                            const bool ok = i < len;
+                            d[u] = ok ? __ldg(pd + i) : 0xFFFFFFFFu;
+                            sc[u] = ok ? __ldg(ps + i) : 0.0f;
+                        }
+                    };
+                    const uint32_t* pd; const float* ps; uint32_t len, i0 = 0;
+                    t = next_token(0, pd, ps, len);
+                    uint32_t dc[8]; float scc[8];
+                    if (t < T) load(pd, ps, len, 0, dc, scc);
+                    while (t < T) {
+                        if (i0 == 0) in_tile += len;
+                        // where is the next chunk?
+                        uint32_t t2 = t, i2 = i0 + CH, len2 = len;
+                        const uint32_t* pd2 = pd; const float* ps2 = ps;
+                        if (i2 >= len) { t2 = next_token(t + 1, pd2, ps2, len2); i2 = 0; }
+                        uint32_t dn[8]; float scn[8];
+                        if (t2 < T) load(pd2, ps2, len2, i2, dn, scn);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (dc[u] != 0xFFFFFFFFu) acc[dc[u] - base] = __fadd_rn(acc[dc[u] - base], scc[u]);
+                        if (t2 != t) __syncthreads();
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { dc[u] = dn[u]; scc[u] = scn[u]; }
+                        t = t2; i0 = i2; len = len2; pd = pd2; ps = ps2;
+                    }
+                }
+#else
                 for (uint32_t t = 0; t < T; ++t) {
                     const uint64_t lo = bounds[t * (sbt + 1) + tile], hi = bounds[t * (sbt + 1) + tile + 1];
                     if (lo >= hi) continue;
@@ -182,6 +237,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     }
                     __syncthreads();
                 }
+#endif
                 if (in_tile == 0) continue;
                 // ---- BM25 score of the vector candidates that live in this tile (bm25.rs:160) ----
                 for (uint32_t j = tid; j < nc; j += BM_THREADS) {
