@@ -198,6 +198,7 @@ int leann_cuda_shards_join(leann_cuda_index* local, int take_ownership, const un
 /* BackendSearcher::len over all shards / number of shards. */
 size_t leann_cuda_shards_len(const leann_cuda_shards* shards);
 size_t leann_cuda_shards_count(const leann_cuda_shards* shards);
+size_t leann_cuda_shards_dims(const leann_cuda_shards* shards);
 /* info[0] = shards, [1] = exchange in use (0 none, 1 NCCL all_gather, 2 peer-memory merge),
  * [2] = exchange steps so far, [3] = bytes moved between GPUs by them. */
 int leann_cuda_shards_info(const leann_cuda_shards* shards, uint64_t* info4);
@@ -211,6 +212,16 @@ int leann_cuda_shards_search(leann_cuda_shards* shards, const float* queries, si
 int leann_cuda_shards_search_device(leann_cuda_shards* shards, const float* d_queries, size_t nq, size_t k, size_t ef,
                                     const uint64_t* d_mask_bits, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
                                     void* cuda_stream, char* err, size_t errlen);
+/* IndexSearcher::search_with_options (index/searcher.rs:123-210) over document-range shards, one process per GPU
+ * (a handle from leann_cuda_shards_join): vector candidates from the sharded backend, BM25 from this rank's postings
+ * (leann_cuda_bm25_build_sharded, documents = the rows of this rank's vector shard), ONE ncclAllGather of the per-rank
+ * block (BM25 top list, scores of the candidates the shard owns, max / min of its dense score vector), then merge,
+ * fusion and post-filter walk on the device. Every rank issues the same call and receives the same answer, which is
+ * bit-identical to leann_cuda_hybrid_search over the unsharded index. filter_mask: global passage bits (nullable). */
+int leann_cuda_shards_hybrid_search(leann_cuda_shards* shards, const leann_cuda_bm25* bm25_shard, const float* queries,
+                                    const char* const* query_texts, const size_t* query_text_bytes, size_t nq, size_t top_k,
+                                    size_t ef, int hybrid, float alpha, const uint64_t* filter_mask, size_t mask_bits,
+                                    uint64_t* idx, float* scores, uint32_t* counts, char* err, size_t errlen);
 void leann_cuda_shards_close(leann_cuda_shards* shards);
 
 /* ---------------------------------------------------------------------------------------------

@@ -78,6 +78,8 @@ def lib():
         "leann_cuda_shards_info": (C.c_int, [vp, u64p]),
         "leann_cuda_shards_search": (C.c_int, [vp, vp, sz, sz, sz, pp, vp, vp, vp, cp, sz]),
         "leann_cuda_shards_search_device": (C.c_int, [vp, vp, sz, sz, sz, vp, vp, vp, vp, vp, cp, sz]),
+        "leann_cuda_shards_dims": (sz, [vp]),
+        "leann_cuda_shards_hybrid_search": (C.c_int, [vp, vp, vp, cpp, szp, sz, sz, sz, C.c_int, C.c_float, vp, sz, vp, vp, vp, cp, sz]),
         "leann_cuda_shards_close": (None, [vp]),
         "leann_cuda_set_visited_hash": (C.c_int, [vp, sz]),
         "leann_cuda_set_coalescing": (C.c_int, [vp, sz, C.c_uint]),
@@ -503,6 +505,25 @@ class ShardedBackend:
         _check(lib().leann_cuda_shards_search(self._h, _np_ptr(q), nq, top_k, ef, mp, _np_ptr(keys), _np_ptr(dists),
                                               _np_ptr(counts), e, 1024), e)
         return keys, dists, counts
+
+    def hybrid_search(self, bm25_shard, queries, query_texts, top_k: int, ef: int, hybrid: bool, alpha: float, filter_mask=None):
+        """search_with_options (index/searcher.rs:123-210) over document-range shards, one process per GPU: vector candidates
+        from this sharded backend, BM25 from `bm25_shard` (this rank's documents, corpus-wide statistics), one all_gather,
+        fusion on the device. Host arrays in/out; every rank gets the same answer."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        idx = np.empty((nq, top_k), dtype=np.uint64)
+        sc = np.empty((nq, top_k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        arr = lens = None
+        if query_texts is not None:
+            _, arr, lens = _strs(query_texts)
+        m = None if filter_mask is None else np.ascontiguousarray(filter_mask, dtype=np.uint64)
+        e = _err()
+        _check(lib().leann_cuda_shards_hybrid_search(self._h, None if bm25_shard is None else bm25_shard._h, _np_ptr(q), arr, lens, nq, top_k, ef,
+                                                     1 if hybrid else 0, C.c_float(alpha), None if m is None else _np_ptr(m),
+                                                     0 if m is None else m.shape[0] * 64, _np_ptr(idx), _np_ptr(sc), _np_ptr(cnt), e, 1024), e)
+        return idx, sc, cnt
 
     def search_device(self, queries, top_k: int, ef: int, mask=None, out=None, stream=None):
         """torch CUDA tensors on the local shard's device; search + exchange + merge on torch's current stream."""

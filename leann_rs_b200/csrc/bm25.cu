@@ -13,6 +13,8 @@
 // computed once at build time (host, same f32 operation order) and the kernels only stream and add.
 // Bound: HBM (postings stream). Algorithmic bytes per query = sum_t df_t * 8.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math_constants.h>
 
 #include "bm25_dev.h"
@@ -526,6 +528,49 @@ void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32
     if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(hybrid_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hybrid_fuse_kernel<<<nq, 128, smem, s>>>(vkeys, vdists, vcnt, fk, cand_bm, bm_idx, bm_score, bm_cnt, bm_k, bmax, bmin, hybrid,
                                              alpha, mask, mask_bits, top_k, out_idx, out_score, out_cnt, nq, cap);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+namespace {
+__global__ void localize_kernel(const uint64_t* __restrict__ g, uint64_t off, uint64_t n_local, size_t count, uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t v = g[i];
+    out[i] = (v >= off && v - off < n_local) ? v - off : ~0ull;
+}
+// Block of rank r (sharded hybrid exchange): [nq][fk] u64 top ids | [nq][fk] f32 top scores | [nq][fk] f32 candidate scores |
+// [nq] f32 max | [nq] f32 min. The candidate scores are summed over ranks in rank order (only the owner's is non-zero: exact).
+__global__ void shard_reduce_kernel(const unsigned char* __restrict__ gathered, size_t block_bytes, uint32_t g, uint32_t nq, uint32_t fk,
+                                    float* __restrict__ cand_bm, float* __restrict__ bmax, float* __restrict__ bmin) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)nq * fk;
+    const size_t off_cb = n * 12, off_mx = n * 16, off_mn = n * 16 + (size_t)nq * 4;
+    if (i < n) {
+        float acc = 0.0f;
+        for (uint32_t r = 0; r < g; ++r) acc = __fadd_rn(acc, reinterpret_cast<const float*>(gathered + r * block_bytes + off_cb)[i]);
+        cand_bm[i] = acc;
+    }
+    if (i < nq) {
+        float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+        for (uint32_t r = 0; r < g; ++r) {
+            mx = fmaxf(mx, reinterpret_cast<const float*>(gathered + r * block_bytes + off_mx)[i]);
+            mn = fminf(mn, reinterpret_cast<const float*>(gathered + r * block_bytes + off_mn)[i]);
+        }
+        bmax[i] = mx; bmin[i] = mn;
+    }
+}
+}  // namespace
+
+void launch_localize_candidates(const uint64_t* global_idx, uint64_t doc_offset, uint64_t n_local, size_t count, uint64_t* local_idx, cudaStream_t s) {
+    if (!count) return;
+    localize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(global_idx, doc_offset, n_local, count, local_idx);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+void launch_shard_reduce(const unsigned char* gathered, size_t block_bytes, uint32_t g, uint32_t nq, uint32_t fk, float* cand_bm, float* bmax,
+                         float* bmin, cudaStream_t s) {
+    const size_t n = std::max<size_t>((size_t)nq * fk, nq);
+    if (!n) return;
+    shard_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gathered, block_bytes, g, nq, fk, cand_bm, bmax, bmin);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -26,6 +26,10 @@ void launch_hybrid_fuse(const uint64_t* vkeys, const float* vdists, const uint32
                         const uint64_t* bm_idx, const float* bm_score, const uint32_t* bm_cnt, uint32_t bm_k,
                         const float* bmax, const float* bmin, int hybrid, float alpha, const uint64_t* mask, uint64_t mask_bits,
                         uint32_t top_k, uint64_t* out_idx, float* out_score, uint32_t* out_cnt, uint32_t nq, cudaStream_t s);
+// document-range shards: candidate ids -> this shard's local ordinals (~0 elsewhere); sum / max / min over the shards' blocks
+void launch_localize_candidates(const uint64_t* global_idx, uint64_t doc_offset, uint64_t n_local, size_t count, uint64_t* local_idx, cudaStream_t s);
+void launch_shard_reduce(const unsigned char* gathered, size_t block_bytes, uint32_t g, uint32_t nq, uint32_t fk, float* cand_bm, float* bmax,
+                         float* bmin, cudaStream_t s);
 void launch_dense_minmax_gather(const float* dense, uint32_t n, const uint64_t* idx, uint32_t m, float* cand_bm, float* bmax,
                                 float* bmin, uint32_t* scratch2, cudaStream_t s);
 

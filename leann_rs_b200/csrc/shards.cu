@@ -409,6 +409,38 @@ void shards_search(leann_cuda_shards* sh, const float* queries, bool on_device, 
 
 }  // namespace
 
+namespace leann {
+// ---- internal surface for the sharded hybrid path (text_api.cu) ------------------------------------------------------
+void shards_describe(const leann_cuda_shards* sh, int* world, int* rank, int* device, uint64_t* offsets16, size_t* local_shards) {
+    *world = sh->world; *rank = sh->loc.empty() ? 0 : sh->loc[0].rank; *device = sh->loc.empty() ? 0 : sh->loc[0].device;
+    for (int i = 0; i < MAX_SHARDS; ++i) offsets16[i] = sh->offset[i];
+    *local_shards = sh->loc.size();
+}
+cudaStream_t shards_stream(leann_cuda_shards* sh) { return sh->loc[0].stream; }
+// search + exchange + merge of the vector part, device buffers, enqueued on `st` (handles with one local shard)
+void shards_vector_search_device(leann_cuda_shards* sh, const float* dq, size_t nq, size_t k, size_t ef, uint64_t* dk, float* dd,
+                                 uint32_t* dc, cudaStream_t st) {
+    shards_search(sh, dq, true, nq, k, ef, nullptr, dk, dd, dc, st);
+}
+// recv[r] = rank r's `bytes` (a plain copy for a world of one)
+void shards_all_gather(leann_cuda_shards* sh, const void* send, void* recv, size_t bytes, cudaStream_t st) {
+    if (sh->world == 1) {
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st));
+        return;
+    }
+    if (sh->loc.size() != 1 || !sh->loc[0].comm) throw Error(LEANN_ERR_INVALID_ARG, "sharded hybrid search needs the process-per-GPU layout (leann_cuda_shards_join)");
+    std::lock_guard<std::mutex> lk(sh->mu);
+    LEANN_NCCL_CHECK(nccl().AllGather(send, recv, bytes, ncclChar, sh->loc[0].comm, st));
+    sh->exchanges++; sh->exchange_bytes += (uint64_t)sh->world * bytes;
+}
+void shards_merge_lists(const uint64_t* const* keys, const float* const* dists, const uint64_t* offsets, uint32_t g, uint32_t nq, uint32_t k,
+                        int descending, uint64_t* ok, float* od, uint32_t* oc, cudaStream_t st) {
+    MergeSrc src{};
+    for (uint32_t r = 0; r < g; ++r) { src.keys[r] = keys[r]; src.dists[r] = dists[r]; src.offset[r] = offsets[r]; }
+    launch_merge_ptr(src, g, nq, k, descending, ok, od, oc, st);
+}
+}  // namespace leann
+
 extern "C" {
 
 int leann_cuda_shards_open(const char* const* base_paths, size_t n_shards, int backend, size_t dims, int metric,
@@ -515,6 +547,7 @@ size_t leann_cuda_shards_len(const leann_cuda_shards* sh) {
     return (size_t)t;
 }
 size_t leann_cuda_shards_count(const leann_cuda_shards* sh) { return sh ? (size_t)sh->world : 0; }
+size_t leann_cuda_shards_dims(const leann_cuda_shards* sh) { return sh ? sh->d : 0; }
 
 int leann_cuda_shards_info(const leann_cuda_shards* sh, uint64_t* info4) {
     if (!sh || !info4) return LEANN_ERR_INVALID_ARG;

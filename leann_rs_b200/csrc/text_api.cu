@@ -13,6 +13,14 @@ using namespace leann;
 
 namespace leann {
 int guard_impl(char* err, size_t errlen, const std::function<void()>& f);
+// sharded backend internals (shards.cu)
+void shards_describe(const leann_cuda_shards* sh, int* world, int* rank, int* device, uint64_t* offsets16, size_t* local_shards);
+cudaStream_t shards_stream(leann_cuda_shards* sh);
+void shards_vector_search_device(leann_cuda_shards* sh, const float* dq, size_t nq, size_t k, size_t ef, uint64_t* dk, float* dd,
+                                 uint32_t* dc, cudaStream_t st);
+void shards_all_gather(leann_cuda_shards* sh, const void* send, void* recv, size_t bytes, cudaStream_t st);
+void shards_merge_lists(const uint64_t* const* keys, const float* const* dists, const uint64_t* offsets, uint32_t g, uint32_t nq, uint32_t k,
+                        int descending, uint64_t* ok, float* od, uint32_t* oc, cudaStream_t st);
 }
 #define GUARD(...) return leann::guard_impl(err, errlen, [&]() __VA_ARGS__)
 
@@ -495,6 +503,97 @@ int leann_cuda_bm25_search_shard(const leann_cuda_bm25* b, const char* const* qu
         if (cand_idx) LEANN_CUDA_CHECK(cudaMemcpyAsync(cand_bm, cb.p, nq * fk * 4, cudaMemcpyDeviceToHost, s));
         LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
         for (size_t i = 0; i < nq * top_k; ++i) if (top_idx[i] != ~0ull) top_idx[i] += doc_offset;
+    });
+}
+
+// search_with_options (searcher.rs:123-210) over document-range shards, one process per GPU, everything on the device:
+//   vector candidates  = the sharded backend (local K1/K2 + ncclAllGather + merge): identical on every rank, global ids;
+//   BM25               = this rank's postings (built with the corpus-wide statistics): local top list, scores of the
+//                        candidates this shard owns, max / min of its dense score vector;
+//   exchange           = ONE ncclAllGather of the packed per-rank block, then top-list merge + sum / max / min reductions;
+//   fusion + post-filter walk on every rank (K3f). No host round trip between the steps.
+int leann_cuda_shards_hybrid_search(leann_cuda_shards* sh, const leann_cuda_bm25* bm, const float* queries,
+                                    const char* const* query_texts, const size_t* query_text_bytes, size_t nq, size_t top_k,
+                                    size_t ef, int hybrid, float alpha, const uint64_t* filter_mask, size_t mask_bits,
+                                    uint64_t* idx, float* scores, uint32_t* counts, char* err, size_t errlen) {
+    GUARD({
+        if (!sh || (nq && (!queries || !idx || !scores))) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        if (nq == 0) return;
+        if (top_k == 0) throw Error(LEANN_ERR_INVALID_ARG, "top_k must be > 0");
+        int world = 1, rank = 0, device = 0;
+        uint64_t offsets[16];
+        size_t local_shards = 0;
+        shards_describe(sh, &world, &rank, &device, offsets, &local_shards);
+        if (local_shards != 1) throw Error(LEANN_ERR_INVALID_ARG, "sharded hybrid search needs a handle with one local shard (leann_cuda_shards_join)");
+        const size_t fk = (filter_mask || hybrid) ? top_k * 5 : top_k;   // searcher.rs:129-133
+        if (hybrid && !query_texts) hybrid = 0;                          // searcher.rs:147
+        if (hybrid && !bm) throw Error(LEANN_ERR_INVALID_ARG, "hybrid search needs this rank's BM25 shard");
+        if (hybrid && bm->device != device) throw Error(LEANN_ERR_INVALID_ARG, "BM25 shard lives on another device");
+        if (fk > 1024) throw Error(LEANN_ERR_INVALID_ARG, "top_k too large for the fused path (5*top_k <= 1024)");
+        DevGuard dg(device);
+        cudaStream_t s = shards_stream(sh);
+        const size_t d = leann_cuda_shards_dims(sh);
+        DevBuf dq(nq * d * 4), vk(nq * fk * 8), vd(nq * fk * 4), vc(nq * 4), oi(nq * top_k * 8), os(nq * top_k * 4), oc(nq * 4);
+        const size_t mask_words = filter_mask ? (mask_bits + 63) / 64 : 0;
+        DevBuf dmask(filter_mask ? mask_words * 8 : 16);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(dq.p, queries, nq * d * 4, cudaMemcpyHostToDevice, s));
+        if (filter_mask) LEANN_CUDA_CHECK(cudaMemcpyAsync(dmask.p, filter_mask, mask_words * 8, cudaMemcpyHostToDevice, s));
+        shards_vector_search_device(sh, dq.as<float>(), nq, fk, ef, vk.as<uint64_t>(), vd.as<float>(), vc.as<uint32_t>(), s);
+        std::unique_ptr<DevBuf> qo, qt, ci, blk, gat, cb, bi, bs, bc, bx, bn;
+        std::unique_ptr<std::lock_guard<std::mutex>> blk_lock;
+        if (hybrid) {
+            std::vector<uint64_t> off;
+            std::vector<uint32_t> terms;
+            tokenize_queries(bm, query_texts, query_text_bytes, nq, off, terms);   // host work while the vector search runs
+            blk_lock.reset(new std::lock_guard<std::mutex>(bm->mu));
+            bm25_ensure_ws(bm, nq);
+            const size_t n = nq * fk;
+            const size_t block_bytes = (n * 16 + nq * 8 + 255) & ~(size_t)255;
+            qo.reset(new DevBuf(off.size() * 8)); qt.reset(new DevBuf(terms.size() * 4)); ci.reset(new DevBuf(n * 8));
+            blk.reset(new DevBuf(block_bytes)); gat.reset(new DevBuf(block_bytes * (size_t)world));
+            cb.reset(new DevBuf(n * 4)); bi.reset(new DevBuf(n * 8)); bs.reset(new DevBuf(n * 4)); bc.reset(new DevBuf(nq * 4));
+            bx.reset(new DevBuf(nq * 4)); bn.reset(new DevBuf(nq * 4));
+            unsigned char* B = blk->as<unsigned char>();
+            uint64_t* b_idx = reinterpret_cast<uint64_t*>(B);
+            float* b_score = reinterpret_cast<float*>(B + n * 8);
+            float* b_cand = reinterpret_cast<float*>(B + n * 12);
+            float* b_max = reinterpret_cast<float*>(B + n * 16);
+            float* b_min = reinterpret_cast<float*>(B + n * 16 + nq * 4);
+            // BM25 top list of this shard on the BM25 handle's stream, concurrently with the vector search on `s`
+            cudaStream_t sb = bm->stream;
+            LEANN_CUDA_CHECK(cudaMemcpyAsync(qo->p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, sb));
+            if (!terms.empty()) LEANN_CUDA_CHECK(cudaMemcpyAsync(qt->p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, sb));
+            LEANN_CUDA_CHECK(cudaStreamSynchronize(sb));   // off / terms are stack-owned
+            launch_bm25_query(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, (uint32_t)fk, bm->n_ctas, nullptr, nullptr,
+                              (uint32_t)fk, nullptr, b_idx, b_score, bc->as<uint32_t>(), b_max, b_min, bm->d_qcounter, sb);
+            if (!bm->ev_join) LEANN_CUDA_CHECK(cudaEventCreateWithFlags(&bm->ev_join, cudaEventDisableTiming));
+            LEANN_CUDA_CHECK(cudaEventRecord(bm->ev_join, sb));
+            // scores of the (global) vector candidates this shard owns
+            launch_localize_candidates(vk.as<uint64_t>(), offsets[rank], bm->host.num_docs, n, ci->as<uint64_t>(), s);
+            launch_bm25_candidates(bm->view(), qo->as<uint64_t>(), qt->as<uint32_t>(), (uint32_t)nq, ci->as<uint64_t>(), vc.as<uint32_t>(),
+                                   (uint32_t)fk, b_cand, s);
+            LEANN_CUDA_CHECK(cudaStreamWaitEvent(s, bm->ev_join, 0));
+            shards_all_gather(sh, B, gat->p, block_bytes, s);
+            const uint64_t* keys[16];
+            const float* dists[16];
+            for (int r = 0; r < world; ++r) {
+                keys[r] = reinterpret_cast<const uint64_t*>(gat->as<unsigned char>() + (size_t)r * block_bytes);
+                dists[r] = reinterpret_cast<const float*>(gat->as<unsigned char>() + (size_t)r * block_bytes + n * 8);
+            }
+            shards_merge_lists(keys, dists, offsets, (uint32_t)world, (uint32_t)nq, (uint32_t)fk, 1, bi->as<uint64_t>(), bs->as<float>(),
+                               bc->as<uint32_t>(), s);
+            launch_shard_reduce(gat->as<unsigned char>(), block_bytes, (uint32_t)world, (uint32_t)nq, (uint32_t)fk, cb->as<float>(),
+                                bx->as<float>(), bn->as<float>(), s);
+        }
+        launch_hybrid_fuse(vk.as<uint64_t>(), vd.as<float>(), vc.as<uint32_t>(), (uint32_t)fk, hybrid ? cb->as<float>() : nullptr,
+                           hybrid ? bi->as<uint64_t>() : nullptr, hybrid ? bs->as<float>() : nullptr, hybrid ? bc->as<uint32_t>() : nullptr,
+                           (uint32_t)(hybrid ? fk : 0), hybrid ? bx->as<float>() : nullptr, hybrid ? bn->as<float>() : nullptr, hybrid, alpha,
+                           filter_mask ? dmask.as<uint64_t>() : nullptr, (uint64_t)mask_words * 64, (uint32_t)top_k, oi.as<uint64_t>(),
+                           os.as<float>(), oc.as<uint32_t>(), (uint32_t)nq, s);
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(idx, oi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaMemcpyAsync(scores, os.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
+        if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, oc.p, nq * 4, cudaMemcpyDeviceToHost, s));
+        LEANN_CUDA_CHECK(cudaStreamSynchronize(s));
     });
 }
 

@@ -57,6 +57,31 @@ def main():
         assert sh.info()["exchange"] == ("nccl_all_gather" if world > 1 else "none")
         sh.close()
         part.close()
+    # ---- hybrid path over document-range shards: bit-identical to the unsharded hybrid search ----
+    nd, dd, nqh = 4000, 64, 48
+    xv, qv = make_data(nd, dd, 21, nq=nqh)
+    rng = np.random.default_rng(5)
+    vocab = [f"tok{i}" for i in range(300)]
+    docs = [" ".join(rng.choice(vocab, size=int(rng.integers(5, 40))).tolist()) for _ in range(nd)]
+    texts = [" ".join(rng.choice(vocab[:60], size=int(rng.integers(1, 5))).tolist()) for _ in range(nqh)]
+    mask = P.pack_mask(rng.random(nd) < 0.4)
+    lo, hi = shard_bounds(nd, world, rank)
+    whole = P.FlatSearcher.from_vectors(xv, metric=P.METRIC_IP, device=local)       # exact backend: the same candidates sharded or not
+    bm_whole = P.Bm25Scorer.build(docs, device=local)
+    part = P.FlatSearcher.from_vectors(xv[lo:hi], metric=P.METRIC_IP, device=local)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, P.Bm25Scorer.shard_stats(docs[lo:hi], device=local))
+    bm_part = P.Bm25Scorer.build_sharded(docs[lo:hi], P.Bm25Scorer.merge_stats(blobs), device=local)
+    uid = [P.ShardedBackend.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    sh = P.ShardedBackend.join(part, uid[0], rank, world, lo)
+    for hybrid, alpha, m in ((True, 0.5, mask), (True, 0.7, None), (False, 0.5, mask), (True, 0.0, None)):
+        ri, rs, rc = P.text.hybrid_search(whole, bm_whole, qv, texts, 10, 0, hybrid, alpha, m)
+        si, ss, sc = sh.hybrid_search(bm_part, qv, texts, 10, 0, hybrid, alpha, m)
+        assert np.array_equal(rc, sc), (hybrid, alpha, rank)
+        assert np.array_equal(ri, si), (hybrid, alpha, rank, float(np.mean(ri == si)))
+        assert np.array_equal(rs.view(np.uint32), ss.view(np.uint32)), (hybrid, alpha, rank)
+    sh.close(); part.close(); whole.close(); bm_part.close(); bm_whole.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -38,6 +38,26 @@ def test_one_shard_handle_equals_backend(pkg):
     flat.close()
 
 
+def test_sharded_hybrid_world_of_one_equals_hybrid_search(pkg):
+    """leann_cuda_shards_hybrid_search with a single shard runs the whole device-resident pipeline (candidate localisation,
+    packed block, merge, reductions, fusion) and must reproduce leann_cuda_hybrid_search bit for bit."""
+    rng = np.random.default_rng(3)
+    nd, d, nq = 5000, 96, 64
+    x, q = make_data(nd, d, 8, nq=nq)
+    vocab = [f"tok{i}" for i in range(400)]
+    docs = [" ".join(rng.choice(vocab, size=int(rng.integers(5, 50))).tolist()) for _ in range(nd)]
+    texts = [" ".join(rng.choice(vocab[:80], size=int(rng.integers(1, 6))).tolist()) for _ in range(nq)]
+    mask = pkg.pack_mask(rng.random(nd) < 0.3)
+    idx = pkg.HnswSearcher.build(x, graph_degree=16, complexity=64, seed=2)
+    bm = pkg.Bm25Scorer.build(docs)
+    sh = pkg.ShardedBackend.join(idx, b"\0" * 128, 0, 1, 0)
+    for hybrid, alpha, m in ((True, 0.5, mask), (True, 0.7, None), (False, 0.5, mask), (False, 0.5, None)):
+        ri, rs, rc = pkg.text.hybrid_search(idx, bm, q, texts, 10, 64, hybrid, alpha, m)
+        si, ss, sc = sh.hybrid_search(bm, q, texts, 10, 64, hybrid, alpha, m)
+        assert np.array_equal(rc, sc) and np.array_equal(ri, si) and np.array_equal(rs.view(np.uint32), ss.view(np.uint32)), (hybrid, alpha)
+    sh.close(); bm.close(); idx.close()
+
+
 def test_sharded_errors(pkg):
     x, _ = make_data(3000, 64, 1)
     a = pkg.FlatSearcher.from_vectors(x, metric=pkg.METRIC_DOT_DESC)
