@@ -61,15 +61,22 @@ merge = lambda gk, gd, desc: P.topk_merge_device(gk, gd, desc)[:2]
 vec = S.ShardedSearcher(lambda qq, k, ef: index.search_device(qq, k, ef)[:2], lo, world, rank, False, merge, dist)
 hy = S.ShardedHybridSearcher(vec, bm.search_shard, lambda *args: P.hybrid_fuse(*args, device=lr), lambda gk, gs: merge(gk, gs, True),
                              lo, world, rank, dist, exchange_device=dev)
+# the same through the library's own sharded handle (leann_cuda_shards_join + leann_cuda_shards_hybrid_search): one all_gather, no host hop
+uid = [P.ShardedBackend.unique_id() if rank == 0 else None]
+if world > 1: dist.broadcast_object_list(uid, src=0)
+sh = P.ShardedBackend.join(index, uid[0], rank, world, lo)
+qh = q.cpu().numpy()
 gc.collect(); gc.freeze(); gc.disable()
 rows = []
-for name, hybrid, m in (("hybrid", True, None), ("hybrid+filter source:*.rs", True, mask), ("filter-only source:*.rs", False, mask)):
-    hy.search(q, texts, a.k, 64, hybrid, 0.5, m, a.n)   # warm
+for name, hybrid, m, abi in (("hybrid", True, None, False), ("hybrid+filter source:*.rs", True, mask, False), ("filter-only source:*.rs", False, mask, False),
+                             ("C ABI: hybrid", True, None, True), ("C ABI: hybrid+filter source:*.rs", True, mask, True)):
+    run = (lambda: sh.hybrid_search(bm, qh, texts, a.k, 64, hybrid, 0.5, m)) if abi else (lambda: hy.search(q, texts, a.k, 64, hybrid, 0.5, m, a.n))
+    run()   # warm
     ts = []
     for _ in range(a.steps):
         if world > 1: dist.barrier()
         torch.cuda.synchronize(); t0 = time.time()
-        idx, sc, cnt = hy.search(q, texts, a.k, 64, hybrid, 0.5, m, a.n)
+        idx, sc, cnt = run()
         dt = time.time() - t0
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = t.item()

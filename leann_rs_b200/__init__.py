@@ -37,6 +37,25 @@ class LeannCudaError(RuntimeError):
 _lib = None
 
 
+def _prefer_bundled_nccl() -> None:
+    """The library loads libnccl.so.2 with dlopen on first sharded use. In a Python process that also imports torch, the copy
+    torch was built against (the `nvidia-nccl` wheel) must be the one that gets mapped: whichever libnccl.so.2 is loaded first
+    satisfies every later request for that SONAME, and an older system copy lacks symbols torch needs. Point the loader at the
+    wheel's file unless the caller chose one (LEANN_CUDA_NCCL_LIB)."""
+    if os.environ.get("LEANN_CUDA_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["LEANN_CUDA_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """Loads libleann_cuda.so; fails loudly when it has not been built (no fallback path)."""
     global _lib
@@ -44,6 +63,7 @@ def lib():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise LeannCudaError(ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    _prefer_bundled_nccl()
     L = C.CDLL(LIB_PATH)
     vp, sz, cp = C.c_void_p, C.c_size_t, C.c_char_p
     u64p, f32p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
