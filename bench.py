@@ -577,7 +577,8 @@ def shard_layout(P, torch, dist, dev, rank, world, n, nq, W, qb, ef, a, max_over
     info = sh.info()
     ms_shard, ms_local, e2e_s = max_over_ranks([ms_shard, ms_local, e2e_s])
     out = {"value": round(nq * a.steps / (ms_shard / 1e3), 1), "unit": "queries/s", "ms_per_step": round(ms_shard / a.steps, 4),
-           "local_search_ms": round(ms_local / a.steps, 4), "merge_ms": round((ms_shard - ms_local) / a.steps, 4),
+           "local_search_ms": round(ms_local / a.steps, 4), "merge_ms": round(max(0.0, (ms_shard - ms_local) / a.steps), 4),
+           "merge_note": "all_gather + merge = difference of two separately timed loops (sharded step, local search alone); 0 means below their run-to-run noise",
            "allgather_bytes": int(world * ((nq * TOP_K * 12 + 255) // 256 * 256)), "exchange": info["exchange"],
            "recall_at_10": round(rec, 4), "ef": ef, "database_rows": n * world, "rows_per_gpu": n, "scaling": "weak (capacity x N at ~constant QPS)",
            "e2e_value": round(nq * a.steps / e2e_s, 1), "api": "leann_cuda_shards_join + leann_cuda_shards_search_device (ncclAllGather + topk_merge_ptr_kernel)",
