@@ -134,3 +134,20 @@ def test_streamed_open_keeps_format_checks(orc, pkg, tmp_path):
     oi, osc, _ = orc.exact_scan(q, x, 5, metric=0)
     assert np.array_equal(fk, oi)
     f.close()
+
+
+def test_save_is_atomic_and_reports_failures(pkg, tmp_path):
+    """writers go through `<file>.tmp`, check every write and rename only a complete file over the target."""
+    x, _ = make_data(800, 32, 4)
+    s = pkg.HnswSearcher.build(x, graph_degree=8, complexity=32, seed=1)
+    base = str(tmp_path / "documents.leann")
+    s.save(base)
+    first = open(base.replace(".leann", ".index"), "rb").read()
+    assert not os.path.exists(base.replace(".leann", ".index") + ".tmp")
+    with pytest.raises(pkg.LeannCudaError) as e:
+        s.save(str(tmp_path / "no_such_dir" / "documents.leann"))
+    assert e.value.code == pkg.ERR_NOT_FOUND
+    s.save(base)                                   # overwriting in place (what add_to_index does) leaves one complete file
+    assert open(base.replace(".leann", ".index"), "rb").read() == first
+    assert sorted(os.listdir(tmp_path)) == ["documents.index"]
+    s.close()
