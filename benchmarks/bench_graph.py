@@ -44,10 +44,18 @@ else:
     idx = P.HnswSearcher.build(x, graph_degree=a.deg, complexity=a.L, metric=metric)
 torch.cuda.synchronize(); t_build = time.time() - t0
 flat = P.FlatSearcher.from_vectors(x, metric=metric if a.metric == "l2" else P.METRIC_IP)
-merge = lambda gk, gd, desc: P.topk_merge_device(gk, gd, desc)[:2]
-gt = S.ShardedSearcher(lambda qq, k, ef: flat.search_device(qq, k, 0)[:2], lo, world, rank, False, merge, dist).search(q, a.k, 0)[0]
-torch.cuda.synchronize(); flat.close(); del flat, x; torch.cuda.empty_cache()
-eng = S.ShardedSearcher(lambda qq, k, ef: idx.search_device(qq, k, ef)[:2], lo, world, rank, False, merge, dist)
+# sharded layout through the library's own handle (leann_cuda_shards_join: ncclCommInitRank inside, one all_gather + merge per batch)
+def joined(local):
+    uid = [P.ShardedBackend.unique_id() if rank == 0 else None]
+    if world > 1: dist.broadcast_object_list(uid, src=0)
+    return P.ShardedBackend.join(local, uid[0] if world > 1 else b"\0" * 128, rank, world, lo)
+class Eng:
+    def __init__(self, sh): self.sh = sh
+    def search(self, qq, k, ef): return self.sh.search_device(qq, k, ef)[:2]
+gsh = joined(flat)
+gt = gsh.search_device(q, a.k, 0)[0]
+torch.cuda.synchronize(); gsh.close(); flat.close(); del flat, x; torch.cuda.empty_cache()
+eng = Eng(joined(idx))
 info = idx.info()
 peak = 6538.0
 try: peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -75,5 +83,5 @@ for ef in a.ef:
     rows.append({"ef": ef, "recall": round(rec, 4), "qps": round(a.nq / ms * 1e3), "ms": round(ms, 3), "step_ms": [round(v, 2) for v in step_ms], "n_dist": round(tot[0] / a.nq, 1),
                  "hops": round(tot[1] / a.nq, 1), "algorithmic_GBps": round(byts / ms / 1e6, 1), "frac_of_hbm_peak": round(byts / ms / 1e6 / peak / world, 4)})
 if world > 1: dist.destroy_process_group()
-if rank == 0: print(json.dumps({"bench": "graph", "gpus": world, "backend": a.backend, "n": a.n, "d": a.d, "metric": a.metric, "degree": a.deg, "L_build": a.L, "k": a.k,
+if rank == 0: print(json.dumps({"bench": "graph", "gpus": world, "exchange": eng.sh.info()["exchange"], "backend": a.backend, "n": a.n, "d": a.d, "metric": a.metric, "degree": a.deg, "L_build": a.L, "k": a.k,
                   "nq": a.nq, "build_s": round(t_build, 2), "info": info, "results": rows}))
