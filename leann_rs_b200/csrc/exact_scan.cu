@@ -165,12 +165,13 @@ __device__ void block_bitonic_sort(unsigned long long* keys, uint32_t n) {
 
 // The (kth+1)-th smallest of n 64-bit keys: MSB-first radix select, 8 bits per pass. `key(i)` reads key i (shared memory
 // staging buffer, or global memory in the low-shared-memory variant). All threads of the block call it; hist = 256
-// counters + 2 words in shared memory.
-template <typename KeyFn>
-__device__ unsigned long long block_kth_smallest(KeyFn key, uint32_t n, uint32_t kth, uint32_t* hist) {
-    unsigned long long prefix = 0;
-    uint32_t remaining = kth;
-    for (int pass = 0; pass < 8; ++pass) {
+// counters + 3 words in shared memory.
+// FIRST_PASS .. LAST_PASS of the 8 byte-wise passes (0 = most significant byte). `prefix` / `remaining` carry the state
+// between a high-half call (passes 0-3) and an optional low-half call (passes 4-7). After the last executed pass,
+// hist[258] = number of keys equal to the prefix on the bytes examined so far.
+template <int FIRST_PASS, int LAST_PASS, typename KeyFn>
+__device__ void block_radix_select(KeyFn key, uint32_t n, unsigned long long& prefix, uint32_t& remaining, uint32_t* hist) {
+    for (int pass = FIRST_PASS; pass <= LAST_PASS; ++pass) {
         const int shift = 56 - 8 * pass;
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
@@ -197,6 +198,7 @@ __device__ unsigned long long block_kth_smallest(KeyFn key, uint32_t n, uint32_t
                 while (j < 7 && remaining >= acc + c[j]) { acc += c[j]; ++j; }
                 hist[256] = lane * 8 + (uint32_t)j;
                 hist[257] = acc;
+                hist[258] = c[j];
             }
         }
         __syncthreads();
@@ -204,7 +206,6 @@ __device__ unsigned long long block_kth_smallest(KeyFn key, uint32_t n, uint32_t
         remaining -= hist[257];
         __syncthreads();
     }
-    return prefix;
 }
 
 // Merge (running best) + (candidates) -> new best, dedupe, new threshold. One block per query.
@@ -220,7 +221,7 @@ select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand
               unsigned long long* __restrict__ best, uint32_t* __restrict__ best_cnt, uint32_t k, uint32_t kpad,
               unsigned long long* __restrict__ thr, uint32_t nq, uint32_t sort_cap) {
     extern __shared__ unsigned long long skeys[];   // [sort_cap] sort buffer (+ [cap + kpad] staging unless LOWSMEM)
-    __shared__ uint32_t s_hist[258];
+    __shared__ uint32_t s_hist[259];
     __shared__ uint32_t s_n;
     const uint32_t q = blockIdx.x;
     if (q >= nq) return;
@@ -241,7 +242,16 @@ select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
         auto skey = [&](uint32_t i) { return LOWSMEM ? gkey(i) : stage[i]; };
-        const unsigned long long cut = block_kth_smallest(skey, total, 2 * k - 1, s_hist);
+        // The cut is the (2k)-th smallest key. Its high half (the score bits) is found in 4 passes; the keys that tie with it
+        // on the score are all kept when they fit in the sort buffer beside the strictly better ones (the usual case: one or
+        // two keys), otherwise 4 more passes over the row-id half pick exactly the ones needed.
+        unsigned long long cut = 0;
+        uint32_t remaining = 2 * k - 1;
+        block_radix_select<0, 3>(skey, total, cut, remaining, s_hist);
+        const uint32_t less = 2 * k - 1 - remaining, ties = s_hist[258];
+        __syncthreads();
+        if (less + ties <= sort_cap) cut |= 0xFFFFFFFFull;
+        else block_radix_select<4, 7>(skey, total, cut, remaining, s_hist);
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             const unsigned long long v = skey(i);
             if (v <= cut && v != ~0ull) {
@@ -250,7 +260,7 @@ select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand
             }
         }
         __syncthreads();
-        total = min(s_n, sort_cap);   // <= 2k + 1 (the cut key itself may be duplicated once)
+        total = min(s_n, sort_cap);   // <= sort_cap by construction (2k + 1 after the exact cut; less + ties after the short one)
         uint32_t n2 = 1;
         while (n2 < total) n2 <<= 1;
         for (uint32_t i = total + threadIdx.x; i < n2; i += blockDim.x) sortbuf[i] = ~0ull;
