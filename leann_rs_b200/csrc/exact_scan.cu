@@ -6,7 +6,9 @@
 // kernel computes a 128-query x 128-row block of f32 scores and appends only the scores that can
 // still enter the top-k (packed 64-bit key <= the query's current k-th best key) to a per-query
 // candidate list; a select kernel then merges candidates into the running top-k and tightens the
-// threshold. The full nq x N score matrix is never materialised.
+// threshold. The full nq x N score matrix is never materialised. Chunks after the first go through the tensor-core
+// pass of exact_scan_tc.cu when it applies; large batches are split into two query halves on two streams so that the
+// re-rank / select of one half overlap the other half's tensor pass (launch_exact_scan).
 // Ordering is total: key = (ordered(score) << 32) | row, so equal scores rank by ascending row —
 // exactly what the reference's stable sort over the enumerate() order yields (recompute.rs:106).
 #include <cuda_runtime.h>

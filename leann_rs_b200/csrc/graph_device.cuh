@@ -1,7 +1,11 @@
 // graph_device.cuh — warp-cooperative building blocks of the graph traversal kernels (K1/K1f and
-// the HNSW builder). One warp owns one query: the query lives in registers, `top` (the bounded
-// result list, usearch sorted_buffer_gt) and `next` (the candidate queue) live in shared memory,
-// the visited set is an epoch-tagged byte map in HBM (exact, no clearing between queries).
+// the HNSW builder). One warp owns one query: the query lives in registers; `top` (the bounded
+// result list, usearch sorted_buffer_gt) and `next` (the candidate queue) live in shared memory
+// (beam_level) or, on short rows under the diskann-rs stop rule, as ONE register-resident list with an
+// "expanded" bit per entry (RegList / beam_level_regs). The visited set is exact in all three of its
+// representations (VisitedSet): an epoch-tagged byte map in HBM (no clearing between queries), a per-warp
+// u32 open-addressing table, or a per-warp bucketed table of 16-bit quotiented entries (q16) that stays
+// in L2; the tables move a traversal that outgrows them to a pooled byte map.
 //
 // Semantics restated from usearch search_for_one_ / search_to_find_in_base_ / search_to_insert_
 // (call site leann-rs src/backend/hnsw.rs:85) and diskann-rs search_with_dists (diskann.rs:56);
