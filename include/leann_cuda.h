@@ -95,6 +95,11 @@ int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t 
  * EmbeddingsWriter (index/embeddings.rs:126-147). Writes the reference's on-disk formats. */
 int leann_cuda_save(const leann_cuda_index* index, const char* base_path, char* err, size_t errlen);
 
+/* Host-only validation of an index file: the header pass and node parser of leann_cuda_open, without touching a device
+ * (same error classes and messages). info[0..7] = n, dims, M (or R), M0, max_level, entry (or medoid), number of
+ * upper-level lists, FNV-1a over every neighbour list in list order (terminated per list) and every key. */
+int leann_cuda_check_index_file(const char* base_path, int backend, size_t dims, uint64_t* info8, char* err, size_t errlen);
+
 /* Cached device layout. leann_cuda_open streams the vectors block of `.index` / `.diskann` /
  * `.embeddings` files from disk to HBM through pinned staging buffers and parses the usearch node block on host threads
  * meanwhile. write_layout_cache stores the parsed, fixed-stride adjacency of an HNSW handle as `<base>.cuda-layout`, bound to

@@ -78,6 +78,7 @@ def lib():
         "leann_cuda_hnsw_add": (C.c_int, [vp, vp, C.c_int, sz, C.c_uint64, sz, C.c_uint64, cp, sz]),
         "leann_cuda_vamana_build": (C.c_int, [vp, C.c_int, sz, sz, sz, sz, C.c_float, C.c_int, C.c_uint64, C.c_int, pp, cp, sz]),
         "leann_cuda_save": (C.c_int, [vp, cp, cp, sz]),
+        "leann_cuda_check_index_file": (C.c_int, [cp, C.c_int, sz, u64p, cp, sz]),
         "leann_cuda_write_layout_cache": (C.c_int, [vp, cp, cp, sz]),
         "leann_cuda_layout_cache_used": (C.c_int, [vp]),
         "leann_cuda_len": (sz, [vp]),
@@ -580,6 +581,15 @@ class BackendType:
         if backend_name == "flat":
             return FlatSearcher.load(index_path, dimensions, device)
         raise LeannCudaError(ERR_INVALID_ARG, f"Unknown backend: {backend_name}")  # searcher.rs:98
+
+
+def check_index_file(base_path: str, backend: int, dimensions: int = 0) -> dict:
+    """Host-only validation of `<base>.index` / `.diskann` / `.embeddings` (no GPU needed): the reader of leann_cuda_open."""
+    out = (C.c_uint64 * 8)()
+    e = _err()
+    _check(lib().leann_cuda_check_index_file(os.fsencode(base_path), backend, dimensions, out, e, 1024), e)
+    names = ["n", "dims", "M", "M0", "max_level", "entry", "n_upper_lists", "adjacency_hash"]
+    return dict(zip(names, [int(x) for x in out]))
 
 
 def topk_merge_device(keys_in, dists_in, descending: bool = False):

@@ -594,6 +594,52 @@ int leann_cuda_vamana_build(const float* vectors, int vectors_on_device, size_t 
     });
 }
 
+// Host-only: parses the whole file exactly as leann_cuda_open does (same header pass, same node parser) and reports what
+// it holds. No device is touched, so index files can be validated on machines without a GPU (and the reader is covered by the
+// CPU test suite).
+int leann_cuda_check_index_file(const char* base_path, int backend, size_t dims, uint64_t* info8, char* err, size_t errlen) {
+    GUARD({
+        if (!base_path || !info8) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
+        std::string base(base_path);
+        auto mix = [](uint64_t h, uint64_t v) { h ^= v; h *= 0x100000001B3ull; return h; };
+        uint64_t h = 0xCBF29CE484222325ull;
+        if (backend == LEANN_BACKEND_HNSW) {
+            const std::string file = with_extension(base, "index");
+            if (is_faiss_index(file)) throw Error(LEANN_ERR_FAISS_FORMAT, "This index was built with Python LEANN (FAISS format).");
+            HostHnsw g;
+            read_usearch_index(file, dims, g);
+            for (size_t i = 0; i < g.n; ++i) {      // level-0 lists, then upper lists, in list order; then keys
+                for (size_t j = 0; j < g.M0 && g.adj0[i * g.M0 + j] != SENT; ++j) h = mix(h, g.adj0[i * g.M0 + j]);
+                h = mix(h, 0xFFFFFFFFFFull);
+                for (int l = 1; l <= g.levels[i]; ++l) {
+                    const uint32_t* p = &g.adjU[((size_t)g.upper_base[i] + (size_t)(l - 1)) * g.M];
+                    for (size_t j = 0; j < g.M && p[j] != SENT; ++j) h = mix(h, p[j]);
+                    h = mix(h, 0xFFFFFFFFFFull);
+                }
+                h = mix(h, g.keys[i]);
+            }
+            info8[0] = g.n; info8[1] = g.d; info8[2] = g.M; info8[3] = g.M0; info8[4] = (uint64_t)g.max_level; info8[5] = g.entry;
+            info8[6] = g.M ? g.adjU.size() / g.M : 0; info8[7] = h;
+        } else if (backend == LEANN_BACKEND_VAMANA) {
+            HostVamana g;
+            read_diskann(with_extension(base, "diskann"), dims, g);
+            for (size_t i = 0; i < g.n; ++i) {
+                for (size_t j = 0; j < g.R && g.adj[i * g.R + j] != SENT; ++j) h = mix(h, g.adj[i * g.R + j]);
+                h = mix(h, 0xFFFFFFFFFFull);
+                h = mix(h, i);
+            }
+            info8[0] = g.n; info8[1] = g.d; info8[2] = g.R; info8[3] = g.R; info8[4] = 0; info8[5] = g.medoid; info8[6] = 0; info8[7] = h;
+        } else if (backend == LEANN_BACKEND_FLAT) {
+            std::vector<float> v;
+            size_t n = 0;
+            read_embeddings(with_extension(base, "embeddings"), dims, v, n);
+            info8[0] = n; info8[1] = dims; info8[2] = info8[3] = info8[4] = info8[5] = info8[6] = 0; info8[7] = h;
+        } else {
+            throw Error(LEANN_ERR_INVALID_ARG, "Unknown backend");
+        }
+    });
+}
+
 int leann_cuda_write_layout_cache(const leann_cuda_index* ix, const char* base_path, char* err, size_t errlen) {
     GUARD({
         if (!ix || !base_path) throw Error(LEANN_ERR_INVALID_ARG, "null argument");
