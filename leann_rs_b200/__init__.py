@@ -190,10 +190,8 @@ def device_count() -> int:
 
 
 def _strs(items: Sequence):
-    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in items]
-    arr = (C.c_char_p * len(bs))(*bs)
-    lens = (C.c_size_t * len(bs))(*[len(b) for b in bs])
-    return bs, arr, lens
+    from .text import _strs as impl   # one implementation (joined buffer + vectorised pointer table)
+    return impl(items)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -449,7 +447,8 @@ class ShardedBackend:
     @classmethod
     def open(cls, base_paths: Sequence[str], backend: int, dimensions: int, devices: Sequence[int],
              metric: int = METRIC_DEFAULT, key_offsets=None, exchange: int = EXCHANGE_AUTO):
-        _, arr, _ = _strs([os.fsencode(p) for p in base_paths])
+        paths = [os.fsencode(p) for p in base_paths]
+        arr = (C.c_char_p * len(paths))(*paths)   # NUL-terminated C strings (no length array in this entry point)
         devs = (C.c_int * len(devices))(*devices)
         offs = None if key_offsets is None else (C.c_uint64 * len(key_offsets))(*key_offsets)
         h, e = C.c_void_p(), _err()
@@ -538,7 +537,7 @@ class ShardedBackend:
         cnt = np.zeros(nq, dtype=np.uint32)
         arr = lens = None
         if query_texts is not None:
-            _, arr, lens = _strs(query_texts)
+            keep, arr, lens = _strs(query_texts)
         m = None if filter_mask is None else np.ascontiguousarray(filter_mask, dtype=np.uint64)
         e = _err()
         _check(lib().leann_cuda_shards_hybrid_search(self._h, None if bm25_shard is None else bm25_shard._h, _np_ptr(q), arr, lens, nq, top_k, ef,

@@ -33,10 +33,23 @@ def _check(code, e):
 
 
 def _strs(items: Sequence):
+    """Python strings / bytes -> (keep-alive, `const char* const*`, `const size_t*`) for the C ABI. One joined buffer plus a
+    vectorised pointer table: building a ctypes array element by element cost ~10 ms per 10k query texts, which sat inside
+    the end-to-end time of every hybrid batch."""
     bs = [s.encode() if isinstance(s, str) else bytes(s) for s in items]
-    arr = (C.c_char_p * max(len(bs), 1))(*bs)
-    lens = (C.c_size_t * max(len(bs), 1))(*[len(b) for b in bs])
-    return bs, arr, lens
+    n = len(bs)
+    lens = np.fromiter(map(len, bs), dtype=np.uint64, count=n) if n else np.zeros(1, dtype=np.uint64)
+    blob = C.create_string_buffer(b"".join(bs) + b"\0")
+    base = C.addressof(blob)
+    ptrs = np.zeros(max(n, 1), dtype=np.uint64)
+    if n:
+        ptrs[0] = base
+        if n > 1:
+            np.cumsum(lens[:-1], out=ptrs[1:])
+            ptrs[1:] += np.uint64(base)
+    arr = C.cast(C.c_void_p(ptrs.ctypes.data), C.POINTER(C.c_char_p))
+    lens_p = C.cast(C.c_void_p(lens.ctypes.data), C.POINTER(C.c_size_t))
+    return (bs, blob, ptrs, lens), arr, lens_p
 
 
 def tokenize(text: str) -> List[str]:
