@@ -19,6 +19,7 @@ for v in "$@"; do
     nopipe) build nopipe -DLEANN_BM_PIPE=0 ;;
     t16k_256x2) build t16k_256x2 -DLEANN_BM_TILE=16384 -DLEANN_BM_MINB=2 -DLEANN_BM_PIPE=0 ;;
     t16k_512x2) build t16k_512x2 -DLEANN_BM_TILE=16384 -DLEANN_BM_THREADS=512 -DLEANN_BM_CAP=4096 -DLEANN_BM_MINB=2 -DLEANN_BM_PIPE=0 ;;
+    t4k_256x4) build t4k_256x4 -DLEANN_BM_TILE=4096 -DLEANN_BM_MINB=4 ;;
     t8k_512x2) build t8k_512x2 -DLEANN_BM_THREADS=512 -DLEANN_BM_CAP=4096 -DLEANN_BM_MINB=2 -DLEANN_BM_PIPE=0 ;;
   esac
 done

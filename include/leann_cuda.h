@@ -238,6 +238,11 @@ int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size
 size_t leann_cuda_bm25_len(const leann_cuda_bm25* bm25);
 /* stats[0..3] = n_docs, n_terms, n_postings, total_tokens; avg_doc_len out (bm25.rs:61-65). */
 int leann_cuda_bm25_stats(const leann_cuda_bm25* bm25, uint64_t* stats4, float* avg_doc_len);
+/* Number of terms the handle also keeps as dense score rows (K3d: terms present in at least half of the documents are
+ * added to the accumulator tile row-wise, 4 B per document instead of 8 B per posting; results are bit-identical).
+ * Tuning, read at build time: LEANN_CUDA_BM25_DENSE_FRAC (df / n_docs threshold, default 0.5, 0 = off),
+ * LEANN_CUDA_BM25_DENSE_MAX (row limit, default 64). */
+size_t leann_cuda_bm25_dense_rows(const leann_cuda_bm25* bm25);
 /* tokenize (bm25.rs:127-132): writes tokens separated by '\n' into out (truncated to cap),
  * returns the number of tokens. */
 size_t leann_cuda_tokenize(const char* text, size_t text_bytes, char* out, size_t cap);

@@ -111,6 +111,7 @@ def lib():
         "leann_cuda_compat_flags": (C.c_uint, []),
         "leann_cuda_bm25_build": (C.c_int, [cpp, szp, sz, C.c_int, pp, cp, sz]),
         "leann_cuda_bm25_len": (sz, [vp]),
+        "leann_cuda_bm25_dense_rows": (sz, [vp]),
         "leann_cuda_bm25_stats": (C.c_int, [vp, u64p, f32p]),
         "leann_cuda_tokenize": (sz, [cp, sz, cp, sz]),
         "leann_cuda_bm25_score": (C.c_int, [vp, cp, sz, vp, cp, sz]),

@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <utility>
+#include <vector>
 #include <math_constants.h>
 
 #include "bm25_dev.h"
@@ -44,7 +47,9 @@ constexpr int BM_TILE = LEANN_BM_TILE;     // documents per shared-memory accumu
 constexpr int BM_CAP = LEANN_BM_CAP;       // candidate keys held in shared memory between prunes
 constexpr int BM_BOUNDS = 2048;   // entries of the (token, tile boundary) -> posting offset table (16 KB)
 constexpr int BM_SPARSE = 1024;   // tiles holding fewer postings are collected by re-walking them instead of a full scan
-constexpr size_t BM_SMEM = (size_t)BM_TILE * 4 + (size_t)BM_CAP * 8 + (size_t)BM_BOUNDS * 8;
+constexpr uint32_t BM_NOT_DENSE = 0xFFFFFFFFu;
+constexpr size_t BM_SMEM = (size_t)BM_TILE * 4 + (size_t)BM_CAP * 8 + (size_t)BM_BOUNDS * 8 + (size_t)(BM_BOUNDS / 2) * 4;
+static_assert(BM_TILE % (4 * BM_THREADS) == 0, "a tile is a whole number of float4 per thread");
 
 __device__ __forceinline__ uint32_t order_f32(float f) {
     uint32_t u = __float_as_uint(f);
@@ -94,6 +99,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
     float* acc = reinterpret_cast<float*>(bm_smem);                                                  // [BM_TILE], zero between tiles
     unsigned long long* buf = reinterpret_cast<unsigned long long*>(bm_smem + (size_t)BM_TILE * 4);   // [BM_CAP]
     unsigned long long* bounds = buf + BM_CAP;                                                         // [T][S + 1] absolute posting offsets
+    uint32_t* tokd = reinterpret_cast<uint32_t*>(bounds + BM_BOUNDS);                                  // [T] dense row of the token, or BM_NOT_DENSE
     __shared__ uint32_t s_cnt, s_q, s_pos, s_minbits;
     __shared__ unsigned long long s_thr;
     const int tid = threadIdx.x;
@@ -133,6 +139,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
         const uint32_t nc = cand_idx ? cand_cnt[q] : 0u;
         for (uint32_t j = tid; j < nc; j += BM_THREADS) cand_bm[(size_t)q * fk + j] = 0.0f;   // bm25.rs:160 unwrap_or(0.0) / untouched tiles
         my_pos = 0; my_min = 0xFFFFFFFFu;
+        for (uint32_t t = tid; t < T; t += BM_THREADS) tokd[t] = b.dense_of ? __ldg(b.dense_of + qtok_term[t0 + t]) : BM_NOT_DENSE;
         const uint32_t n_tiles = (b.n_docs + BM_TILE - 1) / BM_TILE;
         const uint32_t S = T ? max(1u, (uint32_t)BM_BOUNDS / T - 1u) : n_tiles;   // tiles per boundary table
         for (uint32_t sb0 = 0; sb0 < n_tiles && T; sb0 += S) {
@@ -141,6 +148,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
             __syncthreads();
             for (uint32_t e = tid; e < T * (sbt + 1); e += BM_THREADS) {
                 const uint32_t t = e / (sbt + 1), i = e % (sbt + 1);
+                if (tokd[t] != BM_NOT_DENSE) continue;   // dense rows need no slice boundaries
                 const uint32_t term = qtok_term[t0 + t];
                 uint64_t lo = b.term_off[term], hi = b.term_off[term + 1];
                 const uint64_t target = (uint64_t)(sb0 + i) * BM_TILE;
@@ -208,9 +216,34 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     }
                 }
 #else
+                // K3d: a token whose term has a dense row adds the row's tile to the accumulator, float4 by float4 (x + 0.0f == x for
+                // the non-negative partial sums, so documents outside the posting list keep their bits). A thread owns the same
+                // documents in every dense step: two dense tokens in a row need no barrier between them.
+                int prev = 0;   // 0: nothing written since the last barrier, 1: a posting slice, 2: a dense row
                 for (uint32_t t = 0; t < T; ++t) {
+                    const uint32_t dr = tokd[t];
+                    if (dr != BM_NOT_DENSE) {
+                        if (prev == 1) __syncthreads();
+                        prev = 2;
+                        in_tile += BM_SPARSE;   // always the full scan below
+                        const float4* __restrict__ row = reinterpret_cast<const float4*>(b.dense_rows + (size_t)dr * b.n_pad + base);
+                        float4* acc4 = reinterpret_cast<float4*>(acc);
+                        constexpr int NV = BM_TILE / (4 * BM_THREADS);
+                        float4 r[NV];
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) r[u] = __ldg(row + u * BM_THREADS + tid);
+#pragma unroll
+                        for (int u = 0; u < NV; ++u) {
+                            float4 a = acc4[u * BM_THREADS + tid];
+                            a.x = __fadd_rn(a.x, r[u].x); a.y = __fadd_rn(a.y, r[u].y); a.z = __fadd_rn(a.z, r[u].z); a.w = __fadd_rn(a.w, r[u].w);
+                            acc4[u * BM_THREADS + tid] = a;
+                        }
+                        continue;
+                    }
                     const uint64_t lo = bounds[t * (sbt + 1) + tile], hi = bounds[t * (sbt + 1) + tile + 1];
                     if (lo >= hi) continue;
+                    if (prev) __syncthreads();
+                    prev = 1;
                     in_tile += hi - lo;
                     // documents inside one token are distinct: plain shared-memory read-modify-write, 8 postings in flight per thread
                     // 32-bit index inside the slice: one address computation per 8 loads, the rest are immediate offsets
@@ -237,8 +270,8 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                         for (int u = 0; u < 7; ++u)
                             if (d[u] != 0xFFFFFFFFu) acc[d[u] - base] = __fadd_rn(acc[d[u] - base], sc[u]);
                     }
-                    __syncthreads();
                 }
+                if (prev) __syncthreads();
 #endif
                 if (in_tile == 0) continue;
                 // ---- BM25 score of the vector candidates that live in this tile (bm25.rs:160) ----
@@ -490,6 +523,57 @@ void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* 
 }
 
 int bm25_query_ctas_per_sm() { return LEANN_BM_MINB; }
+
+namespace {
+__global__ void dense_of_fill_kernel(uint32_t* __restrict__ dense_of, uint32_t n_terms) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_terms) dense_of[i] = BM_NOT_DENSE;
+}
+// one launch per dense term: row[doc] = score of the term's posting for doc (the rest of the row stays 0.0f)
+__global__ void dense_row_scatter_kernel(Bm25Dev b, uint32_t term, float* __restrict__ row) {
+    const uint64_t p0 = b.term_off[term], p1 = b.term_off[term + 1];
+    for (uint64_t p = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += (uint64_t)gridDim.x * blockDim.x)
+        row[b.post_doc[p]] = b.post_score[p];
+}
+}  // namespace
+
+void bm25_build_dense_rows(leann_cuda_bm25* b) {
+    b->n_dense = 0;
+    const size_t n = b->host.num_docs, n_terms = b->host.term_off.empty() ? 0 : b->host.term_off.size() - 1;
+    double frac = 0.5;
+    if (const char* e = getenv("LEANN_CUDA_BM25_DENSE_FRAC")) frac = atof(e);
+    size_t max_rows = 64;
+    if (const char* e = getenv("LEANN_CUDA_BM25_DENSE_MAX")) max_rows = (size_t)std::max(0, atoi(e));
+    if (!(frac > 0.0) || n == 0 || n_terms == 0 || max_rows == 0) return;
+    const size_t n_pad = (n + BM_TILE - 1) / BM_TILE * BM_TILE;
+    size_t free_b = 0, total_b = 0;
+    LEANN_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    max_rows = std::min(max_rows, free_b / 8 / (n_pad * 4));
+    std::vector<std::pair<uint64_t, uint32_t>> cand;   // (df, term)
+    for (size_t t = 0; t < n_terms; ++t) {
+        const uint64_t df = b->host.term_off[t + 1] - b->host.term_off[t];
+        if ((double)df >= frac * (double)n) cand.emplace_back(df, (uint32_t)t);
+    }
+    std::sort(cand.begin(), cand.end(), [](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) {
+        return x.first != y.first ? x.first > y.first : x.second < y.second;
+    });
+    if (cand.size() > max_rows) cand.resize(max_rows);
+    if (cand.empty()) return;
+    LEANN_CUDA_CHECK(cudaMalloc(&b->d_dense_of, n_terms * 4));
+    LEANN_CUDA_CHECK(cudaMalloc(&b->d_dense_rows, cand.size() * n_pad * 4));
+    LEANN_CUDA_CHECK(cudaMemset(b->d_dense_rows, 0, cand.size() * n_pad * 4));
+    dense_of_fill_kernel<<<(unsigned)((n_terms + 255) / 256), 256>>>(b->d_dense_of, (uint32_t)n_terms);
+    b->n_pad = (uint32_t)n_pad;
+    const Bm25Dev v = b->view();
+    for (size_t r = 0; r < cand.size(); ++r) {
+        const uint32_t row = (uint32_t)r;
+        LEANN_CUDA_CHECK(cudaMemcpy(b->d_dense_of + cand[r].second, &row, 4, cudaMemcpyHostToDevice));
+        dense_row_scatter_kernel<<<592, 256>>>(v, cand[r].second, b->d_dense_rows + r * n_pad);
+    }
+    LEANN_CUDA_CHECK(cudaDeviceSynchronize());
+    LEANN_CUDA_CHECK(cudaGetLastError());
+    b->n_dense = (uint32_t)cand.size();
+}
 
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
                        int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,

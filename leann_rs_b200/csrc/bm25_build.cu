@@ -400,6 +400,7 @@ void bm25_build_device(const char* const* docs, const size_t* doc_bytes, size_t 
     b->d_term_off = d_term_off; sc.release(d_term_off);
     b->d_post_doc = d_post_doc; sc.release(d_post_doc);
     b->d_post_score = d_score; sc.release(d_score);
+    bm25_build_dense_rows(b);
 }
 
 }  // namespace leann

@@ -10,11 +10,20 @@ struct Bm25Dev {
     const uint64_t* term_off;  // [n_terms + 1]
     const uint32_t* post_doc;  // [n_postings] ascending inside a term
     const float* post_score;   // [n_postings] per-posting BM25 contribution (query independent)
+    // dense rows of the most frequent terms (K3d, bm25.cu): dense_of[term] = row or 0xFFFFFFFF; row r holds the term's
+    // per-posting score at [r * n_pad + doc] and 0.0f for documents outside its posting list
+    const uint32_t* dense_of = nullptr;   // [n_terms] or null
+    const float* dense_rows = nullptr;    // [n_dense][n_pad]
+    uint32_t n_pad = 0;                   // n_docs rounded up to whole accumulator tiles
 };
 
 void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
                        cudaStream_t s);
 size_t bm25_max_query_tokens();   // longest query (known tokens, duplicates included) the query kernel takes
+// Builds the dense rows of `b` from its postings (terms whose df * 8 B exceeds the row's 4 B per document, most frequent first,
+// bounded by LEANN_CUDA_BM25_DENSE_MAX rows, default 64, and an eighth of the free memory). LEANN_CUDA_BM25_DENSE_FRAC (default
+// 0.5) is the df / n_docs threshold; 0 disables the rows.
+void bm25_build_dense_rows(leann_cuda_bm25* b);
 int bm25_query_ctas_per_sm();   // resident CTAs per SM the query kernel is built for (persistent pool size)
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
                        int n_ctas, const uint64_t* cand_idx, const uint32_t* cand_cnt, uint32_t fk,
@@ -50,6 +59,9 @@ struct leann_cuda_bm25 {
     uint64_t* d_term_off = nullptr;
     uint32_t* d_post_doc = nullptr;
     float* d_post_score = nullptr;
+    uint32_t* d_dense_of = nullptr;   // see Bm25Dev
+    float* d_dense_rows = nullptr;
+    uint32_t n_dense = 0, n_pad = 0;
     // per-handle workspace
     mutable std::mutex mu;
     mutable float* d_acc = nullptr;   // [n_docs] dense score vector of score_query, zero between calls
@@ -61,5 +73,7 @@ struct leann_cuda_bm25 {
     mutable cudaEvent_t ev_join = nullptr;   // BM25 top-k kernel done (joins the vector search's stream in the hybrid path)
     mutable uint64_t last_postings = 0;
     mutable float last_kernel_ms = 0.0f;
-    leann::Bm25Dev view() const { return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_score}; }
+    leann::Bm25Dev view() const {
+        return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_score, n_dense ? d_dense_of : nullptr, d_dense_rows, n_pad};
+    }
 };

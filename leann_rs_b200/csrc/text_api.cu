@@ -349,6 +349,7 @@ int leann_cuda_bm25_build_sharded(const char* const* docs, const size_t* doc_byt
     });
 }
 size_t leann_cuda_bm25_len(const leann_cuda_bm25* b) { return b ? b->host.num_docs : 0; }
+size_t leann_cuda_bm25_dense_rows(const leann_cuda_bm25* b) { return b ? b->n_dense : 0; }
 int leann_cuda_bm25_stats(const leann_cuda_bm25* b, uint64_t* st, float* avg) {
     if (!b || !st) return LEANN_ERR_INVALID_ARG;
     st[0] = b->host.num_docs; st[1] = b->host.idf.size(); st[2] = b->host.n_postings; st[3] = b->host.total_tokens;
@@ -372,6 +373,7 @@ void leann_cuda_bm25_free(leann_cuda_bm25* b) {
     cudaGetDevice(&prev);
     cudaSetDevice(b->device);
     cudaFree(b->d_term_off); cudaFree(b->d_post_doc); cudaFree(b->d_post_score);
+    cudaFree(b->d_dense_of); cudaFree(b->d_dense_rows);
     cudaFree(b->d_acc); cudaFree(b->d_qcounter);
     if (b->ev0) { cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1); }
     if (b->ev_join) cudaEventDestroy(b->ev_join);

@@ -141,6 +141,10 @@ class Bm25Scorer:
     def __len__(self):
         return int(_core().lib().leann_cuda_bm25_len(self._h))
 
+    def dense_rows(self) -> int:
+        """Terms also kept as dense score rows (K3d); LEANN_CUDA_BM25_DENSE_FRAC / _MAX at build time."""
+        return int(_core().lib().leann_cuda_bm25_dense_rows(self._h))
+
     def stats(self) -> dict:
         st = (C.c_uint64 * 4)()
         avg = C.c_float()

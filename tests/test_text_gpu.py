@@ -86,6 +86,34 @@ def test_bm25_medium_corpus_bits_and_topk(pkg):
     assert "indexed tokens" in e.value.message
 
 
+def test_bm25_dense_rows_do_not_change_a_bit(pkg, monkeypatch):
+    """K3d: frequent terms are added to the accumulator tile from dense rows instead of posting slices. Whatever the
+    threshold (off, default, nearly every term, a row limit of 2), ids, score bits and counts are the same."""
+    docs, queries = _corpus(20000, 5)
+    queries += ["t0", "t0 t1", "t1 t0 t1", "t900 t0 t2 t901 t1", "t0 t1 t2 t3 t4 t5 t6 t7", "t2500", ""]
+    rng = np.random.default_rng(12)
+    queries += [" ".join(f"t{int(i)}" for i in rng.integers(0, 60, size=m)) for m in (40, 400)]
+    results, rows = [], []
+    for frac, mx in (("0", None), (None, None), ("0.002", "1000"), ("0.3", "2")):
+        if frac is None: monkeypatch.delenv("LEANN_CUDA_BM25_DENSE_FRAC", raising=False)
+        else: monkeypatch.setenv("LEANN_CUDA_BM25_DENSE_FRAC", frac)
+        if mx is None: monkeypatch.delenv("LEANN_CUDA_BM25_DENSE_MAX", raising=False)
+        else: monkeypatch.setenv("LEANN_CUDA_BM25_DENSE_MAX", mx)
+        sc = pkg.Bm25Scorer.build(docs)
+        rows.append(sc.dense_rows())
+        idx, scores, cnt = sc.search_batch(queries, 50)
+        results.append((idx.copy(), scores.view(np.uint32).copy(), cnt.copy()))
+    assert rows[0] == 0 and rows[1] >= 3 and rows[2] > rows[1] and rows[3] == 2, rows
+    for r in results[1:]:
+        for a, b in zip(results[0], r):
+            assert np.array_equal(a, b)
+    ref = T.Bm25Scorer(docs)
+    for i in (len(queries) - 9, len(queries) - 6, len(queries) - 2):
+        want = ref.search(queries[i], 50, fast=True)
+        assert results[1][0][i, :len(want)].tolist() == [d for d, _ in want]
+        assert results[1][1][i, :len(want)].tolist() == [int(np.float32(s).view(np.uint32)) for _, s in want]
+
+
 def _fixture_dir(tmp_path, orc, n=3000, d=64, missing=(), with_ids=True, seed=13):
     x, q = make_data(n, d, seed, nq=40)
     g = orc.Hnsw.build(x, M=8, ef_add=32, seed=seed)
