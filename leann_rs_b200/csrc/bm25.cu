@@ -107,7 +107,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
 
     auto prune = [&]() {  // all threads; keeps the K best keys and tightens the threshold
         __syncthreads();
-        uint32_t c = s_cnt;
+        uint32_t c = min(s_cnt, (uint32_t)BM_CAP);   // the optimistic scan may reserve past the end
         for (uint32_t i = c + tid; i < BM_CAP; i += BM_THREADS) buf[i] = ~0ull;
         block_sort_cap(buf);
         if (tid == 0) {
@@ -139,6 +139,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
         const uint32_t nc = cand_idx ? cand_cnt[q] : 0u;
         for (uint32_t j = tid; j < nc; j += BM_THREADS) cand_bm[(size_t)q * fk + j] = 0.0f;   // bm25.rs:160 unwrap_or(0.0) / untouched tiles
         my_pos = 0; my_min = 0xFFFFFFFFu;
+        bool zero_seen = false;   // block-uniform: some document of the corpus scores 0.0 (then bm25.rs:153's minimum is 0.0)
         for (uint32_t t = tid; t < T; t += BM_THREADS) tokd[t] = b.dense_of ? __ldg(b.dense_of + qtok_term[t0 + t]) : BM_NOT_DENSE;
         const uint32_t n_tiles = (b.n_docs + BM_TILE - 1) / BM_TILE;
         const uint32_t S = T ? max(1u, (uint32_t)BM_BOUNDS / T - 1u) : n_tiles;   // tiles per boundary table
@@ -225,7 +226,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     if (dr != BM_NOT_DENSE) {
                         if (prev == 1) __syncthreads();
                         prev = 2;
-                        in_tile += BM_SPARSE;   // always the full scan below
+                        in_tile += BM_TILE;   // an upper bound of the term's postings here: always the full scan below
                         const float4* __restrict__ row = reinterpret_cast<const float4*>(b.dense_rows + (size_t)dr * b.n_pad + base);
                         float4* acc4 = reinterpret_cast<float4*>(acc);
                         constexpr int NV = BM_TILE / (4 * BM_THREADS);
@@ -273,7 +274,10 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                 }
                 if (prev) __syncthreads();
 #endif
+                const uint32_t docs_here = min((uint32_t)BM_TILE, b.n_docs - base);
+                if (in_tile < (uint64_t)docs_here) zero_seen = true;   // fewer postings than documents: some document scores 0.0
                 if (in_tile == 0) continue;
+                const uint32_t c_before = s_cnt;   // nobody appends between the barrier above and the one below
                 // ---- BM25 score of the vector candidates that live in this tile (bm25.rs:160) ----
                 for (uint32_t j = tid; j < nc; j += BM_THREADS) {
                     const uint64_t idx = cand_idx[(size_t)q * fk + j];
@@ -298,22 +302,58 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     }
                 } else {
                     // ---- scan the tile: collect positives, clear the accumulator ----
-                    for (int it = 0; it < BM_TILE / (4 * BM_THREADS); ++it) {
-                        const uint32_t c = s_cnt;
-                        __syncthreads();   // everyone has read the count before anyone appends: the decision is uniform
-                        if (c > BM_CAP - 4 * BM_THREADS) prune();
+                    // Optimistic: no barrier inside the pass. A float4 whose keys do not fit the candidate buffer any more is left
+                    // in place (not cleared, not counted); the pass then ends with a prune and runs again over what is left. Once
+                    // the threshold is established a tile appends a handful of keys and one pass is all there is.
+                    if (c_before > BM_CAP / 2) prune();
+                    float4* acc4 = reinterpret_cast<float4*>(acc);
+                    constexpr int NV = BM_TILE / (4 * BM_THREADS);
+                    for (int pass = 0;; ++pass) {
                         const unsigned long long thr = s_thr;
-                        const int i4 = it * BM_THREADS + tid;
-                        float4 v = reinterpret_cast<float4*>(acc)[i4];
-                        if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
-                            reinterpret_cast<float4*>(acc)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        // smallest score that can still enter: v >= thr_f is necessary for key <= thr, and for v > 0 (bm25.rs:115)
+                        const float thr_f = thr == ~0ull ? __uint_as_float(1u) : unorder_f32(~(uint32_t)(thr >> 32));
+                        const bool track = !zero_seen;   // positives / minimum / zero detection only until a zero score was seen
+                        bool over = false, zero = false;
+#pragma unroll 2
+                        for (int it = 0; it < NV; ++it) {
+                            const int i4 = it * BM_THREADS + tid;
+                            const float4 v = acc4[i4];
                             const uint32_t doc = base + (uint32_t)i4 * 4u;
-                            if (v.x != 0.0f) collect(doc, v.x, thr);
-                            if (v.y != 0.0f) collect(doc + 1, v.y, thr);
-                            if (v.z != 0.0f) collect(doc + 2, v.z, thr);
-                            if (v.w != 0.0f) collect(doc + 3, v.w, thr);
+                            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                            if (m >= thr_f) {
+                                const float vv[4] = {v.x, v.y, v.z, v.w};
+                                unsigned long long key[4];
+                                uint32_t k = 0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    key[j] = ((unsigned long long)(~order_f32(vv[j])) << 32) | (doc + j);
+                                    if (vv[j] > 0.0f && key[j] <= thr) ++k; else key[j] = ~0ull;
+                                }
+                                if (k) {
+                                    uint32_t pos = atomicAdd(&s_cnt, k);
+                                    if (pos + k > BM_CAP) {   // does not fit: fill what this reservation holds of the buffer, come back after a prune
+                                        for (; pos < BM_CAP; ++pos) buf[pos] = ~0ull;
+                                        over = true;
+                                        continue;
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) if (key[j] != ~0ull) buf[pos++] = key[j];
+                                }
+                            }
+                            if (m != 0.0f) acc4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (track) {
+                                my_pos += (v.x > 0.0f) + (v.y > 0.0f) + (v.z > 0.0f) + (v.w > 0.0f);
+                                const float mn4 = fminf(fminf(v.x > 0.0f ? v.x : CUDART_INF_F, v.y > 0.0f ? v.y : CUDART_INF_F),
+                                                        fminf(v.z > 0.0f ? v.z : CUDART_INF_F, v.w > 0.0f ? v.w : CUDART_INF_F));
+                                if (mn4 < CUDART_INF_F) { const uint32_t o = order_f32(mn4); my_min = o < my_min ? o : my_min; }
+                                if (pass == 0)   // cleared entries of an earlier pass are not zero scores
+                                    zero |= (v.x == 0.0f && doc < b.n_docs) || (v.y == 0.0f && doc + 1 < b.n_docs) ||
+                                            (v.z == 0.0f && doc + 2 < b.n_docs) || (v.w == 0.0f && doc + 3 < b.n_docs);
+                            }
                         }
-                        __syncthreads();
+                        if (track && pass == 0 && __syncthreads_or(zero)) zero_seen = true;
+                        if (!__syncthreads_or(over)) break;
+                        prune();
                     }
                 }
             }
@@ -337,7 +377,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
             top_cnt[q] = cnt;
             // bm25.rs:152-153: max / min over the ENTIRE dense score vector (zeros included)
             float mx = cnt ? unorder_f32(~(uint32_t)(buf[0] >> 32)) : 0.0f;
-            float mn = (s_pos < b.n_docs) ? 0.0f : unorder_f32(s_minbits);
+            float mn = (zero_seen || s_pos < b.n_docs) ? 0.0f : unorder_f32(s_minbits);
             if (b.n_docs == 0) { mx = -CUDART_INF_F; mn = CUDART_INF_F; }
             bmax[q] = mx;
             bmin[q] = mn;

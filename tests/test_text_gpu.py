@@ -114,6 +114,30 @@ def test_bm25_dense_rows_do_not_change_a_bit(pkg, monkeypatch):
         assert results[1][1][i, :len(want)].tolist() == [int(np.float32(s).view(np.uint32)) for _, s in want]
 
 
+def test_bm25_min_max_of_the_dense_vector(pkg, monkeypatch):
+    """bm25.rs:152-153 takes max / min over the whole dense score vector. The kernel never materialises it: the minimum is
+    0.0 as soon as one document scores 0.0 and the smallest positive score only when every document matched — with and
+    without dense rows, over several tiles with a partial last one."""
+    rng = np.random.default_rng(21)
+    n = 20000
+    docs = [" ".join(["every"] * int(rng.integers(1, 4)) + [f"x{int(v)}" for v in rng.integers(0, 50, size=int(rng.integers(3, 30)))]) for _ in range(n)]
+    docs[n - 1] = "every tail"
+    queries = ["every", "every x1", "x1 every x2 every", "x1", "x1 x2 x3 x4 x5 x6 x7 x8 x9 x10 x11 x12", "tail", "nothing here", "tail every"]
+    ref = T.Bm25Scorer(docs)
+    dense = [ref.score_query_fast(q) for q in queries]
+    for frac in ("0", "0.5", "0.05"):
+        monkeypatch.setenv("LEANN_CUDA_BM25_DENSE_FRAC", frac)
+        sc = pkg.Bm25Scorer.build(docs)
+        assert (sc.dense_rows() > 0) == (frac != "0")
+        ti, ts, tc, _, bx, bn = sc.search_shard(queries, 20, 0)
+        for i, q in enumerate(queries):
+            assert bx[i].view(np.uint32) == dense[i].max().view(np.uint32), (frac, q)
+            assert bn[i].view(np.uint32) == dense[i].min().view(np.uint32), (frac, q)
+            want = ref.search(q, 20, fast=True)
+            assert int(tc[i]) == len(want) and ti[i, :len(want)].tolist() == [d for d, _ in want], (frac, q)
+    assert dense[0].min() > 0 and dense[3].min() == 0
+
+
 def _fixture_dir(tmp_path, orc, n=3000, d=64, missing=(), with_ids=True, seed=13):
     x, q = make_data(n, d, seed, nq=40)
     g = orc.Hnsw.build(x, M=8, ef_add=32, seed=seed)
