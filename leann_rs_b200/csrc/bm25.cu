@@ -39,9 +39,6 @@ namespace {
 #ifndef LEANN_BM_MINB
 #define LEANN_BM_MINB 3
 #endif
-#ifndef LEANN_BM_PIPE
-#define LEANN_BM_PIPE 0   // software-pipelined accumulation: measured 33.4 ms vs 28.8 ms per 10k queries (profiles/r2_k3_variants.json): off
-#endif
 constexpr int BM_THREADS = LEANN_BM_THREADS;
 constexpr int BM_TILE = LEANN_BM_TILE;     // documents per shared-memory accumulator tile (32 KB of f32)
 constexpr int BM_CAP = LEANN_BM_CAP;       // candidate keys held in shared memory between prunes
@@ -89,6 +86,15 @@ __device__ void block_sort_cap(unsigned long long* keys) {
 // of every posting list; the slice boundaries come from one parallel binary search per query), then the tile is
 // scanned for positives, which feed the running top-K, the positive count and the min/max of hybrid_rerank.
 // Every posting is read once, coalesced; no global read-modify-write.
+//
+// K3d, dense rows: a token whose term has a dense row adds the row's tile float4 by float4 (x + 0.0f == x for the
+// non-negative partial sums, so documents outside the posting list keep their bits); a thread owns the same documents in
+// every dense step and in the scan, so dense steps need no barrier between them. Three consequences are used:
+//   * per document the first two contributions commute exactly (both start from +0.0f): when token 1 is dense and token 0
+//     is not, they are processed in the order 1, 0 so that the tile starts with a dense row;
+//   * a tile that starts with a dense row is initialised by a plain store of the row: the accumulator is never cleared
+//     between the tiles of such a query (once at its end);
+//   * when the last token is dense the scan runs on the sums while they are still in registers.
 __global__ void __launch_bounds__(BM_THREADS, LEANN_BM_MINB)
 bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32_t* __restrict__ qtok_term,
                   uint32_t nq, uint32_t K, const uint64_t* __restrict__ cand_idx,
@@ -96,10 +102,12 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                   uint64_t* __restrict__ top_idx, float* __restrict__ top_score, uint32_t* __restrict__ top_cnt,
                   float* __restrict__ bmax, float* __restrict__ bmin, uint32_t* __restrict__ qcounter) {
     extern __shared__ __align__(16) unsigned char bm_smem[];
-    float* acc = reinterpret_cast<float*>(bm_smem);                                                  // [BM_TILE], zero between tiles
+    float* acc = reinterpret_cast<float*>(bm_smem);                                                  // [BM_TILE]
     unsigned long long* buf = reinterpret_cast<unsigned long long*>(bm_smem + (size_t)BM_TILE * 4);   // [BM_CAP]
     unsigned long long* bounds = buf + BM_CAP;                                                         // [T][S + 1] absolute posting offsets
     uint32_t* tokd = reinterpret_cast<uint32_t*>(bounds + BM_BOUNDS);                                  // [T] dense row of the token, or BM_NOT_DENSE
+    float4* acc4 = reinterpret_cast<float4*>(acc);
+    constexpr int NV = BM_TILE / (4 * BM_THREADS);   // float4 per thread and tile
     __shared__ uint32_t s_cnt, s_q, s_pos, s_minbits;
     __shared__ unsigned long long s_thr;
     const int tid = threadIdx.x;
@@ -107,7 +115,7 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
 
     auto prune = [&]() {  // all threads; keeps the K best keys and tightens the threshold
         __syncthreads();
-        uint32_t c = min(s_cnt, (uint32_t)BM_CAP);   // the optimistic scan may reserve past the end
+        uint32_t c = min(s_cnt, (uint32_t)BM_CAP);   // the scan may reserve past the end
         for (uint32_t i = c + tid; i < BM_CAP; i += BM_THREADS) buf[i] = ~0ull;
         block_sort_cap(buf);
         if (tid == 0) {
@@ -140,9 +148,52 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
         for (uint32_t j = tid; j < nc; j += BM_THREADS) cand_bm[(size_t)q * fk + j] = 0.0f;   // bm25.rs:160 unwrap_or(0.0) / untouched tiles
         my_pos = 0; my_min = 0xFFFFFFFFu;
         bool zero_seen = false;   // block-uniform: some document of the corpus scores 0.0 (then bm25.rs:153's minimum is 0.0)
+        bool zero = false;        // this thread saw one in the current tile
+        bool crowded = false;     // this thread's reservation went past half of the candidate buffer: prune before the next tile
         for (uint32_t t = tid; t < T; t += BM_THREADS) tokd[t] = b.dense_of ? __ldg(b.dense_of + qtok_term[t0 + t]) : BM_NOT_DENSE;
+        __syncthreads();
+        // processing order of the tokens: 1, 0, 2, 3, .. when that puts a dense row first, else 0, 1, 2, ..
+        const bool swap01 = T >= 2 && tokd[0] == BM_NOT_DENSE && tokd[1] != BM_NOT_DENSE;
+        const bool first_dense = T && tokd[swap01 ? 1 : 0] != BM_NOT_DENSE;   // the accumulator is initialised by a store, never cleared
+        const bool fuse_last = T && nc == 0 && tokd[(swap01 && T == 2) ? 0 : T - 1] != BM_NOT_DENSE;   // scan from registers
         const uint32_t n_tiles = (b.n_docs + BM_TILE - 1) / BM_TILE;
         const uint32_t S = T ? max(1u, (uint32_t)BM_BOUNDS / T - 1u) : n_tiles;   // tiles per boundary table
+
+        // One float4 of finished sums: candidates that can still enter the top-K are appended, the statistics of bm25.rs:152-153
+        // are kept while no zero score was seen. false: the candidate buffer is full (nothing was consumed; come back after a prune).
+        auto consume = [&](const float4 v, const uint32_t doc, const unsigned long long thr, const float thr_f) -> bool {
+            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            if (m >= thr_f) {   // v >= thr_f is necessary for key <= thr, and for v > 0 (bm25.rs:115)
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                unsigned long long key[4];
+                uint32_t k = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    key[j] = ((unsigned long long)(~order_f32(vv[j])) << 32) | (doc + j);
+                    if (vv[j] > 0.0f && key[j] <= thr) ++k; else key[j] = ~0ull;
+                }
+                if (k) {
+                    uint32_t pos = atomicAdd(&s_cnt, k);
+                    if (pos + k > BM_CAP) {   // fill what this reservation holds of the buffer
+                        for (; pos < BM_CAP; ++pos) buf[pos] = ~0ull;
+                        return false;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (key[j] != ~0ull) buf[pos++] = key[j];
+                    crowded |= pos > BM_CAP / 2;
+                }
+            }
+            if (!zero_seen) {
+                my_pos += (v.x > 0.0f) + (v.y > 0.0f) + (v.z > 0.0f) + (v.w > 0.0f);
+                const float mn4 = fminf(fminf(v.x > 0.0f ? v.x : CUDART_INF_F, v.y > 0.0f ? v.y : CUDART_INF_F),
+                                        fminf(v.z > 0.0f ? v.z : CUDART_INF_F, v.w > 0.0f ? v.w : CUDART_INF_F));
+                if (mn4 < CUDART_INF_F) { const uint32_t o = order_f32(mn4); my_min = o < my_min ? o : my_min; }
+                zero |= (v.x == 0.0f && doc < b.n_docs) || (v.y == 0.0f && doc + 1 < b.n_docs) ||
+                        (v.z == 0.0f && doc + 2 < b.n_docs) || (v.w == 0.0f && doc + 3 < b.n_docs);
+            }
+            return true;
+        };
+
         for (uint32_t sb0 = 0; sb0 < n_tiles && T; sb0 += S) {
             const uint32_t sbt = min(S, n_tiles - sb0);
             // ---- slice boundaries: lower_bound(first doc of tile) in every token's posting list ----
@@ -165,79 +216,48 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                 const uint32_t base = (sb0 + tile) * BM_TILE;
                 // ---- accumulate, tokens in query order (duplicates counted again, bm25.rs:81) ----
                 uint64_t in_tile = 0;
-#if LEANN_BM_PIPE
-                // (A/B variant, off by default: slower than the plain loop below on B200 — the predicated loads and the register
-                // hand-over cost more than the overlapped latency buys at 24 resident warps per SM.)
-                // Software pipeline over the (token, chunk) sequence of this tile: the 16 loads of chunk c + 1 are issued before the
-                // shared-memory read-modify-writes of chunk c and before the barrier that separates two tokens, so that the load
-                // latency of every slice (and the barrier) overlaps the accumulation of the previous one. The sequence is the same
-                // for all threads of the block (slice bounds are block-uniform); inside one token every posting is a distinct
-                // document, so only the token boundary needs the barrier.
-                {
-                    constexpr uint32_t CH = 8u * BM_THREADS;
-                    uint32_t t = 0;
-                    auto slice = [&](uint32_t tt, const uint32_t*& pd, const float*& ps) -> uint32_t {
-                        const uint64_t lo = bounds[tt * (sbt + 1) + tile], hi = bounds[tt * (sbt + 1) + tile + 1];
-                        pd = b.post_doc + lo; ps = b.post_score + lo;
-                        return hi > lo ? (uint32_t)(hi - lo) : 0u;
-                    };
-                    auto next_token = [&](uint32_t tt, const uint32_t*& pd, const float*& ps, uint32_t& len) {   // first non-empty slice at or after tt
-                        len = 0;
-                        while (tt < T && (len = slice(tt, pd, ps)) == 0) ++tt;
-                        return tt;
-                    };
-                    auto load = [&](const uint32_t* pd, const float* ps, uint32_t len, uint32_t i0, uint32_t (&d)[8], float (&sc)[8]) {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const uint32_t i = i0 + tid + (uint32_t)u * BM_THREADS;
-                            const bool ok = i < len;
-                            d[u] = ok ? __ldg(pd + i) : 0xFFFFFFFFu;
-                            sc[u] = ok ? __ldg(ps + i) : 0.0f;
-                        }
-                    };
-                    const uint32_t* pd; const float* ps; uint32_t len, i0 = 0;
-                    t = next_token(0, pd, ps, len);
-                    uint32_t dc[8]; float scc[8];
-                    if (t < T) load(pd, ps, len, 0, dc, scc);
-                    while (t < T) {
-                        if (i0 == 0) in_tile += len;
-                        // where is the next chunk?
-                        uint32_t t2 = t, i2 = i0 + CH, len2 = len;
-                        const uint32_t* pd2 = pd; const float* ps2 = ps;
-                        if (i2 >= len) { t2 = next_token(t + 1, pd2, ps2, len2); i2 = 0; }
-                        uint32_t dn[8]; float scn[8];
-                        if (t2 < T) load(pd2, ps2, len2, i2, dn, scn);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (dc[u] != 0xFFFFFFFFu) acc[dc[u] - base] = __fadd_rn(acc[dc[u] - base], scc[u]);
-                        if (t2 != t) __syncthreads();
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { dc[u] = dn[u]; scc[u] = scn[u]; }
-                        t = t2; i0 = i2; len = len2; pd = pd2; ps = ps2;
-                    }
-                }
-#else
-                // K3d: a token whose term has a dense row adds the row's tile to the accumulator, float4 by float4 (x + 0.0f == x for
-                // the non-negative partial sums, so documents outside the posting list keep their bits). A thread owns the same
-                // documents in every dense step: two dense tokens in a row need no barrier between them.
-                int prev = 0;   // 0: nothing written since the last barrier, 1: a posting slice, 2: a dense row
-                for (uint32_t t = 0; t < T; ++t) {
+                int prev = 0;         // 0: nothing written since the last barrier, 1: a posting slice, 2: a dense row
+                int resume = 0;       // first float4 of this thread the scan has not consumed yet
+                unsigned long long thr = s_thr;   // stable: written by prune only, between barriers
+                float thr_f = thr == ~0ull ? __uint_as_float(1u) : unorder_f32(~(uint32_t)(thr >> 32));
+                for (uint32_t p = 0; p < T; ++p) {
+                    const uint32_t t = (swap01 && p < 2) ? 1u - p : p;
                     const uint32_t dr = tokd[t];
                     if (dr != BM_NOT_DENSE) {
                         if (prev == 1) __syncthreads();
                         prev = 2;
                         in_tile += BM_TILE;   // an upper bound of the term's postings here: always the full scan below
                         const float4* __restrict__ row = reinterpret_cast<const float4*>(b.dense_rows + (size_t)dr * b.n_pad + base);
-                        float4* acc4 = reinterpret_cast<float4*>(acc);
-                        constexpr int NV = BM_TILE / (4 * BM_THREADS);
                         float4 r[NV];
 #pragma unroll
                         for (int u = 0; u < NV; ++u) r[u] = __ldg(row + u * BM_THREADS + tid);
+                        const bool init = p == 0;   // first_dense: whatever the accumulator holds is stale
+                        if (!(fuse_last && p == T - 1)) {
 #pragma unroll
-                        for (int u = 0; u < NV; ++u) {
-                            float4 a = acc4[u * BM_THREADS + tid];
-                            a.x = __fadd_rn(a.x, r[u].x); a.y = __fadd_rn(a.y, r[u].y); a.z = __fadd_rn(a.z, r[u].z); a.w = __fadd_rn(a.w, r[u].w);
-                            acc4[u * BM_THREADS + tid] = a;
+                            for (int u = 0; u < NV; ++u) {
+                                float4 a = r[u];
+                                if (!init) {
+                                    const float4 o = acc4[u * BM_THREADS + tid];
+                                    a.x = __fadd_rn(o.x, a.x); a.y = __fadd_rn(o.y, a.y); a.z = __fadd_rn(o.z, a.z); a.w = __fadd_rn(o.w, a.w);
+                                }
+                                acc4[u * BM_THREADS + tid] = a;
+                            }
+                        } else {
+                            // last token: the sums are consumed from registers; what does not fit the candidate buffer any more
+                            // is parked in the accumulator for the scan below
+                            resume = NV;
+#pragma unroll
+                            for (int u = 0; u < NV; ++u) {
+                                float4 a = r[u];
+                                const int i4 = u * BM_THREADS + tid;
+                                if (!init) {
+                                    const float4 o = acc4[i4];
+                                    a.x = __fadd_rn(o.x, a.x); a.y = __fadd_rn(o.y, a.y); a.z = __fadd_rn(o.z, a.z); a.w = __fadd_rn(o.w, a.w);
+                                }
+                                if (resume == NV && !consume(a, base + (uint32_t)i4 * 4u, thr, thr_f)) resume = u;
+                                if (resume != NV) acc4[i4] = a;
+                                else if (!first_dense) acc4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
                         }
                         continue;
                     }
@@ -272,18 +292,19 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                             if (d[u] != 0xFFFFFFFFu) acc[d[u] - base] = __fadd_rn(acc[d[u] - base], sc[u]);
                     }
                 }
-                if (prev) __syncthreads();
-#endif
+                const bool fused = fuse_last;   // (a dense last token always runs: the scan from registers happened)
+                if (prev == 1 || (prev == 2 && !fused)) __syncthreads();
                 const uint32_t docs_here = min((uint32_t)BM_TILE, b.n_docs - base);
                 if (in_tile < (uint64_t)docs_here) zero_seen = true;   // fewer postings than documents: some document scores 0.0
                 if (in_tile == 0) continue;
-                const uint32_t c_before = s_cnt;   // nobody appends between the barrier above and the one below
                 // ---- BM25 score of the vector candidates that live in this tile (bm25.rs:160) ----
-                for (uint32_t j = tid; j < nc; j += BM_THREADS) {
-                    const uint64_t idx = cand_idx[(size_t)q * fk + j];
-                    if (idx >= base && idx < (uint64_t)base + BM_TILE && idx < b.n_docs) cand_bm[(size_t)q * fk + j] = acc[idx - base];
+                if (nc) {
+                    for (uint32_t j = tid; j < nc; j += BM_THREADS) {
+                        const uint64_t idx = cand_idx[(size_t)q * fk + j];
+                        if (idx >= base && idx < (uint64_t)base + BM_TILE && idx < b.n_docs) cand_bm[(size_t)q * fk + j] = acc[idx - base];
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 if (in_tile < (uint64_t)BM_SPARSE) {
                     // ---- few postings: collect by re-walking them (the first visit of a document takes and clears its score) ----
                     for (uint32_t t = 0; t < T; ++t) {
@@ -292,71 +313,47 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                         const uint32_t c = s_cnt;
                         __syncthreads();   // everyone has read the count before anyone appends: the decision is uniform
                         if (c > BM_CAP - BM_SPARSE) prune();
-                        const unsigned long long thr = s_thr;
+                        const unsigned long long thr2 = s_thr;
                         for (uint64_t p = lo + tid; p < hi; p += BM_THREADS) {
                             const uint32_t doc = __ldg(b.post_doc + p);
                             const float v = acc[doc - base];
-                            if (v != 0.0f) { acc[doc - base] = 0.0f; collect(doc, v, thr); }
+                            if (v != 0.0f) { acc[doc - base] = 0.0f; collect(doc, v, thr2); }
                         }
                         __syncthreads();
                     }
                 } else {
-                    // ---- scan the tile: collect positives, clear the accumulator ----
-                    // Optimistic: no barrier inside the pass. A float4 whose keys do not fit the candidate buffer any more is left
-                    // in place (not cleared, not counted); the pass then ends with a prune and runs again over what is left. Once
-                    // the threshold is established a tile appends a handful of keys and one pass is all there is.
-                    if (c_before > BM_CAP / 2) prune();
-                    float4* acc4 = reinterpret_cast<float4*>(acc);
-                    constexpr int NV = BM_TILE / (4 * BM_THREADS);
+                    // ---- scan the tile: collect positives, clear the accumulator (unless the next tile overwrites it anyway) ----
+                    // Optimistic: no barrier inside a pass. A thread stops at the first float4 whose keys do not fit the candidate
+                    // buffer; the pass ends with a vote, a prune, and everyone resumes where they stopped. Once the threshold is
+                    // established a tile appends a handful of keys and one pass is all there is.
                     for (int pass = 0;; ++pass) {
-                        const unsigned long long thr = s_thr;
-                        // smallest score that can still enter: v >= thr_f is necessary for key <= thr, and for v > 0 (bm25.rs:115)
-                        const float thr_f = thr == ~0ull ? __uint_as_float(1u) : unorder_f32(~(uint32_t)(thr >> 32));
-                        const bool track = !zero_seen;   // positives / minimum / zero detection only until a zero score was seen
-                        bool over = false, zero = false;
-#pragma unroll 2
-                        for (int it = 0; it < NV; ++it) {
-                            const int i4 = it * BM_THREADS + tid;
-                            const float4 v = acc4[i4];
-                            const uint32_t doc = base + (uint32_t)i4 * 4u;
-                            const float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-                            if (m >= thr_f) {
-                                const float vv[4] = {v.x, v.y, v.z, v.w};
-                                unsigned long long key[4];
-                                uint32_t k = 0;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    key[j] = ((unsigned long long)(~order_f32(vv[j])) << 32) | (doc + j);
-                                    if (vv[j] > 0.0f && key[j] <= thr) ++k; else key[j] = ~0ull;
-                                }
-                                if (k) {
-                                    uint32_t pos = atomicAdd(&s_cnt, k);
-                                    if (pos + k > BM_CAP) {   // does not fit: fill what this reservation holds of the buffer, come back after a prune
-                                        for (; pos < BM_CAP; ++pos) buf[pos] = ~0ull;
-                                        over = true;
-                                        continue;
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) if (key[j] != ~0ull) buf[pos++] = key[j];
-                                }
-                            }
-                            if (m != 0.0f) acc4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (track) {
-                                my_pos += (v.x > 0.0f) + (v.y > 0.0f) + (v.z > 0.0f) + (v.w > 0.0f);
-                                const float mn4 = fminf(fminf(v.x > 0.0f ? v.x : CUDART_INF_F, v.y > 0.0f ? v.y : CUDART_INF_F),
-                                                        fminf(v.z > 0.0f ? v.z : CUDART_INF_F, v.w > 0.0f ? v.w : CUDART_INF_F));
-                                if (mn4 < CUDART_INF_F) { const uint32_t o = order_f32(mn4); my_min = o < my_min ? o : my_min; }
-                                if (pass == 0)   // cleared entries of an earlier pass are not zero scores
-                                    zero |= (v.x == 0.0f && doc < b.n_docs) || (v.y == 0.0f && doc + 1 < b.n_docs) ||
-                                            (v.z == 0.0f && doc + 2 < b.n_docs) || (v.w == 0.0f && doc + 3 < b.n_docs);
+                        if (!(fused && pass == 0)) {
+                            int it = resume;
+                            resume = NV;
+                            for (; it < NV; ++it) {
+                                const int i4 = it * BM_THREADS + tid;
+                                const float4 v = acc4[i4];
+                                if (!consume(v, base + (uint32_t)i4 * 4u, thr, thr_f)) { resume = it; break; }
+                                if (!first_dense && fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) != 0.0f) acc4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
                         }
-                        if (track && pass == 0 && __syncthreads_or(zero)) zero_seen = true;
-                        if (!__syncthreads_or(over)) break;
+                        if (pass == 0 && !zero_seen && __syncthreads_or(zero)) zero_seen = true;
+                        zero = false;
+                        // one vote in the common case; the thread that made the last reservation knows how full the buffer is
+                        if (!__syncthreads_or((resume != NV) | crowded)) break;
                         prune();
+                        crowded = false;
+                        thr = s_thr;
+                        thr_f = thr == ~0ull ? __uint_as_float(1u) : unorder_f32(~(uint32_t)(thr >> 32));
+                        if (!__syncthreads_or(resume != NV)) break;
                     }
                 }
             }
+        }
+        if (first_dense) {   // leave the accumulator zero for the next query
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < NV; ++u) acc4[u * BM_THREADS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         atomicAdd(&s_pos, my_pos);
         atomicMin(&s_minbits, my_min);

@@ -102,7 +102,8 @@ def test_bm25_dense_rows_do_not_change_a_bit(pkg, monkeypatch):
         sc = pkg.Bm25Scorer.build(docs)
         rows.append(sc.dense_rows())
         idx, scores, cnt = sc.search_batch(queries, 50)
-        results.append((idx.copy(), scores.view(np.uint32).copy(), cnt.copy()))
+        big = sc.search_batch(queries[-12:], 1000)   # many candidates: the scan's full-buffer / resume path
+        results.append((idx.copy(), scores.view(np.uint32).copy(), cnt.copy(), big[0].copy(), big[1].view(np.uint32).copy(), big[2].copy()))
     assert rows[0] == 0 and rows[1] >= 3 and rows[2] > rows[1] and rows[3] == 2, rows
     for r in results[1:]:
         for a, b in zip(results[0], r):
