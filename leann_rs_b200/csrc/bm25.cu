@@ -65,8 +65,7 @@ __global__ void bm25_token_dense_kernel(Bm25Dev b, uint32_t term, float* __restr
     scores[doc] = __fadd_rn(scores[doc], b.post_score[p]);
 }
 
-__device__ void block_sort_cap(unsigned long long* keys) {
-    const uint32_t n = BM_CAP;
+__device__ void block_sort_n(unsigned long long* keys, const uint32_t n) {   // n: power of two, ascending
     for (uint32_t size = 2; size <= n; size <<= 1)
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
@@ -113,16 +112,55 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
     const int tid = threadIdx.x;
     for (int i = tid; i < BM_TILE; i += BM_THREADS) acc[i] = 0.0f;
 
-    auto prune = [&]() {  // all threads; keeps the K best keys and tightens the threshold
+    __shared__ uint32_t s_hist[256], s_sel_bin, s_sel_rem;
+    // All threads; keeps the K best (smallest) keys, in no particular order, and tightens the threshold to the K-th best.
+    // Radix select, one byte per round from the top: histogram of the keys that still match the prefix, warp 0 finds the bin
+    // the K-th key falls in. 24 barriers instead of the 66 stages of a full sort of the buffer (this ran ~6 times per query and
+    // was 10 % of the kernel's stall samples).
+    auto prune = [&]() {
         __syncthreads();
-        uint32_t c = min(s_cnt, (uint32_t)BM_CAP);   // the scan may reserve past the end
-        for (uint32_t i = c + tid; i < BM_CAP; i += BM_THREADS) buf[i] = ~0ull;
-        block_sort_cap(buf);
-        if (tid == 0) {
-            uint32_t keep = c < K ? c : K;
-            s_cnt = keep;
-            if (keep == K) s_thr = buf[K - 1];
+        const uint32_t c = min(s_cnt, (uint32_t)BM_CAP);   // the scan may reserve past the end
+        if (c <= K) return;                                // uniform; nothing to drop, the threshold stays
+        constexpr int KPT = BM_CAP / BM_THREADS;
+        unsigned long long mine[KPT];
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) { const uint32_t i = tid + u * BM_THREADS; mine[u] = i < c ? buf[i] : ~0ull; }
+        unsigned long long prefix = 0;
+        uint32_t remaining = K;
+        for (int byte = 7; byte >= 0; --byte) {
+            const int sh = byte * 8;
+            for (int i = tid; i < 256; i += BM_THREADS) s_hist[i] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < KPT; ++u)
+                if (byte == 7 || (mine[u] >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&s_hist[(uint32_t)(mine[u] >> sh) & 255u], 1u);
+            __syncthreads();
+            if (tid < 32) {
+                uint32_t cnt8[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { cnt8[j] = s_hist[tid * 8 + j]; sum += cnt8[j]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off); if (tid >= off) incl += v; }
+                const uint32_t excl = incl - sum;
+                if (excl < remaining && remaining <= incl) {
+                    uint32_t r = remaining - excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (r != 0 && r <= cnt8[j]) { s_sel_bin = tid * 8 + j; s_sel_rem = r; r = 0; }
+                        else if (r != 0) r -= cnt8[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= (unsigned long long)s_sel_bin << sh;
+            remaining = s_sel_rem;
         }
+        // prefix is the K-th smallest key (keys are distinct: the document is part of them)
+        if (tid == 0) { s_cnt = 0; s_thr = prefix; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) if (mine[u] <= prefix) buf[atomicAdd(&s_cnt, 1u)] = mine[u];
         __syncthreads();
     };
     uint32_t my_pos = 0, my_min = 0xFFFFFFFFu;
@@ -224,13 +262,13 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     const uint32_t t = (swap01 && p < 2) ? 1u - p : p;
                     const uint32_t dr = tokd[t];
                     if (dr != BM_NOT_DENSE) {
-                        if (prev == 1) __syncthreads();
-                        prev = 2;
                         in_tile += BM_TILE;   // an upper bound of the term's postings here: always the full scan below
                         const float4* __restrict__ row = reinterpret_cast<const float4*>(b.dense_rows + (size_t)dr * b.n_pad + base);
                         float4 r[NV];
 #pragma unroll
                         for (int u = 0; u < NV; ++u) r[u] = __ldg(row + u * BM_THREADS + tid);
+                        if (prev == 1) __syncthreads();   // after the loads are issued: the wait overlaps their latency
+                        prev = 2;
                         const bool init = p == 0;   // first_dense: whatever the accumulator holds is stale
                         if (!(fuse_last && p == T - 1)) {
 #pragma unroll
@@ -263,34 +301,28 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
                     }
                     const uint64_t lo = bounds[t * (sbt + 1) + tile], hi = bounds[t * (sbt + 1) + tile + 1];
                     if (lo >= hi) continue;
-                    if (prev) __syncthreads();
-                    prev = 1;
                     in_tile += hi - lo;
-                    // documents inside one token are distinct: plain shared-memory read-modify-write, 8 postings in flight per thread
-                    // 32-bit index inside the slice: one address computation per 8 loads, the rest are immediate offsets
+                    // documents inside one token are distinct: plain shared-memory read-modify-write, 8 postings in flight per thread.
+                    // The loads of the first chunk are issued BEFORE the barrier that ends the previous token's writes: they do not
+                    // depend on it, and the wait for the slowest warp overlaps their latency.
                     const uint32_t* __restrict__ pd = b.post_doc + lo;
                     const float* __restrict__ ps = b.post_score + lo;
                     const uint32_t len = (uint32_t)(hi - lo);
-                    uint32_t i = tid;
-                    for (; i + 7 * BM_THREADS < len; i += 8 * BM_THREADS) {
+                    for (uint32_t i0 = 0; i0 < len; i0 += 8 * BM_THREADS) {
                         uint32_t d[8]; float sc[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) { d[u] = __ldg(pd + i + u * BM_THREADS); sc[u] = __ldg(ps + i + u * BM_THREADS); }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) acc[d[u] - base] = __fadd_rn(acc[d[u] - base], sc[u]);
-                    }
-                    if (i < len) {   // remainder (and short slices): its loads are issued together as well
-                        uint32_t d[7]; float sc[7];
-#pragma unroll
-                        for (int u = 0; u < 7; ++u) {
-                            const bool ok = i + (uint32_t)u * BM_THREADS < len;
-                            d[u] = ok ? __ldg(pd + i + u * BM_THREADS) : 0xFFFFFFFFu;
-                            sc[u] = ok ? __ldg(ps + i + u * BM_THREADS) : 0.0f;
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t i = i0 + tid + (uint32_t)u * BM_THREADS;
+                            const bool ok = i < len;
+                            d[u] = ok ? __ldg(pd + i) : 0xFFFFFFFFu;
+                            sc[u] = ok ? __ldg(ps + i) : 0.0f;
                         }
+                        if (i0 == 0 && prev) __syncthreads();
 #pragma unroll
-                        for (int u = 0; u < 7; ++u)
+                        for (int u = 0; u < 8; ++u)
                             if (d[u] != 0xFFFFFFFFu) acc[d[u] - base] = __fadd_rn(acc[d[u] - base], sc[u]);
                     }
+                    prev = 1;
                 }
                 const bool fused = fuse_last;   // (a dense last token always runs: the scan from registers happened)
                 if (prev == 1 || (prev == 2 && !fused)) __syncthreads();
@@ -358,7 +390,14 @@ bm25_query_kernel(Bm25Dev b, const uint64_t* __restrict__ qtok_off, const uint32
         atomicAdd(&s_pos, my_pos);
         atomicMin(&s_minbits, my_min);
         prune();
-        const uint32_t cnt = s_cnt;
+        __syncthreads();
+        const uint32_t cnt = min(s_cnt, K);   // (<= K after the prune)
+        {   // the answer in order: sort the survivors, padded to a power of two
+            uint32_t n2 = 2;
+            while (n2 < cnt) n2 <<= 1;
+            for (uint32_t i = cnt + tid; i < n2; i += BM_THREADS) buf[i] = ~0ull;
+            block_sort_n(buf, n2);
+        }
         for (uint32_t j = tid; j < K; j += BM_THREADS) {
             size_t o = (size_t)q * K + j;
             if (j < cnt) {
