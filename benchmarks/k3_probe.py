@@ -26,5 +26,5 @@ for _ in range(4):
     npost, kms = bm.last_batch()
     rows.append((round(kms, 3), round(host_ms, 1)))
 crc = zlib.crc32(bi.tobytes()) ^ zlib.crc32(bs.tobytes()) ^ zlib.crc32(bc.tobytes())
-print(json.dumps({"lib": os.path.basename(P.LIB_PATH), "dense_frac": os.environ.get("LEANN_CUDA_BM25_DENSE_FRAC"), "dense_rows": bm.dense_rows(), "kernel_ms/host_ms": rows, "postings": npost, "algorithmic_GBps": round(npost * 8 / rows[-1][0] / 1e6, 1),
+print(json.dumps({"lib": os.path.basename(P.LIB_PATH), "dense_frac": os.environ.get("LEANN_CUDA_BM25_DENSE_FRAC"), "dense_rows": bm.dense_rows(), "kernel_ms/host_ms": rows, "postings": npost, "stream_bytes": bm.last_batch_bytes(), "stream_GBps": round(bm.last_batch_bytes() / rows[-1][0] / 1e6, 1), "algorithmic_GBps": round(npost * 8 / rows[-1][0] / 1e6, 1),
                   "build_s": round(t_build, 1), "crc": crc}))

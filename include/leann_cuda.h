@@ -238,9 +238,9 @@ int leann_cuda_bm25_build(const char* const* docs, const size_t* doc_bytes, size
 size_t leann_cuda_bm25_len(const leann_cuda_bm25* bm25);
 /* stats[0..3] = n_docs, n_terms, n_postings, total_tokens; avg_doc_len out (bm25.rs:61-65). */
 int leann_cuda_bm25_stats(const leann_cuda_bm25* bm25, uint64_t* stats4, float* avg_doc_len);
-/* Number of terms the handle also keeps as dense score rows (K3d: terms present in at least half of the documents are
+/* Number of terms the handle also keeps as dense score rows (K3d: terms present in at least a quarter of the documents are
  * added to the accumulator tile row-wise, 4 B per document instead of 8 B per posting; results are bit-identical).
- * Tuning, read at build time: LEANN_CUDA_BM25_DENSE_FRAC (df / n_docs threshold, default 0.5, 0 = off),
+ * Tuning, read at build time: LEANN_CUDA_BM25_DENSE_FRAC (df / n_docs threshold, default 0.25, 0 = off),
  * LEANN_CUDA_BM25_DENSE_MAX (row limit, default 64). */
 size_t leann_cuda_bm25_dense_rows(const leann_cuda_bm25* bm25);
 /* tokenize (bm25.rs:127-132): writes tokens separated by '\n' into out (truncated to cap),
@@ -257,6 +257,9 @@ int leann_cuda_bm25_search(const leann_cuda_bm25* bm25, const char* const* queri
 /* Measurement of the last leann_cuda_bm25_search batch on this handle: postings covered by its query tokens
  * (algorithmic bytes of K3 = postings * 8) and the device time of the query kernel (CUDA events). */
 int leann_cuda_bm25_last_batch(const leann_cuda_bm25* bm25, uint64_t* postings, float* kernel_ms);
+/* Bytes the tokens of that batch make the query kernel stream: 8 per posting, or 4 per document for a token whose term has a
+ * dense row (the roofline numerator of K3 once dense rows exist). */
+uint64_t leann_cuda_bm25_last_batch_bytes(const leann_cuda_bm25* bm25);
 /* hybrid_rerank (bm25.rs:135-170) for one candidate list, evaluated on the device. bm25_scores is
  * the dense host vector of n_docs scores. Output has n entries, stable descending. */
 int leann_cuda_hybrid_rerank(const uint64_t* idx, const float* vec_scores, size_t n,

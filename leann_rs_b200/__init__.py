@@ -123,6 +123,7 @@ def lib():
         "leann_cuda_hybrid_fuse": (C.c_int, [vp, vp, vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, C.c_int, C.c_float, vp, sz, sz, C.c_int,
                                              vp, vp, vp, cp, sz]),
         "leann_cuda_bm25_last_batch": (C.c_int, [vp, u64p, f32p]),
+        "leann_cuda_bm25_last_batch_bytes": (C.c_uint64, [vp]),
         "leann_cuda_hybrid_rerank": (C.c_int, [vp, vp, sz, vp, sz, C.c_float, C.c_int, vp, vp, cp, sz]),
         "leann_cuda_bm25_free": (None, [vp]),
         "leann_cuda_hybrid_search": (C.c_int, [vp, vp, vp, cpp, szp, sz, sz, sz, C.c_int, C.c_float, vp, vp, vp, vp, cp, sz]),

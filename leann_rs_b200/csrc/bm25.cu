@@ -615,8 +615,9 @@ __global__ void dense_row_scatter_kernel(Bm25Dev b, uint32_t term, float* __rest
 
 void bm25_build_dense_rows(leann_cuda_bm25* b) {
     b->n_dense = 0;
+    b->is_dense.clear();
     const size_t n = b->host.num_docs, n_terms = b->host.term_off.empty() ? 0 : b->host.term_off.size() - 1;
-    double frac = 0.5;
+    double frac = 0.25;
     if (const char* e = getenv("LEANN_CUDA_BM25_DENSE_FRAC")) frac = atof(e);
     size_t max_rows = 64;
     if (const char* e = getenv("LEANN_CUDA_BM25_DENSE_MAX")) max_rows = (size_t)std::max(0, atoi(e));
@@ -649,6 +650,8 @@ void bm25_build_dense_rows(leann_cuda_bm25* b) {
     LEANN_CUDA_CHECK(cudaDeviceSynchronize());
     LEANN_CUDA_CHECK(cudaGetLastError());
     b->n_dense = (uint32_t)cand.size();
+    b->is_dense.assign(n_terms, 0);
+    for (auto& c : cand) b->is_dense[c.second] = 1;
 }
 
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,

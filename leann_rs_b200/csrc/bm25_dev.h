@@ -1,5 +1,7 @@
 // bm25_dev.h — device view of the BM25 inverted index and kernel launchers (bm25.cu).
 #pragma once
+#include <vector>
+
 #include "internal.h"
 #include "text.h"
 
@@ -20,9 +22,9 @@ struct Bm25Dev {
 void launch_bm25_dense(const Bm25Dev& b, const uint32_t* terms, const uint64_t* dfs, size_t n_tokens, float* d_scores,
                        cudaStream_t s);
 size_t bm25_max_query_tokens();   // longest query (known tokens, duplicates included) the query kernel takes
-// Builds the dense rows of `b` from its postings (terms whose df * 8 B exceeds the row's 4 B per document, most frequent first,
+// Builds the dense rows of `b` from its postings (terms present in at least a quarter of the documents, most frequent first,
 // bounded by LEANN_CUDA_BM25_DENSE_MAX rows, default 64, and an eighth of the free memory). LEANN_CUDA_BM25_DENSE_FRAC (default
-// 0.5) is the df / n_docs threshold; 0 disables the rows.
+// 0.25) is the df / n_docs threshold; 0 disables the rows.
 void bm25_build_dense_rows(leann_cuda_bm25* b);
 int bm25_query_ctas_per_sm();   // resident CTAs per SM the query kernel is built for (persistent pool size)
 void launch_bm25_query(const Bm25Dev& b, const uint64_t* qtok_off, const uint32_t* qtok_term, uint32_t nq, uint32_t K,
@@ -62,6 +64,7 @@ struct leann_cuda_bm25 {
     uint32_t* d_dense_of = nullptr;   // see Bm25Dev
     float* d_dense_rows = nullptr;
     uint32_t n_dense = 0, n_pad = 0;
+    std::vector<uint8_t> is_dense;    // host copy, per term (empty without dense rows)
     // per-handle workspace
     mutable std::mutex mu;
     mutable float* d_acc = nullptr;   // [n_docs] dense score vector of score_query, zero between calls
@@ -72,6 +75,7 @@ struct leann_cuda_bm25 {
     mutable cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     mutable cudaEvent_t ev_join = nullptr;   // BM25 top-k kernel done (joins the vector search's stream in the hybrid path)
     mutable uint64_t last_postings = 0;
+    mutable uint64_t last_stream_bytes = 0;   // what those tokens make the kernel read: 8 B per posting, or 4 B per document of a dense row
     mutable float last_kernel_ms = 0.0f;
     leann::Bm25Dev view() const {
         return leann::Bm25Dev{(uint32_t)host.num_docs, d_term_off, d_post_doc, d_post_score, n_dense ? d_dense_of : nullptr, d_dense_rows, n_pad};

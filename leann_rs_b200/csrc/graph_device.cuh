@@ -29,6 +29,47 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return r;
 }
 
+// L2 eviction priorities of the short-row traversal (LPV == 8), A/B-able at compile time (benchmarks/k1_variants.sh):
+//   bit 0: vector rows are loaded evict_first (each row is used once; they should not push the visited tables out of L2)
+//   bit 1: the q16 visited tables are read / cleared evict_last (116 MB of tables for 24 warps per SM are meant to stay in L2)
+//   bit 2: adjacency rows are loaded evict_first
+#ifndef LEANN_K1_L2POL
+#define LEANN_K1_L2POL 0
+#endif
+#ifndef LEANN_K1_SPEC
+#define LEANN_K1_SPEC 0   // speculative row prefetch of the register-list traversal (see beam_level_regs)
+#endif
+__device__ __forceinline__ float4 ldg_stream_evict_first(const float4* p) {
+    float4 r;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_u32_evict_first(const uint32_t* p) {
+    uint32_t r;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint4 ldcg_u4_evict_last(const uint4* p) {
+    uint4 r;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_u4_evict_last(uint4* p, const uint4 v) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Per-warp shared-memory state.
@@ -119,7 +160,7 @@ __device__ __forceinline__ void eval_distances(const float4* __restrict__ vecs, 
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
                 uint32_t idx = (uint32_t)(i * LPV + lig);
-                if (ok && idx < d4) x[u][i] = ldg_stream(row + idx);
+                if (ok && idx < d4) x[u][i] = (LPV == 8 && (LEANN_K1_L2POL & 1)) ? ldg_stream_evict_first(row + idx) : ldg_stream(row + idx);
                 else x[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
@@ -318,7 +359,10 @@ struct VisitedSet {
 //     most 3 buckets away; beyond that (or above 62 % load) the traversal moves to a pooled byte map as the u32 table does.
 constexpr uint32_t Q_EMPTY = 0xFFFFu;
 constexpr uint32_t Q_HASH_MUL = 0x9E3779B1u;
-__device__ __forceinline__ uint4 q_bucket(const VisitedSet& v, uint32_t b) { return __ldcg(reinterpret_cast<const uint4*>(v.tbl) + b); }
+__device__ __forceinline__ uint4 q_bucket(const VisitedSet& v, uint32_t b) {
+    if (LEANN_K1_L2POL & 2) return ldcg_u4_evict_last(reinterpret_cast<const uint4*>(v.tbl) + b);
+    return __ldcg(reinterpret_cast<const uint4*>(v.tbl) + b);
+}
 // found: `want` is one of the 8 entries; empties: bit i set = entry i is empty
 __device__ __forceinline__ void q_scan(const uint4 w, uint32_t want, bool& found, uint32_t& empties) {
     const uint32_t x[4] = {w.x, w.y, w.z, w.w};
@@ -399,7 +443,11 @@ __device__ __forceinline__ void visited_begin(VisitedSet& v, int lane) {
     if (v.hashed) {
         uint4* t4 = reinterpret_cast<uint4*>(v.tbl);
         const uint32_t n16 = v.q16 ? v.q_bmask + 1u : v.cap_mask / 4 + 1u;   // 16-byte units to clear
-        for (uint32_t i = lane; i < n16; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+        if ((LEANN_K1_L2POL & 2) && v.q16) {
+            for (uint32_t i = lane; i < n16; i += 32) st_u4_evict_last(t4 + i, make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY));
+        } else {
+            for (uint32_t i = lane; i < n16; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+        }
         __syncwarp();
     } else {
         v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
@@ -740,8 +788,18 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const uint32_t j = c0 + (uint32_t)ch * 32u + lane;
-                sv[ch] = j < adj.deg ? __ldg(row + j) : SENT;
+                sv[ch] = j < adj.deg ? ((LEANN_K1_L2POL & 4) ? ldg_u32_evict_first(row + j) : __ldg(row + j)) : SENT;
             }
+#if LEANN_K1_SPEC > 0
+            // Speculative row prefetch: the first LEANN_K1_SPEC neighbours of the row (list order) are the most likely members of the
+            // first distance batch; their rows are requested from DRAM now, so that the fetch overlaps the two L2 round trips of
+            // the visited test instead of following them. A neighbour that turns out to be visited costs one wasted row.
+            if (c0 == 0 && lane < LEANN_K1_SPEC && sv[0] != SENT) {
+                const char* r = reinterpret_cast<const char*>(g.vecs + (size_t)sv[0] * g.d4);
+                const uint32_t lines = (g.d4 * 16u + 127u) >> 7;
+                for (uint32_t l = 0; l < lines; ++l) prefetch_l2(r + l * 128u);
+            }
+#endif
             bool fr[NCH];
             if (Q16 && vs.hashed) {
                 // bucketed table: all probes of the pass advance together, one bucket load (or one CAS) per round

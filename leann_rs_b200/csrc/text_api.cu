@@ -432,7 +432,12 @@ int leann_cuda_bm25_search(const leann_cuda_bm25* b, const char* const* queries,
                           bn.as<float>(), b->d_qcounter, s);
         LEANN_CUDA_CHECK(cudaEventRecord(b->ev1, s));
         b->last_postings = 0;
-        for (uint32_t t : terms) b->last_postings += b->host.term_off[t + 1] - b->host.term_off[t];
+        b->last_stream_bytes = 0;
+        for (uint32_t t : terms) {
+            const uint64_t df = b->host.term_off[t + 1] - b->host.term_off[t];
+            b->last_postings += df;
+            b->last_stream_bytes += (!b->is_dense.empty() && b->is_dense[t]) ? (uint64_t)b->n_pad * 4 : df * 8;
+        }
         LEANN_CUDA_CHECK(cudaMemcpyAsync(idx, bi.p, nq * top_k * 8, cudaMemcpyDeviceToHost, s));
         LEANN_CUDA_CHECK(cudaMemcpyAsync(scores, bs.p, nq * top_k * 4, cudaMemcpyDeviceToHost, s));
         if (counts) LEANN_CUDA_CHECK(cudaMemcpyAsync(counts, bc.p, nq * 4, cudaMemcpyDeviceToHost, s));
@@ -440,6 +445,7 @@ int leann_cuda_bm25_search(const leann_cuda_bm25* b, const char* const* queries,
         LEANN_CUDA_CHECK(cudaEventElapsedTime(&b->last_kernel_ms, b->ev0, b->ev1));
     });
 }
+uint64_t leann_cuda_bm25_last_batch_bytes(const leann_cuda_bm25* b) { return b ? b->last_stream_bytes : 0; }
 int leann_cuda_bm25_last_batch(const leann_cuda_bm25* b, uint64_t* postings, float* kernel_ms) {
     if (!b) return LEANN_ERR_INVALID_ARG;
     if (postings) *postings = b->last_postings;

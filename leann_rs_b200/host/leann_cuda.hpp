@@ -281,6 +281,7 @@ public:
         check(leann_cuda_bm25_build(p.data(), n.data(), p.size(), device, &b, err, sizeof err), err);
         return Bm25Scorer(b);
     }
+    size_t dense_rows() const { return leann_cuda_bm25_dense_rows(b_.get()); }   // frequent terms also kept row-wise (K3d)
     std::vector<float> score_query(const std::string& query) const {
         std::vector<float> s(leann_cuda_bm25_len(b_.get()));
         char err[1024];

@@ -178,6 +178,10 @@ class Bm25Scorer:
                                         C.c_void_p(cnt.ctypes.data), e, 1024), e)
         return idx, sc, cnt
 
+    def last_batch_bytes(self) -> int:
+        """Bytes the last search_batch's tokens make the kernel stream (8 per posting, 4 per document of a dense row)."""
+        return int(_core().lib().leann_cuda_bm25_last_batch_bytes(self._h))
+
     def last_batch(self):
         """(postings covered by the last search_batch's tokens, device ms of its query kernel)."""
         n, ms = C.c_uint64(), C.c_float()

@@ -55,6 +55,7 @@ extern "C" {
     fn leann_cuda_bm25_build(docs: *const *const c_char, doc_bytes: *const usize, n_docs: usize, device: c_int,
                              out: *mut *mut LeannCudaBm25, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_bm25_free(b: *mut LeannCudaBm25);
+    fn leann_cuda_bm25_dense_rows(b: *const LeannCudaBm25) -> usize;
     fn leann_cuda_filter_parse(expr: *const c_char, out: *mut *mut LeannCudaFilter, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_filter_free(f: *mut LeannCudaFilter);
     fn leann_cuda_metacols_build(metadata_json: *const *const c_char, bytes: *const usize, n: usize,
@@ -353,6 +354,10 @@ impl CudaBm25 {
         };
         check(rc, &err)?;
         Ok(Self(h))
+    }
+    /// Terms the handle also keeps as dense score rows (LEANN_CUDA_BM25_DENSE_FRAC / _MAX at build time; results do not depend on it).
+    pub fn dense_rows(&self) -> usize {
+        unsafe { leann_cuda_bm25_dense_rows(self.0) }
     }
 }
 impl Drop for CudaBm25 {
