@@ -310,12 +310,12 @@ void search_device_launch(const leann_cuda_index* ix, const float* d_queries, si
         const TcIndexView* tvp = nullptr;
         static const bool tc_env_off = getenv("LEANN_CUDA_DISABLE_TC") != nullptr;  // A/B switch for benchmarks
         if (!tc_env_off && !ix->tc_disabled && exact_scan_tc_supported(f, (uint32_t)nq)) {
-            uint32_t dp8 = (uint32_t)((ix->d + 7) / 8 * 8);
+            const uint32_t dp8 = exact_scan_tc_dp8((uint32_t)ix->d, ix->d4, ix->metric);
             if (!ix->tc_bf16) {
                 LEANN_CUDA_CHECK(cudaMalloc(&ix->tc_bf16, ix->n * (size_t)dp8 * 2));
                 LEANN_CUDA_CHECK(cudaMalloc(&ix->tc_norms, ix->n * 4));
                 LEANN_CUDA_CHECK(cudaMalloc(&ix->tc_xmax, 256));
-                exact_scan_tc_prepare(ix->vecs, ix->n, ix->d4, dp8, ix->tc_bf16, ix->tc_norms, ix->tc_xmax, stream);
+                exact_scan_tc_prepare(ix->vecs, ix->n, ix->d4, dp8, ix->tc_bf16, ix->tc_norms, ix->tc_xmax, ix->metric, stream);
             }
             tv.x_bf16 = ix->tc_bf16; tv.xmax_bits = ix->tc_xmax; tv.dp8 = dp8;
             tvp = &tv;

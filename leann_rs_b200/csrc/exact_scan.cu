@@ -409,7 +409,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
     uint32_t kpad = (k + 31) & ~31u;
     size_t d4max = d4;
-    size_t dp8 = ((size_t)d4 * 4 + 7) / 8 * 8;
+    size_t dp8 = ((size_t)d4 * 4 + 4 + 7) / 8 * 8;   // >= exact_scan_tc_dp8 for every metric
     return align256((size_t)nq * SCAN_CAP * 8) + align256((size_t)nq * 4) + align256((size_t)nq * kpad * 8) +
            align256((size_t)nq * 4) + align256((size_t)nq * 8) + 256 + align256((size_t)nq * d4max * 16) +
            // tensor path: bf16 queries, |q|, dot thresholds, candidate row ids
@@ -500,7 +500,7 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         scan_init_kernel<<<(J.nq + 255) / 256, 256, 0, J.stream>>>(J.s.cand_cnt, J.s.best_cnt, J.s.thr, J.nq, J.s.overflow,
                                                                    (uint32_t)std::min<uint64_t>(f.n, SCAN_CAP));
         launch_pad_rows(d_queries + (size_t)J.q0 * f.d, J.s.qpad, J.nq, f.d, f.d4, J.stream);
-        if (use_tc) exact_scan_tc_queries(J.s.qpad, J.nq, f.d4, tv->dp8, J.ts, J.stream);
+        if (use_tc) exact_scan_tc_queries(J.s.qpad, J.nq, f.d4, tv->dp8, f.metric, tv->xmax_bits, J.ts, J.stream);
     };
     auto run_round = [&](ScanJob& J, size_t ri, int attempt) {
         const uint32_t r0 = rounds[ri].first, r1 = rounds[ri].second;
@@ -524,10 +524,19 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
 #undef LEANN_TILE
         }
         LEANN_CUDA_CHECK(cudaGetLastError());
-        if (lowsmem)
-            select_kernel<true><<<J.nq, 256, sel_smem, J.stream>>>(J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.best, J.s.best_cnt, k, kpad, J.s.thr, J.nq, sort_cap);
-        else
-            select_kernel<false><<<J.nq, 256, sel_smem, J.stream>>>(J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.best, J.s.best_cnt, k, kpad, J.s.thr, J.nq, sort_cap);
+        auto select = [&]() {
+            if (lowsmem)
+                select_kernel<true><<<J.nq, 256, sel_smem, J.stream>>>(J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.best, J.s.best_cnt, k, kpad, J.s.thr, J.nq, sort_cap);
+            else
+                select_kernel<false><<<J.nq, 256, sel_smem, J.stream>>>(J.s.cand, J.s.cand_cnt, SCAN_CAP, J.s.best, J.s.best_cnt, k, kpad, J.s.thr, J.nq, sort_cap);
+        };
+        select();
+        if (use_tc && ri == 0 && rounds.size() > 1) {
+            // the later chunks are scored by rerank_kernel: re-score the first chunk's top-k the same way (nq * k rows out of
+            // L2), so that every score in `best` comes from one arithmetic and exact duplicate rows tie exactly
+            exact_scan_tc_canonical_first(f, J.s, J.ts, J.nq, kpad, SCAN_CAP, J.stream);
+            select();
+        }
         note_overflow_kernel<<<1, 1, 0, J.stream>>>(J.s.overflow, (uint32_t)ri);
         LEANN_CUDA_CHECK(cudaGetLastError());
     };

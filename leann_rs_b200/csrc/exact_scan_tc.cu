@@ -342,8 +342,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 // f32 -> bf16 (round to nearest even) rows padded to dp8 elements. Per row: |x| and the rounding residual |x^ - x|
 // (both rounded up: they are only used as upper bounds), optionally stored, optionally folded into two global maxima
 // (max_bits[0] = max |x|, max_bits[1] = max |x^ - x|; non-negative floats order as their bit patterns).
+// AUG (squared-L2 metric): the float4 group after the data (columns 4*d4 .. 4*d4+2, inside the dp8 padding) carries the
+// row term of |q - x|^2 = |q|^2 + |x|^2 - 2 q.x so that the SAME tensor pass yields q.x - |x|^2/2:
+//   rows (aug_rows_kernel, once max|x| is known):  -(h/c) split into three bf16 pieces, h = fl(0.5 * sum of squares);
+//              an f32 has 24 significant bits and each piece takes 8, so hi + mid + lo == h/c exactly;
+//   queries (AUG_QUERY): c, c, c.
+// c = 2^floor(log2 max|x|): a power of two (h/c and c * piece are exact) that keeps the augmented columns at the scale of
+// the data, so the f32 accumulation term of the error bound stays proportional to |q| |x| whatever the units of the data.
+// AUG_SS: `norms` receives the raw sum of squares instead of the norm (input of aug_rows_kernel).
+constexpr int AUG_NONE = 0, AUG_SS = 1, AUG_QUERY = 2;
+__device__ __forceinline__ float tc_l2_scale(const uint32_t* xmax_bits) {
+    const uint32_t e = xmax_bits[0] & 0x7F800000u;
+    return (e == 0u || e == 0x7F800000u) ? 1.0f : __uint_as_float(e);
+}
 __global__ void to_bf16_kernel(const float4* __restrict__ src, uint32_t d4, __nv_bfloat16* __restrict__ dst, uint32_t dp8,
-                               size_t n, float* __restrict__ norms, float* __restrict__ resid, uint32_t* __restrict__ max_bits) {
+                               size_t n, float* __restrict__ norms, float* __restrict__ resid, uint32_t* __restrict__ max_bits,
+                               int aug, const uint32_t* __restrict__ scale_src) {
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     float ss = 0.f, rr = 0.f;
@@ -363,10 +377,15 @@ __global__ void to_bf16_kernel(const float4* __restrict__ src, uint32_t d4, __nv
         ss += __shfl_xor_sync(0xFFFFFFFFu, ss, off);
         rr += __shfl_xor_sync(0xFFFFFFFFu, rr, off);
     }
+    if (aug == AUG_QUERY && row < n && (uint32_t)lane == (d4 & 31u)) {   // this lane stored group d4 (zeros) in the loop above
+        const float c = tc_l2_scale(scale_src);
+        reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[d4 * 2] = __floats2bfloat162_rn(c, c);
+        reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[d4 * 2 + 1] = __floats2bfloat162_rn(c, 0.f);
+    }
     // 1 + 1e-4 covers the f32 rounding of the sums of squares (<= d * 2^-24 relative, d <= 4096) and of sqrtf
     const float nrm = sqrtf(ss) * 1.0001f, res = sqrtf(rr) * 1.0001f;
     if (row < n && lane == 0) {
-        if (norms) norms[row] = nrm;
+        if (norms) norms[row] = aug == AUG_SS ? ss : nrm;
         if (resid) resid[row] = res;
     }
     if (max_bits) {
@@ -383,6 +402,20 @@ __global__ void to_bf16_kernel(const float4* __restrict__ src, uint32_t d4, __nv
     }
 }
 
+// Squared-L2 metric, database side: writes -(h/c) in three exact bf16 pieces into columns 4*d4 .. 4*d4+2 of every row.
+__global__ void aug_rows_kernel(__nv_bfloat16* __restrict__ dst, uint32_t dp8, uint32_t d4, size_t n, const float* __restrict__ ss,
+                                const uint32_t* __restrict__ xmax_bits) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float h = 0.5f * ss[row] / tc_l2_scale(xmax_bits);      // exact: a division by a power of two
+    const __nv_bfloat16 hi = __float2bfloat16_rn(h);
+    const float r1 = h - __bfloat162float(hi);                    // exact
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(mid);                  // exact, <= 8 significant bits: lo is exact
+    reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[d4 * 2] = __floats2bfloat162_rn(-__bfloat162float(hi), -__bfloat162float(mid));
+    reinterpret_cast<__nv_bfloat162*>(dst + row * dp8)[d4 * 2 + 1] = __floats2bfloat162_rn(-r2, 0.f);
+}
+
 // Rigorous bound on |bf16 tensor-core score - f32 score| of query q against any database row (header comment):
 // |q^-q| max|x|  +  |q^| max|x^-x|  +  dp8 * 2^-22 |q^| max|x^|, with |q^| <= |q| (1 + 2^-8), |x^| <= |x| (1 + 2^-8).
 __device__ __forceinline__ float tc_eps(float qnorm, float qres, const uint32_t* xmax_bits, uint32_t dp8) {
@@ -390,6 +423,29 @@ __device__ __forceinline__ float tc_eps(float qnorm, float qres, const uint32_t*
     const float qhat = qnorm * 1.00390625f;
     const float acc = (float)dp8 * 2.3841858e-7f * qhat * (xmax * 1.00390625f);
     return (qres * xmax + qhat * xres + acc) * 1.0001f + 1e-30f;
+}
+
+// Squared-L2 metric through the dot-product pass. With the augmented columns the tensor core computes
+//   s' ~= s* = q.x - |x|^2/2 = (|q|^2 - D*) / 2,     D* = |q - x|^2 (exact arithmetic),
+// and a row must survive whenever its f32 distance D (rerank_kernel, scan_tile_kernel) is <= dk, the exact k-th best:
+//   * |D - D*| <= g D* with g = (d/8 + 32) 2^-24 <= 3.3e-5 for d <= 4096 (sums of non-negative terms, <= 5 roundings per
+//     128 columns and lane + 5 for the butterfly), so D <= dk implies D* <= dk (1 + 1e-4);
+//   * |q|^2 >= L = 0.99975 qnorm^2: qnorm = fl(sqrtf(ss) * 1.0001), ss within g of |q|^2;
+//   * |s' - s*| <= eps + herr: eps = the bf16 bound of the data columns (as tc_eps: |q^-q| max|x| + |q^| max|x^-x|) plus the
+//     f32 accumulation term over the AUGMENTED vectors (|q^_a|^2 = |q^|^2 + 3 c^2, |x^_a|^2 <= |x^|^2 + 1.01 (hmax/c)^2); the
+//     augmented products c * piece are exact and c (hi + mid + lo) == h, so herr = |h - |x|^2/2| <= g h <= 5e-5 hmax.
+// Survivor <=> s' > T with T = (L - dk (1 + 1e-4)) / 2 - eps - herr, rounded down.
+__device__ __forceinline__ float tc_l2_threshold(float dk, float qnorm, float qres, const uint32_t* xmax_bits, uint32_t dp8) {
+    const float xmax = __uint_as_float(xmax_bits[0]), xres = __uint_as_float(xmax_bits[1]);
+    const float c = tc_l2_scale(xmax_bits);
+    const float hmax = 0.5f * xmax * xmax * 1.000001f, hc = hmax / c;
+    const float qhat = qnorm * 1.00390625f, xhat = xmax * 1.00390625f;
+    const float qa = sqrtf(qhat * qhat + 3.f * c * c) * 1.000001f, xa = sqrtf(xhat * xhat + 1.01f * hc * hc) * 1.000001f;
+    const float acc = (float)dp8 * 2.3841858e-7f * qa * xa;
+    const float eps = (qres * xmax + qhat * xres + acc) * 1.0001f + 5e-5f * hmax + 1e-30f;
+    const float L = qnorm * qnorm * 0.99975f;
+    const float T = 0.5f * (L - dk * 1.0001f) - eps;
+    return nextafterf(T - fabsf(T) * 1e-6f - (L + dk) * 1e-6f, -CUDART_INF_F);   // the float operations above round either way
 }
 
 // thr key (packed rank key of the exact k-th best, or ~0) -> dot-space candidate threshold.
@@ -401,6 +457,7 @@ __global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr,
     unsigned long long key = thr[q];
     if (key == ~0ull) { thr_dot[q] = -CUDART_INF_F; return; }
     uint32_t ok = (uint32_t)(key >> 32);
+    if (metric == LEANN_METRIC_L2SQ) { thr_dot[q] = tc_l2_threshold(scan_unorder_f32(ok), qnorm[q], qres[q], xmax_bits, dp8); return; }
     float dotk;
     if (metric == LEANN_METRIC_DOT_DESC) dotk = scan_unorder_f32(~ok);
     else dotk = 1.0f - scan_unorder_f32(ok);   // IP / IP_CLAMP: distance = 1 - dot (clamped at 0: dot >= 1 stays conservative)
@@ -422,15 +479,24 @@ rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32
         const float4* x = X + (size_t)row * d4;
         const float4* qq = Q + (size_t)q * d4;
         float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
-        for (uint32_t j = lane; j < d4; j += 32) {
-            float4 a = qq[j], b = __ldg(&x[j]);
-            ax = fmaf(a.x, b.x, ax); ay = fmaf(a.y, b.y, ay); az = fmaf(a.z, b.z, az); aw = fmaf(a.w, b.w, aw);
+        if (metric == LEANN_METRIC_L2SQ) {
+            for (uint32_t j = lane; j < d4; j += 32) {
+                float4 a = qq[j], b = __ldg(&x[j]);
+                const float tx = a.x - b.x, ty = a.y - b.y, tz = a.z - b.z, tw = a.w - b.w;
+                ax = fmaf(tx, tx, ax); ay = fmaf(ty, ty, ay); az = fmaf(tz, tz, az); aw = fmaf(tw, tw, aw);
+            }
+        } else {
+            for (uint32_t j = lane; j < d4; j += 32) {
+                float4 a = qq[j], b = __ldg(&x[j]);
+                ax = fmaf(a.x, b.x, ax); ay = fmaf(a.y, b.y, ay); az = fmaf(a.z, b.z, az); aw = fmaf(a.w, b.w, aw);
+            }
         }
         float s = (ax + ay) + (az + aw);
         for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
         if (lane == 0) {
             uint32_t ok;
             if (metric == LEANN_METRIC_DOT_DESC) ok = ~scan_order_f32(s);
+            else if (metric == LEANN_METRIC_L2SQ) ok = scan_order_f32(s);
             else {
                 float dd = 1.0f - s;
                 if (metric == LEANN_METRIC_IP_CLAMP) dd = dd < 0.f ? 0.f : dd;
@@ -439,6 +505,21 @@ rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32
             cand[(size_t)q * cap + i] = ((unsigned long long)ok << 32) | row;
         }
     }
+}
+
+// After the first chunk (scored by the f32 tile kernel, a sequential fold): the rows of the running top-k go back into
+// the candidate list so that rerank_kernel re-scores them. From then on every key in `best` carries a score in ONE
+// arithmetic (rerank_kernel's), whichever chunk the row came from: exact duplicate rows tie exactly and rank by ascending
+// row, as the reference's stable sort over enumerate() order does (recompute.rs:106), instead of differing in the last bit.
+__global__ void requeue_best_kernel(const unsigned long long* __restrict__ best, uint32_t* __restrict__ best_cnt, uint32_t kpad,
+                                    unsigned long long* __restrict__ thr, uint32_t* __restrict__ cand_ids,
+                                    uint32_t* __restrict__ cand_cnt, uint32_t cap, uint32_t nq) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const uint32_t n = min(best_cnt[q], cap);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) cand_ids[(size_t)q * cap + i] = (uint32_t)(best[(size_t)q * kpad + i] & 0xFFFFFFFFull);
+    __syncthreads();
+    if (threadIdx.x == 0) { cand_cnt[q] = n; best_cnt[q] = 0; thr[q] = ~0ull; }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -473,19 +554,27 @@ CUtensorMap make_map(const void* base, uint64_t rows, uint32_t dp8, uint32_t box
 }  // namespace
 
 bool exact_scan_tc_supported(const FlatView& f, uint32_t nq) {
-    return (f.metric == LEANN_METRIC_DOT_DESC || f.metric == LEANN_METRIC_IP || f.metric == LEANN_METRIC_IP_CLAMP) && nq >= 1 &&
-           f.d >= 64 && f.n >= 16384;
+    return (f.metric == LEANN_METRIC_DOT_DESC || f.metric == LEANN_METRIC_IP || f.metric == LEANN_METRIC_IP_CLAMP ||
+            f.metric == LEANN_METRIC_L2SQ) && nq >= 1 && f.d >= 64 && f.n >= 16384;
 }
 
-size_t exact_scan_tc_bf16_bytes(size_t n, uint32_t d) { return n * (size_t)((d + 7) / 8 * 8) * 2 + n * 4 + 256; }
+// Columns of the bf16 copies: the data rounded up to 8; the squared-L2 form appends one float4 group (-|x|^2/2 in three
+// pieces for rows, ones for queries) after the 4-padded data.
+uint32_t exact_scan_tc_dp8(uint32_t d, uint32_t d4, int metric) {
+    return metric == LEANN_METRIC_L2SQ ? (d4 * 4 + 4 + 7) / 8 * 8 : (d + 7) / 8 * 8;
+}
+
 
 // Builds the bf16 copy of a database (called once per index) with its row norms (f32, kept for the L2 form of the
 // tensor path) and the two maxima tc_eps needs: xmax_bits[0] = max |x|, xmax_bits[1] = max |x^ - x|.
 void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t dp8, void* bf16_rows, float* norms,
-                           uint32_t* xmax_bits, cudaStream_t s) {
+                           uint32_t* xmax_bits, int metric, cudaStream_t s) {
     LEANN_CUDA_CHECK(cudaMemsetAsync(xmax_bits, 0, 8, s));
     if (!n) return;
-    to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(vecs, d4, (__nv_bfloat16*)bf16_rows, dp8, n, norms, nullptr, xmax_bits);
+    const bool l2 = metric == LEANN_METRIC_L2SQ;
+    to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(vecs, d4, (__nv_bfloat16*)bf16_rows, dp8, n, norms, nullptr, xmax_bits,
+                                                           l2 ? AUG_SS : AUG_NONE, nullptr);
+    if (l2) aug_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((__nv_bfloat16*)bf16_rows, dp8, d4, n, norms, xmax_bits);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -533,8 +622,19 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 
-void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_t dp8, const TcScratch& ts, cudaStream_t stream) {
-    to_bf16_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(qpad, d4, (__nv_bfloat16*)ts.q_bf16, dp8, nq, ts.qnorm, ts.qres, nullptr);
+// Re-scores the running top-k of the first chunk with rerank_kernel (see requeue_best_kernel); the caller runs
+// select_kernel afterwards, exactly as after a tensor round.
+void exact_scan_tc_canonical_first(const FlatView& f, const ScanScratch& s, const TcScratch& ts, uint32_t nq, uint32_t kpad, uint32_t cap,
+                                   cudaStream_t stream) {
+    requeue_best_kernel<<<nq, 128, 0, stream>>>(s.best, s.best_cnt, kpad, s.thr, ts.cand_ids, s.cand_cnt, cap, nq);
+    rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand);
+    LEANN_CUDA_CHECK(cudaGetLastError());
+}
+
+void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_t dp8, int metric, const uint32_t* xmax_bits,
+                           const TcScratch& ts, cudaStream_t stream) {
+    to_bf16_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(qpad, d4, (__nv_bfloat16*)ts.q_bf16, dp8, nq, ts.qnorm, ts.qres, nullptr,
+                                                     metric == LEANN_METRIC_L2SQ ? AUG_QUERY : AUG_NONE, xmax_bits);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -39,6 +39,9 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 #ifndef LEANN_K1_SPEC
 #define LEANN_K1_SPEC 0   // speculative row prefetch of the register-list traversal (see beam_level_regs)
 #endif
+#ifndef LEANN_K1_NOCAS
+#define LEANN_K1_NOCAS 0  // q16 table: first-round inserts by plain stores, conflicts settled inside the warp (see beam_level_regs)
+#endif
 __device__ __forceinline__ float4 ldg_stream_evict_first(const float4* p) {
     float4 r;
     unsigned long long pol;
@@ -816,6 +819,59 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                     act[ch] = sv[ch] != SENT; need_load[ch] = true; fr[ch] = false;
                     any |= act[ch];
                 }
+#if LEANN_K1_NOCAS
+                {   // executed by the whole warp (lanes without a key only take part in the votes)
+                    // Round 1 without atomics. The table belongs to this warp alone, so the only writers that can meet in a bucket
+                    // are the (up to 64) keys of this pass; they settle among themselves who takes which empty entry of the
+                    // snapshot and then STORE (no L2 round trip for the CAS result):
+                    //   same chunk, same bucket: __match_any_sync groups them, the i-th of the group takes the i-th empty entry; a
+                    //       key whose rank is beyond the empties moves on to the next bucket (its bucket is full after the stores);
+                    //   both chunks in one bucket: found through two 2048-bit maps in the (idle) distance staging row — bit
+                    //       (bucket & 63, bucket >> 6 & 31) set by every inserting key of a chunk, read by the other chunk; aliasing
+                    //       only produces false positives. Those keys keep the CAS path below.
+                    static_assert(NCH == 2, "cross-chunk conflict maps are written for two chunks");
+                    uint32_t* T = reinterpret_cast<uint32_t*>(w.st_dist);     // [2][64], MAX_DEG floats = 512 B
+                    reinterpret_cast<uint4*>(T)[lane] = make_uint4(0u, 0u, 0u, 0u);
+                    uint4 wv[NCH];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) if (act[ch]) wv[ch] = q_bucket(vs, bk[ch]);
+                    __syncwarp();
+                    bool ins[NCH];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        ins[ch] = false;
+                        if (act[ch]) {
+                            bool found;
+                            q_scan(wv[ch], want[ch], found, emp[ch]);
+                            need_load[ch] = false;
+                            if (found) act[ch] = false;
+                            else if (emp[ch]) { ins[ch] = true; atomicOr(&T[ch * 64 + (bk[ch] & 63u)], 1u << ((bk[ch] >> 6) & 31u)); }
+                        }
+                    }
+                    __syncwarp();
+                    any = false;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        const bool cross = ins[ch] && ((T[(ch ^ 1) * 64 + (bk[ch] & 63u)] >> ((bk[ch] >> 6) & 31u)) & 1u);
+                        const unsigned grp = __match_any_sync(FULL, ins[ch] ? bk[ch] : (0x80000000u | (uint32_t)lane));
+                        if (ins[ch] && !cross) {
+                            const int rank = __popc(grp & ((1u << lane) - 1u));
+                            if (rank < __popc(emp[ch])) {
+                                uint32_t m = emp[ch];
+                                for (int r = 0; r < rank; ++r) m &= m - 1u;
+                                t16[bk[ch] * 8 + (__ffs((int)m) - 1)] = (unsigned short)want[ch];   // displacement 0
+                                fr[ch] = true;
+                                act[ch] = false;
+                            } else {
+                                emp[ch] = 0;   // the peers of this pass fill the bucket
+                            }
+                        }
+                        if (act[ch] && emp[ch] == 0) { disp[ch] = 1; bk[ch]++; need_load[ch] = true; }
+                        any |= act[ch];
+                    }
+                    __syncwarp();   // the stores above are ordered before the bucket loads of the later rounds
+                }
+#endif
                 while (any) {
                     uint4 w[NCH];
 #pragma unroll

@@ -37,9 +37,13 @@ struct TcScratch {                 // per-call tensor-path scratch
 };
 
 bool exact_scan_tc_supported(const FlatView& f, uint32_t nq);
+uint32_t exact_scan_tc_dp8(uint32_t d, uint32_t d4, int metric);   // columns of the bf16 copies (L2: + the |x|^2/2 group)
 void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t dp8, void* bf16_rows, float* norms,
-                           uint32_t* xmax_bits, cudaStream_t s);
-void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_t dp8, const TcScratch& ts, cudaStream_t stream);
+                           uint32_t* xmax_bits, int metric, cudaStream_t s);
+void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_t dp8, int metric, const uint32_t* xmax_bits,
+                           const TcScratch& ts, cudaStream_t stream);
+void exact_scan_tc_canonical_first(const FlatView& f, const ScanScratch& s, const TcScratch& ts, uint32_t nq, uint32_t kpad, uint32_t cap,
+                                   cudaStream_t stream);
 void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq,
                          uint32_t r0, uint32_t r1, const uint64_t* d_mask, uint32_t cap, int sms, cudaStream_t stream);
 

@@ -238,11 +238,38 @@ bool Bm25GlobalStats::decode(const unsigned char* p, size_t n) {
 
 // ================================= filter =================================
 namespace {
+// Rust str::trim (filter.rs:53,60,122,138,151,156,168,173): strips chars with the Unicode White_Space property — U+0009..000D,
+// U+0020, U+0085, U+00A0, U+1680, U+2000..200A, U+2028, U+2029, U+202F, U+205F, U+3000 — and nothing else (not U+001C..001F).
+// Returns the byte length of the white-space char that starts at s[i], 0 if there is none.
+size_t ws_char_len(const std::string& s, size_t i) {
+    const size_t n = s.size();
+    const unsigned char c = (unsigned char)s[i];
+    if ((c >= 0x09 && c <= 0x0D) || c == 0x20) return 1;
+    if (c == 0xC2 && i + 1 < n) {
+        const unsigned char d = (unsigned char)s[i + 1];
+        return (d == 0x85 || d == 0xA0) ? 2 : 0;
+    }
+    if (i + 2 < n) {
+        const unsigned char d = (unsigned char)s[i + 1], e = (unsigned char)s[i + 2];
+        if (c == 0xE1) return (d == 0x9A && e == 0x80) ? 3 : 0;                                   // U+1680
+        if (c == 0xE2) {
+            if (d == 0x80) return ((e >= 0x80 && e <= 0x8A) || e == 0xA8 || e == 0xA9 || e == 0xAF) ? 3 : 0;   // U+2000..200A, 2028, 2029, 202F
+            return (d == 0x81 && e == 0x9F) ? 3 : 0;                                              // U+205F
+        }
+        if (c == 0xE3) return (d == 0x80 && e == 0x80) ? 3 : 0;                                   // U+3000
+    }
+    return 0;
+}
 std::string trim(const std::string& s) {
     size_t a = 0, b = s.size();
-    auto sp = [](unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };
-    while (a < b && sp((unsigned char)s[a])) ++a;
-    while (b > a && sp((unsigned char)s[b - 1])) --b;
+    for (size_t l; a < b && (l = ws_char_len(s, a)) != 0;) a += l;
+    while (b > a) {
+        size_t st = b - 1;   // start of the last char: step back over at most 3 continuation bytes
+        for (int k = 0; k < 3 && st > a && ((unsigned char)s[st] & 0xC0) == 0x80; ++k) --st;
+        const size_t l = ws_char_len(s, st);
+        if (l == 0 || st + l != b) break;
+        b = st;
+    }
     return s.substr(a, b - a);
 }
 std::vector<std::string> split(const std::string& s, const std::string& sep) {

@@ -169,22 +169,27 @@ def parse_value(s: str) -> Any:  # filter.rs:420-439
     return s
 
 
+# Rust str::trim strips exactly the chars with the Unicode White_Space property (Python's str.strip() would also strip
+# U+001C..U+001F, which Rust keeps).
+_RUST_WS = "\t\n\x0b\x0c\r \x85\xa0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000"
+
+
 def _cond(field, op, value):
     return {"field": field, "op": op, "value": value}
 
 
 def parse_single(s: str) -> Optional[dict]:  # filter.rs:137-316
-    s = s.strip()
+    s = s.strip(_RUST_WS)
     if s.endswith("?"):
         return _cond(s[:-1], "exists", None)
     for key, op in ((" in [", "in"), (" not_in [", "notin")):
         idx = s.find(key)
         if idx >= 0:
-            field = s[:idx].strip()
+            field = s[:idx].strip(_RUST_WS)
             rest = s[idx + len(key):]
             end = rest.find("]")
             if end >= 0:
-                return _cond(field, op, [parse_value(v.strip()) for v in rest[:end].split(",")])
+                return _cond(field, op, [parse_value(v.strip(_RUST_WS)) for v in rest[:end].split(",")])
     if "~" in s:
         a, b = s.split("~", 1)
         return _cond(a, "contains", b)
@@ -215,9 +220,9 @@ def parse_single(s: str) -> Optional[dict]:  # filter.rs:137-316
 
 
 def parse_filter(s: str) -> Optional[dict]:  # filter.rs:52-134
-    s = s.strip()
+    s = s.strip(_RUST_WS)
     if " OR " in s:
-        fs = [f for f in (parse_filter(p.strip()) for p in s.split(" OR ")) if f is not None]
+        fs = [f for f in (parse_filter(p.strip(_RUST_WS)) for p in s.split(" OR ")) if f is not None]
         if len(fs) > 1:
             return {"or": fs}
         return fs[0] if fs else None
@@ -250,7 +255,7 @@ def parse_filter(s: str) -> Optional[dict]:  # filter.rs:52-134
                     cur += c
             if cur:
                 parts.append(cur)
-        fs = [f for f in (parse_single(p.strip()) for p in parts) if f is not None]
+        fs = [f for f in (parse_single(p.strip(_RUST_WS)) for p in parts) if f is not None]
         if len(fs) > 1:
             return {"and": fs}
         return fs[0] if fs else None

@@ -146,11 +146,16 @@ def test_topk_merge(pkg):
                                                    # query tile resident up to 7 k-blocks (d <= 448), streamed beyond; ragged query pairs
                                                    ("dot", 10, 448, 30000, 300), ("ip", 10, 450, 30000, 513), ("dot", 5, 520, 20000, 64),
                                                    # single query and a handful: the query tile is mostly TMA zero fill
-                                                   ("dot", 100, 384, 40000, 1), ("ip", 10, 768, 30000, 3), ("dot", 7, 128, 20000, 17)])
+                                                   ("dot", 100, 384, 40000, 1), ("ip", 10, 768, 30000, 3), ("dot", 7, 128, 20000, 17),
+                                                   # squared L2 through the same tensor pass (|x|^2/2 in three extra bf16 columns);
+                                                   # d = 96 is BASELINE configs[3]; d = 126 / 444 / 448 / 520 put the extra group in a new k-block, the last resident one, the first streamed one
+                                                   ("l2", 10, 96, 40000, 200), ("l2", 100, 128, 50000, 130), ("l2", 10, 126, 30000, 64),
+                                                   ("l2", 1, 64, 20000, 1), ("l2", 17, 444, 30000, 257), ("l2", 10, 448, 20000, 40),
+                                                   ("l2", 10, 520, 20000, 33)])
 def test_exact_scan_tensor_path_parity(orc, pkg, metric_name, k, d, n, nq):
-    x, q = make_data(n, d, 17, nq=nq)
-    pm = {"dot": pkg.METRIC_DOT_DESC, "ip": pkg.METRIC_IP}[metric_name]
-    om = {"dot": 0, "ip": 2}[metric_name]
+    x, q = make_data(n, d, 17, nq=nq, normalize=(metric_name != "l2"))
+    pm = {"dot": pkg.METRIC_DOT_DESC, "ip": pkg.METRIC_IP, "l2": pkg.METRIC_L2SQ}[metric_name]
+    om = {"dot": 0, "ip": 2, "l2": 1}[metric_name]
     s = pkg.FlatSearcher.from_vectors(x, metric=pm)
     keys, scores, counts = s.search_batch(q, k, 0)
     oi, osc, oc = orc.exact_scan(q, x, k, metric=om, nthreads=8)
@@ -184,6 +189,52 @@ def test_exact_scan_tensor_path_unnormalised_mask_and_sorted(orc, pkg):
     keys, scores, counts = s2.search_batch(qs, 10, 0)
     oi, osc, oc = orc.exact_scan(qs, xs, 10, metric=0, nthreads=8)
     _check_topk(keys, scores, oi, osc, True, qs, xs)
+
+
+def test_exact_scan_tensor_path_l2_scales_offsets_and_tie_points(orc, pkg):
+    """Squared L2 on the tensor path: the candidate margin must hold (i) for data far from the origin (all-positive,
+    SIFT-like rows: |x|^2/2 is ~100x a typical distance, so q.x - |x|^2/2 cancels heavily), (ii) at any unit of the data
+    (the extra columns are scaled by a power of two near max|x|), (iii) with widely varying row norms, and (iv) at bf16
+    mantissa tie points, where both operands lose 2^-8 relative at once."""
+    rng = np.random.default_rng(11)
+    n, d = 40000, 128
+    x = (np.abs(rng.standard_normal((n, d))) * 50).astype(np.float32)
+    q = (np.abs(rng.standard_normal((96, d))) * 50).astype(np.float32)
+    for scale in (1.0, 1e-3, 64.0):
+        xs, qs = x * np.float32(scale), q * np.float32(scale)
+        s = pkg.FlatSearcher.from_vectors(xs, metric=pkg.METRIC_L2SQ)
+        keys, scores, counts = s.search_batch(qs, 10, 0)
+        oi, osc, oc = orc.exact_scan(qs, xs, 10, metric=1, nthreads=8)
+        assert np.array_equal(counts, oc)
+        _check_topk(keys, scores, oi, osc, False, qs, xs)
+        gt = orc.exact_f64(qs, xs, 10, metric=1)
+        assert np.mean([len(set(keys[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(qs))]) > 0.999
+        s.close()
+    # widely varying norms + mask
+    x2, q2 = make_data(30000, 96, 23, nq=80, normalize=False)
+    x2 *= np.linspace(0.1, 30.0, 30000, dtype=np.float32)[:, None]
+    bits = rng.random(30000) < 0.05
+    s = pkg.FlatSearcher.from_vectors(x2, metric=pkg.METRIC_L2SQ)
+    keys, scores, counts = s.search_batch(q2, 20, 0, mask=pkg.pack_mask(bits))
+    oi, osc, oc = orc.exact_scan(q2, x2, 20, metric=1, mask=orc.pack_mask(bits), nthreads=8)
+    assert np.array_equal(counts, oc)
+    _check_topk(keys, scores, oi, osc, False, q2, x2)
+    s.close()
+    # tie points: q = x* = (1 + 2^-8) ones round to ones; x* sits in a tensor-path chunk, the first chunk sets a threshold
+    # that only the exact distance 0 beats by less than the bf16 error of the pair
+    c = np.float32(1.0 + 2.0 ** -8)
+    qt = np.full((3, d), c, dtype=np.float32)
+    xt = (rng.integers(-8, 9, size=(20000, d)) / 64.0).astype(np.float32)
+    xt[:5] = np.float32(1.002)
+    star = [7000, 12345, 19999]
+    xt[star] = c
+    s = pkg.FlatSearcher.from_vectors(xt, metric=pkg.METRIC_L2SQ)
+    keys, scores, _ = s.search_batch(qt, 3, 0)
+    oi, osc, _ = orc.exact_scan(qt, xt, 3, metric=1)
+    assert sorted(oi[0].tolist()) == star
+    assert np.array_equal(keys, oi), (keys, oi)
+    assert np.array_equal(scores, osc)   # exact zeros
+    s.close()
 
 
 def test_randomised_exact_scan_matches_oracle(orc, pkg):

@@ -53,8 +53,31 @@ def test_filter_golden(pkg):
         assert [bool((int(words[i // 64]) >> (i % 64)) & 1) for i in range(len(GOLD["metadata"]))] == c["matches"]
 
 
+def test_filter_trim_is_rust_unicode_white_space(pkg):
+    """filter.rs trims with str::trim = the Unicode White_Space property: NBSP, NEL, U+1680, U+2000..200A, U+2028/9, U+202F,
+    U+205F and U+3000 are stripped like ASCII blanks; U+001C..U+001F and U+200B (zero width space) are NOT white space in
+    Rust (Python's str.strip() would strip the former), so they stay part of the field / value."""
+    ws = ["\u00a0", "\u0085", "\u1680", "\u2000", "\u2005", "\u200a", "\u2028", "\u2029", "\u202f", "\u205f", "\u3000", " \t\u00a0\r\n"]
+    for w in ws:
+        for expr in (f"{w}type=code{w}", f"type=code,{w}lines>3{w}", f"type{w} in [{w}code{w},{w}5{w}]", f"{w}lines>3 OR{w} {w}type=5{w}"):
+            ref = T.parse_filter(expr)
+            f = pkg.MetadataFilter.parse(expr)
+            assert ref is not None and f is not None, repr(expr)
+            assert f.describe() == ref, repr(expr)
+            assert "\u00a0" not in str(ref) and "\u3000" not in str(ref)
+    plain = pkg.MetadataFilter.parse("type=code").describe()
+    assert pkg.MetadataFilter.parse("\u3000type=code\u2003").describe() == plain
+    for keep in ("\x1c", "\x1f", "\u200b", "\u180e"):
+        expr = f"{keep}type=code"
+        ref = T.parse_filter(expr)
+        f = pkg.MetadataFilter.parse(expr)
+        assert f is not None and f.describe() == ref
+        assert f.describe() != plain and not f.matches({"type": "code"})      # the field name keeps the character
+
+
 _field = st.sampled_from(["type", "lines", "source", "a.b", "flag", "x"])
-_val = st.sampled_from(["code", "5", "5.0", "-3", "1e2", "true", "false", "*.rs", "*ain*", "ma*", "", " 7", "abc", "inf", "+4"])
+_val = st.sampled_from(["code", "5", "5.0", "-3", "1e2", "true", "false", "*.rs", "*ain*", "ma*", "", " 7", "abc", "inf", "+4", "\u00a07", "\u30005\u2009",
+                        "\x1f5"])
 _op = st.sampled_from(["=", ":", ">", "<", ">=", "<=", "!=", "~", "^", "$", " in [", " not_in ["])
 
 
