@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds A/B variants of the graph-search kernels as alternate libraries with the same ABI:
 #   leann_rs_b200/alt/libleann_cuda_k1_<name>.so, selected at run time with LEANN_CUDA_LIB=<path>.
-# Usage: benchmarks/k1_variants.sh l2pol1 l2pol3 ...   (l2pol<N>: -DLEANN_K1_L2POL=N, spec<N>: -DLEANN_K1_SPEC=N, nocas1: -DLEANN_K1_NOCAS=1; see graph_device.cuh)
+# Usage: benchmarks/k1_variants.sh l2pol1 l2pol3 ...   (l2pol<N>: -DLEANN_K1_L2POL=N, spec<N>: -DLEANN_K1_SPEC=N; see graph_device.cuh)
 set -e
 cd "$(dirname "$0")/../leann_rs_b200"
 make -j8 -s
@@ -18,7 +18,6 @@ for v in "$@"; do
   case $v in
     l2pol*) build $v -DLEANN_K1_L2POL=${v#l2pol} & pids="$pids $!" ;;
     spec*) build $v -DLEANN_K1_SPEC=${v#spec} & pids="$pids $!" ;;
-    nocas*) build $v -DLEANN_K1_NOCAS=${v#nocas} & pids="$pids $!" ;;
   esac
 done
 for p in $pids; do wait $p; done

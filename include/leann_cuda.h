@@ -144,8 +144,12 @@ int leann_cuda_search(const leann_cuda_index* index, const float* queries, size_
 /* Visited set of the graph traversal. By default every resident warp owns a byte map over the n nodes (exact, never cleared);
  * when n * resident warps would not fit in a third of device memory (tens of millions of short vectors per GPU) the library
  * switches to per-warp hash tables of about 2 * ef * degree node ids with a small shared pool of byte maps for traversals
- * that outgrow theirs. capacity 0 = automatic, 1 = byte maps only (fewer warps on large indexes), >= 1024 = force hash
- * tables of this size (tests use a tiny table to exercise the spill). Results never depend on the choice. */
+ * that outgrow theirs. Short rows (d <= 128) under the diskann-rs stop rule keep (the first level of) their table in shared
+ * memory (up to 2^24 rows per GPU). capacity 0 = automatic, 1 = byte maps only (fewer warps on large indexes), 2 / 3 =
+ * stand-alone shared-memory tables wherever the kernel supports them (3: 256-entry limit), 4 / 5 = shared-memory first level
+ * + hash-table overflow level (5: tiny levels) — 3 and 5 exist for tests, every traversal then overflows and spills —,
+ * >= 1024 = force hash tables of this size (tests use a tiny table to exercise the spill). 6..1023 are invalid.
+ * Results never depend on the choice. */
 int leann_cuda_set_visited_hash(leann_cuda_index* index, size_t capacity);
 int leann_cuda_set_coalescing(leann_cuda_index* index, size_t max_batch, unsigned max_wait_us);
 int leann_cuda_coalescing_stats(const leann_cuda_index* index, uint64_t* batches, uint64_t* requests);

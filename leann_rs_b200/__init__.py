@@ -298,7 +298,9 @@ class BackendSearcher:
         lib().leann_cuda_set_coalescing(self._h, max_batch, max_wait_us)
 
     def set_visited_hash(self, capacity: int):
-        """Visited set of the traversal: 0 auto, 1 byte maps only, >= 1024 force per-warp hash tables of this capacity."""
+        """Visited set of the traversal: 0 auto, 1 byte maps only, 2 / 3 stand-alone shared-memory tables where supported
+        (3: 256-entry limit), 4 / 5 shared-memory first level + hash overflow level (5: tiny levels; 3 and 5 are for tests),
+        >= 1024 force per-warp hash tables of this capacity."""
         rc = lib().leann_cuda_set_visited_hash(self._h, capacity)
         if rc != 0:
             raise LeannCudaError(rc, "invalid visited-hash capacity")

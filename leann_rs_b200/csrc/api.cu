@@ -234,7 +234,10 @@ static_assert(Q_HASH_INV * 0x9E3779B1u == 1u, "hash multiplier inverse");
 
 // q16 table for the register-list kernels: `slots` 16-bit entries per warp in buckets of 8. Sized for <= ~33 % load at
 // the expected 0.7 * ef * degree visited nodes; the slot space must split into bucket bits + at most 14 remainder bits.
-bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* rem_bits, uint32_t* key_bits) {
+// `first_level` > 0: the table is the overflow level of the hybrid form, whose shared-memory level absorbs that many members;
+// `tiny`: 1024 entries (tests: overflow and spill on every traversal).
+bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* rem_bits, uint32_t* key_bits, size_t first_level = 0,
+              bool tiny = false) {
     const bool off = getenv("LEANN_CUDA_DISABLE_Q16") != nullptr;   // A/B switch for benchmarks (read per launch)
     const SearchWorkspace& ws = ix->ws;
     if (off || ix->vhash_mode == 1 || ws.n_warps <= 0 || ix->n < 2) return false;
@@ -242,7 +245,10 @@ bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* 
     uint32_t B = 1;
     while (B < 32 && ((uint64_t)1 << B) < ix->n) ++B;
     uint32_t S = 8192;
-    while ((size_t)S * 10 < 21 * ef * ix->M0 && S < 65536) S <<= 1;          // S >= 3 * 0.7 * ef * degree
+    size_t expect10 = 7 * ef * ix->M0;                                        // 10 x the expected 0.7 * ef * degree members
+    if (first_level) expect10 = expect10 > 10 * first_level + 5120 ? expect10 - 10 * first_level : 5120;
+    while ((size_t)S * 10 < 3 * expect10 && S < 65536) S <<= 1;               // S >= 3 x expected
+    if (tiny) S = 1024;
     if (ix->vhash_mode >= 1024) S = std::max<uint32_t>(1024u, std::min<uint32_t>(65536u, next_pow2((uint32_t)std::min<size_t>(ix->vhash_mode, 65536))));   // tests: tiny tables exercise the spill
     auto bucket_bits = [](uint32_t s) { uint32_t b = 0; while ((8u << b) < s) ++b; return b; };
     while (B > bucket_bits(S) + 14 && S < 65536) S <<= 1;
@@ -251,6 +257,41 @@ bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* 
     if ((size_t)ws.n_warps * S * 2 > ((size_t)256 << 20) && !ws.large_mode && ix->vhash_mode == 0) return false;
     *slots = S; *rem_bits = B - bb; *key_bits = B;
     return true;
+}
+
+// Shared-memory visited tables (graph_device.cuh "smv") for the register-list kernels (short rows, d <= 128, diskann-rs stop
+// rule, throughput batches), up to 2^24 rows per GPU. Small indexes keep the byte maps (they live in L2).
+//   hybrid (smem_vis = 2): 4096 two-choice entries per warp in shared memory take the first ~3000 members of a traversal, the
+//       q16 table in global memory the rest; the usual 6 CTAs per SM;
+//   stand-alone (smem_vis = 1): 8192 entries per warp, 3 CTAs per SM, byte-map spill; taken when the expected 0.7 * ef * degree
+//       members stay under 75 % load.
+// Both are bit-identical to the other forms and both are OFF by default: on the 12.5M x 96 shard the hybrid measured 1.2 %
+// faster at L = 50 (where it never touches its q16 level) and 3.7 % slower at L = 100, the stand-alone form equal at L = 100
+// and 3 % slower at L = 50 (profiles/r2_k1_smv_ab.log, r2_k1_hybrid_ab.log) — taking the visited set off the L2 / DRAM path
+// buys almost nothing, i.e. the short-row traversal is not bound by memory transactions (see also benchmarks/gather_probe.cu:
+// random 384-byte rows alone stream at 6.9 TB/s). LEANN_CUDA_SMV = 0 / 1 / 2 selects none / stand-alone / hybrid (read once). Visited-set modes (leann_cuda_set_visited_hash):
+// 2 / 3 force the stand-alone form (3: 256-entry limit, every traversal spills), 4 / 5 the hybrid (5: 64-entry first level and a
+// 1024-entry q16 level, every traversal overflows and spills).
+void smv_plan(const leann_cuda_index* ix, SearchParams& p) {
+    static const int env_mode = [] { const char* e = getenv("LEANN_CUDA_SMV"); return e ? atoi(e) : 0; }();
+    const size_t vm = ix->vhash_mode;
+    int mode = vm == 0 ? env_mode : (vm == 2 || vm == 3) ? 1 : (vm == 4 || vm == 5) ? 2 : 0;
+    if (mode <= 0 || mode > 2 || ix->n < 2 || ix->d4 > 32) return;
+    if (vm == 0 && ix->n < 65536) return;
+    if (!graph_search_uses_reg_lists(ix->view(), p)) return;
+    uint32_t B = 1;
+    while (B < 32 && ((uint64_t)1 << B) < ix->n) ++B;
+    if (mode == 1) {
+        B = std::max<uint32_t>(B, 11u);
+        if (B > 24 || (size_t)7 * p.ef * ix->M0 > (size_t)10 * 6144) return;
+        p.smem_vis = 1;
+        p.smv_limit = vm == 3 ? 256u : 6656u;
+    } else {
+        if (B < 10 || B > 24) return;
+        p.smem_vis = 2;                      // confirmed once the q16 level is planned (search_device_launch)
+        p.smv_limit = vm == 5 ? 64u : 3072u;
+    }
+    p.q_key_bits = B; p.q_inv = Q_HASH_INV;
 }
 
 void ensure_l2_hash(const leann_cuda_index* ix, uint32_t cap) {
@@ -345,26 +386,46 @@ void search_device_launch(const leann_cuda_index* ix, const float* d_queries, si
     p.nq = (uint32_t)nq; p.k = (uint32_t)k; p.ef = (uint32_t)eff;
     p.next_cap = (uint32_t)leann_cuda_queue_capacity(eff, d_mask != nullptr);
     p.next_capp = next_pow2(p.next_cap);
-    ensure_workspace(ix, nq, graph_search_warps_per_sm(ix->view(), p.ef, p.next_capp), p.ef);
     p.mask = d_mask;
     p.nonstrict_term = (ix->backend == LEANN_BACKEND_VAMANA ? compat::DISKANN_STOP_STRICT : compat::USEARCH_STOP_STRICT) ? 0 : 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+    // batches of at most two queries per SM leave most of the machine idle with one warp per query: give each query a CTA
+    const bool coop = nq <= (size_t)sms * 2 && ix->coop_small_batches;
+    p.coop_ctas = coop ? 1 : 0;
+    p.coop_warps = nq <= (size_t)sms ? 8 : 4;
+    p.vhash = nullptr; p.vhash_cap = 1024u;
+    p.vhash16 = 0; p.q_rem_bits = 0; p.q_key_bits = 32; p.q_inv = 0;
+    p.smem_vis = 0; p.smv_limit = 0;
+    if (!coop) smv_plan(ix, p);   // short rows, throughput batch: visited tables in shared memory (fewer resident warps)
+    p.row_ring = 0;
+    {
+        // LEANN_CUDA_RING = 1: rows of a hop through a shared-memory ring of bulk async copies (A/B form, measured slower: off)
+        static const int ring_env = [] { const char* e = getenv("LEANN_CUDA_RING"); return e ? atoi(e) : 0; }();
+        if (!coop && !p.smem_vis && ring_env && ix->d4 <= 32 && graph_search_uses_reg_lists(ix->view(), p)) p.row_ring = 1;
+    }
+    const int warps_per_sm = graph_search_warps_per_sm(ix->view(), p.ef, p.next_capp, p.nonstrict_term, p.smem_vis, p.row_ring);
+    ensure_workspace(ix, nq, warps_per_sm, p.ef);
     p.out_keys = d_keys; p.out_dists = d_dists; p.out_counts = d_counts; p.out_stats = d_stats;
     p.visited = ix->ws.visited; p.epochs = ix->ws.epochs; p.counter = ix->ws.counter;
     p.n_pad = ix->ws.n_pad;
     p.n_warps = (int)std::min<size_t>((size_t)ix->ws.n_warps, (nq + 3) & ~(size_t)3);
+    if (p.smem_vis) p.n_warps = std::min(p.n_warps, std::max(4, warps_per_sm * sms));   // the workspace may have been sized by a launch with more resident warps
     p.vhash = ix->ws.large_mode ? ix->ws.vhash : nullptr;
     p.vhash_cap = ix->ws.large_mode ? ix->ws.vhash_cap : 1024u;
     p.pool_locks = ix->ws.pool_locks; p.pool_slots = std::max<uint32_t>(ix->ws.pool_slots, 1u);
-    // batches of at most two queries per SM leave most of the machine idle with one warp per query: give each query a CTA
-    {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
-        p.coop_ctas = (nq <= (size_t)sms * 2 && ix->coop_small_batches) ? (int)std::min<size_t>(nq, (size_t)ix->ws.n_warps) : 0;
-        p.coop_warps = nq <= (size_t)sms ? 8 : 4;
+    p.coop_ctas = coop ? (int)std::min<size_t>(nq, (size_t)ix->ws.n_warps) : 0;
+    if (p.smem_vis == 2) {   // hybrid: the overflow level is a (smaller) q16 table
+        uint32_t q16_slots = 0, rem_bits = 0, key_bits = 0;
+        if (q16_plan(ix, p.ef, &q16_slots, &rem_bits, &key_bits, p.smv_limit, ix->vhash_mode == 5) && key_bits == p.q_key_bits) {
+            ensure_l2_hash(ix, q16_slots / 2);   // words per warp
+            p.vhash = ix->ws.vhash; p.vhash_cap = q16_slots; p.vhash16 = 1; p.q_rem_bits = rem_bits;
+        } else {
+            p.smem_vis = 0; p.smv_limit = 0; p.q_key_bits = 32; p.q_inv = 0;
+        }
     }
     // throughput batches only: a latency-bound single traversal pays more for the CAS round trips than it saves (measured +20 %)
-    p.vhash16 = 0; p.q_rem_bits = 0; p.q_key_bits = 32; p.q_inv = 0;
-    if (p.coop_ctas == 0) {
+    if (p.coop_ctas == 0 && !p.smem_vis) {
         uint32_t q16_slots = 0;
         if (graph_search_uses_reg_lists(ix->view(), p) && q16_plan(ix, p.ef, &q16_slots, &p.q_rem_bits, &p.q_key_bits)) {
             // short rows: bucketed table of 16-bit quotiented entries (graph_device.cuh), L2-resident for all resident warps
@@ -567,7 +628,7 @@ int leann_cuda_hnsw_add(leann_cuda_index* ix, const float* vectors, int vectors_
 }
 
 int leann_cuda_set_visited_hash(leann_cuda_index* ix, size_t capacity) {
-    if (!ix || (capacity > 1 && capacity < 1024)) return LEANN_ERR_INVALID_ARG;
+    if (!ix || (capacity > 5 && capacity < 1024)) return LEANN_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->vhash_mode = capacity;
     return LEANN_OK;

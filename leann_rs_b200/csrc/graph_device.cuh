@@ -39,9 +39,6 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 #ifndef LEANN_K1_SPEC
 #define LEANN_K1_SPEC 0   // speculative row prefetch of the register-list traversal (see beam_level_regs)
 #endif
-#ifndef LEANN_K1_NOCAS
-#define LEANN_K1_NOCAS 0  // q16 table: first-round inserts by plain stores, conflicts settled inside the warp (see beam_level_regs)
-#endif
 __device__ __forceinline__ float4 ldg_stream_evict_first(const float4* p) {
     float4 r;
     unsigned long long pol;
@@ -73,6 +70,11 @@ __device__ __forceinline__ void st_u4_evict_last(uint4* p, const uint4 v) {
     asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Per-warp shared-memory state.
@@ -173,6 +175,87 @@ __device__ __forceinline__ void eval_distances(const float4* __restrict__ vecs, 
             int j = b + u * GROUPS + gid;
             if (j < cnt && lig == 0) st_dist[j] = finish_distance(v, metric);
         }
+    }
+    __syncwarp();
+}
+
+// ---- row ring: the rows of a hop through shared memory (short rows, register-list kernels) -------------------------
+// eval_distances holds U * VPL float4 per lane while a batch of U * 32/LPV rows is in flight and pays one L2 / DRAM round
+// trip per batch (5-6 per hop at d = 96: the largest single stall of the traversal). Here the rows travel as bulk async
+// copies (cp.async.bulk, one instruction per row, issued by as many lanes as there are rows) into a per-warp ring of
+// RING_STAGES x RING_ROWS rows; an mbarrier per stage counts the bytes. Stage t + RING_STAGES is requested as soon as stage t
+// has been consumed, so after the first stage of a hop the copies overlap the arithmetic, and no registers are tied up by
+// rows in flight. The arithmetic (lane mapping, accumulators, reduction tree) is eval_distances', bit for bit.
+constexpr int RING_ROWS = 8, RING_STAGES = 2;
+struct RowRing {
+    uint32_t rows;      // shared-space address of [RING_STAGES][RING_ROWS][row_bytes]
+    uint32_t bars;      // shared-space address of RING_STAGES mbarriers (8 bytes each)
+    uint32_t phase;     // bit s = parity the next wait on stage s expects
+};
+__device__ __forceinline__ void ring_init(const RowRing& r, int lane) {
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < RING_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(r.bars + 8u * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+template <int LPV, int VPL>
+__device__ __forceinline__ void eval_distances_ring(RowRing& r, const float4* __restrict__ vecs, uint32_t d4, int metric,
+                                                    const float4 (&q)[VPL], const uint32_t* st_slot, float* st_dist, int cnt,
+                                                    int lane) {
+    constexpr int GROUPS = 32 / LPV;
+    static_assert(RING_ROWS % GROUPS == 0, "a stage holds whole compute steps");
+    const int gid = lane / LPV, lig = lane % LPV;
+    const uint32_t row_bytes = d4 * 16u, row_stride = (uint32_t)(VPL * LPV) * 16u;
+    const int n_stages = (cnt + RING_ROWS - 1) / RING_ROWS;
+    auto issue = [&](int t) {
+        const int s = t % RING_STAGES, first = t * RING_ROWS;
+        const int nrows = min(RING_ROWS, cnt - first);
+        const uint32_t bar = r.bars + 8u * (uint32_t)s;
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nrows * row_bytes) : "memory");
+        __syncwarp();
+        if (lane < nrows) {
+            const float4* src = vecs + (size_t)st_slot[first + lane] * d4;
+            const uint32_t dst = r.rows + (uint32_t)(s * RING_ROWS + lane) * row_stride;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"(row_bytes), "r"(bar)
+                         : "memory");
+        }
+    };
+#pragma unroll
+    for (int t = 0; t < RING_STAGES; ++t)
+        if (t < n_stages) issue(t);
+    for (int t = 0; t < n_stages; ++t) {
+        const int s = t % RING_STAGES;
+        const uint32_t bar = r.bars + 8u * (uint32_t)s, par = (r.phase >> s) & 1u;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(par)
+                : "memory");
+        }
+        r.phase ^= 1u << s;
+#pragma unroll
+        for (int step = 0; step < RING_ROWS / GROUPS; ++step) {
+            const int slot = step * GROUPS + gid, j = t * RING_ROWS + slot;
+            const bool ok = j < cnt;
+            float4 x[VPL];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const uint32_t idx = (uint32_t)(i * LPV + lig);
+                if (ok && idx < d4) x[i] = lds_f4(r.rows + (uint32_t)(s * RING_ROWS + slot) * row_stride + idx * 16u);
+                else x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float v = group_reduce<LPV>(lane_partial<VPL>(q, x, metric));
+            if (ok && lig == 0) st_dist[j] = finish_distance(v, metric);
+        }
+        __syncwarp();   // every lane has read stage s before it is refilled
+        if (t + RING_STAGES < n_stages) issue(t + RING_STAGES);
     }
     __syncwarp();
 }
@@ -347,6 +430,10 @@ struct VisitedSet {
     uint8_t* pool_vis; uint32_t* pool_epochs; uint32_t* pool_locks; uint32_t n_slots; int slot;   // spill pool
     // q16: `tbl` holds 16-bit quotiented entries in buckets of 8 (one 16-byte load tests a key against a whole bucket)
     bool q16 = false; uint32_t q_rem_bits = 0, q_bmask = 0, q_kmask = 0, q_inv = 0;
+    // smv: a table in shared memory (two-choice buckets, below); stbl = its shared-space address. With q16 set as well the
+    // shared table is the first level and `tbl` the overflow level ("hybrid"): s_count of the `count` members live in shared
+    // memory, ovf = the shared table is closed (inserts and unresolved lookups go to `tbl`).
+    bool smv = false, ovf = false; uint32_t stbl = 0, s_bmask = 0, s_rem_bits = 0, s_limit = 0, s_count = 0;
 };
 
 // ---- q16: bucketed, quotiented visited table --------------------------------------------------------------------------
@@ -401,6 +488,95 @@ __device__ __forceinline__ int q_test_and_set(VisitedSet& v, uint32_t s) {
     return -1;
 }
 
+// ---- smv: the visited table of a traversal in SHARED memory ----------------------------------------------------------
+// Short rows make the traversal DRAM-transaction bound, and the q16 tables above still cost a bucket load and a CAS through L2
+// (or DRAM: 116 MB of tables share the L2 with the row stream) per neighbour test — about a fifth of the DRAM traffic of a hop.
+// A warp can keep (part of) its table in shared memory: buckets of eight 16-bit entries, TWO candidate buckets per key so
+// that the table works at 60-80 % load (the single-home form above needs <= 33 %):
+//   h = (slot * odd) mod 2^B (a bijection), b1 = top bits, rem = the other <= 15 bits, b2 = b1 ^ g(rem), g != 0;
+//   entry = rem << 1 | alt (0xFFFF = empty): alt = 0 in bucket b1, alt = 1 in bucket b2 — the pair (bucket, entry) identifies
+//   the slot exactly, a lookup reads the two buckets (two LDS.128) and nothing else. (The one key per 2^15 whose alt entry
+//   would equal the empty marker never enters the table: it is treated as "no room".)
+// The table is private to the warp, so inserts need no atomics: the lanes of a chunk that picked the same bucket (least loaded
+// of their two) are grouped with __match_any_sync, the i-th of a group takes the i-th empty entry of the snapshot, the others
+// retry after a __syncwarp.
+//   * stand-alone (1024 buckets = 16 KB per warp, 3 CTAs of 4 warps per SM): a key without room, or a table above its load
+//     limit, moves the traversal to a pooled byte map as the other table forms do;
+//   * hybrid (512 buckets = 8 KB per warp, the usual 6 CTAs per SM): the shared table takes the first ~3000 members of a
+//     traversal; once it is closed (limit reached, or a key without room) later members go to the warp's q16 table in global
+//     memory, which is cleared only then. A lookup tries shared memory first and the q16 table only after the closure.
+constexpr uint32_t SMV_BUCKETS = 1024, SMV_BYTES = SMV_BUCKETS * 16;   // stand-alone
+constexpr uint32_t HYB_BUCKETS = 512, HYB_BYTES = HYB_BUCKETS * 16;    // hybrid first level
+__device__ __forceinline__ uint32_t smv_alt(uint32_t rem, uint32_t bmask) {
+    const uint32_t g = ((rem * 0x5BD1u) >> 3) & bmask;
+    return g ? g : 1u;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
+}
+// One chunk of up to 32 keys (one per lane, SENT = none), executed by the whole warp. Returns per lane: true = the key was
+// not in the table and now is. `unresolved` is set for a key that is not in the table and was not inserted: no room, or
+// `insert` is false (closed table: the caller looks further).
+__device__ __forceinline__ bool smv_test_and_set(const VisitedSet& v, uint32_t s, int lane, bool& unresolved, bool insert) {
+    const uint32_t h = (s * Q_HASH_MUL) & v.q_kmask;
+    const uint32_t rem = h & ((1u << v.s_rem_bits) - 1u);
+    const uint32_t b1 = h >> v.s_rem_bits, b2 = b1 ^ smv_alt(rem, v.s_bmask);
+    const uint32_t e1 = rem << 1, e2 = e1 | 1u;
+    const unsigned lt = (1u << lane) - 1u;
+    bool pend = s != SENT, fresh = false;
+    // equal keys inside the chunk (a malformed adjacency row): only the first lane decides, the others are "already seen"
+    if (__match_any_sync(FULL, s) & lt) pend = false;
+    unresolved = false;
+    if (pend && e2 == Q_EMPTY) { unresolved = true; pend = false; }
+    for (;;) {
+        uint32_t em1 = 0, em2 = 0;
+        int tgt = 0;
+        if (pend) {
+            const uint4 w1 = lds_u4(v.stbl + b1 * 16u), w2 = lds_u4(v.stbl + b2 * 16u);
+            bool f1, f2;
+            q_scan(w1, e1, f1, em1);
+            q_scan(w2, e2, f2, em2);
+            if (f1 || f2) pend = false;
+            else if (!insert || (em1 | em2) == 0u) { unresolved = true; pend = false; }
+            else tgt = __popc(em1) >= __popc(em2) ? 0 : 1;     // least loaded; the home bucket on a tie
+        }
+        const uint32_t tb = tgt ? b2 : b1;
+        const unsigned grp = __match_any_sync(FULL, pend ? tb : (0x80000000u | (uint32_t)lane));
+        if (pend) {
+            const int rank = __popc(grp & lt);
+            uint32_t m = tgt ? em2 : em1;
+            if (rank < __popc(m)) {
+                for (int r = 0; r < rank; ++r) m &= m - 1u;
+                sts_u16(v.stbl + tb * 16u + (uint32_t)(__ffs((int)m) - 1) * 2u, tgt ? e2 : e1);
+                fresh = true;
+                pend = false;
+            }
+        }
+        __syncwarp();   // orders the stores before the next round's (and the next chunk's) bucket loads
+        if (!__any_sync(FULL, pend)) break;
+    }
+    return fresh;
+}
+// clears the warp's q16 table in global memory (start of a query; hybrid: when the shared table closes)
+__device__ __forceinline__ void q16_clear(const VisitedSet& v, int lane) {
+    uint4* t4 = reinterpret_cast<uint4*>(v.tbl);
+    const uint32_t n16 = v.q_bmask + 1u;
+    if (LEANN_K1_L2POL & 2) {
+        for (uint32_t i = lane; i < n16; i += 32) st_u4_evict_last(t4 + i, make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY));
+    } else {
+        for (uint32_t i = lane; i < n16; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+    }
+    __syncwarp();
+}
+
 // warp: take a byte map from the pool and replay the table into it (the set stays exact for any query)
 __device__ __forceinline__ void visited_spill(VisitedSet& v, uint32_t warp_id, int lane) {
     int slot = 0;
@@ -415,7 +591,23 @@ __device__ __forceinline__ void visited_spill(VisitedSet& v, uint32_t warp_id, i
     v.vis = v.pool_vis + (size_t)slot * v.n_pad;
     v.epoch_slot = v.pool_epochs + slot;
     v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
-    if (v.q16) {
+    if (v.smv) {
+        for (uint32_t b = lane; b <= v.s_bmask; b += 32) {
+            const uint4 w = lds_u4(v.stbl + b * 16u);
+            const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t e = (i & 1) ? (x[i >> 1] >> 16) : (x[i >> 1] & 0xFFFFu);
+                if (e != Q_EMPTY) {
+                    const uint32_t rem = e >> 1;
+                    const uint32_t home = (e & 1u) ? (b ^ smv_alt(rem, v.s_bmask)) : b;
+                    const uint32_t h = (home << v.s_rem_bits) | rem;
+                    v.vis[(h * v.q_inv) & v.q_kmask] = v.tag;
+                }
+            }
+        }
+    }
+    if (v.q16 && (!v.smv || v.ovf)) {
         for (uint32_t b = lane; b <= v.q_bmask; b += 32) {
             const uint4 w = q_bucket(v, b);
             const uint32_t x[4] = {w.x, w.y, w.z, w.w};
@@ -429,7 +621,8 @@ __device__ __forceinline__ void visited_spill(VisitedSet& v, uint32_t warp_id, i
                 }
             }
         }
-    } else {
+    }
+    if (!v.smv && !v.q16) {
         for (uint32_t i = lane; i <= v.cap_mask; i += 32) {
             const uint32_t s = __ldcg(v.tbl + i);
             if (s != VIS_EMPTY) v.vis[s] = v.tag;
@@ -442,15 +635,18 @@ __device__ __forceinline__ void visited_spill(VisitedSet& v, uint32_t warp_id, i
 __device__ __forceinline__ void visited_begin(VisitedSet& v, int lane) {
     v.count = 0;
     v.slot = -1;
-    v.hashed = v.tbl != nullptr;
-    if (v.hashed) {
+    v.hashed = v.tbl != nullptr || v.smv;
+    v.ovf = false;
+    v.s_count = 0;
+    if (v.smv) {   // (hybrid: the q16 level is cleared when the shared table closes)
+        for (uint32_t i = lane; i <= v.s_bmask; i += 32) sts_u4(v.stbl + i * 16u, make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY));
+        __syncwarp();
+    } else if (v.q16) {
+        q16_clear(v, lane);
+    } else if (v.hashed) {
         uint4* t4 = reinterpret_cast<uint4*>(v.tbl);
-        const uint32_t n16 = v.q16 ? v.q_bmask + 1u : v.cap_mask / 4 + 1u;   // 16-byte units to clear
-        if ((LEANN_K1_L2POL & 2) && v.q16) {
-            for (uint32_t i = lane; i < n16; i += 32) st_u4_evict_last(t4 + i, make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY));
-        } else {
-            for (uint32_t i = lane; i < n16; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
-        }
+        const uint32_t n16 = v.cap_mask / 4 + 1u;   // 16-byte units to clear
+        for (uint32_t i = lane; i < n16; i += 32) t4[i] = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
         __syncwarp();
     } else {
         v.tag = next_epoch(v.epoch_slot, v.vis, v.n_pad, lane);
@@ -474,7 +670,7 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t s) 
 // warp: account for `added` new members; when the table passes its limit, move to a pooled byte map
 __device__ __forceinline__ void visited_added(VisitedSet& v, uint32_t added, uint32_t warp_id, int lane) {
     v.count += added;
-    if (v.hashed && v.count > v.limit) visited_spill(v, warp_id, lane);
+    if (v.hashed && v.count - v.s_count > v.limit) visited_spill(v, warp_id, lane);   // s_count: members held by the hybrid's shared level
 }
 __device__ __forceinline__ void visited_end(VisitedSet& v, int lane) {
     if (v.slot >= 0) {
@@ -712,17 +908,31 @@ struct RegList {
 // two-list form bit for bit (the randomised parity tests include duplicate rows); the queue can no longer overflow, so the
 // `dropped` counter stays 0.
 constexpr uint32_t XBIT = 0x80000000u;
-template <int LPV, int VPL, int U, int EPL, bool SINGLE, bool Q16>
+template <int LPV, int VPL, int U, int EPL, bool SINGLE, bool Q16, bool SMV = false, bool RING = false>
 __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAdj adj, const float4 (&q)[VPL], WarpLists& w,
                                                int ef, int next_cap, int nonstrict, VisitedSet& vs, uint32_t warp_id,
                                                uint32_t start, float start_d, Counters& c, int lane,
-                                               uint32_t k, uint64_t* __restrict__ out_keys, float* __restrict__ out_dists) {
+                                               uint32_t k, uint64_t* __restrict__ out_keys, float* __restrict__ out_dists,
+                                               RowRing* ring = nullptr) {
     RegList<EPL> top, next;
     top.clear();
     if (!SINGLE) next.clear();
     float radius = CUDART_INF_F;
     if (!SINGLE) next.template insert<compat::NEXT_FIFO_AMONG_EQUALS>(start_d, start, next_cap, lane);
-    if (lane == 0) { if (Q16 && vs.hashed) q_test_and_set(vs, start); else visited_test_and_set(vs, start); }   // empty table: cannot fail
+    if (SMV && vs.hashed) {
+        bool f;
+        smv_test_and_set(vs, lane == 0 ? start : SENT, lane, f, true);
+        if (__any_sync(FULL, f)) {
+            // the one key per 2^15 that the shared table cannot hold: the hybrid opens its q16 level for it, the stand-alone
+            // form moves to a byte map
+            if (Q16) { vs.ovf = true; q16_clear(vs, lane); if (lane == 0) q_test_and_set(vs, start); }
+            else { visited_spill(vs, warp_id, lane); if (lane == 0) vs.vis[start] = vs.tag; }
+        } else if (Q16) {
+            vs.s_count = 1;
+        }
+    } else if (lane == 0) {
+        if (Q16 && vs.hashed) q_test_and_set(vs, start); else visited_test_and_set(vs, start);   // empty table: cannot fail
+    }
     __syncwarp();
     visited_added(vs, 1u, warp_id, lane);
     top.template insert<!compat::TOP_NEWCOMER_BEFORE_EQUALS, !SINGLE>(start_d, start, ef, lane);
@@ -803,8 +1013,36 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                 for (uint32_t l = 0; l < lines; ++l) prefetch_l2(r + l * 128u);
             }
 #endif
-            bool fr[NCH];
-            if (Q16 && vs.hashed) {
+            bool fr[NCH], go[NCH];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) { fr[ch] = false; go[ch] = sv[ch] != SENT; }
+            const bool hashed0 = vs.hashed;
+            bool q16_stage = Q16 && hashed0;
+            if (SMV && hashed0) {
+                // shared-memory table: the chunks go one after the other (a chunk's stores are visible to the next)
+                bool anygo = false;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) { fr[ch] = smv_test_and_set(vs, sv[ch], lane, go[ch], Q16 ? !vs.ovf : true); anygo |= go[ch]; }
+                anygo = __any_sync(FULL, anygo);
+                if (Q16) {
+                    // hybrid: unresolved keys go on to the q16 level; the shared level closes at its limit or when a key found no room
+                    if (!vs.ovf) {
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ++ch) vs.s_count += (uint32_t)__popc(__ballot_sync(FULL, fr[ch]));
+                        if (anygo || vs.s_count > vs.s_limit) { vs.ovf = true; q16_clear(vs, lane); }
+                    }
+                    q16_stage = anygo;
+                } else if (anygo) {
+                    // both buckets of some key are full: continue this query on a pooled byte map (the table is replayed into it)
+                    visited_spill(vs, warp_id, lane);
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        if (go[ch] && vs.vis[sv[ch]] != vs.tag) { vs.vis[sv[ch]] = vs.tag; fr[ch] = true; }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (q16_stage) {
                 // bucketed table: all probes of the pass advance together, one bucket load (or one CAS) per round
                 unsigned short* t16 = reinterpret_cast<unsigned short*>(vs.tbl);
                 uint32_t bk[NCH], want[NCH], emp[NCH], disp[NCH];
@@ -816,62 +1054,9 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                     bk[ch] = h >> vs.q_rem_bits;
                     want[ch] = (h & ((1u << vs.q_rem_bits) - 1u)) << 2;
                     disp[ch] = 0; emp[ch] = 0;
-                    act[ch] = sv[ch] != SENT; need_load[ch] = true; fr[ch] = false;
+                    act[ch] = go[ch]; need_load[ch] = true;
                     any |= act[ch];
                 }
-#if LEANN_K1_NOCAS
-                {   // executed by the whole warp (lanes without a key only take part in the votes)
-                    // Round 1 without atomics. The table belongs to this warp alone, so the only writers that can meet in a bucket
-                    // are the (up to 64) keys of this pass; they settle among themselves who takes which empty entry of the
-                    // snapshot and then STORE (no L2 round trip for the CAS result):
-                    //   same chunk, same bucket: __match_any_sync groups them, the i-th of the group takes the i-th empty entry; a
-                    //       key whose rank is beyond the empties moves on to the next bucket (its bucket is full after the stores);
-                    //   both chunks in one bucket: found through two 2048-bit maps in the (idle) distance staging row — bit
-                    //       (bucket & 63, bucket >> 6 & 31) set by every inserting key of a chunk, read by the other chunk; aliasing
-                    //       only produces false positives. Those keys keep the CAS path below.
-                    static_assert(NCH == 2, "cross-chunk conflict maps are written for two chunks");
-                    uint32_t* T = reinterpret_cast<uint32_t*>(w.st_dist);     // [2][64], MAX_DEG floats = 512 B
-                    reinterpret_cast<uint4*>(T)[lane] = make_uint4(0u, 0u, 0u, 0u);
-                    uint4 wv[NCH];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) if (act[ch]) wv[ch] = q_bucket(vs, bk[ch]);
-                    __syncwarp();
-                    bool ins[NCH];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        ins[ch] = false;
-                        if (act[ch]) {
-                            bool found;
-                            q_scan(wv[ch], want[ch], found, emp[ch]);
-                            need_load[ch] = false;
-                            if (found) act[ch] = false;
-                            else if (emp[ch]) { ins[ch] = true; atomicOr(&T[ch * 64 + (bk[ch] & 63u)], 1u << ((bk[ch] >> 6) & 31u)); }
-                        }
-                    }
-                    __syncwarp();
-                    any = false;
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        const bool cross = ins[ch] && ((T[(ch ^ 1) * 64 + (bk[ch] & 63u)] >> ((bk[ch] >> 6) & 31u)) & 1u);
-                        const unsigned grp = __match_any_sync(FULL, ins[ch] ? bk[ch] : (0x80000000u | (uint32_t)lane));
-                        if (ins[ch] && !cross) {
-                            const int rank = __popc(grp & ((1u << lane) - 1u));
-                            if (rank < __popc(emp[ch])) {
-                                uint32_t m = emp[ch];
-                                for (int r = 0; r < rank; ++r) m &= m - 1u;
-                                t16[bk[ch] * 8 + (__ffs((int)m) - 1)] = (unsigned short)want[ch];   // displacement 0
-                                fr[ch] = true;
-                                act[ch] = false;
-                            } else {
-                                emp[ch] = 0;   // the peers of this pass fill the bucket
-                            }
-                        }
-                        if (act[ch] && emp[ch] == 0) { disp[ch] = 1; bk[ch]++; need_load[ch] = true; }
-                        any |= act[ch];
-                    }
-                    __syncwarp();   // the stores above are ordered before the bucket loads of the later rounds
-                }
-#endif
                 while (any) {
                     uint4 w[NCH];
 #pragma unroll
@@ -923,7 +1108,7 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                         }
                     __syncwarp();
                 }
-            } else if (!Q16 && vs.hashed) {
+            } else if (!Q16 && !SMV && hashed0) {
                 uint32_t h[NCH];
                 bool act[NCH];
                 bool any = false;
@@ -942,7 +1127,7 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
                             else { h[ch] = (h[ch] + 1u) & vs.cap_mask; any = true; }
                         }
                 }
-            } else {
+            } else if (!hashed0) {
                 uint8_t tg[NCH];
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) tg[ch] = sv[ch] != SENT ? vs.vis[sv[ch]] : vs.tag;
@@ -964,14 +1149,16 @@ __device__ __forceinline__ int beam_level_regs(const GraphView& g, const LevelAd
         c.n_dist += cnt;
         visited_added(vs, (uint32_t)cnt, warp_id, lane);
         {
-            constexpr int BATCH = U * (32 / LPV);
+            // rows beyond the first batch (ring: beyond the stages requested at once) are pulled into L2 now
+            constexpr int BATCH = RING ? RING_ROWS * RING_STAGES : U * (32 / LPV);
             const uint32_t lines = (g.d4 * 16u + 127u) >> 7;
             for (int j = BATCH + lane; j < cnt; j += 32) {
                 const char* r = reinterpret_cast<const char*>(g.vecs + (size_t)w.st_slot[j] * g.d4);
                 for (uint32_t l = 0; l < lines; ++l) prefetch_l2(r + l * 128u);
             }
         }
-        eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+        if constexpr (RING) eval_distances_ring<LPV, VPL>(*ring, g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
+        else eval_distances<LPV, VPL, U>(g.vecs, g.d4, g.metric, q, w.st_slot, w.st_dist, cnt, lane);
         // ---- replay the inserts in list order (usearch loop), lists in registers ----
         for (int base = 0; base < cnt; base += 32) {
             const int j = base + lane;

@@ -19,7 +19,10 @@ namespace leann {
 
 // EPL > 0: `top` / `next` live in registers (RegList<EPL>, graph_device.cuh); the host picks that instantiation for short
 // rows when max(ef, queue capacity) <= 32 * EPL and no mask is set. Shared memory then holds only the staging row.
-template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE = false, bool Q16 = false>
+template <int LPV, int VPL>
+constexpr size_t ring_bytes() { return (size_t)RING_STAGES * RING_ROWS * VPL * LPV * 16 + 16 * ((RING_STAGES * 8 + 15) / 16); }
+
+template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE = false, bool Q16 = false, bool SMV = false, bool RING = false>
 __global__ void __launch_bounds__(128, MINB)
 graph_search_kernel(const GraphView g, const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -30,7 +33,8 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
 
     const uint32_t ef_pad = EPL > 0 ? 0u : ((p.ef + 31u) & ~31u);
     const uint32_t ncapp = EPL > 0 ? 0u : p.next_capp;
-    const size_t per_warp = (size_t)ef_pad * 8 + (size_t)ncapp * 8 + (size_t)MAX_DEG * 8;
+    constexpr size_t vis_bytes = SMV ? (Q16 ? HYB_BYTES : SMV_BYTES) : 0u;
+    const size_t per_warp = (size_t)ef_pad * 8 + (size_t)ncapp * 8 + (size_t)MAX_DEG * 8 + vis_bytes + (RING ? ring_bytes<LPV, VPL>() : 0u);
     unsigned char* base = smem_raw + per_warp * warp_in_block;
     WarpLists w;
     w.top_d = reinterpret_cast<float*>(base);
@@ -57,6 +61,25 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         vs.tbl = p.vhash + (size_t)warp_global * (p.vhash_cap / 2u);
         vs.limit = p.vhash_cap / 8u * 5u;
     }
+    if (SMV) {      // two-choice table in this warp's shared memory (after the staging rows)
+        vs.smv = true;
+        vs.stbl = (uint32_t)__cvta_generic_to_shared(base + (size_t)MAX_DEG * 8);
+        vs.s_bmask = (Q16 ? HYB_BUCKETS : SMV_BUCKETS) - 1u;
+        vs.s_rem_bits = p.q_key_bits - (Q16 ? 9u : 10u);
+        if (Q16) {  // hybrid: first level here, overflow level = the q16 table set up above
+            vs.s_limit = p.smv_limit;
+        } else {    // stand-alone
+            vs.q16 = false; vs.tbl = nullptr; vs.vis = nullptr; vs.epoch_slot = nullptr;
+            vs.limit = p.smv_limit;
+        }
+    }
+
+    RowRing ring{0u, 0u, 0u};
+    if constexpr (RING) {   // rows of a hop travel through this warp's shared-memory ring (graph_device.cuh)
+        ring.rows = (uint32_t)__cvta_generic_to_shared(base + (size_t)MAX_DEG * 8 + vis_bytes);
+        ring.bars = ring.rows + (uint32_t)(RING_STAGES * RING_ROWS * VPL * LPV * 16);
+        ring_init(ring, lane);
+    }
 
     for (;;) {
         uint32_t qi = 0;
@@ -82,9 +105,9 @@ graph_search_kernel(const GraphView g, const SearchParams p) {
         LevelAdj adj{g.adj0, g.adjU, g.upper_base, g.deg0, 0};
         int cnt;
         if constexpr (EPL > 0) {
-            cnt = beam_level_regs<LPV, VPL, U, EPL, SINGLE, Q16>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
+            cnt = beam_level_regs<LPV, VPL, U, EPL, SINGLE, Q16, SMV, RING>(g, adj, q, w, (int)p.ef, (int)p.next_cap, p.nonstrict_term, vs,
                                                     (uint32_t)warp_global, cur, cur_d, c, lane, p.k,
-                                                    p.out_keys + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k);
+                                                    p.out_keys + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k, &ring);
             visited_end(vs, lane);
         } else {
             beam_level<LPV, VPL, U, (LPV < 32)>(g, adj, q, w, (int)p.ef, (int)p.next_cap, (int)p.next_capp - 1, p.nonstrict_term,
@@ -229,7 +252,7 @@ inline bool use_single_list(const GraphView& g, const SearchParams& p) {
            getenv("LEANN_CUDA_DISABLE_SINGLE_LIST") == nullptr;
 }
 
-template <int LPV, int VPL, int U, int MINB, int EPL = 0, bool SINGLE = false, bool Q16 = false>
+template <int LPV, int VPL, int U, int MINB, int EPL = 0, bool SINGLE = false, bool Q16 = false, bool SMV = false, bool RING = false>
 int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op);
 
 // short rows, diskann-rs stop rule: register-list instantiation (one list with an expanded bit; u32 / byte-map or q16
@@ -237,11 +260,30 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
 // 1M x 256 HNSW indexes it measured 3-9 % slower than the shared-memory lists (two sorted inserts per accepted neighbour).
 template <int LPV, int VPL, int U, int MINB>
 int launch_reg(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
+    if (p.smem_vis == 1) {
+        // visited tables in shared memory, stand-alone (graph_device.cuh "smv"): 3 CTAs of 4 warps per SM, so the register
+        // budget is no longer 80 per thread; unroll 3 measured best of {2, 3, 4} (profiles/r2_k1_smv_ab.log); A/B switch
+        // LEANN_CUDA_SMV_U (read per launch)
+        const char* e = getenv("LEANN_CUDA_SMV_U");
+        const int u = e ? atoi(e) : 3;
+        if (u == 4) return launch_t<LPV, VPL, 4, 3, REG_EPL, true, false, true>(g, p, stream, op);
+        if (u == 2) return launch_t<LPV, VPL, 2, 3, REG_EPL, true, false, true>(g, p, stream, op);
+        return launch_t<LPV, VPL, 3, 3, REG_EPL, true, false, true>(g, p, stream, op);
+    }
+    // hybrid: shared-memory first level + q16 overflow level, the usual occupancy (op 1 is asked before the q16 table exists)
+    if (p.smem_vis == 2) return launch_t<LPV, VPL, U, MINB, REG_EPL, true, true, true>(g, p, stream, op);
     const bool q16 = p.vhash != nullptr && p.vhash16 != 0;
+    if (p.row_ring) {
+        // rows through a shared-memory ring of bulk async copies (graph_device.cuh eval_distances_ring). Bit-identical and OFF by
+        // default: 4.88 vs 4.66 ms at L = 100, 2.72 vs 2.61 ms at L = 50 on the 12.5M x 96 shard; with 7 CTAs per SM (72
+        // registers) 5.66 / 3.15 ms (profiles/r2_k1_ring_ab.log)
+        return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true, false, true>(g, p, stream, op)
+                   : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false, false, true>(g, p, stream, op);
+    }
     return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false>(g, p, stream, op);
 }
 
-template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE, bool Q16>
+template <int LPV, int VPL, int U, int MINB, int EPL, bool SINGLE, bool Q16, bool SMV, bool RING>
 int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
     if constexpr (EPL == 0 && LPV < 32) {
         // short rows: the register-list instantiation when the lists fit (small batches keep the cooperative kernel)
@@ -249,8 +291,9 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
         if (!off && p.coop_ctas == 0 && use_reg_lists(p) && use_single_list(g, p)) return launch_reg<LPV, VPL, U, MINB>(g, p, stream, op);
     }
     const int warps_per_block = 4;
-    size_t smem = (EPL > 0 ? (size_t)MAX_DEG * 8 : graph_search_smem_per_warp(p.ef, p.next_capp)) * warps_per_block;
-    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL, SINGLE, Q16>;
+    size_t smem = (EPL > 0 ? (size_t)MAX_DEG * 8 + (SMV ? (Q16 ? HYB_BYTES : SMV_BYTES) : 0u) + (RING ? ring_bytes<LPV, VPL>() : 0u)
+                           : graph_search_smem_per_warp(p.ef, p.next_capp)) * warps_per_block;
+    auto kern = graph_search_kernel<LPV, VPL, U, MINB, EPL, SINGLE, Q16, SMV, RING>;
     if (smem > 48 * 1024) LEANN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (op == 1) {
         int blocks_per_sm = 0;
@@ -312,9 +355,9 @@ bool graph_search_uses_reg_lists(const GraphView& g, const SearchParams& p) {
            getenv("LEANN_CUDA_DISABLE_REG_LISTS") == nullptr;
 }
 
-int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp) {
+int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp, int nonstrict_term, int smem_vis, int row_ring) {
     SearchParams p{};
-    p.ef = ef; p.next_capp = next_capp;
+    p.ef = ef; p.next_capp = next_capp; p.nonstrict_term = nonstrict_term; p.smem_vis = smem_vis; p.row_ring = row_ring;
     return dispatch_search(g, p, nullptr, 1);
 }
 

@@ -132,6 +132,8 @@ struct SearchParams {
     uint32_t* vhash; uint32_t vhash_cap;              // nullable: per-warp visited hash tables (large-index mode)
     uint32_t vhash16, q_rem_bits, q_key_bits, q_inv;  // vhash16 != 0: the tables hold vhash_cap 16-bit quotiented entries in buckets of 8
     uint32_t* pool_locks; uint32_t pool_slots;        // byte-map spill pool of the large-index mode (maps in `visited`)
+    int row_ring;                                     // != 0: rows of a hop through a shared-memory ring of bulk async copies (A/B form)
+    int smem_vis; uint32_t smv_limit;                 // smem_vis != 0: register-list kernel with the visited table in shared memory (spill above smv_limit entries)
     int coop_warps;  // 4 or 8 warps per CTA of the small-batch kernel
     int coop_ctas;   // > 0: small batch, launch this many multi-warp CTAs (one query each at a time) instead of the warp pool
 };
@@ -141,7 +143,7 @@ int reduction_lanes(size_t dims);
 void launch_graph_search(const GraphView& g, const SearchParams& p, cudaStream_t stream);
 size_t graph_search_smem_per_warp(uint32_t ef, uint32_t next_capp);
 int graph_search_max_warps(int device);
-int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp);
+int graph_search_warps_per_sm(const GraphView& g, uint32_t ef, uint32_t next_capp, int nonstrict_term = 0, int smem_vis = 0, int row_ring = 0);
 bool graph_search_uses_reg_lists(const GraphView& g, const SearchParams& p);   // register-list kernel (short rows): supports the q16 table
 
 // Exact scan (K2 + K2r)

@@ -243,7 +243,7 @@ def test_visited_set_modes_are_equivalent(orc, pkg, tmp_path):
         qt = torch.from_numpy(q).cuda()
         for ef in (32, 200):
             ok, od, oc, ost = g.search(q, k, ef, lanes=pkg.reduction_lanes(d), next_cap=pkg.queue_capacity(ef, False))
-            for mode in (0, 1024, 1, 65536):
+            for mode in (0, 1024, 1, 65536, 2, 3, 4, 5):   # 2-5: shared-memory tables (short rows, ef <= 128); 3, 5 = every traversal overflows / spills
                 s.set_visited_hash(mode)
                 for lo, hi in ((0, 500), (0, 40)):            # warp pool, CTA per query
                     stats = torch.zeros((hi - lo, 4), dtype=torch.int64, device="cuda")
@@ -254,6 +254,42 @@ def test_visited_set_modes_are_equivalent(orc, pkg, tmp_path):
         assert ost[:, 0].max() > 768          # the 1024-slot tables did have to spill
         with pytest.raises(pkg.LeannCudaError):
             s.set_visited_hash(100)
+        s.set_visited_hash(0)
+
+
+def test_row_ring_form_is_bit_identical(pkg, tmp_path):
+    """A/B form of the short-row traversal: rows of a hop as bulk async copies through a shared-memory ring
+    (LEANN_CUDA_RING=1, read once per process, hence the child process). Same index file, same queries: keys, distance bits
+    and work counters must equal the default form's, for both visited-set forms the register-list kernel supports."""
+    import subprocess, sys, json, zlib, os
+    import torch
+    n, d, k = 40000, 96, 10
+    x, q = make_data(n, d, 29, nq=600, normalize=False)
+    base = str(tmp_path / "ring.leann")
+    pkg.DiskAnnSearcher.build(x, graph_degree=64, complexity=100, metric=pkg.METRIC_L2SQ).save(base)
+    np.save(str(tmp_path / "q.npy"), q)
+    prog = (
+        "import sys, json, zlib, numpy as np, torch\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "import leann_rs_b200 as P\n"
+        f"s = P.DiskAnnSearcher.load({base!r}, {d}, metric=P.METRIC_L2SQ)\n"
+        f"q = torch.from_numpy(np.load({str(tmp_path / 'q.npy')!r})).cuda()\n"
+        "out = {}\n"
+        "for mode in (0, 65536):\n"
+        "    s.set_visited_hash(mode)\n"
+        "    for ef in (32, 100):\n"
+        "        st = torch.zeros((q.shape[0], 4), dtype=torch.int64, device='cuda')\n"
+        f"        kk, dd, cc = s.search_device(q, {k}, ef, stats=st)\n"
+        "        out[f'{mode}/{ef}'] = [zlib.crc32(kk.cpu().numpy().tobytes()), zlib.crc32(dd.cpu().numpy().tobytes()), zlib.crc32(st[:, :3].cpu().numpy().tobytes())]\n"
+        "print('RESULT ' + json.dumps(out))\n")
+    res = {}
+    for ring in ("0", "1"):
+        env = dict(os.environ, LEANN_CUDA_RING=ring)
+        r = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[ring] = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert res["0"] == res["1"], res
+    assert len({tuple(v) for kq, v in res["0"].items() if kq.endswith("/100")}) == 1      # visited-set forms agree as well
 
 
 def test_handmade_index_hand_traced_on_gpu(pkg, tmp_path):
