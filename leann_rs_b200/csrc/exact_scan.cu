@@ -15,6 +15,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "scan_common.h"
@@ -478,12 +479,20 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         LEANN_CUDA_CHECK(cudaStreamWaitEvent(aux.helper, aux.fork, 0));
     }
 
-    // Round boundaries: the first chunk holds SCAN_CAP rows (cannot overflow), later ones grow geometrically so
-    // that the expected number of survivors per query and round stays near growth * k.
+    // Round boundaries: the first chunk (f32 tiles, every row is a candidate, cannot overflow) holds SCAN_CAP rows, later
+    // chunks grow geometrically so that the expected number of survivors per query and round stays near growth * k.
+    // A smaller first chunk (LEANN_CUDA_SCAN_FIRST = rows, A/B) saves tile work but adds a round, and a round costs about 1 ms
+    // of launches, re-rank and select for 10 000 queries: 1024 rows measured 13.3 vs 12.4 ms on 1.25M x 384 and 66.9 vs 67.2 ms
+    // on 10M x 384 (profiles/r2_k2_first_chunk_ab.log): left at SCAN_CAP.
     const uint32_t growth = std::max<uint32_t>(2u, SCAN_CAP / (8u * k));
+    uint32_t first_rows = SCAN_CAP;
+    {
+        static const int first_env = [] { const char* e = getenv("LEANN_CUDA_SCAN_FIRST"); return e ? atoi(e) : 0; }();
+        if (first_env >= 128) first_rows = std::min<uint32_t>(SCAN_CAP, std::max<uint32_t>((uint32_t)first_env, k));
+    }
     std::vector<std::pair<uint32_t, uint32_t>> rounds;
     for (uint32_t r0 = 0; r0 < f.n;) {
-        uint64_t want = r0 == 0 ? SCAN_CAP : (uint64_t)r0 * growth;
+        uint64_t want = r0 == 0 ? first_rows : (uint64_t)r0 * growth;
         uint32_t r1 = (uint32_t)std::min<uint64_t>(f.n, (uint64_t)r0 + want);
         rounds.emplace_back(r0, r1);
         r0 = r1;
@@ -498,7 +507,7 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
 
     auto begin_job = [&](ScanJob& J) {
         scan_init_kernel<<<(J.nq + 255) / 256, 256, 0, J.stream>>>(J.s.cand_cnt, J.s.best_cnt, J.s.thr, J.nq, J.s.overflow,
-                                                                   (uint32_t)std::min<uint64_t>(f.n, SCAN_CAP));
+                                                                   (uint32_t)std::min<uint64_t>(f.n, first_rows));
         launch_pad_rows(d_queries + (size_t)J.q0 * f.d, J.s.qpad, J.nq, f.d, f.d4, J.stream);
         if (use_tc) exact_scan_tc_queries(J.s.qpad, J.nq, f.d4, tv->dp8, f.metric, tv->xmax_bits, J.ts, J.stream);
     };
