@@ -414,7 +414,7 @@ size_t exact_scan_scratch_bytes(uint32_t d4, uint32_t nq, uint32_t k) {
     return align256((size_t)nq * SCAN_CAP * 8) + align256((size_t)nq * 4) + align256((size_t)nq * kpad * 8) +
            align256((size_t)nq * 4) + align256((size_t)nq * 8) + 256 + align256((size_t)nq * d4max * 16) +
            // tensor path: bf16 queries, |q|, dot thresholds, candidate row ids
-           align256((size_t)nq * dp8 * 2) + 3 * align256((size_t)nq * 4) + align256((size_t)nq * SCAN_CAP * 4);
+           align256((size_t)nq * dp8 * 2) + 4 * align256((size_t)nq * 4) + 2 * align256((size_t)nq * SCAN_CAP * 4);
 }
 
 // One half (or all) of a query batch: its own slice of every per-query scratch array, its own overflow words and stream.
@@ -450,7 +450,9 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         ts.qnorm = (float*)p; p += align256((size_t)nq * 4);
         ts.qres = (float*)p; p += align256((size_t)nq * 4);
         ts.thr_dot = (float*)p; p += align256((size_t)nq * 4);
+        ts.cut_slack = (float*)p; p += align256((size_t)nq * 4);
         ts.cand_ids = (uint32_t*)p; p += align256((size_t)nq * SCAN_CAP * 4);
+        ts.cand_sc = (float*)p; p += align256((size_t)nq * SCAN_CAP * 4);
     }
     if ((size_t)(p - (unsigned char*)scratch) > scratch_bytes) throw Error(LEANN_ERR_INVALID_ARG, "exact scan: scratch too small");
 
@@ -472,6 +474,7 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         if (use_tc) {
             J.ts.q_bf16 = (unsigned char*)ts.q_bf16 + (size_t)J.q0 * tv->dp8 * 2; J.ts.qnorm = ts.qnorm + J.q0; J.ts.qres = ts.qres + J.q0;
             J.ts.thr_dot = ts.thr_dot + J.q0; J.ts.cand_ids = ts.cand_ids + (size_t)J.q0 * SCAN_CAP;
+            J.ts.cut_slack = ts.cut_slack + J.q0; J.ts.cand_sc = ts.cand_sc + (size_t)J.q0 * SCAN_CAP;
         }
     }
     if (split) {   // the helper stream starts after everything already queued on the caller's stream
@@ -516,7 +519,7 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
         dim3 grid((r1 - r0 + TN - 1) / TN, (J.nq + TM - 1) / TM);
         if (use_tc && ri > 0) {
             // tensor-core pass + fp32 re-rank for every chunk after the first
-            exact_scan_tc_round(f, *tv, J.s, J.ts, J.nq, r0, r1, d_mask, SCAN_CAP, sms, J.stream);
+            exact_scan_tc_round(f, *tv, J.s, J.ts, J.nq, k, r0, r1, d_mask, SCAN_CAP, sms, J.stream);
         } else {
             const bool direct = ri == 0 && attempt == 0;   // no threshold yet: slot = row offset, cand_cnt preset by scan_init
 #define LEANN_TILE(M)                                                                                                            \

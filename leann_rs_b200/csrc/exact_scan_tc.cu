@@ -47,7 +47,7 @@ constexpr int TC_B_BYTES = TC_NH * TC_K * 2;   // 16 KB: one k-block of this CTA
 constexpr int TC_MAX_RES_KB = 7;  // query tile stays resident in shared memory up to 7 k-blocks (d <= 448)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 256;
-constexpr int TC_QBUF = 16;      // survivors buffered per query row before one slot reservation
+constexpr int TC_QBUF = 8;       // survivors (row id + tensor-core score) buffered per query row before one slot reservation
 constexpr int TC_BAR_BYTES = 512;
 constexpr size_t TC_SMEM_MAX = 225280;  // 220 KB of the 227 KB opt-in limit: the rest lets a select_kernel<true> / rerank CTA of the
                                         // other query half share the SM (launch_exact_scan)
@@ -151,6 +151,7 @@ struct TcParams {
     const float* thr_dot;          // [nq] strict candidate threshold in dot space (-inf = everything)
     const uint64_t* mask;          // nullable
     uint32_t* cand_ids;            // [nq][cap]
+    float* cand_sc;                // [nq][cap] tensor-core score of each survivor (rerank_kernel's approximate cut)
     uint32_t* cand_cnt;            // [nq]
     uint32_t cap;
     uint32_t* overflow;
@@ -177,7 +178,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t* a_full = bars + 2 * TC_MAX_STAGES + 4;      // [7] per resident k-block; leader's copy
     uint64_t* a_empty = a_full + TC_MAX_RES_KB;           // [7] one per CTA (multicast commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + TC_MAX_RES_KB);
-    uint32_t* s_qbuf = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + TC_BAR_BYTES);  // [TC_QBUF][128]
+    uint32_t* s_qbuf = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + TC_BAR_BYTES);  // [2][TC_QBUF][128]: ids, scores
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -289,13 +290,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const float T = q < p.nq ? p.thr_dot[q] : CUDART_INF_F;   // survivor <=> score > T
             // survivors are buffered per thread and appended with ONE slot reservation per TC_QBUF rows
             uint32_t* myq = s_qbuf + (quad * 32 + lane);   // slot i at myq[i * 128], conflict-free
+            uint32_t* mys = myq + TC_QBUF * 128;           // the survivor's score bits
             int nbuf = 0;
             auto flush = [&]() {
                 if (nbuf == 0) return;
                 uint32_t pos = atomicAdd(&p.cand_cnt[q], (uint32_t)nbuf);
                 for (int i = 0; i < nbuf; ++i) {
-                    if (pos + i < p.cap) p.cand_ids[(size_t)q * p.cap + pos + i] = myq[i * 128];
-                    else *p.overflow = 1u;
+                    if (pos + i < p.cap) {
+                        p.cand_ids[(size_t)q * p.cap + pos + i] = myq[i * 128];
+                        p.cand_sc[(size_t)q * p.cap + pos + i] = __uint_as_float(mys[i * 128]);
+                    } else {
+                        *p.overflow = 1u;
+                    }
                 }
                 nbuf = 0;
             };
@@ -316,8 +322,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         m &= m - 1u;
                         const uint32_t row = row_base + (uint32_t)c + j;
                         if (row < p.r1 && (!p.mask || ((p.mask[row >> 6] >> (row & 63u)) & 1ull))) {
-                            myq[(nbuf++) * 128] = row;
-                            if (nbuf == TC_QBUF) flush();
+                            uint32_t sc = r[0];   // r[j] by selects: a dynamic index would send the 32 registers to local memory
+#pragma unroll
+                            for (int jj = 1; jj < 32; ++jj) sc = ((uint32_t)jj == j) ? r[jj] : sc;
+                            myq[nbuf * 128] = row;
+                            mys[nbuf * 128] = sc;
+                            if (++nbuf == TC_QBUF) flush();
                         }
                     }
                 }
@@ -448,12 +458,27 @@ __device__ __forceinline__ float tc_l2_threshold(float dk, float qnorm, float qr
     return nextafterf(T - fabsf(T) * 1e-6f - (L + dk) * 1e-6f, -CUDART_INF_F);   // the float operations above round either way
 }
 
-// thr key (packed rank key of the exact k-th best, or ~0) -> dot-space candidate threshold.
+// thr key (packed rank key of the exact k-th best, or ~0) -> dot-space candidate threshold; and, per query, the slack of
+// rerank_kernel's approximate cut: cut_slack = 2 (eps + delta), eps = the bound on |tensor-core score - exact score| used for
+// the threshold, delta = 5e-5 |q| max|x| (L2: 5e-5 (|q| + max|x|)^2) for the f32 rounding of the re-rank itself.
 __global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr, const float* __restrict__ qnorm,
                                      const float* __restrict__ qres, const uint32_t* xmax_bits, uint32_t dp8, uint32_t nq, int metric,
-                                     float* __restrict__ thr_dot) {
+                                     float* __restrict__ thr_dot, float* __restrict__ cut_slack) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    const float xmax = __uint_as_float(xmax_bits[0]);
+    if (metric == LEANN_METRIC_L2SQ) {
+        // tc_l2_threshold(0) = L / 2 - eps (rounded down): recover a bound on eps from it
+        const float L = qnorm[q] * qnorm[q] * 0.99975f;
+        const float eps = (0.5f * L - tc_l2_threshold(0.f, qnorm[q], qres[q], xmax_bits, dp8)) * 1.001f;
+        const float qx = qnorm[q] + xmax;
+        cut_slack[q] = 2.f * (eps + 5e-5f * qx * qx) * 1.001f;
+    } else {
+        // IP metrics return 1 - dot: two rows must also differ by more than the rounding of that subtraction, or the cut could
+        // drop the lower row id of a pair that ties after rounding
+        const float ip = metric == LEANN_METRIC_DOT_DESC ? 0.f : 4.8e-7f * (1.0f + qnorm[q] * xmax);
+        cut_slack[q] = 2.f * (tc_eps(qnorm[q], qres[q], xmax_bits, dp8) + 5e-5f * qnorm[q] * xmax + ip) * 1.001f;
+    }
     unsigned long long key = thr[q];
     if (key == ~0ull) { thr_dot[q] = -CUDART_INF_F; return; }
     uint32_t ok = (uint32_t)(key >> 32);
@@ -465,16 +490,69 @@ __global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr,
 }
 
 // K2r: exact f32 score of every survivor -> packed rank key in cand[q][i].
+// Approximate cut (cand_sc != nullptr): a round keeps every row whose tensor-core score beats (k-th best so far) - eps,
+// about (growth - 1) k rows per query, of which at most k can enter the top-k. With a = the k-th largest tensor-core score
+// among the survivors, at least k survivors have an exact score >= a - eps, so a survivor below a - 2 eps (minus the f32
+// slack of the re-rank, dot_threshold_kernel) cannot be among the k best: it gets the sentinel key instead of a 4 d-byte row
+// read. (Clamped IP distances tie at 0 for every dot >= 1: rows that may reach 1 are never cut.) One block per query; the
+// k-th largest is a 4-pass radix select over the scores in global memory (a few hundred values; the block must fit beside a
+// resident scan_tc CTA, so nothing is staged in shared memory).
 __global__ void __launch_bounds__(256)
 rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32_t d4, uint32_t nq, int metric,
               const uint32_t* __restrict__ cand_ids, const uint32_t* __restrict__ cand_cnt, uint32_t cap,
-              unsigned long long* __restrict__ cand) {
+              unsigned long long* __restrict__ cand, const float* __restrict__ cand_sc, const float* __restrict__ cut_slack, uint32_t k) {
+    __shared__ uint32_t s_hist[259];
     const uint32_t q = blockIdx.x;
     if (q >= nq) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t n = cand_cnt[q];
     if (n > cap) n = cap;
+    float cut = -CUDART_INF_F;
+    if (cand_sc != nullptr && n > 2 * k) {   // block-uniform
+        const float* sc = cand_sc + (size_t)q * cap;
+        uint32_t prefix = 0, remaining = k - 1;   // k-th smallest of ~order(score) = k-th largest score
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t v = ~scan_order_f32(sc[i]);
+                if (pass == 0 || (v >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(v >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t c[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; sum += c[j]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                    if (lane >= off) incl += t;
+                }
+                const uint32_t before = incl - sum;
+                if (remaining >= before && remaining < incl) {   // exactly one lane
+                    uint32_t acc = before;
+                    int j = 0;
+                    while (j < 7 && remaining >= acc + c[j]) { acc += c[j]; ++j; }
+                    s_hist[256] = (uint32_t)lane * 8u + (uint32_t)j;
+                    s_hist[257] = acc;
+                }
+            }
+            __syncthreads();
+            prefix |= s_hist[256] << shift;
+            remaining -= s_hist[257];
+            __syncthreads();
+        }
+        const float a = scan_unorder_f32(~prefix);
+        cut = a - cut_slack[q];
+        if (metric == LEANN_METRIC_IP_CLAMP) cut = fminf(cut, 1.0f - cut_slack[q]);
+    }
     for (uint32_t i = warp; i < n; i += blockDim.x >> 5) {
+        if (cand_sc != nullptr && cand_sc[(size_t)q * cap + i] < cut) {
+            if (lane == 0) cand[(size_t)q * cap + i] = ~0ull;
+            continue;
+        }
         const uint32_t row = cand_ids[(size_t)q * cap + i];
         const float4* x = X + (size_t)row * d4;
         const float4* qq = Q + (size_t)q * d4;
@@ -580,9 +658,9 @@ void exact_scan_tc_prepare(const float4* vecs, size_t n, uint32_t d4, uint32_t d
 
 // One round over rows [r0, r1): tensor pass -> re-rank. `s.thr` must hold the current exact thresholds;
 // on return s.cand / s.cand_cnt hold exact packed keys ready for select_kernel.
-void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq,
+void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq, uint32_t k,
                          uint32_t r0, uint32_t r1, const uint64_t* d_mask, uint32_t cap, int sms, cudaStream_t stream) {
-    dot_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.thr, ts.qnorm, ts.qres, tv.xmax_bits, tv.dp8, nq, f.metric, ts.thr_dot);
+    dot_threshold_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(s.thr, ts.qnorm, ts.qres, tv.xmax_bits, tv.dp8, nq, f.metric, ts.thr_dot, ts.cut_slack);
     CUtensorMap mq = make_map(ts.q_bf16, nq, tv.dp8, TC_M);
     CUtensorMap mx = make_map(tv.x_bf16, f.n, tv.dp8, TC_NH);
     TcParams p;
@@ -593,7 +671,7 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
     const bool resident = p.kblocks <= (uint32_t)TC_MAX_RES_KB;
     const size_t a_bytes = resident ? (size_t)p.kblocks * TC_A_BYTES : 0;
     const size_t stage_bytes = resident ? TC_B_BYTES : TC_A_BYTES + TC_B_BYTES;
-    const size_t fixed = 1024 /*align*/ + TC_BAR_BYTES + (size_t)128 * TC_QBUF * 4 + a_bytes;
+    const size_t fixed = 1024 /*align*/ + TC_BAR_BYTES + (size_t)2 * 128 * TC_QBUF * 4 + a_bytes;
     p.stages = (uint32_t)std::min<size_t>(TC_MAX_STAGES, (TC_SMEM_MAX - fixed) / stage_bytes);
     const size_t smem = fixed + (size_t)p.stages * stage_bytes;
     const uint32_t max_pairs = (uint32_t)std::max(1, sms / 2);
@@ -601,7 +679,7 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
     uint64_t want = (uint64_t)p.tiles_total * p.n_qpairs / ((uint64_t)max_pairs * 6u);
     p.group = (uint32_t)std::min<uint64_t>(32u, std::max<uint64_t>(4u, want));
     p.n_groups = (p.tiles_total + p.group - 1) / p.group;
-    p.thr_dot = ts.thr_dot; p.mask = d_mask; p.cand_ids = ts.cand_ids; p.cand_cnt = s.cand_cnt; p.cap = cap; p.overflow = s.overflow;
+    p.thr_dot = ts.thr_dot; p.mask = d_mask; p.cand_ids = ts.cand_ids; p.cand_sc = ts.cand_sc; p.cand_cnt = s.cand_cnt; p.cap = cap; p.overflow = s.overflow;
     const uint32_t items = p.n_qpairs * p.n_groups;
     const int grid = 2 * (int)std::min<uint32_t>(max_pairs, items);
     static unsigned long long attr_seen = 0;   // cudaFuncSetAttribute is per device
@@ -618,7 +696,9 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
     if (resident) scan_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mq, mx, p);
     else scan_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(mq, mx, p);
     LEANN_CUDA_CHECK(cudaGetLastError());
-    rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand);
+    static const bool no_cut = getenv("LEANN_CUDA_SCAN_NO_CUT") != nullptr;   // A/B switch for benchmarks
+    rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand,
+                                          no_cut ? nullptr : ts.cand_sc, ts.cut_slack, k);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -627,7 +707,7 @@ void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScr
 void exact_scan_tc_canonical_first(const FlatView& f, const ScanScratch& s, const TcScratch& ts, uint32_t nq, uint32_t kpad, uint32_t cap,
                                    cudaStream_t stream) {
     requeue_best_kernel<<<nq, 128, 0, stream>>>(s.best, s.best_cnt, kpad, s.thr, ts.cand_ids, s.cand_cnt, cap, nq);
-    rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand);
+    rerank_kernel<<<nq, 256, 0, stream>>>(f.vecs, s.qpad, f.d4, nq, f.metric, ts.cand_ids, s.cand_cnt, cap, s.cand, nullptr, nullptr, 0u);
     LEANN_CUDA_CHECK(cudaGetLastError());
 }
 

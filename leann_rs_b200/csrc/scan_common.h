@@ -33,7 +33,9 @@ struct TcScratch {                 // per-call tensor-path scratch
     float* qnorm;                  // [nq] |q|
     float* qres;                   // [nq] |q^ - q| (bf16 rounding residual)
     float* thr_dot;                // [nq]
+    float* cut_slack;              // [nq] slack of the re-rank's approximate cut (dot_threshold_kernel)
     uint32_t* cand_ids;            // [nq][cap]
+    float* cand_sc;                // [nq][cap] tensor-core score of each survivor
 };
 
 bool exact_scan_tc_supported(const FlatView& f, uint32_t nq);
@@ -44,7 +46,7 @@ void exact_scan_tc_queries(const float4* qpad, uint32_t nq, uint32_t d4, uint32_
                            const TcScratch& ts, cudaStream_t stream);
 void exact_scan_tc_canonical_first(const FlatView& f, const ScanScratch& s, const TcScratch& ts, uint32_t nq, uint32_t kpad, uint32_t cap,
                                    cudaStream_t stream);
-void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq,
+void exact_scan_tc_round(const FlatView& f, const TcIndexView& tv, const ScanScratch& s, const TcScratch& ts, uint32_t nq, uint32_t k,
                          uint32_t r0, uint32_t r1, const uint64_t* d_mask, uint32_t cap, int sms, cudaStream_t stream);
 
 }  // namespace leann
