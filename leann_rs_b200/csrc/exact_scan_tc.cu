@@ -493,20 +493,23 @@ __global__ void dot_threshold_kernel(const unsigned long long* __restrict__ thr,
 // Approximate cut (cand_sc != nullptr): a round keeps every row whose tensor-core score beats (k-th best so far) - eps,
 // about (growth - 1) k rows per query, of which at most k can enter the top-k. With a = the k-th largest tensor-core score
 // among the survivors, at least k survivors have an exact score >= a - eps, so a survivor below a - 2 eps (minus the f32
-// slack of the re-rank, dot_threshold_kernel) cannot be among the k best: it gets the sentinel key instead of a 4 d-byte row
-// read. (Clamped IP distances tie at 0 for every dot >= 1: rows that may reach 1 are never cut.) One block per query; the
-// k-th largest is a 4-pass radix select over the scores in global memory (a few hundred values; the block must fit beside a
+// slack of the re-rank, dot_threshold_kernel) cannot be among the k best: it is dropped instead of costing a 4 d-byte row
+// read; the kept keys are written compacted and cand_cnt becomes their number. (Clamped IP distances tie at 0 for every
+// dot >= 1: rows that may reach 1 are never cut.) One block per query; the k-th largest is a 4-pass radix select over the scores in global memory (a few hundred values; the block must fit beside a
 // resident scan_tc CTA, so nothing is staged in shared memory).
 __global__ void __launch_bounds__(256)
 rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32_t d4, uint32_t nq, int metric,
-              const uint32_t* __restrict__ cand_ids, const uint32_t* __restrict__ cand_cnt, uint32_t cap,
+              const uint32_t* __restrict__ cand_ids, uint32_t* __restrict__ cand_cnt, uint32_t cap,
               unsigned long long* __restrict__ cand, const float* __restrict__ cand_sc, const float* __restrict__ cut_slack, uint32_t k) {
     __shared__ uint32_t s_hist[259];
+    __shared__ uint32_t s_kept;
     const uint32_t q = blockIdx.x;
     if (q >= nq) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t n = cand_cnt[q];
     if (n > cap) n = cap;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
     float cut = -CUDART_INF_F;
     if (cand_sc != nullptr && n > 2 * k) {   // block-uniform
         const float* sc = cand_sc + (size_t)q * cap;
@@ -549,10 +552,7 @@ rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32
         if (metric == LEANN_METRIC_IP_CLAMP) cut = fminf(cut, 1.0f - cut_slack[q]);
     }
     for (uint32_t i = warp; i < n; i += blockDim.x >> 5) {
-        if (cand_sc != nullptr && cand_sc[(size_t)q * cap + i] < cut) {
-            if (lane == 0) cand[(size_t)q * cap + i] = ~0ull;
-            continue;
-        }
+        if (cand_sc != nullptr && cand_sc[(size_t)q * cap + i] < cut) continue;
         const uint32_t row = cand_ids[(size_t)q * cap + i];
         const float4* x = X + (size_t)row * d4;
         const float4* qq = Q + (size_t)q * d4;
@@ -580,9 +580,11 @@ rerank_kernel(const float4* __restrict__ X, const float4* __restrict__ Q, uint32
                 if (metric == LEANN_METRIC_IP_CLAMP) dd = dd < 0.f ? 0.f : dd;
                 ok = scan_order_f32(dd);
             }
-            cand[(size_t)q * cap + i] = ((unsigned long long)ok << 32) | row;
+            cand[(size_t)q * cap + atomicAdd(&s_kept, 1u)] = ((unsigned long long)ok << 32) | row;   // compacted: select_kernel sees only the kept keys
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) cand_cnt[q] = s_kept;
 }
 
 // After the first chunk (scored by the f32 tile kernel, a sequential fold): the rows of the running top-k go back into
