@@ -487,7 +487,11 @@ void launch_exact_scan(const FlatView& f, const float* d_queries, uint32_t nq, u
     // A smaller first chunk (LEANN_CUDA_SCAN_FIRST = rows, A/B) saves tile work but adds a round, and a round costs about 1 ms
     // of launches, re-rank and select for 10 000 queries: 1024 rows measured 13.3 vs 12.4 ms on 1.25M x 384 and 66.9 vs 67.2 ms
     // on 10M x 384 (profiles/r2_k2_first_chunk_ab.log): left at SCAN_CAP.
-    const uint32_t growth = std::max<uint32_t>(2u, SCAN_CAP / (8u * k));
+    uint32_t growth = std::max<uint32_t>(2u, SCAN_CAP / (8u * k));
+    {
+        static const int growth_env = [] { const char* e = getenv("LEANN_CUDA_SCAN_GROWTH"); return e ? atoi(e) : 0; }();   // A/B
+        if (growth_env >= 2) growth = (uint32_t)growth_env;
+    }
     uint32_t first_rows = SCAN_CAP;
     {
         static const int first_env = [] { const char* e = getenv("LEANN_CUDA_SCAN_FIRST"); return e ? atoi(e) : 0; }();
