@@ -267,7 +267,7 @@ bool q16_plan(const leann_cuda_index* ix, size_t ef, uint32_t* slots, uint32_t* 
 //       members stay under 75 % load.
 // Both are bit-identical to the other forms and both are OFF by default: on the 12.5M x 96 shard the hybrid measured 1.2 %
 // faster at L = 50 (where it never touches its q16 level) and 3.7 % slower at L = 100, the stand-alone form equal at L = 100
-// and 3 % slower at L = 50 (profiles/r2_k1_smv_ab.log, r2_k1_hybrid_ab.log) — taking the visited set off the L2 / DRAM path
+// and 3 % slower at L = 50 with unroll 3 (profiles/r2_k1_smv_ab.log, r2_k1_hybrid_ab.log) — taking the visited set off the L2 / DRAM path
 // buys almost nothing, i.e. the short-row traversal is not bound by memory transactions (see also benchmarks/gather_probe.cu:
 // random 384-byte rows alone stream at 6.9 TB/s). LEANN_CUDA_SMV = 0 / 1 / 2 selects none / stand-alone / hybrid (read once). Visited-set modes (leann_cuda_set_visited_hash):
 // 2 / 3 force the stand-alone form (3: 256-entry limit, every traversal spills), 4 / 5 the hybrid (5: 64-entry first level and a

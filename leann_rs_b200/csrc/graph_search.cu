@@ -260,25 +260,23 @@ int launch_t(const GraphView& g, const SearchParams& p, cudaStream_t stream, int
 // 1M x 256 HNSW indexes it measured 3-9 % slower than the shared-memory lists (two sorted inserts per accepted neighbour).
 template <int LPV, int VPL, int U, int MINB>
 int launch_reg(const GraphView& g, const SearchParams& p, cudaStream_t stream, int op) {
-    if (p.smem_vis == 1) {
+    // The A/B forms below exist for rows of at most 128 floats (the host never selects them beyond that: api.cu smv_plan)
+    if constexpr (VPL <= 4) {
         // visited tables in shared memory, stand-alone (graph_device.cuh "smv"): 3 CTAs of 4 warps per SM, so the register
-        // budget is no longer 80 per thread; unroll 3 measured best of {2, 3, 4} (profiles/r2_k1_smv_ab.log); A/B switch
-        // LEANN_CUDA_SMV_U (read per launch)
-        const char* e = getenv("LEANN_CUDA_SMV_U");
-        const int u = e ? atoi(e) : 3;
-        if (u == 4) return launch_t<LPV, VPL, 4, 3, REG_EPL, true, false, true>(g, p, stream, op);
-        if (u == 2) return launch_t<LPV, VPL, 2, 3, REG_EPL, true, false, true>(g, p, stream, op);
-        return launch_t<LPV, VPL, 3, 3, REG_EPL, true, false, true>(g, p, stream, op);
+        // budget is no longer 80 per thread; unroll 3 measured best of {2, 3, 4} (profiles/r2_k1_smv_ab.log)
+        if (p.smem_vis == 1) return launch_t<LPV, VPL, 3, 3, REG_EPL, true, false, true>(g, p, stream, op);
+        // hybrid: shared-memory first level + q16 overflow level, the usual occupancy (op 1 is asked before the q16 table exists)
+        if (p.smem_vis == 2) return launch_t<LPV, VPL, U, MINB, REG_EPL, true, true, true>(g, p, stream, op);
     }
-    // hybrid: shared-memory first level + q16 overflow level, the usual occupancy (op 1 is asked before the q16 table exists)
-    if (p.smem_vis == 2) return launch_t<LPV, VPL, U, MINB, REG_EPL, true, true, true>(g, p, stream, op);
     const bool q16 = p.vhash != nullptr && p.vhash16 != 0;
-    if (p.row_ring) {
-        // rows through a shared-memory ring of bulk async copies (graph_device.cuh eval_distances_ring). Bit-identical and OFF by
-        // default: 4.88 vs 4.66 ms at L = 100, 2.72 vs 2.61 ms at L = 50 on the 12.5M x 96 shard; with 7 CTAs per SM (72
-        // registers) 5.66 / 3.15 ms (profiles/r2_k1_ring_ab.log)
-        return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true, false, true>(g, p, stream, op)
-                   : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false, false, true>(g, p, stream, op);
+    if constexpr (VPL <= 4) {
+        if (p.row_ring) {
+            // rows through a shared-memory ring of bulk async copies (graph_device.cuh eval_distances_ring). Bit-identical and OFF
+            // by default: 4.88 vs 4.66 ms at L = 100, 2.72 vs 2.61 ms at L = 50 on the 12.5M x 96 shard; with 7 CTAs per SM (72
+            // registers) 5.66 / 3.15 ms (profiles/r2_k1_ring_ab.log)
+            return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true, false, true>(g, p, stream, op)
+                       : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false, false, true>(g, p, stream, op);
+        }
     }
     return q16 ? launch_t<LPV, VPL, U, MINB, REG_EPL, true, true>(g, p, stream, op) : launch_t<LPV, VPL, U, MINB, REG_EPL, true, false>(g, p, stream, op);
 }
