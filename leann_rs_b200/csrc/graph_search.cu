@@ -5,8 +5,10 @@
 //
 // Persistent grid: a fixed pool of warps pulls queries from an atomic counter, so long and short
 // traversals balance and the visited workspace is sized by the grid, not the batch.
-// Bound: HBM gather bandwidth on long rows (0.91 of the copy peak at d = 768); DRAM transactions and load latency
-// on short rows (0.58 at d = 96). Algorithmic bytes per query =
+// Bound: HBM gather bandwidth on long rows (0.91 of the copy peak at d = 768); on short rows (0.58 at d = 96) the dependent
+// latency of a hop: about 2 300 instructions and five memory round trips paid in sequence by one warp, with 24 warps per SM
+// to cover them ("What bounds K1 on short rows": DRAM transactions are not the limit).
+// Algorithmic bytes per query =
 //     n_dist * d4*16  +  n_hops0 * deg0*4  +  n_hops_upper * degU*4      
 // all three counted by the kernel itself (out_stats) and by the oracle.
 // Instantiations: <LPV lanes per vector, VPL float4 per lane, U unroll, MINB CTAs per SM> per row length (dispatch_search);
