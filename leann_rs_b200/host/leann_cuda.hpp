@@ -76,6 +76,9 @@ public:
     size_t dims() const { return dims_; }
     /// Merge concurrent single-query calls (the axum handlers of serve.rs) into batched launches.
     void set_coalescing(size_t max_batch, unsigned max_wait_us) { leann_cuda_set_coalescing(h_, max_batch, max_wait_us); }
+    /// Visited-set representation of the traversal (tuning hook; results never depend on it): 0 automatic, 1 byte maps only,
+    /// 2..5 the shared-memory table forms, >= 1024 per-warp hash tables of that capacity. False for a rejected capacity.
+    bool set_visited_hash(size_t capacity) { return leann_cuda_set_visited_hash(h_, capacity) == LEANN_OK; }
     /// Persist the parsed adjacency as `<index_path>.cuda-layout` so later loads stream it instead of parsing the node block.
     void write_layout_cache(const std::string& index_path) const {
         char err[1024];

@@ -64,6 +64,7 @@ extern "C" {
                                 err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_metacols_free(cols: *mut LeannCudaMetacols);
     fn leann_cuda_set_coalescing(index: *mut LeannCudaIndex, max_batch: usize, max_wait_us: u32) -> c_int;
+    fn leann_cuda_set_visited_hash(index: *mut LeannCudaIndex, capacity: usize) -> c_int;
     fn leann_cuda_write_layout_cache(index: *const LeannCudaIndex, base_path: *const c_char, err: *mut c_char, errlen: usize) -> c_int;
     fn leann_cuda_vamana_build(vectors: *const c_float, vectors_on_device: c_int, n: usize, dims: usize, graph_degree: usize,
                                complexity: usize, alpha: c_float, metric: c_int, seed: u64, device: c_int,
@@ -166,6 +167,13 @@ impl CudaSearcher {
     /// `max_wait_us > 0` lets a leader wait for company, `max_batch <= 1` turns it off.
     pub fn set_coalescing(&mut self, max_batch: usize, max_wait_us: u32) {
         unsafe { leann_cuda_set_coalescing(self.handle, max_batch, max_wait_us) };
+    }
+
+    /// Visited-set representation of the traversal (a tuning hook, results never depend on it): 0 = automatic, 1 = byte maps
+    /// only, 2..=5 = the shared-memory table forms, >= 1024 = per-warp hash tables of that capacity. Returns false for a
+    /// capacity the library rejects (6..=1023).
+    pub fn set_visited_hash(&mut self, capacity: usize) -> bool {
+        unsafe { leann_cuda_set_visited_hash(self.handle, capacity) == 0 }
     }
 
     /// Writes `<index_path>.cuda-layout` (the parsed adjacency, bound to the `.index` file by size, mtime and header hash):
